@@ -1,0 +1,224 @@
+"""Generate golden vectors from the UNMODIFIED reference (run in the authoring container only).
+
+    python tests/golden/make_golden.py            # rewrites tests/golden/*.npz
+
+The reference (/root/reference, read-only, pure Python) cannot travel to the GPU box and has
+import-time dependencies that are absent here (pytorch_lightning, torch_ema, rdkit, Bio).  We
+inject minimal ``sys.modules`` stubs for those, import
+``ProteinReDiff.model.ProteinReDiffModel`` as is, load the seeded synthetic state-dict from
+``protein_redesign_b200.synthetic`` with ``strict=True`` (which also pins the state-dict
+names/shapes), run it on seeded synthetic batches and store the outputs.
+
+Nothing of the reference is copied: fixtures hold only numeric outputs plus checksums of the
+seeded inputs, which the tests regenerate locally.
+"""
+from __future__ import annotations
+
+import contextlib
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+
+from protein_redesign_b200 import synthetic as syn  # noqa: E402
+
+REFERENCE_ROOT = "/root/reference"
+
+
+def install_stubs() -> None:
+    pl = types.ModuleType("pytorch_lightning")
+
+    class LightningModule(torch.nn.Module):
+        @property
+        def device(self):
+            return next(self.parameters()).device
+
+        def save_hyperparameters(self, *a, **k):
+            pass
+
+        def log(self, *a, **k):
+            pass
+
+    pl.LightningModule = LightningModule
+    sys.modules["pytorch_lightning"] = pl
+
+    te = types.ModuleType("torch_ema")
+
+    class ExponentialMovingAverage:
+        def __init__(self, params, decay):
+            pass
+
+        def to(self, *a, **k):
+            return self
+
+        def update(self, *a, **k):
+            pass
+
+        def state_dict(self):
+            return {}
+
+        def load_state_dict(self, *a, **k):
+            pass
+
+        @contextlib.contextmanager
+        def average_parameters(self):
+            yield
+
+    te.ExponentialMovingAverage = ExponentialMovingAverage
+    sys.modules["torch_ema"] = te
+
+    rdkit = types.ModuleType("rdkit")
+    chem = types.ModuleType("rdkit.Chem")
+    for n in ("Atom", "Bond", "Mol"):
+        setattr(chem, n, type(n, (), {}))
+    rdkit.Chem = chem
+    sys.modules["rdkit"] = rdkit
+    sys.modules["rdkit.Chem"] = chem
+    bio = types.ModuleType("Bio")
+    pdb = types.ModuleType("Bio.PDB")
+    pdbp = types.ModuleType("Bio.PDB.PDBParser")
+    pdbp.PDBParser = type("PDBParser", (), {})
+    sys.modules["Bio"] = bio
+    sys.modules["Bio.PDB"] = pdb
+    sys.modules["Bio.PDB.PDBParser"] = pdbp
+
+
+def load_reference_model(cfg: syn.DenoiserConfig, seed: int):
+    install_stubs()
+    if REFERENCE_ROOT not in sys.path:
+        sys.path.insert(0, REFERENCE_ROOT)
+    from ProteinReDiff.model import ProteinReDiffModel  # type: ignore
+
+    model = ProteinReDiffModel(cfg.to_namespace())
+    sd = syn.make_state_dict(cfg, seed)
+    model.load_state_dict(sd, strict=True)
+    model.eval()
+    return model, sd
+
+
+def clone_batch(b):
+    return {k: (v.clone() if isinstance(v, torch.Tensor) else v) for k, v in b.items()}
+
+
+def ref_prepare(model, batch, torch_seed):
+    torch.manual_seed(torch_seed)
+    return model.prepare_batch(clone_batch(batch))
+
+
+def capture_modules(model, names):
+    """Forward hooks that record the output of the named submodules."""
+    store = {}
+    handles = []
+    mods = dict(model.named_modules())
+    for n in names:
+        def hook(mod, inp, out, n=n):
+            if isinstance(out, tuple):  # Denoiser returns (single, pair, cache)
+                for i, o in enumerate(out):
+                    if isinstance(o, torch.Tensor):
+                        store[f"{n}:{i}"] = o.detach().clone()
+            else:
+                store[n] = out.detach().clone()
+        handles.append(mods[n].register_forward_hook(hook))
+    return store, handles
+
+
+def gen_step_case(tag, cfg, sizes, seed, n_total=None, two_chains=False, probes=False, out=None):
+    model, sd = load_reference_model(cfg, seed)
+    batch = syn.make_batch(cfg, sizes, seed=seed, n_total=n_total, two_chains=two_chains)
+    pb = ref_prepare(model, batch, torch_seed=seed)
+    z, seq_t, mask, t = syn.make_step_inputs(batch, cfg.num_steps, seed)
+    rec = {
+        "weights_checksum": syn.checksum(sd),
+        "batch_checksum": syn.checksum(batch),
+        "inputs_checksum": syn.checksum([z, seq_t, mask, t]),
+        "keep_mask": pb["residue_extra_mask"].numpy(),
+        "drop_mask": pb["residue_inv_extra_mask"].numpy(),
+        "residue_one_hot": pb["residue_one_hot"].numpy(),
+        "residue_type_masked": pb["residue_type_masked"].numpy(),
+        "x": pb["x"].numpy(),
+    }
+    names = []
+    if probes:
+        names = ["Denoiser.opm", "Denoiser.SPAAttnBlock"]
+        for k in range(cfg.num_blocks):
+            p = f"Denoiser.folding_blocks.{k}."
+            names += [p + s for s in ("attn_bias", "single_attn", "single_fc", "outer_linear", "pair_mul_outgoing",
+                                      "pair_mul_incoming", "pair_attn_starting", "pair_attn_ending", "pair_fc")]
+        names += ["Denoiser", "weight_radial", "embed_dist", "embed_beta", "embed_residue_type", "embed_residue_esm"]
+    store, handles = capture_modules(model, names)
+    with torch.inference_mode():
+        noise_pred, seq_pred = model.sample_step(pb, z, seq_t, mask, t)
+        fwd_noise, fwd_seq = model.forward(pb, z, seq_t, mask, t)
+    for h in handles:
+        h.remove()
+    assert torch.equal(noise_pred, fwd_noise) and torch.equal(seq_pred, fwd_seq)
+    rec["noise_pred"] = noise_pred.numpy()
+    rec["seq_pred"] = seq_pred.numpy()
+    for n, v in store.items():
+        rec["probe:" + n] = v.numpy()
+    path = os.path.join(HERE, f"step_{tag}.npz")
+    np.savez_compressed(path, **rec)
+    print(f"{tag}: noise rms {noise_pred.square().mean().sqrt():.4f} logits rms {seq_pred.square().mean().sqrt():.4f}"
+          f" -> {os.path.relpath(path, ROOT)} ({os.path.getsize(path) / 1024:.0f} KiB)")
+
+
+def gen_sample_case(tag, cfg, sizes, seed, n_total=None):
+    """Full sampler with injected noise: torch.randn_like is replaced by draws from a seeded
+    generator, in the reference's own draw order."""
+    model, sd = load_reference_model(cfg, seed)
+    batch = syn.make_batch(cfg, sizes, seed=seed, n_total=n_total)
+    g = torch.Generator().manual_seed(seed + 31337)
+    draws = []
+
+    def fake_randn_like(x, **kw):
+        n = torch.randn(x.shape, generator=g, dtype=x.dtype)
+        draws.append(n)
+        return n
+
+    orig = torch.randn_like
+    torch.randn_like = fake_randn_like
+    try:
+        torch.manual_seed(seed)
+        pos, logits = model.sample(clone_batch(batch))
+    finally:
+        torch.randn_like = orig
+    rec = {
+        "weights_checksum": syn.checksum(sd),
+        "batch_checksum": syn.checksum(batch),
+        "pos": pos.numpy(),
+        "logits": logits.numpy(),
+        "num_draws": len(draws),
+    }
+    # schedule tables pinned as well (model.py:172-190)
+    for k in ("betas", "alphas", "alphas_cumprod", "sqrt_betas", "sqrt_alphas", "sqrt_one_minus_alphas_cumprod",
+              "sqrt_alphas_cumprod"):
+        rec["sched:" + k] = getattr(model, k).numpy()
+    path = os.path.join(HERE, f"sample_{tag}.npz")
+    np.savez_compressed(path, **rec)
+    print(f"{tag}: pos rms {pos.square().mean().sqrt():.3f} A -> {os.path.relpath(path, ROOT)}")
+
+
+def main():
+    torch.set_num_threads(os.cpu_count() or 1)
+    # (1) tiny dims, every module probed, ragged batch with padding + two chains.
+    gen_step_case("tiny_probes", syn.TINY, [(5, 14), (3, 9)], seed=1, n_total=22, two_chains=True, probes=True)
+    # (2) README dims (BASELINE config 1 shape family), one ragged batch.
+    gen_step_case("readme_n40", syn.README, [(8, 32), (6, 27)], seed=2)
+    # (3) paper dims (north-star dims) at a size the CPU finishes in seconds; includes padding.
+    gen_step_case("paper_n72", syn.PAPER, [(12, 60), (9, 50)], seed=3)
+    gen_step_case("paper_n128", syn.PAPER, [(16, 112)], seed=4)
+    # (4) sampler trajectories with injected noise (cosine + linear schedules).
+    gen_sample_case("tiny_T8", syn.DenoiserConfig(**{**syn.TINY.__dict__, "num_steps": 8, "mask_prob": 0.3}),
+                    [(5, 14), (3, 9)], seed=5)
+    gen_sample_case("tiny_T6_cos", syn.DenoiserConfig(**{**syn.TINY.__dict__, "num_steps": 6, "mask_prob": 1.0,
+                                                         "diffusion_schedule": "cosine"}), [(4, 12)], seed=6)
+
+
+if __name__ == "__main__":
+    main()
