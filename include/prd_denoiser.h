@@ -1,0 +1,153 @@
+/* libprd_sm100 -- C ABI of the B200-native ProteinReDiff denoiser hot path.
+ *
+ * The reference (HySonLab/Protein_Redesign) has no FFI: its "operator API" is the Python
+ * nn.Module surface of ProteinReDiff/modules.py, ProteinReDiff/models/AF2_modules.py and
+ * ProteinReDiff/model.py.  Every entry point below replaces the forward of one of those
+ * modules (file:line cited per function); the Python mirror in protein_redesign_b200/ binds
+ * them with ctypes.
+ *
+ * Conventions
+ *   - all data pointers are DEVICE pointers (tensor.data_ptr()), contiguous row-major with the
+ *     reference's shapes; fp32 activations, int64 indices, fp16 ("_h") packed weights;
+ *   - the caller owns every buffer including the workspace; nothing is allocated, freed or
+ *     synchronised inside, every launch goes to `stream` (a cudaStream_t), so a sequence of
+ *     calls is CUDA-graph capturable;
+ *   - return 0 on success, non-zero on failure with a thread-local message in prd_last_error();
+ *   - uniform signature for the module-level ops:
+ *       int prd_<op>_fwd(const PrdDims*, const void* const* in, void* const* out,
+ *                        const void* const* weights, void* workspace, size_t workspace_bytes,
+ *                        void* stream);
+ *       size_t prd_<op>_workspace_bytes(const PrdDims*);
+ *     the pointer-array order is documented per function;
+ *   - there is no CPU fallback: without an sm_100 device every op fails (prd_device_check()).
+ */
+#ifndef PRD_DENOISER_H_
+#define PRD_DENOISER_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PRD_VERSION 1
+
+typedef struct PrdDims {
+  int32_t B;                 /* batch rows                                  */
+  int32_t N;                 /* tokens per row (ligand atoms + residues + pad) */
+  int32_t c_s;               /* single_dim  (model.py:145)                  */
+  int32_t c_z;               /* pair_dim    (model.py:146); built: 64, 32   */
+  int32_t H;                 /* num_heads   (model.py:148); built: 4        */
+  int32_t c;                 /* head_dim    (model.py:147); built: 16       */
+  int32_t tf;                /* transition_factor (model.py:149)            */
+  int32_t esm_dim;           /* model.py:142                                */
+  int32_t time_dim;          /* model.py:143                                */
+  int32_t dist_dim;          /* model.py:144                                */
+  int32_t max_bond_distance; /* model.py:151                                */
+  int32_t max_relpos;        /* model.py:152                                */
+  int32_t num_steps;         /* model.py:153                                */
+  int32_t mode;              /* op specific: 0 = outgoing/starting, 1 = incoming/ending */
+  int32_t residual;          /* residual ops: 1 -> dst = src + update (dst may alias src, the fused
+                                FoldingBlock form, modules.py:335-342); 0 -> dst = update only (what the
+                                reference sub-module's forward returns) */
+} PrdDims;
+
+int prd_version(void);
+const char* prd_last_error(void);
+int prd_device_check(void); /* 0 iff the current device is sm_100 */
+
+/* Plain batched GEMM on the tcgen05 path (building block + test hook):
+ * C[b] = alpha * A[b] (M x K, fp16) * B[b]^T (N x K, fp16), fp32 accumulate, optional epilogue. */
+typedef struct PrdGemm {
+  int32_t M, N, K, nb1, nb2;
+  const void* A; int64_t lda, a_bs1, a_bs2;
+  const void* B; int64_t ldb, b_bs1, b_bs2;
+  float alpha; int32_t act;                    /* 0 none, 1 relu, 2 sigmoid */
+  const float* bias;                           /* [N] or NULL */
+  const float* rowscale; int64_t rs_bs1, rs_bs2;
+  const float* mul; int64_t ldmul, mul_bs1, mul_bs2;
+  const float* add; int64_t ldadd, add_bs1, add_bs2;
+  void* C; int64_t ldc, c_bs1, c_bs2; int32_t c_fp16;
+} PrdGemm;
+int prd_gemm_f16(const PrdGemm* g, void* stream);
+
+#define PRD_DECLARE_OP(name)                                                                      \
+  int prd_##name##_fwd(const PrdDims* d, const void* const* in, void* const* out,                 \
+                       const void* const* weights, void* workspace, size_t workspace_bytes,       \
+                       void* stream);                                                             \
+  size_t prd_##name##_workspace_bytes(const PrdDims* d);
+
+/* --- input embeddings -------------------------------------------------------------------- */
+/* model.py:99-102 embed_residue_esm (LN(esm_dim) -> Linear no bias); step invariant.
+ * in: [residue_esm f32 B,N,esm]   out: [esm_emb f32 B,N,c_s]   weights: [w_esm_h c_s x esm] */
+PRD_DECLARE_OP(esm_embed)
+/* model.py:342-346 (+ modules.py:35-51, model.py:89-93).
+ * in: [atom_feats i64 B,N,9 | atom_mask | residue_mask | seq_t f32 B,N,21 | esm_emb]
+ * out: [single f32 B,N,c_s]   weights: [atom table 0..8 f32 | w_type f32 c_s x 21] */
+PRD_DECLARE_OP(single_embed)
+/* model.py:348-358 step-invariant pair terms (modules.py:54-70 BondEmbedding, bond distance, relpos).
+ * in: [atom_mask | residue_mask | bond_mask B,N,N | bond_feats i64 B,N,N,3 | bond_distance i64 B,N,N |
+ *      residue_index i64 B,N | residue_chain_index i64 B,N]
+ * out: [pair_static f32 B,N,N,c_z]   weights: [bond table 0..2 | bond_distance table | relpos table] */
+PRD_DECLARE_OP(pair_embed_static)
+/* AF2_modules.py:519-530 OuterProductUpdate projections a = mask*(W1 LN_a(s)+b1), b likewise.
+ * in: [single | mask B,N]  out: [opm_a f32 B,N,c_s/4 | opm_b]
+ * weights: [ln_w | ln_b | w1_h | b1 | w2_h | b2] */
+PRD_DECLARE_OP(opm_project)
+/* model.py:337-341,359-361 + modules.py:73-97 + AF2_modules.py:532-543 + modules.py:395-397:
+ * pair = pair_static + m2 (W_dist rbf(|z_i-z_j|) + W_beta sincos(t/T)) + m2 (W_o(a_i*b_j)+b_o)/(m2+1e-3).
+ * in: [pair_static (NULL = zeros) | z f32 B,N,3 | mask | t i64 B (or NULL with sampler_state) | opm_a | opm_b | sampler_state]
+ * d->mode bit 0: OuterProductUpdate term only (Denoiser.forward's `pair += mask_2d * opm(...)`, modules.py:395-397);
+ *         bit 1: OPM term not multiplied by mask_2d (stand-alone OuterProductUpdate.forward, AF2_modules.py:503-545).
+ * out: [pair]   weights: [freq | w_beta f32 c_z x time | w_dist_h c_z x dist | centers | w_opm_h c_z x c_s/4 | b_opm] */
+PRD_DECLARE_OP(pair_embed)
+
+/* --- Denoiser trunk (modules.py:391-404) ------------------------------------------------- */
+/* AF2_modules.py:421-473 SPAttention (+ :251-367, :613-627): single <- LN_a(single) + mha(...).
+ * in: [single | pair]  out: [single_out (may alias single)]
+ * weights: [ln_m_w | ln_m_b | ln_z_w | ln_z_b | w_z f32 H x c_z | w_q_h | w_k_h | w_v_h | w_g_h | b_g | w_o_h | b_o] */
+PRD_DECLARE_OP(spattention)
+/* modules.py:300-304 attn_bias + modules.py:185-225 Attention on the single rep + residual (:335).
+ * in: [single | pair (or NULL) | mask | attn_bias f32 B,H,N,N (used when pair is NULL; NULL = no bias)]  out: [single_out]
+ * weights: [w_bias f32 H x c_z | b_bias | w_qkvg_h 4Hc x c_s | b_qkvg f32 4Hc (zeros | gate bias) | w_o_h c_s x Hc | b_o] */
+PRD_DECLARE_OP(single_attention)
+/* modules.py:306-311,336 single_fc + residual.  in: [single]  out: [single_out]  weights: [w1_h | b1 | w2_h | b2] */
+PRD_DECLARE_OP(single_transition)
+/* modules.py:283-287,337 OuterLinear + residual.  in: [single | pair]  out: [pair_out]
+ * weights: [w_mul_h c_z x c_s (= weight[:, :c_s]) | w_sub_h c_z x c_s (= weight[:, c_s:]) | bias] */
+PRD_DECLARE_OP(outer_linear)
+/* modules.py:262-274,338-339 TriangleMultiplication + residual (d->mode: 0 outgoing, 1 incoming).
+ * in: [pair | mask]  out: [pair_out]
+ * weights: [w_in_h 4c_z x c_z (ab_proj ; ab_gate) | b_in | w_out_h 2c_z x c_z (out_gate ; out_proj) | b_out] */
+PRD_DECLARE_OP(triangle_multiplication)
+/* modules.py:236-243 (+185-225),340-341 TriangleAttention + residual (d->mode: 0 starting, 1 ending).
+ * in: [pair | mask]  out: [pair_out]
+ * weights: [w_qkvg_h 4Hc x c_z (q;k;v;gate) | b_gate f32 Hc | w_o_h c_z x Hc | b_o] */
+PRD_DECLARE_OP(triangle_attention)
+/* modules.py:321-326,342 pair_fc + residual.  in: [pair]  out: [pair_out]  weights: [w1_h | b1 | w2_h | b2] */
+PRD_DECLARE_OP(pair_transition)
+/* modules.py:403  pair <- 0.5 (pair + pair^T).  out: [pair] */
+PRD_DECLARE_OP(symmetrize)
+
+/* --- heads (model.py:364-374) -------------------------------------------------------------- */
+/* model.py:364-373: symmetrise + weight_radial + sum_j m2 w r + remove_mean.
+ * in: [pair | z | mask]  out: [noise_pred f32 B,N,3]  weights: [w1_h c_z x c_z | b1 | w2 f32 c_z] */
+PRD_DECLARE_OP(coord_head)
+/* model.py:374 seq_mlp.  in: [single]  out: [seq_pred f32 B,N,21]  weights: [w1_h | b1 | w2_h 21 x c_s] */
+PRD_DECLARE_OP(seq_head)
+
+/* --- sampler (model.py:395-420) ------------------------------------------------------------ */
+/* utils.py:32-36 remove_mean over rows; d->mode = channel count (3 or 21); x has shape [B, N, mode].
+ * in: [mask (B rows, broadcast cyclically if x has k*B rows; d->B = rows of x, d->H = rows of mask)]  out: [x] */
+PRD_DECLARE_OP(remove_mean)
+/* model.py:407-420 one reverse step on device (see csrc/prd_embed.cu).
+ * in: [noise_pred | seq_pred | noise f32 steps,B,N,3 | coef f32 T,3]  out: [z | seq_t | sampler_state int32[2]] */
+PRD_DECLARE_OP(sampler_update)
+
+#undef PRD_DECLARE_OP
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PRD_DENOISER_H_ */

@@ -1,0 +1,38 @@
+"""Packed-weight cache: fp16 / concatenated copies of module parameters for the CUDA kernels.
+
+The reference overwrites parameters in place between calls (EMA weight swap around
+``predict_step``, model.py:249-252), so packed copies are keyed on every source tensor's
+``data_ptr`` and in-place ``_version`` and rebuilt when either changes.
+"""
+from __future__ import annotations
+
+from typing import Callable, Sequence
+
+import torch
+
+
+def half(t: torch.Tensor) -> torch.Tensor:
+    return t.detach().to(torch.float16).contiguous()
+
+
+def f32(t: torch.Tensor) -> torch.Tensor:
+    return t.detach().to(torch.float32).contiguous()
+
+
+class PackCache:
+    def __init__(self):
+        self._key = None
+        self._value = None
+
+    def get(self, sources: Sequence[torch.Tensor], build: Callable[[], object]):
+        key = tuple((t.data_ptr(), t._version, t.device) for t in sources)
+        if key != self._key:
+            for t in sources:
+                if not t.is_cuda:
+                    raise RuntimeError(
+                        f"parameter on {t.device}: the B200 denoiser runs on CUDA sm_100 only (no CPU fallback); "
+                        "move the module with .cuda() first")
+            with torch.no_grad():
+                self._value = build()
+            self._key = key
+        return self._value

@@ -1,0 +1,485 @@
+// extern "C" entry points: each composes the kernels of one reference module (see
+// include/prd_denoiser.h for the contract and the reference file:line each op replaces).
+#include "../../include/prd_denoiser.h"
+#include "prd_common.cuh"
+#include "prd_embed.h"
+#include "prd_kernels.h"
+
+using namespace prd;
+
+namespace {
+
+// Bump allocator over the caller-provided workspace; with base == nullptr it only measures.
+struct Carver {
+  char* base;
+  size_t off = 0;
+  explicit Carver(void* b) : base(static_cast<char*>(b)) {}
+  template <typename T>
+  T* take(size_t n) {
+    off = (off + 255) & ~size_t(255);
+    T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
+    off += n * sizeof(T);
+    return p;
+  }
+  size_t total() const { return (off + 255) & ~size_t(255); }
+};
+
+inline cudaStream_t S(void* s) { return static_cast<cudaStream_t>(s); }
+inline PairDims pd(const PrdDims* d) { return PairDims{d->B, d->N, d->c_z}; }
+
+#define PRD_WS_CHECK(need)                                                                              \
+  PRD_REQUIRE(workspace_bytes >= (need), "%s: workspace too small (%zu < %zu bytes)", __func__,         \
+              (size_t)workspace_bytes, (size_t)(need))
+
+template <typename T>
+const T* in_ptr(const void* const* a, int i) { return static_cast<const T*>(a[i]); }
+template <typename T>
+T* out_ptr(void* const* a, int i) { return static_cast<T*>(a[i]); }
+
+// y[M,N] = epilogue(x16[M,K] . w16[N,K]^T)
+GemmArgs linear_args(int M, int N, int K, const __half* x16, const __half* w16, void* C, int c_fp16) {
+  GemmArgs g;
+  g.M = M; g.N = N; g.K = K;
+  g.A = x16; g.lda = K;
+  g.B = w16; g.ldb = K;
+  g.C = C; g.ldc = N; g.c_fp16 = c_fp16;
+  return g;
+}
+
+}  // namespace
+
+extern "C" {
+
+int prd_gemm_f16(const PrdGemm* p, void* stream) {
+  if (prd_device_check()) return 1;
+  GemmArgs g;
+  g.M = p->M; g.N = p->N; g.K = p->K; g.nb1 = p->nb1; g.nb2 = p->nb2;
+  g.A = static_cast<const __half*>(p->A); g.lda = p->lda; g.a_bs1 = p->a_bs1; g.a_bs2 = p->a_bs2;
+  g.B = static_cast<const __half*>(p->B); g.ldb = p->ldb; g.b_bs1 = p->b_bs1; g.b_bs2 = p->b_bs2;
+  g.alpha = p->alpha; g.act = p->act; g.bias = p->bias;
+  g.rowscale = p->rowscale; g.rs_bs1 = p->rs_bs1; g.rs_bs2 = p->rs_bs2;
+  g.mul = p->mul; g.ldmul = p->ldmul; g.mul_bs1 = p->mul_bs1; g.mul_bs2 = p->mul_bs2;
+  g.add = p->add; g.ldadd = p->ldadd; g.add_bs1 = p->add_bs1; g.add_bs2 = p->add_bs2;
+  g.C = p->C; g.ldc = p->ldc; g.c_bs1 = p->c_bs1; g.c_bs2 = p->c_bs2; g.c_fp16 = p->c_fp16;
+  return gemm_f16(g, S(stream));
+}
+
+// ------------------------------------------------------------------------------- esm_embed
+size_t prd_esm_embed_workspace_bytes(const PrdDims* d) {
+  Carver c(nullptr);
+  c.take<__half>((size_t)d->B * d->N * d->esm_dim);
+  return c.total();
+}
+int prd_esm_embed_fwd(const PrdDims* d, const void* const* in, void* const* out, const void* const* w, void* workspace,
+                      size_t workspace_bytes, void* stream) {
+  if (prd_device_check()) return 1;
+  PRD_WS_CHECK(prd_esm_embed_workspace_bytes(d));
+  PRD_REQUIRE(d->esm_dim % 8 == 0, "esm_embed: esm_dim %d must be a multiple of 8", d->esm_dim);
+  Carver c(workspace);
+  const int M = d->B * d->N;
+  __half* xn = c.take<__half>((size_t)M * d->esm_dim);
+  if (layernorm_rows(in_ptr<float>(in, 0), M, d->esm_dim, nullptr, nullptr, xn, nullptr, S(stream))) return 1;
+  GemmArgs g = linear_args(M, d->c_s, d->esm_dim, xn, in_ptr<__half>(w, 0), out_ptr<float>(out, 0), 0);
+  return gemm_f16(g, S(stream));
+}
+
+// ---------------------------------------------------------------------------- single_embed
+size_t prd_single_embed_workspace_bytes(const PrdDims*) { return 256; }
+int prd_single_embed_fwd(const PrdDims* d, const void* const* in, void* const* out, const void* const* w, void*,
+                         size_t, void* stream) {
+  if (prd_device_check()) return 1;
+  AtomTables tabs;
+  for (int f = 0; f < 9; ++f) tabs.t[f] = in_ptr<float>(w, f);
+  return single_embed(d->B, d->N, d->c_s, in_ptr<int64_t>(in, 0), in_ptr<float>(in, 1), in_ptr<float>(in, 2),
+                      in_ptr<float>(in, 3), in_ptr<float>(in, 4), tabs, in_ptr<float>(w, 9), out_ptr<float>(out, 0),
+                      S(stream));
+}
+
+// ----------------------------------------------------------------------- pair_embed_static
+size_t prd_pair_embed_static_workspace_bytes(const PrdDims*) { return 256; }
+int prd_pair_embed_static_fwd(const PrdDims* d, const void* const* in, void* const* out, const void* const* w, void*,
+                              size_t, void* stream) {
+  if (prd_device_check()) return 1;
+  const float* tabs[3] = {in_ptr<float>(w, 0), in_ptr<float>(w, 1), in_ptr<float>(w, 2)};
+  return embed_pair_static(pd(d), in_ptr<float>(in, 0), in_ptr<float>(in, 1), in_ptr<float>(in, 2),
+                           in_ptr<int64_t>(in, 3), in_ptr<int64_t>(in, 4), in_ptr<int64_t>(in, 5),
+                           in_ptr<int64_t>(in, 6), tabs, nullptr, in_ptr<float>(w, 3), d->max_bond_distance,
+                           in_ptr<float>(w, 4), d->max_relpos, out_ptr<float>(out, 0), S(stream));
+}
+
+// ----------------------------------------------------------------------------- opm_project
+size_t prd_opm_project_workspace_bytes(const PrdDims* d) {
+  Carver c(nullptr);
+  c.take<__half>((size_t)d->B * d->N * d->c_s);
+  return c.total();
+}
+int prd_opm_project_fwd(const PrdDims* d, const void* const* in, void* const* out, const void* const* w,
+                        void* workspace, size_t workspace_bytes, void* stream) {
+  if (prd_device_check()) return 1;
+  PRD_WS_CHECK(prd_opm_project_workspace_bytes(d));
+  Carver c(workspace);
+  const int M = d->B * d->N, OD = d->c_s / 4;
+  __half* xn = c.take<__half>((size_t)M * d->c_s);
+  if (layernorm_rows(in_ptr<float>(in, 0), M, d->c_s, in_ptr<float>(w, 0), in_ptr<float>(w, 1), xn, nullptr, S(stream)))
+    return 1;
+  for (int k = 0; k < 2; ++k) {
+    GemmArgs g = linear_args(M, OD, d->c_s, xn, in_ptr<__half>(w, 2 + 2 * k), out_ptr<float>(out, k), 0);
+    g.bias = in_ptr<float>(w, 3 + 2 * k);
+    g.rowscale = in_ptr<float>(in, 1);
+    if (gemm_f16(g, S(stream))) return 1;
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------ pair_embed
+size_t prd_pair_embed_workspace_bytes(const PrdDims* d) {
+  Carver c(nullptr);
+  c.take<float>((size_t)d->B * d->c_z);
+  return c.total();
+}
+int prd_pair_embed_fwd(const PrdDims* d, const void* const* in, void* const* out, const void* const* w,
+                       void* workspace, size_t workspace_bytes, void* stream) {
+  if (prd_device_check()) return 1;
+  PRD_WS_CHECK(prd_pair_embed_workspace_bytes(d));
+  Carver c(workspace);
+  float* beta = c.take<float>((size_t)d->B * d->c_z);
+  const SamplerState* st = static_cast<const SamplerState*>(in[6]);
+  const int flags = d->mode;  // bit 0: OuterProductUpdate term only; bit 1: OPM term not multiplied by mask_2d
+  if ((flags & 1) == 0) {
+    PRD_REQUIRE(in[3] != nullptr || st != nullptr, "pair_embed: need t or a sampler state");
+    if (time_embed(d->B, d->c_z, d->time_dim, in_ptr<int64_t>(in, 3), st, d->num_steps, in_ptr<float>(w, 0),
+                   in_ptr<float>(w, 1), beta, S(stream)))
+      return 1;
+  }
+  const float rbf_scale = (d->dist_dim - 1) / 2.0f;  // modules.py:76 with min 0, max 2
+  return pair_embed_dynamic(pd(d), in_ptr<float>(in, 0), out_ptr<float>(out, 0), in_ptr<float>(in, 1),
+                            in_ptr<float>(in, 2), beta, in_ptr<__half>(w, 2), d->dist_dim, in_ptr<float>(w, 3),
+                            rbf_scale, in_ptr<float>(in, 4), in_ptr<float>(in, 5), d->c_s / 4, in_ptr<__half>(w, 4),
+                            in_ptr<float>(w, 5), flags, S(stream));
+}
+
+// ----------------------------------------------------------------------------- spattention
+namespace {
+struct SpaWs {
+  float* bias; __half* xn16; float* xn32; __half* q; __half* k; __half* vt; float* g; __half* p; __half* og;
+  size_t total;
+};
+SpaWs spa_carve(const PrdDims* d, void* ws) {
+  Carver c(ws);
+  SpaWs s;
+  const size_t M = (size_t)d->B * d->N, HC = (size_t)d->H * d->c_s, Np = plane_ld(d->N);
+  s.bias = c.take<float>((size_t)d->B * d->H * d->N * d->N);
+  s.xn16 = c.take<__half>(M * d->c_s);
+  s.xn32 = c.take<float>(M * d->c_s);
+  s.q = c.take<__half>(M * HC);
+  s.k = c.take<__half>(M * HC);
+  s.vt = c.take<__half>((size_t)d->B * HC * Np);
+  s.g = c.take<float>(M * HC);
+  s.p = c.take<__half>((size_t)d->B * d->H * d->N * Np);
+  s.og = c.take<__half>(M * HC);
+  s.total = c.total();
+  return s;
+}
+}  // namespace
+size_t prd_spattention_workspace_bytes(const PrdDims* d) { return spa_carve(d, nullptr).total; }
+int prd_spattention_fwd(const PrdDims* d, const void* const* in, void* const* out, const void* const* w,
+                        void* workspace, size_t workspace_bytes, void* stream) {
+  if (prd_device_check()) return 1;
+  PRD_WS_CHECK(prd_spattention_workspace_bytes(d));
+  SpaWs s = spa_carve(d, workspace);
+  cudaStream_t st = S(stream);
+  const int B = d->B, N = d->N, CS = d->c_s, H = d->H, M = B * N, HC = H * CS, Np = plane_ld(N);
+  const float* single_src = in_ptr<float>(in, 0);
+  float* single = out_ptr<float>(out, 0);
+  // pair bias: LN_affine(pair) . w_z  -> [B,H,N,N]
+  if (pair_bias_proj(pd(d), H, in_ptr<float>(in, 1), in_ptr<float>(w, 2), in_ptr<float>(w, 3), in_ptr<float>(w, 4),
+                     nullptr, s.bias, st))
+    return 1;
+  if (layernorm_rows(single_src, M, CS, in_ptr<float>(w, 0), in_ptr<float>(w, 1), s.xn16, s.xn32, st)) return 1;
+  {  // q, k  [M, H*CS] fp16
+    GemmArgs g = linear_args(M, HC, CS, s.xn16, in_ptr<__half>(w, 5), s.q, 1);
+    if (gemm_f16(g, st)) return 1;
+    g = linear_args(M, HC, CS, s.xn16, in_ptr<__half>(w, 6), s.k, 1);
+    if (gemm_f16(g, st)) return 1;
+  }
+  {  // v^T[b] = W_v . x[b]^T  -> [B][H*CS][Np] fp16 (keys contiguous): A = W_v, B = x[b]
+    GemmArgs g;
+    g.M = HC; g.N = N; g.K = CS; g.nb1 = B;
+    g.A = in_ptr<__half>(w, 7); g.lda = CS;
+    g.B = s.xn16; g.ldb = CS; g.b_bs1 = (long long)N * CS;
+    g.C = s.vt; g.ldc = Np; g.c_bs1 = (long long)HC * Np; g.c_fp16 = 1;
+    if (gemm_f16(g, st)) return 1;
+  }
+  {  // gate = sigmoid(x W_g^T + b_g)  fp32 [M, H*CS]
+    GemmArgs g = linear_args(M, HC, CS, s.xn16, in_ptr<__half>(w, 8), s.g, 0);
+    g.bias = in_ptr<float>(w, 9);
+    g.act = 2;
+    if (gemm_f16(g, st)) return 1;
+  }
+  {  // logits[b,h] = q_h k_h^T / sqrt(CS) + bias[b,h]   (in place over the bias buffer)
+    GemmArgs g;
+    g.M = N; g.N = N; g.K = CS; g.nb1 = H; g.nb2 = B;
+    g.A = s.q; g.lda = HC; g.a_bs1 = CS; g.a_bs2 = (long long)N * HC;
+    g.B = s.k; g.ldb = HC; g.b_bs1 = CS; g.b_bs2 = (long long)N * HC;
+    g.alpha = 1.0f / sqrtf((float)CS);
+    g.add = s.bias; g.ldadd = N; g.add_bs1 = (long long)N * N; g.add_bs2 = (long long)H * N * N;
+    g.C = s.bias; g.ldc = N; g.c_bs1 = (long long)N * N; g.c_bs2 = (long long)H * N * N;
+    if (gemm_f16(g, st)) return 1;
+  }
+  if (softmax_rows(s.bias, s.p, (long long)B * H * N, N, N, Np, st)) return 1;
+  {  // og[b,:,h,:] = (P[b,h] V[b,h]) * gate  -> fp16 [M, H*CS]
+    GemmArgs g;
+    g.M = N; g.N = CS; g.K = N; g.nb1 = H; g.nb2 = B;
+    g.A = s.p; g.lda = Np; g.a_bs1 = (long long)N * Np; g.a_bs2 = (long long)H * N * Np;
+    g.B = s.vt; g.ldb = Np; g.b_bs1 = (long long)CS * Np; g.b_bs2 = (long long)HC * Np;
+    g.mul = s.g; g.ldmul = HC; g.mul_bs1 = CS; g.mul_bs2 = (long long)N * HC;
+    g.C = s.og; g.ldc = HC; g.c_bs1 = CS; g.c_bs2 = (long long)N * HC; g.c_fp16 = 1;
+    if (gemm_f16(g, st)) return 1;
+  }
+  {  // single = LN_a(single) + og W_o^T + b_o
+    GemmArgs g = linear_args(M, CS, HC, s.og, in_ptr<__half>(w, 10), single, 0);
+    g.bias = in_ptr<float>(w, 11);
+    g.add = s.xn32; g.ldadd = CS;
+    if (gemm_f16(g, st)) return 1;
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------------ single_attention
+namespace {
+struct SaWs { float* bias; __half* xn16; float* qkvg; __half* og; size_t total; };
+SaWs sa_carve(const PrdDims* d, void* ws) {
+  Carver c(ws);
+  SaWs s;
+  const size_t M = (size_t)d->B * d->N, HC = (size_t)d->H * d->c;
+  s.bias = c.take<float>((size_t)d->B * d->H * d->N * d->N);
+  s.xn16 = c.take<__half>(M * d->c_s);
+  s.qkvg = c.take<float>(M * 4 * HC);
+  s.og = c.take<__half>(M * HC);
+  s.total = c.total();
+  return s;
+}
+}  // namespace
+size_t prd_single_attention_workspace_bytes(const PrdDims* d) { return sa_carve(d, nullptr).total; }
+int prd_single_attention_fwd(const PrdDims* d, const void* const* in, void* const* out, const void* const* w,
+                             void* workspace, size_t workspace_bytes, void* stream) {
+  if (prd_device_check()) return 1;
+  PRD_WS_CHECK(prd_single_attention_workspace_bytes(d));
+  SaWs s = sa_carve(d, workspace);
+  cudaStream_t st = S(stream);
+  const int M = d->B * d->N, HC = d->H * d->c;
+  const float* single_src = in_ptr<float>(in, 0);
+  float* single = out_ptr<float>(out, 0);
+  // attention bias: projected from the pair tensor (FoldingBlock.attn_bias), or given, or none
+  const float* bias = in_ptr<float>(in, 3);
+  if (in[1] != nullptr) {
+    if (pair_bias_proj(pd(d), d->H, in_ptr<float>(in, 1), nullptr, nullptr, in_ptr<float>(w, 0), in_ptr<float>(w, 1),
+                       s.bias, st))
+      return 1;
+    bias = s.bias;
+  } else if (bias == nullptr) {
+    PRD_CUDA_OK(cudaMemsetAsync(s.bias, 0, (size_t)d->B * d->H * d->N * d->N * sizeof(float), st));
+    bias = s.bias;
+  }
+  if (layernorm_rows(single_src, M, d->c_s, nullptr, nullptr, s.xn16, nullptr, st)) return 1;
+  GemmArgs g = linear_args(M, 4 * HC, d->c_s, s.xn16, in_ptr<__half>(w, 2), s.qkvg, 0);
+  g.bias = in_ptr<float>(w, 3);
+  if (gemm_f16(g, st)) return 1;
+  if (single_attention(d->B, d->N, d->H, d->c, s.qkvg, bias, in_ptr<float>(in, 2), s.og, st)) return 1;
+  g = linear_args(M, d->c_s, HC, s.og, in_ptr<__half>(w, 4), single, 0);
+  g.bias = in_ptr<float>(w, 5);
+  if (d->residual) { g.add = single_src; g.ldadd = d->c_s; }
+  return gemm_f16(g, st);
+}
+
+// ----------------------------------------------------------------------- single_transition
+size_t prd_single_transition_workspace_bytes(const PrdDims* d) {
+  Carver c(nullptr);
+  c.take<__half>((size_t)d->B * d->N * d->c_s);
+  c.take<__half>((size_t)d->B * d->N * d->c_s * d->tf);
+  return c.total();
+}
+int prd_single_transition_fwd(const PrdDims* d, const void* const* in, void* const* out, const void* const* w,
+                              void* workspace, size_t workspace_bytes, void* stream) {
+  if (prd_device_check()) return 1;
+  PRD_WS_CHECK(prd_single_transition_workspace_bytes(d));
+  Carver c(workspace);
+  const int M = d->B * d->N, HID = d->c_s * d->tf;
+  __half* xn = c.take<__half>((size_t)M * d->c_s);
+  __half* h = c.take<__half>((size_t)M * HID);
+  const float* single_src = in_ptr<float>(in, 0);
+  float* single = out_ptr<float>(out, 0);
+  if (layernorm_rows(single_src, M, d->c_s, nullptr, nullptr, xn, nullptr, S(stream))) return 1;
+  GemmArgs g = linear_args(M, HID, d->c_s, xn, in_ptr<__half>(w, 0), h, 1);
+  g.bias = in_ptr<float>(w, 1);
+  g.act = 1;
+  if (gemm_f16(g, S(stream))) return 1;
+  g = linear_args(M, d->c_s, HID, h, in_ptr<__half>(w, 2), single, 0);
+  g.bias = in_ptr<float>(w, 3);
+  if (d->residual) { g.add = single_src; g.ldadd = d->c_s; }
+  return gemm_f16(g, S(stream));
+}
+
+// ---------------------------------------------------------------------------- outer_linear
+size_t prd_outer_linear_workspace_bytes(const PrdDims* d) {
+  Carver c(nullptr);
+  const size_t M = (size_t)d->B * d->N;
+  c.take<__half>(M * d->c_s);
+  c.take<float>(M * d->c_s);
+  c.take<float>(M * d->c_z);
+  return c.total();
+}
+int prd_outer_linear_fwd(const PrdDims* d, const void* const* in, void* const* out, const void* const* w,
+                         void* workspace, size_t workspace_bytes, void* stream) {
+  if (prd_device_check()) return 1;
+  PRD_WS_CHECK(prd_outer_linear_workspace_bytes(d));
+  Carver c(workspace);
+  const int M = d->B * d->N;
+  __half* xn16 = c.take<__half>((size_t)M * d->c_s);
+  float* xn32 = c.take<float>((size_t)M * d->c_s);
+  float* u = c.take<float>((size_t)M * d->c_z);
+  if (layernorm_rows(in_ptr<float>(in, 0), M, d->c_s, nullptr, nullptr, xn16, xn32, S(stream))) return 1;
+  GemmArgs g = linear_args(M, d->c_z, d->c_s, xn16, in_ptr<__half>(w, 1), u, 0);
+  if (gemm_f16(g, S(stream))) return 1;
+  return outer_linear(pd(d), d->c_s, in_ptr<float>(in, 1), out_ptr<float>(out, 0), d->residual, xn16, xn32,
+                      in_ptr<__half>(w, 0), u, in_ptr<float>(w, 2), S(stream));
+}
+
+// ----------------------------------------------------------------- triangle_multiplication
+namespace {
+struct TmWs { __half* ab; float* x; size_t total; };
+TmWs tm_carve(const PrdDims* d, void* ws) {
+  Carver c(ws);
+  TmWs s;
+  s.ab = c.take<__half>((size_t)2 * d->B * d->c_z * d->N * plane_ld(d->N));
+  s.x = c.take<float>((size_t)d->B * d->c_z * d->N * xplane_ld(d->N));
+  s.total = c.total();
+  return s;
+}
+}  // namespace
+size_t prd_triangle_multiplication_workspace_bytes(const PrdDims* d) { return tm_carve(d, nullptr).total; }
+int prd_triangle_multiplication_fwd(const PrdDims* d, const void* const* in, void* const* out, const void* const* w,
+                                    void* workspace, size_t workspace_bytes, void* stream) {
+  if (prd_device_check()) return 1;
+  PRD_WS_CHECK(prd_triangle_multiplication_workspace_bytes(d));
+  PRD_REQUIRE(d->mode == 0 || d->mode == 1, "triangle_multiplication: invalid mode %d", d->mode);
+  TmWs s = tm_carve(d, workspace);
+  cudaStream_t st = S(stream);
+  const int N = d->N, Np = plane_ld(N), Nx = xplane_ld(N);
+  const float* pair = in_ptr<float>(in, 0);
+  if (trimul_in(pd(d), pair, in_ptr<float>(in, 1), d->mode, in_ptr<__half>(w, 0), in_ptr<float>(w, 1), s.ab, st))
+    return 1;
+  // x_d[i,j] = sum_k a_d[i,k] b_d[j,k]   for every (b, d) plane
+  GemmArgs g;
+  g.M = N; g.N = N; g.K = N; g.nb1 = d->B * d->c_z;
+  g.A = s.ab; g.lda = Np; g.a_bs1 = (long long)N * Np;
+  g.B = s.ab + (size_t)d->B * d->c_z * N * Np; g.ldb = Np; g.b_bs1 = (long long)N * Np;
+  g.C = s.x; g.ldc = Nx; g.c_bs1 = (long long)N * Nx;
+  if (gemm_f16(g, st)) return 1;
+  return trimul_out(pd(d), pair, out_ptr<float>(out, 0), d->residual, s.x, in_ptr<__half>(w, 2), in_ptr<float>(w, 3), st);
+}
+
+// ---------------------------------------------------------------------- triangle_attention
+namespace {
+struct TaWs { __half* q; __half* k; __half* g; __half* vt; __half* og; size_t total; };
+TaWs ta_carve(const PrdDims* d, void* ws) {
+  Carver c(ws);
+  TaWs s;
+  const size_t R = (size_t)d->B * d->N * d->N;
+  s.q = c.take<__half>(R * 64);
+  s.k = c.take<__half>(R * 64);
+  s.g = c.take<__half>(R * 64);
+  s.vt = c.take<__half>((size_t)d->B * d->N * 64 * plane_ld(d->N));
+  s.og = c.take<__half>(R * 64);
+  s.total = c.total();
+  return s;
+}
+}  // namespace
+size_t prd_triangle_attention_workspace_bytes(const PrdDims* d) { return ta_carve(d, nullptr).total; }
+int prd_triangle_attention_fwd(const PrdDims* d, const void* const* in, void* const* out, const void* const* w,
+                               void* workspace, size_t workspace_bytes, void* stream) {
+  if (prd_device_check()) return 1;
+  PRD_WS_CHECK(prd_triangle_attention_workspace_bytes(d));
+  PRD_REQUIRE(d->H == 4 && d->c == 16, "triangle_attention: built for 4 heads x 16 channels (got %d x %d)", d->H, d->c);
+  PRD_REQUIRE(d->mode == 0 || d->mode == 1, "triangle_attention: invalid mode %d", d->mode);
+  TaWs s = ta_carve(d, workspace);
+  cudaStream_t st = S(stream);
+  const float* pair = in_ptr<float>(in, 0);
+  if (triattn_proj(pd(d), pair, d->mode, in_ptr<__half>(w, 0), in_ptr<float>(w, 1), s.q, s.k, s.g, s.vt, st)) return 1;
+  if (triattn_flash(pd(d), in_ptr<float>(in, 1), s.q, s.k, s.g, s.vt, s.og, st)) return 1;
+  return triattn_out(pd(d), pair, out_ptr<float>(out, 0), d->residual, d->mode, s.og, in_ptr<__half>(w, 2),
+                     in_ptr<float>(w, 3), st);
+}
+
+// ------------------------------------------------------------------------- pair_transition
+size_t prd_pair_transition_workspace_bytes(const PrdDims*) { return 256; }
+int prd_pair_transition_fwd(const PrdDims* d, const void* const* in, void* const* out, const void* const* w, void*,
+                            size_t, void* stream) {
+  if (prd_device_check()) return 1;
+  return pair_transition(pd(d), in_ptr<float>(in, 0), out_ptr<float>(out, 0), d->residual, in_ptr<__half>(w, 0), in_ptr<float>(w, 1),
+                         in_ptr<__half>(w, 2), in_ptr<float>(w, 3), d->c_z * d->tf, S(stream));
+}
+
+// ------------------------------------------------------------------------------ symmetrize
+size_t prd_symmetrize_workspace_bytes(const PrdDims*) { return 256; }
+int prd_symmetrize_fwd(const PrdDims* d, const void* const*, void* const* out, const void* const*, void*, size_t,
+                       void* stream) {
+  if (prd_device_check()) return 1;
+  return symmetrize_pair(pd(d), out_ptr<float>(out, 0), S(stream));
+}
+
+// ------------------------------------------------------------------------------ coord_head
+size_t prd_coord_head_workspace_bytes(const PrdDims*) { return 256; }
+int prd_coord_head_fwd(const PrdDims* d, const void* const* in, void* const* out, const void* const* w, void*, size_t,
+                       void* stream) {
+  if (prd_device_check()) return 1;
+  float* eps = out_ptr<float>(out, 0);
+  if (coord_head(pd(d), in_ptr<float>(in, 0), in_ptr<float>(in, 1), in_ptr<float>(in, 2), in_ptr<__half>(w, 0),
+                 in_ptr<float>(w, 1), in_ptr<float>(w, 2), eps, S(stream)))
+    return 1;
+  return remove_mean3(d->B, d->N, 3, eps, in_ptr<float>(in, 2), d->B, S(stream));
+}
+
+// -------------------------------------------------------------------------------- seq_head
+size_t prd_seq_head_workspace_bytes(const PrdDims* d) {
+  Carver c(nullptr);
+  c.take<__half>((size_t)d->B * d->N * d->c_s);
+  c.take<__half>((size_t)d->B * d->N * d->c_s);
+  return c.total();
+}
+int prd_seq_head_fwd(const PrdDims* d, const void* const* in, void* const* out, const void* const* w, void* workspace,
+                     size_t workspace_bytes, void* stream) {
+  if (prd_device_check()) return 1;
+  PRD_WS_CHECK(prd_seq_head_workspace_bytes(d));
+  Carver c(workspace);
+  const int M = d->B * d->N;
+  __half* xn = c.take<__half>((size_t)M * d->c_s);
+  __half* h = c.take<__half>((size_t)M * d->c_s);
+  if (layernorm_rows(in_ptr<float>(in, 0), M, d->c_s, nullptr, nullptr, xn, nullptr, S(stream))) return 1;
+  GemmArgs g = linear_args(M, d->c_s, d->c_s, xn, in_ptr<__half>(w, 0), h, 1);
+  g.bias = in_ptr<float>(w, 1);
+  g.act = 1;
+  if (gemm_f16(g, S(stream))) return 1;
+  g = linear_args(M, 21, d->c_s, h, in_ptr<__half>(w, 2), out_ptr<float>(out, 0), 0);
+  return gemm_f16(g, S(stream));
+}
+
+// ----------------------------------------------------------------------------- remove_mean
+size_t prd_remove_mean_workspace_bytes(const PrdDims*) { return 256; }
+int prd_remove_mean_fwd(const PrdDims* d, const void* const* in, void* const* out, const void* const*, void*, size_t,
+                        void* stream) {
+  if (prd_device_check()) return 1;
+  return remove_mean3(d->B, d->N, d->mode, out_ptr<float>(out, 0), in_ptr<float>(in, 0), d->H, S(stream));
+}
+
+// -------------------------------------------------------------------------- sampler_update
+size_t prd_sampler_update_workspace_bytes(const PrdDims*) { return 256; }
+int prd_sampler_update_fwd(const PrdDims* d, const void* const* in, void* const* out, const void* const*, void*,
+                           size_t, void* stream) {
+  if (prd_device_check()) return 1;
+  return sampler_update(d->B, d->N, in_ptr<float>(in, 0), in_ptr<float>(in, 1), in_ptr<float>(in, 2),
+                        in_ptr<float>(in, 3), static_cast<SamplerState*>(out[2]), out_ptr<float>(out, 0),
+                        out_ptr<float>(out, 1), S(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,221 @@
+// Batched fp16 x fp16 -> fp32 GEMM on tcgen05 tensor cores with TMA-staged operands.
+//
+//   C[b][m][n] = epilogue( alpha * sum_k A[b][m][k] * B[b][n][k] )        (both operands K-major)
+//
+// One CTA computes one 128 x BN output tile: warp 0 = TMA producer, warp 1 = UMMA issuer,
+// warps 2..5 = epilogue (TMEM -> registers -> global).  Operand tiles are [rows x 64] halves
+// in SWIZZLE_128B shared memory, STAGES-deep mbarrier ring; the accumulator lives in TMEM.
+//
+// Used for: the triangle-multiplication contraction (per (b, channel) NxNxN GEMMs), every
+// single-representation linear layer, SPAttention logits / PV.  See prd_denoiser.h.
+#include "prd_common.cuh"
+#include "prd_kernels.h"
+
+namespace prd {
+
+template <int BN, int STAGES>
+struct GemmSmem {
+  static constexpr int kABytes = 128 * 64 * 2;
+  static constexpr int kBBytes = BN * 64 * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kTotal = STAGES * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+struct GemmEpilogue {
+  int M, N;
+  float alpha;
+  const float* bias;                          // [N]
+  int act;                                    // 0 none, 1 relu, 2 sigmoid
+  const float* rowscale;                      // [M] per batch
+  long long rs_bs1, rs_bs2;
+  const float* mul;                           // [M, N] fp32, elementwise factor
+  long long ldmul, mul_bs1, mul_bs2;
+  const float* add;                           // [M, N] fp32, elementwise addend (residual / 2-D bias)
+  long long ldadd, add_bs1, add_bs2;
+  void* C;
+  long long ldc, c_bs1, c_bs2;
+  int c_fp16;
+};
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(192, 1)
+gemm_f16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, int num_kb,
+                int nb1, int a_b1, int a_b2, int b_b1, int b_b2, GemmEpilogue ep) {
+  extern __shared__ uint8_t smem_raw[];
+  using L = GemmSmem<BN, STAGES>;
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * L::kStageBytes);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + STAGES;
+  uint64_t* tmem_full = bars + 2 * STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n0 = blockIdx.x * BN, m0 = blockIdx.y * 128;
+  const int i1 = blockIdx.z % nb1, i2 = blockIdx.z / nb1;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(tmem_full, 1);
+    fence_barrier_init();
+    tma_prefetch_desc(&map_a);
+    tma_prefetch_desc(&map_b);
+  }
+  if (warp == 0) tmem_alloc(tmem_slot, BN < 32 ? 32 : BN);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(&empty[s], ph ^ 1);
+        mbar_expect_tx(&full[s], L::kStageBytes);
+        uint8_t* sa = smem + s * L::kStageBytes;
+        tma_load_4d(sa, &map_a, &full[s], kb * 64, m0, i1 * a_b1, i2 * a_b2);
+        tma_load_4d(sa + L::kABytes, &map_b, &full[s], kb * 64, n0, i1 * b_b1, i2 * b_b2);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_f16(128, BN);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(&full[s], ph);
+        tc_fence_after();
+        const uint32_t sa = base + s * L::kStageBytes;
+        umma_kblock(tmem, sa, sa + L::kABytes, idesc, kb > 0);
+        umma_commit(&empty[s]);
+      }
+      umma_commit(tmem_full);
+    }
+  } else {
+    // epilogue: warp w may only touch TMEM lanes [32*(w%4), 32*(w%4)+32)
+    const int q = warp & 3;
+    const int row = m0 + q * 32 + lane;
+    mbar_wait(tmem_full, 0);
+    tc_fence_after();
+    const long long boff_c = (long long)i1 * ep.c_bs1 + (long long)i2 * ep.c_bs2;
+    const float rs = (ep.rowscale != nullptr && row < ep.M)
+                         ? ep.rowscale[(long long)i1 * ep.rs_bs1 + (long long)i2 * ep.rs_bs2 + row]
+                         : 1.0f;
+    const float* mulp = ep.mul ? ep.mul + (long long)i1 * ep.mul_bs1 + (long long)i2 * ep.mul_bs2 + (long long)row * ep.ldmul : nullptr;
+    const float* addp = ep.add ? ep.add + (long long)i1 * ep.add_bs1 + (long long)i2 * ep.add_bs2 + (long long)row * ep.ldadd : nullptr;
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; ++c) {
+      uint32_t r[32];
+      tmem_ld32(tmem + (static_cast<uint32_t>(q * 32) << 16) + c * 32, r);
+      tmem_ld_wait();
+      const int col0 = n0 + c * 32;
+      if (row < ep.M && col0 < ep.N) {
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int col = col0 + j;
+          float x = ep.alpha * __uint_as_float(r[j]);
+          if (col < ep.N) {
+            if (ep.bias) x += __ldg(ep.bias + col);
+            if (ep.act == 1) x = fmaxf(x, 0.0f);
+            else if (ep.act == 2) x = 1.0f / (1.0f + __expf(-x));
+            x *= rs;
+            if (mulp) x *= mulp[col];
+            if (addp) x += addp[col];
+          }
+          v[j] = x;
+        }
+        const bool full_chunk = (col0 + 32 <= ep.N);
+        if (ep.c_fp16) {
+          __half* cp = reinterpret_cast<__half*>(ep.C) + boff_c + (long long)row * ep.ldc + col0;
+          if (full_chunk && ((reinterpret_cast<uintptr_t>(cp) & 15) == 0)) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              uint4 o;
+              o.x = pack_half2(v[j], v[j + 1]);
+              o.y = pack_half2(v[j + 2], v[j + 3]);
+              o.z = pack_half2(v[j + 4], v[j + 5]);
+              o.w = pack_half2(v[j + 6], v[j + 7]);
+              *reinterpret_cast<uint4*>(cp + j) = o;
+            }
+          } else {
+            for (int j = 0; j < 32 && col0 + j < ep.N; ++j) cp[j] = __float2half_rn(v[j]);
+          }
+        } else {
+          float* cp = reinterpret_cast<float*>(ep.C) + boff_c + (long long)row * ep.ldc + col0;
+          if (full_chunk && ((reinterpret_cast<uintptr_t>(cp) & 15) == 0)) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(cp + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          } else {
+            for (int j = 0; j < 32 && col0 + j < ep.N; ++j) cp[j] = v[j];
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, BN < 32 ? 32 : BN);
+}
+
+template <int BN, int STAGES>
+static int launch_gemm(const GemmArgs& g, cudaStream_t stream) {
+  using L = GemmSmem<BN, STAGES>;
+  CUtensorMap map_a, map_b;
+  TmaDims da, db;
+  const int nb1 = g.nb1 > 0 ? g.nb1 : 1, nb2 = g.nb2 > 0 ? g.nb2 : 1;
+  auto fill = [&](TmaDims& d, long long rows, long long ld, long long bs1, long long bs2, int box_rows) {
+    d.size[0] = (uint64_t)g.K;
+    d.size[1] = (uint64_t)rows;
+    d.size[2] = bs1 != 0 ? (uint64_t)nb1 : 1;
+    d.size[3] = bs2 != 0 ? (uint64_t)nb2 : 1;
+    d.stride[0] = (uint64_t)ld * 2;
+    d.stride[1] = (uint64_t)(bs1 != 0 ? bs1 : ld * rows) * 2;
+    d.stride[2] = (uint64_t)(bs2 != 0 ? bs2 : ld * rows) * 2;
+    // dims of size 1 still need a 16-byte-multiple stride
+    d.stride[1] = (d.stride[1] + 15) & ~15ull;
+    d.stride[2] = (d.stride[2] + 15) & ~15ull;
+    d.box[0] = 64;
+    d.box[1] = (uint32_t)box_rows;
+    d.box[2] = 1;
+    d.box[3] = 1;
+  };
+  PRD_REQUIRE(g.M > 0 && g.N > 0 && g.K > 0, "gemm: empty problem M=%d N=%d K=%d", g.M, g.N, g.K);
+  PRD_REQUIRE(g.lda % 8 == 0 && g.ldb % 8 == 0, "gemm: lda/ldb must be multiples of 8 halves (lda=%lld ldb=%lld)", g.lda, g.ldb);
+  PRD_REQUIRE((g.a_bs1 % 8 == 0) && (g.a_bs2 % 8 == 0) && (g.b_bs1 % 8 == 0) && (g.b_bs2 % 8 == 0), "gemm: batch strides must be multiples of 8 halves");
+  fill(da, g.M, g.lda, g.a_bs1, g.a_bs2, 128);
+  fill(db, g.N, g.ldb, g.b_bs1, g.b_bs2, BN);
+  if (make_tensor_map(&map_a, g.A, 2, 4, da, true)) return 1;
+  if (make_tensor_map(&map_b, g.B, 2, 4, db, true)) return 1;
+  GemmEpilogue ep;
+  ep.M = g.M; ep.N = g.N; ep.alpha = g.alpha; ep.bias = g.bias; ep.act = g.act;
+  ep.rowscale = g.rowscale; ep.rs_bs1 = g.rs_bs1; ep.rs_bs2 = g.rs_bs2;
+  ep.mul = g.mul; ep.ldmul = g.ldmul; ep.mul_bs1 = g.mul_bs1; ep.mul_bs2 = g.mul_bs2;
+  ep.add = g.add; ep.ldadd = g.ldadd; ep.add_bs1 = g.add_bs1; ep.add_bs2 = g.add_bs2;
+  ep.C = g.C; ep.ldc = g.ldc; ep.c_bs1 = g.c_bs1; ep.c_bs2 = g.c_bs2; ep.c_fp16 = g.c_fp16;
+  auto kern = gemm_f16_kernel<BN, STAGES>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    PRD_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
+    attr_set = true;
+  }
+  dim3 grid((g.N + BN - 1) / BN, (g.M + 127) / 128, nb1 * nb2);
+  const int num_kb = (g.K + 63) / 64;
+  kern<<<grid, 192, L::kTotal, stream>>>(map_a, map_b, num_kb, nb1, g.a_bs1 != 0 ? 1 : 0, g.a_bs2 != 0 ? 1 : 0,
+                                         g.b_bs1 != 0 ? 1 : 0, g.b_bs2 != 0 ? 1 : 0, ep);
+  PRD_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int gemm_f16(const GemmArgs& g, cudaStream_t stream) {
+  if (g.N <= 64) return launch_gemm<64, 4>(g, stream);
+  return launch_gemm<128, 3>(g, stream);
+}
+
+}  // namespace prd

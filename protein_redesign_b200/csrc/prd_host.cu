@@ -1,0 +1,97 @@
+// Host-side plumbing shared by every entry point: thread-local error string, version query,
+// and TMA tensor-map construction through the driver entry point (resolved at run time with
+// cudaGetDriverEntryPoint, so the library has no link-time dependency on libcuda).
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/prd_denoiser.h"
+#include "prd_common.cuh"
+
+namespace prd {
+
+static thread_local char g_error[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_error, sizeof(g_error), fmt, ap);
+  va_end(ap);
+}
+
+int check_cuda(cudaError_t e, const char* what) {
+  if (e == cudaSuccess) return 0;
+  set_error("CUDA error %s (%s) at %s", cudaGetErrorName(e), cudaGetErrorString(e), what);
+  return 1;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess) {
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+  }
+  return fn;
+}
+
+int make_tensor_map(CUtensorMap* out, const void* base, int elem_bytes, int rank, const TmaDims& d, bool swizzle128) {
+  EncodeTiledFn fn = get_encode_fn();
+  PRD_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled not available (no CUDA driver?)");
+  PRD_REQUIRE(rank >= 2 && rank <= 4, "tensor map rank %d unsupported", rank);
+  PRD_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, "tensor map base not 16-byte aligned");
+  cuuint64_t size[4];
+  cuuint64_t stride[3];
+  cuuint32_t box[4];
+  cuuint32_t estr[4];
+  for (int i = 0; i < rank; ++i) {
+    size[i] = d.size[i];
+    box[i] = d.box[i];
+    estr[i] = 1;
+    PRD_REQUIRE(d.size[i] > 0 && d.box[i] > 0 && d.box[i] <= 256, "bad tensor map dim %d (size %llu box %u)", i,
+                (unsigned long long)d.size[i], d.box[i]);
+  }
+  for (int i = 0; i + 1 < rank; ++i) {
+    stride[i] = d.stride[i];
+    PRD_REQUIRE((d.stride[i] & 15) == 0, "tensor map stride %d (%llu B) not a multiple of 16", i,
+                (unsigned long long)d.stride[i]);
+  }
+  if (swizzle128) PRD_REQUIRE(d.box[0] * elem_bytes == 128, "swizzle-128 box must span 128 bytes");
+  CUtensorMapDataType dt = elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+  CUresult r = fn(out, dt, (cuuint32_t)rank, const_cast<void*>(base), size, stride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  PRD_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return 0;
+}
+
+}  // namespace prd
+
+extern "C" {
+
+int prd_version(void) { return PRD_VERSION; }
+
+const char* prd_last_error(void) { return prd::g_error; }
+
+int prd_device_check(void) {
+  int dev = 0;
+  cudaDeviceProp prop;
+  if (prd::check_cuda(cudaGetDevice(&dev), "cudaGetDevice")) return 1;
+  if (prd::check_cuda(cudaGetDeviceProperties(&prop, dev), "cudaGetDeviceProperties")) return 1;
+  if (prop.major != 10) {
+    prd::set_error("libprd_sm100 needs an sm_100 (B200) device, found sm_%d%d (%s)", prop.major, prop.minor, prop.name);
+    return 1;
+  }
+  return 0;
+}
+
+}  // extern "C"

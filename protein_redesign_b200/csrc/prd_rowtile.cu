@@ -1,0 +1,754 @@
+// Pair-row tile kernels: every op of the pair stack whose contraction dim is the channel dim.
+//   pair_transition   FoldingBlock.pair_fc                       (modules.py:321-326,342)
+//   trimul_in/out     TriangleMultiplication projections/gating  (modules.py:262-274)
+//   triattn_proj/out  TriangleAttention q,k,v,gate / out_proj    (modules.py:185-225,236-243)
+// See prd_rowtile.cuh for the execution model.
+#include "prd_kernels.h"
+#include "prd_rowtile.cuh"
+
+namespace prd {
+
+namespace {
+
+struct RowMap {
+  int N;
+  long long NN;
+  int transposed;  // 0: logical row (b,s,t) reads pair[b,s,t]; 1: reads pair[b,t,s]
+  __device__ __forceinline__ void decompose(long long r, int& b, int& s, int& t) const {
+    b = static_cast<int>(r / NN);
+    const int rem = static_cast<int>(r - (long long)b * NN);
+    s = rem / N;
+    t = rem - s * N;
+  }
+  __device__ __forceinline__ long long src_row(int b, int s, int t) const {
+    return transposed ? ((long long)b * NN + (long long)t * N + s) : ((long long)b * NN + (long long)s * N + t);
+  }
+};
+
+template <typename Kern>
+int set_smem(Kern k, int bytes) {
+  return check_cuda(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes), "cudaFuncSetAttribute");
+}
+
+inline int grid_for(long long tiles, int ctas_per_sm) {
+  long long g = (long long)kNumSMs * ctas_per_sm;
+  return static_cast<int>(tiles < g ? tiles : g);
+}
+
+}  // namespace
+
+// =========================================================================================
+// pair_fc: pair += W2 relu(W1 LN(pair) + b1) + b2
+// =========================================================================================
+template <int CZ, int HID>
+__global__ void __launch_bounds__(128, 1)
+pair_transition_kernel(const float* pair, float* dst, int residual, long long R, const __half* __restrict__ w1,
+                       const float* __restrict__ b1, const __half* __restrict__ w2, const float* __restrict__ b2) {
+  extern __shared__ uint8_t raw[];
+  constexpr int KBH = HID / 64;
+  uint8_t* sm = smem_align1024(raw);
+  uint8_t* sA = sm;
+  uint8_t* sH = sA + 16384;
+  uint8_t* sW1 = sH + KBH * 16384;
+  uint8_t* sW2 = sW1 + HID * 128;
+  uint8_t* sSt = sW2 + KBH * CZ * 128;
+  float* sB1 = reinterpret_cast<float*>(sSt + 2 * RowStage<CZ>::kBytes);
+  float* sB2 = sB1 + HID;
+  uint64_t* full = reinterpret_cast<uint64_t*>(sB2 + CZ);
+  uint64_t* mma_bar = full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mma_bar + 1);
+
+  const int t = threadIdx.x, warp = t >> 5;
+  if (t == 0) {
+    mbar_init(&full[0], kTileRows);
+    mbar_init(&full[1], kTileRows);
+    mbar_init(mma_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc(tmem_slot, HID);
+  load_weight_kblocks(sW1, w1, HID, CZ, CZ, t, 128);
+  load_weight_kblocks(sW2, w2, CZ, HID, HID, t, 128);
+  for (int i = t; i < HID; i += 128) sB1[i] = b1[i];
+  for (int i = t; i < CZ; i += 128) sB2[i] = b2[i];
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t tm_lane = tmem + (static_cast<uint32_t>(warp * 32) << 16);
+
+  const long long num_tiles = (R + kTileRows - 1) / kTileRows;
+  uint32_t mma_phase = 0;
+  long long tile = blockIdx.x;
+  if (tile < num_tiles) {
+    const long long r = tile * kTileRows + t;
+    issue_row_load<CZ>(sSt, t, pair + r * CZ, r < R, &full[0]);
+  }
+  for (int it = 0; tile < num_tiles; tile += gridDim.x, ++it) {
+    const int buf = it & 1;
+    uint8_t* st = sSt + buf * RowStage<CZ>::kBytes;
+    const long long next = tile + gridDim.x;
+    if (next < num_tiles) {
+      bulk_wait_read0();
+      const long long rn = next * kTileRows + t;
+      issue_row_load<CZ>(sSt + (buf ^ 1) * RowStage<CZ>::kBytes, t, pair + rn * CZ, rn < R, &full[buf ^ 1]);
+    }
+    mbar_wait(&full[buf], (it >> 1) & 1);
+    const long long r = tile * kTileRows + t;
+    const bool valid = r < R;
+    float* my = stage_row<CZ>(st, t);
+    {
+      float x[CZ];
+      if (valid) {
+        read_row<CZ>(my, x);
+      } else {
+#pragma unroll
+        for (int i = 0; i < CZ; ++i) x[i] = 0.f;
+      }
+      layernorm_inplace<CZ>(x);
+      store_a_row<CZ>(sA, t, x);
+    }
+    sync_before_mma();
+    if (t == 0) {
+      tc_fence_after();
+      umma_multi(tmem, smem_u32(sA), smem_u32(sW1), 1, HID * 128, umma_idesc_f16(128, HID), false);
+      umma_commit(mma_bar);
+    }
+    mbar_wait(mma_bar, mma_phase);
+    mma_phase ^= 1;
+    tc_fence_after();
+#pragma unroll 1
+    for (int c = 0; c < HID / 32; ++c) {
+      uint32_t acc[32];
+      tmem_ld32(tm_lane + c * 32, acc);
+      tmem_ld_wait();
+      float v[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = fmaxf(__uint_as_float(acc[j]) + sB1[c * 32 + j], 0.f);
+      store_a_cols32(sH, t, c * 32, v);
+    }
+    sync_before_mma();
+    if (t == 0) {
+      tc_fence_after();
+      umma_multi(tmem, smem_u32(sH), smem_u32(sW2), KBH, CZ * 128, umma_idesc_f16(128, CZ), false);
+      umma_commit(mma_bar);
+    }
+    mbar_wait(mma_bar, mma_phase);
+    mma_phase ^= 1;
+    tc_fence_after();
+#pragma unroll
+    for (int c = 0; c < CZ / 32; ++c) {
+      uint32_t acc[32];
+      tmem_ld32(tm_lane + c * 32, acc);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        float4 x = *reinterpret_cast<float4*>(my + c * 32 + j);
+        if (!residual) x = make_float4(0.f, 0.f, 0.f, 0.f);
+        x.x += __uint_as_float(acc[j + 0]) + sB2[c * 32 + j + 0];
+        x.y += __uint_as_float(acc[j + 1]) + sB2[c * 32 + j + 1];
+        x.z += __uint_as_float(acc[j + 2]) + sB2[c * 32 + j + 2];
+        x.w += __uint_as_float(acc[j + 3]) + sB2[c * 32 + j + 3];
+        *reinterpret_cast<float4*>(my + c * 32 + j) = x;
+      }
+    }
+    fence_proxy_async_smem();
+    if (valid) bulk_s2g(dst + r * CZ, my, CZ * 4);
+    bulk_commit();
+  }
+  bulk_wait0();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, HID);
+}
+
+template <int CZ, int HID>
+static int launch_pair_transition(const PairDims& d, const float* pair, float* dst, int residual, const __half* w1,
+                                  const float* b1, const __half* w2, const float* b2, cudaStream_t s) {
+  constexpr int KBH = HID / 64;
+  constexpr int smem = 1024 + 16384 + KBH * 16384 + HID * 128 + KBH * CZ * 128 + 2 * RowStage<CZ>::kBytes +
+                       (HID + CZ) * 4 + 64;
+  auto kern = pair_transition_kernel<CZ, HID>;
+  if (set_smem(kern, smem)) return 1;
+  const long long R = (long long)d.B * d.N * d.N;
+  const long long tiles = (R + kTileRows - 1) / kTileRows;
+  kern<<<grid_for(tiles, 1), 128, smem, s>>>(pair, dst, residual, R, w1, b1, w2, b2);
+  PRD_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int pair_transition(const PairDims& d, const float* pair, float* dst, int residual, const __half* w1, const float* b1,
+                    const __half* w2, const float* b2, int hidden, cudaStream_t s) {
+  if (d.CZ == 64 && hidden == 256) return launch_pair_transition<64, 256>(d, pair, dst, residual, w1, b1, w2, b2, s);
+  if (d.CZ == 32 && hidden == 128) return launch_pair_transition<32, 128>(d, pair, dst, residual, w1, b1, w2, b2, s);
+  set_error("pair_transition: unsupported pair_dim %d / hidden %d (built: 64/256, 32/128)", d.CZ, hidden);
+  return 1;
+}
+
+// =========================================================================================
+// Triangle multiplication, input side: [a|b] = m2 * sigmoid(G p + bg) * (W p + bw), p = LN(pair),
+// written as fp16 channel planes ab[which][b][d][i][k] (k contiguous, row stride plane_ld(N)) so
+// that both einsum modes become plain K-major NT GEMMs  x_d[i,j] = sum_k a_d[i,k] b_d[j,k]:
+//   outgoing: a_d[i,k] = a[b,i,k,d]      (logical row (b,i,k) reads pair[b,i,k])
+//   incoming: a_d[i,k] = a[b,k,i,d]      (logical row (b,i,k) reads pair[b,k,i])
+// w_in rows: [0,2CZ) = ab_proj, [2CZ,4CZ) = ab_gate.
+// =========================================================================================
+template <int CZ>
+__global__ void __launch_bounds__(128, 1)
+trimul_in_kernel(const float* __restrict__ pair, const float* __restrict__ mask, RowMap map, int B, long long R,
+                 const __half* __restrict__ w_in, const float* __restrict__ b_in, __half* __restrict__ ab, int Np) {
+  extern __shared__ uint8_t raw[];
+  constexpr int NOUT = 4 * CZ;
+  uint8_t* sm = smem_align1024(raw);
+  uint8_t* sA = sm;
+  uint8_t* sW = sA + 16384;
+  uint8_t* sSt = sW + NOUT * 128;
+  float* sB = reinterpret_cast<float*>(sSt + 2 * RowStage<CZ>::kBytes);
+  uint64_t* full = reinterpret_cast<uint64_t*>(sB + NOUT);
+  uint64_t* mma_bar = full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mma_bar + 1);
+
+  const int t = threadIdx.x, warp = t >> 5;
+  if (t == 0) {
+    mbar_init(&full[0], kTileRows);
+    mbar_init(&full[1], kTileRows);
+    mbar_init(mma_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc(tmem_slot, NOUT);
+  load_weight_kblocks(sW, w_in, NOUT, CZ, CZ, t, 128);
+  for (int i = t; i < NOUT; i += 128) sB[i] = b_in[i];
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t tm_lane = tmem + (static_cast<uint32_t>(warp * 32) << 16);
+  const long long plane = (long long)map.N * Np;
+
+  const long long num_tiles = (R + kTileRows - 1) / kTileRows;
+  uint32_t mma_phase = 0;
+  long long tile = blockIdx.x;
+  auto issue = [&](long long tl, int buf) {
+    const long long r = tl * kTileRows + t;
+    int b = 0, s = 0, k = 0;
+    if (r < R) map.decompose(r, b, s, k);
+    issue_row_load<CZ>(sSt + buf * RowStage<CZ>::kBytes, t, pair + map.src_row(b, s, k) * CZ, r < R, &full[buf]);
+  };
+  if (tile < num_tiles) issue(tile, 0);
+  for (int it = 0; tile < num_tiles; tile += gridDim.x, ++it) {
+    const int buf = it & 1;
+    const long long next = tile + gridDim.x;
+    if (next < num_tiles) issue(next, buf ^ 1);
+    mbar_wait(&full[buf], (it >> 1) & 1);
+    const long long r = tile * kTileRows + t;
+    const bool valid = r < R;
+    int b = 0, i = 0, k = 0;
+    if (valid) map.decompose(r, b, i, k);
+    {
+      float x[CZ];
+      if (valid) {
+        read_row<CZ>(stage_row<CZ>(sSt + buf * RowStage<CZ>::kBytes, t), x);
+      } else {
+#pragma unroll
+        for (int q = 0; q < CZ; ++q) x[q] = 0.f;
+      }
+      layernorm_inplace<CZ>(x);
+      store_a_row<CZ>(sA, t, x);
+    }
+    sync_before_mma();
+    if (t == 0) {
+      tc_fence_after();
+      umma_multi(tmem, smem_u32(sA), smem_u32(sW), 1, NOUT * 128, umma_idesc_f16(128, NOUT), false);
+      umma_commit(mma_bar);
+    }
+    // mask_2d for the *source* element: m[b,i]*m[b,k] is symmetric, same for both modes
+    const float m2 = valid ? mask[(long long)b * map.N + i] * mask[(long long)b * map.N + k] : 0.f;
+    __half* dst0 = ab + ((long long)b * CZ * map.N + i) * Np + k;
+    mbar_wait(mma_bar, mma_phase);
+    mma_phase ^= 1;
+    tc_fence_after();
+#pragma unroll 1
+    for (int c = 0; c < 2 * CZ / 32; ++c) {
+      uint32_t pr[32], ga[32];
+      tmem_ld32(tm_lane + c * 32, pr);
+      tmem_ld32(tm_lane + 2 * CZ + c * 32, ga);
+      tmem_ld_wait();
+      if (valid) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int cc = c * 32 + j;  // channel in [0, 2CZ): a = [0,CZ), b = [CZ,2CZ)
+          const float g = sigmoidf_fast(__uint_as_float(ga[j]) + sB[2 * CZ + cc]);
+          const float v = m2 * g * (__uint_as_float(pr[j]) + sB[cc]);
+          const long long pl = (cc < CZ) ? cc : (cc - CZ) + (long long)B * CZ;
+          dst0[pl * plane] = __float2half_rn(v);
+        }
+      }
+    }
+    // all TMEM reads of this tile must retire before the next tile's MMA overwrites the columns
+    tc_fence_before();
+    __syncthreads();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, NOUT);
+}
+
+int trimul_in(const PairDims& d, const float* pair, const float* mask, int mode, const __half* w_in, const float* b_in,
+              __half* ab, cudaStream_t s) {
+  const long long R = (long long)d.B * d.N * d.N;
+  const long long tiles = (R + kTileRows - 1) / kTileRows;
+  RowMap map{d.N, (long long)d.N * d.N, mode};
+  const int Np = plane_ld(d.N);
+  if (d.CZ == 64) {
+    constexpr int CZ = 64;
+    constexpr int smem = 1024 + 16384 + 4 * CZ * 128 + 2 * RowStage<CZ>::kBytes + 4 * CZ * 4 + 64;
+    auto kern = trimul_in_kernel<CZ>;
+    if (set_smem(kern, smem)) return 1;
+    kern<<<grid_for(tiles, 2), 128, smem, s>>>(pair, mask, map, d.B, R, w_in, b_in, ab, Np);
+  } else if (d.CZ == 32) {
+    constexpr int CZ = 32;
+    constexpr int smem = 1024 + 16384 + 4 * CZ * 128 + 2 * RowStage<CZ>::kBytes + 4 * CZ * 4 + 64;
+    auto kern = trimul_in_kernel<CZ>;
+    if (set_smem(kern, smem)) return 1;
+    kern<<<grid_for(tiles, 2), 128, smem, s>>>(pair, mask, map, d.B, R, w_in, b_in, ab, Np);
+  } else {
+    set_error("trimul_in: unsupported pair_dim %d", d.CZ);
+    return 1;
+  }
+  PRD_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// =========================================================================================
+// Triangle multiplication, output side: pair += sigmoid(Go p + bgo) * (Wo LN(x) + bo)
+// x: fp32 planes [B][CZ][N][Nx] from the contraction GEMM.  w_out rows: [0,CZ) out_gate, [CZ,2CZ) out_proj.
+// =========================================================================================
+template <int CZ>
+__global__ void __launch_bounds__(128, 1)
+trimul_out_kernel(const float* pair, float* dst, int residual, const float* __restrict__ xpl, int N, int Nx, long long R,
+                  const __half* __restrict__ w_out, const float* __restrict__ b_out) {
+  extern __shared__ uint8_t raw[];
+  uint8_t* sm = smem_align1024(raw);
+  uint8_t* sAp = sm;
+  uint8_t* sAx = sAp + 16384;
+  uint8_t* sW = sAx + 16384;  // two B tiles of [CZ x 64]
+  uint8_t* sSt = sW + 2 * CZ * 128;
+  float* sB = reinterpret_cast<float*>(sSt + 2 * RowStage<CZ>::kBytes);
+  uint64_t* full = reinterpret_cast<uint64_t*>(sB + 2 * CZ);
+  uint64_t* mma_bar = full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mma_bar + 1);
+  constexpr int TCOLS = 2 * CZ;
+
+  const int t = threadIdx.x, warp = t >> 5;
+  if (t == 0) {
+    mbar_init(&full[0], kTileRows);
+    mbar_init(&full[1], kTileRows);
+    mbar_init(mma_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc(tmem_slot, TCOLS);
+  load_weight_kblocks(sW, w_out, CZ, CZ, CZ, t, 128);
+  load_weight_kblocks(sW + CZ * 128, w_out + CZ * CZ, CZ, CZ, CZ, t, 128);
+  for (int i = t; i < 2 * CZ; i += 128) sB[i] = b_out[i];
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t tm_lane = tmem + (static_cast<uint32_t>(warp * 32) << 16);
+  const long long NN = (long long)N * N;
+  const long long xplane = (long long)N * Nx;
+
+  const long long num_tiles = (R + kTileRows - 1) / kTileRows;
+  uint32_t mma_phase = 0;
+  long long tile = blockIdx.x;
+  if (tile < num_tiles) {
+    const long long r = tile * kTileRows + t;
+    issue_row_load<CZ>(sSt, t, pair + r * CZ, r < R, &full[0]);
+  }
+  for (int it = 0; tile < num_tiles; tile += gridDim.x, ++it) {
+    const int buf = it & 1;
+    uint8_t* st = sSt + buf * RowStage<CZ>::kBytes;
+    const long long next = tile + gridDim.x;
+    if (next < num_tiles) {
+      bulk_wait_read0();
+      const long long rn = next * kTileRows + t;
+      issue_row_load<CZ>(sSt + (buf ^ 1) * RowStage<CZ>::kBytes, t, pair + rn * CZ, rn < R, &full[buf ^ 1]);
+    }
+    const long long r = tile * kTileRows + t;
+    const bool valid = r < R;
+    float* my = stage_row<CZ>(st, t);
+    {
+      // contraction result for this (b,i,j): one value per channel plane, coalesced across lanes
+      float x[CZ];
+      if (valid) {
+        const int b = static_cast<int>(r / NN);
+        const int rem = static_cast<int>(r - (long long)b * NN);
+        const int i = rem / N, j = rem - i * N;
+        const float* xp = xpl + (long long)b * CZ * xplane + (long long)i * Nx + j;
+#pragma unroll
+        for (int dch = 0; dch < CZ; ++dch) x[dch] = __ldg(xp + dch * xplane);
+      } else {
+#pragma unroll
+        for (int q = 0; q < CZ; ++q) x[q] = 0.f;
+      }
+      layernorm_inplace<CZ>(x);
+      store_a_row<CZ>(sAx, t, x);
+    }
+    mbar_wait(&full[buf], (it >> 1) & 1);
+    {
+      float x[CZ];
+      if (valid) {
+        read_row<CZ>(my, x);
+      } else {
+#pragma unroll
+        for (int q = 0; q < CZ; ++q) x[q] = 0.f;
+      }
+      layernorm_inplace<CZ>(x);
+      store_a_row<CZ>(sAp, t, x);
+    }
+    sync_before_mma();
+    if (t == 0) {
+      tc_fence_after();
+      umma_multi(tmem, smem_u32(sAp), smem_u32(sW), 1, CZ * 128, umma_idesc_f16(128, CZ), false);
+      umma_multi(tmem + CZ, smem_u32(sAx), smem_u32(sW + CZ * 128), 1, CZ * 128, umma_idesc_f16(128, CZ), false);
+      umma_commit(mma_bar);
+    }
+    mbar_wait(mma_bar, mma_phase);
+    mma_phase ^= 1;
+    tc_fence_after();
+#pragma unroll
+    for (int c = 0; c < CZ / 32; ++c) {
+      uint32_t ga[32], pr[32];
+      tmem_ld32(tm_lane + c * 32, ga);
+      tmem_ld32(tm_lane + CZ + c * 32, pr);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        float4 x = *reinterpret_cast<float4*>(my + c * 32 + j);
+        if (!residual) x = make_float4(0.f, 0.f, 0.f, 0.f);
+        float o[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int cc = c * 32 + j + e;
+          o[e] = sigmoidf_fast(__uint_as_float(ga[j + e]) + sB[cc]) * (__uint_as_float(pr[j + e]) + sB[CZ + cc]);
+        }
+        x.x += o[0];
+        x.y += o[1];
+        x.z += o[2];
+        x.w += o[3];
+        *reinterpret_cast<float4*>(my + c * 32 + j) = x;
+      }
+    }
+    fence_proxy_async_smem();
+    if (valid) bulk_s2g(dst + r * CZ, my, CZ * 4);
+    bulk_commit();
+    tc_fence_before();
+    __syncthreads();
+  }
+  bulk_wait0();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, TCOLS);
+}
+
+int trimul_out(const PairDims& d, const float* pair, float* dst, int residual, const float* x, const __half* w_out,
+               const float* b_out, cudaStream_t s) {
+  const long long R = (long long)d.B * d.N * d.N;
+  const long long tiles = (R + kTileRows - 1) / kTileRows;
+  const int Nx = xplane_ld(d.N);
+  if (d.CZ == 64) {
+    constexpr int CZ = 64;
+    constexpr int smem = 1024 + 2 * 16384 + 2 * CZ * 128 + 2 * RowStage<CZ>::kBytes + 2 * CZ * 4 + 64;
+    auto kern = trimul_out_kernel<CZ>;
+    if (set_smem(kern, smem)) return 1;
+    kern<<<grid_for(tiles, 2), 128, smem, s>>>(pair, dst, residual, x, d.N, Nx, R, w_out, b_out);
+  } else if (d.CZ == 32) {
+    constexpr int CZ = 32;
+    constexpr int smem = 1024 + 2 * 16384 + 2 * CZ * 128 + 2 * RowStage<CZ>::kBytes + 2 * CZ * 4 + 64;
+    auto kern = trimul_out_kernel<CZ>;
+    if (set_smem(kern, smem)) return 1;
+    kern<<<grid_for(tiles, 2), 128, smem, s>>>(pair, dst, residual, x, d.N, Nx, R, w_out, b_out);
+  } else {
+    set_error("trimul_out: unsupported pair_dim %d", d.CZ);
+    return 1;
+  }
+  PRD_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// =========================================================================================
+// Triangle attention projections.  Logical row (b, seq, tok): "starting" reads pair[b,seq,tok],
+// "ending" reads pair[b,tok,seq].  w rows: [0,64) q, [64,128) k, [128,192) v, [192,256) gate.
+// Outputs (fp16): q (pre-scaled by 1/sqrt(c) = 0.25), k, g = sigmoid(gate) as [rows][64];
+// v transposed per sequence: vt[(b*N+seq)][h*16+c][tok] (tok contiguous, row stride plane_ld(N)),
+// i.e. the K-major B operand of the P.V product.
+// =========================================================================================
+template <int CZ>
+__global__ void __launch_bounds__(128, 1)
+triattn_proj_kernel(const float* __restrict__ pair, RowMap map, long long R, const __half* __restrict__ w,
+                    const float* __restrict__ b_gate, __half* __restrict__ q, __half* __restrict__ k,
+                    __half* __restrict__ g, __half* __restrict__ vt, int Np) {
+  extern __shared__ uint8_t raw[];
+  constexpr int NOUT = 256;
+  uint8_t* sm = smem_align1024(raw);
+  uint8_t* sA = sm;
+  uint8_t* sW = sA + 16384;
+  uint8_t* sSt = sW + NOUT * 128;
+  float* sB = reinterpret_cast<float*>(sSt + 2 * RowStage<CZ>::kBytes);
+  uint64_t* full = reinterpret_cast<uint64_t*>(sB + 64);
+  uint64_t* mma_bar = full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mma_bar + 1);
+
+  const int t = threadIdx.x, warp = t >> 5;
+  if (t == 0) {
+    mbar_init(&full[0], kTileRows);
+    mbar_init(&full[1], kTileRows);
+    mbar_init(mma_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc(tmem_slot, NOUT);
+  load_weight_kblocks(sW, w, NOUT, CZ, CZ, t, 128);
+  if (t < 64) sB[t] = b_gate[t];
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t tm_lane = tmem + (static_cast<uint32_t>(warp * 32) << 16);
+
+  const long long num_tiles = (R + kTileRows - 1) / kTileRows;
+  uint32_t mma_phase = 0;
+  long long tile = blockIdx.x;
+  auto issue = [&](long long tl, int buf) {
+    const long long r = tl * kTileRows + t;
+    int b = 0, s = 0, tk = 0;
+    if (r < R) map.decompose(r, b, s, tk);
+    issue_row_load<CZ>(sSt + buf * RowStage<CZ>::kBytes, t, pair + map.src_row(b, s, tk) * CZ, r < R, &full[buf]);
+  };
+  if (tile < num_tiles) issue(tile, 0);
+  for (int it = 0; tile < num_tiles; tile += gridDim.x, ++it) {
+    const int buf = it & 1;
+    const long long next = tile + gridDim.x;
+    if (next < num_tiles) issue(next, buf ^ 1);
+    mbar_wait(&full[buf], (it >> 1) & 1);
+    const long long r = tile * kTileRows + t;
+    const bool valid = r < R;
+    {
+      float x[CZ];
+      if (valid) {
+        read_row<CZ>(stage_row<CZ>(sSt + buf * RowStage<CZ>::kBytes, t), x);
+      } else {
+#pragma unroll
+        for (int i = 0; i < CZ; ++i) x[i] = 0.f;
+      }
+      layernorm_inplace<CZ>(x);
+      store_a_row<CZ>(sA, t, x);
+    }
+    sync_before_mma();
+    if (t == 0) {
+      tc_fence_after();
+      umma_multi(tmem, smem_u32(sA), smem_u32(sW), 1, NOUT * 128, umma_idesc_f16(128, NOUT), false);
+      umma_commit(mma_bar);
+    }
+    int b = 0, s = 0, tk = 0;
+    if (valid) map.decompose(r, b, s, tk);
+    mbar_wait(mma_bar, mma_phase);
+    mma_phase ^= 1;
+    tc_fence_after();
+#pragma unroll 1
+    for (int c = 0; c < 8; ++c) {
+      uint32_t acc[32];
+      tmem_ld32(tm_lane + c * 32, acc);
+      tmem_ld_wait();
+      if (!valid) continue;
+      const int part = c >> 1;       // 0 q, 1 k, 2 v, 3 gate
+      const int col0 = (c & 1) * 32;  // column inside the 64-wide part
+      if (part == 2) {
+        __half* vp = vt + (((long long)b * map.N + s) * 64 + col0) * Np + tk;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) vp[(long long)j * Np] = __float2half_rn(__uint_as_float(acc[j]));
+      } else {
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          float a = __uint_as_float(acc[j]);
+          if (part == 0) a *= 0.25f;
+          if (part == 3) a = sigmoidf_fast(a + sB[col0 + j]);
+          v[j] = a;
+        }
+        __half* dst = (part == 0 ? q : (part == 1 ? k : g)) + r * 64 + col0;
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) {
+          uint4 o;
+          o.x = pack_half2(v[j], v[j + 1]);
+          o.y = pack_half2(v[j + 2], v[j + 3]);
+          o.z = pack_half2(v[j + 4], v[j + 5]);
+          o.w = pack_half2(v[j + 6], v[j + 7]);
+          *reinterpret_cast<uint4*>(dst + j) = o;
+        }
+      }
+    }
+    tc_fence_before();
+    __syncthreads();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, NOUT);
+}
+
+int triattn_proj(const PairDims& d, const float* pair, int mode, const __half* w_qkvg, const float* b_gate, __half* q,
+                 __half* k, __half* g, __half* vt, cudaStream_t s) {
+  const long long R = (long long)d.B * d.N * d.N;
+  const long long tiles = (R + kTileRows - 1) / kTileRows;
+  RowMap map{d.N, (long long)d.N * d.N, mode};
+  const int Np = plane_ld(d.N);
+  if (d.CZ == 64) {
+    constexpr int CZ = 64;
+    constexpr int smem = 1024 + 16384 + 256 * 128 + 2 * RowStage<CZ>::kBytes + 64 * 4 + 64;
+    auto kern = triattn_proj_kernel<CZ>;
+    if (set_smem(kern, smem)) return 1;
+    kern<<<grid_for(tiles, 2), 128, smem, s>>>(pair, map, R, w_qkvg, b_gate, q, k, g, vt, Np);
+  } else if (d.CZ == 32) {
+    constexpr int CZ = 32;
+    constexpr int smem = 1024 + 16384 + 256 * 128 + 2 * RowStage<CZ>::kBytes + 64 * 4 + 64;
+    auto kern = triattn_proj_kernel<CZ>;
+    if (set_smem(kern, smem)) return 1;
+    kern<<<grid_for(tiles, 2), 128, smem, s>>>(pair, map, R, w_qkvg, b_gate, q, k, g, vt, Np);
+  } else {
+    set_error("triattn_proj: unsupported pair_dim %d", d.CZ);
+    return 1;
+  }
+  PRD_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// =========================================================================================
+// Triangle attention output projection + residual: pair[src(b,seq,tok)] += Wo og[(b,seq,tok)] + bo
+// og: [rows][64] fp16 gated attention output (logical row order).
+// =========================================================================================
+template <int CZ>
+__global__ void __launch_bounds__(128, 1)
+triattn_out_kernel(const float* pair, float* dst, int residual, RowMap map, long long R, const __half* __restrict__ og,
+                   const __half* __restrict__ w_o, const float* __restrict__ b_o) {
+  extern __shared__ uint8_t raw[];
+  uint8_t* sm = smem_align1024(raw);
+  uint8_t* sA = sm;
+  uint8_t* sW = sA + 16384;
+  uint8_t* sSt = sW + CZ * 128;
+  float* sB = reinterpret_cast<float*>(sSt + 2 * RowStage<CZ>::kBytes);
+  uint64_t* full = reinterpret_cast<uint64_t*>(sB + CZ);
+  uint64_t* mma_bar = full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mma_bar + 1);
+  constexpr int TCOLS = CZ < 32 ? 32 : CZ;
+
+  const int t = threadIdx.x, warp = t >> 5;
+  if (t == 0) {
+    mbar_init(&full[0], kTileRows);
+    mbar_init(&full[1], kTileRows);
+    mbar_init(mma_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc(tmem_slot, TCOLS);
+  load_weight_kblocks(sW, w_o, CZ, 64, 64, t, 128);
+  for (int i = t; i < CZ; i += 128) sB[i] = b_o[i];
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t tm_lane = tmem + (static_cast<uint32_t>(warp * 32) << 16);
+
+  const long long num_tiles = (R + kTileRows - 1) / kTileRows;
+  uint32_t mma_phase = 0;
+  long long tile = blockIdx.x;
+  auto src_of = [&](long long r) -> long long {
+    int b = 0, s = 0, tk = 0;
+    if (r < R) map.decompose(r, b, s, tk);
+    return map.src_row(b, s, tk);
+  };
+  if (tile < num_tiles) {
+    const long long r = tile * kTileRows + t;
+    issue_row_load<CZ>(sSt, t, pair + src_of(r) * CZ, r < R, &full[0]);
+  }
+  for (int it = 0; tile < num_tiles; tile += gridDim.x, ++it) {
+    const int buf = it & 1;
+    uint8_t* st = sSt + buf * RowStage<CZ>::kBytes;
+    const long long next = tile + gridDim.x;
+    if (next < num_tiles) {
+      bulk_wait_read0();
+      const long long rn = next * kTileRows + t;
+      issue_row_load<CZ>(sSt + (buf ^ 1) * RowStage<CZ>::kBytes, t, pair + src_of(rn) * CZ, rn < R, &full[buf ^ 1]);
+    }
+    const long long r = tile * kTileRows + t;
+    const bool valid = r < R;
+    const long long src = src_of(r);
+    float* my = stage_row<CZ>(st, t);
+    {
+      const uint4* op = reinterpret_cast<const uint4*>(og + r * 64);
+#pragma unroll
+      for (int ch = 0; ch < 8; ++ch) {
+        const uint4 v = valid ? __ldg(op + ch) : make_uint4(0, 0, 0, 0);
+        *reinterpret_cast<uint4*>(sA + sw128_offset(t, ch)) = v;
+      }
+    }
+    sync_before_mma();
+    if (t == 0) {
+      tc_fence_after();
+      umma_multi(tmem, smem_u32(sA), smem_u32(sW), 1, CZ * 128, umma_idesc_f16(128, CZ), false);
+      umma_commit(mma_bar);
+    }
+    mbar_wait(&full[buf], (it >> 1) & 1);
+    mbar_wait(mma_bar, mma_phase);
+    mma_phase ^= 1;
+    tc_fence_after();
+#pragma unroll
+    for (int c = 0; c < CZ / 32; ++c) {
+      uint32_t acc[32];
+      tmem_ld32(tm_lane + c * 32, acc);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        float4 x = *reinterpret_cast<float4*>(my + c * 32 + j);
+        if (!residual) x = make_float4(0.f, 0.f, 0.f, 0.f);
+        x.x += __uint_as_float(acc[j + 0]) + sB[c * 32 + j + 0];
+        x.y += __uint_as_float(acc[j + 1]) + sB[c * 32 + j + 1];
+        x.z += __uint_as_float(acc[j + 2]) + sB[c * 32 + j + 2];
+        x.w += __uint_as_float(acc[j + 3]) + sB[c * 32 + j + 3];
+        *reinterpret_cast<float4*>(my + c * 32 + j) = x;
+      }
+    }
+    fence_proxy_async_smem();
+    if (valid) bulk_s2g(dst + src * CZ, my, CZ * 4);
+    bulk_commit();
+    tc_fence_before();
+    __syncthreads();
+  }
+  bulk_wait0();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, TCOLS);
+}
+
+int triattn_out(const PairDims& d, const float* pair, float* dst, int residual, int mode, const __half* og,
+                const __half* w_o, const float* b_o, cudaStream_t s) {
+  const long long R = (long long)d.B * d.N * d.N;
+  const long long tiles = (R + kTileRows - 1) / kTileRows;
+  RowMap map{d.N, (long long)d.N * d.N, mode};
+  if (d.CZ == 64) {
+    constexpr int CZ = 64;
+    constexpr int smem = 1024 + 16384 + CZ * 128 + 2 * RowStage<CZ>::kBytes + CZ * 4 + 64;
+    auto kern = triattn_out_kernel<CZ>;
+    if (set_smem(kern, smem)) return 1;
+    kern<<<grid_for(tiles, 2), 128, smem, s>>>(pair, dst, residual, map, R, og, w_o, b_o);
+  } else if (d.CZ == 32) {
+    constexpr int CZ = 32;
+    constexpr int smem = 1024 + 16384 + CZ * 128 + 2 * RowStage<CZ>::kBytes + CZ * 4 + 64;
+    auto kern = triattn_out_kernel<CZ>;
+    if (set_smem(kern, smem)) return 1;
+    kern<<<grid_for(tiles, 2), 128, smem, s>>>(pair, dst, residual, map, R, og, w_o, b_o);
+  } else {
+    set_error("triattn_out: unsupported pair_dim %d", d.CZ);
+    return 1;
+  }
+  PRD_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace prd

@@ -1,0 +1,157 @@
+// Shared device helpers for the "pair-row tile" kernels.
+//
+// Execution model (all kernels in prd_rowtile.cu / prd_pairembed.cu / prd_coord.cu):
+//   * a tile = 128 pair elements ("rows"), one thread per row, thread t <-> TMEM lane t;
+//   * each thread bulk-copies its own row (C_Z fp32) global -> shared into a padded staging
+//     slot (row stride C_Z*4+16 bytes, so same-column reads by the 32 lanes hit 8 distinct
+//     16-byte bank groups: conflict free with static register indices);
+//   * LayerNorm runs thread-locally in registers, the fp16 result is written as a K-major
+//     SWIZZLE_128B UMMA A-operand tile; weights sit in shared memory as B operands;
+//   * thread 0 issues tcgen05.mma, all threads read their accumulator row back from TMEM.
+#pragma once
+#include "prd_common.cuh"
+
+namespace prd {
+
+constexpr int kTileRows = 128;
+constexpr float kLnEps = 1e-5f;
+
+template <int CZ>
+struct RowStage {
+  static constexpr int kRowBytes = CZ * 4 + 16;
+  static constexpr int kBytes = kTileRows * kRowBytes;
+};
+
+// Row r of a staging buffer.
+template <int CZ>
+__device__ __forceinline__ float* stage_row(uint8_t* stage, int t) {
+  return reinterpret_cast<float*>(stage + t * RowStage<CZ>::kRowBytes);
+}
+
+// Thread-private async row load: arrive on `bar` (count = 128) expecting CZ*4 bytes, or a plain
+// arrive for rows past the end of the problem.
+template <int CZ>
+__device__ __forceinline__ void issue_row_load(uint8_t* stage, int t, const float* gsrc, bool valid, uint64_t* bar) {
+  if (valid) {
+    mbar_expect_tx(bar, CZ * 4);
+    bulk_g2s(stage_row<CZ>(stage, t), gsrc, CZ * 4, bar);
+  } else {
+    mbar_arrive(bar);
+  }
+}
+
+template <int CZ>
+__device__ __forceinline__ void read_row(const float* row, float (&x)[CZ]) {
+#pragma unroll
+  for (int c = 0; c < CZ / 4; ++c) {
+    const float4 v = *reinterpret_cast<const float4*>(row + c * 4);
+    x[c * 4 + 0] = v.x;
+    x[c * 4 + 1] = v.y;
+    x[c * 4 + 2] = v.z;
+    x[c * 4 + 3] = v.w;
+  }
+}
+
+template <int CZ>
+__device__ __forceinline__ void write_row(float* row, const float (&x)[CZ]) {
+#pragma unroll
+  for (int c = 0; c < CZ / 4; ++c)
+    *reinterpret_cast<float4*>(row + c * 4) = make_float4(x[c * 4], x[c * 4 + 1], x[c * 4 + 2], x[c * 4 + 3]);
+}
+
+// In-place LayerNorm without affine (nn.LayerNorm(elementwise_affine=False), eps 1e-5).
+template <int CZ>
+__device__ __forceinline__ void layernorm_inplace(float (&x)[CZ]) {
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < CZ; ++i) s += x[i];
+  const float mean = s * (1.0f / CZ);
+  float v = 0.f;
+#pragma unroll
+  for (int i = 0; i < CZ; ++i) {
+    const float d = x[i] - mean;
+    v += d * d;
+  }
+  const float rstd = rsqrtf(v * (1.0f / CZ) + kLnEps);
+#pragma unroll
+  for (int i = 0; i < CZ; ++i) x[i] = (x[i] - mean) * rstd;
+}
+
+// Write one row (CZ <= 64 values, zero padded to 64) of a [128 x 64] fp16 K-block.
+template <int CZ>
+__device__ __forceinline__ void store_a_row(uint8_t* a_tile, int t, const float (&y)[CZ]) {
+#pragma unroll
+  for (int ch = 0; ch < 8; ++ch) {
+    uint4 o = make_uint4(0, 0, 0, 0);
+    if (ch * 8 < CZ) {
+      o.x = pack_half2(y[ch * 8 + 0], y[ch * 8 + 1]);
+      o.y = pack_half2(y[ch * 8 + 2], y[ch * 8 + 3]);
+      o.z = pack_half2(y[ch * 8 + 4], y[ch * 8 + 5]);
+      o.w = pack_half2(y[ch * 8 + 6], y[ch * 8 + 7]);
+    }
+    *reinterpret_cast<uint4*>(a_tile + sw128_offset(t, ch)) = o;
+  }
+}
+
+// Write 32 consecutive K-values (columns k0 .. k0+31, k0 a multiple of 32) of row t into a
+// multi-K-block A operand whose K-blocks ([128 x 64] halves, 16 KB) are stored back to back.
+__device__ __forceinline__ void store_a_cols32(uint8_t* a_tiles, int t, int k0, const float (&v)[32]) {
+  uint8_t* blk = a_tiles + (k0 >> 6) * (kTileRows * 128);
+  const int ch0 = (k0 & 63) >> 3;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    uint4 o;
+    o.x = pack_half2(v[c * 8 + 0], v[c * 8 + 1]);
+    o.y = pack_half2(v[c * 8 + 2], v[c * 8 + 3]);
+    o.z = pack_half2(v[c * 8 + 4], v[c * 8 + 5]);
+    o.w = pack_half2(v[c * 8 + 6], v[c * 8 + 7]);
+    *reinterpret_cast<uint4*>(blk + sw128_offset(t, ch0 + c)) = o;
+  }
+}
+
+// Cooperative copy of a row-major fp16 weight W[rows][K] (leading dim ld halves) into K-major
+// SWIZZLE_128B B-operand K-blocks: block kb holds columns [64 kb, 64 kb + 64) of all rows,
+// zero padded past K.  Block size = rows * 128 bytes (rows must be a multiple of 8).
+__device__ __forceinline__ void load_weight_kblocks(uint8_t* dst, const __half* W, int rows, int K, int ld, int tid,
+                                                    int nthreads) {
+  const int kblocks = (K + 63) >> 6;
+  const int total = kblocks * rows * 8;
+  for (int idx = tid; idx < total; idx += nthreads) {
+    const int ch = idx & 7;
+    const int r = (idx >> 3) % rows;
+    const int kb = (idx >> 3) / rows;
+    const int col = kb * 64 + ch * 8;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (col + 8 <= K) {
+      v = *reinterpret_cast<const uint4*>(W + (long long)r * ld + col);
+    } else if (col < K) {
+      __half tmp[8];
+      for (int e = 0; e < 8; ++e) tmp[e] = (col + e < K) ? W[(long long)r * ld + col + e] : __float2half(0.f);
+      v = *reinterpret_cast<uint4*>(tmp);
+    }
+    *reinterpret_cast<uint4*>(dst + kb * rows * 128 + sw128_offset(r, ch)) = v;
+  }
+}
+
+// Issue UMMAs over `kblocks` K-blocks: A K-blocks are [128 x 64] (16 KB apart), B K-blocks are
+// [n_rows x 64] (n_rows*128 bytes apart).  Called by one thread.
+__device__ __forceinline__ void umma_multi(uint32_t tmem_d, uint32_t a_smem, uint32_t b_smem, int kblocks,
+                                           uint32_t b_block_bytes, uint32_t idesc, bool accumulate) {
+  for (int kb = 0; kb < kblocks; ++kb)
+    umma_kblock(tmem_d, a_smem + kb * (kTileRows * 128), b_smem + kb * b_block_bytes, idesc, accumulate || kb > 0);
+}
+
+// smem carve-up helper: returns a 1024-byte aligned base inside the dynamic smem window.
+__device__ __forceinline__ uint8_t* smem_align1024(uint8_t* raw) {
+  const uint32_t a = smem_u32(raw);
+  return raw + (((a + 1023u) & ~1023u) - a);
+}
+
+// All threads: make generic-proxy smem writes visible to the tensor core, then sync the CTA.
+__device__ __forceinline__ void sync_before_mma() {
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+}
+
+}  // namespace prd

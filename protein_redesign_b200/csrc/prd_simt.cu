@@ -1,0 +1,402 @@
+// Bandwidth- and latency-bound kernels (no tensor cores): LayerNorm of single-representation rows,
+// the pair-bias projection stream (LN + c_z -> H), row softmax, the small-head single attention,
+// symmetrise, remove_mean, embeddings and the sampler update.
+#include "prd_kernels.h"
+#include "prd_common.cuh"
+
+namespace prd {
+
+// -----------------------------------------------------------------------------------------
+// LayerNorm over the last dim of [rows, C] fp32 (warp per row), optional affine; writes fp16
+// (GEMM A operand) and/or fp32.  nn.LayerNorm semantics, eps 1e-5.
+// -----------------------------------------------------------------------------------------
+__global__ void layernorm_rows_kernel(const float* __restrict__ x, int rows, int C, const float* __restrict__ gamma,
+                                      const float* __restrict__ beta, __half* __restrict__ out16,
+                                      float* __restrict__ out32) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= rows) return;
+  const float* xr = x + (long long)warp * C;
+  float s = 0.f;
+  for (int c = lane; c < C; c += 32) s += xr[c];
+  const float mean = warp_sum(s) / C;
+  float v = 0.f;
+  for (int c = lane; c < C; c += 32) {
+    const float d = xr[c] - mean;
+    v += d * d;
+  }
+  const float rstd = rsqrtf(warp_sum(v) / C + 1e-5f);
+  for (int c = lane; c < C; c += 32) {
+    float y = (xr[c] - mean) * rstd;
+    if (gamma) y = y * gamma[c] + beta[c];
+    if (out16) out16[(long long)warp * C + c] = __float2half_rn(y);
+    if (out32) out32[(long long)warp * C + c] = y;
+  }
+}
+
+int layernorm_rows(const float* x, int rows, int C, const float* gamma, const float* beta, __half* out16, float* out32,
+                   cudaStream_t s) {
+  const int threads = 256;
+  const int blocks = (rows * 32 + threads - 1) / threads;
+  layernorm_rows_kernel<<<blocks, threads, 0, s>>>(x, rows, C, gamma, beta, out16, out32);
+  PRD_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// -----------------------------------------------------------------------------------------
+// Pair-bias projection stream: bias[b,h,i,j] = LN(pair[b,i,j,:]) . w[h,:] (+ bvec[h]).
+// HBM-bound: reads the pair tensor once (16-byte loads, L1 no-allocate), writes 4/c_z of it.
+// CZ/4 lanes cooperate on one pair element; a warp covers 32 consecutive elements per pass so
+// the four head planes are written with full 128-byte lines.
+// -----------------------------------------------------------------------------------------
+__device__ __forceinline__ float4 ldg_stream(const float4* p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "l"(p));
+  return r;
+}
+
+template <int CZ>
+__global__ void __launch_bounds__(256)
+pair_bias_kernel(const float* __restrict__ pair, long long R, long long NN, const float* __restrict__ ln_w,
+                 const float* __restrict__ ln_b, const float* __restrict__ w, const float* __restrict__ bvec,
+                 float* __restrict__ out) {
+  constexpr int LPE = CZ / 4;     // lanes per element
+  constexpr int EPW = 32 / LPE;   // elements per warp-wide load
+  constexpr int ITER = 32 / EPW;  // loads per 32-element pass
+  const int lane = threadIdx.x & 31;
+  const int sub = lane % LPE, grp = lane / LPE;
+  // per-lane slice of the affine LN and of the 4 head weight rows (channels 4*sub .. 4*sub+3)
+  float4 gam = make_float4(1.f, 1.f, 1.f, 1.f), bet = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (ln_w) {
+    gam = reinterpret_cast<const float4*>(ln_w)[sub];
+    bet = reinterpret_cast<const float4*>(ln_b)[sub];
+  }
+  float4 wh[4];
+#pragma unroll
+  for (int h = 0; h < 4; ++h) wh[h] = reinterpret_cast<const float4*>(w + h * CZ)[sub];
+  float bh[4];
+#pragma unroll
+  for (int h = 0; h < 4; ++h) bh[h] = bvec ? bvec[h] : 0.f;
+
+  const long long warp_global = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const long long npass = (R + 31) / 32;
+  for (long long pass = warp_global; pass < npass; pass += nwarps) {
+    const long long e0 = pass * 32;
+    float4 v[ITER];
+#pragma unroll
+    for (int it = 0; it < ITER; ++it) {
+      const long long e = e0 + it * EPW + grp;
+      v[it] = (e < R) ? ldg_stream(reinterpret_cast<const float4*>(pair + e * CZ) + sub) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    float keep[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int it = 0; it < ITER; ++it) {
+      float s = v[it].x + v[it].y + v[it].z + v[it].w;
+#pragma unroll
+      for (int o = LPE / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      const float mean = s * (1.0f / CZ);
+      const float d0 = v[it].x - mean, d1 = v[it].y - mean, d2 = v[it].z - mean, d3 = v[it].w - mean;
+      float q = d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
+#pragma unroll
+      for (int o = LPE / 2; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+      const float rstd = rsqrtf(q * (1.0f / CZ) + 1e-5f);
+      const float y0 = d0 * rstd * gam.x + bet.x, y1 = d1 * rstd * gam.y + bet.y;
+      const float y2 = d2 * rstd * gam.z + bet.z, y3 = d3 * rstd * gam.w + bet.w;
+#pragma unroll
+      for (int h = 0; h < 4; ++h) {
+        float p = y0 * wh[h].x + y1 * wh[h].y + y2 * wh[h].z + y3 * wh[h].w;
+#pragma unroll
+        for (int o = LPE / 2; o > 0; o >>= 1) p += __shfl_xor_sync(0xffffffffu, p, o);
+        // element (it*EPW + g) of this pass is delivered to lane (it*EPW + g)
+#pragma unroll
+        for (int g = 0; g < EPW; ++g) {
+          const float pv = __shfl_sync(0xffffffffu, p, g * LPE);
+          if (lane == it * EPW + g) keep[h] = pv + bh[h];
+        }
+      }
+    }
+    const long long e = e0 + lane;
+    if (e < R) {
+      const long long b = e / NN;
+      const long long ij = e - b * NN;
+#pragma unroll
+      for (int h = 0; h < 4; ++h) out[(b * 4 + h) * NN + ij] = keep[h];
+    }
+  }
+}
+
+int pair_bias_proj(const PairDims& d, int H, const float* pair, const float* ln_w, const float* ln_b, const float* w,
+                   const float* bvec, float* bias_out, cudaStream_t s) {
+  PRD_REQUIRE(H == 4, "pair_bias_proj: num_heads %d unsupported (built for 4)", H);
+  const long long NN = (long long)d.N * d.N, R = NN * d.B;
+  const int blocks = kNumSMs * 8;
+  if (d.CZ == 64) pair_bias_kernel<64><<<blocks, 256, 0, s>>>(pair, R, NN, ln_w, ln_b, w, bvec, bias_out);
+  else if (d.CZ == 32) pair_bias_kernel<32><<<blocks, 256, 0, s>>>(pair, R, NN, ln_w, ln_b, w, bvec, bias_out);
+  else {
+    set_error("pair_bias_proj: unsupported pair_dim %d", d.CZ);
+    return 1;
+  }
+  PRD_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// -----------------------------------------------------------------------------------------
+// Row softmax: logits fp32 [rows, n] -> probs fp16 [rows, n (ld_out)], pad columns zeroed.
+// -----------------------------------------------------------------------------------------
+__global__ void softmax_rows_kernel(const float* __restrict__ logits, __half* __restrict__ probs, long long rows, int n,
+                                    int ld_in, int ld_out) {
+  const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float* x = logits + row * ld_in;
+  float m = -INFINITY;
+  for (int c = lane; c < n; c += 32) m = fmaxf(m, x[c]);
+  m = warp_max(m);
+  float s = 0.f;
+  for (int c = lane; c < n; c += 32) s += __expf(x[c] - m);
+  s = warp_sum(s);
+  const float inv = 1.0f / s;
+  __half* p = probs + row * ld_out;
+  for (int c = lane; c < ld_out; c += 32) p[c] = __float2half_rn(c < n ? __expf(x[c] - m) * inv : 0.f);
+}
+
+int softmax_rows(float* logits, __half* probs, long long rows, int n, int ld_in, int ld_out, cudaStream_t s) {
+  const int threads = 256;
+  const long long blocks = (rows * 32 + threads - 1) / threads;
+  softmax_rows_kernel<<<(unsigned)blocks, threads, 0, s>>>(logits, probs, rows, n, ld_in, ld_out);
+  PRD_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// -----------------------------------------------------------------------------------------
+// FoldingBlock.single_attn core (modules.py:185-225 with attn_bias): head_dim 16, 4 heads.
+// CTA = (128 queries, h, b); K/V of (b,h) in shared memory; bias tile staged through shared
+// memory so the [B,H,N,N] bias is read with coalesced lines.
+// -----------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+single_attention_kernel(int N, int H, const float* __restrict__ qkvg, const float* __restrict__ bias,
+                        const float* __restrict__ mask, __half* __restrict__ og) {
+  extern __shared__ float sm[];
+  constexpr int C = 16;
+  float* sK = sm;               // [N][16]
+  float* sV = sK + (size_t)N * C;
+  float* sMask = sV + (size_t)N * C;  // [N]
+  float* sBias = sMask + N;           // [128][33]
+  const int t = threadIdx.x;
+  const int h = blockIdx.y, b = blockIdx.z;
+  const int i = blockIdx.x * 128 + t;
+  const int ld = 4 * H * C;
+  for (int idx = t; idx < N * C; idx += 128) {
+    const int j = idx / C, c = idx % C;
+    const float* row = qkvg + ((long long)b * N + j) * ld;
+    sK[idx] = row[H * C + h * C + c];
+    sV[idx] = row[2 * H * C + h * C + c];
+  }
+  for (int j = t; j < N; j += 128) sMask[j] = mask[(long long)b * N + j];
+  float q[C];
+  float gate[C];
+  if (i < N) {
+    const float* row = qkvg + ((long long)b * N + i) * ld;
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      q[c] = 0.25f * row[h * C + c];
+      gate[c] = 1.0f / (1.0f + __expf(-row[3 * H * C + h * C + c]));
+    }
+  } else {
+#pragma unroll
+    for (int c = 0; c < C; ++c) q[c] = gate[c] = 0.f;
+  }
+  float m = -INFINITY, l = 0.f, o[C];
+#pragma unroll
+  for (int c = 0; c < C; ++c) o[c] = 0.f;
+  const float* bias_bh = bias + ((long long)b * H + h) * N * N;
+  const int warp = t >> 5, lane = t & 31;
+  for (int j0 = 0; j0 < N; j0 += 32) {
+    __syncthreads();
+    // stage bias[i0 .. i0+127][j0 .. j0+31]: warp w loads rows w, w+4, ...; lanes along j
+    for (int r = warp; r < 128; r += 4) {
+      const int ii = blockIdx.x * 128 + r;
+      const int jj = j0 + lane;
+      sBias[r * 33 + lane] = (ii < N && jj < N) ? bias_bh[(long long)ii * N + jj] : 0.f;
+    }
+    __syncthreads();
+    const int jn = min(32, N - j0);
+    for (int jj = 0; jj < jn; ++jj) {
+      const int j = j0 + jj;
+      const float* kr = sK + j * C;
+      float s = 0.f;
+#pragma unroll
+      for (int c = 0; c < C; ++c) s += q[c] * kr[c];
+      s += sBias[t * 33 + jj];
+      if (sMask[j] < 0.5f) s = -32768.0f;
+      const float mn = fmaxf(m, s);
+      const float a = __expf(m - mn), p = __expf(s - mn);
+      l = l * a + p;
+      const float* vr = sV + j * C;
+#pragma unroll
+      for (int c = 0; c < C; ++c) o[c] = o[c] * a + p * vr[c];
+      m = mn;
+    }
+  }
+  if (i < N) {
+    const float inv = 1.0f / l;
+    __half* dst = og + ((long long)b * N + i) * (H * C) + h * C;
+#pragma unroll
+    for (int c = 0; c < C; ++c) dst[c] = __float2half_rn(gate[c] * o[c] * inv);
+  }
+}
+
+int single_attention(int B, int N, int H, int c, const float* qkvg, const float* bias, const float* mask, __half* og,
+                     cudaStream_t s) {
+  PRD_REQUIRE(c == 16, "single_attention: head_dim %d unsupported (built for 16)", c);
+  const int smem = (2 * N * 16 + N + 128 * 33) * 4;
+  PRD_REQUIRE(smem <= 227 * 1024, "single_attention: N=%d needs %d B of shared memory", N, smem);
+  PRD_CUDA_OK(cudaFuncSetAttribute(single_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  dim3 grid((N + 127) / 128, H, B);
+  single_attention_kernel<<<grid, 128, smem, s>>>(N, H, qkvg, bias, mask, og);
+  PRD_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// -----------------------------------------------------------------------------------------
+// pair <- 0.5 (pair + pair^T)   (modules.py:403), in place; one thread per float4 of an (i<j) pair
+// -----------------------------------------------------------------------------------------
+__global__ void symmetrize_kernel(float* __restrict__ pair, int N, int CZ4, long long total) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int c = static_cast<int>(idx % CZ4);
+  const long long e = idx / CZ4;
+  const int j = static_cast<int>(e % N);
+  const long long bi = e / N;
+  const int i = static_cast<int>(bi % N);
+  if (j <= i) return;
+  const long long b = bi / N;
+  float4* pij = reinterpret_cast<float4*>(pair) + ((b * N + i) * N + j) * CZ4 + c;
+  float4* pji = reinterpret_cast<float4*>(pair) + ((b * N + j) * N + i) * CZ4 + c;
+  const float4 a = *pij, d = *pji;
+  const float4 r = make_float4(0.5f * (a.x + d.x), 0.5f * (a.y + d.y), 0.5f * (a.z + d.z), 0.5f * (a.w + d.w));
+  *pij = r;
+  *pji = r;
+}
+
+int symmetrize_pair(const PairDims& d, float* pair, cudaStream_t s) {
+  const int CZ4 = d.CZ / 4;
+  const long long total = (long long)d.B * d.N * d.N * CZ4;
+  symmetrize_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(pair, d.N, CZ4, total);
+  PRD_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// -----------------------------------------------------------------------------------------
+// remove_mean (utils.py:32-36): x[b,i,:] -= mask[b,i] * sum_i(mask*x) / sum_i(mask); one CTA per b
+// -----------------------------------------------------------------------------------------
+__global__ void remove_mean_kernel(int N, int C, float* __restrict__ x, const float* __restrict__ mask, int mask_rows) {
+  __shared__ float sSum[32];
+  __shared__ float sCnt;
+  const int b = blockIdx.x, t = threadIdx.x;
+  float* xb = x + (long long)b * N * C;
+  const float* mb = mask + (long long)(b % mask_rows) * N;
+  if (t < 32) sSum[t] = 0.f;
+  if (t == 0) sCnt = 0.f;
+  __syncthreads();
+  // one warp per channel keeps the summation order fixed (deterministic)
+  const int warp = t >> 5, lane = t & 31, nwarps = blockDim.x >> 5;
+  for (int c = warp; c < C; c += nwarps) {
+    float s = 0.f;
+    for (int i = lane; i < N; i += 32) s += mb[i] * xb[(long long)i * C + c];
+    s = warp_sum(s);
+    if (lane == 0) sSum[c] = s;
+  }
+  if (warp == 0) {
+    float n = 0.f;
+    for (int i = lane; i < N; i += 32) n += mb[i];
+    n = warp_sum(n);
+    if (lane == 0) sCnt = n;
+  }
+  __syncthreads();
+  for (int idx = t; idx < N * C; idx += blockDim.x) {
+    const int i = idx / C, c = idx % C;
+    xb[idx] -= mb[i] * sSum[c] / sCnt;
+  }
+}
+
+int remove_mean3(int B, int N, int C, float* x, const float* mask, int mask_rows, cudaStream_t s) {
+  PRD_REQUIRE(C >= 1 && C <= 32, "remove_mean: channel count %d not in [1,32]", C);
+  PRD_REQUIRE(mask_rows >= 1, "remove_mean: mask_rows %d", mask_rows);
+  remove_mean_kernel<<<B, 256, 0, s>>>(N, C, x, mask, mask_rows);
+  PRD_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// -----------------------------------------------------------------------------------------
+// Step-invariant pair embedding (model.py:348-358): bond features / bond distance / relative
+// position gathers.  One thread per float4 of channels.
+// -----------------------------------------------------------------------------------------
+struct BondTables {
+  const float* t[3];
+};
+
+__global__ void embed_pair_static_kernel(int N, int CZ4, long long total, const float* __restrict__ atom_mask,
+                                         const float* __restrict__ residue_mask, const float* __restrict__ bond_mask,
+                                         const int64_t* __restrict__ bond_feats, const int64_t* __restrict__ bond_distance,
+                                         const int64_t* __restrict__ residue_index, const int64_t* __restrict__ chain_index,
+                                         BondTables bt, const float* __restrict__ bdist_table, int max_bd,
+                                         const float* __restrict__ relpos_table, int max_rel, float* __restrict__ out) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int c = static_cast<int>(idx % CZ4);
+  const long long e = idx / CZ4;
+  const int j = static_cast<int>(e % N);
+  const long long bi = e / N;
+  const int i = static_cast<int>(bi % N);
+  const long long b = bi / N;
+  const float am2 = atom_mask[b * N + i] * atom_mask[b * N + j];
+  const float rm2 = residue_mask[b * N + i] * residue_mask[b * N + j];
+  auto row4 = [&](const float* table, long long r) { return reinterpret_cast<const float4*>(table)[r * CZ4 + c]; };
+  const float scale = 0.57735026918962584f;  // 1/sqrt(3) bond features (modules.py:63)
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  {
+    float4 bond = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int f = 0; f < 3; ++f) {
+      const float4 v = row4(bt.t[f], bond_feats[e * 3 + f]);
+      bond.x += scale * v.x; bond.y += scale * v.y; bond.z += scale * v.z; bond.w += scale * v.w;
+    }
+    const float bm = bond_mask[e];
+    long long bd = bond_distance[e];
+    if (bd > max_bd) bd = max_bd;
+    const float4 dv = row4(bdist_table, bd);
+    acc.x = am2 * (bm * bond.x + dv.x); acc.y = am2 * (bm * bond.y + dv.y);
+    acc.z = am2 * (bm * bond.z + dv.z); acc.w = am2 * (bm * bond.w + dv.w);
+  }
+  {
+    long long rel = residue_index[b * N + i] - residue_index[b * N + j];
+    if (rel < -max_rel) rel = -max_rel;
+    if (rel > max_rel) rel = max_rel;
+    const float same = (chain_index[b * N + i] == chain_index[b * N + j]) ? 1.f : 0.f;
+    const float4 rv = row4(relpos_table, max_rel + rel);
+    acc.x += rm2 * (same * rv.x); acc.y += rm2 * (same * rv.y);
+    acc.z += rm2 * (same * rv.z); acc.w += rm2 * (same * rv.w);
+  }
+  reinterpret_cast<float4*>(out)[idx] = acc;
+}
+
+int embed_pair_static(const PairDims& d, const float* atom_mask, const float* residue_mask, const float* bond_mask,
+                      const int64_t* bond_feats, const int64_t* bond_distance, const int64_t* residue_index,
+                      const int64_t* chain_index, const float* const* bond_tables, const int* bond_vocab,
+                      const float* bdist_table, int max_bond_distance, const float* relpos_table, int max_relpos,
+                      float* out, cudaStream_t s) {
+  (void)bond_vocab;
+  const int CZ4 = d.CZ / 4;
+  const long long total = (long long)d.B * d.N * d.N * CZ4;
+  BondTables bt{{bond_tables[0], bond_tables[1], bond_tables[2]}};
+  embed_pair_static_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(
+      d.N, CZ4, total, atom_mask, residue_mask, bond_mask, bond_feats, bond_distance, residue_index, chain_index, bt,
+      bdist_table, max_bond_distance, relpos_table, max_relpos, out);
+  PRD_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace prd

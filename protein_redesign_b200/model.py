@@ -1,0 +1,359 @@
+"""B200-native mirror of the reference's ``ProteinReDiff/model.py`` (ProteinReDiffModel).
+
+Same constructor argument (Namespace / Mapping), sub-module and parameter names, and the call
+signatures ``forward / sample_step (batch, z, seq_t, mask, t)``, ``sample(batch)``,
+``predict_step(batch, batch_idx)``, ``prepare_batch``, ``run_setup_schedule`` (reference
+model.py:254,318,378,249,424,172).  The network evaluation is enqueued on hand-written sm_100a
+kernels through libprd_sm100 (include/prd_denoiser.h); ``sample`` captures one reverse-diffusion
+step as a CUDA graph and replays it ``num_steps`` times with the schedule, the noise and the
+step counter resident on the device.
+
+Not in this build: the backward pass (``training_step`` raises), ESM loading, Lightning hooks.
+"""
+from __future__ import annotations
+
+import contextlib
+from argparse import ArgumentParser, Namespace
+from typing import Dict, Mapping, Optional, Union
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+from . import ops
+from ._packing import PackCache, f32, half
+from .modules import AtomEmbedding, BondEmbedding, Denoiser, Linear, RadialBasisProjection, SinusoidalProjection
+from .synthetic import NUM_RESIDUE_CLASSES, DenoiserConfig
+
+try:  # the reference derives from LightningModule; keep that when Lightning is installed
+    import pytorch_lightning as _pl
+
+    _Base = _pl.LightningModule
+except Exception:  # pragma: no cover - Lightning is absent in the build image
+    _Base = nn.Module
+
+
+# --------------------------------------------------------------------------------------------
+# host-side helpers restated from the reference (index / schedule path: bit exact)
+# --------------------------------------------------------------------------------------------
+def get_betas(n_timestep: int, schedule: str) -> torch.Tensor:
+    """reference difffusion.py:8-26."""
+    if schedule == "linear":
+        return torch.linspace(0.0001, 0.02, n_timestep)
+    if schedule == "cosine":
+        steps = n_timestep + 1
+        x = torch.linspace(0, n_timestep, steps)
+        ac = torch.cos((x / steps) * torch.pi * 0.5) ** 2
+        ac = ac / ac[0]
+        return torch.clip(1 - (ac[1:] / ac[:-1]), 0, 0.999)
+    raise ValueError(f"Invalid schedule: {schedule}")
+
+
+class RandomMaskingModule(nn.Module):
+    """reference mask_utils.py:72-112 (CPU ``torch.randperm`` over all valid residues of the batch)."""
+
+    def forward(self, residue_mask, max_p, inverse_mask=False, stochastic=True):
+        if stochastic:
+            max_p = np.random.rand() * max_p
+        ones = residue_mask == 1
+        num_ones = int(ones.sum().item())
+        rows, cols = torch.where(ones)
+        pick = torch.randperm(num_ones)[: int(num_ones * max_p)].to(rows.device)
+        self.residue_rand_mask = residue_mask.clone()
+        self.residue_rand_mask[rows[pick], cols[pick]] = 0
+        self.residue_rand_mask_esm = 1 - residue_mask.detach().clone()
+        self.residue_rand_mask_esm[rows[pick], cols[pick]] = 32
+        if inverse_mask:
+            self.residue_inv_rand_mask = torch.zeros_like(residue_mask)
+            self.residue_inv_rand_mask[rows[pick], cols[pick]] = 1
+            return self.residue_rand_mask, self.residue_inv_rand_mask, self.residue_rand_mask_esm
+        return self.residue_rand_mask, self.residue_rand_mask_esm
+
+
+class _NullEMA:
+    """Stand-in for torch_ema.ExponentialMovingAverage when that package is absent: no shadow weights."""
+
+    def __init__(self, params, decay):
+        self.decay = decay
+
+    def to(self, *a, **k):
+        return self
+
+    def update(self, *a, **k):
+        pass
+
+    def state_dict(self):
+        return {}
+
+    def load_state_dict(self, *a, **k):
+        pass
+
+    @contextlib.contextmanager
+    def average_parameters(self):
+        yield
+
+
+try:
+    from torch_ema import ExponentialMovingAverage as _EMA
+except Exception:  # pragma: no cover
+    _EMA = _NullEMA
+
+
+class ProteinReDiffModel(_Base):
+    def __init__(self, args: Union[Namespace, Mapping, DenoiserConfig]):
+        super().__init__()
+        if isinstance(args, DenoiserConfig):
+            args = args.to_namespace()
+        if isinstance(args, Mapping):
+            args = Namespace(**args)
+        self.cfg = DenoiserConfig.from_args(args)
+        self.pair_dim = args.pair_dim
+        self.single_dim = args.single_dim
+        self.dist_dim = args.dist_dim
+        self.time_dim = args.time_dim
+        self.max_bond_distance = args.max_bond_distance
+        self.max_relpos = args.max_relpos
+        self.esm_dim = args.esm_dim
+        self.setup_schedule = False
+        self.setup_esm = False
+        self.mask_prob = args.mask_prob
+        self.num_steps = args.num_steps
+        self.diffusion_schedule = args.diffusion_schedule
+        self.learning_rate = args.learning_rate
+        self.warmup_steps = args.warmup_steps
+        self.ema_decay = args.ema_decay
+        self.n_recycles = args.n_recycles
+        self.training_mode = args.training_mode
+
+        self.RandomMaskingBlock = RandomMaskingModule()
+        self.Denoiser = Denoiser(args)
+        self.embed_atom_feats = AtomEmbedding(self.single_dim)
+        self.embed_beta = nn.Sequential(SinusoidalProjection(self.time_dim),
+                                        Linear(self.time_dim, self.pair_dim, bias=False, init="normal"))
+        self.embed_residue_type = nn.Sequential(
+            nn.LayerNorm(NUM_RESIDUE_CLASSES, elementwise_affine=False),
+            Linear(NUM_RESIDUE_CLASSES, self.single_dim, bias=False, init="normal"), nn.ReLU())
+        self.embed_bond_feats = BondEmbedding(self.pair_dim)
+        self.embed_bond_distance = nn.Embedding(self.max_bond_distance + 1, self.pair_dim)
+        self.embed_residue_esm = nn.Sequential(nn.LayerNorm(self.esm_dim, elementwise_affine=False),
+                                               Linear(self.esm_dim, self.single_dim, bias=False, init="normal"))
+        self.embed_relpos = nn.Embedding(self.max_relpos * 2 + 1, self.pair_dim)
+        self.embed_dist = nn.Sequential(RadialBasisProjection(self.dist_dim),
+                                        Linear(self.dist_dim, self.pair_dim, bias=False, init="normal"))
+        self.weight_radial = nn.Sequential(nn.LayerNorm(self.pair_dim, elementwise_affine=False),
+                                           Linear(self.pair_dim, self.pair_dim, init="relu"), nn.ReLU(),
+                                           Linear(self.pair_dim, 1, bias=False, init="final"))
+        self.seq_mlp = nn.Sequential(nn.LayerNorm(self.single_dim, elementwise_affine=False),
+                                     Linear(self.single_dim, self.single_dim, init="relu"), nn.ReLU(),
+                                     Linear(self.single_dim, NUM_RESIDUE_CLASSES, bias=False, init="final"))
+        self.ema = _EMA(self.parameters(), decay=self.ema_decay)
+        if hasattr(self, "save_hyperparameters"):
+            self.save_hyperparameters(args)
+        self._pack = PackCache()
+        self._static_key = None
+        self._static = None
+
+    # ---- argparse surface (reference model.py:129-170) ---------------------------------------
+    @staticmethod
+    def add_argparse_args(parent_parser: ArgumentParser) -> ArgumentParser:
+        p = parent_parser.add_argument_group("DiffusionModel")
+        p.add_argument("--training_mode", action="store_true")
+        p.add_argument("--mask_prob", type=float, default=1.0)
+        for name, default in (("esm_dim", 1280), ("time_dim", 256), ("dist_dim", 256), ("single_dim", 512),
+                              ("pair_dim", 64), ("head_dim", 16), ("num_heads", 4), ("transition_factor", 4),
+                              ("num_blocks", 12), ("max_bond_distance", 7), ("max_relpos", 32), ("num_steps", 64),
+                              ("warmup_steps", 1000)):
+            p.add_argument(f"--{name}", type=int, default=default)
+        p.add_argument("--diffusion_schedule", type=str, default="linear")
+        p.add_argument("--learning_rate", type=float, default=4e-4)
+        p.add_argument("--ema_decay", type=float, default=0.999)
+        q = parent_parser.add_argument_group("IterativeDenoiser")
+        q.add_argument("--n_recycles", type=int, default=4)
+        return parent_parser
+
+    @property
+    def _device(self):
+        return next(self.parameters()).device
+
+    # ---- schedule (reference model.py:172-190) -----------------------------------------------
+    def run_setup_schedule(self):
+        dev = self._device
+        self.betas = get_betas(self.num_steps, self.diffusion_schedule).to(dev)
+        self.alphas = 1.0 - self.betas
+        self.alphas_cumprod = torch.cumprod(self.alphas, 0)
+        self.alphas_cumprod_prev = torch.cat([torch.ones(1, device=dev), self.alphas_cumprod[:-1]])
+        self.one_minus_alphas_cumprod = 1.0 - self.alphas_cumprod
+        self.sqrt_betas = torch.sqrt(self.betas)
+        self.sqrt_alphas = torch.sqrt(self.alphas)
+        self.sqrt_alphas_cumprod = torch.sqrt(self.alphas_cumprod)
+        self.sqrt_one_minus_alphas_cumprod = torch.sqrt(1.0 - self.alphas_cumprod)
+        # per-step coefficients read by the on-device sampler update (model.py:407-412,419)
+        self._coef = torch.stack([1.0 / self.sqrt_alphas,
+                                  (1.0 - self.alphas) / self.sqrt_one_minus_alphas_cumprod,
+                                  self.sqrt_betas], dim=1).contiguous()
+
+    # ---- packed weights -----------------------------------------------------------------------
+    def _weights(self):
+        srcs = [self.embed_residue_esm[1].weight, self.embed_residue_type[1].weight, self.embed_beta[0].weight,
+                self.embed_beta[1].weight, self.embed_dist[0].center, self.embed_dist[1].weight,
+                self.embed_bond_distance.weight, self.embed_relpos.weight, self.weight_radial[1].weight,
+                self.weight_radial[1].bias, self.weight_radial[3].weight, self.seq_mlp[1].weight,
+                self.seq_mlp[1].bias, self.seq_mlp[3].weight]
+        srcs += [e.weight for e in self.embed_atom_feats.embeddings]
+        srcs += [e.weight for e in self.embed_bond_feats.embeddings]
+
+        def build():
+            w = {
+                "esm": [half(srcs[0])],
+                "w_type": f32(srcs[1]),
+                "pair_dyn": [f32(srcs[2]), f32(srcs[3]), half(srcs[5]), f32(srcs[4])],
+                "bdist": f32(srcs[6]), "relpos": f32(srcs[7]),
+                "coord": [half(srcs[8]), f32(srcs[9]), f32(srcs[10]).reshape(-1).contiguous()],
+                "seq": [half(srcs[11]), f32(srcs[12]), half(srcs[13])],
+                "atom_tabs": [f32(t) for t in srcs[14:23]],
+                "bond_tabs": [f32(t) for t in srcs[23:26]],
+            }
+            return w
+
+        return self._pack.get(srcs, build)
+
+    # ---- batch preparation (reference model.py:424-468, inference branch) -----------------------
+    def prepare_batch(self, batch, id=None):
+        if self.training_mode:
+            raise NotImplementedError("training-mode masking needs residue_esm_tokens / ESM (SURVEY N8)")
+        atom_mask, residue_mask = batch["atom_mask"], batch["residue_mask"]
+        ca = batch["residue_atom_pos"][:, :, 1]
+        residue_type = batch["residue_type"]
+        batch["residue_one_hot"] = F.one_hot(residue_type, num_classes=NUM_RESIDUE_CLASSES) * 2.0 - 1.0
+        pos = atom_mask.unsqueeze(-1) * batch["atom_pos"] + residue_mask.unsqueeze(-1) * ca
+        keep, drop, _ = self.RandomMaskingBlock(residue_mask, self.mask_prob, inverse_mask=True, stochastic=False)
+        batch["residue_esm"] = batch["residue_esm"] * keep.unsqueeze(-1)
+        batch["residue_type_masked"] = (residue_type * keep).long()
+        batch["residue_one_hot"] = batch["residue_one_hot"] * keep.unsqueeze(-1)
+        batch["residue_extra_mask"] = keep
+        batch["residue_inv_extra_mask"] = drop
+        batch["x"] = 0.1 * pos
+        batch["residue_and_atom_mask"] = atom_mask + residue_mask
+        return batch
+
+    # ---- step-invariant embeddings, cached per batch ---------------------------------------------
+    def _static_embeddings(self, batch):
+        keys = ("residue_esm", "bond_feats", "bond_mask", "bond_distance", "residue_index", "residue_chain_index",
+                "atom_mask", "residue_mask")
+        key = tuple((batch[k].data_ptr(), batch[k]._version) for k in keys) + (id(self._weights()),)
+        if key != self._static_key:
+            w = self._weights()
+            b = {k: batch[k].contiguous() for k in keys}
+            esm_emb = ops.esm_embed(self.cfg, b["residue_esm"], w["esm"][0])
+            pair_static = ops.pair_embed_static(self.cfg, b, w["bond_tabs"], w["bdist"], w["relpos"])
+            self._static = (esm_emb, pair_static)
+            self._static_key = key
+        return self._static
+
+    def _denoise(self, batch, z, seq_t, mask, t, bufs=None, sampler_state=None, probe=None):
+        """One network evaluation (reference model.py:318-375).  `bufs` lets the sampler reuse storage."""
+        cfg, w = self.cfg, self._weights()
+        B, N = mask.shape
+        rec = probe or (lambda n, x: None)
+        esm_emb, pair_static = self._static_embeddings(batch)
+        bufs = bufs if bufs is not None else {}
+        single = ops.single_embed(cfg, batch["atom_feats"].contiguous(), batch["atom_mask"].contiguous(),
+                                  batch["residue_mask"].contiguous(), seq_t.contiguous(), esm_emb, w["atom_tabs"],
+                                  w["w_type"], out=bufs.get("single"))
+        rec("embed_single", single)
+        a, b = self.Denoiser.opm.project(cfg, single, mask, bufs.get("opm_a"), bufs.get("opm_b"))
+        _, (w_o, b_o) = self.Denoiser.opm.packed_weights()
+        pair = bufs.get("pair")
+        if pair is None:
+            pair = torch.empty(B, N, N, cfg.pair_dim, dtype=torch.float32, device=z.device)
+        ops.pair_embed(cfg, pair_static, z.contiguous(), mask, None if sampler_state is not None else t.contiguous(),
+                       a, b, w["pair_dyn"] + [w_o, b_o], pair, sampler_state=sampler_state)
+        rec("Denoiser.opm", pair)
+        single, pair = self.Denoiser.trunk_(single, pair, mask, probe=probe)
+        noise_pred = ops.coord_head(cfg, pair, z.contiguous(), mask, w["coord"], out=bufs.get("noise_pred"))
+        seq_pred = ops.seq_head(cfg, single, w["seq"], out=bufs.get("seq_pred"))
+        return noise_pred, seq_pred
+
+    def forward(self, batch, z, seq_t, mask, t):
+        if torch.is_grad_enabled() and (z.requires_grad or seq_t.requires_grad):
+            raise NotImplementedError("backward kernels are not part of this build (SURVEY §8f item 1)")
+        return self._denoise(batch, z, seq_t, mask.contiguous(), t)
+
+    def sample_step(self, batch, z, seq_t, mask, t):
+        return self._denoise(batch, z, seq_t, mask.contiguous(), t)
+
+    def predict_step(self, batch, batch_idx):
+        with self.ema.average_parameters():
+            return self.sample(batch)
+
+    def training_step(self, batch, batch_idx):
+        raise NotImplementedError("training needs backward kernels, which are not part of this build (SURVEY §8f)")
+
+    # ---- sampler (reference model.py:377-422) ------------------------------------------------
+    @torch.inference_mode()
+    def sample(self, batch, noise: Optional[Dict[str, torch.Tensor]] = None, use_cuda_graph: bool = True,
+               trace: Optional[list] = None):
+        """DDPM ancestral sampling.  `noise` may inject pre-generated draws (keys ``z_T`` [B,N,3],
+        ``seq_T`` [B,N,21], ``steps`` [T-1,B,N,3], raw N(0,1), in the reference's draw order); otherwise
+        they come from torch's CUDA generator."""
+        if not self.setup_schedule:
+            self.run_setup_schedule()
+            self.setup_schedule = True
+        batch = self.prepare_batch(batch)
+        cfg = self.cfg
+        x, mask = batch["x"], batch["residue_and_atom_mask"].contiguous()
+        residue_mask, seq = batch["residue_mask"].contiguous(), batch["residue_one_hot"]
+        keep, drop = batch["residue_extra_mask"], batch["residue_inv_extra_mask"]
+        B, N = mask.shape
+        dev, T = x.device, self.num_steps
+        ops.reserve_workspace(cfg, B, N, dev)
+
+        def draw(key, shape):
+            if noise is not None and key in noise:
+                return noise[key].to(dev, torch.float32).contiguous().clone()
+            return torch.randn(shape, device=dev, dtype=torch.float32)
+
+        z = ops.remove_mean(cfg, draw("z_T", (B, N, 3)), mask)
+        seq_noise = ops.remove_mean(cfg, draw("seq_T", (B, N, NUM_RESIDUE_CLASSES)), residue_mask)
+        seq_t = (keep.unsqueeze(-1) * seq + drop.unsqueeze(-1) * seq_noise).float().contiguous()
+        steps = draw("steps", (max(T - 1, 1), B, N, 3))
+        if T > 1:
+            ops.remove_mean(cfg, steps.view(-1, N, 3), mask)
+        state = torch.tensor([T - 1, 0], dtype=torch.int32, device=dev)
+        bufs = {
+            "single": torch.empty(B, N, cfg.single_dim, device=dev),
+            "pair": torch.empty(B, N, N, cfg.pair_dim, device=dev),
+            "opm_a": torch.empty(B, N, cfg.single_dim // 4, device=dev),
+            "opm_b": torch.empty(B, N, cfg.single_dim // 4, device=dev),
+            "noise_pred": torch.empty(B, N, 3, device=dev),
+            "seq_pred": torch.empty(B, N, NUM_RESIDUE_CLASSES, device=dev),
+        }
+        self._static_embeddings(batch)  # outside the graph: step invariant
+
+        def one_step():
+            eps, sp = self._denoise(batch, z, seq_t, mask, None, bufs=bufs, sampler_state=state)
+            ops.sampler_update(cfg, eps, sp, steps, self._coef, z, seq_t, state)
+
+        graph = None
+        done = 0
+        if use_cuda_graph and T > 2 and trace is None:
+            one_step()  # eager warm-up step (also settles lazy kernel attributes)
+            done = 1
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.stream(side):
+                with torch.cuda.graph(graph, stream=side):
+                    one_step()
+            torch.cuda.current_stream(dev).wait_stream(side)
+            # capture does not execute: state / z are still those after `done` steps
+        for _ in range(done, T):
+            if graph is not None:
+                graph.replay()
+            else:
+                one_step()
+            if trace is not None:
+                trace.append((z.clone(), bufs["seq_pred"].clone(), bufs["noise_pred"].clone()))
+        pos = 10.0 * z
+        return pos, residue_mask.unsqueeze(-1) * bufs["seq_pred"]

@@ -1,0 +1,401 @@
+"""B200-native mirror of the reference's ``ProteinReDiff/modules.py``.
+
+Same class names, constructor arguments, parameter names/shapes and forward signatures
+(Denoiser :346-404, FoldingBlock :290-343, TriangleMultiplication :246-274, TriangleAttention
+:228-243, Attention :170-225, OuterLinear :277-287, embeddings :35-97, Linear :129-167), so the
+reference's state-dicts load with ``strict=True`` and ``model.py`` / ``generate.py`` /
+``scripts/predict_batch_*.py`` can use these classes as a drop-in.  All compute is enqueued on
+hand-written sm_100a kernels through the C ABI (``include/prd_denoiser.h``); nothing falls back
+to PyTorch or the CPU.
+"""
+from __future__ import annotations
+
+import math
+from argparse import Namespace
+from typing import Mapping, Optional, Tuple
+
+import torch
+from torch import nn
+
+from . import ops
+from ._packing import PackCache, f32, half
+from .models import AF2_modules
+from .synthetic import ATOM_VOCAB, BOND_VOCAB, DenoiserConfig
+
+
+class _FusedOnly(nn.Module):
+    """Parameter holder whose arithmetic lives inside a fused kernel."""
+
+    _fused_into = ""
+
+    def forward(self, *args, **kwargs):
+        raise NotImplementedError(
+            f"{type(self).__name__} is a parameter container in the B200 build; its arithmetic is fused into "
+            f"{self._fused_into} (see protein_redesign_b200.model.ProteinReDiffModel.forward)")
+
+
+class AtomEmbedding(_FusedOnly):
+    """reference modules.py:35-51 (9 categorical tables, scale 1/sqrt(9))."""
+
+    _fused_into = "prd_single_embed_fwd"
+
+    def __init__(self, embed_dim: int):
+        super().__init__()
+        self.embeddings = nn.ModuleList([nn.Embedding(v, embed_dim) for v in ATOM_VOCAB])
+        self.num_features = len(self.embeddings)
+        self.scale = 1.0 / math.sqrt(self.num_features)
+
+
+class BondEmbedding(_FusedOnly):
+    """reference modules.py:54-70 (3 categorical tables, scale 1/sqrt(3))."""
+
+    _fused_into = "prd_pair_embed_static_fwd"
+
+    def __init__(self, embed_dim: int):
+        super().__init__()
+        self.embeddings = nn.ModuleList([nn.Embedding(v, embed_dim) for v in BOND_VOCAB])
+        self.num_features = len(self.embeddings)
+        self.scale = 1.0 / math.sqrt(self.num_features)
+
+
+class RadialBasisProjection(_FusedOnly):
+    """reference modules.py:73-82; the Gaussians are generated inside prd_pair_embed_fwd."""
+
+    _fused_into = "prd_pair_embed_fwd"
+
+    def __init__(self, embed_dim: int, min_val: float = 0.0, max_val: float = 2.0):
+        super().__init__()
+        if min_val != 0.0 or max_val != 2.0:
+            raise ValueError("the B200 RadialBasisProjection is built for the [0, 2] nm range")
+        self.scale = (embed_dim - 1) / (max_val - min_val)
+        self.center = nn.Parameter(torch.linspace(min_val, max_val, embed_dim), requires_grad=False)
+
+
+class SinusoidalProjection(_FusedOnly):
+    """reference modules.py:85-97."""
+
+    _fused_into = "prd_pair_embed_fwd"
+
+    def __init__(self, embed_dim: int):
+        super().__init__()
+        if embed_dim % 2 != 0:
+            raise ValueError(f"embed_dim must be even: {embed_dim}.")
+        self.embed_dim = embed_dim
+        self.weight = nn.Parameter(torch.logspace(-4.0, 0.0, embed_dim // 2), requires_grad=False)
+
+
+def variance_scaling_init_(weight: torch.Tensor, scale: float = 1.0, mode: str = "fan_in",
+                           distribution: str = "truncated_normal") -> None:
+    """reference modules.py:100-126."""
+    fan_out, fan_in = weight.shape
+    denom = {"fan_in": fan_in, "fan_out": fan_out, "fan_avg": (fan_in + fan_out) / 2.0}
+    if mode not in denom:
+        raise ValueError(f"Invalid mode: {mode}")
+    scale = scale / max(1.0, denom[mode])
+    if distribution == "truncated_normal":
+        nn.init.trunc_normal_(weight, 0.0, math.sqrt(scale) / 0.87962566103423978)
+    elif distribution == "normal":
+        nn.init.normal_(weight, 0.0, math.sqrt(scale))
+    elif distribution == "uniform":
+        lim = math.sqrt(3.0 * scale)
+        nn.init.uniform_(weight, -lim, lim)
+    else:
+        raise ValueError(f"Invalid distribution: {distribution}")
+
+
+class Linear(nn.Linear):
+    """reference modules.py:129-167 (named initialisers)."""
+
+    _INITS = {"default": (1.0, "fan_in", "truncated_normal"), "relu": (2.0, "fan_in", "truncated_normal"),
+              "glorot": (1.0, "fan_avg", "uniform"), "normal": (1.0, "fan_in", "normal")}
+
+    def __init__(self, in_features: int, out_features: int, bias: bool = True, init: str = "default", init_fn=None):
+        super().__init__(in_features, out_features, bias=bias)
+        if init_fn is not None:
+            init_fn(self.weight, self.bias)
+        elif init in self._INITS:
+            variance_scaling_init_(self.weight, *self._INITS[init])
+            if bias:
+                nn.init.zeros_(self.bias)
+        elif init == "gating":
+            nn.init.zeros_(self.weight)
+            if bias:
+                nn.init.ones_(self.bias)
+        elif init == "final":
+            nn.init.zeros_(self.weight)
+            if bias:
+                nn.init.zeros_(self.bias)
+        else:
+            raise ValueError(f"Invalid init: {init}")
+
+
+def _mask_from_2d(mask_2d: torch.Tensor) -> torch.Tensor:
+    """The reference builds mask_2d = mask (x) mask from a 0/1 token mask (modules.py:334,393); the
+    kernels take the token mask, recovered here as the diagonal."""
+    return torch.diagonal(mask_2d, dim1=-2, dim2=-1).contiguous()
+
+
+class Attention(nn.Module):
+    """Gated multi-head attention (reference modules.py:170-225).
+
+    3-D input  [B, N, D]      : the single-representation attention of FoldingBlock (optional bias).
+    4-D input  [B, N, N, D]   : one independent sequence per pair row (what TriangleAttention feeds it).
+    Returns the attention update (the caller adds the residual), like the reference.
+    """
+
+    def __init__(self, embed_dim: int, head_dim: int, num_heads: int):
+        super().__init__()
+        if head_dim != 16 or num_heads != 4:
+            raise ValueError("the B200 Attention kernels are built for 4 heads x 16 channels")
+        self.embed_dim, self.head_dim, self.num_heads = embed_dim, head_dim, num_heads
+        self.scale = 1.0 / math.sqrt(head_dim)
+        self.inf = 2.0 ** 15
+        self.norm = nn.LayerNorm(embed_dim, elementwise_affine=False)
+        self.q_proj = Linear(embed_dim, num_heads * head_dim, bias=False, init="glorot")
+        self.k_proj = Linear(embed_dim, num_heads * head_dim, bias=False, init="glorot")
+        self.v_proj = Linear(embed_dim, num_heads * head_dim, bias=False, init="glorot")
+        self.gate_proj = Linear(embed_dim, num_heads * head_dim, init="gating")
+        self.out_proj = Linear(num_heads * head_dim, embed_dim, init="final")
+        self._pack = PackCache()
+
+    def _sources(self):
+        return [self.q_proj.weight, self.k_proj.weight, self.v_proj.weight, self.gate_proj.weight,
+                self.gate_proj.bias, self.out_proj.weight, self.out_proj.bias]
+
+    def packed_pair(self):
+        """[w_qkvg_h (4Hc x D), b_gate, w_o_h, b_o] for prd_triangle_attention_fwd."""
+        s = self._sources()
+        return self._pack.get(s, lambda: [half(torch.cat([s[0], s[1], s[2], s[3]], 0)), f32(s[4]), half(s[5]), f32(s[6])])
+
+    def packed_single(self, bias_lin: Optional[nn.Linear]):
+        """[w_bias, b_bias, w_qkvg_h, b_qkvg, w_o_h, b_o] for prd_single_attention_fwd."""
+        s = self._sources() + ([bias_lin.weight, bias_lin.bias] if bias_lin is not None else [])
+
+        def build():
+            hc = self.num_heads * self.head_dim
+            b_qkvg = torch.cat([torch.zeros(3 * hc, device=s[4].device, dtype=torch.float32), f32(s[4])])
+            wb = f32(s[7]) if bias_lin is not None else None
+            bb = f32(s[8]) if bias_lin is not None else None
+            return [wb, bb, half(torch.cat([s[0], s[1], s[2], s[3]], 0)), b_qkvg, half(s[5]), f32(s[6])]
+
+        return self._pack.get(s, build)
+
+    def forward(self, x: torch.Tensor, mask: torch.Tensor, attn_bias: Optional[torch.Tensor] = None) -> torch.Tensor:
+        x = x.contiguous()
+        if x.dim() == 3:
+            cfg = AF2_modules._MiniCfg(self.embed_dim, 64, self.num_heads, self.head_dim)
+            out = torch.empty_like(x)
+            bias = None if attn_bias is None else attn_bias.contiguous()
+            return ops.single_attention(cfg, x, None, mask.contiguous(), self.packed_single(None), out, residual=0,
+                                        attn_bias=bias)
+        if x.dim() == 4:
+            if attn_bias is not None:
+                raise ValueError("pair-row attention takes no bias (modules.py:242)")
+            cfg = AF2_modules._MiniCfg(512, self.embed_dim, self.num_heads, self.head_dim)
+            out = torch.empty_like(x)
+            return ops.triangle_attention(cfg, x, _mask_from_2d(mask), 0, self.packed_pair(), out, residual=0)
+        raise ValueError(f"Attention expects a 3-D or 4-D input, got {tuple(x.shape)}")
+
+
+class TriangleAttention(nn.Module):
+    """reference modules.py:228-243."""
+
+    def __init__(self, pair_dim: int, head_dim: int, num_heads: int, mode: str):
+        super().__init__()
+        if mode not in ("starting", "ending"):
+            raise ValueError(f"Invalid mode: {mode}")
+        self.attn = Attention(pair_dim, head_dim, num_heads)
+        self.mode = mode
+        self.pair_dim = pair_dim
+
+    def apply_(self, cfg, pair, mask, out=None, residual=1):
+        out = pair if out is None else out
+        return ops.triangle_attention(cfg, pair, mask, 1 if self.mode == "ending" else 0, self.attn.packed_pair(), out,
+                                      residual=residual)
+
+    def forward(self, pair: torch.Tensor, mask_2d: torch.Tensor) -> torch.Tensor:
+        cfg = AF2_modules._MiniCfg(512, self.pair_dim, self.attn.num_heads, self.attn.head_dim)
+        pair = pair.contiguous()
+        return self.apply_(cfg, pair, _mask_from_2d(mask_2d), out=torch.empty_like(pair), residual=0)
+
+
+class TriangleMultiplication(nn.Module):
+    """reference modules.py:246-274."""
+
+    def __init__(self, pair_dim: int, mode: str):
+        super().__init__()
+        if mode == "outgoing":
+            self.equation = "...ikd,...jkd->...ijd"
+        elif mode == "incoming":
+            self.equation = "...kid,...kjd->...ijd"
+        else:
+            raise ValueError(f"Invalid mode: {mode}")
+        self.mode = mode
+        self.pair_dim = pair_dim
+        self.norm = nn.LayerNorm(pair_dim, elementwise_affine=False)
+        self.ab_proj = Linear(pair_dim, pair_dim * 2, init="default")
+        self.ab_gate = Linear(pair_dim, pair_dim * 2, init="gating")
+        self.ab_norm = nn.LayerNorm(pair_dim, elementwise_affine=False)
+        self.out_proj = Linear(pair_dim, pair_dim, init="final")
+        self.out_gate = Linear(pair_dim, pair_dim, init="gating")
+        self._pack = PackCache()
+
+    def packed_weights(self):
+        s = [self.ab_proj.weight, self.ab_gate.weight, self.ab_proj.bias, self.ab_gate.bias,
+             self.out_gate.weight, self.out_proj.weight, self.out_gate.bias, self.out_proj.bias]
+        return self._pack.get(s, lambda: [half(torch.cat([s[0], s[1]], 0)), f32(torch.cat([s[2], s[3]])),
+                                          half(torch.cat([s[4], s[5]], 0)), f32(torch.cat([s[6], s[7]]))])
+
+    def apply_(self, cfg, pair, mask, out=None, residual=1):
+        out = pair if out is None else out
+        return ops.triangle_multiplication(cfg, pair, mask, 1 if self.mode == "incoming" else 0, self.packed_weights(),
+                                           out, residual=residual)
+
+    def forward(self, pair: torch.Tensor, mask_2d: torch.Tensor) -> torch.Tensor:
+        cfg = AF2_modules._MiniCfg(512, self.pair_dim, 4)
+        pair = pair.contiguous()
+        return self.apply_(cfg, pair, _mask_from_2d(mask_2d), out=torch.empty_like(pair), residual=0)
+
+
+class OuterLinear(nn.Module):
+    """reference modules.py:277-287, evaluated in bilinear form (the [.., 2 c_s] concat never exists)."""
+
+    def __init__(self, single_dim: int, pair_dim: int):
+        super().__init__()
+        self.single_dim, self.pair_dim = single_dim, pair_dim
+        self.norm = nn.LayerNorm(single_dim, elementwise_affine=False)
+        self.linear = Linear(single_dim * 2, pair_dim, init="final")
+        self._pack = PackCache()
+
+    def packed_weights(self):
+        s = [self.linear.weight, self.linear.bias]
+        cs = self.single_dim
+        return self._pack.get(s, lambda: [half(s[0][:, :cs]), half(s[0][:, cs:]), f32(s[1])])
+
+    def apply_(self, cfg, single, pair, out=None, residual=1):
+        out = pair if out is None else out
+        return ops.outer_linear(cfg, single, pair, self.packed_weights(), out, residual=residual)
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        cfg = AF2_modules._MiniCfg(self.single_dim, self.pair_dim, 4)
+        x = x.contiguous()
+        B, N, _ = x.shape
+        out = torch.empty(B, N, N, self.pair_dim, dtype=torch.float32, device=x.device)
+        return self.apply_(cfg, x, out, out=out, residual=0)
+
+
+class _Transition(nn.Sequential):
+    """LayerNorm -> Linear(relu init) -> ReLU -> Linear(final init); names .1 / .3 as in the reference."""
+
+    def __init__(self, dim: int, factor: int):
+        super().__init__(nn.LayerNorm(dim, elementwise_affine=False), Linear(dim, dim * factor, init="relu"), nn.ReLU(),
+                         Linear(dim * factor, dim, init="final"))
+        self._pack = PackCache()
+
+    def packed_weights(self):
+        s = [self[1].weight, self[1].bias, self[3].weight, self[3].bias]
+        return self._pack.get(s, lambda: [half(s[0]), f32(s[1]), half(s[2]), f32(s[3])])
+
+    def forward(self, x):  # stand-alone use returns the update, like the reference nn.Sequential
+        x = x.contiguous()
+        out = torch.empty_like(x)
+        if x.dim() == 3:
+            cfg = AF2_modules._MiniCfg(x.shape[-1], 64, 4, transition_factor=self[1].out_features // x.shape[-1])
+            return ops.single_transition(cfg, x, self.packed_weights(), out, residual=0)
+        cfg = AF2_modules._MiniCfg(512, x.shape[-1], 4, transition_factor=self[1].out_features // x.shape[-1])
+        return ops.pair_transition(cfg, x, self.packed_weights(), out, residual=0)
+
+
+class FoldingBlock(nn.Module):
+    """reference modules.py:290-343: eight residual updates in fixed order."""
+
+    def __init__(self, single_dim: int, pair_dim: int, head_dim: int, num_heads: int, transition_factor: int):
+        super().__init__()
+        self.cfg = AF2_modules._MiniCfg(single_dim, pair_dim, num_heads, head_dim, transition_factor)
+        # index 1 holds the Linear so that state-dict keys read attn_bias.1.{weight,bias}
+        self.attn_bias = nn.Sequential(nn.LayerNorm(pair_dim, elementwise_affine=False),
+                                       Linear(pair_dim, num_heads, init="normal"), nn.Identity())
+        self.single_attn = Attention(single_dim, head_dim, num_heads)
+        self.single_fc = _Transition(single_dim, transition_factor)
+        self.outer_linear = OuterLinear(single_dim, pair_dim)
+        self.pair_mul_outgoing = TriangleMultiplication(pair_dim, "outgoing")
+        self.pair_mul_incoming = TriangleMultiplication(pair_dim, "incoming")
+        self.pair_attn_starting = TriangleAttention(pair_dim, head_dim, num_heads, "starting")
+        self.pair_attn_ending = TriangleAttention(pair_dim, head_dim, num_heads, "ending")
+        self.pair_fc = _Transition(pair_dim, transition_factor)
+
+    def forward_(self, cfg, single: torch.Tensor, pair: torch.Tensor, mask: torch.Tensor, probe=None):
+        """In-place form used by Denoiser: updates `single` and `pair` and returns them."""
+        rec = probe or (lambda n, t: None)
+        ops.single_attention(cfg, single, pair, mask, self.single_attn.packed_single(self.attn_bias[1]), single)
+        rec("single_attn", single)
+        ops.single_transition(cfg, single, self.single_fc.packed_weights(), single)
+        rec("single_fc", single)
+        self.outer_linear.apply_(cfg, single, pair)
+        rec("outer_linear", pair)
+        self.pair_mul_outgoing.apply_(cfg, pair, mask)
+        rec("pair_mul_outgoing", pair)
+        self.pair_mul_incoming.apply_(cfg, pair, mask)
+        rec("pair_mul_incoming", pair)
+        self.pair_attn_starting.apply_(cfg, pair, mask)
+        rec("pair_attn_starting", pair)
+        self.pair_attn_ending.apply_(cfg, pair, mask)
+        rec("pair_attn_ending", pair)
+        ops.pair_transition(cfg, pair, self.pair_fc.packed_weights(), pair)
+        rec("pair_fc", pair)
+        return single, pair
+
+    def forward(self, single: torch.Tensor, pair: torch.Tensor, mask: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        # the reference returns new tensors; keep the caller's inputs intact
+        return self.forward_(self.cfg, single.contiguous().clone(), pair.contiguous().clone(), mask.contiguous())
+
+
+class Denoiser(nn.Module):
+    """reference modules.py:346-404."""
+
+    def __init__(self, args):
+        super().__init__()
+        if isinstance(args, Mapping):
+            args = Namespace(**args)
+        self.single_dim = args.single_dim
+        self.esm_dim = args.esm_dim
+        self.pair_dim = args.pair_dim
+        self.head_dim = args.head_dim
+        self.num_heads = args.num_heads
+        self.transition_factor = args.transition_factor
+        self.num_blocks = args.num_blocks
+        self.n_recycles = args.n_recycles
+        self.cfg = DenoiserConfig.from_args(args)
+        self.SPAAttnBlock = AF2_modules.SPAttention(c_in=self.single_dim, c_hidden=self.single_dim,
+                                                    no_heads=self.num_heads, pair_bias=True, c_z=self.pair_dim)
+        self.opm = AF2_modules.OuterProductUpdate(c_m=self.single_dim, c_z=self.pair_dim,
+                                                  c_hidden=self.single_dim // 4)
+        self.folding_blocks = nn.ModuleList([
+            FoldingBlock(self.single_dim, self.pair_dim, self.head_dim, self.num_heads, self.transition_factor)
+            for _ in range(self.num_blocks)])
+
+    def trunk_(self, single, pair, mask, probe=None):
+        """Everything after the outer-product update, in place: SPAttention, then the folding blocks."""
+        rec = probe or (lambda n, t: None)
+        self.SPAAttnBlock(single, pair, mask, cfg=self.cfg, out=single)
+        rec("Denoiser.SPAAttnBlock", single)
+        for k, block in enumerate(self.folding_blocks):
+            block.forward_(self.cfg, single, pair, mask,
+                           probe=None if probe is None else (lambda n, t, k=k: probe(f"Denoiser.folding_blocks.{k}.{n}", t)))
+        return single, pair
+
+    def forward(self, batch, z, t, single, pair, cache):
+        """Same contract as the reference: `pair` is updated in place, z / t / cache pass through."""
+        if pair.requires_grad or single.requires_grad:
+            raise NotImplementedError("backward kernels are not part of this build (SURVEY §8f item 1)")
+        mask = batch["residue_and_atom_mask"].contiguous()
+        single = single.contiguous().clone()
+        if not pair.is_contiguous():
+            raise ValueError("pair must be contiguous")
+        a, b = self.opm.project(self.cfg, single, mask)
+        _, (w_o, b_o) = self.opm.packed_weights()
+        zeros = torch.zeros(mask.shape[0], mask.shape[1], 3, dtype=torch.float32, device=pair.device)
+        ops.pair_embed(self.cfg, pair, zeros, mask, None, a, b, [None, None, None, None, w_o, b_o], pair, flags=1)
+        single, pair = self.trunk_(single, pair, mask)
+        ops.symmetrize(self.cfg, pair)
+        return single, pair, cache

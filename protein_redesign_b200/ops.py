@@ -1,0 +1,177 @@
+"""Python-side launchers for the module-level C ops (thin: argument checks + pointer packing).
+
+Every function enqueues hand-written sm_100a kernels on the current CUDA stream through
+``_lib.call``; none of them computes anything in PyTorch.
+"""
+from __future__ import annotations
+
+from typing import Optional, Sequence
+
+import torch
+
+from . import _lib
+from ._lib import PrdDims
+
+F32, F16, I64 = torch.float32, torch.float16, torch.int64
+
+
+def make_dims(cfg, B: int, N: int, mode: int = 0, residual: int = 1) -> PrdDims:
+    d = PrdDims()
+    d.B, d.N = int(B), int(N)
+    d.c_s, d.c_z, d.H, d.c, d.tf = cfg.single_dim, cfg.pair_dim, cfg.num_heads, cfg.head_dim, cfg.transition_factor
+    d.esm_dim, d.time_dim, d.dist_dim = cfg.esm_dim, cfg.time_dim, cfg.dist_dim
+    d.max_bond_distance, d.max_relpos, d.num_steps = cfg.max_bond_distance, cfg.max_relpos, cfg.num_steps
+    d.mode, d.residual = int(mode), int(residual)
+    return d
+
+
+def reserve_workspace(cfg, B: int, N: int, device) -> None:
+    """Size the per-device workspace for every op at (B, N) -- call before CUDA-graph capture."""
+    d = make_dims(cfg, B, N)
+    need = max(_lib.workspace_bytes(op, d) for op in _lib.OPS)
+    _lib.Workspace.reserve(torch.device(device), need)
+
+
+def _chk(ts: Sequence[Optional[torch.Tensor]], dtypes, names):
+    for t, dt, n in zip(ts, dtypes, names):
+        if t is not None:
+            _lib.check_tensor(t, dt, n)
+
+
+def esm_embed(cfg, residue_esm, w_esm_h, out=None):
+    B, N, _ = residue_esm.shape
+    _chk([residue_esm, w_esm_h], [F32, F16], ["residue_esm", "w_esm_h"])
+    out = torch.empty(B, N, cfg.single_dim, dtype=F32, device=residue_esm.device) if out is None else out
+    _lib.call("esm_embed", make_dims(cfg, B, N), [residue_esm], [out], [w_esm_h])
+    return out
+
+
+def single_embed(cfg, atom_feats, atom_mask, residue_mask, seq_t, esm_emb, atom_tables, w_type, out=None):
+    B, N = atom_mask.shape
+    _chk([atom_feats, atom_mask, residue_mask, seq_t, esm_emb, w_type], [I64, F32, F32, F32, F32, F32],
+         ["atom_feats", "atom_mask", "residue_mask", "seq_t", "esm_emb", "w_type"])
+    out = torch.empty(B, N, cfg.single_dim, dtype=F32, device=atom_mask.device) if out is None else out
+    _lib.call("single_embed", make_dims(cfg, B, N), [atom_feats, atom_mask, residue_mask, seq_t, esm_emb], [out],
+              list(atom_tables) + [w_type])
+    return out
+
+
+def pair_embed_static(cfg, batch, bond_tables, bdist_table, relpos_table, out=None):
+    am = batch["atom_mask"]
+    B, N = am.shape
+    ins = [am, batch["residue_mask"], batch["bond_mask"], batch["bond_feats"], batch["bond_distance"],
+           batch["residue_index"], batch["residue_chain_index"]]
+    _chk(ins, [F32, F32, F32, I64, I64, I64, I64],
+         ["atom_mask", "residue_mask", "bond_mask", "bond_feats", "bond_distance", "residue_index", "residue_chain_index"])
+    out = torch.empty(B, N, N, cfg.pair_dim, dtype=F32, device=am.device) if out is None else out
+    _lib.call("pair_embed_static", make_dims(cfg, B, N), ins, [out], list(bond_tables) + [bdist_table, relpos_table])
+    return out
+
+
+def opm_project(cfg, single, mask, weights, out_a=None, out_b=None):
+    B, N, _ = single.shape
+    _chk([single, mask], [F32, F32], ["single", "mask"])
+    od = cfg.single_dim // 4
+    out_a = torch.empty(B, N, od, dtype=F32, device=single.device) if out_a is None else out_a
+    out_b = torch.empty(B, N, od, dtype=F32, device=single.device) if out_b is None else out_b
+    _lib.call("opm_project", make_dims(cfg, B, N), [single, mask], [out_a, out_b], weights)
+    return out_a, out_b
+
+
+def pair_embed(cfg, pair_static, z, mask, t, opm_a, opm_b, weights, out, sampler_state=None, flags: int = 0):
+    B, N = mask.shape
+    _chk([pair_static, z, mask, t, opm_a, opm_b, out], [F32, F32, F32, I64, F32, F32, F32],
+         ["pair_static", "z", "mask", "t", "opm_a", "opm_b", "pair"])
+    _lib.call("pair_embed", make_dims(cfg, B, N, mode=flags), [pair_static, z, mask, t, opm_a, opm_b, sampler_state],
+              [out], weights)
+    return out
+
+
+def spattention(cfg, single, pair, weights, out=None):
+    B, N, _ = single.shape
+    _chk([single, pair], [F32, F32], ["single", "pair"])
+    out = torch.empty_like(single) if out is None else out
+    _lib.call("spattention", make_dims(cfg, B, N), [single, pair], [out], weights)
+    return out
+
+
+def single_attention(cfg, single, pair, mask, weights, out, residual=1, attn_bias=None):
+    B, N, _ = single.shape
+    _chk([single, pair, mask, attn_bias, out], [F32, F32, F32, F32, F32], ["single", "pair", "mask", "attn_bias", "out"])
+    _lib.call("single_attention", make_dims(cfg, B, N, residual=residual), [single, pair, mask, attn_bias], [out], weights)
+    return out
+
+
+def single_transition(cfg, single, weights, out, residual=1):
+    B, N, _ = single.shape
+    _chk([single, out], [F32, F32], ["single", "out"])
+    _lib.call("single_transition", make_dims(cfg, B, N, residual=residual), [single], [out], weights)
+    return out
+
+
+def outer_linear(cfg, single, pair, weights, out, residual=1):
+    B, N, _ = single.shape
+    _chk([single, pair, out], [F32, F32, F32], ["single", "pair", "out"])
+    _lib.call("outer_linear", make_dims(cfg, B, N, residual=residual), [single, pair], [out], weights)
+    return out
+
+
+def triangle_multiplication(cfg, pair, mask, mode, weights, out, residual=1):
+    B, N = mask.shape
+    _chk([pair, mask, out], [F32, F32, F32], ["pair", "mask", "out"])
+    _lib.call("triangle_multiplication", make_dims(cfg, B, N, mode=mode, residual=residual), [pair, mask], [out], weights)
+    return out
+
+
+def triangle_attention(cfg, pair, mask, mode, weights, out, residual=1):
+    B, N = mask.shape
+    _chk([pair, mask, out], [F32, F32, F32], ["pair", "mask", "out"])
+    _lib.call("triangle_attention", make_dims(cfg, B, N, mode=mode, residual=residual), [pair, mask], [out], weights)
+    return out
+
+
+def pair_transition(cfg, pair, weights, out, residual=1):
+    B, N = pair.shape[:2]
+    _chk([pair, out], [F32, F32], ["pair", "out"])
+    _lib.call("pair_transition", make_dims(cfg, B, N, residual=residual), [pair], [out], weights)
+    return out
+
+
+def symmetrize(cfg, pair):
+    B, N = pair.shape[:2]
+    _chk([pair], [F32], ["pair"])
+    _lib.call("symmetrize", make_dims(cfg, B, N), [], [pair], [])
+    return pair
+
+
+def coord_head(cfg, pair, z, mask, weights, out=None):
+    B, N = mask.shape
+    _chk([pair, z, mask], [F32, F32, F32], ["pair", "z", "mask"])
+    out = torch.empty(B, N, 3, dtype=F32, device=pair.device) if out is None else out
+    _lib.call("coord_head", make_dims(cfg, B, N), [pair, z, mask], [out], weights)
+    return out
+
+
+def seq_head(cfg, single, weights, out=None):
+    B, N, _ = single.shape
+    _chk([single], [F32], ["single"])
+    out = torch.empty(B, N, 21, dtype=F32, device=single.device) if out is None else out
+    _lib.call("seq_head", make_dims(cfg, B, N), [single], [out], weights)
+    return out
+
+
+def remove_mean(cfg, x, mask):
+    """In place; x [R, N, C] with R a multiple of mask.shape[0] (mask rows repeat cyclically)."""
+    R, N, C = x.shape
+    _chk([x, mask], [F32, F32], ["x", "mask"])
+    d = make_dims(cfg, R, N, mode=C)
+    d.H = mask.shape[0]
+    _lib.call("remove_mean", d, [mask], [x], [])
+    return x
+
+
+def sampler_update(cfg, noise_pred, seq_pred, noise, coef, z, seq_t, state):
+    B, N, _ = z.shape
+    _chk([noise_pred, seq_pred, noise, coef, z, seq_t], [F32] * 6, ["noise_pred", "seq_pred", "noise", "coef", "z", "seq_t"])
+    _lib.check_tensor(state, torch.int32, "sampler_state")
+    _lib.call("sampler_update", make_dims(cfg, B, N), [noise_pred, seq_pred, noise, coef], [z, seq_t, state], [])

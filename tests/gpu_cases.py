@@ -1,0 +1,350 @@
+"""GPU parity cases: every C-ABI op (and the whole step / sampler) against the CPU oracle.
+
+Each case returns ``{metric_name: (value, bound)}``; ``tests/test_gpu_parity.py`` asserts
+value <= bound, ``tools/gpu_diag.py`` runs every case in its own process (a CUDA fault poisons the
+context) and logs the numbers.
+
+Tolerances: the kernels use fp16 tensor-core operands with fp32 accumulation and fp32 LayerNorm /
+softmax statistics; operand rounding is 2^-11 relative, so single ops land at ~1e-4..5e-4 relative
+L2 and the full 4-block step at <= 1e-3 (north_star tolerance) on coordinates and logits.
+"""
+from __future__ import annotations
+
+import dataclasses
+import math
+
+import torch
+import torch.nn.functional as F
+
+from oracle import denoiser_ref as ref
+from protein_redesign_b200 import _lib, ops
+from protein_redesign_b200 import synthetic as syn
+from protein_redesign_b200.model import ProteinReDiffModel
+
+DEV = "cuda:0"
+OP_TOL = 2e-3      # single fused op, relative L2 vs fp32 oracle
+STEP_TOL = 1e-3    # whole denoiser step (north_star: <= 1e-3 relative on coords and logits)
+
+
+def rel(a, b):
+    a = a.detach().double().cpu()
+    b = b.detach().double().cpu()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def _model(cfg, seed):
+    sd = syn.make_state_dict(cfg, seed)
+    m = ProteinReDiffModel(cfg)
+    m.load_state_dict(sd, strict=True)
+    return m.to(DEV).eval(), sd
+
+
+def _to_dev(batch):
+    return {k: (v.to(DEV) if isinstance(v, torch.Tensor) else v) for k, v in batch.items()}
+
+
+def _pair_inputs(cfg, B, N, seed, pad=0):
+    g = torch.Generator().manual_seed(seed)
+    pair = torch.randn(B, N, N, cfg.pair_dim, generator=g) * 1.5 + 0.3
+    single = torch.randn(B, N, cfg.single_dim, generator=g)
+    mask = torch.ones(B, N)
+    if pad:
+        mask[:, N - pad:] = 0
+        if B > 1:
+            mask[1, N - 2 * pad:] = 0
+    return single, pair, mask
+
+
+# ------------------------------------------------------------------------------------------
+# tcgen05 + TMA machinery
+# ------------------------------------------------------------------------------------------
+def case_gemm(M=256, N=128, K=64, nb1=1, nb2=1, epilogue=False, out_fp16=False, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    a = (torch.randn(nb2, nb1, M, K, generator=g)).half()
+    b = (torch.randn(nb2, nb1, N, K, generator=g)).half()
+    want = torch.matmul(a.float(), b.float().transpose(-1, -2))
+    kw = {}
+    if epilogue:
+        bias = torch.randn(N, generator=g)
+        rowscale = torch.rand(nb2, nb1, M, generator=g)
+        mul = torch.randn(nb2, nb1, M, N, generator=g)
+        add = torch.randn(nb2, nb1, M, N, generator=g)
+        want = torch.relu(0.5 * want + bias) * rowscale.unsqueeze(-1) * mul + add
+        kw = dict(alpha=0.5, bias=bias.to(DEV), act=1, rowscale=rowscale.to(DEV).contiguous(),
+                  mul=mul.to(DEV).contiguous(), add=add.to(DEV).contiguous())
+    out = torch.full((nb2, nb1, M, N), float("nan"), dtype=torch.float16 if out_fp16 else torch.float32, device=DEV)
+    _lib.gemm_f16(a.to(DEV).contiguous(), b.to(DEV).contiguous(), out, **kw)
+    torch.cuda.synchronize()
+    return {"rel": (rel(out.float(), want), 2e-3 if out_fp16 else 1e-5 * math.sqrt(K) + 1e-6)}
+
+
+# ------------------------------------------------------------------------------------------
+# module-level ops vs oracle
+# ------------------------------------------------------------------------------------------
+def _block_prefix(k=0):
+    return f"Denoiser.folding_blocks.{k}."
+
+
+def case_pair_transition(cfg=syn.PAPER, B=1, N=72, seed=0):
+    m, sd = _model(cfg, seed)
+    _, pair, _ = _pair_inputs(cfg, B, N, seed)
+    want = pair + ref.transition(sd, _block_prefix() + "pair_fc.", pair)
+    blk = m.Denoiser.folding_blocks[0]
+    p = pair.to(DEV).contiguous()
+    ops.pair_transition(cfg, p, blk.pair_fc.packed_weights(), p)
+    upd = blk.pair_fc(pair.to(DEV))  # module-level form returns the update
+    torch.cuda.synchronize()
+    return {"rel": (rel(p, want), OP_TOL), "rel_update": (rel(upd, want - pair), OP_TOL)}
+
+
+def case_trimul(cfg=syn.PAPER, B=2, N=72, mode="outgoing", seed=0, pad=5):
+    m, sd = _model(cfg, seed)
+    _, pair, mask = _pair_inputs(cfg, B, N, seed, pad)
+    m2 = mask.unsqueeze(-1) * mask.unsqueeze(-2)
+    upd = ref.triangle_multiplication(sd, _block_prefix() + f"pair_mul_{mode}.", pair, m2, mode)
+    mod = getattr(m.Denoiser.folding_blocks[0], f"pair_mul_{mode}")
+    p = pair.to(DEV).contiguous()
+    mod.apply_(cfg, p, mask.to(DEV))
+    got_upd = mod(pair.to(DEV), m2.to(DEV))
+    torch.cuda.synchronize()
+    return {"rel": (rel(p, pair + upd), OP_TOL), "rel_update": (rel(got_upd, upd), 2 * OP_TOL)}
+
+
+def case_triattn(cfg=syn.PAPER, B=2, N=72, mode="starting", seed=0, pad=5):
+    m, sd = _model(cfg, seed)
+    _, pair, mask = _pair_inputs(cfg, B, N, seed, pad)
+    m2 = mask.unsqueeze(-1) * mask.unsqueeze(-2)
+    upd = ref.triangle_attention(sd, _block_prefix() + f"pair_attn_{mode}.", pair, m2, cfg.num_heads, mode)
+    mod = getattr(m.Denoiser.folding_blocks[0], f"pair_attn_{mode}")
+    p = pair.to(DEV).contiguous()
+    mod.apply_(cfg, p, mask.to(DEV))
+    got_upd = mod(pair.to(DEV), m2.to(DEV))
+    torch.cuda.synchronize()
+    return {"rel": (rel(p, pair + upd), OP_TOL), "rel_update": (rel(got_upd, upd), 2 * OP_TOL)}
+
+
+def case_outer_linear(cfg=syn.PAPER, B=2, N=72, seed=0):
+    m, sd = _model(cfg, seed)
+    single, pair, _ = _pair_inputs(cfg, B, N, seed)
+    upd = ref.outer_linear(sd, _block_prefix() + "outer_linear.", single)
+    mod = m.Denoiser.folding_blocks[0].outer_linear
+    p = pair.to(DEV).contiguous()
+    mod.apply_(cfg, single.to(DEV).contiguous(), p)
+    got_upd = mod(single.to(DEV))
+    torch.cuda.synchronize()
+    return {"rel": (rel(p, pair + upd), OP_TOL), "rel_update": (rel(got_upd, upd), OP_TOL)}
+
+
+def case_single_attention(cfg=syn.PAPER, B=2, N=72, seed=0, pad=5):
+    m, sd = _model(cfg, seed)
+    single, pair, mask = _pair_inputs(cfg, B, N, seed, pad)
+    p = _block_prefix()
+    bias = ref.attn_bias_from_pair(sd, p, pair)
+    want = single + ref.gated_attention(sd, p + "single_attn.", single, mask, cfg.num_heads, bias)
+    blk = m.Denoiser.folding_blocks[0]
+    s = single.to(DEV).contiguous()
+    ops.single_attention(cfg, s, pair.to(DEV).contiguous(), mask.to(DEV), blk.single_attn.packed_single(blk.attn_bias[1]), s)
+    upd = blk.single_attn(single.to(DEV), mask.to(DEV), attn_bias=bias.to(DEV).contiguous())
+    torch.cuda.synchronize()
+    return {"rel": (rel(s, want), OP_TOL), "rel_update": (rel(upd, want - single), OP_TOL)}
+
+
+def case_single_transition(cfg=syn.PAPER, B=2, N=72, seed=0):
+    m, sd = _model(cfg, seed)
+    single, _, _ = _pair_inputs(cfg, B, N, seed)
+    want = single + ref.transition(sd, _block_prefix() + "single_fc.", single)
+    blk = m.Denoiser.folding_blocks[0]
+    s = single.to(DEV).contiguous()
+    ops.single_transition(cfg, s, blk.single_fc.packed_weights(), s)
+    torch.cuda.synchronize()
+    return {"rel": (rel(s, want), OP_TOL)}
+
+
+def case_spattention(cfg=syn.PAPER, B=2, N=72, seed=0):
+    m, sd = _model(cfg, seed)
+    single, pair, mask = _pair_inputs(cfg, B, N, seed)
+    want = ref.single_pair_attention(sd, single, pair, cfg.num_heads)
+    got = m.Denoiser.SPAAttnBlock(single.to(DEV), pair.to(DEV), mask.to(DEV), cfg=cfg)
+    torch.cuda.synchronize()
+    return {"rel": (rel(got, want), OP_TOL)}
+
+
+def case_opm(cfg=syn.PAPER, B=2, N=72, seed=0, pad=5):
+    m, sd = _model(cfg, seed)
+    single, pair, mask = _pair_inputs(cfg, B, N, seed, pad)
+    want = ref.outer_product_update(sd, single, mask)
+    got = m.Denoiser.opm(single.to(DEV), mask.to(DEV), cfg=cfg)
+    torch.cuda.synchronize()
+    return {"rel": (rel(got, want), OP_TOL)}
+
+
+def case_embeddings(cfg=syn.PAPER, sizes=((9, 50), (12, 60)), seed=0):
+    m, sd = _model(cfg, seed)
+    batch = syn.make_batch(cfg, list(sizes), seed=seed, two_chains=True)
+    z, seq_t, mask, t = syn.make_step_inputs(batch, cfg.num_steps, seed)
+    torch.manual_seed(seed)
+    pb = ref.prepare_batch(batch, cfg.mask_prob)
+    want_single = ref.embed_single(sd, pb, seq_t)
+    want_static = ref.embed_pair_static(sd, pb, cfg.max_bond_distance, cfg.max_relpos)
+    want_pair = want_static + ref.embed_pair_dynamic(sd, z, t, mask, cfg.num_steps)
+    m2 = mask.unsqueeze(-1) * mask.unsqueeze(-2)
+    want_pair_opm = want_pair + m2.unsqueeze(-1) * ref.outer_product_update(sd, want_single, mask)
+    db = _to_dev(pb)
+    w = m._weights()
+    esm_emb, pair_static = m._static_embeddings(db)
+    single = ops.single_embed(cfg, db["atom_feats"], db["atom_mask"], db["residue_mask"], seq_t.to(DEV), esm_emb,
+                              w["atom_tabs"], w["w_type"])
+    a, b = m.Denoiser.opm.project(cfg, single, mask.to(DEV))
+    _, (w_o, b_o) = m.Denoiser.opm.packed_weights()
+    pair = torch.empty_like(pair_static)
+    ops.pair_embed(cfg, pair_static, z.to(DEV), mask.to(DEV), t.to(DEV), a, b, w["pair_dyn"] + [w_o, b_o], pair)
+    torch.cuda.synchronize()
+    return {"single": (rel(single, want_single), OP_TOL), "pair_static": (rel(pair_static, want_static), 1e-6),
+            "pair": (rel(pair, want_pair_opm), OP_TOL)}
+
+
+def case_heads(cfg=syn.PAPER, B=2, N=72, seed=0, pad=5):
+    m, sd = _model(cfg, seed)
+    single, pair, mask = _pair_inputs(cfg, B, N, seed, pad)
+    g = torch.Generator().manual_seed(seed + 1)
+    z = torch.randn(B, N, 3, generator=g)
+    sym = 0.5 * (pair + pair.transpose(1, 2))
+    want_noise = ref.coord_head(sd, sym, z, mask)
+    want_seq = ref.seq_head(sd, single)
+    w = m._weights()
+    noise = ops.coord_head(cfg, pair.to(DEV).contiguous(), z.to(DEV), mask.to(DEV), w["coord"])
+    seq = ops.seq_head(cfg, single.to(DEV).contiguous(), w["seq"])
+    p2 = pair.to(DEV).contiguous()
+    ops.symmetrize(cfg, p2)
+    torch.cuda.synchronize()
+    return {"noise": (rel(noise, want_noise), OP_TOL), "seq": (rel(seq, want_seq), OP_TOL),
+            "sym_maxabs": (float((p2.cpu() - sym).abs().max()), 0.0)}
+
+
+def case_pair_bias(cfg=syn.PAPER, B=2, N=72, seed=0):
+    m, sd = _model(cfg, seed)
+    _, pair, _ = _pair_inputs(cfg, B, N, seed)
+    want = ref.attn_bias_from_pair(sd, _block_prefix(), pair)
+    blk = m.Denoiser.folding_blocks[0]
+    # reach the stream kernel through single_attention's workspace is awkward; use the op with zero single
+    # instead: compare through the full single_attention case.  Here: SPA bias path (affine LN) via spattention
+    # is covered by case_spattention.  Direct check uses the same kernel via a 1-token trick is not possible,
+    # so this case only checks shapes/values through single_attention with single = 0.
+    single = torch.zeros(B, N, cfg.single_dim)
+    mask = torch.ones(B, N)
+    wantd = ref.gated_attention(sd, _block_prefix() + "single_attn.", single, mask, cfg.num_heads, want)
+    s = single.to(DEV).contiguous()
+    ops.single_attention(cfg, s, pair.to(DEV).contiguous(), mask.to(DEV), blk.single_attn.packed_single(blk.attn_bias[1]), s)
+    torch.cuda.synchronize()
+    return {"rel": (rel(s, wantd), OP_TOL)}
+
+
+# ------------------------------------------------------------------------------------------
+# whole step / sampler
+# ------------------------------------------------------------------------------------------
+def case_step(cfg=syn.PAPER, sizes=((12, 60), (9, 50)), seed=3, n_total=None, golden=None, probes=False):
+    m, sd = _model(cfg, seed)
+    batch = syn.make_batch(cfg, list(sizes), seed=seed, n_total=n_total)
+    z, seq_t, mask, t = syn.make_step_inputs(batch, cfg.num_steps, seed)
+    torch.manual_seed(seed)
+    pb = ref.prepare_batch(batch, cfg.mask_prob)
+    want_probes = {}
+    with torch.inference_mode():
+        want_noise, want_seq = ref.denoiser_step(sd, cfg, pb, z, seq_t, mask, t,
+                                                 probe=(lambda n, v: want_probes.__setitem__(n, v.clone())) if probes else None)
+    torch.manual_seed(seed)
+    db = m.prepare_batch(_to_dev(batch))
+    got_probes = {}
+    with torch.inference_mode():
+        noise, seq = m._denoise(db, z.to(DEV), seq_t.to(DEV), mask.to(DEV), t.to(DEV),
+                                probe=(lambda n, v: got_probes.__setitem__(n, v.clone())) if probes else None)
+    torch.cuda.synchronize()
+    out = {"noise": (rel(noise, want_noise), STEP_TOL), "seq": (rel(seq, want_seq), STEP_TOL),
+           "prep_keep": (float((db["residue_extra_mask"].cpu() - pb["residue_extra_mask"]).abs().max()), 0.0),
+           "pad_noise": (float((noise.cpu() * (1 - mask).unsqueeze(-1)).abs().max()), 0.0)}
+    if golden is not None:
+        out["noise_vs_reference"] = (rel(noise, torch.from_numpy(golden["noise_pred"])), STEP_TOL)
+        out["seq_vs_reference"] = (rel(seq, torch.from_numpy(golden["seq_pred"])), STEP_TOL)
+    for n, v in got_probes.items():
+        if n in want_probes:
+            out["probe:" + n] = (rel(v, want_probes[n]), 5e-3)
+    return out
+
+
+def case_sample(cfg=None, sizes=((8, 32), (6, 27)), seed=5, T=8, graph=True):
+    cfg = cfg or dataclasses.replace(syn.README, num_steps=T, mask_prob=0.3)
+    m, sd = _model(cfg, seed)
+    batch = syn.make_batch(cfg, list(sizes), seed=seed)
+    B, N = batch["atom_mask"].shape
+    g = torch.Generator().manual_seed(seed + 31337)
+    draws = {"z_T": torch.randn(B, N, 3, generator=g), "seq_T": torch.randn(B, N, 21, generator=g),
+             "steps": torch.randn(T - 1, B, N, 3, generator=g)}
+    order = [draws["z_T"], draws["seq_T"]] + [draws["steps"][i] for i in range(T - 1)]
+    it = iter(order)
+    torch.manual_seed(seed)
+    trace = []
+    with torch.inference_mode():
+        want_pos, want_logits = ref.sample(sd, cfg, batch, randn_like=lambda x: next(it).clone(), trace=trace)
+    torch.manual_seed(seed)
+    pos, logits = m.sample(_to_dev(batch), noise=draws, use_cuda_graph=graph)
+    torch.cuda.synchronize()
+    rmsd = float(((pos.cpu() - want_pos) ** 2).sum(-1).mean().sqrt())
+    return {"pos_rel": (rel(pos, want_pos), 5e-3), "logits_rel": (rel(logits, want_logits), 5e-3),
+            "rmsd_angstrom": (rmsd, 0.05)}
+
+
+def case_invariants(cfg=syn.PAPER, sizes=((10, 54),), seed=7):
+    """E(3) equivariance of noise_pred / invariance of seq_pred under a rigid motion of z, and batch-row
+    independence: size-independent properties checked on the CUDA path itself."""
+    m, sd = _model(cfg, seed)
+    batch = syn.make_batch(cfg, list(sizes), seed=seed)
+    z, seq_t, mask, t = syn.make_step_inputs(batch, cfg.num_steps, seed)
+    torch.manual_seed(seed)
+    db = m.prepare_batch(_to_dev(batch))
+    g = torch.Generator().manual_seed(0)
+    q, _ = torch.linalg.qr(torch.randn(3, 3, generator=g))
+    shift = torch.randn(1, 1, 3, generator=g)
+    with torch.inference_mode():
+        n0, s0 = m._denoise(db, z.to(DEV), seq_t.to(DEV), mask.to(DEV), t.to(DEV))
+        n0, s0 = n0.clone(), s0.clone()
+        n1, s1 = m._denoise(db, (z @ q + shift).to(DEV).contiguous(), seq_t.to(DEV), mask.to(DEV), t.to(DEV))
+    torch.cuda.synchronize()
+    mean = (mask.unsqueeze(-1) * n0.cpu()).sum(1) / mask.sum(1, keepdim=True)
+    return {"equivariance": (rel(n1, n0.cpu() @ q), 2e-3), "invariance": (rel(s1, s0), 2e-3),
+            "zero_mean": (float(mean.abs().max()), 1e-5)}
+
+
+CASES = {
+    "gemm_basic": lambda: case_gemm(256, 128, 64),
+    "gemm_k512": lambda: case_gemm(384, 256, 512),
+    "gemm_tails": lambda: case_gemm(200, 72, 136),
+    "gemm_n48": lambda: case_gemm(130, 48, 64),
+    "gemm_batch": lambda: case_gemm(128, 128, 128, nb1=3, nb2=2),
+    "gemm_epilogue": lambda: case_gemm(200, 136, 128, nb1=2, epilogue=True),
+    "gemm_fp16_out": lambda: case_gemm(256, 128, 256, out_fp16=True),
+    "pair_transition": lambda: case_pair_transition(),
+    "pair_transition_readme": lambda: case_pair_transition(syn.README, 2, 40),
+    "trimul_outgoing": lambda: case_trimul(mode="outgoing"),
+    "trimul_incoming": lambda: case_trimul(mode="incoming"),
+    "trimul_readme": lambda: case_trimul(syn.README, 2, 40, "incoming"),
+    "triattn_starting": lambda: case_triattn(mode="starting"),
+    "triattn_ending": lambda: case_triattn(mode="ending"),
+    "triattn_n200": lambda: case_triattn(B=1, N=200, mode="ending", pad=9),
+    "triattn_readme": lambda: case_triattn(syn.README, 2, 40, "starting"),
+    "outer_linear": lambda: case_outer_linear(),
+    "outer_linear_readme": lambda: case_outer_linear(syn.README, 2, 140),
+    "single_attention": lambda: case_single_attention(),
+    "single_transition": lambda: case_single_transition(),
+    "spattention": lambda: case_spattention(),
+    "opm": lambda: case_opm(),
+    "embeddings": lambda: case_embeddings(),
+    "embeddings_readme": lambda: case_embeddings(syn.README),
+    "heads": lambda: case_heads(),
+    "pair_bias": lambda: case_pair_bias(),
+    "step_paper_n72": lambda: case_step(probes=True),
+    "step_readme_n40": lambda: case_step(syn.README, ((8, 32), (6, 27)), seed=2),
+    "step_paper_n128": lambda: case_step(syn.PAPER, ((16, 112),), seed=4),
+    "sample_eager": lambda: case_sample(graph=False),
+    "sample_graph": lambda: case_sample(graph=True),
+    "invariants": lambda: case_invariants(),
+}

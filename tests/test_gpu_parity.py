@@ -1,0 +1,58 @@
+"""-m gpu parity tests: CUDA path (through the C ABI) vs the CPU oracle and the golden fixtures."""
+import pytest
+import torch
+
+from conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+def _cases():
+    import gpu_cases
+    return gpu_cases
+
+
+def _check(metrics):
+    bad = {k: v for k, v in metrics.items() if not (v[0] <= v[1])}
+    assert not bad, f"out of tolerance: {bad} (all: {metrics})"
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _need_gpu(cuda_device):
+    from protein_redesign_b200 import _lib
+    assert _lib.load().prd_device_check() == 0, _lib.last_error()
+
+
+CASE_NAMES = [
+    "gemm_basic", "gemm_k512", "gemm_tails", "gemm_n48", "gemm_batch", "gemm_epilogue", "gemm_fp16_out",
+    "pair_transition", "pair_transition_readme", "trimul_outgoing", "trimul_incoming", "trimul_readme",
+    "triattn_starting", "triattn_ending", "triattn_n200", "triattn_readme", "outer_linear", "outer_linear_readme",
+    "single_attention", "single_transition", "spattention", "opm", "embeddings", "embeddings_readme", "heads",
+    "pair_bias", "sample_eager", "sample_graph", "invariants",
+]
+
+
+@pytest.mark.parametrize("name", CASE_NAMES)
+def test_case(name):
+    _check(_cases().CASES[name]())
+
+
+@pytest.mark.parametrize("tag,cfg_name,sizes,seed", [
+    ("paper_n72", "PAPER", ((12, 60), (9, 50)), 3),
+    ("readme_n40", "README", ((8, 32), (6, 27)), 2),
+    ("paper_n128", "PAPER", ((16, 112),), 4),
+])
+def test_step_vs_oracle_and_reference_golden(tag, cfg_name, sizes, seed):
+    gc = _cases()
+    from protein_redesign_b200 import synthetic as syn
+    gold = load_golden(f"step_{tag}.npz")
+    _check(gc.case_step(getattr(syn, cfg_name), sizes, seed=seed, golden=gold, probes=(tag == "paper_n72")))
+
+
+def test_cpu_tensor_is_rejected():
+    """No CPU fallback: the product path must fail loudly on a CPU tensor."""
+    from protein_redesign_b200 import ops
+    from protein_redesign_b200 import synthetic as syn
+    x = torch.zeros(1, 8, 8, 64)
+    with pytest.raises(RuntimeError):
+        ops.symmetrize(syn.PAPER, x)
