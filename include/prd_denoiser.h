@@ -56,6 +56,7 @@ typedef struct PrdDims {
 int prd_version(void);
 const char* prd_last_error(void);
 int prd_device_check(void); /* 0 iff the current device is sm_100 */
+long long prd_launch_count(void); /* kernels launched by this library so far in this process */
 
 /* Plain batched GEMM on the tcgen05 path (building block + test hook):
  * C[b] = alpha * A[b] (M x K, fp16) * B[b]^T (N x K, fp16), fp32 accumulate, optional epilogue. */
@@ -144,6 +145,12 @@ PRD_DECLARE_OP(remove_mean)
 /* model.py:407-420 one reverse step on device (see csrc/prd_embed.cu).
  * in: [noise_pred | seq_pred | noise f32 steps,B,N,3 | coef f32 T,3]  out: [z | seq_t | sampler_state int32[2]] */
 PRD_DECLARE_OP(sampler_update)
+
+/* Profiling hook used by bench.py: average duration (ms) of ONE named kernel ("triattn_flash",
+ * "trimul_gemm", "pair_bias") over `iters` launches on the data a previous full op left in the
+ * workspace; CUDA events on `stream`.  aux: mask (triattn_flash) / pair (pair_bias). */
+int prd_profile_kernel(const char* name, const PrdDims* d, void* workspace, size_t workspace_bytes,
+                       const void* aux, int iters, float* ms_out, void* stream);
 
 #undef PRD_DECLARE_OP
 

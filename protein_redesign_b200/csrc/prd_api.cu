@@ -5,6 +5,8 @@
 #include "prd_embed.h"
 #include "prd_kernels.h"
 
+#include <string>
+
 using namespace prd;
 
 namespace {
@@ -409,6 +411,63 @@ int prd_triangle_attention_fwd(const PrdDims* d, const void* const* in, void* co
   if (triattn_flash(pd(d), in_ptr<float>(in, 1), s.q, s.k, s.g, s.vt, s.og, st)) return 1;
   return triattn_out(pd(d), pair, out_ptr<float>(out, 0), d->residual, d->mode, s.og, in_ptr<__half>(w, 2),
                      in_ptr<float>(w, 3), st);
+}
+
+// -------------------------------------------------------------------------- profiling hook
+// Runs one named kernel `iters` times on the data a previous full op left in the workspace and
+// returns its average duration (CUDA events on `stream`).  aux: "triattn_flash" -> mask [B,N];
+// "pair_bias" -> pair [B,N,N,c_z]; "trimul_gemm" -> unused.
+int prd_profile_kernel(const char* name, const PrdDims* d, void* workspace, size_t workspace_bytes, const void* aux,
+                       int iters, float* ms_out, void* stream) {
+  if (prd_device_check()) return 1;
+  PRD_REQUIRE(iters > 0 && ms_out != nullptr, "profile_kernel: bad arguments");
+  cudaStream_t st = S(stream);
+  cudaEvent_t e0, e1;
+  PRD_CUDA_OK(cudaEventCreate(&e0));
+  PRD_CUDA_OK(cudaEventCreate(&e1));
+  int rc = 0;
+  const std::string n(name);
+  auto run = [&]() -> int {
+    if (n == "triattn_flash") {
+      PRD_WS_CHECK(prd_triangle_attention_workspace_bytes(d));
+      TaWs s = ta_carve(d, workspace);
+      return triattn_flash(pd(d), static_cast<const float*>(aux), s.q, s.k, s.g, s.vt, s.og, st);
+    }
+    if (n == "trimul_gemm") {
+      PRD_WS_CHECK(prd_triangle_multiplication_workspace_bytes(d));
+      TmWs s = tm_carve(d, workspace);
+      const int N = d->N, Np = plane_ld(N), Nx = xplane_ld(N);
+      GemmArgs g;
+      g.M = N; g.N = N; g.K = N; g.nb1 = d->B * d->c_z;
+      g.A = s.ab; g.lda = Np; g.a_bs1 = (long long)N * Np;
+      g.B = s.ab + (size_t)d->B * d->c_z * N * Np; g.ldb = Np; g.b_bs1 = (long long)N * Np;
+      g.C = s.x; g.ldc = Nx; g.c_bs1 = (long long)N * Nx;
+      return gemm_f16(g, st);
+    }
+    if (n == "pair_bias") {
+      PRD_WS_CHECK(prd_single_attention_workspace_bytes(d));
+      SaWs s = sa_carve(d, workspace);
+      const float* pair = static_cast<const float*>(aux);
+      return pair_bias_proj(pd(d), d->H, pair, nullptr, nullptr, pair, nullptr, s.bias, st);
+    }
+    set_error("profile_kernel: unknown kernel '%s'", name);
+    return 1;
+  };
+  rc = run();  // warm-up
+  if (rc == 0) {
+    cudaEventRecord(e0, st);
+    for (int i = 0; i < iters && rc == 0; ++i) rc = run();
+    cudaEventRecord(e1, st);
+    if (rc == 0 && check_cuda(cudaEventSynchronize(e1), "cudaEventSynchronize")) rc = 1;
+    float ms = 0.f;
+    if (rc == 0) {
+      cudaEventElapsedTime(&ms, e0, e1);
+      *ms_out = ms / iters;
+    }
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  return rc;
 }
 
 // ------------------------------------------------------------------------- pair_transition

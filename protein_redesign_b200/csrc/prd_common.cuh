@@ -36,6 +36,14 @@ int check_cuda(cudaError_t e, const char* what);
     }                                                       \
   } while (0)
 
+// count of kernels launched by this library in this process (prd_launch_count())
+extern long long g_launches;
+#define PRD_LAUNCHED()                       \
+  do {                                       \
+    ++::prd::g_launches;                     \
+    PRD_CUDA_OK(cudaGetLastError());         \
+  } while (0)
+
 constexpr int kNumSMs = 148;
 
 // ---------------------------------------------------------------------------------------

@@ -49,7 +49,7 @@ int single_embed(int B, int N, int CS, const int64_t* atom_feats, const float* a
                  const float* seq_t, const float* esm_emb, const AtomTables& tabs, const float* w_type, float* single,
                  cudaStream_t s) {
   single_embed_kernel<<<B * N, 128, 0, s>>>(CS, atom_feats, atom_mask, residue_mask, seq_t, esm_emb, tabs, w_type, single);
-  PRD_CUDA_OK(cudaGetLastError());
+  PRD_LAUNCHED();
   return 0;
 }
 
@@ -80,7 +80,7 @@ __global__ void time_embed_kernel(int CZ, int TD, const int64_t* __restrict__ t,
 int time_embed(int B, int CZ, int TD, const int64_t* t, const SamplerState* st, int num_steps, const float* freq,
                const float* w_beta, float* beta, cudaStream_t s) {
   time_embed_kernel<<<B, 64, TD * sizeof(float), s>>>(CZ, TD, t, st, num_steps, freq, w_beta, beta);
-  PRD_CUDA_OK(cudaGetLastError());
+  PRD_LAUNCHED();
   return 0;
 }
 
@@ -132,9 +132,9 @@ int sampler_update(int B, int N, const float* eps, const float* seq_pred, const 
                    SamplerState* st, float* z, float* seq_t, cudaStream_t s) {
   const long long n_tok = (long long)B * N;
   sampler_update_kernel<<<(unsigned)((n_tok + 127) / 128), 128, 0, s>>>(n_tok, eps, seq_pred, noise, coef, st, z, seq_t);
-  PRD_CUDA_OK(cudaGetLastError());
+  PRD_LAUNCHED();
   sampler_advance_kernel<<<1, 32, 0, s>>>(st);
-  PRD_CUDA_OK(cudaGetLastError());
+  PRD_LAUNCHED();
   return 0;
 }
 

@@ -209,7 +209,7 @@ static int launch_gemm(const GemmArgs& g, cudaStream_t stream) {
   const int num_kb = (g.K + 63) / 64;
   kern<<<grid, 192, L::kTotal, stream>>>(map_a, map_b, num_kb, nb1, g.a_bs1 != 0 ? 1 : 0, g.a_bs2 != 0 ? 1 : 0,
                                          g.b_bs1 != 0 ? 1 : 0, g.b_bs2 != 0 ? 1 : 0, ep);
-  PRD_CUDA_OK(cudaGetLastError());
+  PRD_LAUNCHED();
   return 0;
 }
 

@@ -11,6 +11,7 @@
 namespace prd {
 
 static thread_local char g_error[512] = "";
+long long g_launches = 0;
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -82,15 +83,21 @@ int prd_version(void) { return PRD_VERSION; }
 
 const char* prd_last_error(void) { return prd::g_error; }
 
+long long prd_launch_count(void) { return prd::g_launches; }
+
 int prd_device_check(void) {
+  static int cached[64] = {0};  // per device: 0 unknown, 1 ok, 2 wrong architecture
   int dev = 0;
-  cudaDeviceProp prop;
   if (prd::check_cuda(cudaGetDevice(&dev), "cudaGetDevice")) return 1;
-  if (prd::check_cuda(cudaGetDeviceProperties(&prop, dev), "cudaGetDeviceProperties")) return 1;
-  if (prop.major != 10) {
-    prd::set_error("libprd_sm100 needs an sm_100 (B200) device, found sm_%d%d (%s)", prop.major, prop.minor, prop.name);
+  if (dev >= 0 && dev < 64 && cached[dev] == 1) return 0;
+  int major = 0, minor = 0;
+  if (prd::check_cuda(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev), "cudaDeviceGetAttribute")) return 1;
+  if (prd::check_cuda(cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev), "cudaDeviceGetAttribute")) return 1;
+  if (major != 10) {
+    prd::set_error("libprd_sm100 needs an sm_100 (B200) device, found sm_%d%d", major, minor);
     return 1;
   }
+  if (dev >= 0 && dev < 64) cached[dev] = 1;
   return 0;
 }
 

@@ -167,7 +167,7 @@ int outer_linear(const PairDims& d, int CS, const float* pair, float* dst, int r
     set_error("outer_linear: unsupported pair_dim %d", d.CZ);
     return 1;
   }
-  PRD_CUDA_OK(cudaGetLastError());
+  PRD_LAUNCHED();
   return 0;
 }
 
@@ -344,7 +344,7 @@ int pair_embed_dynamic(const PairDims& d, const float* pair_static, float* pair,
     set_error("pair_embed: unsupported pair_dim %d", d.CZ);
     return 1;
   }
-  PRD_CUDA_OK(cudaGetLastError());
+  PRD_LAUNCHED();
   return 0;
 }
 
@@ -480,7 +480,7 @@ int coord_head(const PairDims& d, const float* pair, const float* z, const float
     set_error("coord_head: unsupported pair_dim %d", d.CZ);
     return 1;
   }
-  PRD_CUDA_OK(cudaGetLastError());
+  PRD_LAUNCHED();
   return 0;
 }
 

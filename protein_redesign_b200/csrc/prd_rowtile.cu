@@ -172,7 +172,7 @@ static int launch_pair_transition(const PairDims& d, const float* pair, float* d
   const long long R = (long long)d.B * d.N * d.N;
   const long long tiles = (R + kTileRows - 1) / kTileRows;
   kern<<<grid_for(tiles, 1), 128, smem, s>>>(pair, dst, residual, R, w1, b1, w2, b2);
-  PRD_CUDA_OK(cudaGetLastError());
+  PRD_LAUNCHED();
   return 0;
 }
 
@@ -314,7 +314,7 @@ int trimul_in(const PairDims& d, const float* pair, const float* mask, int mode,
     set_error("trimul_in: unsupported pair_dim %d", d.CZ);
     return 1;
   }
-  PRD_CUDA_OK(cudaGetLastError());
+  PRD_LAUNCHED();
   return 0;
 }
 
@@ -471,7 +471,7 @@ int trimul_out(const PairDims& d, const float* pair, float* dst, int residual, c
     set_error("trimul_out: unsupported pair_dim %d", d.CZ);
     return 1;
   }
-  PRD_CUDA_OK(cudaGetLastError());
+  PRD_LAUNCHED();
   return 0;
 }
 
@@ -616,7 +616,7 @@ int triattn_proj(const PairDims& d, const float* pair, int mode, const __half* w
     set_error("triattn_proj: unsupported pair_dim %d", d.CZ);
     return 1;
   }
-  PRD_CUDA_OK(cudaGetLastError());
+  PRD_LAUNCHED();
   return 0;
 }
 
@@ -747,7 +747,7 @@ int triattn_out(const PairDims& d, const float* pair, float* dst, int residual, 
     set_error("triattn_out: unsupported pair_dim %d", d.CZ);
     return 1;
   }
-  PRD_CUDA_OK(cudaGetLastError());
+  PRD_LAUNCHED();
   return 0;
 }
 

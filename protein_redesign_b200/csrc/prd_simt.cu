@@ -38,7 +38,7 @@ int layernorm_rows(const float* x, int rows, int C, const float* gamma, const fl
   const int threads = 256;
   const int blocks = (rows * 32 + threads - 1) / threads;
   layernorm_rows_kernel<<<blocks, threads, 0, s>>>(x, rows, C, gamma, beta, out16, out32);
-  PRD_CUDA_OK(cudaGetLastError());
+  PRD_LAUNCHED();
   return 0;
 }
 
@@ -138,7 +138,7 @@ int pair_bias_proj(const PairDims& d, int H, const float* pair, const float* ln_
     set_error("pair_bias_proj: unsupported pair_dim %d", d.CZ);
     return 1;
   }
-  PRD_CUDA_OK(cudaGetLastError());
+  PRD_LAUNCHED();
   return 0;
 }
 
@@ -166,7 +166,7 @@ int softmax_rows(float* logits, __half* probs, long long rows, int n, int ld_in,
   const int threads = 256;
   const long long blocks = (rows * 32 + threads - 1) / threads;
   softmax_rows_kernel<<<(unsigned)blocks, threads, 0, s>>>(logits, probs, rows, n, ld_in, ld_out);
-  PRD_CUDA_OK(cudaGetLastError());
+  PRD_LAUNCHED();
   return 0;
 }
 
@@ -256,7 +256,7 @@ int single_attention(int B, int N, int H, int c, const float* qkvg, const float*
   PRD_CUDA_OK(cudaFuncSetAttribute(single_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   dim3 grid((N + 127) / 128, H, B);
   single_attention_kernel<<<grid, 128, smem, s>>>(N, H, qkvg, bias, mask, og);
-  PRD_CUDA_OK(cudaGetLastError());
+  PRD_LAUNCHED();
   return 0;
 }
 
@@ -285,7 +285,7 @@ int symmetrize_pair(const PairDims& d, float* pair, cudaStream_t s) {
   const int CZ4 = d.CZ / 4;
   const long long total = (long long)d.B * d.N * d.N * CZ4;
   symmetrize_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(pair, d.N, CZ4, total);
-  PRD_CUDA_OK(cudaGetLastError());
+  PRD_LAUNCHED();
   return 0;
 }
 
@@ -326,7 +326,7 @@ int remove_mean3(int B, int N, int C, float* x, const float* mask, int mask_rows
   PRD_REQUIRE(C >= 1 && C <= 32, "remove_mean: channel count %d not in [1,32]", C);
   PRD_REQUIRE(mask_rows >= 1, "remove_mean: mask_rows %d", mask_rows);
   remove_mean_kernel<<<B, 256, 0, s>>>(N, C, x, mask, mask_rows);
-  PRD_CUDA_OK(cudaGetLastError());
+  PRD_LAUNCHED();
   return 0;
 }
 
@@ -395,7 +395,7 @@ int embed_pair_static(const PairDims& d, const float* atom_mask, const float* re
   embed_pair_static_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(
       d.N, CZ4, total, atom_mask, residue_mask, bond_mask, bond_feats, bond_distance, residue_index, chain_index, bt,
       bdist_table, max_bond_distance, relpos_table, max_relpos, out);
-  PRD_CUDA_OK(cudaGetLastError());
+  PRD_LAUNCHED();
   return 0;
 }
 

@@ -213,7 +213,7 @@ int triattn_flash(const PairDims& d, const float* mask, const __half* q, const _
   PRD_REQUIRE(nseq * nkt <= 2147483647LL, "triattn_flash: grid overflow");
   dim3 grid((unsigned)(nseq * nkt));
   triattn_flash_kernel<<<grid, 128, smem, s>>>(mq, mk, mv, mask, g, og, N);
-  PRD_CUDA_OK(cudaGetLastError());
+  PRD_LAUNCHED();
   return 0;
 }
 
