@@ -190,6 +190,15 @@ def run_ours(args):
     def reset_state():
         state.copy_(torch.tensor([T - 1, 0], dtype=torch.int32))
 
+    if args.profile_eager:
+        with torch.inference_mode():
+            model._static_embeddings(batch)
+            for _ in range(args.warmup + args.steps):
+                one_step()
+            torch.cuda.synchronize()
+        print(json.dumps({"profile_eager": True, "steps": args.steps, "warmup": args.warmup}))
+        return
+
     with torch.inference_mode():
         model._static_embeddings(batch)
         one_step()
@@ -322,6 +331,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-eager", action="store_true",
+                    help="run the steps eagerly (no CUDA graph, no e2e / CPU legs): for ncu launch lists")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

@@ -19,13 +19,21 @@ def f32(t: torch.Tensor) -> torch.Tensor:
     return t.detach().to(torch.float32).contiguous()
 
 
+def tensor_version(t: torch.Tensor) -> int:
+    """In-place modification counter; inference tensors do not track one."""
+    try:
+        return t._version
+    except RuntimeError:
+        return -1
+
+
 class PackCache:
     def __init__(self):
         self._key = None
         self._value = None
 
     def get(self, sources: Sequence[torch.Tensor], build: Callable[[], object]):
-        key = tuple((t.data_ptr(), t._version, t.device) for t in sources)
+        key = tuple((t.data_ptr(), tensor_version(t), t.device) for t in sources)
         if key != self._key:
             for t in sources:
                 if not t.is_cuda:

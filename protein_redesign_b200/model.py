@@ -22,7 +22,7 @@ import torch.nn.functional as F
 from torch import nn
 
 from . import ops
-from ._packing import PackCache, f32, half
+from ._packing import PackCache, f32, half, tensor_version
 from .modules import AtomEmbedding, BondEmbedding, Denoiser, Linear, RadialBasisProjection, SinusoidalProjection
 from .synthetic import NUM_RESIDUE_CLASSES, DenoiserConfig
 
@@ -241,7 +241,7 @@ class ProteinReDiffModel(_Base):
     def _static_embeddings(self, batch):
         keys = ("residue_esm", "bond_feats", "bond_mask", "bond_distance", "residue_index", "residue_chain_index",
                 "atom_mask", "residue_mask")
-        key = tuple((batch[k].data_ptr(), batch[k]._version) for k in keys) + (id(self._weights()),)
+        key = tuple((batch[k].data_ptr(), tensor_version(batch[k])) for k in keys) + (id(self._weights()),)
         if key != self._static_key:
             w = self._weights()
             b = {k: batch[k].contiguous() for k in keys}
