@@ -44,3 +44,23 @@ class PackCache:
                 self._value = build()
             self._key = key
         return self._value
+
+
+def split_rows(w: torch.Tensor) -> torch.Tensor:
+    """fp16 pair (hi, lo) of an fp32 weight [rows, K], stacked along rows -> [2*rows, K].
+
+    w ~= hi + lo to ~22 bits: the kernels run the activation against both halves, which removes
+    the *systematic* error a single fp16 rounding of the weights would add to every row
+    (tools/precision_study.py)."""
+    w = w.detach().to(torch.float32)
+    hi = w.to(torch.float16)
+    lo = (w - hi.to(torch.float32)).to(torch.float16)
+    return torch.cat([hi, lo], dim=0).contiguous()
+
+
+def split_k(w: torch.Tensor) -> torch.Tensor:
+    """Same pair stored along K: [rows, 2K] = [hi | lo] (layout of the GEMM's split operand)."""
+    w = w.detach().to(torch.float32)
+    hi = w.to(torch.float16)
+    lo = (w - hi.to(torch.float32)).to(torch.float16)
+    return torch.cat([hi, lo], dim=1).contiguous()

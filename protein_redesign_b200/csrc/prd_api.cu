@@ -38,12 +38,13 @@ const T* in_ptr(const void* const* a, int i) { return static_cast<const T*>(a[i]
 template <typename T>
 T* out_ptr(void* const* a, int i) { return static_cast<T*>(a[i]); }
 
-// y[M,N] = epilogue(x16[M,K] . w16[N,K]^T)
+// y[M,N] = epilogue(x16[M,K] . w[N,K]^T) with the weight stored as an fp16 pair [hi | lo] along K
+// (w16 is [N, 2K]): activations keep one fp16 rounding (random, averages out), weights keep ~22 bits.
 GemmArgs linear_args(int M, int N, int K, const __half* x16, const __half* w16, void* C, int c_fp16) {
   GemmArgs g;
   g.M = M; g.N = N; g.K = K;
   g.A = x16; g.lda = K;
-  g.B = w16; g.ldb = K;
+  g.B = w16; g.ldb = 2 * K; g.split = 1;
   g.C = C; g.ldc = N; g.c_fp16 = c_fp16;
   return g;
 }
@@ -206,8 +207,8 @@ int prd_spattention_fwd(const PrdDims* d, const void* const* in, void* const* ou
   }
   {  // v^T[b] = W_v . x[b]^T  -> [B][H*CS][Np] fp16 (keys contiguous): A = W_v, B = x[b]
     GemmArgs g;
-    g.M = HC; g.N = N; g.K = CS; g.nb1 = B;
-    g.A = in_ptr<__half>(w, 7); g.lda = CS;
+    g.M = HC; g.N = N; g.K = CS; g.nb1 = B; g.split = 2;
+    g.A = in_ptr<__half>(w, 7); g.lda = 2 * CS;
     g.B = s.xn16; g.ldb = CS; g.b_bs1 = (long long)N * CS;
     g.C = s.vt; g.ldc = Np; g.c_bs1 = (long long)HC * Np; g.c_fp16 = 1;
     if (gemm_f16(g, st)) return 1;

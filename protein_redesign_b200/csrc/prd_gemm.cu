@@ -40,7 +40,10 @@ struct GemmEpilogue {
 template <int BN, int STAGES>
 __global__ void __launch_bounds__(192, 1)
 gemm_f16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, int num_kb,
-                int nb1, int a_b1, int a_b2, int b_b1, int b_b2, GemmEpilogue ep) {
+                int a_wrap, int b_wrap, int nb1, int a_b1, int a_b2, int b_b1, int b_b2, GemmEpilogue ep) {
+  // a_wrap / b_wrap: K-blocks after which that operand's K coordinate wraps to 0.  With a weight
+  // stored as [hi | lo] along K (fp16 pair, removes the systematic weight rounding) the activation
+  // operand is simply read twice: sum_k x_k (w_hi + w_lo)_k.
   extern __shared__ uint8_t smem_raw[];
   using L = GemmSmem<BN, STAGES>;
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -79,8 +82,8 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         mbar_wait(&empty[s], ph ^ 1);
         mbar_expect_tx(&full[s], L::kStageBytes);
         uint8_t* sa = smem + s * L::kStageBytes;
-        tma_load_4d(sa, &map_a, &full[s], kb * 64, m0, i1 * a_b1, i2 * a_b2);
-        tma_load_4d(sa + L::kABytes, &map_b, &full[s], kb * 64, n0, i1 * b_b1, i2 * b_b2);
+        tma_load_4d(sa, &map_a, &full[s], (kb % a_wrap) * 64, m0, i1 * a_b1, i2 * a_b2);
+        tma_load_4d(sa + L::kABytes, &map_b, &full[s], (kb % b_wrap) * 64, n0, i1 * b_b1, i2 * b_b2);
       }
     }
   } else if (warp == 1) {
@@ -170,8 +173,10 @@ static int launch_gemm(const GemmArgs& g, cudaStream_t stream) {
   CUtensorMap map_a, map_b;
   TmaDims da, db;
   const int nb1 = g.nb1 > 0 ? g.nb1 : 1, nb2 = g.nb2 > 0 ? g.nb2 : 1;
-  auto fill = [&](TmaDims& d, long long rows, long long ld, long long bs1, long long bs2, int box_rows) {
-    d.size[0] = (uint64_t)g.K;
+  const int kb_half = (g.K + 63) / 64;
+  if (g.split != 0) PRD_REQUIRE(g.K % 64 == 0, "gemm: split weights need K %% 64 == 0 (K=%d)", g.K);
+  auto fill = [&](TmaDims& d, long long rows, long long ld, long long bs1, long long bs2, int box_rows, bool is_split) {
+    d.size[0] = (uint64_t)(is_split ? 2 * g.K : g.K);
     d.size[1] = (uint64_t)rows;
     d.size[2] = bs1 != 0 ? (uint64_t)nb1 : 1;
     d.size[3] = bs2 != 0 ? (uint64_t)nb2 : 1;
@@ -189,8 +194,8 @@ static int launch_gemm(const GemmArgs& g, cudaStream_t stream) {
   PRD_REQUIRE(g.M > 0 && g.N > 0 && g.K > 0, "gemm: empty problem M=%d N=%d K=%d", g.M, g.N, g.K);
   PRD_REQUIRE(g.lda % 8 == 0 && g.ldb % 8 == 0, "gemm: lda/ldb must be multiples of 8 halves (lda=%lld ldb=%lld)", g.lda, g.ldb);
   PRD_REQUIRE((g.a_bs1 % 8 == 0) && (g.a_bs2 % 8 == 0) && (g.b_bs1 % 8 == 0) && (g.b_bs2 % 8 == 0), "gemm: batch strides must be multiples of 8 halves");
-  fill(da, g.M, g.lda, g.a_bs1, g.a_bs2, 128);
-  fill(db, g.N, g.ldb, g.b_bs1, g.b_bs2, BN);
+  fill(da, g.M, g.lda, g.a_bs1, g.a_bs2, 128, g.split == 2);
+  fill(db, g.N, g.ldb, g.b_bs1, g.b_bs2, BN, g.split == 1);
   if (make_tensor_map(&map_a, g.A, 2, 4, da, true)) return 1;
   if (make_tensor_map(&map_b, g.B, 2, 4, db, true)) return 1;
   GemmEpilogue ep;
@@ -206,8 +211,10 @@ static int launch_gemm(const GemmArgs& g, cudaStream_t stream) {
     attr_set = true;
   }
   dim3 grid((g.N + BN - 1) / BN, (g.M + 127) / 128, nb1 * nb2);
-  const int num_kb = (g.K + 63) / 64;
-  kern<<<grid, 192, L::kTotal, stream>>>(map_a, map_b, num_kb, nb1, g.a_bs1 != 0 ? 1 : 0, g.a_bs2 != 0 ? 1 : 0,
+  const int num_kb = g.split != 0 ? 2 * kb_half : kb_half;
+  const int a_wrap = g.split == 1 ? kb_half : num_kb;
+  const int b_wrap = g.split == 2 ? kb_half : num_kb;
+  kern<<<grid, 192, L::kTotal, stream>>>(map_a, map_b, num_kb, a_wrap, b_wrap, nb1, g.a_bs1 != 0 ? 1 : 0, g.a_bs2 != 0 ? 1 : 0,
                                          g.b_bs1 != 0 ? 1 : 0, g.b_bs2 != 0 ? 1 : 0, ep);
   PRD_LAUNCHED();
   return 0;

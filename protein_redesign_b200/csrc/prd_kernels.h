@@ -27,6 +27,8 @@ struct GemmArgs {
   void* C = nullptr;  // fp32 or fp16 [M, N]
   long long ldc = 0, c_bs1 = 0, c_bs2 = 0;
   int c_fp16 = 0;
+  // 0: plain.  1: B is a weight stored as [hi | lo] along K (ldb >= 2K).  2: same for A.
+  int split = 0;
 };
 // v = alpha*acc (+bias) -> act -> *rowscale -> *mul -> +add
 int gemm_f16(const GemmArgs& g, cudaStream_t stream);

@@ -192,8 +192,8 @@ pair_embed_kernel(const float* __restrict__ pstatic, float* __restrict__ pair, c
   uint8_t* sm = smem_align1024(raw);
   uint8_t* sA1 = sm;                         // rbf, KBD x 16 KB
   uint8_t* sA2 = sA1 + KBD * 16384;          // a_i*b_j, KBO x 16 KB
-  uint8_t* sW1 = sA2 + KBO * 16384;          // W_dist, KBD x [CZ x 64]
-  uint8_t* sW2 = sW1 + KBD * CZ * 128;       // W_opm,  KBO x [CZ x 64]
+  uint8_t* sW1 = sA2 + KBO * 16384;          // W_dist hi then lo, each KBD x [CZ x 64]
+  uint8_t* sW2 = sW1 + 2 * KBD * CZ * 128;   // W_opm,  KBO x [CZ x 64]
   uint8_t* sSt = sW2 + KBO * CZ * 128;       // one padded row stage
   float* sC = reinterpret_cast<float*>(sSt + RowStage<CZ>::kBytes);  // centers [DD]
   float* sBo = sC + DD;                                            // b_opm [CZ]
@@ -209,7 +209,10 @@ pair_embed_kernel(const float* __restrict__ pstatic, float* __restrict__ pair, c
     fence_barrier_init();
   }
   if (warp == 0) tmem_alloc(tmem_slot, TCOLS);
-  if (with_dist) load_weight_kblocks(sW1, w_dist, CZ, DD, DD, t, 128);
+  if (with_dist) {
+    load_weight_kblocks(sW1, w_dist, CZ, DD, DD, t, 128);
+    load_weight_kblocks(sW1 + KBD * CZ * 128, w_dist + CZ * DD, CZ, DD, DD, t, 128);
+  }
   load_weight_kblocks(sW2, w_opm, CZ, OD, OD, t, 128);
   if (with_dist)
     for (int i = t; i < DD; i += 128) sC[i] = centers[i];
@@ -269,7 +272,10 @@ pair_embed_kernel(const float* __restrict__ pstatic, float* __restrict__ pair, c
     sync_before_mma();
     if (t == 0) {
       tc_fence_after();
-      if (with_dist) umma_multi(tmem, smem_u32(sA1), smem_u32(sW1), KBD, CZ * 128, umma_idesc_f16(128, CZ), false);
+      if (with_dist) {
+        umma_multi(tmem, smem_u32(sA1), smem_u32(sW1), KBD, CZ * 128, umma_idesc_f16(128, CZ), false);
+        umma_multi(tmem, smem_u32(sA1), smem_u32(sW1 + KBD * CZ * 128), KBD, CZ * 128, umma_idesc_f16(128, CZ), true);
+      }
       umma_multi(tmem + CZ, smem_u32(sA2), smem_u32(sW2), KBO, CZ * 128, umma_idesc_f16(128, CZ), false);
       umma_commit(mma_bar);
     }
@@ -326,7 +332,7 @@ int pair_embed_dynamic(const PairDims& d, const float* pair_static, float* pair,
   const int grid = (int)(tiles < kNumSMs ? tiles : kNumSMs);
   if (d.CZ == 64) {
     constexpr int CZ = 64;
-    const int smem = 1024 + (KBD + KBO) * 16384 + (KBD + KBO) * CZ * 128 + RowStage<CZ>::kBytes + (dist_dim + CZ) * 4 + 64;
+    const int smem = 1024 + (KBD + KBO) * 16384 + (2 * KBD + KBO) * CZ * 128 + RowStage<CZ>::kBytes + (dist_dim + CZ) * 4 + 64;
     PRD_REQUIRE(smem <= 227 * 1024, "pair_embed: shared memory %d B exceeds 227 KB", smem);
     auto kern = pair_embed_kernel<CZ>;
     PRD_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -334,7 +340,7 @@ int pair_embed_dynamic(const PairDims& d, const float* pair_static, float* pair,
                                  opm_dim, w_opm, b_opm, d.N, R, flags);
   } else if (d.CZ == 32) {
     constexpr int CZ = 32;
-    const int smem = 1024 + (KBD + KBO) * 16384 + (KBD + KBO) * CZ * 128 + RowStage<CZ>::kBytes + (dist_dim + CZ) * 4 + 64;
+    const int smem = 1024 + (KBD + KBO) * 16384 + (2 * KBD + KBO) * CZ * 128 + RowStage<CZ>::kBytes + (dist_dim + CZ) * 4 + 64;
     PRD_REQUIRE(smem <= 227 * 1024, "pair_embed: shared memory %d B exceeds 227 KB", smem);
     auto kern = pair_embed_kernel<CZ>;
     PRD_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -361,8 +367,8 @@ coord_head_kernel(const float* __restrict__ pair, const float* __restrict__ z, c
   extern __shared__ uint8_t raw[];
   uint8_t* sm = smem_align1024(raw);
   uint8_t* sA = sm;
-  uint8_t* sW = sA + 16384;
-  uint8_t* sSt = sW + CZ * 128;  // two stages: row (i,j) and transposed row (j,i)
+  uint8_t* sW = sA + 16384;          // W1 hi then lo
+  uint8_t* sSt = sW + 2 * CZ * 128;  // two stages: row (i,j) and transposed row (j,i)
   float* sB1 = reinterpret_cast<float*>(sSt + 2 * RowStage<CZ>::kBytes);
   float* sW2 = sB1 + CZ;
   float* sRed = sW2 + CZ;  // [4 warps][3]
@@ -380,6 +386,7 @@ coord_head_kernel(const float* __restrict__ pair, const float* __restrict__ z, c
   }
   if (warp == 0) tmem_alloc(tmem_slot, TCOLS);
   load_weight_kblocks(sW, w1, CZ, CZ, CZ, t, 128);
+  load_weight_kblocks(sW + CZ * 128, w1 + CZ * CZ, CZ, CZ, CZ, t, 128);
   for (int q = t; q < CZ; q += 128) {
     sB1[q] = b1[q];
     sW2[q] = w2[q];
@@ -420,6 +427,7 @@ coord_head_kernel(const float* __restrict__ pair, const float* __restrict__ z, c
     if (t == 0) {
       tc_fence_after();
       umma_multi(tmem, smem_u32(sA), smem_u32(sW), 1, CZ * 128, umma_idesc_f16(128, CZ), false);
+      umma_multi(tmem, smem_u32(sA), smem_u32(sW + CZ * 128), 1, CZ * 128, umma_idesc_f16(128, CZ), true);
       umma_commit(mma_bar);
     }
     mbar_wait(mma_bar, mma_phase);
@@ -466,13 +474,13 @@ int coord_head(const PairDims& d, const float* pair, const float* z, const float
   const int grid = d.B * d.N;
   if (d.CZ == 64) {
     constexpr int CZ = 64;
-    constexpr int smem = 1024 + 16384 + CZ * 128 + 2 * RowStage<CZ>::kBytes + (2 * CZ + 16) * 4 + 64;
+    constexpr int smem = 1024 + 16384 + 2 * CZ * 128 + 2 * RowStage<CZ>::kBytes + (2 * CZ + 16) * 4 + 64;
     auto kern = coord_head_kernel<CZ>;
     PRD_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     kern<<<grid, 128, smem, s>>>(pair, z, mask, w1, b1, w2, eps_raw, d.N);
   } else if (d.CZ == 32) {
     constexpr int CZ = 32;
-    constexpr int smem = 1024 + 16384 + CZ * 128 + 2 * RowStage<CZ>::kBytes + (2 * CZ + 16) * 4 + 64;
+    constexpr int smem = 1024 + 16384 + 2 * CZ * 128 + 2 * RowStage<CZ>::kBytes + (2 * CZ + 16) * 4 + 64;
     auto kern = coord_head_kernel<CZ>;
     PRD_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     kern<<<grid, 128, smem, s>>>(pair, z, mask, w1, b1, w2, eps_raw, d.N);

@@ -38,36 +38,59 @@ inline int grid_for(long long tiles, int ctas_per_sm) {
 }  // namespace
 
 // =========================================================================================
-// pair_fc: pair += W2 relu(W1 LN(pair) + b1) + b2
+// pair_fc: dst = [pair +] W2 relu(W1 LN(pair) + b1) + b2
+// Both weights are fp16 hi + lo pairs (w1: [2][HID][CZ], w2: [2][CZ][HID]); the hidden layer is
+// processed in two halves so that A, the hidden tile, both split weights and one row stage fit
+// in shared memory.  The row itself stays in registers for the residual; the single stage is
+// re-armed for the next tile as soon as the row has been read (prefetch), and the hidden-tile
+// buffer doubles as the output staging area.
 // =========================================================================================
+template <int CZ, int HID>
+struct PairFcSmem {
+  static constexpr int HH = HID / 2;        // hidden columns per half
+  static constexpr int KBHH = HH / 64;      // K-blocks per half
+  static constexpr int KBH = HID / 64;
+  static constexpr int kHBytes = (KBHH * 16384 > RowStage<CZ>::kBytes ? KBHH * 16384 : RowStage<CZ>::kBytes + 1023) / 1024 * 1024;
+  static constexpr int kA = 0;
+  static constexpr int kH = kA + 16384;
+  static constexpr int kW1 = kH + kHBytes;                 // hi, lo: 2 * HID * 128
+  static constexpr int kW2 = kW1 + 2 * HID * 128;          // hi, lo: 2 * KBH * CZ * 128
+  static constexpr int kStage = kW2 + 2 * KBH * CZ * 128;
+  static constexpr int kBias = kStage + RowStage<CZ>::kBytes;
+  static constexpr int kBars = kBias + (HID + CZ) * 4;
+  static constexpr int kTotal = kBars + 64 + 1024;
+  static constexpr int kTmemCols = (HID + CZ) <= 256 ? 256 : 512;
+};
+
 template <int CZ, int HID>
 __global__ void __launch_bounds__(128, 1)
 pair_transition_kernel(const float* pair, float* dst, int residual, long long R, const __half* __restrict__ w1,
                        const float* __restrict__ b1, const __half* __restrict__ w2, const float* __restrict__ b2) {
   extern __shared__ uint8_t raw[];
-  constexpr int KBH = HID / 64;
+  using L = PairFcSmem<CZ, HID>;
   uint8_t* sm = smem_align1024(raw);
-  uint8_t* sA = sm;
-  uint8_t* sH = sA + 16384;
-  uint8_t* sW1 = sH + KBH * 16384;
-  uint8_t* sW2 = sW1 + HID * 128;
-  uint8_t* sSt = sW2 + KBH * CZ * 128;
-  float* sB1 = reinterpret_cast<float*>(sSt + 2 * RowStage<CZ>::kBytes);
+  uint8_t* sA = sm + L::kA;
+  uint8_t* sH = sm + L::kH;
+  uint8_t* sW1 = sm + L::kW1;
+  uint8_t* sW2 = sm + L::kW2;
+  uint8_t* sSt = sm + L::kStage;
+  float* sB1 = reinterpret_cast<float*>(sm + L::kBias);
   float* sB2 = sB1 + HID;
-  uint64_t* full = reinterpret_cast<uint64_t*>(sB2 + CZ);
-  uint64_t* mma_bar = full + 2;
+  uint64_t* full = reinterpret_cast<uint64_t*>(sm + L::kBars);
+  uint64_t* mma_bar = full + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mma_bar + 1);
 
   const int t = threadIdx.x, warp = t >> 5;
   if (t == 0) {
-    mbar_init(&full[0], kTileRows);
-    mbar_init(&full[1], kTileRows);
+    mbar_init(full, kTileRows);
     mbar_init(mma_bar, 1);
     fence_barrier_init();
   }
-  if (warp == 0) tmem_alloc(tmem_slot, HID);
+  if (warp == 0) tmem_alloc(tmem_slot, L::kTmemCols);
   load_weight_kblocks(sW1, w1, HID, CZ, CZ, t, 128);
+  load_weight_kblocks(sW1 + HID * 128, w1 + HID * CZ, HID, CZ, CZ, t, 128);
   load_weight_kblocks(sW2, w2, CZ, HID, HID, t, 128);
+  load_weight_kblocks(sW2 + L::KBH * CZ * 128, w2 + CZ * HID, CZ, HID, HID, t, 128);
   for (int i = t; i < HID; i += 128) sB1[i] = b1[i];
   for (int i = t; i < CZ; i += 128) sB2[i] = b2[i];
   tc_fence_before();
@@ -75,103 +98,122 @@ pair_transition_kernel(const float* pair, float* dst, int residual, long long R,
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   const uint32_t tm_lane = tmem + (static_cast<uint32_t>(warp * 32) << 16);
+  const uint32_t tm_out = HID;  // accumulator columns of the second GEMM
 
   const long long num_tiles = (R + kTileRows - 1) / kTileRows;
   uint32_t mma_phase = 0;
   long long tile = blockIdx.x;
   if (tile < num_tiles) {
     const long long r = tile * kTileRows + t;
-    issue_row_load<CZ>(sSt, t, pair + r * CZ, r < R, &full[0]);
+    issue_row_load<CZ>(sSt, t, pair + r * CZ, r < R, full);
   }
   for (int it = 0; tile < num_tiles; tile += gridDim.x, ++it) {
-    const int buf = it & 1;
-    uint8_t* st = sSt + buf * RowStage<CZ>::kBytes;
-    const long long next = tile + gridDim.x;
-    if (next < num_tiles) {
-      bulk_wait_read0();
-      const long long rn = next * kTileRows + t;
-      issue_row_load<CZ>(sSt + (buf ^ 1) * RowStage<CZ>::kBytes, t, pair + rn * CZ, rn < R, &full[buf ^ 1]);
-    }
-    mbar_wait(&full[buf], (it >> 1) & 1);
+    mbar_wait(full, it & 1);
     const long long r = tile * kTileRows + t;
     const bool valid = r < R;
-    float* my = stage_row<CZ>(st, t);
-    {
-      float x[CZ];
-      if (valid) {
-        read_row<CZ>(my, x);
-      } else {
+    float x[CZ];
+    if (valid) {
+      read_row<CZ>(stage_row<CZ>(sSt, t), x);
+    } else {
 #pragma unroll
-        for (int i = 0; i < CZ; ++i) x[i] = 0.f;
-      }
-      layernorm_inplace<CZ>(x);
-      store_a_row<CZ>(sA, t, x);
+      for (int i = 0; i < CZ; ++i) x[i] = 0.f;
     }
+    {  // the stage slot of this thread is free again: prefetch the next tile's row
+      const long long next = tile + gridDim.x;
+      if (next < num_tiles) {
+        const long long rn = next * kTileRows + t;
+        issue_row_load<CZ>(sSt, t, pair + rn * CZ, rn < R, full);
+      }
+    }
+    {
+      float y[CZ];
+#pragma unroll
+      for (int i = 0; i < CZ; ++i) y[i] = x[i];
+      layernorm_inplace<CZ>(y);
+      store_a_row<CZ>(sA, t, y);
+    }
+    bulk_wait_read0();  // previous tile's output rows (staged in sH) have been read by the bulk store
     sync_before_mma();
     if (t == 0) {
       tc_fence_after();
       umma_multi(tmem, smem_u32(sA), smem_u32(sW1), 1, HID * 128, umma_idesc_f16(128, HID), false);
+      umma_multi(tmem, smem_u32(sA), smem_u32(sW1 + HID * 128), 1, HID * 128, umma_idesc_f16(128, HID), true);
       umma_commit(mma_bar);
     }
     mbar_wait(mma_bar, mma_phase);
     mma_phase ^= 1;
     tc_fence_after();
 #pragma unroll 1
-    for (int c = 0; c < HID / 32; ++c) {
-      uint32_t acc[32];
-      tmem_ld32(tm_lane + c * 32, acc);
-      tmem_ld_wait();
-      float v[32];
+    for (int half = 0; half < 2; ++half) {
+#pragma unroll 1
+      for (int c = 0; c < L::HH / 32; ++c) {
+        uint32_t acc[32];
+        tmem_ld32(tm_lane + half * L::HH + c * 32, acc);
+        tmem_ld_wait();
+        float v[32];
 #pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = fmaxf(__uint_as_float(acc[j]) + sB1[c * 32 + j], 0.f);
-      store_a_cols32(sH, t, c * 32, v);
-    }
-    sync_before_mma();
-    if (t == 0) {
+        for (int j = 0; j < 32; ++j) v[j] = fmaxf(__uint_as_float(acc[j]) + sB1[half * L::HH + c * 32 + j], 0.f);
+        store_a_cols32(sH, t, c * 32, v);
+      }
+      sync_before_mma();
+      if (t == 0) {
+        tc_fence_after();
+        const uint32_t idesc = umma_idesc_f16(128, CZ);
+        for (int kb = 0; kb < L::KBHH; ++kb)
+          umma_kblock(tmem + tm_out, smem_u32(sH) + kb * 16384, smem_u32(sW2) + (half * L::KBHH + kb) * CZ * 128, idesc,
+                      half > 0 || kb > 0);
+        for (int kb = 0; kb < L::KBHH; ++kb)
+          umma_kblock(tmem + tm_out, smem_u32(sH) + kb * 16384,
+                      smem_u32(sW2) + (L::KBH + half * L::KBHH + kb) * CZ * 128, idesc, true);
+        umma_commit(mma_bar);
+      }
+      mbar_wait(mma_bar, mma_phase);  // the hidden tile is rewritten next: its UMMAs must be done
+      mma_phase ^= 1;
       tc_fence_after();
-      umma_multi(tmem, smem_u32(sH), smem_u32(sW2), KBH, CZ * 128, umma_idesc_f16(128, CZ), false);
-      umma_commit(mma_bar);
     }
-    mbar_wait(mma_bar, mma_phase);
-    mma_phase ^= 1;
-    tc_fence_after();
+    float* my = stage_row<CZ>(sH, t);  // output staging aliases the hidden tile (its UMMAs are complete)
 #pragma unroll
     for (int c = 0; c < CZ / 32; ++c) {
       uint32_t acc[32];
-      tmem_ld32(tm_lane + c * 32, acc);
+      tmem_ld32(tm_lane + tm_out + c * 32, acc);
       tmem_ld_wait();
 #pragma unroll
       for (int j = 0; j < 32; j += 4) {
-        float4 x = *reinterpret_cast<float4*>(my + c * 32 + j);
-        if (!residual) x = make_float4(0.f, 0.f, 0.f, 0.f);
-        x.x += __uint_as_float(acc[j + 0]) + sB2[c * 32 + j + 0];
-        x.y += __uint_as_float(acc[j + 1]) + sB2[c * 32 + j + 1];
-        x.z += __uint_as_float(acc[j + 2]) + sB2[c * 32 + j + 2];
-        x.w += __uint_as_float(acc[j + 3]) + sB2[c * 32 + j + 3];
-        *reinterpret_cast<float4*>(my + c * 32 + j) = x;
+        float4 o;
+        o.x = __uint_as_float(acc[j + 0]) + sB2[c * 32 + j + 0];
+        o.y = __uint_as_float(acc[j + 1]) + sB2[c * 32 + j + 1];
+        o.z = __uint_as_float(acc[j + 2]) + sB2[c * 32 + j + 2];
+        o.w = __uint_as_float(acc[j + 3]) + sB2[c * 32 + j + 3];
+        if (residual) {
+          o.x += x[c * 32 + j + 0];
+          o.y += x[c * 32 + j + 1];
+          o.z += x[c * 32 + j + 2];
+          o.w += x[c * 32 + j + 3];
+        }
+        *reinterpret_cast<float4*>(my + c * 32 + j) = o;
       }
     }
     fence_proxy_async_smem();
     if (valid) bulk_s2g(dst + r * CZ, my, CZ * 4);
     bulk_commit();
+    // TMEM columns and sA are rewritten by the next tile only after its sync_before_mma
   }
   bulk_wait0();
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem, HID);
+  if (warp == 0) tmem_dealloc(tmem, L::kTmemCols);
 }
 
 template <int CZ, int HID>
 static int launch_pair_transition(const PairDims& d, const float* pair, float* dst, int residual, const __half* w1,
                                   const float* b1, const __half* w2, const float* b2, cudaStream_t s) {
-  constexpr int KBH = HID / 64;
-  constexpr int smem = 1024 + 16384 + KBH * 16384 + HID * 128 + KBH * CZ * 128 + 2 * RowStage<CZ>::kBytes +
-                       (HID + CZ) * 4 + 64;
+  using L = PairFcSmem<CZ, HID>;
+  static_assert(L::kTotal <= 227 * 1024, "pair_fc shared memory budget");
   auto kern = pair_transition_kernel<CZ, HID>;
-  if (set_smem(kern, smem)) return 1;
+  if (set_smem(kern, L::kTotal)) return 1;
   const long long R = (long long)d.B * d.N * d.N;
   const long long tiles = (R + kTileRows - 1) / kTileRows;
-  kern<<<grid_for(tiles, 1), 128, smem, s>>>(pair, dst, residual, R, w1, b1, w2, b2);
+  kern<<<grid_for(tiles, 1), 128, L::kTotal, s>>>(pair, dst, residual, R, w1, b1, w2, b2);
   PRD_LAUNCHED();
   return 0;
 }
@@ -200,8 +242,9 @@ trimul_in_kernel(const float* __restrict__ pair, const float* __restrict__ mask,
   constexpr int NOUT = 4 * CZ;
   uint8_t* sm = smem_align1024(raw);
   uint8_t* sA = sm;
-  uint8_t* sW = sA + 16384;
-  uint8_t* sSt = sW + NOUT * 128;
+  uint8_t* sW = sA + 16384;            // hi
+  uint8_t* sWl = sW + NOUT * 128;      // lo (weight = hi + lo, both fp16: removes the systematic rounding)
+  uint8_t* sSt = sWl + NOUT * 128;
   float* sB = reinterpret_cast<float*>(sSt + 2 * RowStage<CZ>::kBytes);
   uint64_t* full = reinterpret_cast<uint64_t*>(sB + NOUT);
   uint64_t* mma_bar = full + 2;
@@ -216,6 +259,7 @@ trimul_in_kernel(const float* __restrict__ pair, const float* __restrict__ mask,
   }
   if (warp == 0) tmem_alloc(tmem_slot, NOUT);
   load_weight_kblocks(sW, w_in, NOUT, CZ, CZ, t, 128);
+  load_weight_kblocks(sWl, w_in + NOUT * CZ, NOUT, CZ, CZ, t, 128);
   for (int i = t; i < NOUT; i += 128) sB[i] = b_in[i];
   tc_fence_before();
   __syncthreads();
@@ -258,6 +302,7 @@ trimul_in_kernel(const float* __restrict__ pair, const float* __restrict__ mask,
     if (t == 0) {
       tc_fence_after();
       umma_multi(tmem, smem_u32(sA), smem_u32(sW), 1, NOUT * 128, umma_idesc_f16(128, NOUT), false);
+      umma_multi(tmem, smem_u32(sA), smem_u32(sWl), 1, NOUT * 128, umma_idesc_f16(128, NOUT), true);
       umma_commit(mma_bar);
     }
     // mask_2d for the *source* element: m[b,i]*m[b,k] is symmetric, same for both modes
@@ -300,13 +345,13 @@ int trimul_in(const PairDims& d, const float* pair, const float* mask, int mode,
   const int Np = plane_ld(d.N);
   if (d.CZ == 64) {
     constexpr int CZ = 64;
-    constexpr int smem = 1024 + 16384 + 4 * CZ * 128 + 2 * RowStage<CZ>::kBytes + 4 * CZ * 4 + 64;
+    constexpr int smem = 1024 + 16384 + 2 * 4 * CZ * 128 + 2 * RowStage<CZ>::kBytes + 4 * CZ * 4 + 64;
     auto kern = trimul_in_kernel<CZ>;
     if (set_smem(kern, smem)) return 1;
     kern<<<grid_for(tiles, 2), 128, smem, s>>>(pair, mask, map, d.B, R, w_in, b_in, ab, Np);
   } else if (d.CZ == 32) {
     constexpr int CZ = 32;
-    constexpr int smem = 1024 + 16384 + 4 * CZ * 128 + 2 * RowStage<CZ>::kBytes + 4 * CZ * 4 + 64;
+    constexpr int smem = 1024 + 16384 + 2 * 4 * CZ * 128 + 2 * RowStage<CZ>::kBytes + 4 * CZ * 4 + 64;
     auto kern = trimul_in_kernel<CZ>;
     if (set_smem(kern, smem)) return 1;
     kern<<<grid_for(tiles, 2), 128, smem, s>>>(pair, mask, map, d.B, R, w_in, b_in, ab, Np);
@@ -330,8 +375,8 @@ trimul_out_kernel(const float* pair, float* dst, int residual, const float* __re
   uint8_t* sm = smem_align1024(raw);
   uint8_t* sAp = sm;
   uint8_t* sAx = sAp + 16384;
-  uint8_t* sW = sAx + 16384;  // two B tiles of [CZ x 64]
-  uint8_t* sSt = sW + 2 * CZ * 128;
+  uint8_t* sW = sAx + 16384;  // four B tiles of [CZ x 64]: gate_hi, proj_hi, gate_lo, proj_lo
+  uint8_t* sSt = sW + 4 * CZ * 128;
   float* sB = reinterpret_cast<float*>(sSt + 2 * RowStage<CZ>::kBytes);
   uint64_t* full = reinterpret_cast<uint64_t*>(sB + 2 * CZ);
   uint64_t* mma_bar = full + 2;
@@ -346,8 +391,7 @@ trimul_out_kernel(const float* pair, float* dst, int residual, const float* __re
     fence_barrier_init();
   }
   if (warp == 0) tmem_alloc(tmem_slot, TCOLS);
-  load_weight_kblocks(sW, w_out, CZ, CZ, CZ, t, 128);
-  load_weight_kblocks(sW + CZ * 128, w_out + CZ * CZ, CZ, CZ, CZ, t, 128);
+  for (int q = 0; q < 4; ++q) load_weight_kblocks(sW + q * CZ * 128, w_out + q * CZ * CZ, CZ, CZ, CZ, t, 128);
   for (int i = t; i < 2 * CZ; i += 128) sB[i] = b_out[i];
   tc_fence_before();
   __syncthreads();
@@ -409,7 +453,9 @@ trimul_out_kernel(const float* pair, float* dst, int residual, const float* __re
     if (t == 0) {
       tc_fence_after();
       umma_multi(tmem, smem_u32(sAp), smem_u32(sW), 1, CZ * 128, umma_idesc_f16(128, CZ), false);
+      umma_multi(tmem, smem_u32(sAp), smem_u32(sW + 2 * CZ * 128), 1, CZ * 128, umma_idesc_f16(128, CZ), true);
       umma_multi(tmem + CZ, smem_u32(sAx), smem_u32(sW + CZ * 128), 1, CZ * 128, umma_idesc_f16(128, CZ), false);
+      umma_multi(tmem + CZ, smem_u32(sAx), smem_u32(sW + 3 * CZ * 128), 1, CZ * 128, umma_idesc_f16(128, CZ), true);
       umma_commit(mma_bar);
     }
     mbar_wait(mma_bar, mma_phase);
@@ -457,13 +503,13 @@ int trimul_out(const PairDims& d, const float* pair, float* dst, int residual, c
   const int Nx = xplane_ld(d.N);
   if (d.CZ == 64) {
     constexpr int CZ = 64;
-    constexpr int smem = 1024 + 2 * 16384 + 2 * CZ * 128 + 2 * RowStage<CZ>::kBytes + 2 * CZ * 4 + 64;
+    constexpr int smem = 1024 + 2 * 16384 + 4 * CZ * 128 + 2 * RowStage<CZ>::kBytes + 2 * CZ * 4 + 64;
     auto kern = trimul_out_kernel<CZ>;
     if (set_smem(kern, smem)) return 1;
     kern<<<grid_for(tiles, 2), 128, smem, s>>>(pair, dst, residual, x, d.N, Nx, R, w_out, b_out);
   } else if (d.CZ == 32) {
     constexpr int CZ = 32;
-    constexpr int smem = 1024 + 2 * 16384 + 2 * CZ * 128 + 2 * RowStage<CZ>::kBytes + 2 * CZ * 4 + 64;
+    constexpr int smem = 1024 + 2 * 16384 + 4 * CZ * 128 + 2 * RowStage<CZ>::kBytes + 2 * CZ * 4 + 64;
     auto kern = trimul_out_kernel<CZ>;
     if (set_smem(kern, smem)) return 1;
     kern<<<grid_for(tiles, 2), 128, smem, s>>>(pair, dst, residual, x, d.N, Nx, R, w_out, b_out);
@@ -492,7 +538,8 @@ triattn_proj_kernel(const float* __restrict__ pair, RowMap map, long long R, con
   uint8_t* sm = smem_align1024(raw);
   uint8_t* sA = sm;
   uint8_t* sW = sA + 16384;
-  uint8_t* sSt = sW + NOUT * 128;
+  uint8_t* sWl = sW + NOUT * 128;
+  uint8_t* sSt = sWl + NOUT * 128;
   float* sB = reinterpret_cast<float*>(sSt + 2 * RowStage<CZ>::kBytes);
   uint64_t* full = reinterpret_cast<uint64_t*>(sB + 64);
   uint64_t* mma_bar = full + 2;
@@ -507,6 +554,7 @@ triattn_proj_kernel(const float* __restrict__ pair, RowMap map, long long R, con
   }
   if (warp == 0) tmem_alloc(tmem_slot, NOUT);
   load_weight_kblocks(sW, w, NOUT, CZ, CZ, t, 128);
+  load_weight_kblocks(sWl, w + NOUT * CZ, NOUT, CZ, CZ, t, 128);
   if (t < 64) sB[t] = b_gate[t];
   tc_fence_before();
   __syncthreads();
@@ -546,6 +594,7 @@ triattn_proj_kernel(const float* __restrict__ pair, RowMap map, long long R, con
     if (t == 0) {
       tc_fence_after();
       umma_multi(tmem, smem_u32(sA), smem_u32(sW), 1, NOUT * 128, umma_idesc_f16(128, NOUT), false);
+      umma_multi(tmem, smem_u32(sA), smem_u32(sWl), 1, NOUT * 128, umma_idesc_f16(128, NOUT), true);
       umma_commit(mma_bar);
     }
     int b = 0, s = 0, tk = 0;
@@ -602,13 +651,13 @@ int triattn_proj(const PairDims& d, const float* pair, int mode, const __half* w
   const int Np = plane_ld(d.N);
   if (d.CZ == 64) {
     constexpr int CZ = 64;
-    constexpr int smem = 1024 + 16384 + 256 * 128 + 2 * RowStage<CZ>::kBytes + 64 * 4 + 64;
+    constexpr int smem = 1024 + 16384 + 2 * 256 * 128 + 2 * RowStage<CZ>::kBytes + 64 * 4 + 64;
     auto kern = triattn_proj_kernel<CZ>;
     if (set_smem(kern, smem)) return 1;
     kern<<<grid_for(tiles, 2), 128, smem, s>>>(pair, map, R, w_qkvg, b_gate, q, k, g, vt, Np);
   } else if (d.CZ == 32) {
     constexpr int CZ = 32;
-    constexpr int smem = 1024 + 16384 + 256 * 128 + 2 * RowStage<CZ>::kBytes + 64 * 4 + 64;
+    constexpr int smem = 1024 + 16384 + 2 * 256 * 128 + 2 * RowStage<CZ>::kBytes + 64 * 4 + 64;
     auto kern = triattn_proj_kernel<CZ>;
     if (set_smem(kern, smem)) return 1;
     kern<<<grid_for(tiles, 2), 128, smem, s>>>(pair, map, R, w_qkvg, b_gate, q, k, g, vt, Np);
@@ -632,7 +681,8 @@ triattn_out_kernel(const float* pair, float* dst, int residual, RowMap map, long
   uint8_t* sm = smem_align1024(raw);
   uint8_t* sA = sm;
   uint8_t* sW = sA + 16384;
-  uint8_t* sSt = sW + CZ * 128;
+  uint8_t* sWl = sW + CZ * 128;
+  uint8_t* sSt = sWl + CZ * 128;
   float* sB = reinterpret_cast<float*>(sSt + 2 * RowStage<CZ>::kBytes);
   uint64_t* full = reinterpret_cast<uint64_t*>(sB + CZ);
   uint64_t* mma_bar = full + 2;
@@ -648,6 +698,7 @@ triattn_out_kernel(const float* pair, float* dst, int residual, RowMap map, long
   }
   if (warp == 0) tmem_alloc(tmem_slot, TCOLS);
   load_weight_kblocks(sW, w_o, CZ, 64, 64, t, 128);
+  load_weight_kblocks(sWl, w_o + CZ * 64, CZ, 64, 64, t, 128);
   for (int i = t; i < CZ; i += 128) sB[i] = b_o[i];
   tc_fence_before();
   __syncthreads();
@@ -692,6 +743,7 @@ triattn_out_kernel(const float* pair, float* dst, int residual, RowMap map, long
     if (t == 0) {
       tc_fence_after();
       umma_multi(tmem, smem_u32(sA), smem_u32(sW), 1, CZ * 128, umma_idesc_f16(128, CZ), false);
+      umma_multi(tmem, smem_u32(sA), smem_u32(sWl), 1, CZ * 128, umma_idesc_f16(128, CZ), true);
       umma_commit(mma_bar);
     }
     mbar_wait(&full[buf], (it >> 1) & 1);
@@ -733,13 +785,13 @@ int triattn_out(const PairDims& d, const float* pair, float* dst, int residual, 
   RowMap map{d.N, (long long)d.N * d.N, mode};
   if (d.CZ == 64) {
     constexpr int CZ = 64;
-    constexpr int smem = 1024 + 16384 + CZ * 128 + 2 * RowStage<CZ>::kBytes + CZ * 4 + 64;
+    constexpr int smem = 1024 + 16384 + 2 * CZ * 128 + 2 * RowStage<CZ>::kBytes + CZ * 4 + 64;
     auto kern = triattn_out_kernel<CZ>;
     if (set_smem(kern, smem)) return 1;
     kern<<<grid_for(tiles, 2), 128, smem, s>>>(pair, dst, residual, map, R, og, w_o, b_o);
   } else if (d.CZ == 32) {
     constexpr int CZ = 32;
-    constexpr int smem = 1024 + 16384 + CZ * 128 + 2 * RowStage<CZ>::kBytes + CZ * 4 + 64;
+    constexpr int smem = 1024 + 16384 + 2 * CZ * 128 + 2 * RowStage<CZ>::kBytes + CZ * 4 + 64;
     auto kern = triattn_out_kernel<CZ>;
     if (set_smem(kern, smem)) return 1;
     kern<<<grid_for(tiles, 2), 128, smem, s>>>(pair, dst, residual, map, R, og, w_o, b_o);

@@ -20,45 +20,69 @@ namespace prd {
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kMaskFillLog2 = -32768.0f * kLog2e;  // modules.py:177,220 in the exp2 domain
 
+// Per-key softmax terms in the exp2 domain: t_j = s_j * mul_j + add_j
+//   valid key   : mul = log2(e), add = 0
+//   masked key  : mul = 0,       add = -2^15 * log2(e)   (the reference's finite fill value)
+//   j >= N (pad): mul = 0,       add = -inf               (does not exist: p = 0)
+// A key tile whose 128 keys are all valid takes a fast path without any per-key loads.
 __global__ void __launch_bounds__(128, 2)
 triattn_flash_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
                      const __grid_constant__ CUtensorMap map_vt, const float* __restrict__ mask,
                      const __half* __restrict__ g, __half* __restrict__ og, int N) {
   extern __shared__ uint8_t raw[];
   uint8_t* sm = smem_align1024(raw);
-  uint8_t* sQ = sm;                // [128 x 64] halves, 16 KB
-  uint8_t* sK = sQ + 16384;        // [128 keys x 64], 16 KB
-  uint8_t* sVt = sK + 16384;       // 2 boxes of [64 rows x 64 keys], 8 KB each
-  uint8_t* sP = sVt + 16384;       // 2 K-blocks of [128 x 64 keys], 32 KB
-  float* sMask = reinterpret_cast<float*>(sP + 32768);  // key mask of this sequence, N floats (padded to 128s)
+  uint8_t* sQ = sm;                 // [128 x 64] halves, 16 KB
+  uint8_t* sK = sQ + 16384;         // 2 buffers of [128 keys x 64], 16 KB each (next tile prefetched)
+  uint8_t* sVt = sK + 32768;        // 2 boxes of [64 rows x 64 keys], 8 KB each
+  uint8_t* sP = sVt + 16384;        // 2 K-blocks of [128 x 64 keys], 32 KB
   const int nkt = (N + 127) / 128;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sMask + nkt * 128);
+  float2* sKey = reinterpret_cast<float2*>(sP + 32768);  // (mul, add) per key, nkt * 128 entries
+  int* sAllValid = reinterpret_cast<int*>(sKey + nkt * 128);  // per key tile
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sAllValid + ((nkt + 1) & ~1));
   uint64_t* bar_q = bars;
-  uint64_t* bar_kv = bars + 1;
-  uint64_t* bar_s = bars + 2;
-  uint64_t* bar_o = bars + 3;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+  uint64_t* bar_k = bars + 1;  // [2]
+  uint64_t* bar_v = bars + 3;
+  uint64_t* bar_s = bars + 4;
+  uint64_t* bar_o = bars + 5;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
 
   const int t = threadIdx.x, warp = t >> 5;
-  const int nkt_grid = (N + 127) / 128;
-  const int qt = blockIdx.x % nkt_grid;  // the q-tiles of one sequence are adjacent CTAs: K/V stay in L2
-  const int seq = blockIdx.x / nkt_grid;  // b * N + s
+  const int qt = blockIdx.x % nkt;   // the q-tiles of one sequence are adjacent CTAs: K/V stay in L2
+  const int seq = blockIdx.x / nkt;  // b * N + s
   const int b = seq / N;
   if (t == 0) {
     mbar_init(bar_q, 1);
-    mbar_init(bar_kv, 1);
+    mbar_init(&bar_k[0], 1);
+    mbar_init(&bar_k[1], 1);
+    mbar_init(bar_v, 1);
     mbar_init(bar_s, 1);
     mbar_init(bar_o, 1);
     fence_barrier_init();
     tma_prefetch_desc(&map_q);
     tma_prefetch_desc(&map_k);
     tma_prefetch_desc(&map_vt);
+    mbar_expect_tx(bar_q, 16384);
+    tma_load_3d(sQ, &map_q, bar_q, 0, qt * 128, seq);
+    mbar_expect_tx(&bar_k[0], 16384);
+    tma_load_3d(sK, &map_k, &bar_k[0], 0, 0, seq);
   }
   if (warp == 0) tmem_alloc(tmem_slot, 256);
   {
-    // key mask = m[b,seq_pos] * m[b,key]  (mask_2d row / column; symmetric, so one formula for both modes)
+    // key mask = m[b,seq_pos] * m[b,key]  (mask_2d row / column; symmetric, one formula for both modes)
     const float ms = mask[seq];
-    for (int j = t; j < nkt * 128; j += 128) sMask[j] = (j < N) ? ms * mask[(long long)b * N + j] : -1.0f;
+    for (int j = t; j < nkt * 128; j += 128) {
+      float2 e;
+      if (j >= N) e = make_float2(0.f, -INFINITY);
+      else if (ms * mask[(long long)b * N + j] < 0.5f) e = make_float2(0.f, kMaskFillLog2);
+      else e = make_float2(kLog2e, 0.f);
+      sKey[j] = e;
+    }
+  }
+  __syncthreads();
+  if (t < nkt) {
+    int all = 1;
+    for (int j = 0; j < 128; ++j) all &= (sKey[t * 128 + j].x != 0.f) ? 1 : 0;
+    sAllValid[t] = all;
   }
   tc_fence_before();
   __syncthreads();
@@ -66,11 +90,6 @@ triattn_flash_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
   const uint32_t tmem = *tmem_slot;
   const uint32_t tm_lane = tmem + (static_cast<uint32_t>(warp * 32) << 16);
   const uint32_t tm_o = 128;  // column offset of the four 16-column O chunks
-
-  if (t == 0) {
-    mbar_expect_tx(bar_q, 16384);
-    tma_load_3d(sQ, &map_q, bar_q, 0, qt * 128, seq);
-  }
 
   float o[4][16];
   float mrow[4], lrow[4];
@@ -82,69 +101,107 @@ triattn_flash_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
     for (int c = 0; c < 16; ++c) o[h][c] = 0.f;
   }
   uint32_t ph_s = 0, ph_o = 0;
+  const uint64_t dq = umma_desc_sw128(smem_u32(sQ));
 
   for (int kt = 0; kt < nkt; ++kt) {
+    uint8_t* sKc = sK + (kt & 1) * 16384;
     if (t == 0) {
-      mbar_expect_tx(bar_kv, 32768);
-      tma_load_3d(sK, &map_k, bar_kv, 0, kt * 128, seq);
-      tma_load_3d(sVt, &map_vt, bar_kv, kt * 128, 0, seq);
-      tma_load_3d(sVt + 8192, &map_vt, bar_kv, kt * 128 + 64, 0, seq);
+      // V^T of this tile (its buffer was released by the end-of-tile barrier) and K of the next tile
+      mbar_expect_tx(bar_v, 16384);
+      tma_load_3d(sVt, &map_vt, bar_v, kt * 128, 0, seq);
+      tma_load_3d(sVt + 8192, &map_vt, bar_v, kt * 128 + 64, 0, seq);
+      if (kt + 1 < nkt) {
+        mbar_expect_tx(&bar_k[(kt + 1) & 1], 16384);
+        tma_load_3d(sK + ((kt + 1) & 1) * 16384, &map_k, &bar_k[(kt + 1) & 1], 0, (kt + 1) * 128, seq);
+      }
+      if (kt == 0) mbar_wait(bar_q, 0);
+      mbar_wait(&bar_k[kt & 1], (kt >> 1) & 1);
+      tc_fence_after();
+      umma_f16(tmem, dq, umma_desc_sw128(smem_u32(sKc)), umma_idesc_f16(128, 128), 0u);  // S for head 0
+      umma_commit(bar_s);
     }
-    if (kt == 0) mbar_wait(bar_q, 0);
-    mbar_wait(bar_kv, kt & 1);
+    const bool all_valid = sAllValid[kt] != 0;
+    const float2* keyp = sKey + kt * 128;
 #pragma unroll
     for (int h = 0; h < 4; ++h) {
-      if (t == 0) {
-        tc_fence_after();
-        // head h = halves [16h, 16h+16) of every 128-byte row: advance the descriptors by 32 bytes
-        umma_f16(tmem, umma_desc_sw128(smem_u32(sQ)) + 2 * h, umma_desc_sw128(smem_u32(sK)) + 2 * h,
-                 umma_idesc_f16(128, 128), 0u);
-        umma_commit(bar_s);
-      }
       mbar_wait(bar_s, ph_s);
       ph_s ^= 1;
       tc_fence_after();
-      // pass A: row max over this key tile (log2 domain)
+      // pass A: row max over this key tile (exp2 domain)
       float mx = mrow[h];
+      if (all_valid) {
+        float raw_max = -INFINITY;
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t sv[32];
-        tmem_ld32(tm_lane + c * 32, sv);
-        tmem_ld_wait();
+        for (int c = 0; c < 4; ++c) {
+          uint32_t sv[32];
+          tmem_ld32(tm_lane + c * 32, sv);
+          tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const float km = sMask[kt * 128 + c * 32 + j];
-          const float v = km < 0.f ? -INFINITY : (km < 0.5f ? kMaskFillLog2 : __uint_as_float(sv[j]) * kLog2e);
-          mx = fmaxf(mx, v);
+          for (int j = 0; j < 32; ++j) raw_max = fmaxf(raw_max, __uint_as_float(sv[j]));
+        }
+        mx = fmaxf(mx, raw_max * kLog2e);
+      } else {
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          uint32_t sv[32];
+          tmem_ld32(tm_lane + c * 32, sv);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float2 e = keyp[c * 32 + j];
+            mx = fmaxf(mx, fmaf(__uint_as_float(sv[j]), e.x, e.y));
+          }
         }
       }
       const float alpha = ex2_approx(mrow[h] - mx);
       mrow[h] = mx;
-      // pass B: p = exp2(s - m), row sum, fp16 P tile
+      // pass B: p = exp2(t - m), row sum, fp16 P tile
       float rs = 0.f;
+      if (all_valid) {
+        const float nmx = -mx;
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t sv[32];
-        tmem_ld32(tm_lane + c * 32, sv);
-        tmem_ld_wait();
-        float p[32];
+        for (int c = 0; c < 4; ++c) {
+          uint32_t sv[32];
+          tmem_ld32(tm_lane + c * 32, sv);
+          tmem_ld_wait();
+          float p[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const float km = sMask[kt * 128 + c * 32 + j];
-          const float v = km < 0.f ? -INFINITY : (km < 0.5f ? kMaskFillLog2 : __uint_as_float(sv[j]) * kLog2e);
-          p[j] = ex2_approx(v - mx);
-          rs += p[j];
+          for (int j = 0; j < 32; ++j) {
+            p[j] = ex2_approx(fmaf(__uint_as_float(sv[j]), kLog2e, nmx));
+            rs += p[j];
+          }
+          store_a_cols32(sP, t, c * 32, p);
         }
-        store_a_cols32(sP, t, c * 32, p);
+      } else {
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          uint32_t sv[32];
+          tmem_ld32(tm_lane + c * 32, sv);
+          tmem_ld_wait();
+          float p[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float2 e = keyp[c * 32 + j];
+            p[j] = ex2_approx(fmaf(__uint_as_float(sv[j]), e.x, e.y) - mx);
+            rs += p[j];
+          }
+          store_a_cols32(sP, t, c * 32, p);
+        }
       }
       lrow[h] = lrow[h] * alpha + rs;
-      sync_before_mma();
+      sync_before_mma();  // P visible to the tensor core; every thread is done reading S
       if (t == 0) {
         tc_fence_after();
+        if (h == 0) mbar_wait(bar_v, kt & 1);
         const uint32_t idesc = umma_idesc_f16(128, 16);
         umma_kblock(tmem + tm_o + 16 * h, smem_u32(sP), smem_u32(sVt) + h * 2048, idesc, false);
         umma_kblock(tmem + tm_o + 16 * h, smem_u32(sP) + 16384, smem_u32(sVt) + 8192 + h * 2048, idesc, true);
         umma_commit(bar_o);
+        if (h < 3) {
+          // S of the next head is computed while this head's P.V finishes and O is read back
+          umma_f16(tmem, dq + 2 * (h + 1), umma_desc_sw128(smem_u32(sKc)) + 2 * (h + 1), umma_idesc_f16(128, 128), 0u);
+          umma_commit(bar_s);
+        }
       }
       mbar_wait(bar_o, ph_o);
       ph_o ^= 1;
@@ -157,7 +214,7 @@ triattn_flash_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
         for (int c = 0; c < 16; ++c) o[h][c] = o[h][c] * alpha + __uint_as_float(ov[c]);
       }
     }
-    // K / V^T / P buffers and the S columns are reused by the next key tile
+    // V^T / P buffers and the K buffer of tile kt-1... are reused: all UMMAs of this tile are complete
     tc_fence_before();
     __syncthreads();
   }
@@ -208,7 +265,7 @@ int triattn_flash(const PairDims& d, const float* mask, const __half* q, const _
   t.box[0] = 64; t.box[1] = 64; t.box[2] = 1;
   if (make_tensor_map(&mv, vt, 2, 3, t, true)) return 1;
   const int nkt = (N + 127) / 128;
-  const int smem = 1024 + 16384 * 3 + 32768 + nkt * 128 * 4 + 64;
+  const int smem = 1024 + 16384 * 4 + 32768 + nkt * 128 * 8 + ((nkt + 1) & ~1) * 4 + 64;
   PRD_CUDA_OK(cudaFuncSetAttribute(triattn_flash_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   PRD_REQUIRE(nseq * nkt <= 2147483647LL, "triattn_flash: grid overflow");
   dim3 grid((unsigned)(nseq * nkt));

@@ -22,7 +22,7 @@ import torch.nn.functional as F
 from torch import nn
 
 from . import ops
-from ._packing import PackCache, f32, half, tensor_version
+from ._packing import PackCache, f32, half, split_k, split_rows, tensor_version
 from .modules import AtomEmbedding, BondEmbedding, Denoiser, Linear, RadialBasisProjection, SinusoidalProjection
 from .synthetic import NUM_RESIDUE_CLASSES, DenoiserConfig
 
@@ -205,12 +205,12 @@ class ProteinReDiffModel(_Base):
 
         def build():
             w = {
-                "esm": [half(srcs[0])],
+                "esm": [split_k(srcs[0])],
                 "w_type": f32(srcs[1]),
-                "pair_dyn": [f32(srcs[2]), f32(srcs[3]), half(srcs[5]), f32(srcs[4])],
+                "pair_dyn": [f32(srcs[2]), f32(srcs[3]), split_rows(srcs[5]), f32(srcs[4])],
                 "bdist": f32(srcs[6]), "relpos": f32(srcs[7]),
-                "coord": [half(srcs[8]), f32(srcs[9]), f32(srcs[10]).reshape(-1).contiguous()],
-                "seq": [half(srcs[11]), f32(srcs[12]), half(srcs[13])],
+                "coord": [split_rows(srcs[8]), f32(srcs[9]), f32(srcs[10]).reshape(-1).contiguous()],
+                "seq": [split_k(srcs[11]), f32(srcs[12]), split_k(srcs[13])],
                 "atom_tabs": [f32(t) for t in srcs[14:23]],
                 "bond_tabs": [f32(t) for t in srcs[23:26]],
             }

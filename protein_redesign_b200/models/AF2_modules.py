@@ -16,7 +16,7 @@ import torch
 from torch import nn
 
 from .. import ops
-from .._packing import PackCache, half
+from .._packing import PackCache, half, split_k
 
 
 def _trunc_normal_(w: torch.Tensor, scale: float) -> None:
@@ -105,8 +105,8 @@ class SPAttention(nn.Module):
 
         def build():
             f = lambda t: t.detach().float().contiguous()
-            return [f(srcs[0]), f(srcs[1]), f(srcs[2]), f(srcs[3]), f(srcs[4]), half(srcs[5]), half(srcs[6]),
-                    half(srcs[7]), half(srcs[8]), f(srcs[9]), half(srcs[10]), f(srcs[11])]
+            return [f(srcs[0]), f(srcs[1]), f(srcs[2]), f(srcs[3]), f(srcs[4]), split_k(srcs[5]), split_k(srcs[6]),
+                    split_k(srcs[7]), split_k(srcs[8]), f(srcs[9]), split_k(srcs[10]), f(srcs[11])]
 
         return self._pack.get(srcs, build)
 
@@ -143,7 +143,7 @@ class OuterProductUpdate(nn.Module):
 
         def build():
             f = lambda t: t.detach().float().contiguous()
-            proj = [f(srcs[0]), f(srcs[1]), half(srcs[2]), f(srcs[3]), half(srcs[4]), f(srcs[5])]
+            proj = [f(srcs[0]), f(srcs[1]), split_k(srcs[2]), f(srcs[3]), split_k(srcs[4]), f(srcs[5])]
             out = [half(srcs[6]), f(srcs[7])]
             return proj, out
 

@@ -18,7 +18,7 @@ import torch
 from torch import nn
 
 from . import ops
-from ._packing import PackCache, f32, half
+from ._packing import PackCache, f32, half, split_k, split_rows
 from .models import AF2_modules
 from .synthetic import ATOM_VOCAB, BOND_VOCAB, DenoiserConfig
 
@@ -157,6 +157,7 @@ class Attention(nn.Module):
         self.gate_proj = Linear(embed_dim, num_heads * head_dim, init="gating")
         self.out_proj = Linear(num_heads * head_dim, embed_dim, init="final")
         self._pack = PackCache()
+        self._pack_single = PackCache()
 
     def _sources(self):
         return [self.q_proj.weight, self.k_proj.weight, self.v_proj.weight, self.gate_proj.weight,
@@ -165,7 +166,8 @@ class Attention(nn.Module):
     def packed_pair(self):
         """[w_qkvg_h (4Hc x D), b_gate, w_o_h, b_o] for prd_triangle_attention_fwd."""
         s = self._sources()
-        return self._pack.get(s, lambda: [half(torch.cat([s[0], s[1], s[2], s[3]], 0)), f32(s[4]), half(s[5]), f32(s[6])])
+        return self._pack.get(s, lambda: [split_rows(torch.cat([s[0], s[1], s[2], s[3]], 0)), f32(s[4]),
+                                          split_rows(s[5]), f32(s[6])])
 
     def packed_single(self, bias_lin: Optional[nn.Linear]):
         """[w_bias, b_bias, w_qkvg_h, b_qkvg, w_o_h, b_o] for prd_single_attention_fwd."""
@@ -176,9 +178,9 @@ class Attention(nn.Module):
             b_qkvg = torch.cat([torch.zeros(3 * hc, device=s[4].device, dtype=torch.float32), f32(s[4])])
             wb = f32(s[7]) if bias_lin is not None else None
             bb = f32(s[8]) if bias_lin is not None else None
-            return [wb, bb, half(torch.cat([s[0], s[1], s[2], s[3]], 0)), b_qkvg, half(s[5]), f32(s[6])]
+            return [wb, bb, split_k(torch.cat([s[0], s[1], s[2], s[3]], 0)), b_qkvg, split_k(s[5]), f32(s[6])]
 
-        return self._pack.get(s, build)
+        return self._pack_single.get(s, build)
 
     def forward(self, x: torch.Tensor, mask: torch.Tensor, attn_bias: Optional[torch.Tensor] = None) -> torch.Tensor:
         x = x.contiguous()
@@ -243,8 +245,8 @@ class TriangleMultiplication(nn.Module):
     def packed_weights(self):
         s = [self.ab_proj.weight, self.ab_gate.weight, self.ab_proj.bias, self.ab_gate.bias,
              self.out_gate.weight, self.out_proj.weight, self.out_gate.bias, self.out_proj.bias]
-        return self._pack.get(s, lambda: [half(torch.cat([s[0], s[1]], 0)), f32(torch.cat([s[2], s[3]])),
-                                          half(torch.cat([s[4], s[5]], 0)), f32(torch.cat([s[6], s[7]]))])
+        return self._pack.get(s, lambda: [split_rows(torch.cat([s[0], s[1]], 0)), f32(torch.cat([s[2], s[3]])),
+                                          split_rows(torch.cat([s[4], s[5]], 0)), f32(torch.cat([s[6], s[7]]))])
 
     def apply_(self, cfg, pair, mask, out=None, residual=1):
         out = pair if out is None else out
@@ -270,7 +272,7 @@ class OuterLinear(nn.Module):
     def packed_weights(self):
         s = [self.linear.weight, self.linear.bias]
         cs = self.single_dim
-        return self._pack.get(s, lambda: [half(s[0][:, :cs]), half(s[0][:, cs:]), f32(s[1])])
+        return self._pack.get(s, lambda: [half(s[0][:, :cs]), split_k(s[0][:, cs:]), f32(s[1])])
 
     def apply_(self, cfg, single, pair, out=None, residual=1):
         out = pair if out is None else out
@@ -291,19 +293,29 @@ class _Transition(nn.Sequential):
         super().__init__(nn.LayerNorm(dim, elementwise_affine=False), Linear(dim, dim * factor, init="relu"), nn.ReLU(),
                          Linear(dim * factor, dim, init="final"))
         self._pack = PackCache()
+        self._pack_pair = PackCache()
 
-    def packed_weights(self):
-        s = [self[1].weight, self[1].bias, self[3].weight, self[3].bias]
-        return self._pack.get(s, lambda: [half(s[0]), f32(s[1]), half(s[2]), f32(s[3])])
+    def _sources(self):
+        return [self[1].weight, self[1].bias, self[3].weight, self[3].bias]
+
+    def packed_single(self):
+        """[w1 (hi|lo along K), b1, w2 (hi|lo along K), b2] for the GEMM-based single transition."""
+        s = self._sources()
+        return self._pack.get(s, lambda: [split_k(s[0]), f32(s[1]), split_k(s[2]), f32(s[3])])
+
+    def packed_pair(self):
+        """[w1 (hi;lo rows), b1, w2 (hi;lo rows), b2] for the fused pair-row kernel."""
+        s = self._sources()
+        return self._pack_pair.get(s, lambda: [split_rows(s[0]), f32(s[1]), split_rows(s[2]), f32(s[3])])
 
     def forward(self, x):  # stand-alone use returns the update, like the reference nn.Sequential
         x = x.contiguous()
         out = torch.empty_like(x)
         if x.dim() == 3:
             cfg = AF2_modules._MiniCfg(x.shape[-1], 64, 4, transition_factor=self[1].out_features // x.shape[-1])
-            return ops.single_transition(cfg, x, self.packed_weights(), out, residual=0)
+            return ops.single_transition(cfg, x, self.packed_single(), out, residual=0)
         cfg = AF2_modules._MiniCfg(512, x.shape[-1], 4, transition_factor=self[1].out_features // x.shape[-1])
-        return ops.pair_transition(cfg, x, self.packed_weights(), out, residual=0)
+        return ops.pair_transition(cfg, x, self.packed_pair(), out, residual=0)
 
 
 class FoldingBlock(nn.Module):
@@ -329,7 +341,7 @@ class FoldingBlock(nn.Module):
         rec = probe or (lambda n, t: None)
         ops.single_attention(cfg, single, pair, mask, self.single_attn.packed_single(self.attn_bias[1]), single)
         rec("single_attn", single)
-        ops.single_transition(cfg, single, self.single_fc.packed_weights(), single)
+        ops.single_transition(cfg, single, self.single_fc.packed_single(), single)
         rec("single_fc", single)
         self.outer_linear.apply_(cfg, single, pair)
         rec("outer_linear", pair)
@@ -341,7 +353,7 @@ class FoldingBlock(nn.Module):
         rec("pair_attn_starting", pair)
         self.pair_attn_ending.apply_(cfg, pair, mask)
         rec("pair_attn_ending", pair)
-        ops.pair_transition(cfg, pair, self.pair_fc.packed_weights(), pair)
+        ops.pair_transition(cfg, pair, self.pair_fc.packed_pair(), pair)
         rec("pair_fc", pair)
         return single, pair
 

@@ -91,7 +91,7 @@ def case_pair_transition(cfg=syn.PAPER, B=1, N=72, seed=0):
     want = pair + ref.transition(sd, _block_prefix() + "pair_fc.", pair)
     blk = m.Denoiser.folding_blocks[0]
     p = pair.to(DEV).contiguous()
-    ops.pair_transition(cfg, p, blk.pair_fc.packed_weights(), p)
+    ops.pair_transition(cfg, p, blk.pair_fc.packed_pair(), p)
     upd = blk.pair_fc(pair.to(DEV))  # module-level form returns the update
     torch.cuda.synchronize()
     return {"rel": (rel(p, want), OP_TOL), "rel_update": (rel(upd, want - pair), OP_TOL)}
@@ -155,7 +155,7 @@ def case_single_transition(cfg=syn.PAPER, B=2, N=72, seed=0):
     want = single + ref.transition(sd, _block_prefix() + "single_fc.", single)
     blk = m.Denoiser.folding_blocks[0]
     s = single.to(DEV).contiguous()
-    ops.single_transition(cfg, s, blk.single_fc.packed_weights(), s)
+    ops.single_transition(cfg, s, blk.single_fc.packed_single(), s)
     torch.cuda.synchronize()
     return {"rel": (rel(s, want), OP_TOL)}
 

@@ -75,7 +75,7 @@ def test_no_cpu_fallback():
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         ops.symmetrize(syn.README, torch.zeros(1, 8, 8, 32))
     with pytest.raises(RuntimeError, match="no CPU fallback"):
-        model.Denoiser.folding_blocks[0].pair_fc.packed_weights()  # CPU parameters cannot be packed
+        model.Denoiser.folding_blocks[0].pair_fc.packed_pair()  # CPU parameters cannot be packed
 
 
 def test_prepare_batch_matches_oracle_bit_exact():
