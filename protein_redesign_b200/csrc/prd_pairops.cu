@@ -11,31 +11,38 @@
 namespace prd {
 
 // =========================================================================================
-// OuterLinear:  pair[b,i,j,z] += sum_d W1[z,d] x_i[d] x_j[d] + u[b,i,z] - u[b,j,z] + bias[z]
+// OuterLinear:  dst[b,i,j,z] = [pair +] sum_d W1[z,d] x_i[d] x_j[d] + u[b,i,z] - u[b,j,z] + bias[z]
 // with x = LN(single), u = x W2^T (precomputed), W = [W1 | W2] = linear.weight[:, :c_s | c_s:].
-// CTA = (j-tile of 128 tokens, chunk of i, b).  A = x[b, j-tile, :] stays in shared memory
-// (c_s/64 K-blocks, TMA); for every i the B operand (W1 * x_i) is rebuilt in shared memory and
-// one [128 x c_z] accumulator is produced by c_s/16 UMMAs.
+// CTA (256 threads) = (j-tile of 128 tokens, chunk of i, b).  A = x[b, j-tile, :] stays in shared
+// memory (c_s/64 K-blocks, TMA).  W1 lives in REGISTERS (each thread owns a fixed set of 16-byte
+// chunks), so for every i the B operand (W1 * x_i) is rebuilt with pure register x smem math;
+// c_s/16 UMMAs then produce one [128 x c_z] accumulator.  Two accumulators alternate: the UMMAs of
+// row i run while the epilogue of row i-1 (TMEM -> registers -> global) is in flight, and the
+// residual pair values of row i-1 are prefetched before the B operand is rebuilt.
 // =========================================================================================
-template <int CZ>
-__global__ void __launch_bounds__(128, 1)
+template <int CZ, int KBS>
+__global__ void __launch_bounds__(256, 1)
 outer_linear_kernel(const __grid_constant__ CUtensorMap map_x, const float* pair, float* dst, int residual,
                     const float* __restrict__ xn32, const __half* __restrict__ w1, const float* __restrict__ u,
-                    const float* __restrict__ bias, int N, int CS, int ilen) {
+                    const float* __restrict__ bias, int N, int ilen) {
   extern __shared__ uint8_t raw[];
-  const int KBS = CS / 64;
+  constexpr int CS = KBS * 64;
+  constexpr int NCH = KBS * CZ * 8 / 256;  // 16-byte W1 chunks per thread
+  constexpr int HC = CZ / 2;               // accumulator columns per thread (two warp groups split them)
   uint8_t* sm = smem_align1024(raw);
   uint8_t* sA = sm;                        // KBS x 16 KB
   uint8_t* sB = sA + KBS * 16384;          // KBS x [CZ x 64]
   float* sXi = reinterpret_cast<float*>(sB + KBS * CZ * 128);
-  float* sUi = sXi + CS;
-  float* sBias = sUi + CZ;
+  float* sUi = sXi + CS;                   // [2][CZ]
+  float* sBias = sUi + 2 * CZ;
   uint64_t* bar_a = reinterpret_cast<uint64_t*>(sBias + CZ);
   uint64_t* mma_bar = bar_a + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mma_bar + 1);
-  constexpr int TCOLS = CZ < 32 ? 32 : CZ;
+  constexpr int TCOLS = 2 * CZ < 32 ? 32 : 2 * CZ;
 
   const int t = threadIdx.x, warp = t >> 5;
+  const int grp = warp >> 2;               // 0: columns [0, HC), 1: columns [HC, CZ)
+  const int lane_row = (warp & 3) * 32 + (t & 31);
   const int jt = blockIdx.x, b = blockIdx.z;
   const int i0 = blockIdx.y * ilen;
   const int i1 = min(N, i0 + ilen);
@@ -46,99 +53,144 @@ outer_linear_kernel(const __grid_constant__ CUtensorMap map_x, const float* pair
     tma_prefetch_desc(&map_x);
   }
   if (warp == 0) tmem_alloc(tmem_slot, TCOLS);
-  for (int i = t; i < CZ; i += 128) sBias[i] = bias[i];
+  for (int i = t; i < CZ; i += 256) sBias[i] = bias[i];
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  const uint32_t tm_lane = tmem + (static_cast<uint32_t>(warp * 32) << 16);
+  const uint32_t tm_lane = tmem + (static_cast<uint32_t>((warp & 3) * 32) << 16);
   if (t == 0) {
     mbar_expect_tx(bar_a, KBS * 16384);
     for (int kb = 0; kb < KBS; ++kb) tma_load_3d(sA + kb * 16384, &map_x, bar_a, kb * 64, jt * 128, b);
   }
-  const int j = jt * 128 + t;
-  const bool valid = j < N;
-  float uj[CZ];
-  if (valid) {
-    const float4* up = reinterpret_cast<const float4*>(u + ((long long)b * N + j) * CZ);
+  // this thread's W1 chunks (fixed for the whole kernel)
+  uint4 wreg[NCH];
 #pragma unroll
-    for (int c = 0; c < CZ / 4; ++c) {
+  for (int n = 0; n < NCH; ++n) {
+    const int idx = t + 256 * n;
+    const int ch = idx & 7, z = (idx >> 3) % CZ, kb = (idx >> 3) / CZ;
+    wreg[n] = __ldg(reinterpret_cast<const uint4*>(w1 + (long long)z * CS + kb * 64 + ch * 8));
+  }
+  const int j = jt * 128 + lane_row;
+  const bool valid = j < N;
+  float uj[HC];
+  if (valid) {
+    const float4* up = reinterpret_cast<const float4*>(u + ((long long)b * N + j) * CZ + grp * HC);
+#pragma unroll
+    for (int c = 0; c < HC / 4; ++c) {
       const float4 v = __ldg(up + c);
       uj[c * 4] = v.x; uj[c * 4 + 1] = v.y; uj[c * 4 + 2] = v.z; uj[c * 4 + 3] = v.w;
     }
   } else {
 #pragma unroll
-    for (int c = 0; c < CZ; ++c) uj[c] = 0.f;
+    for (int c = 0; c < HC; ++c) uj[c] = 0.f;
   }
   mbar_wait(bar_a, 0);
+
   uint32_t mma_phase = 0;
-  for (int i = i0; i < i1; ++i) {
-    const float* xi = xn32 + ((long long)b * N + i) * CS;
-    for (int d = t; d < CS; d += 128) sXi[d] = xi[d];
-    if (t < CZ) sUi[t] = u[((long long)b * N + i) * CZ + t];
-    __syncthreads();
-    // B'[z][d] = W1[z][d] * x_i[d]   (fp32 product, rounded once to fp16)
-    const int total = KBS * CZ * 8;
-    for (int idx = t; idx < total; idx += 128) {
-      const int ch = idx & 7;
-      const int z = (idx >> 3) % CZ;
-      const int kb = (idx >> 3) / CZ;
-      const int d0 = kb * 64 + ch * 8;
-      const uint4 wv = __ldg(reinterpret_cast<const uint4*>(w1 + (long long)z * CS + d0));
-      const __half2* w2 = reinterpret_cast<const __half2*>(&wv);
-      const float4 xa = *reinterpret_cast<const float4*>(sXi + d0);
-      const float4 xb = *reinterpret_cast<const float4*>(sXi + d0 + 4);
-      const float2 f0 = __half22float2(w2[0]), f1 = __half22float2(w2[1]);
-      const float2 f2 = __half22float2(w2[2]), f3 = __half22float2(w2[3]);
-      uint4 o;
-      o.x = pack_half2(f0.x * xa.x, f0.y * xa.y);
-      o.y = pack_half2(f1.x * xa.z, f1.y * xa.w);
-      o.z = pack_half2(f2.x * xb.x, f2.y * xb.y);
-      o.w = pack_half2(f3.x * xb.z, f3.y * xb.w);
-      *reinterpret_cast<uint4*>(sB + kb * CZ * 128 + sw128_offset(z, ch)) = o;
-    }
-    sync_before_mma();
-    if (t == 0) {
-      tc_fence_after();
-      umma_multi(tmem, smem_u32(sA), smem_u32(sB), KBS, CZ * 128, umma_idesc_f16(128, CZ), false);
-      umma_commit(mma_bar);
-    }
-    mbar_wait(mma_bar, mma_phase);
-    mma_phase ^= 1;
-    tc_fence_after();
-    const long long roff = (((long long)b * N + i) * N + j) * CZ;
-    const float* prow = pair + roff;
-    float* drow = dst + roff;
+  // epilogue of row `ie` from accumulator `ie & 1`; `res` holds the prefetched residual values
+  auto epilogue = [&](int ie, const float4 (&res)[HC / 4]) {
+    float* drow = dst + (((long long)b * N + ie) * N + j) * CZ + grp * HC;
+    const float* ui = sUi + (ie & 1) * CZ + grp * HC;
+    const float* bs = sBias + grp * HC;
 #pragma unroll
-    for (int c = 0; c < CZ / 32; ++c) {
-      uint32_t acc[32];
-      tmem_ld32(tm_lane + c * 32, acc);
+    for (int c = 0; c < HC / 16; ++c) {
+      uint32_t acc[16];
+      tmem_ld16(tm_lane + (ie & 1) * CZ + grp * HC + c * 16, acc);
       tmem_ld_wait();
       if (valid) {
 #pragma unroll
-        for (int q = 0; q < 32; q += 4) {
-          float4 x = residual ? *reinterpret_cast<const float4*>(prow + c * 32 + q) : make_float4(0.f, 0.f, 0.f, 0.f);
-          x.x += __uint_as_float(acc[q + 0]) + sUi[c * 32 + q + 0] - uj[c * 32 + q + 0] + sBias[c * 32 + q + 0];
-          x.y += __uint_as_float(acc[q + 1]) + sUi[c * 32 + q + 1] - uj[c * 32 + q + 1] + sBias[c * 32 + q + 1];
-          x.z += __uint_as_float(acc[q + 2]) + sUi[c * 32 + q + 2] - uj[c * 32 + q + 2] + sBias[c * 32 + q + 2];
-          x.w += __uint_as_float(acc[q + 3]) + sUi[c * 32 + q + 3] - uj[c * 32 + q + 3] + sBias[c * 32 + q + 3];
-          *reinterpret_cast<float4*>(drow + c * 32 + q) = x;
+        for (int q = 0; q < 16; q += 4) {
+          float4 x = res[c * 4 + q / 4];
+          x.x += __uint_as_float(acc[q + 0]) + ui[c * 16 + q + 0] - uj[c * 16 + q + 0] + bs[c * 16 + q + 0];
+          x.y += __uint_as_float(acc[q + 1]) + ui[c * 16 + q + 1] - uj[c * 16 + q + 1] + bs[c * 16 + q + 1];
+          x.z += __uint_as_float(acc[q + 2]) + ui[c * 16 + q + 2] - uj[c * 16 + q + 2] + bs[c * 16 + q + 2];
+          x.w += __uint_as_float(acc[q + 3]) + ui[c * 16 + q + 3] - uj[c * 16 + q + 3] + bs[c * 16 + q + 3];
+          *reinterpret_cast<float4*>(drow + c * 16 + q) = x;
         }
       }
     }
-    // sXi / sUi / sB and the accumulator columns are rewritten by the next i
-    tc_fence_before();
+  };
+
+  for (int i = i0; i <= i1; ++i) {
+    // (1) prefetch the residual of row i-1 (consumed after the UMMAs of row i are issued)
+    float4 res[HC / 4];
+#pragma unroll
+    for (int c = 0; c < HC / 4; ++c) res[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (i > i0 && residual && valid) {
+      const float4* pr = reinterpret_cast<const float4*>(pair + (((long long)b * N + (i - 1)) * N + j) * CZ + grp * HC);
+#pragma unroll
+      for (int c = 0; c < HC / 4; ++c) res[c] = pr[c];
+    }
+    if (i < i1) {
+      // (2) x_i, u_i -> shared
+      const float* xi = xn32 + ((long long)b * N + i) * CS;
+      for (int d = t; d < CS; d += 256) sXi[d] = xi[d];
+    }
+    // (3) the UMMAs of row i-1 read sB: they must be complete before sB is rebuilt
+    if (i > i0) {
+      mbar_wait(mma_bar, mma_phase);
+      mma_phase ^= 1;
+      tc_fence_after();
+    }
     __syncthreads();
+    if (i < i1) {
+      // u_i is read by the epilogue of row i (next iteration); its slot was last read by the epilogue of
+      // row i-2, which every thread finished before the barrier above
+      if (t < CZ) sUi[(i & 1) * CZ + t] = u[((long long)b * N + i) * CZ + t];
+      // (4) B'[z][d] = W1[z][d] * x_i[d]   (fp32 product, rounded once to fp16)
+#pragma unroll
+      for (int n = 0; n < NCH; ++n) {
+        const int idx = t + 256 * n;
+        const int ch = idx & 7, z = (idx >> 3) % CZ, kb = (idx >> 3) / CZ;
+        const int d0 = kb * 64 + ch * 8;
+        const __half2* w2 = reinterpret_cast<const __half2*>(&wreg[n]);
+        const float4 xa = *reinterpret_cast<const float4*>(sXi + d0);
+        const float4 xb = *reinterpret_cast<const float4*>(sXi + d0 + 4);
+        const float2 f0 = __half22float2(w2[0]), f1 = __half22float2(w2[1]);
+        const float2 f2 = __half22float2(w2[2]), f3 = __half22float2(w2[3]);
+        uint4 o;
+        o.x = pack_half2(f0.x * xa.x, f0.y * xa.y);
+        o.y = pack_half2(f1.x * xa.z, f1.y * xa.w);
+        o.z = pack_half2(f2.x * xb.x, f2.y * xb.y);
+        o.w = pack_half2(f3.x * xb.z, f3.y * xb.w);
+        *reinterpret_cast<uint4*>(sB + kb * CZ * 128 + sw128_offset(z, ch)) = o;
+      }
+      sync_before_mma();
+      if (t == 0) {
+        tc_fence_after();
+        umma_multi(tmem + (i & 1) * CZ, smem_u32(sA), smem_u32(sB), KBS, CZ * 128, umma_idesc_f16(128, CZ), false);
+        umma_commit(mma_bar);
+      }
+    }
+    // (5) epilogue of row i-1 overlaps the UMMAs of row i
+    if (i > i0) epilogue(i - 1, res);
+    // the accumulator (i-1)&1 is rewritten by row i+1 only after the next __syncthreads
+    tc_fence_before();
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem, TCOLS);
 }
 
+template <int CZ, int KBS>
+static int launch_outer_linear(const CUtensorMap& mx, dim3 grid, const float* pair, float* dst, int residual,
+                               const float* xn32, const __half* w1, const float* u, const float* bias, int N, int ilen,
+                               cudaStream_t s) {
+  constexpr int smem = 1024 + KBS * 16384 + KBS * CZ * 128 + (KBS * 64 + 3 * CZ) * 4 + 64;
+  static_assert(smem <= 227 * 1024, "outer_linear shared memory budget");
+  auto kern = outer_linear_kernel<CZ, KBS>;
+  PRD_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  kern<<<grid, 256, smem, s>>>(mx, pair, dst, residual, xn32, w1, u, bias, N, ilen);
+  PRD_LAUNCHED();
+  return 0;
+}
+
 int outer_linear(const PairDims& d, int CS, const float* pair, float* dst, int residual, const __half* xn16,
                  const float* xn32, const __half* w1, const float* u, const float* bias, cudaStream_t s) {
-  PRD_REQUIRE(CS % 64 == 0 && CS <= 512, "outer_linear: single_dim %d must be a multiple of 64 and <= 512", CS);
-  const int N = d.N, KBS = CS / 64;
+  PRD_REQUIRE(CS == 512 || CS == 256, "outer_linear: single_dim %d unsupported (built: 512, 256)", CS);
+  PRD_REQUIRE(d.CZ == 64 || d.CZ == 32, "outer_linear: pair_dim %d unsupported (built: 64, 32)", d.CZ);
+  const int N = d.N;
   CUtensorMap mx;
   TmaDims t;
   t.size[0] = (uint64_t)CS; t.size[1] = (uint64_t)N; t.size[2] = (uint64_t)d.B; t.size[3] = 1;
@@ -146,29 +198,17 @@ int outer_linear(const PairDims& d, int CS, const float* pair, float* dst, int r
   t.box[0] = 64; t.box[1] = 128; t.box[2] = 1; t.box[3] = 1;
   if (make_tensor_map(&mx, xn16, 2, 3, t, true)) return 1;
   const int jtiles = (N + 127) / 128;
-  // enough CTAs for a few waves; every CTA re-uses its A tile for `ilen` rows
+  // enough CTAs for a few waves; every CTA re-uses its A tile and its W1 registers for `ilen` rows
   int ichunks = (4 * kNumSMs + jtiles * d.B - 1) / (jtiles * d.B);
   if (ichunks > N) ichunks = N;
   if (ichunks < 1) ichunks = 1;
   const int ilen = (N + ichunks - 1) / ichunks;
   ichunks = (N + ilen - 1) / ilen;
   dim3 grid(jtiles, ichunks, d.B);
-  if (d.CZ == 64) {
-    const int smem = 1024 + KBS * 16384 + KBS * 64 * 128 + (CS + 2 * 64) * 4 + 64;
-    auto kern = outer_linear_kernel<64>;
-    PRD_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    kern<<<grid, 128, smem, s>>>(mx, pair, dst, residual, xn32, w1, u, bias, N, CS, ilen);
-  } else if (d.CZ == 32) {
-    const int smem = 1024 + KBS * 16384 + KBS * 32 * 128 + (CS + 2 * 32) * 4 + 64;
-    auto kern = outer_linear_kernel<32>;
-    PRD_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    kern<<<grid, 128, smem, s>>>(mx, pair, dst, residual, xn32, w1, u, bias, N, CS, ilen);
-  } else {
-    set_error("outer_linear: unsupported pair_dim %d", d.CZ);
-    return 1;
-  }
-  PRD_LAUNCHED();
-  return 0;
+  if (d.CZ == 64 && CS == 512) return launch_outer_linear<64, 8>(mx, grid, pair, dst, residual, xn32, w1, u, bias, N, ilen, s);
+  if (d.CZ == 64 && CS == 256) return launch_outer_linear<64, 4>(mx, grid, pair, dst, residual, xn32, w1, u, bias, N, ilen, s);
+  if (d.CZ == 32 && CS == 512) return launch_outer_linear<32, 8>(mx, grid, pair, dst, residual, xn32, w1, u, bias, N, ilen, s);
+  return launch_outer_linear<32, 4>(mx, grid, pair, dst, residual, xn32, w1, u, bias, N, ilen, s);
 }
 
 // =========================================================================================
