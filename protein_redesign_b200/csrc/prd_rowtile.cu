@@ -232,57 +232,61 @@ int pair_transition(const PairDims& d, const float* pair, float* dst, int residu
 // that both einsum modes become plain K-major NT GEMMs  x_d[i,j] = sum_k a_d[i,k] b_d[j,k]:
 //   outgoing: a_d[i,k] = a[b,i,k,d]      (logical row (b,i,k) reads pair[b,i,k])
 //   incoming: a_d[i,k] = a[b,k,i,d]      (logical row (b,i,k) reads pair[b,k,i])
-// w_in rows: [0,2CZ) = ab_proj, [2CZ,4CZ) = ab_gate.
+// w_in: fp16 pair [hi; lo], each [4CZ x CZ] with rows [0,2CZ) = ab_proj, [2CZ,4CZ) = ab_gate.
+// 256 threads = two compute groups (see Group).
 // =========================================================================================
 template <int CZ>
-__global__ void __launch_bounds__(128, 1)
+__global__ void __launch_bounds__(256, 1)
 trimul_in_kernel(const float* __restrict__ pair, const float* __restrict__ mask, RowMap map, int B, long long R,
                  const __half* __restrict__ w_in, const float* __restrict__ b_in, __half* __restrict__ ab, int Np) {
   extern __shared__ uint8_t raw[];
   constexpr int NOUT = 4 * CZ;
+  constexpr int kGroupBytes = 16384 + (RowStage<CZ>::kBytes + 1023) / 1024 * 1024;
   uint8_t* sm = smem_align1024(raw);
-  uint8_t* sA = sm;
-  uint8_t* sW = sA + 16384;            // hi
-  uint8_t* sWl = sW + NOUT * 128;      // lo (weight = hi + lo, both fp16: removes the systematic rounding)
-  uint8_t* sSt = sWl + NOUT * 128;
-  float* sB = reinterpret_cast<float*>(sSt + 2 * RowStage<CZ>::kBytes);
-  uint64_t* full = reinterpret_cast<uint64_t*>(sB + NOUT);
-  uint64_t* mma_bar = full + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mma_bar + 1);
+  uint8_t* sW = sm;                  // hi
+  uint8_t* sWl = sW + NOUT * 128;    // lo
+  uint8_t* sG = sWl + NOUT * 128;    // per group: A tile, row stage
+  float* sB = reinterpret_cast<float*>(sG + 2 * kGroupBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + NOUT);  // full[2], mma[2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
 
-  const int t = threadIdx.x, warp = t >> 5;
-  if (t == 0) {
-    mbar_init(&full[0], kTileRows);
-    mbar_init(&full[1], kTileRows);
-    mbar_init(mma_bar, 1);
+  const Group g;
+  uint8_t* sA = sG + g.grp * kGroupBytes;
+  uint8_t* sSt = sA + 16384;
+  uint64_t* full = bars + g.grp;
+  uint64_t* mma_bar = bars + 2 + g.grp;
+  if (threadIdx.x == 0) {
+    mbar_init(&bars[0], kTileRows);
+    mbar_init(&bars[1], kTileRows);
+    mbar_init(&bars[2], 1);
+    mbar_init(&bars[3], 1);
     fence_barrier_init();
   }
-  if (warp == 0) tmem_alloc(tmem_slot, NOUT);
-  load_weight_kblocks(sW, w_in, NOUT, CZ, CZ, t, 128);
-  load_weight_kblocks(sWl, w_in + NOUT * CZ, NOUT, CZ, CZ, t, 128);
-  for (int i = t; i < NOUT; i += 128) sB[i] = b_in[i];
+  if (threadIdx.x < 32) tmem_alloc(tmem_slot, 2 * NOUT);
+  load_weight_kblocks(sW, w_in, NOUT, CZ, CZ, threadIdx.x, 256);
+  load_weight_kblocks(sWl, w_in + NOUT * CZ, NOUT, CZ, CZ, threadIdx.x, 256);
+  for (int i = threadIdx.x; i < NOUT; i += 256) sB[i] = b_in[i];
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem = *tmem_slot;
-  const uint32_t tm_lane = tmem + (static_cast<uint32_t>(warp * 32) << 16);
+  const uint32_t tmem = *tmem_slot + g.grp * NOUT;
+  const uint32_t tm_lane = tmem + (static_cast<uint32_t>(g.warp * 32) << 16);
   const long long plane = (long long)map.N * Np;
+  const int t = g.t;
 
   const long long num_tiles = (R + kTileRows - 1) / kTileRows;
+  const long long stride = (long long)gridDim.x * 2;
   uint32_t mma_phase = 0;
-  long long tile = blockIdx.x;
-  auto issue = [&](long long tl, int buf) {
+  long long tile = (long long)blockIdx.x * 2 + g.grp;
+  auto issue = [&](long long tl) {
     const long long r = tl * kTileRows + t;
     int b = 0, s = 0, k = 0;
     if (r < R) map.decompose(r, b, s, k);
-    issue_row_load<CZ>(sSt + buf * RowStage<CZ>::kBytes, t, pair + map.src_row(b, s, k) * CZ, r < R, &full[buf]);
+    issue_row_load<CZ>(sSt, t, pair + map.src_row(b, s, k) * CZ, r < R, full);
   };
-  if (tile < num_tiles) issue(tile, 0);
-  for (int it = 0; tile < num_tiles; tile += gridDim.x, ++it) {
-    const int buf = it & 1;
-    const long long next = tile + gridDim.x;
-    if (next < num_tiles) issue(next, buf ^ 1);
-    mbar_wait(&full[buf], (it >> 1) & 1);
+  if (tile < num_tiles) issue(tile);
+  for (int it = 0; tile < num_tiles; tile += stride, ++it) {
+    mbar_wait(full, it & 1);
     const long long r = tile * kTileRows + t;
     const bool valid = r < R;
     int b = 0, i = 0, k = 0;
@@ -290,15 +294,16 @@ trimul_in_kernel(const float* __restrict__ pair, const float* __restrict__ mask,
     {
       float x[CZ];
       if (valid) {
-        read_row<CZ>(stage_row<CZ>(sSt + buf * RowStage<CZ>::kBytes, t), x);
+        read_row<CZ>(stage_row<CZ>(sSt, t), x);
       } else {
 #pragma unroll
         for (int q = 0; q < CZ; ++q) x[q] = 0.f;
       }
+      if (tile + stride < num_tiles) issue(tile + stride);  // this thread's stage slot is free again
       layernorm_inplace<CZ>(x);
       store_a_row<CZ>(sA, t, x);
     }
-    sync_before_mma();
+    g.sync_before_mma();
     if (t == 0) {
       tc_fence_after();
       umma_multi(tmem, smem_u32(sA), smem_u32(sW), 1, NOUT * 128, umma_idesc_f16(128, NOUT), false);
@@ -321,105 +326,105 @@ trimul_in_kernel(const float* __restrict__ pair, const float* __restrict__ mask,
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
           const int cc = c * 32 + j;  // channel in [0, 2CZ): a = [0,CZ), b = [CZ,2CZ)
-          const float g = sigmoidf_fast(__uint_as_float(ga[j]) + sB[2 * CZ + cc]);
-          const float v = m2 * g * (__uint_as_float(pr[j]) + sB[cc]);
+          const float gt = sigmoidf_fast(__uint_as_float(ga[j]) + sB[2 * CZ + cc]);
+          const float v = m2 * gt * (__uint_as_float(pr[j]) + sB[cc]);
           const long long pl = (cc < CZ) ? cc : (cc - CZ) + (long long)B * CZ;
           dst0[pl * plane] = __float2half_rn(v);
         }
       }
     }
-    // all TMEM reads of this tile must retire before the next tile's MMA overwrites the columns
+    // the next tile's UMMA overwrites these TMEM columns only after the group barrier in sync_before_mma
     tc_fence_before();
-    __syncthreads();
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem, NOUT);
+  if (threadIdx.x < 32) tmem_dealloc(*tmem_slot, 2 * NOUT);
 }
 
-int trimul_in(const PairDims& d, const float* pair, const float* mask, int mode, const __half* w_in, const float* b_in,
-              __half* ab, cudaStream_t s) {
+template <int CZ>
+static int launch_trimul_in(const PairDims& d, const float* pair, const float* mask, int mode, const __half* w_in,
+                            const float* b_in, __half* ab, cudaStream_t s) {
   const long long R = (long long)d.B * d.N * d.N;
   const long long tiles = (R + kTileRows - 1) / kTileRows;
   RowMap map{d.N, (long long)d.N * d.N, mode};
-  const int Np = plane_ld(d.N);
-  if (d.CZ == 64) {
-    constexpr int CZ = 64;
-    constexpr int smem = 1024 + 16384 + 2 * 4 * CZ * 128 + 2 * RowStage<CZ>::kBytes + 4 * CZ * 4 + 64;
-    auto kern = trimul_in_kernel<CZ>;
-    if (set_smem(kern, smem)) return 1;
-    kern<<<grid_for(tiles, 2), 128, smem, s>>>(pair, mask, map, d.B, R, w_in, b_in, ab, Np);
-  } else if (d.CZ == 32) {
-    constexpr int CZ = 32;
-    constexpr int smem = 1024 + 16384 + 2 * 4 * CZ * 128 + 2 * RowStage<CZ>::kBytes + 4 * CZ * 4 + 64;
-    auto kern = trimul_in_kernel<CZ>;
-    if (set_smem(kern, smem)) return 1;
-    kern<<<grid_for(tiles, 2), 128, smem, s>>>(pair, mask, map, d.B, R, w_in, b_in, ab, Np);
-  } else {
-    set_error("trimul_in: unsupported pair_dim %d", d.CZ);
-    return 1;
-  }
+  constexpr int kGroupBytes = 16384 + (RowStage<CZ>::kBytes + 1023) / 1024 * 1024;
+  constexpr int smem = 1024 + 2 * 4 * CZ * 128 + 2 * kGroupBytes + 4 * CZ * 4 + 64;
+  auto kern = trimul_in_kernel<CZ>;
+  if (set_smem(kern, smem)) return 1;
+  kern<<<grid_for((tiles + 1) / 2, 1), 256, smem, s>>>(pair, mask, map, d.B, R, w_in, b_in, ab, plane_ld(d.N));
   PRD_LAUNCHED();
   return 0;
 }
 
+int trimul_in(const PairDims& d, const float* pair, const float* mask, int mode, const __half* w_in, const float* b_in,
+              __half* ab, cudaStream_t s) {
+  if (d.CZ == 64) return launch_trimul_in<64>(d, pair, mask, mode, w_in, b_in, ab, s);
+  if (d.CZ == 32) return launch_trimul_in<32>(d, pair, mask, mode, w_in, b_in, ab, s);
+  set_error("trimul_in: unsupported pair_dim %d", d.CZ);
+  return 1;
+}
+
 // =========================================================================================
-// Triangle multiplication, output side: pair += sigmoid(Go p + bgo) * (Wo LN(x) + bo)
-// x: fp32 planes [B][CZ][N][Nx] from the contraction GEMM.  w_out rows: [0,CZ) out_gate, [CZ,2CZ) out_proj.
+// Triangle multiplication, output side: dst = [pair +] sigmoid(Go p + bgo) * (Wo LN(x) + bo)
+// x: fp32 planes [B][CZ][N][Nx] from the contraction GEMM.  w_out: fp16 pair, four [CZ x CZ] tiles
+// in the order out_gate_hi, out_proj_hi, out_gate_lo, out_proj_lo.  Two compute groups; the pair row
+// stays in registers for the residual, the output is staged over the (then idle) A tiles.
 // =========================================================================================
 template <int CZ>
-__global__ void __launch_bounds__(128, 1)
+__global__ void __launch_bounds__(256, 1)
 trimul_out_kernel(const float* pair, float* dst, int residual, const float* __restrict__ xpl, int N, int Nx, long long R,
                   const __half* __restrict__ w_out, const float* __restrict__ b_out) {
   extern __shared__ uint8_t raw[];
+  constexpr int kStage = (RowStage<CZ>::kBytes + 1023) / 1024 * 1024;
+  constexpr int kAO = kStage > 32768 ? kStage : 32768;  // A_p | A_x, re-used as the output stage
+  constexpr int kGroupBytes = kAO + kStage;
   uint8_t* sm = smem_align1024(raw);
-  uint8_t* sAp = sm;
-  uint8_t* sAx = sAp + 16384;
-  uint8_t* sW = sAx + 16384;  // four B tiles of [CZ x 64]: gate_hi, proj_hi, gate_lo, proj_lo
-  uint8_t* sSt = sW + 4 * CZ * 128;
-  float* sB = reinterpret_cast<float*>(sSt + 2 * RowStage<CZ>::kBytes);
-  uint64_t* full = reinterpret_cast<uint64_t*>(sB + 2 * CZ);
-  uint64_t* mma_bar = full + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mma_bar + 1);
+  uint8_t* sW = sm;  // four B tiles of [CZ x 64]
+  uint8_t* sG = sW + 4 * CZ * 128;
+  float* sB = reinterpret_cast<float*>(sG + 2 * kGroupBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + 2 * CZ);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
   constexpr int TCOLS = 2 * CZ;
 
-  const int t = threadIdx.x, warp = t >> 5;
-  if (t == 0) {
-    mbar_init(&full[0], kTileRows);
-    mbar_init(&full[1], kTileRows);
-    mbar_init(mma_bar, 1);
+  const Group g;
+  uint8_t* sAp = sG + g.grp * kGroupBytes;
+  uint8_t* sAx = sAp + 16384;
+  uint8_t* sSt = sAp + kAO;
+  uint64_t* full = bars + g.grp;
+  uint64_t* mma_bar = bars + 2 + g.grp;
+  if (threadIdx.x == 0) {
+    mbar_init(&bars[0], kTileRows);
+    mbar_init(&bars[1], kTileRows);
+    mbar_init(&bars[2], 1);
+    mbar_init(&bars[3], 1);
     fence_barrier_init();
   }
-  if (warp == 0) tmem_alloc(tmem_slot, TCOLS);
-  for (int q = 0; q < 4; ++q) load_weight_kblocks(sW + q * CZ * 128, w_out + q * CZ * CZ, CZ, CZ, CZ, t, 128);
-  for (int i = t; i < 2 * CZ; i += 128) sB[i] = b_out[i];
+  if (threadIdx.x < 32) tmem_alloc(tmem_slot, 2 * TCOLS);
+  for (int q = 0; q < 4; ++q) load_weight_kblocks(sW + q * CZ * 128, w_out + q * CZ * CZ, CZ, CZ, CZ, threadIdx.x, 256);
+  for (int i = threadIdx.x; i < 2 * CZ; i += 256) sB[i] = b_out[i];
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem = *tmem_slot;
-  const uint32_t tm_lane = tmem + (static_cast<uint32_t>(warp * 32) << 16);
+  const uint32_t tmem = *tmem_slot + g.grp * TCOLS;
+  const uint32_t tm_lane = tmem + (static_cast<uint32_t>(g.warp * 32) << 16);
   const long long NN = (long long)N * N;
   const long long xplane = (long long)N * Nx;
+  const int t = g.t;
 
   const long long num_tiles = (R + kTileRows - 1) / kTileRows;
+  const long long stride = (long long)gridDim.x * 2;
   uint32_t mma_phase = 0;
-  long long tile = blockIdx.x;
+  long long tile = (long long)blockIdx.x * 2 + g.grp;
   if (tile < num_tiles) {
     const long long r = tile * kTileRows + t;
-    issue_row_load<CZ>(sSt, t, pair + r * CZ, r < R, &full[0]);
+    issue_row_load<CZ>(sSt, t, pair + r * CZ, r < R, full);
   }
-  for (int it = 0; tile < num_tiles; tile += gridDim.x, ++it) {
-    const int buf = it & 1;
-    uint8_t* st = sSt + buf * RowStage<CZ>::kBytes;
-    const long long next = tile + gridDim.x;
-    if (next < num_tiles) {
-      bulk_wait_read0();
-      const long long rn = next * kTileRows + t;
-      issue_row_load<CZ>(sSt + (buf ^ 1) * RowStage<CZ>::kBytes, t, pair + rn * CZ, rn < R, &full[buf ^ 1]);
-    }
+  for (int it = 0; tile < num_tiles; tile += stride, ++it) {
     const long long r = tile * kTileRows + t;
     const bool valid = r < R;
-    float* my = stage_row<CZ>(st, t);
+    // the previous tile's output rows were staged over the A tiles: its bulk stores must have read them
+    bulk_wait_read0();
+    g.bar();
     {
       // contraction result for this (b,i,j): one value per channel plane, coalesced across lanes
       float x[CZ];
@@ -437,19 +442,26 @@ trimul_out_kernel(const float* pair, float* dst, int residual, const float* __re
       layernorm_inplace<CZ>(x);
       store_a_row<CZ>(sAx, t, x);
     }
-    mbar_wait(&full[buf], (it >> 1) & 1);
-    {
-      float x[CZ];
-      if (valid) {
-        read_row<CZ>(my, x);
-      } else {
+    mbar_wait(full, it & 1);
+    float xr[CZ];
+    if (valid) {
+      read_row<CZ>(stage_row<CZ>(sSt, t), xr);
+    } else {
 #pragma unroll
-        for (int q = 0; q < CZ; ++q) x[q] = 0.f;
-      }
-      layernorm_inplace<CZ>(x);
-      store_a_row<CZ>(sAp, t, x);
+      for (int q = 0; q < CZ; ++q) xr[q] = 0.f;
     }
-    sync_before_mma();
+    if (tile + stride < num_tiles) {
+      const long long rn = (tile + stride) * kTileRows + t;
+      issue_row_load<CZ>(sSt, t, pair + rn * CZ, rn < R, full);
+    }
+    {
+      float y[CZ];
+#pragma unroll
+      for (int q = 0; q < CZ; ++q) y[q] = xr[q];
+      layernorm_inplace<CZ>(y);
+      store_a_row<CZ>(sAp, t, y);
+    }
+    g.sync_before_mma();
     if (t == 0) {
       tc_fence_after();
       umma_multi(tmem, smem_u32(sAp), smem_u32(sW), 1, CZ * 128, umma_idesc_f16(128, CZ), false);
@@ -461,6 +473,7 @@ trimul_out_kernel(const float* pair, float* dst, int residual, const float* __re
     mbar_wait(mma_bar, mma_phase);
     mma_phase ^= 1;
     tc_fence_after();
+    float* my = stage_row<CZ>(sAp, t);  // output stage over the A tiles (their UMMAs are complete)
 #pragma unroll
     for (int c = 0; c < CZ / 32; ++c) {
       uint32_t ga[32], pr[32];
@@ -469,128 +482,125 @@ trimul_out_kernel(const float* pair, float* dst, int residual, const float* __re
       tmem_ld_wait();
 #pragma unroll
       for (int j = 0; j < 32; j += 4) {
-        float4 x = *reinterpret_cast<float4*>(my + c * 32 + j);
-        if (!residual) x = make_float4(0.f, 0.f, 0.f, 0.f);
         float o[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const int cc = c * 32 + j + e;
           o[e] = sigmoidf_fast(__uint_as_float(ga[j + e]) + sB[cc]) * (__uint_as_float(pr[j + e]) + sB[CZ + cc]);
+          if (residual) o[e] += xr[cc];
         }
-        x.x += o[0];
-        x.y += o[1];
-        x.z += o[2];
-        x.w += o[3];
-        *reinterpret_cast<float4*>(my + c * 32 + j) = x;
+        *reinterpret_cast<float4*>(my + c * 32 + j) = make_float4(o[0], o[1], o[2], o[3]);
       }
     }
     fence_proxy_async_smem();
     if (valid) bulk_s2g(dst + r * CZ, my, CZ * 4);
     bulk_commit();
     tc_fence_before();
-    __syncthreads();
   }
   bulk_wait0();
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem, TCOLS);
+  if (threadIdx.x < 32) tmem_dealloc(*tmem_slot, 2 * TCOLS);
 }
 
-int trimul_out(const PairDims& d, const float* pair, float* dst, int residual, const float* x, const __half* w_out,
-               const float* b_out, cudaStream_t s) {
+template <int CZ>
+static int launch_trimul_out(const PairDims& d, const float* pair, float* dst, int residual, const float* x,
+                             const __half* w_out, const float* b_out, cudaStream_t s) {
   const long long R = (long long)d.B * d.N * d.N;
   const long long tiles = (R + kTileRows - 1) / kTileRows;
-  const int Nx = xplane_ld(d.N);
-  if (d.CZ == 64) {
-    constexpr int CZ = 64;
-    constexpr int smem = 1024 + 2 * 16384 + 4 * CZ * 128 + 2 * RowStage<CZ>::kBytes + 2 * CZ * 4 + 64;
-    auto kern = trimul_out_kernel<CZ>;
-    if (set_smem(kern, smem)) return 1;
-    kern<<<grid_for(tiles, 2), 128, smem, s>>>(pair, dst, residual, x, d.N, Nx, R, w_out, b_out);
-  } else if (d.CZ == 32) {
-    constexpr int CZ = 32;
-    constexpr int smem = 1024 + 2 * 16384 + 4 * CZ * 128 + 2 * RowStage<CZ>::kBytes + 2 * CZ * 4 + 64;
-    auto kern = trimul_out_kernel<CZ>;
-    if (set_smem(kern, smem)) return 1;
-    kern<<<grid_for(tiles, 2), 128, smem, s>>>(pair, dst, residual, x, d.N, Nx, R, w_out, b_out);
-  } else {
-    set_error("trimul_out: unsupported pair_dim %d", d.CZ);
-    return 1;
-  }
+  constexpr int kStage = (RowStage<CZ>::kBytes + 1023) / 1024 * 1024;
+  constexpr int kAO = kStage > 32768 ? kStage : 32768;
+  constexpr int smem = 1024 + 4 * CZ * 128 + 2 * (kAO + kStage) + 2 * CZ * 4 + 64;
+  auto kern = trimul_out_kernel<CZ>;
+  if (set_smem(kern, smem)) return 1;
+  kern<<<grid_for((tiles + 1) / 2, 1), 256, smem, s>>>(pair, dst, residual, x, d.N, xplane_ld(d.N), R, w_out, b_out);
   PRD_LAUNCHED();
   return 0;
 }
 
+int trimul_out(const PairDims& d, const float* pair, float* dst, int residual, const float* x, const __half* w_out,
+               const float* b_out, cudaStream_t s) {
+  if (d.CZ == 64) return launch_trimul_out<64>(d, pair, dst, residual, x, w_out, b_out, s);
+  if (d.CZ == 32) return launch_trimul_out<32>(d, pair, dst, residual, x, w_out, b_out, s);
+  set_error("trimul_out: unsupported pair_dim %d", d.CZ);
+  return 1;
+}
+
 // =========================================================================================
 // Triangle attention projections.  Logical row (b, seq, tok): "starting" reads pair[b,seq,tok],
-// "ending" reads pair[b,tok,seq].  w rows: [0,64) q, [64,128) k, [128,192) v, [192,256) gate.
+// "ending" reads pair[b,tok,seq].  w: fp16 pair [hi; lo], each [256 x CZ] with rows [0,64) q,
+// [64,128) k, [128,192) v, [192,256) gate.
 // Outputs (fp16): q (pre-scaled by 1/sqrt(c) = 0.25), k, g = sigmoid(gate) as [rows][64];
 // v transposed per sequence: vt[(b*N+seq)][h*16+c][tok] (tok contiguous, row stride plane_ld(N)),
-// i.e. the K-major B operand of the P.V product.
+// i.e. the K-major B operand of the P.V product.  Two compute groups.
 // =========================================================================================
 template <int CZ>
-__global__ void __launch_bounds__(128, 1)
+__global__ void __launch_bounds__(256, 1)
 triattn_proj_kernel(const float* __restrict__ pair, RowMap map, long long R, const __half* __restrict__ w,
                     const float* __restrict__ b_gate, __half* __restrict__ q, __half* __restrict__ k,
-                    __half* __restrict__ g, __half* __restrict__ vt, int Np) {
+                    __half* __restrict__ gout, __half* __restrict__ vt, int Np) {
   extern __shared__ uint8_t raw[];
   constexpr int NOUT = 256;
+  constexpr int kGroupBytes = 16384 + (RowStage<CZ>::kBytes + 1023) / 1024 * 1024;
   uint8_t* sm = smem_align1024(raw);
-  uint8_t* sA = sm;
-  uint8_t* sW = sA + 16384;
+  uint8_t* sW = sm;
   uint8_t* sWl = sW + NOUT * 128;
-  uint8_t* sSt = sWl + NOUT * 128;
-  float* sB = reinterpret_cast<float*>(sSt + 2 * RowStage<CZ>::kBytes);
-  uint64_t* full = reinterpret_cast<uint64_t*>(sB + 64);
-  uint64_t* mma_bar = full + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mma_bar + 1);
+  uint8_t* sG = sWl + NOUT * 128;
+  float* sB = reinterpret_cast<float*>(sG + 2 * kGroupBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + 64);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
 
-  const int t = threadIdx.x, warp = t >> 5;
-  if (t == 0) {
-    mbar_init(&full[0], kTileRows);
-    mbar_init(&full[1], kTileRows);
-    mbar_init(mma_bar, 1);
+  const Group g;
+  uint8_t* sA = sG + g.grp * kGroupBytes;
+  uint8_t* sSt = sA + 16384;
+  uint64_t* full = bars + g.grp;
+  uint64_t* mma_bar = bars + 2 + g.grp;
+  if (threadIdx.x == 0) {
+    mbar_init(&bars[0], kTileRows);
+    mbar_init(&bars[1], kTileRows);
+    mbar_init(&bars[2], 1);
+    mbar_init(&bars[3], 1);
     fence_barrier_init();
   }
-  if (warp == 0) tmem_alloc(tmem_slot, NOUT);
-  load_weight_kblocks(sW, w, NOUT, CZ, CZ, t, 128);
-  load_weight_kblocks(sWl, w + NOUT * CZ, NOUT, CZ, CZ, t, 128);
-  if (t < 64) sB[t] = b_gate[t];
+  if (threadIdx.x < 32) tmem_alloc(tmem_slot, 2 * NOUT);
+  load_weight_kblocks(sW, w, NOUT, CZ, CZ, threadIdx.x, 256);
+  load_weight_kblocks(sWl, w + NOUT * CZ, NOUT, CZ, CZ, threadIdx.x, 256);
+  if (threadIdx.x < 64) sB[threadIdx.x] = b_gate[threadIdx.x];
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem = *tmem_slot;
-  const uint32_t tm_lane = tmem + (static_cast<uint32_t>(warp * 32) << 16);
+  const uint32_t tmem = *tmem_slot + g.grp * NOUT;
+  const uint32_t tm_lane = tmem + (static_cast<uint32_t>(g.warp * 32) << 16);
+  const int t = g.t;
 
   const long long num_tiles = (R + kTileRows - 1) / kTileRows;
+  const long long stride = (long long)gridDim.x * 2;
   uint32_t mma_phase = 0;
-  long long tile = blockIdx.x;
-  auto issue = [&](long long tl, int buf) {
+  long long tile = (long long)blockIdx.x * 2 + g.grp;
+  auto issue = [&](long long tl) {
     const long long r = tl * kTileRows + t;
     int b = 0, s = 0, tk = 0;
     if (r < R) map.decompose(r, b, s, tk);
-    issue_row_load<CZ>(sSt + buf * RowStage<CZ>::kBytes, t, pair + map.src_row(b, s, tk) * CZ, r < R, &full[buf]);
+    issue_row_load<CZ>(sSt, t, pair + map.src_row(b, s, tk) * CZ, r < R, full);
   };
-  if (tile < num_tiles) issue(tile, 0);
-  for (int it = 0; tile < num_tiles; tile += gridDim.x, ++it) {
-    const int buf = it & 1;
-    const long long next = tile + gridDim.x;
-    if (next < num_tiles) issue(next, buf ^ 1);
-    mbar_wait(&full[buf], (it >> 1) & 1);
+  if (tile < num_tiles) issue(tile);
+  for (int it = 0; tile < num_tiles; tile += stride, ++it) {
+    mbar_wait(full, it & 1);
     const long long r = tile * kTileRows + t;
     const bool valid = r < R;
     {
       float x[CZ];
       if (valid) {
-        read_row<CZ>(stage_row<CZ>(sSt + buf * RowStage<CZ>::kBytes, t), x);
+        read_row<CZ>(stage_row<CZ>(sSt, t), x);
       } else {
 #pragma unroll
         for (int i = 0; i < CZ; ++i) x[i] = 0.f;
       }
+      if (tile + stride < num_tiles) issue(tile + stride);
       layernorm_inplace<CZ>(x);
       store_a_row<CZ>(sA, t, x);
     }
-    sync_before_mma();
+    g.sync_before_mma();
     if (t == 0) {
       tc_fence_after();
       umma_multi(tmem, smem_u32(sA), smem_u32(sW), 1, NOUT * 128, umma_idesc_f16(128, NOUT), false);
@@ -623,7 +633,7 @@ triattn_proj_kernel(const float* __restrict__ pair, RowMap map, long long R, con
           if (part == 3) a = sigmoidf_fast(a + sB[col0 + j]);
           v[j] = a;
         }
-        __half* dst = (part == 0 ? q : (part == 1 ? k : g)) + r * 64 + col0;
+        __half* dstp = (part == 0 ? q : (part == 1 ? k : gout)) + r * 64 + col0;
 #pragma unroll
         for (int j = 0; j < 32; j += 8) {
           uint4 o;
@@ -631,106 +641,98 @@ triattn_proj_kernel(const float* __restrict__ pair, RowMap map, long long R, con
           o.y = pack_half2(v[j + 2], v[j + 3]);
           o.z = pack_half2(v[j + 4], v[j + 5]);
           o.w = pack_half2(v[j + 6], v[j + 7]);
-          *reinterpret_cast<uint4*>(dst + j) = o;
+          *reinterpret_cast<uint4*>(dstp + j) = o;
         }
       }
     }
     tc_fence_before();
-    __syncthreads();
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem, NOUT);
+  if (threadIdx.x < 32) tmem_dealloc(*tmem_slot, 2 * NOUT);
 }
 
-int triattn_proj(const PairDims& d, const float* pair, int mode, const __half* w_qkvg, const float* b_gate, __half* q,
-                 __half* k, __half* g, __half* vt, cudaStream_t s) {
+template <int CZ>
+static int launch_triattn_proj(const PairDims& d, const float* pair, int mode, const __half* w_qkvg, const float* b_gate,
+                               __half* q, __half* k, __half* g, __half* vt, cudaStream_t s) {
   const long long R = (long long)d.B * d.N * d.N;
   const long long tiles = (R + kTileRows - 1) / kTileRows;
   RowMap map{d.N, (long long)d.N * d.N, mode};
-  const int Np = plane_ld(d.N);
-  if (d.CZ == 64) {
-    constexpr int CZ = 64;
-    constexpr int smem = 1024 + 16384 + 2 * 256 * 128 + 2 * RowStage<CZ>::kBytes + 64 * 4 + 64;
-    auto kern = triattn_proj_kernel<CZ>;
-    if (set_smem(kern, smem)) return 1;
-    kern<<<grid_for(tiles, 2), 128, smem, s>>>(pair, map, R, w_qkvg, b_gate, q, k, g, vt, Np);
-  } else if (d.CZ == 32) {
-    constexpr int CZ = 32;
-    constexpr int smem = 1024 + 16384 + 2 * 256 * 128 + 2 * RowStage<CZ>::kBytes + 64 * 4 + 64;
-    auto kern = triattn_proj_kernel<CZ>;
-    if (set_smem(kern, smem)) return 1;
-    kern<<<grid_for(tiles, 2), 128, smem, s>>>(pair, map, R, w_qkvg, b_gate, q, k, g, vt, Np);
-  } else {
-    set_error("triattn_proj: unsupported pair_dim %d", d.CZ);
-    return 1;
-  }
+  constexpr int kGroupBytes = 16384 + (RowStage<CZ>::kBytes + 1023) / 1024 * 1024;
+  constexpr int smem = 1024 + 2 * 256 * 128 + 2 * kGroupBytes + 64 * 4 + 64;
+  auto kern = triattn_proj_kernel<CZ>;
+  if (set_smem(kern, smem)) return 1;
+  kern<<<grid_for((tiles + 1) / 2, 1), 256, smem, s>>>(pair, map, R, w_qkvg, b_gate, q, k, g, vt, plane_ld(d.N));
   PRD_LAUNCHED();
   return 0;
 }
 
+int triattn_proj(const PairDims& d, const float* pair, int mode, const __half* w_qkvg, const float* b_gate, __half* q,
+                 __half* k, __half* g, __half* vt, cudaStream_t s) {
+  if (d.CZ == 64) return launch_triattn_proj<64>(d, pair, mode, w_qkvg, b_gate, q, k, g, vt, s);
+  if (d.CZ == 32) return launch_triattn_proj<32>(d, pair, mode, w_qkvg, b_gate, q, k, g, vt, s);
+  set_error("triattn_proj: unsupported pair_dim %d", d.CZ);
+  return 1;
+}
+
 // =========================================================================================
-// Triangle attention output projection + residual: pair[src(b,seq,tok)] += Wo og[(b,seq,tok)] + bo
-// og: [rows][64] fp16 gated attention output (logical row order).
+// Triangle attention output projection + residual: dst[src(b,seq,tok)] = [pair +] Wo og[(b,seq,tok)] + bo
+// og: [rows][64] fp16 gated attention output (logical row order).  w_o: fp16 pair [hi; lo], [CZ x 64]
+// each.  Two compute groups, one stage per group used for both the residual row and the output.
 // =========================================================================================
 template <int CZ>
-__global__ void __launch_bounds__(128, 1)
+__global__ void __launch_bounds__(256, 1)
 triattn_out_kernel(const float* pair, float* dst, int residual, RowMap map, long long R, const __half* __restrict__ og,
                    const __half* __restrict__ w_o, const float* __restrict__ b_o) {
   extern __shared__ uint8_t raw[];
+  constexpr int kGroupBytes = 16384 + (RowStage<CZ>::kBytes + 1023) / 1024 * 1024;
   uint8_t* sm = smem_align1024(raw);
-  uint8_t* sA = sm;
-  uint8_t* sW = sA + 16384;
+  uint8_t* sW = sm;
   uint8_t* sWl = sW + CZ * 128;
-  uint8_t* sSt = sWl + CZ * 128;
-  float* sB = reinterpret_cast<float*>(sSt + 2 * RowStage<CZ>::kBytes);
-  uint64_t* full = reinterpret_cast<uint64_t*>(sB + CZ);
-  uint64_t* mma_bar = full + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mma_bar + 1);
+  uint8_t* sG = sm + ((2 * CZ * 128 + 1023) / 1024) * 1024;
+  float* sB = reinterpret_cast<float*>(sG + 2 * kGroupBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + CZ);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
   constexpr int TCOLS = CZ < 32 ? 32 : CZ;
 
-  const int t = threadIdx.x, warp = t >> 5;
-  if (t == 0) {
-    mbar_init(&full[0], kTileRows);
-    mbar_init(&full[1], kTileRows);
-    mbar_init(mma_bar, 1);
+  const Group g;
+  uint8_t* sA = sG + g.grp * kGroupBytes;
+  uint8_t* sSt = sA + 16384;
+  uint64_t* full = bars + g.grp;
+  uint64_t* mma_bar = bars + 2 + g.grp;
+  if (threadIdx.x == 0) {
+    mbar_init(&bars[0], kTileRows);
+    mbar_init(&bars[1], kTileRows);
+    mbar_init(&bars[2], 1);
+    mbar_init(&bars[3], 1);
     fence_barrier_init();
   }
-  if (warp == 0) tmem_alloc(tmem_slot, TCOLS);
-  load_weight_kblocks(sW, w_o, CZ, 64, 64, t, 128);
-  load_weight_kblocks(sWl, w_o + CZ * 64, CZ, 64, 64, t, 128);
-  for (int i = t; i < CZ; i += 128) sB[i] = b_o[i];
+  if (threadIdx.x < 32) tmem_alloc(tmem_slot, 2 * TCOLS);
+  load_weight_kblocks(sW, w_o, CZ, 64, 64, threadIdx.x, 256);
+  load_weight_kblocks(sWl, w_o + CZ * 64, CZ, 64, 64, threadIdx.x, 256);
+  for (int i = threadIdx.x; i < CZ; i += 256) sB[i] = b_o[i];
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem = *tmem_slot;
-  const uint32_t tm_lane = tmem + (static_cast<uint32_t>(warp * 32) << 16);
+  const uint32_t tmem = *tmem_slot + g.grp * TCOLS;
+  const uint32_t tm_lane = tmem + (static_cast<uint32_t>(g.warp * 32) << 16);
+  const int t = g.t;
 
   const long long num_tiles = (R + kTileRows - 1) / kTileRows;
+  const long long stride = (long long)gridDim.x * 2;
   uint32_t mma_phase = 0;
-  long long tile = blockIdx.x;
-  auto src_of = [&](long long r) -> long long {
-    int b = 0, s = 0, tk = 0;
-    if (r < R) map.decompose(r, b, s, tk);
-    return map.src_row(b, s, tk);
-  };
-  if (tile < num_tiles) {
-    const long long r = tile * kTileRows + t;
-    issue_row_load<CZ>(sSt, t, pair + src_of(r) * CZ, r < R, &full[0]);
-  }
-  for (int it = 0; tile < num_tiles; tile += gridDim.x, ++it) {
-    const int buf = it & 1;
-    uint8_t* st = sSt + buf * RowStage<CZ>::kBytes;
-    const long long next = tile + gridDim.x;
-    if (next < num_tiles) {
-      bulk_wait_read0();
-      const long long rn = next * kTileRows + t;
-      issue_row_load<CZ>(sSt + (buf ^ 1) * RowStage<CZ>::kBytes, t, pair + src_of(rn) * CZ, rn < R, &full[buf ^ 1]);
-    }
+  long long tile = (long long)blockIdx.x * 2 + g.grp;
+  for (int it = 0; tile < num_tiles; tile += stride, ++it) {
     const long long r = tile * kTileRows + t;
     const bool valid = r < R;
-    const long long src = src_of(r);
-    float* my = stage_row<CZ>(st, t);
+    long long src = 0;
+    if (valid) {
+      int b, s, tk;
+      map.decompose(r, b, s, tk);
+      src = map.src_row(b, s, tk);
+    }
+    bulk_wait_read0();  // this thread's previous output row has left the stage
+    issue_row_load<CZ>(sSt, t, pair + src * CZ, valid && residual, full);
     {
       const uint4* op = reinterpret_cast<const uint4*>(og + r * 64);
 #pragma unroll
@@ -739,17 +741,18 @@ triattn_out_kernel(const float* pair, float* dst, int residual, RowMap map, long
         *reinterpret_cast<uint4*>(sA + sw128_offset(t, ch)) = v;
       }
     }
-    sync_before_mma();
+    g.sync_before_mma();
     if (t == 0) {
       tc_fence_after();
       umma_multi(tmem, smem_u32(sA), smem_u32(sW), 1, CZ * 128, umma_idesc_f16(128, CZ), false);
       umma_multi(tmem, smem_u32(sA), smem_u32(sWl), 1, CZ * 128, umma_idesc_f16(128, CZ), true);
       umma_commit(mma_bar);
     }
-    mbar_wait(&full[buf], (it >> 1) & 1);
+    mbar_wait(full, it & 1);
     mbar_wait(mma_bar, mma_phase);
     mma_phase ^= 1;
     tc_fence_after();
+    float* my = stage_row<CZ>(sSt, t);
 #pragma unroll
     for (int c = 0; c < CZ / 32; ++c) {
       uint32_t acc[32];
@@ -757,8 +760,7 @@ triattn_out_kernel(const float* pair, float* dst, int residual, RowMap map, long
       tmem_ld_wait();
 #pragma unroll
       for (int j = 0; j < 32; j += 4) {
-        float4 x = *reinterpret_cast<float4*>(my + c * 32 + j);
-        if (!residual) x = make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 x = (residual && valid) ? *reinterpret_cast<float4*>(my + c * 32 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
         x.x += __uint_as_float(acc[j + 0]) + sB[c * 32 + j + 0];
         x.y += __uint_as_float(acc[j + 1]) + sB[c * 32 + j + 1];
         x.z += __uint_as_float(acc[j + 2]) + sB[c * 32 + j + 2];
@@ -770,37 +772,34 @@ triattn_out_kernel(const float* pair, float* dst, int residual, RowMap map, long
     if (valid) bulk_s2g(dst + src * CZ, my, CZ * 4);
     bulk_commit();
     tc_fence_before();
-    __syncthreads();
   }
   bulk_wait0();
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem, TCOLS);
+  if (threadIdx.x < 32) tmem_dealloc(*tmem_slot, 2 * TCOLS);
+}
+
+template <int CZ>
+static int launch_triattn_out(const PairDims& d, const float* pair, float* dst, int residual, int mode, const __half* og,
+                              const __half* w_o, const float* b_o, cudaStream_t s) {
+  const long long R = (long long)d.B * d.N * d.N;
+  const long long tiles = (R + kTileRows - 1) / kTileRows;
+  RowMap map{d.N, (long long)d.N * d.N, mode};
+  constexpr int kGroupBytes = 16384 + (RowStage<CZ>::kBytes + 1023) / 1024 * 1024;
+  constexpr int smem = 1024 + ((2 * CZ * 128 + 1023) / 1024) * 1024 + 2 * kGroupBytes + CZ * 4 + 64;
+  auto kern = triattn_out_kernel<CZ>;
+  if (set_smem(kern, smem)) return 1;
+  kern<<<grid_for((tiles + 1) / 2, 1), 256, smem, s>>>(pair, dst, residual, map, R, og, w_o, b_o);
+  PRD_LAUNCHED();
+  return 0;
 }
 
 int triattn_out(const PairDims& d, const float* pair, float* dst, int residual, int mode, const __half* og,
                 const __half* w_o, const float* b_o, cudaStream_t s) {
-  const long long R = (long long)d.B * d.N * d.N;
-  const long long tiles = (R + kTileRows - 1) / kTileRows;
-  RowMap map{d.N, (long long)d.N * d.N, mode};
-  if (d.CZ == 64) {
-    constexpr int CZ = 64;
-    constexpr int smem = 1024 + 16384 + 2 * CZ * 128 + 2 * RowStage<CZ>::kBytes + CZ * 4 + 64;
-    auto kern = triattn_out_kernel<CZ>;
-    if (set_smem(kern, smem)) return 1;
-    kern<<<grid_for(tiles, 2), 128, smem, s>>>(pair, dst, residual, map, R, og, w_o, b_o);
-  } else if (d.CZ == 32) {
-    constexpr int CZ = 32;
-    constexpr int smem = 1024 + 16384 + 2 * CZ * 128 + 2 * RowStage<CZ>::kBytes + CZ * 4 + 64;
-    auto kern = triattn_out_kernel<CZ>;
-    if (set_smem(kern, smem)) return 1;
-    kern<<<grid_for(tiles, 2), 128, smem, s>>>(pair, dst, residual, map, R, og, w_o, b_o);
-  } else {
-    set_error("triattn_out: unsupported pair_dim %d", d.CZ);
-    return 1;
-  }
-  PRD_LAUNCHED();
-  return 0;
+  if (d.CZ == 64) return launch_triattn_out<64>(d, pair, dst, residual, mode, og, w_o, b_o, s);
+  if (d.CZ == 32) return launch_triattn_out<32>(d, pair, dst, residual, mode, og, w_o, b_o, s);
+  set_error("triattn_out: unsupported pair_dim %d", d.CZ);
+  return 1;
 }
 
 }  // namespace prd

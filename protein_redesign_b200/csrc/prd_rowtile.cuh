@@ -147,6 +147,28 @@ __device__ __forceinline__ uint8_t* smem_align1024(uint8_t* raw) {
   return raw + (((a + 1023u) & ~1023u) - a);
 }
 
+// Two independent 128-thread compute groups per CTA (warps 0-3 / 4-7): each group owns a tile, its
+// own A operand, row stage, mbarriers and TMEM columns, and shares only the weight tiles.  With one
+// warp per scheduler a row kernel is latency bound (every dependent instruction stalls); a second
+// group lets the schedulers overlap one tile's LayerNorm / epilogue with the other's UMMA wait.
+struct Group {
+  int grp;   // 0 or 1
+  int t;     // thread index inside the group, 0..127 (= tile row = TMEM lane)
+  int warp;  // warp index inside the group, 0..3 (= TMEM lane quarter)
+  __device__ __forceinline__ Group() {
+    grp = threadIdx.x >> 7;
+    t = threadIdx.x & 127;
+    warp = t >> 5;
+  }
+  __device__ __forceinline__ void bar() const { asm volatile("bar.sync %0, 128;" ::"r"(grp + 1) : "memory"); }
+  // make generic-proxy smem writes visible to the tensor core, then sync the group
+  __device__ __forceinline__ void sync_before_mma() const {
+    fence_proxy_async_smem();
+    tc_fence_before();
+    bar();
+  }
+};
+
 // All threads: make generic-proxy smem writes visible to the tensor core, then sync the CTA.
 __device__ __forceinline__ void sync_before_mma() {
   fence_proxy_async_smem();
