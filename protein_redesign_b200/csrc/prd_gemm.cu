@@ -19,6 +19,7 @@ struct GemmSmem {
   static constexpr int kBBytes = BN * 64 * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kTotal = STAGES * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;  // two accumulators
 };
 
 struct GemmEpilogue {
@@ -37,10 +38,28 @@ struct GemmEpilogue {
   int c_fp16;
 };
 
+struct GemmTiling {
+  int tiles_n, tiles_m, nb1;
+  long long total;
+  __device__ __forceinline__ void decode(long long tile, int& n0, int& m0, int& i1, int& i2, int bn) const {
+    const int tn = static_cast<int>(tile % tiles_n);
+    long long r = tile / tiles_n;
+    const int tm = static_cast<int>(r % tiles_m);
+    r /= tiles_m;
+    i1 = static_cast<int>(r % nb1);
+    i2 = static_cast<int>(r / nb1);
+    n0 = tn * bn;
+    m0 = tm * 128;
+  }
+};
+
+// Persistent: every CTA walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...  The accumulator is
+// double buffered in TMEM, so the epilogue of tile i (TMEM -> registers -> global) overlaps the
+// TMA / UMMA main loop of tile i+1.
 template <int BN, int STAGES>
 __global__ void __launch_bounds__(192, 1)
 gemm_f16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, int num_kb,
-                int a_wrap, int b_wrap, int nb1, int a_b1, int a_b2, int b_b1, int b_b2, GemmEpilogue ep) {
+                int a_wrap, int b_wrap, GemmTiling tl, int a_b1, int a_b2, int b_b1, int b_b2, GemmEpilogue ep) {
   // a_wrap / b_wrap: K-blocks after which that operand's K coordinate wraps to 0.  With a weight
   // stored as [hi | lo] along K (fp16 pair, removes the systematic weight rounding) the activation
   // operand is simply read twice: sum_k x_k (w_hi + w_lo)_k.
@@ -51,24 +70,25 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * L::kStageBytes);
   uint64_t* full = bars;
   uint64_t* empty = bars + STAGES;
-  uint64_t* tmem_full = bars + 2 * STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
+  uint64_t* tmem_full = bars + 2 * STAGES;       // [2]
+  uint64_t* tmem_empty = bars + 2 * STAGES + 2;  // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n0 = blockIdx.x * BN, m0 = blockIdx.y * 128;
-  const int i1 = blockIdx.z % nb1, i2 = blockIdx.z / nb1;
-
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
     }
-    mbar_init(tmem_full, 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&tmem_full[b], 1);
+      mbar_init(&tmem_empty[b], 128);
+    }
     fence_barrier_init();
     tma_prefetch_desc(&map_a);
     tma_prefetch_desc(&map_b);
   }
-  if (warp == 0) tmem_alloc(tmem_slot, BN < 32 ? 32 : BN);
+  if (warp == 0) tmem_alloc(tmem_slot, L::kTmemCols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -76,95 +96,123 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
 
   if (warp == 0) {
     if (lane == 0) {
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (kb / STAGES) & 1;
-        mbar_wait(&empty[s], ph ^ 1);
-        mbar_expect_tx(&full[s], L::kStageBytes);
-        uint8_t* sa = smem + s * L::kStageBytes;
-        tma_load_4d(sa, &map_a, &full[s], (kb % a_wrap) * 64, m0, i1 * a_b1, i2 * a_b2);
-        tma_load_4d(sa + L::kABytes, &map_b, &full[s], (kb % b_wrap) * 64, n0, i1 * b_b1, i2 * b_b2);
+      long long it = 0;  // running k-block counter across tiles
+      for (long long tile = blockIdx.x; tile < tl.total; tile += gridDim.x) {
+        int n0, m0, i1, i2;
+        tl.decode(tile, n0, m0, i1, i2, BN);
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = static_cast<int>(it % STAGES);
+          const uint32_t ph = static_cast<uint32_t>((it / STAGES) & 1);
+          mbar_wait(&empty[s], ph ^ 1);
+          mbar_expect_tx(&full[s], L::kStageBytes);
+          uint8_t* sa = smem + s * L::kStageBytes;
+          tma_load_4d(sa, &map_a, &full[s], (kb % a_wrap) * 64, m0, i1 * a_b1, i2 * a_b2);
+          tma_load_4d(sa + L::kABytes, &map_b, &full[s], (kb % b_wrap) * 64, n0, i1 * b_b1, i2 * b_b2);
+        }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_f16(128, BN);
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (kb / STAGES) & 1;
-        mbar_wait(&full[s], ph);
+      long long it = 0;
+      int lt = 0;  // local tile counter
+      for (long long tile = blockIdx.x; tile < tl.total; tile += gridDim.x, ++lt) {
+        const int buf = lt & 1;
+        mbar_wait(&tmem_empty[buf], ((lt >> 1) & 1) ^ 1);  // epilogue has drained this accumulator
         tc_fence_after();
-        const uint32_t sa = base + s * L::kStageBytes;
-        umma_kblock(tmem, sa, sa + L::kABytes, idesc, kb > 0);
-        umma_commit(&empty[s]);
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = static_cast<int>(it % STAGES);
+          const uint32_t ph = static_cast<uint32_t>((it / STAGES) & 1);
+          mbar_wait(&full[s], ph);
+          tc_fence_after();
+          const uint32_t sa = base + s * L::kStageBytes;
+          umma_kblock(tmem + buf * BN, sa, sa + L::kABytes, idesc, kb > 0);
+          umma_commit(&empty[s]);
+        }
+        umma_commit(&tmem_full[buf]);
       }
-      umma_commit(tmem_full);
     }
   } else {
     // epilogue: warp w may only touch TMEM lanes [32*(w%4), 32*(w%4)+32)
     const int q = warp & 3;
-    const int row = m0 + q * 32 + lane;
-    mbar_wait(tmem_full, 0);
-    tc_fence_after();
-    const long long boff_c = (long long)i1 * ep.c_bs1 + (long long)i2 * ep.c_bs2;
-    const float rs = (ep.rowscale != nullptr && row < ep.M)
-                         ? ep.rowscale[(long long)i1 * ep.rs_bs1 + (long long)i2 * ep.rs_bs2 + row]
-                         : 1.0f;
-    const float* mulp = ep.mul ? ep.mul + (long long)i1 * ep.mul_bs1 + (long long)i2 * ep.mul_bs2 + (long long)row * ep.ldmul : nullptr;
-    const float* addp = ep.add ? ep.add + (long long)i1 * ep.add_bs1 + (long long)i2 * ep.add_bs2 + (long long)row * ep.ldadd : nullptr;
+    int lt = 0;
+    for (long long tile = blockIdx.x; tile < tl.total; tile += gridDim.x, ++lt) {
+      int n0, m0, i1, i2;
+      tl.decode(tile, n0, m0, i1, i2, BN);
+      const int buf = lt & 1;
+      const int row = m0 + q * 32 + lane;
+      mbar_wait(&tmem_full[buf], (lt >> 1) & 1);
+      tc_fence_after();
+      const long long boff_c = (long long)i1 * ep.c_bs1 + (long long)i2 * ep.c_bs2;
+      const float rs = (ep.rowscale != nullptr && row < ep.M)
+                           ? ep.rowscale[(long long)i1 * ep.rs_bs1 + (long long)i2 * ep.rs_bs2 + row]
+                           : 1.0f;
+      const float* mulp = ep.mul ? ep.mul + (long long)i1 * ep.mul_bs1 + (long long)i2 * ep.mul_bs2 + (long long)row * ep.ldmul : nullptr;
+      const float* addp = ep.add ? ep.add + (long long)i1 * ep.add_bs1 + (long long)i2 * ep.add_bs2 + (long long)row * ep.ldadd : nullptr;
+      const bool plain = ep.bias == nullptr && ep.act == 0 && ep.rowscale == nullptr && mulp == nullptr &&
+                         addp == nullptr && ep.alpha == 1.0f;
 #pragma unroll 1
-    for (int c = 0; c < BN / 32; ++c) {
-      uint32_t r[32];
-      tmem_ld32(tmem + (static_cast<uint32_t>(q * 32) << 16) + c * 32, r);
-      tmem_ld_wait();
-      const int col0 = n0 + c * 32;
-      if (row < ep.M && col0 < ep.N) {
-        float v[32];
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld32(tmem + buf * BN + (static_cast<uint32_t>(q * 32) << 16) + c * 32, r);
+        tmem_ld_wait();
+        const int col0 = n0 + c * 32;
+        if (row < ep.M && col0 < ep.N) {
+          float v[32];
+          if (plain) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int col = col0 + j;
-          float x = ep.alpha * __uint_as_float(r[j]);
-          if (col < ep.N) {
-            if (ep.bias) x += __ldg(ep.bias + col);
-            if (ep.act == 1) x = fmaxf(x, 0.0f);
-            else if (ep.act == 2) x = 1.0f / (1.0f + __expf(-x));
-            x *= rs;
-            if (mulp) x *= mulp[col];
-            if (addp) x += addp[col];
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const int col = col0 + j;
+              float x = ep.alpha * __uint_as_float(r[j]);
+              if (col < ep.N) {
+                if (ep.bias) x += __ldg(ep.bias + col);
+                if (ep.act == 1) x = fmaxf(x, 0.0f);
+                else if (ep.act == 2) x = 1.0f / (1.0f + __expf(-x));
+                x *= rs;
+                if (mulp) x *= mulp[col];
+                if (addp) x += addp[col];
+              }
+              v[j] = x;
+            }
           }
-          v[j] = x;
-        }
-        const bool full_chunk = (col0 + 32 <= ep.N);
-        if (ep.c_fp16) {
-          __half* cp = reinterpret_cast<__half*>(ep.C) + boff_c + (long long)row * ep.ldc + col0;
-          if (full_chunk && ((reinterpret_cast<uintptr_t>(cp) & 15) == 0)) {
+          const bool full_chunk = (col0 + 32 <= ep.N);
+          if (ep.c_fp16) {
+            __half* cp = reinterpret_cast<__half*>(ep.C) + boff_c + (long long)row * ep.ldc + col0;
+            if (full_chunk && ((reinterpret_cast<uintptr_t>(cp) & 15) == 0)) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              uint4 o;
-              o.x = pack_half2(v[j], v[j + 1]);
-              o.y = pack_half2(v[j + 2], v[j + 3]);
-              o.z = pack_half2(v[j + 4], v[j + 5]);
-              o.w = pack_half2(v[j + 6], v[j + 7]);
-              *reinterpret_cast<uint4*>(cp + j) = o;
+              for (int j = 0; j < 32; j += 8) {
+                uint4 o;
+                o.x = pack_half2(v[j], v[j + 1]);
+                o.y = pack_half2(v[j + 2], v[j + 3]);
+                o.z = pack_half2(v[j + 4], v[j + 5]);
+                o.w = pack_half2(v[j + 6], v[j + 7]);
+                *reinterpret_cast<uint4*>(cp + j) = o;
+              }
+            } else {
+              for (int j = 0; j < 32 && col0 + j < ep.N; ++j) cp[j] = __float2half_rn(v[j]);
             }
           } else {
-            for (int j = 0; j < 32 && col0 + j < ep.N; ++j) cp[j] = __float2half_rn(v[j]);
-          }
-        } else {
-          float* cp = reinterpret_cast<float*>(ep.C) + boff_c + (long long)row * ep.ldc + col0;
-          if (full_chunk && ((reinterpret_cast<uintptr_t>(cp) & 15) == 0)) {
+            float* cp = reinterpret_cast<float*>(ep.C) + boff_c + (long long)row * ep.ldc + col0;
+            if (full_chunk && ((reinterpret_cast<uintptr_t>(cp) & 15) == 0)) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(cp + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-          } else {
-            for (int j = 0; j < 32 && col0 + j < ep.N; ++j) cp[j] = v[j];
+              for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(cp + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            } else {
+              for (int j = 0; j < 32 && col0 + j < ep.N; ++j) cp[j] = v[j];
+            }
           }
         }
       }
+      // this thread's TMEM reads of the accumulator are complete: hand it back to the MMA warp
+      tc_fence_before();
+      mbar_arrive(&tmem_empty[buf]);
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem, BN < 32 ? 32 : BN);
+  if (warp == 0) tmem_dealloc(tmem, L::kTmemCols);
 }
 
 template <int BN, int STAGES>
@@ -210,19 +258,26 @@ static int launch_gemm(const GemmArgs& g, cudaStream_t stream) {
     PRD_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
     attr_set = true;
   }
-  dim3 grid((g.N + BN - 1) / BN, (g.M + 127) / 128, nb1 * nb2);
+  GemmTiling tl;
+  tl.tiles_n = (g.N + BN - 1) / BN;
+  tl.tiles_m = (g.M + 127) / 128;
+  tl.nb1 = nb1;
+  tl.total = (long long)tl.tiles_n * tl.tiles_m * nb1 * nb2;
+  const int grid = (int)(tl.total < kNumSMs ? tl.total : kNumSMs);
   const int num_kb = g.split != 0 ? 2 * kb_half : kb_half;
   const int a_wrap = g.split == 1 ? kb_half : num_kb;
   const int b_wrap = g.split == 2 ? kb_half : num_kb;
-  kern<<<grid, 192, L::kTotal, stream>>>(map_a, map_b, num_kb, a_wrap, b_wrap, nb1, g.a_bs1 != 0 ? 1 : 0, g.a_bs2 != 0 ? 1 : 0,
-                                         g.b_bs1 != 0 ? 1 : 0, g.b_bs2 != 0 ? 1 : 0, ep);
+  kern<<<grid, 192, L::kTotal, stream>>>(map_a, map_b, num_kb, a_wrap, b_wrap, tl, g.a_bs1 != 0 ? 1 : 0,
+                                         g.a_bs2 != 0 ? 1 : 0, g.b_bs1 != 0 ? 1 : 0, g.b_bs2 != 0 ? 1 : 0, ep);
   PRD_LAUNCHED();
   return 0;
 }
 
 int gemm_f16(const GemmArgs& g, cudaStream_t stream) {
-  if (g.N <= 64) return launch_gemm<64, 4>(g, stream);
-  return launch_gemm<128, 3>(g, stream);
+  if (g.N <= 64) return launch_gemm<64, 6>(g, stream);
+  if (g.N % 256 == 0 && (long long)((g.M + 127) / 128) * (g.N / 256) * (g.nb1 > 0 ? g.nb1 : 1) * (g.nb2 > 0 ? g.nb2 : 1) >= kNumSMs)
+    return launch_gemm<256, 4>(g, stream);
+  return launch_gemm<128, 5>(g, stream);
 }
 
 }  // namespace prd

@@ -112,6 +112,19 @@ outer_linear_kernel(const __grid_constant__ CUtensorMap map_x, const float* pair
     }
   };
 
+  // x_i / u_i are fetched one row ahead into registers so their global latency is off the critical path
+  constexpr int XPT = CS / 256;  // floats of x_i per thread
+  float xnext[XPT];
+  float unext = 0.f;
+  auto fetch_row = [&](int i) {
+    if (i < i1) {
+      const float* xi = xn32 + ((long long)b * N + i) * CS;
+#pragma unroll
+      for (int q = 0; q < XPT; ++q) xnext[q] = __ldg(xi + t + 256 * q);
+      if (t < CZ) unext = __ldg(u + ((long long)b * N + i) * CZ + t);
+    }
+  };
+  fetch_row(i0);
   for (int i = i0; i <= i1; ++i) {
     // (1) prefetch the residual of row i-1 (consumed after the UMMAs of row i are issued)
     float4 res[HC / 4];
@@ -122,11 +135,13 @@ outer_linear_kernel(const __grid_constant__ CUtensorMap map_x, const float* pair
 #pragma unroll
       for (int c = 0; c < HC / 4; ++c) res[c] = pr[c];
     }
+    float ucur = unext;
     if (i < i1) {
-      // (2) x_i, u_i -> shared
-      const float* xi = xn32 + ((long long)b * N + i) * CS;
-      for (int d = t; d < CS; d += 256) sXi[d] = xi[d];
+      // (2) x_i -> shared (from the registers filled one iteration ago), then fetch row i+1
+#pragma unroll
+      for (int q = 0; q < XPT; ++q) sXi[t + 256 * q] = xnext[q];
     }
+    fetch_row(i + 1);
     // (3) the UMMAs of row i-1 read sB: they must be complete before sB is rebuilt
     if (i > i0) {
       mbar_wait(mma_bar, mma_phase);
@@ -137,7 +152,7 @@ outer_linear_kernel(const __grid_constant__ CUtensorMap map_x, const float* pair
     if (i < i1) {
       // u_i is read by the epilogue of row i (next iteration); its slot was last read by the epilogue of
       // row i-2, which every thread finished before the barrier above
-      if (t < CZ) sUi[(i & 1) * CZ + t] = u[((long long)b * N + i) * CZ + t];
+      if (t < CZ) sUi[(i & 1) * CZ + t] = ucur;
       // (4) B'[z][d] = W1[z][d] * x_i[d]   (fp32 product, rounded once to fp16)
 #pragma unroll
       for (int n = 0; n < NCH; ++n) {

@@ -316,6 +316,8 @@ trimul_in_kernel(const float* __restrict__ pair, const float* __restrict__ mask,
     mbar_wait(mma_bar, mma_phase);
     mma_phase ^= 1;
     tc_fence_after();
+    // channel cc in [0, 2CZ): a = [0,CZ) -> planes of tensor 0, b = [CZ,2CZ) -> planes of tensor 1.
+    // One running pointer per 32-channel chunk, advanced by the plane stride: no 64-bit multiplies.
 #pragma unroll 1
     for (int c = 0; c < 2 * CZ / 32; ++c) {
       uint32_t pr[32], ga[32];
@@ -323,13 +325,16 @@ trimul_in_kernel(const float* __restrict__ pair, const float* __restrict__ mask,
       tmem_ld32(tm_lane + 2 * CZ + c * 32, ga);
       tmem_ld_wait();
       if (valid) {
+        const int cc0 = c * 32;
+        const long long pl0 = (cc0 < CZ) ? cc0 : (cc0 - CZ) + (long long)B * CZ;
+        __half* dp = dst0 + pl0 * plane;
+        const float* bp = sB + cc0;
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-          const int cc = c * 32 + j;  // channel in [0, 2CZ): a = [0,CZ), b = [CZ,2CZ)
-          const float gt = sigmoidf_fast(__uint_as_float(ga[j]) + sB[2 * CZ + cc]);
-          const float v = m2 * gt * (__uint_as_float(pr[j]) + sB[cc]);
-          const long long pl = (cc < CZ) ? cc : (cc - CZ) + (long long)B * CZ;
-          dst0[pl * plane] = __float2half_rn(v);
+          const float gt = sigmoidf_fast(__uint_as_float(ga[j]) + bp[2 * CZ + j]);
+          const float v = m2 * gt * (__uint_as_float(pr[j]) + bp[j]);
+          *dp = __float2half_rn(v);
+          dp += plane;
         }
       }
     }

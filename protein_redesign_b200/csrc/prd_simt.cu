@@ -56,17 +56,27 @@ __device__ __forceinline__ float4 ldg_stream(const float4* p) {
   return r;
 }
 
+// Streaming design: the pair tensor is pulled through a 3-stage shared-memory ring with 32 KB bulk
+// copies (cp.async.bulk + mbarrier), so ~96 KB per CTA are in flight independent of what the warps
+// are doing; the 8 warps then normalise / project 16 elements each per stage straight from shared
+// memory (16-byte conflict-free reads) and write 64-byte runs of the four head planes.
 template <int CZ>
 __global__ void __launch_bounds__(256)
 pair_bias_kernel(const float* __restrict__ pair, long long R, long long NN, const float* __restrict__ ln_w,
                  const float* __restrict__ ln_b, const float* __restrict__ w, const float* __restrict__ bvec,
                  float* __restrict__ out) {
-  constexpr int LPE = CZ / 4;     // lanes per element
-  constexpr int EPW = 32 / LPE;   // elements per warp-wide load
-  constexpr int ITER = 32 / EPW;  // loads per 32-element pass
-  const int lane = threadIdx.x & 31;
+  constexpr int LPE = CZ / 4;          // lanes per element
+  constexpr int EPW = 32 / LPE;        // elements per warp-wide read
+  constexpr int ELEMS = 128;           // elements per stage
+  constexpr int ITER = 16 / EPW;       // reads per warp per stage (16 elements per warp)
+  constexpr int STAGES = 3;
+  constexpr int kStageBytes = ELEMS * CZ * 4;
+  extern __shared__ __align__(128) uint8_t smem_pb[];
+  float* stage = reinterpret_cast<float*>(smem_pb);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem_pb + STAGES * kStageBytes);
+
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int sub = lane % LPE, grp = lane / LPE;
-  // per-lane slice of the affine LN and of the 4 head weight rows (channels 4*sub .. 4*sub+3)
   float4 gam = make_float4(1.f, 1.f, 1.f, 1.f), bet = make_float4(0.f, 0.f, 0.f, 0.f);
   if (ln_w) {
     gam = reinterpret_cast<const float4*>(ln_w)[sub];
@@ -79,25 +89,39 @@ pair_bias_kernel(const float* __restrict__ pair, long long R, long long NN, cons
 #pragma unroll
   for (int h = 0; h < 4; ++h) bh[h] = bvec ? bvec[h] : 0.f;
 
-  const long long warp_global = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
-  const long long npass = (R + 31) / 32;
-  for (long long pass = warp_global; pass < npass; pass += nwarps) {
-    const long long e0 = pass * 32;
-    float4 v[ITER];
-#pragma unroll
-    for (int it = 0; it < ITER; ++it) {
-      const long long e = e0 + it * EPW + grp;
-      v[it] = (e < R) ? ldg_stream(reinterpret_cast<const float4*>(pair + e * CZ) + sub) : make_float4(0.f, 0.f, 0.f, 0.f);
+  const long long nchunks = (R + ELEMS - 1) / ELEMS;
+  auto load = [&](long long chunk, int s) {
+    const long long e0 = chunk * ELEMS;
+    const long long n = (R - e0 < ELEMS) ? (R - e0) : ELEMS;
+    const uint32_t bytes = static_cast<uint32_t>(n * CZ * 4);
+    mbar_expect_tx(&full[s], bytes);
+    bulk_g2s(stage + s * (kStageBytes / 4), pair + e0 * CZ, bytes, &full[s]);
+  };
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) mbar_init(&full[s], 1);
+    fence_barrier_init();
+    for (int s = 0; s < STAGES; ++s) {
+      const long long c = (long long)blockIdx.x + (long long)s * gridDim.x;
+      if (c < nchunks) load(c, s);
     }
+  }
+  __syncthreads();
+  int it_chunk = 0;
+  for (long long chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x, ++it_chunk) {
+    const int s = it_chunk % STAGES;
+    mbar_wait(&full[s], (it_chunk / STAGES) & 1);
+    const float4* st = reinterpret_cast<const float4*>(stage + s * (kStageBytes / 4));
+    const long long e0 = chunk * ELEMS + warp * 16;
     float keep[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (int it = 0; it < ITER; ++it) {
-      float s = v[it].x + v[it].y + v[it].z + v[it].w;
+      const int el = warp * 16 + it * EPW + grp;  // element inside the stage
+      const float4 v = st[el * LPE + sub];
+      float sm = v.x + v.y + v.z + v.w;
 #pragma unroll
-      for (int o = LPE / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-      const float mean = s * (1.0f / CZ);
-      const float d0 = v[it].x - mean, d1 = v[it].y - mean, d2 = v[it].z - mean, d3 = v[it].w - mean;
+      for (int o = LPE / 2; o > 0; o >>= 1) sm += __shfl_xor_sync(0xffffffffu, sm, o);
+      const float mean = sm * (1.0f / CZ);
+      const float d0 = v.x - mean, d1 = v.y - mean, d2 = v.z - mean, d3 = v.w - mean;
       float q = d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
 #pragma unroll
       for (int o = LPE / 2; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
@@ -109,20 +133,25 @@ pair_bias_kernel(const float* __restrict__ pair, long long R, long long NN, cons
         float p = y0 * wh[h].x + y1 * wh[h].y + y2 * wh[h].z + y3 * wh[h].w;
 #pragma unroll
         for (int o = LPE / 2; o > 0; o >>= 1) p += __shfl_xor_sync(0xffffffffu, p, o);
-        // element (it*EPW + g) of this pass is delivered to lane (it*EPW + g)
+        // element (it*EPW + g) of this warp's 16 is delivered to lane (it*EPW + g)
 #pragma unroll
-        for (int g = 0; g < EPW; ++g) {
-          const float pv = __shfl_sync(0xffffffffu, p, g * LPE);
-          if (lane == it * EPW + g) keep[h] = pv + bh[h];
+        for (int g2 = 0; g2 < EPW; ++g2) {
+          const float pv = __shfl_sync(0xffffffffu, p, g2 * LPE);
+          if (lane == it * EPW + g2) keep[h] = pv + bh[h];
         }
       }
     }
     const long long e = e0 + lane;
-    if (e < R) {
+    if (lane < 16 && e < R) {
       const long long b = e / NN;
       const long long ij = e - b * NN;
 #pragma unroll
       for (int h = 0; h < 4; ++h) out[(b * 4 + h) * NN + ij] = keep[h];
+    }
+    __syncthreads();  // every warp is done with stage s
+    if (threadIdx.x == 0) {
+      const long long c = chunk + (long long)STAGES * gridDim.x;
+      if (c < nchunks) load(c, s);
     }
   }
 }
@@ -131,10 +160,17 @@ int pair_bias_proj(const PairDims& d, int H, const float* pair, const float* ln_
                    const float* bvec, float* bias_out, cudaStream_t s) {
   PRD_REQUIRE(H == 4, "pair_bias_proj: num_heads %d unsupported (built for 4)", H);
   const long long NN = (long long)d.N * d.N, R = NN * d.B;
-  const int blocks = kNumSMs * 8;
-  if (d.CZ == 64) pair_bias_kernel<64><<<blocks, 256, 0, s>>>(pair, R, NN, ln_w, ln_b, w, bvec, bias_out);
-  else if (d.CZ == 32) pair_bias_kernel<32><<<blocks, 256, 0, s>>>(pair, R, NN, ln_w, ln_b, w, bvec, bias_out);
-  else {
+  const long long nchunks = (R + 127) / 128;
+  const int blocks = (int)(nchunks < 2 * kNumSMs ? nchunks : 2 * kNumSMs);
+  if (d.CZ == 64) {
+    constexpr int smem = 3 * 128 * 64 * 4 + 64;
+    PRD_CUDA_OK(cudaFuncSetAttribute(pair_bias_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    pair_bias_kernel<64><<<blocks, 256, smem, s>>>(pair, R, NN, ln_w, ln_b, w, bvec, bias_out);
+  } else if (d.CZ == 32) {
+    constexpr int smem = 3 * 128 * 32 * 4 + 64;
+    PRD_CUDA_OK(cudaFuncSetAttribute(pair_bias_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    pair_bias_kernel<32><<<blocks, 256, smem, s>>>(pair, R, NN, ln_w, ln_b, w, bvec, bias_out);
+  } else {
     set_error("pair_bias_proj: unsupported pair_dim %d", d.CZ);
     return 1;
   }
