@@ -439,7 +439,10 @@ trimul_out_kernel(const float* pair, float* dst, int residual, const float* __re
         const int i = rem / N, j = rem - i * N;
         const float* xp = xpl + (long long)b * CZ * xplane + (long long)i * Nx + j;
 #pragma unroll
-        for (int dch = 0; dch < CZ; ++dch) x[dch] = __ldg(xp + dch * xplane);
+        for (int dch = 0; dch < CZ; ++dch) {
+          x[dch] = __ldg(xp);
+          xp += xplane;
+        }
       } else {
 #pragma unroll
         for (int q = 0; q < CZ; ++q) x[q] = 0.f;
@@ -628,7 +631,10 @@ triattn_proj_kernel(const float* __restrict__ pair, RowMap map, long long R, con
       if (part == 2) {
         __half* vp = vt + (((long long)b * map.N + s) * 64 + col0) * Np + tk;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) vp[(long long)j * Np] = __float2half_rn(__uint_as_float(acc[j]));
+        for (int j = 0; j < 32; ++j) {
+          *vp = __float2half_rn(__uint_as_float(acc[j]));
+          vp += Np;
+        }
       } else {
         float v[32];
 #pragma unroll

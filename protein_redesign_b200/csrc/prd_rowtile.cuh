@@ -109,6 +109,21 @@ __device__ __forceinline__ void store_a_cols32(uint8_t* a_tiles, int t, int k0, 
   }
 }
 
+// Same for 16 consecutive K-values (k0 a multiple of 16).
+__device__ __forceinline__ void store_a_cols16(uint8_t* a_tiles, int t, int k0, const float (&v)[16]) {
+  uint8_t* blk = a_tiles + (k0 >> 6) * (kTileRows * 128);
+  const int ch0 = (k0 & 63) >> 3;
+#pragma unroll
+  for (int c = 0; c < 2; ++c) {
+    uint4 o;
+    o.x = pack_half2(v[c * 8 + 0], v[c * 8 + 1]);
+    o.y = pack_half2(v[c * 8 + 2], v[c * 8 + 3]);
+    o.z = pack_half2(v[c * 8 + 4], v[c * 8 + 5]);
+    o.w = pack_half2(v[c * 8 + 6], v[c * 8 + 7]);
+    *reinterpret_cast<uint4*>(blk + sw128_offset(t, ch0 + c)) = o;
+  }
+}
+
 // Cooperative copy of a row-major fp16 weight W[rows][K] (leading dim ld halves) into K-major
 // SWIZZLE_128B B-operand K-blocks: block kb holds columns [64 kb, 64 kb + 64) of all rows,
 // zero padded past K.  Block size = rows * 128 bytes (rows must be a multiple of 8).
