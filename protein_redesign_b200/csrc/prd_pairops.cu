@@ -28,16 +28,19 @@ outer_linear_kernel(const __grid_constant__ CUtensorMap map_x, const float* pair
   extern __shared__ uint8_t raw[];
   constexpr int CS = KBS * 64;
   constexpr int NCH = KBS * CZ * 8 / 256;  // 16-byte W1 chunks per thread
+  constexpr int CPK = NCH / KBS;           // ... per K-block
   constexpr int HC = CZ / 2;               // accumulator columns per thread (two warp groups split them)
+  constexpr int RB = 4;                    // ring of B-operand K-blocks
   uint8_t* sm = smem_align1024(raw);
   uint8_t* sA = sm;                        // KBS x 16 KB
-  uint8_t* sB = sA + KBS * 16384;          // KBS x [CZ x 64]
-  float* sXi = reinterpret_cast<float*>(sB + KBS * CZ * 128);
+  uint8_t* sB = sA + KBS * 16384;          // RB x [CZ x 64]
+  float* sXi = reinterpret_cast<float*>(sB + RB * CZ * 128);
   float* sUi = sXi + CS;                   // [2][CZ]
   float* sBias = sUi + 2 * CZ;
   uint64_t* bar_a = reinterpret_cast<uint64_t*>(sBias + CZ);
-  uint64_t* mma_bar = bar_a + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mma_bar + 1);
+  uint64_t* ring_free = bar_a + 1;         // [RB]
+  uint64_t* acc_full = ring_free + RB;     // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 2);
   constexpr int TCOLS = 2 * CZ < 32 ? 32 : 2 * CZ;
 
   const int t = threadIdx.x, warp = t >> 5;
@@ -48,7 +51,9 @@ outer_linear_kernel(const __grid_constant__ CUtensorMap map_x, const float* pair
   const int i1 = min(N, i0 + ilen);
   if (t == 0) {
     mbar_init(bar_a, 1);
-    mbar_init(mma_bar, 1);
+    for (int q = 0; q < RB; ++q) mbar_init(&ring_free[q], 1);
+    mbar_init(&acc_full[0], 1);
+    mbar_init(&acc_full[1], 1);
     fence_barrier_init();
     tma_prefetch_desc(&map_x);
   }
@@ -63,12 +68,13 @@ outer_linear_kernel(const __grid_constant__ CUtensorMap map_x, const float* pair
     mbar_expect_tx(bar_a, KBS * 16384);
     for (int kb = 0; kb < KBS; ++kb) tma_load_3d(sA + kb * 16384, &map_x, bar_a, kb * 64, jt * 128, b);
   }
-  // this thread's W1 chunks (fixed for the whole kernel)
+  // this thread's W1 chunks (fixed for the whole kernel): chunk n covers K-block n / CPK,
+  // row z = (t >> 3) + 32 * (n % CPK), 16-byte column chunk ch = t & 7
+  const int ch = t & 7;
   uint4 wreg[NCH];
 #pragma unroll
   for (int n = 0; n < NCH; ++n) {
-    const int idx = t + 256 * n;
-    const int ch = idx & 7, z = (idx >> 3) % CZ, kb = (idx >> 3) / CZ;
+    const int kb = n / CPK, z = (t >> 3) + 32 * (n % CPK);
     wreg[n] = __ldg(reinterpret_cast<const uint4*>(w1 + (long long)z * CS + kb * 64 + ch * 8));
   }
   const int j = jt * 128 + lane_row;
@@ -87,7 +93,6 @@ outer_linear_kernel(const __grid_constant__ CUtensorMap map_x, const float* pair
   }
   mbar_wait(bar_a, 0);
 
-  uint32_t mma_phase = 0;
   // epilogue of row `ie` from accumulator `ie & 1`; `res` holds the prefetched residual values
   auto epilogue = [&](int ie, const float4 (&res)[HC / 4]) {
     float* drow = dst + (((long long)b * N + ie) * N + j) * CZ + grp * HC;
@@ -125,8 +130,9 @@ outer_linear_kernel(const __grid_constant__ CUtensorMap map_x, const float* pair
     }
   };
   fetch_row(i0);
+  uint32_t ring_it = 0;  // K-blocks generated so far (ring position)
   for (int i = i0; i <= i1; ++i) {
-    // (1) prefetch the residual of row i-1 (consumed after the UMMAs of row i are issued)
+    // (1) prefetch the residual of row i-1 (consumed by its epilogue at the end of this iteration)
     float4 res[HC / 4];
 #pragma unroll
     for (int c = 0; c < HC / 4; ++c) res[c] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -135,52 +141,57 @@ outer_linear_kernel(const __grid_constant__ CUtensorMap map_x, const float* pair
 #pragma unroll
       for (int c = 0; c < HC / 4; ++c) res[c] = pr[c];
     }
-    float ucur = unext;
+    const float ucur = unext;
     if (i < i1) {
-      // (2) x_i -> shared (from the registers filled one iteration ago), then fetch row i+1
+      // (2) x_i -> shared (registers filled one iteration ago); every thread finished reading the previous
+      // x in the K-block barriers of the previous row
 #pragma unroll
       for (int q = 0; q < XPT; ++q) sXi[t + 256 * q] = xnext[q];
+      // u_i is read by the epilogue of row i (next iteration); its slot was last read by the epilogue of
+      // row i-2, i.e. before the barriers of row i-1
+      if (t < CZ) sUi[(i & 1) * CZ + t] = ucur;
     }
     fetch_row(i + 1);
-    // (3) the UMMAs of row i-1 read sB: they must be complete before sB is rebuilt
-    if (i > i0) {
-      mbar_wait(mma_bar, mma_phase);
-      mma_phase ^= 1;
-      tc_fence_after();
-    }
     __syncthreads();
     if (i < i1) {
-      // u_i is read by the epilogue of row i (next iteration); its slot was last read by the epilogue of
-      // row i-2, which every thread finished before the barrier above
-      if (t < CZ) sUi[(i & 1) * CZ + t] = ucur;
-      // (4) B'[z][d] = W1[z][d] * x_i[d]   (fp32 product, rounded once to fp16)
+      // (3) per K-block: B'[z][d] = W1[z][d] * x_i[d] into a ring slot, then its four UMMAs are issued while
+      // the next K-block is being built
 #pragma unroll
-      for (int n = 0; n < NCH; ++n) {
-        const int idx = t + 256 * n;
-        const int ch = idx & 7, z = (idx >> 3) % CZ, kb = (idx >> 3) / CZ;
+      for (int kb = 0; kb < KBS; ++kb, ++ring_it) {
+        const uint32_t slot = ring_it % RB;
+        if (ring_it >= RB) mbar_wait(&ring_free[slot], ((ring_it / RB) - 1) & 1);
         const int d0 = kb * 64 + ch * 8;
-        const __half2* w2 = reinterpret_cast<const __half2*>(&wreg[n]);
         const float4 xa = *reinterpret_cast<const float4*>(sXi + d0);
         const float4 xb = *reinterpret_cast<const float4*>(sXi + d0 + 4);
-        const float2 f0 = __half22float2(w2[0]), f1 = __half22float2(w2[1]);
-        const float2 f2 = __half22float2(w2[2]), f3 = __half22float2(w2[3]);
-        uint4 o;
-        o.x = pack_half2(f0.x * xa.x, f0.y * xa.y);
-        o.y = pack_half2(f1.x * xa.z, f1.y * xa.w);
-        o.z = pack_half2(f2.x * xb.x, f2.y * xb.y);
-        o.w = pack_half2(f3.x * xb.z, f3.y * xb.w);
-        *reinterpret_cast<uint4*>(sB + kb * CZ * 128 + sw128_offset(z, ch)) = o;
-      }
-      sync_before_mma();
-      if (t == 0) {
-        tc_fence_after();
-        umma_multi(tmem + (i & 1) * CZ, smem_u32(sA), smem_u32(sB), KBS, CZ * 128, umma_idesc_f16(128, CZ), false);
-        umma_commit(mma_bar);
+        uint8_t* sBs = sB + slot * (CZ * 128);
+#pragma unroll
+        for (int n = 0; n < CPK; ++n) {
+          const int z = (t >> 3) + 32 * n;
+          const __half2* w2 = reinterpret_cast<const __half2*>(&wreg[kb * CPK + n]);
+          const float2 f0 = __half22float2(w2[0]), f1 = __half22float2(w2[1]);
+          const float2 f2 = __half22float2(w2[2]), f3 = __half22float2(w2[3]);
+          uint4 o;
+          o.x = pack_half2(f0.x * xa.x, f0.y * xa.y);
+          o.y = pack_half2(f1.x * xa.z, f1.y * xa.w);
+          o.z = pack_half2(f2.x * xb.x, f2.y * xb.y);
+          o.w = pack_half2(f3.x * xb.z, f3.y * xb.w);
+          *reinterpret_cast<uint4*>(sBs + sw128_offset(z, ch)) = o;
+        }
+        sync_before_mma();
+        if (t == 0) {
+          tc_fence_after();
+          umma_kblock(tmem + (i & 1) * CZ, smem_u32(sA) + kb * 16384, smem_u32(sBs), umma_idesc_f16(128, CZ), kb > 0);
+          umma_commit(&ring_free[slot]);
+          if (kb == KBS - 1) umma_commit(&acc_full[i & 1]);
+        }
       }
     }
-    // (5) epilogue of row i-1 overlaps the UMMAs of row i
-    if (i > i0) epilogue(i - 1, res);
-    // the accumulator (i-1)&1 is rewritten by row i+1 only after the next __syncthreads
+    // (4) epilogue of row i-1 while the UMMAs of row i drain
+    if (i > i0) {
+      mbar_wait(&acc_full[(i - 1) & 1], ((i - 1 - i0) >> 1) & 1);
+      tc_fence_after();
+      epilogue(i - 1, res);
+    }
     tc_fence_before();
   }
   tc_fence_before();
@@ -192,7 +203,7 @@ template <int CZ, int KBS>
 static int launch_outer_linear(const CUtensorMap& mx, dim3 grid, const float* pair, float* dst, int residual,
                                const float* xn32, const __half* w1, const float* u, const float* bias, int N, int ilen,
                                cudaStream_t s) {
-  constexpr int smem = 1024 + KBS * 16384 + KBS * CZ * 128 + (KBS * 64 + 3 * CZ) * 4 + 64;
+  constexpr int smem = 1024 + KBS * 16384 + 4 * CZ * 128 + (KBS * 64 + 3 * CZ) * 4 + 128;
   static_assert(smem <= 227 * 1024, "outer_linear shared memory budget");
   auto kern = outer_linear_kernel<CZ, KBS>;
   PRD_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));

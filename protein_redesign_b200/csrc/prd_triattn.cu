@@ -107,8 +107,11 @@ triattn_flash_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
   const uint32_t tmem = *tmem_slot;
   constexpr uint32_t kOcol = 256;  // O chunks: column 256 + g*64 + h*16
 
+  // Register budget: the CTA pool is 384 threads x 168 registers (what ptxas allocates under the launch
+  // bound); the third warpgroup shrinks to 72, which frees exactly the 12288 registers the two softmax
+  // warpgroups need to grow to 216 (setmaxnreg can only move registers inside the CTA's own pool).
   if (warp >= 8) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
     if (warp == 8 && lane == 0) {
       // ---------------- TMA producer ----------------
       mbar_expect_tx(bar_q, 32768);
