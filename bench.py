@@ -265,7 +265,7 @@ def run_ours(args):
         # ---- dominant kernel alone (roofline) ------------------------------------------------------
         roof = None
         if rank == 0 and hasattr(lib, "prd_profile_kernel"):
-            roof = profile_dominant(lib, cfg, B, N, dev, mask)
+            roof = profile_dominant(lib, cfg, B, N, dev, mask, bufs["pair"])
 
     if world > 1:
         t_all = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
@@ -302,26 +302,55 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-def profile_dominant(lib, cfg, B, N, dev, mask):
-    """Average duration of the triangle-attention core kernel alone (events on the launch stream)."""
+def profile_dominant(lib, cfg, B, N, dev, mask, pair):
+    """Average duration of individual kernels, each timed alone (CUDA events on the launch stream) on the
+    data the last step left in the workspace.  Returns the roofline object of the dominant kernel (the
+    triangle-attention core) and a list for the other kernels north_star names."""
     from protein_redesign_b200 import _lib, ops
 
     peaks = load_peaks()
     d = ops.make_dims(cfg, B, N)
-    ws = _lib.Workspace.reserve(dev, _lib.workspace_bytes("triangle_attention", d))
-    ms = ctypes.c_float(0.0)
+    ws = _lib.Workspace.reserve(dev, max(_lib.workspace_bytes(op, d) for op in _lib.OPS))
     lib.prd_profile_kernel.restype = ctypes.c_int
-    rc = lib.prd_profile_kernel(b"triattn_flash", ctypes.byref(d), ctypes.c_void_p(ws.data_ptr()),
-                                ctypes.c_size_t(ws.numel()), ctypes.c_void_p(mask.data_ptr()), 5, ctypes.byref(ms),
-                                ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
-    if rc != 0:
-        return {"error": _lib.last_error()}
-    flops = 2.0 * 2.0 * B * N * cfg.num_heads * N * N * cfg.head_dim  # QK^T + PV per call (SURVEY §8d)
-    achieved = flops / (ms.value * 1e-3) / 1e12
-    return {"kernel": "triattn_flash_kernel", "bound": "tensor", "achieved": achieved, "peak": peaks["tflops"],
-            "unit": "TFLOP/s", "frac": achieved / peaks["tflops"], "traffic": None, "peak_source": peaks["source"],
-            "ms_per_launch": ms.value,
-            "note": "co-limited by MUFU exp: 1.07e9 exp per launch (B*N*H*N*N)"}
+    stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+    def time_kernel(name, aux):
+        ms = ctypes.c_float(0.0)
+        rc = lib.prd_profile_kernel(name.encode(), ctypes.byref(d), ctypes.c_void_p(ws.data_ptr()),
+                                    ctypes.c_size_t(ws.numel()), ctypes.c_void_p(aux.data_ptr() if aux is not None else 0),
+                                    5, ctypes.byref(ms), stream)
+        if rc != 0:
+            raise RuntimeError(_lib.last_error())
+        return ms.value
+
+    P = 4.0 * B * N * N * cfg.pair_dim  # bytes of one fp32 pair tensor
+    out = []
+    # triangle-multiplication contraction: 2*B*N^3*c_z flop; a, b fp16 planes in, x fp32 planes out
+    ms = time_kernel("trimul_gemm", None)
+    flops = 2.0 * B * N ** 3 * cfg.pair_dim
+    out.append({"kernel": "gemm_f16_kernel (tri-mul contraction)", "bound": "tensor", "achieved": flops / ms / 1e9,
+                "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": flops / ms / 1e9 / peaks["tflops"], "traffic": None,
+                "ms_per_launch": ms, "hbm_floor_ms": (P + P) / peaks["hbm_gbs"] / 1e6,
+                "note": "HBM floor: 0.5 P (a) + 0.5 P (b) + 1 P (x fp32) = 2 P"})
+    # pair-bias stream: reads P, writes P/16
+    ms = time_kernel("pair_bias", pair)
+    nbytes = P + P * 4 / cfg.pair_dim
+    out.append({"kernel": "pair_bias_kernel (LN + c_z->4 bias stream)", "bound": "hbm", "achieved": nbytes / ms / 1e6,
+                "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": nbytes / ms / 1e6 / peaks["hbm_gbs"], "traffic": None,
+                "ms_per_launch": ms})
+    # triangle attention core (dominant): QK^T + PV flops; co-limited by 4*B*N^3 exp2 on the MUFU pipe
+    ms = time_kernel("triattn_flash", mask)
+    flops = 2.0 * 2.0 * B * N * cfg.num_heads * N * N * cfg.head_dim
+    n_exp = float(B) * N * cfg.num_heads * N * N
+    mufu_floor_ms = n_exp / (148 * 16 * 1.965e9) * 1e3
+    roof = {"kernel": "triattn_flash_kernel", "bound": "tensor", "achieved": flops / ms / 1e9, "peak": peaks["tflops"],
+            "unit": "TFLOP/s", "frac": flops / ms / 1e9 / peaks["tflops"], "traffic": None,
+            "peak_source": peaks["source"], "ms_per_launch": ms, "mufu_floor_ms": mufu_floor_ms,
+            "mufu_frac": mufu_floor_ms / ms,
+            "note": "K=16 attention: the binding unit is the MUFU exp2 pipe (%.2e exp2 per launch at 16/clk/SM), "
+                    "not the tensor pipe" % n_exp,
+            "others": out}
+    return roof
 
 
 def main():

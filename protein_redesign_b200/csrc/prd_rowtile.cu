@@ -15,8 +15,15 @@ struct RowMap {
   long long NN;
   int transposed;  // 0: logical row (b,s,t) reads pair[b,s,t]; 1: reads pair[b,t,s]
   __device__ __forceinline__ void decompose(long long r, int& b, int& s, int& t) const {
-    b = static_cast<int>(r / NN);
-    const int rem = static_cast<int>(r - (long long)b * NN);
+    int rem;
+    if (r < 0x7fffffffLL && NN < 0x7fffffffLL) {  // 32-bit division (the 64-bit one costs ~100 instructions)
+      const unsigned r32 = static_cast<unsigned>(r), nn32 = static_cast<unsigned>(NN);
+      b = static_cast<int>(r32 / nn32);
+      rem = static_cast<int>(r32 - static_cast<unsigned>(b) * nn32);
+    } else {
+      b = static_cast<int>(r / NN);
+      rem = static_cast<int>(r - (long long)b * NN);
+    }
     s = rem / N;
     t = rem - s * N;
   }
@@ -434,8 +441,14 @@ trimul_out_kernel(const float* pair, float* dst, int residual, const float* __re
       // contraction result for this (b,i,j): one value per channel plane, coalesced across lanes
       float x[CZ];
       if (valid) {
-        const int b = static_cast<int>(r / NN);
-        const int rem = static_cast<int>(r - (long long)b * NN);
+        int b, rem;
+        if (r < 0x7fffffffLL && NN < 0x7fffffffLL) {
+          b = static_cast<int>(static_cast<unsigned>(r) / static_cast<unsigned>(NN));
+          rem = static_cast<int>(static_cast<unsigned>(r) - static_cast<unsigned>(b) * static_cast<unsigned>(NN));
+        } else {
+          b = static_cast<int>(r / NN);
+          rem = static_cast<int>(r - (long long)b * NN);
+        }
         const int i = rem / N, j = rem - i * N;
         const float* xp = xpl + (long long)b * CZ * xplane + (long long)i * Nx + j;
 #pragma unroll

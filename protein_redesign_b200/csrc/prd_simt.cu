@@ -44,114 +44,96 @@ int layernorm_rows(const float* x, int rows, int C, const float* gamma, const fl
 
 // -----------------------------------------------------------------------------------------
 // Pair-bias projection stream: bias[b,h,i,j] = LN(pair[b,i,j,:]) . w[h,:] (+ bvec[h]).
-// HBM-bound: reads the pair tensor once (16-byte loads, L1 no-allocate), writes 4/c_z of it.
-// CZ/4 lanes cooperate on one pair element; a warp covers 32 consecutive elements per pass so
-// the four head planes are written with full 128-byte lines.
+// HBM-bound: reads the pair tensor once, writes 4/c_z of it.
 // -----------------------------------------------------------------------------------------
-__device__ __forceinline__ float4 ldg_stream(const float4* p) {
-  float4 r;
-  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
-               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
-               : "l"(p));
-  return r;
-}
-
-// Streaming design: the pair tensor is pulled through a 3-stage shared-memory ring with 32 KB bulk
-// copies (cp.async.bulk + mbarrier), so ~96 KB per CTA are in flight independent of what the warps
-// are doing; the 8 warps then normalise / project 16 elements each per stage straight from shared
-// memory (16-byte conflict-free reads) and write 64-byte runs of the four head planes.
+// Streaming design: one thread per pair element.  Every thread bulk-copies its own 4*CZ-byte row
+// (cp.async.bulk + mbarrier) into a padded slot of a 3-stage shared-memory ring, so three rows per
+// thread (~200 KB per SM) are in flight no matter what the warps are doing; LayerNorm and the four
+// head dot products then run thread-locally in registers (no shuffles), and consecutive threads
+// write consecutive positions of the four head planes (full 128-byte lines).
 template <int CZ>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 1)
 pair_bias_kernel(const float* __restrict__ pair, long long R, long long NN, const float* __restrict__ ln_w,
                  const float* __restrict__ ln_b, const float* __restrict__ w, const float* __restrict__ bvec,
                  float* __restrict__ out) {
-  constexpr int LPE = CZ / 4;          // lanes per element
-  constexpr int EPW = 32 / LPE;        // elements per warp-wide read
-  constexpr int ELEMS = 128;           // elements per stage
-  constexpr int ITER = 16 / EPW;       // reads per warp per stage (16 elements per warp)
+  constexpr int ROWS = 256;                 // elements per stage = threads per CTA
   constexpr int STAGES = 3;
-  constexpr int kStageBytes = ELEMS * CZ * 4;
+  constexpr int kRowBytes = CZ * 4 + 16;    // padded: same-column reads of 32 lanes hit distinct banks
+  constexpr int kStageBytes = ROWS * kRowBytes;
   extern __shared__ __align__(128) uint8_t smem_pb[];
-  float* stage = reinterpret_cast<float*>(smem_pb);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem_pb + STAGES * kStageBytes);
-
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int sub = lane % LPE, grp = lane / LPE;
-  float4 gam = make_float4(1.f, 1.f, 1.f, 1.f), bet = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (ln_w) {
-    gam = reinterpret_cast<const float4*>(ln_w)[sub];
-    bet = reinterpret_cast<const float4*>(ln_b)[sub];
+  float* sW = reinterpret_cast<float*>(full + STAGES);  // [4][CZ] folded weights, [4] folded bias
+  const int t = threadIdx.x;
+  // fold the affine LayerNorm into the projection:  (y*g + b) . w_h = y . (g*w_h) + b . w_h
+  for (int i = t; i < 4 * CZ; i += 256) sW[i] = w[i] * (ln_w ? ln_w[i % CZ] : 1.0f);
+  if (t < 4) {
+    float acc = bvec ? bvec[t] : 0.f;
+    if (ln_b)
+      for (int c = 0; c < CZ; ++c) acc += ln_b[c] * w[t * CZ + c];
+    sW[4 * CZ + t] = acc;
   }
-  float4 wh[4];
-#pragma unroll
-  for (int h = 0; h < 4; ++h) wh[h] = reinterpret_cast<const float4*>(w + h * CZ)[sub];
-  float bh[4];
-#pragma unroll
-  for (int h = 0; h < 4; ++h) bh[h] = bvec ? bvec[h] : 0.f;
-
-  const long long nchunks = (R + ELEMS - 1) / ELEMS;
-  auto load = [&](long long chunk, int s) {
-    const long long e0 = chunk * ELEMS;
-    const long long n = (R - e0 < ELEMS) ? (R - e0) : ELEMS;
-    const uint32_t bytes = static_cast<uint32_t>(n * CZ * 4);
-    mbar_expect_tx(&full[s], bytes);
-    bulk_g2s(stage + s * (kStageBytes / 4), pair + e0 * CZ, bytes, &full[s]);
-  };
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; ++s) mbar_init(&full[s], 1);
+  if (t == 0) {
+    for (int s = 0; s < STAGES; ++s) mbar_init(&full[s], ROWS);
     fence_barrier_init();
-    for (int s = 0; s < STAGES; ++s) {
-      const long long c = (long long)blockIdx.x + (long long)s * gridDim.x;
-      if (c < nchunks) load(c, s);
-    }
   }
   __syncthreads();
-  int it_chunk = 0;
-  for (long long chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x, ++it_chunk) {
-    const int s = it_chunk % STAGES;
-    mbar_wait(&full[s], (it_chunk / STAGES) & 1);
-    const float4* st = reinterpret_cast<const float4*>(stage + s * (kStageBytes / 4));
-    const long long e0 = chunk * ELEMS + warp * 16;
-    float keep[4] = {0.f, 0.f, 0.f, 0.f};
+  const long long nchunks = (R + ROWS - 1) / ROWS;
+  auto load = [&](long long chunk, int s) {
+    const long long e = chunk * ROWS + t;
+    uint8_t* dst = smem_pb + s * kStageBytes + t * kRowBytes;
+    if (e < R) {
+      mbar_expect_tx(&full[s], CZ * 4);
+      bulk_g2s(dst, pair + e * CZ, CZ * 4, &full[s]);
+    } else {
+      mbar_arrive(&full[s]);
+    }
+  };
+  for (int s = 0; s < STAGES; ++s) {
+    const long long c = (long long)blockIdx.x + (long long)s * gridDim.x;
+    if (c < nchunks) load(c, s);
+  }
+  int it = 0;
+  for (long long chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x, ++it) {
+    const int s = it % STAGES;
+    mbar_wait(&full[s], (it / STAGES) & 1);
+    const float* row = reinterpret_cast<const float*>(smem_pb + s * kStageBytes + t * kRowBytes);
+    float x[CZ];
 #pragma unroll
-    for (int it = 0; it < ITER; ++it) {
-      const int el = warp * 16 + it * EPW + grp;  // element inside the stage
-      const float4 v = st[el * LPE + sub];
-      float sm = v.x + v.y + v.z + v.w;
+    for (int c = 0; c < CZ / 4; ++c) {
+      const float4 v = *reinterpret_cast<const float4*>(row + c * 4);
+      x[c * 4] = v.x; x[c * 4 + 1] = v.y; x[c * 4 + 2] = v.z; x[c * 4 + 3] = v.w;
+    }
+    // this thread's slot is free again: refill it for the chunk three rounds ahead
+    {
+      const long long cn = chunk + (long long)STAGES * gridDim.x;
+      if (cn < nchunks) load(cn, s);
+    }
+    float sum = 0.f;
 #pragma unroll
-      for (int o = LPE / 2; o > 0; o >>= 1) sm += __shfl_xor_sync(0xffffffffu, sm, o);
-      const float mean = sm * (1.0f / CZ);
-      const float d0 = v.x - mean, d1 = v.y - mean, d2 = v.z - mean, d3 = v.w - mean;
-      float q = d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
+    for (int c = 0; c < CZ; ++c) sum += x[c];
+    const float mean = sum * (1.0f / CZ);
+    float var = 0.f;
 #pragma unroll
-      for (int o = LPE / 2; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
-      const float rstd = rsqrtf(q * (1.0f / CZ) + 1e-5f);
-      const float y0 = d0 * rstd * gam.x + bet.x, y1 = d1 * rstd * gam.y + bet.y;
-      const float y2 = d2 * rstd * gam.z + bet.z, y3 = d3 * rstd * gam.w + bet.w;
+    for (int c = 0; c < CZ; ++c) {
+      x[c] -= mean;
+      var += x[c] * x[c];
+    }
+    const float rstd = rsqrtf(var * (1.0f / CZ) + 1e-5f);
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int c = 0; c < CZ; c += 4) {
 #pragma unroll
       for (int h = 0; h < 4; ++h) {
-        float p = y0 * wh[h].x + y1 * wh[h].y + y2 * wh[h].z + y3 * wh[h].w;
-#pragma unroll
-        for (int o = LPE / 2; o > 0; o >>= 1) p += __shfl_xor_sync(0xffffffffu, p, o);
-        // element (it*EPW + g) of this warp's 16 is delivered to lane (it*EPW + g)
-#pragma unroll
-        for (int g2 = 0; g2 < EPW; ++g2) {
-          const float pv = __shfl_sync(0xffffffffu, p, g2 * LPE);
-          if (lane == it * EPW + g2) keep[h] = pv + bh[h];
-        }
+        const float4 wv = *reinterpret_cast<const float4*>(sW + h * CZ + c);  // broadcast
+        acc[h] += x[c] * wv.x + x[c + 1] * wv.y + x[c + 2] * wv.z + x[c + 3] * wv.w;
       }
     }
-    const long long e = e0 + lane;
-    if (lane < 16 && e < R) {
+    const long long e = chunk * ROWS + t;
+    if (e < R) {
       const long long b = e / NN;
       const long long ij = e - b * NN;
 #pragma unroll
-      for (int h = 0; h < 4; ++h) out[(b * 4 + h) * NN + ij] = keep[h];
-    }
-    __syncthreads();  // every warp is done with stage s
-    if (threadIdx.x == 0) {
-      const long long c = chunk + (long long)STAGES * gridDim.x;
-      if (c < nchunks) load(c, s);
+      for (int h = 0; h < 4; ++h) out[(b * 4 + h) * NN + ij] = acc[h] * rstd + sW[4 * CZ + h];
     }
   }
 }
@@ -160,14 +142,14 @@ int pair_bias_proj(const PairDims& d, int H, const float* pair, const float* ln_
                    const float* bvec, float* bias_out, cudaStream_t s) {
   PRD_REQUIRE(H == 4, "pair_bias_proj: num_heads %d unsupported (built for 4)", H);
   const long long NN = (long long)d.N * d.N, R = NN * d.B;
-  const long long nchunks = (R + 127) / 128;
-  const int blocks = (int)(nchunks < 2 * kNumSMs ? nchunks : 2 * kNumSMs);
+  const long long nchunks = (R + 255) / 256;
+  const int blocks = (int)(nchunks < kNumSMs ? nchunks : kNumSMs);
   if (d.CZ == 64) {
-    constexpr int smem = 3 * 128 * 64 * 4 + 64;
+    constexpr int smem = 3 * 256 * (64 * 4 + 16) + 64 + (4 * 64 + 4) * 4;
     PRD_CUDA_OK(cudaFuncSetAttribute(pair_bias_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     pair_bias_kernel<64><<<blocks, 256, smem, s>>>(pair, R, NN, ln_w, ln_b, w, bvec, bias_out);
   } else if (d.CZ == 32) {
-    constexpr int smem = 3 * 128 * 32 * 4 + 64;
+    constexpr int smem = 3 * 256 * (32 * 4 + 16) + 64 + (4 * 32 + 4) * 4;
     PRD_CUDA_OK(cudaFuncSetAttribute(pair_bias_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     pair_bias_kernel<32><<<blocks, 256, smem, s>>>(pair, R, NN, ln_w, ln_b, w, bvec, bias_out);
   } else {

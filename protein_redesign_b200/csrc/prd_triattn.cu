@@ -12,8 +12,6 @@
 // Inputs come from triattn_proj (prd_rowtile.cu): q (x 1/sqrt(c)), k, g=sigmoid(gate) as
 // [B*N seq][N tok][64] fp16 and vt [B*N seq][64][plane_ld(N)] fp16.
 // Output og [B*N*N][64] fp16 = g * softmax(..) v, consumed by triattn_out.
-#include <stdlib.h>
-
 #include "prd_kernels.h"
 #include "prd_rowtile.cuh"
 
@@ -28,288 +26,12 @@ constexpr float kMaskFillLog2 = -32768.0f * kLog2e;  // modules.py:177,220 in th
 //   j >= N (pad): mul = 0,       add = -inf               (does not exist: p = 0)
 // A key tile whose 128 keys are all valid takes a fast path without any per-key loads.
 //
-// Warp-specialised CTA (384 threads, one CTA per SM):
-//   warps 0-3  softmax group 0  (query tile 2*qp)      thread <-> query row <-> TMEM lane
-//   warps 4-7  softmax group 1  (query tile 2*qp + 1)
-//   warp  8    TMA producer: Q tiles once, K / V^T tiles double buffered
-//   warp  9    UMMA issuer for both groups
-//   warps 10-11 idle (complete the third warpgroup so setmaxnreg can move their registers)
-// The two groups share the K / V^T tiles; while one group is waiting for its next S tile the
-// other one is in its exp2 loop, which keeps the MUFU pipe busy.
-// Per group and head: S (128 TMEM columns) -> pass A max, pass B exp2 -> P (fp16, smem) ->
-// O_h (16 TMEM columns).  O chunks are read back once per key tile and rescaled in registers.
-constexpr int kFlashThreads = 384;
-
-__global__ void __launch_bounds__(kFlashThreads, 1)
-triattn_flash_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
-                     const __grid_constant__ CUtensorMap map_vt, const float* __restrict__ mask,
-                     const __half* __restrict__ g, __half* __restrict__ og, int N) {
-  extern __shared__ uint8_t raw[];
-  uint8_t* sm = smem_align1024(raw);
-  uint8_t* sQ = sm;                 // 2 x [128 x 64] halves (one per group)
-  uint8_t* sK = sQ + 32768;         // 2 stages x [128 keys x 64]
-  uint8_t* sVt = sK + 32768;        // 2 stages x 2 boxes of [64 rows x 64 keys]
-  uint8_t* sP = sVt + 32768;        // 2 groups x 2 K-blocks of [128 x 64 keys]
-  const int nkt = (N + 127) / 128;
-  float2* sKey = reinterpret_cast<float2*>(sP + 65536);       // (mul, add) per key, nkt * 128 entries
-  int* sAllValid = reinterpret_cast<int*>(sKey + nkt * 128);  // per key tile
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sAllValid + ((nkt + 1) & ~1));
-  uint64_t* bar_q = bars;            // [1]
-  uint64_t* kv_full = bars + 1;      // [2]
-  uint64_t* kv_free = bars + 3;      // [2]
-  uint64_t* s_full = bars + 5;       // [2] per group
-  uint64_t* sp_ready = bars + 7;     // [2] per group: S consumed and P written (128 arrivals)
-  uint64_t* p_free = bars + 9;       // [2] per group
-  uint64_t* o_full = bars + 11;      // [2] per group
-  uint64_t* o_free = bars + 13;      // [2] per group (128 arrivals)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int npair = (nkt + 1) / 2;
-  const int qp = blockIdx.x % npair;   // the q-tile pairs of one sequence are adjacent CTAs (K/V stay in L2)
-  const int seq = blockIdx.x / npair;  // b * N + s
-  const int b = seq / N;
-  if (threadIdx.x == 0) {
-    mbar_init(bar_q, 1);
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&kv_full[i], 1);
-      mbar_init(&kv_free[i], 1);
-      mbar_init(&s_full[i], 1);
-      mbar_init(&sp_ready[i], 128);
-      mbar_init(&p_free[i], 1);
-      mbar_init(&o_full[i], 1);
-      mbar_init(&o_free[i], 128);
-    }
-    fence_barrier_init();
-    tma_prefetch_desc(&map_q);
-    tma_prefetch_desc(&map_k);
-    tma_prefetch_desc(&map_vt);
-  }
-  if (warp == 8) tmem_alloc(tmem_slot, 512);
-  {
-    // key mask = m[b,seq_pos] * m[b,key]  (mask_2d row / column; symmetric, one formula for both modes)
-    const float ms = mask[seq];
-    for (int j = threadIdx.x; j < nkt * 128; j += kFlashThreads) {
-      float2 e;
-      if (j >= N) e = make_float2(0.f, -INFINITY);
-      else if (ms * mask[(long long)b * N + j] < 0.5f) e = make_float2(0.f, kMaskFillLog2);
-      else e = make_float2(kLog2e, 0.f);
-      sKey[j] = e;
-    }
-  }
-  __syncthreads();
-  if (threadIdx.x < nkt) {
-    int all = 1;
-    for (int j = 0; j < 128; ++j) all &= (sKey[threadIdx.x * 128 + j].x != 0.f) ? 1 : 0;
-    sAllValid[threadIdx.x] = all;
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem = *tmem_slot;
-  constexpr uint32_t kOcol = 256;  // O chunks: column 256 + g*64 + h*16
-
-  // Register budget: the CTA pool is 384 threads x 168 registers (what ptxas allocates under the launch
-  // bound); the third warpgroup shrinks to 72, which frees exactly the 12288 registers the two softmax
-  // warpgroups need to grow to 216 (setmaxnreg can only move registers inside the CTA's own pool).
-  if (warp >= 8) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
-    if (warp == 8 && lane == 0) {
-      // ---------------- TMA producer ----------------
-      mbar_expect_tx(bar_q, 32768);
-      tma_load_3d(sQ, &map_q, bar_q, 0, (2 * qp) * 128, seq);
-      tma_load_3d(sQ + 16384, &map_q, bar_q, 0, (2 * qp + 1) * 128, seq);
-      for (int kt = 0; kt < nkt; ++kt) {
-        const int st = kt & 1;
-        if (kt >= 2) mbar_wait(&kv_free[st], ((kt >> 1) - 1) & 1);
-        mbar_expect_tx(&kv_full[st], 32768);
-        tma_load_3d(sK + st * 16384, &map_k, &kv_full[st], 0, kt * 128, seq);
-        tma_load_3d(sVt + st * 16384, &map_vt, &kv_full[st], kt * 128, 0, seq);
-        tma_load_3d(sVt + st * 16384 + 8192, &map_vt, &kv_full[st], kt * 128 + 64, 0, seq);
-      }
-    } else if (warp == 9 && lane == 0) {
-      // ---------------- UMMA issuer ----------------
-      const uint32_t idesc_s = umma_idesc_f16(128, 128), idesc_o = umma_idesc_f16(128, 16);
-      uint32_t n_sp[2] = {0, 0};  // sp_ready waits done per group
-      mbar_wait(bar_q, 0);
-      for (int kt = 0; kt < nkt; ++kt) {
-        const int st = kt & 1;
-        mbar_wait(&kv_full[st], (kt >> 1) & 1);
-        tc_fence_after();
-        const uint64_t dk = umma_desc_sw128(smem_u32(sK + st * 16384));
-        const uint32_t vt0 = smem_u32(sVt + st * 16384);
-        for (int gi = 0; gi < 2; ++gi) {  // S of head 0: the S buffers were released by sp_ready(h=3) of the previous tile
-          umma_f16(tmem + gi * 128, umma_desc_sw128(smem_u32(sQ + gi * 16384)), dk, idesc_s, 0u);
-          umma_commit(&s_full[gi]);
-        }
-        for (int h = 0; h < 4; ++h) {
-          for (int gi = 0; gi < 2; ++gi) {
-            mbar_wait(&sp_ready[gi], n_sp[gi] & 1);
-            ++n_sp[gi];
-            tc_fence_after();
-            if (h == 0 && kt > 0) {
-              mbar_wait(&o_free[gi], (kt - 1) & 1);  // the group has read the O chunks of the previous tile
-              tc_fence_after();
-            }
-            if (h < 3) {  // the S tile the group waits for next goes first
-              umma_f16(tmem + gi * 128, umma_desc_sw128(smem_u32(sQ + gi * 16384)) + 2 * (h + 1), dk + 2 * (h + 1), idesc_s, 0u);
-              umma_commit(&s_full[gi]);
-            }
-            const uint32_t d_o = tmem + kOcol + gi * 64 + h * 16;
-            const uint32_t p0 = smem_u32(sP + gi * 32768);
-            umma_kblock(d_o, p0, vt0 + h * 2048, idesc_o, false);
-            umma_kblock(d_o, p0 + 16384, vt0 + 8192 + h * 2048, idesc_o, true);
-            umma_commit(&p_free[gi]);
-            if (h == 3) umma_commit(&o_full[gi]);
-          }
-        }
-        umma_commit(&kv_free[st]);  // every UMMA reading this K / V^T stage has been issued; arrives when they finish
-      }
-    }
-  } else {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
-    // ---------------- softmax groups ----------------
-    const int gi = warp >> 2;
-    const int t = threadIdx.x & 127;
-    const uint32_t tm_lane = tmem + (static_cast<uint32_t>((warp & 3) * 32) << 16);
-    const uint32_t tm_s = tm_lane + gi * 128;
-    const uint32_t tm_o = tm_lane + kOcol + gi * 64;
-    uint8_t* sPg = sP + gi * 32768;
-    float o[4][16];
-    float mrow[4], lrow[4];
-#pragma unroll
-    for (int h = 0; h < 4; ++h) {
-      mrow[h] = -INFINITY;
-      lrow[h] = 0.f;
-#pragma unroll
-      for (int c = 0; c < 16; ++c) o[h][c] = 0.f;
-    }
-    uint32_t n_s = 0;  // S tiles consumed so far (= P tiles written)
-    for (int kt = 0; kt < nkt; ++kt) {
-      const bool all_valid = sAllValid[kt] != 0;
-      const float2* keyp = sKey + kt * 128;
-      float alpha[4];
-#pragma unroll
-      for (int h = 0; h < 4; ++h) {
-        mbar_wait(&s_full[gi], n_s & 1);
-        tc_fence_after();
-        // pass A: row max over this key tile (exp2 domain)
-        float mx = mrow[h];
-        if (all_valid) {
-          float raw_max = -INFINITY;
-#pragma unroll 1
-          for (int c = 0; c < 4; ++c) {
-            uint32_t sv[32];
-            tmem_ld32(tm_s + c * 32, sv);
-            tmem_ld_wait();
-#pragma unroll
-            for (int j = 0; j < 32; ++j) raw_max = fmaxf(raw_max, __uint_as_float(sv[j]));
-          }
-          mx = fmaxf(mx, raw_max * kLog2e);
-        } else {
-#pragma unroll 1
-          for (int c = 0; c < 4; ++c) {
-            uint32_t sv[32];
-            tmem_ld32(tm_s + c * 32, sv);
-            tmem_ld_wait();
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const float2 e = keyp[c * 32 + j];
-              mx = fmaxf(mx, fmaf(__uint_as_float(sv[j]), e.x, e.y));
-            }
-          }
-        }
-        alpha[h] = ex2_approx(mrow[h] - mx);
-        mrow[h] = mx;
-        // the P buffer is free once the P.V UMMAs of the previous head have completed
-        if (n_s > 0) mbar_wait(&p_free[gi], (n_s - 1) & 1);
-        // pass B: p = exp2(t - m), row sum, fp16 P tile
-        float rs = 0.f;
-        if (all_valid) {
-          const float nmx = -mx;
-#pragma unroll 1
-          for (int c = 0; c < 8; ++c) {
-            uint32_t sv[16];
-            tmem_ld16(tm_s + c * 16, sv);
-            tmem_ld_wait();
-            float p[16];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              p[j] = ex2_approx(fmaf(__uint_as_float(sv[j]), kLog2e, nmx));
-              rs += p[j];
-            }
-            store_a_cols16(sPg, t, c * 16, p);
-          }
-        } else {
-#pragma unroll 1
-          for (int c = 0; c < 8; ++c) {
-            uint32_t sv[16];
-            tmem_ld16(tm_s + c * 16, sv);
-            tmem_ld_wait();
-            float p[16];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const float2 e = keyp[c * 16 + j];
-              p[j] = ex2_approx(fmaf(__uint_as_float(sv[j]), e.x, e.y) - mx);
-              rs += p[j];
-            }
-            store_a_cols16(sPg, t, c * 16, p);
-          }
-        }
-        lrow[h] = lrow[h] * alpha[h] + rs;
-        ++n_s;
-        // S fully read and P visible to the tensor core: let the issuer run P.V(h) and S(h+1)
-        fence_proxy_async_smem();
-        tc_fence_before();
-        mbar_arrive(&sp_ready[gi]);
-      }
-      // the four P.V products of this key tile: read back once, rescale in registers
-      mbar_wait(&o_full[gi], kt & 1);
-      tc_fence_after();
-#pragma unroll
-      for (int h = 0; h < 4; ++h) {
-        uint32_t ov[16];
-        tmem_ld16(tm_o + 16 * h, ov);
-        tmem_ld_wait();
-#pragma unroll
-        for (int c = 0; c < 16; ++c) o[h][c] = o[h][c] * alpha[h] + __uint_as_float(ov[c]);
-      }
-      tc_fence_before();
-      mbar_arrive(&o_free[gi]);
-    }
-
-    const int tok = (2 * qp + gi) * 128 + t;
-    if (tok < N) {
-      const long long r = (long long)seq * N + tok;
-      const uint4* gp = reinterpret_cast<const uint4*>(g + r * 64);
-      uint4* op = reinterpret_cast<uint4*>(og + r * 64);
-#pragma unroll
-      for (int h = 0; h < 4; ++h) {
-        const float inv = 1.0f / lrow[h];
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          const uint4 gv = __ldg(gp + h * 2 + half);
-          const __half2* g2 = reinterpret_cast<const __half2*>(&gv);
-          uint4 ovv;
-          uint32_t* o32 = reinterpret_cast<uint32_t*>(&ovv);
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const float2 gf = __half22float2(g2[e]);
-            o32[e] = pack_half2(o[h][half * 8 + 2 * e] * inv * gf.x, o[h][half * 8 + 2 * e + 1] * inv * gf.y);
-          }
-          op[h * 2 + half] = ovv;
-        }
-      }
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 8) tmem_dealloc(tmem, 512);
-}
-
-// ---- variant A: one softmax group per CTA, two CTAs per SM (desynchronise naturally) ----
+// One softmax group (128 threads) per CTA, two CTAs per SM: the two CTAs drift apart, so one is in
+// its exp2 loop while the other waits for an S tile.  (A warp-specialised single-CTA variant with two
+// softmax groups sharing K/V, a TMA warp and a UMMA warp was measured 20 % slower -- the groups ran in
+// lockstep -- see profiles/r01_flash_variants.md.)
 __global__ void __launch_bounds__(128, 2)
-triattn_flash_cta2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
+triattn_flash_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
                      const __grid_constant__ CUtensorMap map_vt, const float* __restrict__ mask,
                      const __half* __restrict__ g, __half* __restrict__ og, int N) {
   extern __shared__ uint8_t raw[];
@@ -418,16 +140,16 @@ triattn_flash_cta2_kernel(const __grid_constant__ CUtensorMap map_q, const __gri
       // pass A: row max over this key tile (exp2 domain)
       float mx = mrow[h];
       if (all_valid) {
-        float raw_max = -INFINITY;
+        float rm[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};  // independent chains (ILP)
 #pragma unroll 1
         for (int c = 0; c < 4; ++c) {
           uint32_t sv[32];
           tmem_ld32(tm_lane + c * 32, sv);
           tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 32; ++j) raw_max = fmaxf(raw_max, __uint_as_float(sv[j]));
+          for (int j = 0; j < 32; ++j) rm[j & 3] = fmaxf(rm[j & 3], __uint_as_float(sv[j]));
         }
-        mx = fmaxf(mx, raw_max * kLog2e);
+        mx = fmaxf(mx, fmaxf(fmaxf(rm[0], rm[1]), fmaxf(rm[2], rm[3])) * kLog2e);
       } else {
 #pragma unroll 1
         for (int c = 0; c < 4; ++c) {
@@ -449,6 +171,7 @@ triattn_flash_cta2_kernel(const __grid_constant__ CUtensorMap map_q, const __gri
       float rs = 0.f;
       if (all_valid) {
         const float nmx = -mx;
+        float r4[4] = {0.f, 0.f, 0.f, 0.f};  // independent chains (ILP)
 #pragma unroll 1
         for (int c = 0; c < 4; ++c) {
           uint32_t sv[32];
@@ -458,10 +181,11 @@ triattn_flash_cta2_kernel(const __grid_constant__ CUtensorMap map_q, const __gri
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             p[j] = ex2_approx(fmaf(__uint_as_float(sv[j]), kLog2e, nmx));
-            rs += p[j];
+            r4[j & 3] += p[j];
           }
           store_a_cols32(sP, t, c * 32, p);
         }
+        rs = (r4[0] + r4[1]) + (r4[2] + r4[3]);
       } else {
 #pragma unroll 1
         for (int c = 0; c < 4; ++c) {
@@ -563,22 +287,11 @@ int triattn_flash(const PairDims& d, const float* mask, const __half* q, const _
   t.box[0] = 64; t.box[1] = 64; t.box[2] = 1;
   if (make_tensor_map(&mv, vt, 2, 3, t, true)) return 1;
   const int nkt = (N + 127) / 128;
-  const int npair = (nkt + 1) / 2;
-  const int smem = 1024 + 32768 * 3 + 65536 + nkt * 128 * 8 + ((nkt + 1) & ~1) * 4 + 256;
+  const int smem = 1024 + 16384 * 4 + 32768 + nkt * 128 * 8 + ((nkt + 1) & ~1) * 4 + 128;
+  PRD_REQUIRE(smem <= 113 * 1024, "triattn_flash: N=%d needs %d B of shared memory", N, smem);
   PRD_CUDA_OK(cudaFuncSetAttribute(triattn_flash_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  static const bool use_ws = [] { const char* e = getenv("PRD_FLASH"); return e != nullptr && e[0] == 'b'; }();
-  if (!use_ws) {
-    const int smem_a = 1024 + 16384 * 4 + 32768 + nkt * 128 * 8 + ((nkt + 1) & ~1) * 4 + 128;
-    PRD_CUDA_OK(cudaFuncSetAttribute(triattn_flash_cta2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_a));
-    PRD_REQUIRE(nseq * nkt <= 2147483647LL, "triattn_flash: grid overflow");
-    triattn_flash_cta2_kernel<<<(unsigned)(nseq * nkt), 128, smem_a, s>>>(mq, mk, mv, mask, g, og, N);
-    PRD_LAUNCHED();
-    return 0;
-  }
-  PRD_REQUIRE(smem <= 227 * 1024, "triattn_flash: N=%d needs %d B of shared memory", N, smem);
-  PRD_REQUIRE(nseq * npair <= 2147483647LL, "triattn_flash: grid overflow");
-  dim3 grid((unsigned)(nseq * npair));
-  triattn_flash_kernel<<<grid, kFlashThreads, smem, s>>>(mq, mk, mv, mask, g, og, N);
+  PRD_REQUIRE(nseq * nkt <= 2147483647LL, "triattn_flash: grid overflow");
+  triattn_flash_kernel<<<(unsigned)(nseq * nkt), 128, smem, s>>>(mq, mk, mv, mask, g, og, N);
   PRD_LAUNCHED();
   return 0;
 }
