@@ -61,8 +61,8 @@ pair_bias_kernel(const float* __restrict__ pair, long long R, long long NN, cons
   constexpr int kRowBytes = CZ * 4 + 16;    // padded: same-column reads of 32 lanes hit distinct banks
   constexpr int kStageBytes = ROWS * kRowBytes;
   extern __shared__ __align__(128) uint8_t smem_pb[];
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem_pb + STAGES * kStageBytes);
-  float* sW = reinterpret_cast<float*>(full + STAGES);  // [4][CZ] folded weights, [4] folded bias
+  float* sW = reinterpret_cast<float*>(smem_pb + STAGES * kStageBytes);  // [4][CZ] folded weights, [4] folded bias (16-byte aligned)
+  uint64_t* full = reinterpret_cast<uint64_t*>(sW + 4 * CZ + 4);
   const int t = threadIdx.x;
   // fold the affine LayerNorm into the projection:  (y*g + b) . w_h = y . (g*w_h) + b . w_h
   for (int i = t; i < 4 * CZ; i += 256) sW[i] = w[i] * (ln_w ? ln_w[i % CZ] : 1.0f);

@@ -141,13 +141,20 @@ triattn_flash_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
       float mx = mrow[h];
       if (all_valid) {
         float rm[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};  // independent chains (ILP)
-#pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
-          uint32_t sv[32];
-          tmem_ld32(tm_lane + c * 32, sv);
-          tmem_ld_wait();
+        // 16-column chunks, double buffered: the TMEM load of chunk c+1 is in flight while chunk c is reduced
+        uint32_t sa[16], sb[16];
+        tmem_ld16(tm_lane, sa);
+        tmem_ld_wait16(sa);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) rm[j & 3] = fmaxf(rm[j & 3], __uint_as_float(sv[j]));
+        for (int c = 0; c < 8; c += 2) {
+          tmem_ld16(tm_lane + (c + 1) * 16, sb);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) rm[j & 3] = fmaxf(rm[j & 3], __uint_as_float(sa[j]));
+          tmem_ld_wait16(sb);
+          if (c + 2 < 8) tmem_ld16(tm_lane + (c + 2) * 16, sa);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) rm[j & 3] = fmaxf(rm[j & 3], __uint_as_float(sb[j]));
+          if (c + 2 < 8) tmem_ld_wait16(sa);
         }
         mx = fmaxf(mx, fmaxf(fmaxf(rm[0], rm[1]), fmaxf(rm[2], rm[3])) * kLog2e);
       } else {
@@ -172,18 +179,33 @@ triattn_flash_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
       if (all_valid) {
         const float nmx = -mx;
         float r4[4] = {0.f, 0.f, 0.f, 0.f};  // independent chains (ILP)
-#pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
-          uint32_t sv[32];
-          tmem_ld32(tm_lane + c * 32, sv);
-          tmem_ld_wait();
-          float p[32];
+        uint32_t sa[16], sb[16];
+        tmem_ld16(tm_lane, sa);
+        tmem_ld_wait16(sa);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            p[j] = ex2_approx(fmaf(__uint_as_float(sv[j]), kLog2e, nmx));
-            r4[j & 3] += p[j];
+        for (int c = 0; c < 8; c += 2) {
+          tmem_ld16(tm_lane + (c + 1) * 16, sb);
+          {
+            float p[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              p[j] = ex2_approx(fmaf(__uint_as_float(sa[j]), kLog2e, nmx));
+              r4[j & 3] += p[j];
+            }
+            store_a_cols16(sP, t, c * 16, p);
           }
-          store_a_cols32(sP, t, c * 32, p);
+          tmem_ld_wait16(sb);
+          if (c + 2 < 8) tmem_ld16(tm_lane + (c + 2) * 16, sa);
+          {
+            float p[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              p[j] = ex2_approx(fmaf(__uint_as_float(sb[j]), kLog2e, nmx));
+              r4[j & 3] += p[j];
+            }
+            store_a_cols16(sP, t, (c + 1) * 16, p);
+          }
+          if (c + 2 < 8) tmem_ld_wait16(sa);
         }
         rs = (r4[0] + r4[1]) + (r4[2] + r4[3]);
       } else {
