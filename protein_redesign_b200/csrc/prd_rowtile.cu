@@ -551,7 +551,7 @@ int trimul_out(const PairDims& d, const float* pair, float* dst, int residual, c
 // Triangle attention projections.  Logical row (b, seq, tok): "starting" reads pair[b,seq,tok],
 // "ending" reads pair[b,tok,seq].  w: fp16 pair [hi; lo], each [256 x CZ] with rows [0,64) q,
 // [64,128) k, [128,192) v, [192,256) gate.
-// Outputs (fp16): q (pre-scaled by 1/sqrt(c) = 0.25), k, g = sigmoid(gate) as [rows][64];
+// Outputs (fp16): q (pre-scaled by log2(e)/sqrt(c): the flash kernel works in the exp2 domain), k, g = sigmoid(gate) as [rows][64];
 // v transposed per sequence: vt[(b*N+seq)][h*16+c][tok] (tok contiguous, row stride plane_ld(N)),
 // i.e. the K-major B operand of the P.V product.  Two compute groups.
 // =========================================================================================
@@ -653,7 +653,7 @@ triattn_proj_kernel(const float* __restrict__ pair, RowMap map, long long R, con
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
           float a = __uint_as_float(acc[j]);
-          if (part == 0) a *= 0.25f;
+          if (part == 0) a *= 0.25f * 1.4426950408889634f;
           if (part == 3) a = sigmoidf_fast(a + sB[col0 + j]);
           v[j] = a;
         }

@@ -2,293 +2,635 @@
 // modules.py:236-243): flash-style gated attention, 4 heads x 16 channels, key mask with the
 // reference's finite fill value (-2^15), online softmax, S = QK^T and O = PV on tcgen05.
 //
-// One CTA = one (sequence, 128-query tile).  Thread t owns query row t (TMEM lane t):
-//   S_h  = Q_h K_h^T   one UMMA, M=128 N=128 K=16 (head h = 32-byte K-slice of the 128-byte rows)
-//   P_h  = exp2(S_h - m)  -> fp16 A operand in shared memory (SWIZZLE_128B, 2 K-blocks)
-//   O_h += P_h V_h     8 UMMAs, M=128 N=16 K=16, B = V^T tile [16 x 128 keys] (K-major)
-// Running max / sum / output (4 x 16 fp32) stay in registers; the per-key-tile partial product is
-// read back from TMEM and rescaled there, so no TMEM "correction" pass is needed.
+// Persistent kernel, one CTA per SM, 12 warps:
+//   warps 0-3 / 4-7   softmax groups A / B: each group owns one work unit (sequence, 128-query tile) at a
+//                     time; thread t of a group owns query row t (= TMEM lane t)
+//   warps 8 / 9       UMMA issue for group A / B        warps 10 / 11   TMA loads for group A / B
+// The exp2 (MUFU) pipe is the binding unit of this kernel (16 exp2/clk/SM against 128 scores per row per
+// item).  The two groups hand a per-scheduler token back and forth (mbarriers tok[g][w]) so that on every
+// SM sub-partition exactly one warp is in its exp2 pass while its partner does everything else (row max,
+// O read-back, epilogue, waiting for UMMAs): without the token the two drift into lock step, share the
+// pipe during the exp2 pass and leave it idle during the rest (measured: 55 % MUFU utilisation).
 //
-// Inputs come from triattn_proj (prd_rowtile.cu): q (x 1/sqrt(c)), k, g=sigmoid(gate) as
+// An "item" is (key tile kt, head h), G = global item counter of the group across its units:
+//   S_G   = Q_h K_h^T        one UMMA, M=128 N=128 K=16 -> TMEM buffer G&1 (two 128-column buffers / group)
+//   pass A  row max of S_G (FMNMX3), exp2 domain: q is pre-scaled by log2(e)/sqrt(c) in triattn_proj
+//   pass B  P = exp2(S_G - m) (FADD2, MUFU, packed row sum) -> fp16 A operand in shared memory
+//           (SWIZZLE_128B, 2 K-blocks of 64 keys)
+//   O_G   = P V_h            2 x 4 UMMAs, M=128 N=16 K=16, issued per 64-key half as soon as it is
+//                            written; the product lands in columns [0,16) of S_G's own (now consumed)
+//                            TMEM buffer, is read back by the threads during item G+1 and
+//                            rescaled/accumulated in registers (4 x 16 fp32 per row).
+// S_{G+1} is issued into the other buffer as soon as every thread has read O_{G-1} out of it, i.e. one
+// full exp2 pass before it is needed: UMMA latency is off the critical path.  Threads synchronise only
+// through mbarriers (P half ready, P.V done, O read, token), never with a CTA-wide barrier.  The TMA warp
+// runs ahead across unit boundaries (next unit's Q / K / V are loaded while the current one finishes).
+//
+// Inputs come from triattn_proj (prd_rowtile.cu): q (x log2(e)/sqrt(c)), k, g=sigmoid(gate) as
 // [B*N seq][N tok][64] fp16 and vt [B*N seq][64][plane_ld(N)] fp16.
 // Output og [B*N*N][64] fp16 = g * softmax(..) v, consumed by triattn_out.
 #include "prd_kernels.h"
 #include "prd_rowtile.cuh"
+#include <stdlib.h>
+
+#include <algorithm>
 
 namespace prd {
 
+constexpr int kFlashThreads = 384;
+constexpr bool kFlashPolyHalf = true;  // every other column pair: exp2 on the FMA pipe (exp2_poly2)
+constexpr bool kFlashToken = false;  // strict per-scheduler MUFU ping-pong between the two groups; measured slower (2.32 vs 1.78 ms):
+                                     // a lone warp in its exp2 pass is latency bound, two overlapping passes fill each other's bubbles
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kMaskFillLog2 = -32768.0f * kLog2e;  // modules.py:177,220 in the exp2 domain
 
+// ---- packed fp32x2 / 3-input max helpers (sm_100: FADD2, FMNMX3) ----
+__device__ __forceinline__ uint64_t pack_f2(float a, float b) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void unpack_f2(uint64_t v, float& a, float& b) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+}
+__device__ __forceinline__ uint64_t fadd2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ uint64_t fsub2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+// exp2 of two non-positive arguments on the FMA pipe (no MUFU): Cody-Waite split x = n + f, |f| <= 1/2,
+// degree-3 minimax polynomial for 2^f (max relative error 7.5e-5, well below the fp16 rounding of P that
+// follows), n added into the exponent field.  Arguments are clamped at -24 (2^-24 is below fp16 range).
+// Half of the exponentials of the all-valid path go through here: the MUFU pipe (16 exp2/clk/SM) is the
+// binding unit of this kernel, the FMA pipe has room.
+__device__ __forceinline__ uint64_t exp2_poly2(uint64_t x) {
+  float a, b;
+  unpack_f2(x, a, b);
+  a = fmaxf(a, -24.f);
+  b = fmaxf(b, -24.f);
+  x = pack_f2(a, b);
+  const uint64_t magic = pack_f2(12582912.f, 12582912.f);  // 1.5 * 2^23: the sum's low mantissa bits = round(x)
+  const uint64_t t = fadd2(x, magic);
+  const uint64_t f = fsub2(x, fsub2(t, magic));
+  uint64_t p = pack_f2(5.516747385e-02f, 5.516747385e-02f);
+  p = ffma2(p, f, pack_f2(2.426107377e-01f, 2.426107377e-01f));
+  p = ffma2(p, f, pack_f2(6.932617426e-01f, 6.932617426e-01f));
+  p = ffma2(p, f, pack_f2(9.999281168e-01f, 9.999281168e-01f));
+  float ta, tb, pa, pb;
+  unpack_f2(t, ta, tb);
+  unpack_f2(p, pa, pb);
+  pa = __int_as_float(__float_as_int(pa) + (__float_as_int(ta) << 23));
+  pb = __int_as_float(__float_as_int(pb) + (__float_as_int(tb) << 23));
+  return pack_f2(pa, pb);
+}
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
+__device__ __forceinline__ uint32_t cvt_f16x2(float lo, float hi) {
+  uint32_t y;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(y) : "f"(hi), "f"(lo));
+  return y;
+}
+// One elected lane of a fully converged warp (warp-uniform control flow around it keeps UMMA / TMA operands
+// in uniform registers; an `if (lane == 0)` branch costs ~15 instructions per tcgen05.mma instead).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ void tmem_ld_wait32(uint32_t (&r)[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                 "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]),
+                 "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]),
+                 "+r"(r[23]), "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]),
+                 "+r"(r[30]), "+r"(r[31])
+               :
+               : "memory");
+}
+
 // Per-key softmax terms in the exp2 domain: t_j = s_j * mul_j + add_j
-//   valid key   : mul = log2(e), add = 0
-//   masked key  : mul = 0,       add = -2^15 * log2(e)   (the reference's finite fill value)
-//   j >= N (pad): mul = 0,       add = -inf               (does not exist: p = 0)
+//   valid key   : mul = 1, add = 0
+//   masked key  : mul = 0, add = -2^15 * log2(e)   (the reference's finite fill value)
+//   j >= N (pad): mul = 0, add = -inf               (does not exist: p = 0)
 // A key tile whose 128 keys are all valid takes a fast path without any per-key loads.
+
+// kTrace: debug instantiation that records clock64() at phase boundaries (PRD_FLASH_TRACE=<file>,
+// tools/flash_trace.py).
+constexpr int kTraceCtas = 8, kTraceEvents = 512;
+#define FLASH_TRACE(ev)                                                                  \
+  do {                                                                                   \
+    if (kTrace && tr != nullptr && (threadIdx.x & 31) == 0 && tr_n < kTraceEvents) {     \
+      tr[tr_n++] = (clock64() << 8) | (ev);                                              \
+    }                                                                                    \
+  } while (0)
+
+// pass A: running row max over one 128-key S tile.
+template <bool kAllValid>
+__device__ __forceinline__ float flash_row_max(uint32_t tS, const float2* keyp, float mx) {
+  if (kAllValid) {
+    float rm[4] = {mx, -INFINITY, -INFINITY, -INFINITY};  // independent chains (ILP)
+    uint32_t sa[32], sb[32];
+    // tcgen05.wait::ld waits for ALL outstanding loads, so the next chunk's load is issued right after
+    // the wait and is in flight while the current chunk is reduced
+    tmem_ld32(tS, sa);
+    tmem_ld_wait32(sa);
+    tmem_ld32(tS + 32, sb);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) rm[j & 3] = fmax3(rm[j & 3], __uint_as_float(sa[2 * j]), __uint_as_float(sa[2 * j + 1]));
+    tmem_ld_wait32(sb);
+    tmem_ld32(tS + 64, sa);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) rm[j & 3] = fmax3(rm[j & 3], __uint_as_float(sb[2 * j]), __uint_as_float(sb[2 * j + 1]));
+    tmem_ld_wait32(sa);
+    tmem_ld32(tS + 96, sb);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) rm[j & 3] = fmax3(rm[j & 3], __uint_as_float(sa[2 * j]), __uint_as_float(sa[2 * j + 1]));
+    tmem_ld_wait32(sb);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) rm[j & 3] = fmax3(rm[j & 3], __uint_as_float(sb[2 * j]), __uint_as_float(sb[2 * j + 1]));
+    return fmaxf(fmaxf(rm[0], rm[1]), fmaxf(rm[2], rm[3]));
+  } else {
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c) {
+      uint32_t sv[32];
+      tmem_ld32(tS + c * 32, sv);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const float2 e = keyp[c * 32 + j];
+        mx = fmaxf(mx, fmaf(__uint_as_float(sv[j]), e.x, e.y));
+      }
+    }
+    return mx;
+  }
+}
+
+// volatile flavours: keep the hand-written software pipeline below in program order up to ptxas
+__device__ __forceinline__ uint64_t fadd2v(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm volatile("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ float ex2v(float x) {
+  float y;
+  asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// in-place flavours ("+" ties input and output to the same register: no temporaries for ptxas to funnel
+// every MUFU operand through, which serialises the stream on write-after-read scoreboards)
+__device__ __forceinline__ void fadd2_ip(uint64_t& x, uint64_t b) { asm volatile("add.rn.f32x2 %0, %0, %1;" : "+l"(x) : "l"(b)); }
+__device__ __forceinline__ void ex2_ip(float& x) { asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(x)); }
+__device__ __forceinline__ uint32_t cvt_f16x2v(float lo, float hi) {
+  uint32_t y;
+  asm volatile("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(y) : "f"(hi), "f"(lo));
+  return y;
+}
+__device__ __forceinline__ void sts128v(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
+// pass B: P = exp2(t - m) as the fp16 A operand, row sum returned.  Each 64-key half is announced on
+// bar_pr[half] (count 128) as soon as this thread has written it.
+// The caller has already issued the TMEM load of the first 16 columns into b0 (before waiting for its
+// turn on the MUFU pipe).
 //
-// One softmax group (128 threads) per CTA, two CTAs per SM: the two CTAs drift apart, so one is in
-// its exp2 loop while the other waits for an S tile.  (A warp-specialised single-CTA variant with two
-// softmax groups sharing K/V, a TMA warp and a UMMA warp was measured 20 % slower -- the groups ran in
-// lockstep -- see profiles/r01_flash_variants.md.)
-__global__ void __launch_bounds__(128, 2)
+// All-valid path: one flat software pipeline over the 64 column pairs of the item, in 8 chunks of 16
+// columns held in three rotating 16-register buffers:
+//   stage L  tcgen05.ld of chunk c+2            (in flight during chunk c)
+//   stage A  x = s - m (FADD2) of chunk c+1     (interleaved with the MUFUs of chunk c)
+//   stage M  p = exp2(x) (2 MUFU per pair) of chunk c
+//   stage C  row sum (FADD2), fp16 pack (F2FP), 16-byte store of chunk c, 3 pairs behind stage M
+// so the MUFU stream never drains at a chunk boundary and every MUFU operand has its own register.
+template <bool kAllValid, bool kTrace>
+__device__ __forceinline__ float flash_row_exp(uint32_t tS, const float2* keyp, float mx, uint8_t* sP, int t,
+                                               uint64_t* bar_pr, uint32_t (&b0)[16], long long* tr, int& tr_n) {
+  if (kAllValid) {
+    const uint64_t nm2 = pack_f2(-mx, -mx);
+    uint64_t racc[4] = {0ull, 0ull, 0ull, 0ull};
+    const uint32_t sP_row = smem_u32(sP) + t * 128;
+    uint32_t b1[16], b2[16];
+    uint64_t x[3][8];
+    uint32_t ph[2][8];
+    constexpr int kLag = 3;
+    auto pack_chunk = [&](int bi, const uint32_t(&s)[16]) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) x[bi][j] = pack_f2(__uint_as_float(s[2 * j]), __uint_as_float(s[2 * j + 1]));
+    };
+    auto consume = [&](int c, int i) {  // stage C of pair i of chunk c
+      float a, b;
+      unpack_f2(x[c % 3][i], a, b);
+      racc[i & 3] = fadd2v(racc[i & 3], x[c % 3][i]);
+      ph[c & 1][i] = cvt_f16x2v(a, b);
+      if ((i & 3) == 3) {
+        const int k0 = c * 16;
+        sts128v(sP_row + (k0 >> 6) * (kTileRows * 128) + (((((k0 & 63) >> 3) + (i >> 2)) ^ (t & 7)) << 4), ph[c & 1][i - 3],
+                ph[c & 1][i - 2], ph[c & 1][i - 1], ph[c & 1][i]);
+        if ((c == 3 || c == 7) && i == 7) {
+          tc_fence_before();  // all TMEM reads of this half of the S buffer are done (P.V overwrites columns 0-15)
+          fence_proxy_async_smem();
+          mbar_arrive(&bar_pr[c >> 2]);
+        }
+      }
+    };
+    tmem_ld_wait16(b0);
+    tmem_ld16(tS + 16, b1);
+    pack_chunk(0, b0);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) x[0][j] = fadd2v(x[0][j], nm2);
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      // chunk c+1 has landed; start the load of chunk c+2 (its buffer held chunk c-1, whose last kLag pairs are
+      // consumed just below: the register dependency orders the load behind them)
+      if (c + 1 < 8) {
+        if (c % 3 == 0) tmem_ld_wait16(b1);
+        if (c % 3 == 1) tmem_ld_wait16(b2);
+        if (c % 3 == 2) tmem_ld_wait16(b0);
+        if (c % 3 == 0) pack_chunk(1, b1);
+        if (c % 3 == 1) pack_chunk(2, b2);
+        if (c % 3 == 2) pack_chunk(0, b0);
+      }
+      FLASH_TRACE(40 + c);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (kFlashPolyHalf && (j & 1)) {
+          if (c + 1 < 8) x[(c + 1) % 3][j] = fadd2v(x[(c + 1) % 3][j], nm2);
+          x[c % 3][j] = exp2_poly2(x[c % 3][j]);
+        } else {
+          float a, b;
+          unpack_f2(x[c % 3][j], a, b);
+          a = ex2v(a);
+          if (c + 1 < 8) x[(c + 1) % 3][j] = fadd2v(x[(c + 1) % 3][j], nm2);
+          b = ex2v(b);
+          x[c % 3][j] = pack_f2(a, b);
+        }
+        if (j >= kLag) consume(c, j - kLag);
+        else if (c > 0) consume(c - 1, j + 8 - kLag);
+        if (j == kLag - 1 && c + 2 < 8) {
+          if (c % 3 == 0) tmem_ld16(tS + (c + 2) * 16, b2);
+          if (c % 3 == 1) tmem_ld16(tS + (c + 2) * 16, b0);
+          if (c % 3 == 2) tmem_ld16(tS + (c + 2) * 16, b1);
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 8 - kLag; i < 8; ++i) consume(7, i);
+    float r0, r1, r2, r3;
+    unpack_f2(fadd2(racc[0], racc[1]), r0, r1);
+    unpack_f2(fadd2(racc[2], racc[3]), r2, r3);
+    return (r0 + r1) + (r2 + r3);
+  } else {
+    float rs = 0.f;
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c) {
+      uint32_t sv[32];
+      tmem_ld32(tS + c * 32, sv);
+      tmem_ld_wait();
+      float p[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const float2 e = keyp[c * 32 + j];
+        p[j] = ex2_approx(fmaf(__uint_as_float(sv[j]), e.x, e.y) - mx);
+        rs += p[j];
+      }
+      store_a_cols32(sP, t, c * 32, p);
+      if (c & 1) {
+        tc_fence_before();
+        fence_proxy_async_smem();
+        mbar_arrive(&bar_pr[c >> 1]);
+      }
+    }
+    return rs;
+  }
+}
+
+constexpr int kFlashGroupFixed = 16384 + 32768 + 16384 + 32768;  // Q, 2 K, V^T, P
+
+template <bool kTrace>
+__global__ void __launch_bounds__(kFlashThreads, 1)
 triattn_flash_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
                      const __grid_constant__ CUtensorMap map_vt, const float* __restrict__ mask,
-                     const __half* __restrict__ g, __half* __restrict__ og, int N) {
-  extern __shared__ uint8_t raw[];
-  uint8_t* sm = smem_align1024(raw);
-  uint8_t* sQ = sm;                 // [128 x 64] halves, 16 KB
-  uint8_t* sK = sQ + 16384;         // 2 buffers of [128 keys x 64], 16 KB each (next tile prefetched)
-  uint8_t* sVt = sK + 32768;        // 2 boxes of [64 rows x 64 keys], 8 KB each
-  uint8_t* sP = sVt + 16384;        // 2 K-blocks of [128 x 64 keys], 32 KB
-  const int nkt = (N + 127) / 128;
-  float2* sKey = reinterpret_cast<float2*>(sP + 32768);  // (mul, add) per key, nkt * 128 entries
-  int* sAllValid = reinterpret_cast<int*>(sKey + nkt * 128);  // per key tile
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sAllValid + ((nkt + 1) & ~1));
-  uint64_t* bar_q = bars;
-  uint64_t* bar_k = bars + 1;  // [2]
-  uint64_t* bar_v = bars + 3;
-  uint64_t* bar_s = bars + 4;
-  uint64_t* bar_o = bars + 5;
-  uint64_t* bar_p = bars + 6;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 7);
+                     const __half* __restrict__ g_gate, __half* __restrict__ og, int N, int total_units,
+                     long long* trace) {
+  long long* tr = nullptr;
+  int tr_n = 0;
+  if (kTrace && blockIdx.x < kTraceCtas) tr = trace + ((long long)blockIdx.x * 12 + (threadIdx.x >> 5)) * kTraceEvents;
 
-  const int t = threadIdx.x, warp = t >> 5;
-  const int qt = blockIdx.x % nkt;   // the q-tiles of one sequence are adjacent CTAs: K/V stay in L2
-  const int seq = blockIdx.x / nkt;  // b * N + s
-  const int b = seq / N;
-  if (t == 0) {
-    mbar_init(bar_q, 1);
-    mbar_init(&bar_k[0], 1);
-    mbar_init(&bar_k[1], 1);
-    mbar_init(bar_v, 1);
-    mbar_init(bar_s, 1);
-    mbar_init(bar_o, 1);
-    mbar_init(bar_p, 1);
+  extern __shared__ uint8_t raw[];
+  const int nkt = (N + 127) / 128;
+  const int n_items = nkt * 4;
+  const int group_bytes = (kFlashGroupFixed + nkt * 1024 + 64 + 1023) & ~1023;
+  uint8_t* sm = smem_align1024(raw);
+  uint64_t* bars_all = reinterpret_cast<uint64_t*>(sm + 2 * group_bytes);
+  uint64_t* tok = bars_all + 32;  // [2 groups][4 warps]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tok + 8);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int grp = warp < 8 ? (warp >> 2) : (warp & 1);  // softmax warps 0-3 / 4-7, control warps 8,10 / 9,11
+  uint8_t* gsm = sm + grp * group_bytes;
+  uint8_t* sQ = gsm;                  // [128 x 64] halves, 16 KB
+  uint8_t* sK = sQ + 16384;           // 2 buffers of [128 keys x 64], 16 KB each
+  uint8_t* sVt = sK + 32768;          // 2 K-blocks (64 keys each) of [64 (h,c) rows x 64 keys], 8 KB each
+  uint8_t* sP = sVt + 16384;          // 2 K-blocks of [128 x 64 keys], 32 KB
+  float2* sKey = reinterpret_cast<float2*>(sP + 32768);    // (mul, add) per key, nkt * 128 entries
+  int* sWarpValid = reinterpret_cast<int*>(sKey + nkt * 128);  // [nkt][4]: the warp's 32 keys of the tile are all valid
+  uint64_t* bars = bars_all + grp * 16;
+  uint64_t* bar_q = bars;        // Q tile loaded
+  uint64_t* bar_k = bars + 1;    // [2] K tile loaded
+  uint64_t* bar_v = bars + 3;    // [4] V^T slice of head h loaded
+  uint64_t* bar_s = bars + 7;    // [2] S tile complete in TMEM buffer
+  uint64_t* bar_pr = bars + 9;   // [2] P half written by all 128 threads
+  uint64_t* bar_pv = bars + 11;  // P.V of the item complete (P and V_h free, O partial readable)
+  uint64_t* bar_or = bars + 12;  // all 128 threads have read the previous item's O partial
+
+  if (threadIdx.x == 0) {
+    for (int gg = 0; gg < 2; ++gg) {
+      uint64_t* b = bars_all + gg * 16;
+      for (int i = 0; i < 9; ++i) mbar_init(&b[i], 1);  // q, k[2], v[4], s[2]
+      mbar_init(&b[9], 128);
+      mbar_init(&b[10], 128);
+      mbar_init(&b[11], 1);
+      mbar_init(&b[12], 128);
+    }
+    for (int i = 0; i < 8; ++i) mbar_init(&tok[i], 1);
     fence_barrier_init();
+    for (int w = 0; w < 4; ++w) mbar_arrive(&tok[w]);  // group A goes first
     tma_prefetch_desc(&map_q);
     tma_prefetch_desc(&map_k);
     tma_prefetch_desc(&map_vt);
-    mbar_expect_tx(bar_q, 16384);
-    tma_load_3d(sQ, &map_q, bar_q, 0, qt * 128, seq);
-    mbar_expect_tx(&bar_k[0], 16384);
-    tma_load_3d(sK, &map_k, &bar_k[0], 0, 0, seq);
   }
-  if (warp == 0) tmem_alloc(tmem_slot, 256);
-  {
-    // key mask = m[b,seq_pos] * m[b,key]  (mask_2d row / column; symmetric, one formula for both modes)
-    const float ms = mask[seq];
-    for (int j = t; j < nkt * 128; j += 128) {
-      float2 e;
-      if (j >= N) e = make_float2(0.f, -INFINITY);
-      else if (ms * mask[(long long)b * N + j] < 0.5f) e = make_float2(0.f, kMaskFillLog2);
-      else e = make_float2(kLog2e, 0.f);
-      sKey[j] = e;
-    }
-  }
-  __syncthreads();
-  if (t < nkt) {
-    int all = 1;
-    for (int j = 0; j < 128; ++j) all &= (sKey[t * 128 + j].x != 0.f) ? 1 : 0;
-    sAllValid[t] = all;
-  }
+  if (warp == 0) tmem_alloc(tmem_slot, 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem = *tmem_slot;
-  const uint32_t tm_lane = tmem + (static_cast<uint32_t>(warp * 32) << 16);
-  const uint32_t tm_o = 128;  // column offset of the four 16-column O chunks
+  const uint32_t tmem = *tmem_slot + grp * 256;
 
-  float o[4][16];
-  float mrow[4], lrow[4];
-#pragma unroll
-  for (int h = 0; h < 4; ++h) {
-    mrow[h] = -INFINITY;
-    lrow[h] = 0.f;
-#pragma unroll
-    for (int c = 0; c < 16; ++c) o[h][c] = 0.f;
-  }
-  uint32_t ph_s = 0, n_p = 0;
-  const uint64_t dq = umma_desc_sw128(smem_u32(sQ));
+  // work units: unit u = (sequence u / nkt, query tile u % nkt); CTA c takes unit pairs c, c + grid, ...;
+  // group g takes unit 2 * pair + g.  The q-tiles of one sequence are processed close together in time
+  // (K / V stay in L2).
+  const int npairs = (total_units + 1) >> 1;
+  const int rounds = ((int)blockIdx.x < npairs) ? (npairs - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+  auto unit_of = [&](int r) { return 2 * ((int)blockIdx.x + r * (int)gridDim.x) + grp; };
+  const int nu = (rounds > 0 && unit_of(rounds - 1) >= total_units) ? rounds - 1 : rounds;  // this group's units
+  const int total_items = nu * n_items;
+  FLASH_TRACE(1);
 
-  for (int kt = 0; kt < nkt; ++kt) {
-    uint8_t* sKc = sK + (kt & 1) * 16384;
-    if (t == 0) {
-      // V^T of this tile (its buffer was released by the end-of-tile barrier) and K of the next tile
-      mbar_expect_tx(bar_v, 16384);
-      tma_load_3d(sVt, &map_vt, bar_v, kt * 128, 0, seq);
-      tma_load_3d(sVt + 8192, &map_vt, bar_v, kt * 128 + 64, 0, seq);
-      if (kt + 1 < nkt) {
-        mbar_expect_tx(&bar_k[(kt + 1) & 1], 16384);
-        tma_load_3d(sK + ((kt + 1) & 1) * 16384, &map_k, &bar_k[(kt + 1) & 1], 0, (kt + 1) * 128, seq);
+  if (warp >= 10) {
+    // ------------------------------------------------------------------ TMA warp of group grp
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
+    if (nu > 0) {
+      auto load_q = [&](int r) {
+        if (r >= nu) return;
+        const int u = unit_of(r);
+        mbar_expect_tx(bar_q, 16384);
+        tma_load_3d(sQ, &map_q, bar_q, 0, (u % nkt) * 128, u / nkt);
+      };
+      auto load_k = [&](int gk) {  // gk = r * nkt + kt
+        const int r = gk / nkt;
+        if (r >= nu) return;
+        const int u = unit_of(r);
+        uint64_t* bar = &bar_k[gk & 1];
+        mbar_expect_tx(bar, 16384);
+        tma_load_3d(sK + (gk & 1) * 16384, &map_k, bar, 0, (gk - r * nkt) * 128, u / nkt);
+      };
+      auto load_v = [&](int gk, int h) {
+        const int r = gk / nkt;
+        if (r >= nu) return;
+        const int u = unit_of(r);
+        const int key0 = (gk - r * nkt) * 128;
+        mbar_expect_tx(&bar_v[h], 4096);
+        tma_load_3d(sVt + h * 2048, &map_vt, &bar_v[h], key0, h * 16, u / nkt);
+        tma_load_3d(sVt + 8192 + h * 2048, &map_vt, &bar_v[h], key0 + 64, h * 16, u / nkt);
+      };
+      if (elect_one()) {
+        load_q(0);
+        load_k(0);
+        load_k(1);
+        for (int h = 0; h < 4; ++h) load_v(0, h);
       }
-      if (kt == 0) {
-        mbar_wait(bar_q, 0);
-        mbar_wait(&bar_k[0], 0);
-        tc_fence_after();
-        umma_f16(tmem, dq, umma_desc_sw128(smem_u32(sKc)), umma_idesc_f16(128, 128), 0u);  // S for head 0
-        umma_commit(bar_s);
+      int r = 0, it = 0;
+      for (int G = 0; G < total_items; ++G) {
+        const int h = it & 3, gk = r * nkt + (it >> 2);
+        // P.V_G complete (and with it every UMMA issued before: S_G, S_{G+1}): V slice h, after the last head
+        // the K buffer, and after the unit's last S the Q tile may be overwritten
+        mbar_wait(bar_pv, G & 1);
+        if (elect_one()) {
+          load_v(gk + 1, h);
+          if (h == 3) load_k(gk + 2);
+          if (it == n_items - 2) load_q(r + 1);
+        }
+        __syncwarp();
+        if (++it == n_items) {
+          it = 0;
+          ++r;
+        }
       }
     }
-    float alpha[4];
-    const bool all_valid = sAllValid[kt] != 0;
-    const float2* keyp = sKey + kt * 128;
-#pragma unroll
-    for (int h = 0; h < 4; ++h) {
-      mbar_wait(bar_s, ph_s);
-      ph_s ^= 1;
+  } else if (warp >= 8) {
+    // ------------------------------------------------------------------ UMMA warp of group grp
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
+    if (nu > 0) {
+      const uint64_t dq = umma_desc_sw128(smem_u32(sQ));
+      const uint64_t dk0 = umma_desc_sw128(smem_u32(sK));
+      const uint64_t dp0 = umma_desc_sw128(smem_u32(sP)), dp1 = umma_desc_sw128(smem_u32(sP) + 16384);
+      const uint64_t dv0 = umma_desc_sw128(smem_u32(sVt)), dv1 = umma_desc_sw128(smem_u32(sVt) + 8192);
+      const uint32_t idesc_s = umma_idesc_f16(128, 128), idesc_o = umma_idesc_f16(128, 16);
+      mbar_wait(bar_q, 0);
+      mbar_wait(&bar_k[0], 0);
       tc_fence_after();
-      // pass A: row max over this key tile (exp2 domain)
-      float mx = mrow[h];
-      if (all_valid) {
-        float rm[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};  // independent chains (ILP)
-        // 16-column chunks, double buffered: the TMEM load of chunk c+1 is in flight while chunk c is reduced
-        uint32_t sa[16], sb[16];
-        tmem_ld16(tm_lane, sa);
-        tmem_ld_wait16(sa);
-#pragma unroll
-        for (int c = 0; c < 8; c += 2) {
-          tmem_ld16(tm_lane + (c + 1) * 16, sb);
-#pragma unroll
-          for (int j = 0; j < 16; ++j) rm[j & 3] = fmaxf(rm[j & 3], __uint_as_float(sa[j]));
-          tmem_ld_wait16(sb);
-          if (c + 2 < 8) tmem_ld16(tm_lane + (c + 2) * 16, sa);
-#pragma unroll
-          for (int j = 0; j < 16; ++j) rm[j & 3] = fmaxf(rm[j & 3], __uint_as_float(sb[j]));
-          if (c + 2 < 8) tmem_ld_wait16(sa);
-        }
-        mx = fmaxf(mx, fmaxf(fmaxf(rm[0], rm[1]), fmaxf(rm[2], rm[3])) * kLog2e);
-      } else {
-#pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
-          uint32_t sv[32];
-          tmem_ld32(tm_lane + c * 32, sv);
-          tmem_ld_wait();
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float2 e = keyp[c * 32 + j];
-            mx = fmaxf(mx, fmaf(__uint_as_float(sv[j]), e.x, e.y));
-          }
-        }
+      if (elect_one()) {
+        umma_f16(tmem, dq, dk0, idesc_s, 0u);
+        umma_commit(&bar_s[0]);
       }
-      alpha[h] = ex2_approx(mrow[h] - mx);
-      mrow[h] = mx;
-      // the P buffer is free once the P.V UMMAs of the previous head have completed
-      if (n_p > 0) mbar_wait(bar_p, (n_p - 1) & 1);
-      // pass B: p = exp2(t - m), row sum, fp16 P tile
-      float rs = 0.f;
-      if (all_valid) {
-        const float nmx = -mx;
-        float r4[4] = {0.f, 0.f, 0.f, 0.f};  // independent chains (ILP)
-        uint32_t sa[16], sb[16];
-        tmem_ld16(tm_lane, sa);
-        tmem_ld_wait16(sa);
-#pragma unroll
-        for (int c = 0; c < 8; c += 2) {
-          tmem_ld16(tm_lane + (c + 1) * 16, sb);
-          {
-            float p[16];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              p[j] = ex2_approx(fmaf(__uint_as_float(sa[j]), kLog2e, nmx));
-              r4[j & 3] += p[j];
-            }
-            store_a_cols16(sP, t, c * 16, p);
-          }
-          tmem_ld_wait16(sb);
-          if (c + 2 < 8) tmem_ld16(tm_lane + (c + 2) * 16, sa);
-          {
-            float p[16];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              p[j] = ex2_approx(fmaf(__uint_as_float(sb[j]), kLog2e, nmx));
-              r4[j & 3] += p[j];
-            }
-            store_a_cols16(sP, t, (c + 1) * 16, p);
-          }
-          if (c + 2 < 8) tmem_ld_wait16(sa);
+      __syncwarp();
+      int r = 0, it = 0;
+      for (int G = 0; G < total_items; ++G) {
+        const int h = it & 3, gk = r * nkt + (it >> 2);
+        int r1 = r, it1 = it + 1;
+        if (it1 == n_items) {
+          it1 = 0;
+          ++r1;
         }
-        rs = (r4[0] + r4[1]) + (r4[2] + r4[3]);
-      } else {
-#pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
-          uint32_t sv[32];
-          tmem_ld32(tm_lane + c * 32, sv);
-          tmem_ld_wait();
-          float p[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float2 e = keyp[c * 32 + j];
-            p[j] = ex2_approx(fmaf(__uint_as_float(sv[j]), e.x, e.y) - mx);
-            rs += p[j];
-          }
-          store_a_cols32(sP, t, c * 32, p);
-        }
-      }
-      lrow[h] = lrow[h] * alpha[h] + rs;
-      ++n_p;
-      sync_before_mma();  // P visible to the tensor core; every thread is done reading S
-      if (t == 0) {
-        tc_fence_after();
-        // the S tile every thread waits for next goes first: next head, or head 0 of the next key tile
-        if (h < 3) {
-          umma_f16(tmem, dq + 2 * (h + 1), umma_desc_sw128(smem_u32(sKc)) + 2 * (h + 1), umma_idesc_f16(128, 128), 0u);
-          umma_commit(bar_s);
-        } else if (kt + 1 < nkt) {
-          mbar_wait(&bar_k[(kt + 1) & 1], ((kt + 1) >> 1) & 1);
+        // every thread has read O_{G-1}: the other S buffer is free
+        mbar_wait(bar_or, G & 1);
+        FLASH_TRACE(10);
+        if (G + 1 < total_items) {
+          const int h1 = it1 & 3, gk1 = r1 * nkt + (it1 >> 2);
+          if (it1 == 0) mbar_wait(bar_q, r1 & 1);
+          if (h1 == 0) mbar_wait(&bar_k[gk1 & 1], (gk1 >> 1) & 1);
           tc_fence_after();
-          umma_f16(tmem, dq, umma_desc_sw128(smem_u32(sK + ((kt + 1) & 1) * 16384)), umma_idesc_f16(128, 128), 0u);
-          umma_commit(bar_s);
+          if (elect_one()) {
+            umma_f16(tmem + ((G + 1) & 1) * 128, dq + 2 * h1, dk0 + (gk1 & 1) * (16384 >> 4) + 2 * h1, idesc_s, 0u);
+            umma_commit(&bar_s[(G + 1) & 1]);
+          }
+          __syncwarp();
         }
-        if (h == 0) mbar_wait(bar_v, kt & 1);
-        const uint32_t idesc = umma_idesc_f16(128, 16);
-        umma_kblock(tmem + tm_o + 16 * h, smem_u32(sP), smem_u32(sVt) + h * 2048, idesc, false);
-        umma_kblock(tmem + tm_o + 16 * h, smem_u32(sP) + 16384, smem_u32(sVt) + 8192 + h * 2048, idesc, true);
-        umma_commit(bar_p);
-        if (h == 3) umma_commit(bar_o);
+        FLASH_TRACE(11);
+        mbar_wait(&bar_v[h], gk & 1);
+        const uint32_t tO = tmem + (G & 1) * 128;
+        mbar_wait(&bar_pr[0], G & 1);
+        tc_fence_after();
+        FLASH_TRACE(12);
+        if (elect_one()) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_f16(tO, dp0 + 2 * k, dv0 + h * (2048 >> 4) + 2 * k, idesc_o, k > 0 ? 1u : 0u);
+        }
+        __syncwarp();
+        mbar_wait(&bar_pr[1], G & 1);
+        tc_fence_after();
+        FLASH_TRACE(13);
+        if (elect_one()) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_f16(tO, dp1 + 2 * k, dv1 + h * (2048 >> 4) + 2 * k, idesc_o, 1u);
+          umma_commit(bar_pv);
+        }
+        __syncwarp();
+        FLASH_TRACE(14);
+        r = r1;
+        it = it1;
       }
     }
-    // the four P.V products of this key tile: read back once, rescale in registers
-    mbar_wait(bar_o, kt & 1);
-    tc_fence_after();
-#pragma unroll
-    for (int h = 0; h < 4; ++h) {
-      uint32_t ov[16];
-      tmem_ld16(tm_lane + tm_o + 16 * h, ov);
-      tmem_ld_wait();
-#pragma unroll
-      for (int c = 0; c < 16; ++c) o[h][c] = o[h][c] * alpha[h] + __uint_as_float(ov[c]);
-    }
-    // V^T / P buffers and the O columns are reused by the next key tile
-    tc_fence_before();
-    __syncthreads();
-  }
-
-  const int tok = qt * 128 + t;
-  if (tok < N) {
-    const long long r = (long long)seq * N + tok;
-    const uint4* gp = reinterpret_cast<const uint4*>(g + r * 64);
-    uint4* op = reinterpret_cast<uint4*>(og + r * 64);
-#pragma unroll
-    for (int h = 0; h < 4; ++h) {
-      const float inv = 1.0f / lrow[h];
-#pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        const uint4 gv = __ldg(gp + h * 2 + half);
-        const __half2* g2 = reinterpret_cast<const __half2*>(&gv);
-        uint4 ovv;
-        uint32_t* o32 = reinterpret_cast<uint32_t*>(&ovv);
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float2 gf = __half22float2(g2[e]);
-          o32[e] = pack_half2(o[h][half * 8 + 2 * e] * inv * gf.x, o[h][half * 8 + 2 * e + 1] * inv * gf.y);
+  } else {
+    // ------------------------------------------------------------------ softmax group grp
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
+    const int t = threadIdx.x & 127, w = warp & 3;
+    const uint32_t tm_lane = tmem + (static_cast<uint32_t>(w * 32) << 16);
+    uint64_t* tok_mine = &tok[grp * 4 + w];
+    uint64_t* tok_other = &tok[(grp ^ 1) * 4 + w];
+    int prev_seq = -1;
+    int G = 0;
+    if (nu > 0) mbar_arrive(bar_or);  // "O_{-1} has been read"
+    for (int r = 0; r < nu; ++r) {
+      const int u = unit_of(r);
+      const int seq = u / nkt, qt = u - seq * nkt;
+      const bool partner = kFlashToken && (u ^ 1) < total_units;  // the other group runs a unit in this round: take turns on the MUFU
+      if (seq != prev_seq) {
+        // key mask = m[b,seq_pos] * m[b,key]  (mask_2d row / column; symmetric, one formula for both modes).
+        // Every thread of the group is past its last read of the previous table (it has seen P.V of the last item).
+        prev_seq = seq;
+        const int b = seq / N;
+        const float ms = mask[seq];
+        for (int kt = 0; kt < nkt; ++kt) {
+          const int j = kt * 128 + t;
+          float2 e;
+          if (j >= N) e = make_float2(0.f, -INFINITY);
+          else if (ms * mask[(long long)b * N + j] < 0.5f) e = make_float2(0.f, kMaskFillLog2);
+          else e = make_float2(1.f, 0.f);
+          sKey[j] = e;
+          const bool all = __all_sync(0xffffffffu, e.x != 0.f);
+          if (lane == 0) sWarpValid[kt * 4 + w] = all ? 1 : 0;
         }
-        op[h * 2 + half] = ovv;
+        asm volatile("bar.sync %0, 128;" ::"r"(grp + 1) : "memory");
       }
+      float o[4][16];
+      float mrow[4], lrow[4], alpha[4];
+#pragma unroll
+      for (int h = 0; h < 4; ++h) {
+        mrow[h] = -INFINITY;
+        lrow[h] = 0.f;
+        alpha[h] = 0.f;
+#pragma unroll
+        for (int c = 0; c < 16; ++c) o[h][c] = 0.f;
+      }
+      for (int kt = 0; kt < nkt; ++kt) {
+        const int4 wv = *reinterpret_cast<const int4*>(sWarpValid + kt * 4);
+        const bool all_valid = (wv.x & wv.y & wv.z & wv.w) != 0;
+        const float2* keyp = sKey + kt * 128;
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+          const uint32_t tS = tm_lane + (G & 1) * 128;
+          FLASH_TRACE(20);
+          mbar_wait(&bar_s[G & 1], (G >> 1) & 1);
+          tc_fence_after();
+          FLASH_TRACE(21);
+          const float mx = all_valid ? flash_row_max<true>(tS, keyp, mrow[h]) : flash_row_max<false>(tS, keyp, mrow[h]);
+          alpha[h] = ex2_approx(mrow[h] - mx);
+          mrow[h] = mx;
+          FLASH_TRACE(22);
+          if (kt > 0 || h > 0) {
+            // O partial of the previous item: columns [0,16) of the other S buffer
+            const int hp = (h + 3) & 3;  // static after unrolling
+            mbar_wait(bar_pv, (G - 1) & 1);
+            tc_fence_after();
+            uint32_t ov[16];
+            tmem_ld16(tm_lane + ((G - 1) & 1) * 128, ov);
+            tmem_ld_wait16(ov);
+            tc_fence_before();
+            mbar_arrive(bar_or);
+#pragma unroll
+            for (int c = 0; c < 16; ++c) o[hp][c] = fmaf(o[hp][c], alpha[hp], __uint_as_float(ov[c]));
+          }
+          FLASH_TRACE(23);
+          uint32_t sa[16];
+          if (all_valid) tmem_ld16(tS, sa);  // in flight while this warp waits for its turn
+          if (partner) mbar_wait(tok_mine, G & 1);
+          FLASH_TRACE(24);
+          const float rs = all_valid ? flash_row_exp<true, kTrace>(tS, keyp, mx, sP, t, bar_pr, sa, tr, tr_n)
+                                     : flash_row_exp<false, kTrace>(tS, keyp, mx, sP, t, bar_pr, sa, tr, tr_n);
+          if (partner && lane == 0) mbar_arrive(tok_other);
+          lrow[h] = fmaf(lrow[h], alpha[h], rs);
+          FLASH_TRACE(25);
+          ++G;
+        }
+      }
+      // ---- unit epilogue: last O partial, normalise, gate, store
+      const int tok_i = qt * 128 + t;
+      const long long row = (long long)seq * N + tok_i;
+      uint4 gv[8];
+      if (tok_i < N) {
+        const uint4* gp = reinterpret_cast<const uint4*>(g_gate + row * 64);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) gv[i] = __ldg(gp + i);
+      }
+      {
+        mbar_wait(bar_pv, (G - 1) & 1);
+        tc_fence_after();
+        uint32_t ov[16];
+        tmem_ld16(tm_lane + ((G - 1) & 1) * 128, ov);
+        tmem_ld_wait16(ov);
+        tc_fence_before();
+        mbar_arrive(bar_or);  // for the first item of the next unit
+#pragma unroll
+        for (int c = 0; c < 16; ++c) o[3][c] = fmaf(o[3][c], alpha[3], __uint_as_float(ov[c]));
+      }
+      FLASH_TRACE(30);
+      if (tok_i < N) {
+        uint4* op = reinterpret_cast<uint4*>(og + row * 64);
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+          const float inv = 1.0f / lrow[h];
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            const __half2* g2 = reinterpret_cast<const __half2*>(&gv[h * 2 + half]);
+            uint4 ovv;
+            uint32_t* o32 = reinterpret_cast<uint32_t*>(&ovv);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float2 gf = __half22float2(g2[e]);
+              o32[e] = pack_half2(o[h][half * 8 + 2 * e] * inv * gf.x, o[h][half * 8 + 2 * e + 1] * inv * gf.y);
+            }
+            op[h * 2 + half] = ovv;
+          }
+        }
+      }
+      FLASH_TRACE(31);
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem, 256);
+  if (warp == 0) tmem_dealloc(*tmem_slot, 512);
 }
 
 int triattn_flash(const PairDims& d, const float* mask, const __half* q, const __half* k, const __half* g,
@@ -303,17 +645,39 @@ int triattn_flash(const PairDims& d, const float* mask, const __half* q, const _
   t.box[0] = 64; t.box[1] = 128; t.box[2] = 1; t.box[3] = 1;
   if (make_tensor_map(&mq, q, 2, 3, t, true)) return 1;
   if (make_tensor_map(&mk, k, 2, 3, t, true)) return 1;
-  // vt: [seq][64 (h,c)][tok], tok contiguous, row stride Np
+  // vt: [seq][64 (h,c)][tok], tok contiguous, row stride Np; one box = one head's 16 rows x 64 keys
   t.size[0] = (uint64_t)N; t.size[1] = 64; t.size[2] = (uint64_t)nseq;
   t.stride[0] = (uint64_t)Np * 2; t.stride[1] = (uint64_t)Np * 2 * 64;
-  t.box[0] = 64; t.box[1] = 64; t.box[2] = 1;
+  t.box[0] = 64; t.box[1] = 16; t.box[2] = 1;
   if (make_tensor_map(&mv, vt, 2, 3, t, true)) return 1;
   const int nkt = (N + 127) / 128;
-  const int smem = 1024 + 16384 * 4 + 32768 + nkt * 128 * 8 + ((nkt + 1) & ~1) * 4 + 128;
-  PRD_REQUIRE(smem <= 113 * 1024, "triattn_flash: N=%d needs %d B of shared memory", N, smem);
-  PRD_CUDA_OK(cudaFuncSetAttribute(triattn_flash_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  PRD_REQUIRE(nseq * nkt <= 2147483647LL, "triattn_flash: grid overflow");
-  triattn_flash_kernel<<<(unsigned)(nseq * nkt), 128, smem, s>>>(mq, mk, mv, mask, g, og, N);
+  const int group_bytes = (kFlashGroupFixed + nkt * 1024 + 64 + 1023) & ~1023;
+  const int smem = 1024 + 2 * group_bytes + 48 * 8 + 16;
+  PRD_REQUIRE(smem <= 227 * 1024, "triattn_flash: N=%d needs %d B of shared memory", N, smem);
+  PRD_REQUIRE(nseq * nkt <= 2147483647LL, "triattn_flash: too many work units");
+  const int total_units = (int)(nseq * nkt);
+  const int grid = std::min((total_units + 1) / 2, kNumSMs);
+  if (const char* path = getenv("PRD_FLASH_TRACE")) {
+    // debug: phase timeline of the first kTraceCtas CTAs written to `path` (tools/flash_trace.py)
+    static long long* dtrace = nullptr;
+    const size_t n = (size_t)kTraceCtas * 12 * kTraceEvents;
+    if (!dtrace) PRD_CUDA_OK(cudaMalloc(&dtrace, n * 8));
+    PRD_CUDA_OK(cudaMemsetAsync(dtrace, 0, n * 8, s));
+    PRD_CUDA_OK(cudaFuncSetAttribute(triattn_flash_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    triattn_flash_kernel<true><<<grid, kFlashThreads, smem, s>>>(mq, mk, mv, mask, g, og, N, total_units, dtrace);
+    PRD_LAUNCHED();
+    PRD_CUDA_OK(cudaStreamSynchronize(s));
+    long long* h = (long long*)malloc(n * 8);
+    PRD_CUDA_OK(cudaMemcpy(h, dtrace, n * 8, cudaMemcpyDeviceToHost));
+    if (FILE* f = fopen(path, "wb")) {
+      fwrite(h, 8, n, f);
+      fclose(f);
+    }
+    free(h);
+    return 0;
+  }
+  PRD_CUDA_OK(cudaFuncSetAttribute(triattn_flash_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  triattn_flash_kernel<false><<<grid, kFlashThreads, smem, s>>>(mq, mk, mv, mask, g, og, N, total_units, nullptr);
   PRD_LAUNCHED();
   return 0;
 }

@@ -1,0 +1,67 @@
+"""Time individual kernels at the north-star size (B=8, N=512, paper dims) without running a full bench:
+runs one triangle-attention / triangle-multiplication op to fill the workspace, then times the named
+kernels alone through prd_profile_kernel (CUDA events on the launch stream).
+Usage: python tools/kprof.py [triattn_flash trimul_gemm pair_bias ...] [--B 8] [--N 512] [--iters 10]"""
+import argparse
+import ctypes
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+from protein_redesign_b200 import _lib, ops  # noqa: E402
+from protein_redesign_b200 import synthetic as syn  # noqa: E402
+from protein_redesign_b200.model import ProteinReDiffModel  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("kernels", nargs="*", default=["triattn_flash"])
+    ap.add_argument("--B", type=int, default=8)
+    ap.add_argument("--N", type=int, default=512)
+    ap.add_argument("--iters", type=int, default=10)
+    ap.add_argument("--pad", type=int, default=0)
+    a = ap.parse_args()
+    cfg, dev = syn.PAPER, torch.device("cuda:0")
+    m = ProteinReDiffModel(cfg)
+    m.load_state_dict(syn.make_state_dict(cfg, 0), strict=True)
+    m = m.to(dev).eval()
+    g = torch.Generator().manual_seed(0)
+    pair = (torch.randn(a.B, a.N, a.N, cfg.pair_dim, generator=g) * 1.5 + 0.3).to(dev)
+    mask = torch.ones(a.B, a.N, device=dev)
+    if a.pad:
+        mask[:, a.N - a.pad:] = 0
+    blk = m.Denoiser.folding_blocks[0]
+    lib = _lib.load()
+    d = ops.make_dims(cfg, a.B, a.N)
+    ops.reserve_workspace(cfg, a.B, a.N, dev)
+    ws = _lib.Workspace.reserve(dev, max(_lib.workspace_bytes(op, d) for op in _lib.OPS))
+    stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    lib.prd_profile_kernel.restype = ctypes.c_int
+    res = {}
+    for name in a.kernels:
+        if name == "triattn_flash":
+            blk.pair_attn_starting.apply_(cfg, pair, mask)
+            aux = mask
+        elif name == "trimul_gemm":
+            blk.pair_mul_outgoing.apply_(cfg, pair, mask)
+            aux = None
+        else:
+            aux = pair
+        torch.cuda.synchronize()
+        ms = ctypes.c_float(0.0)
+        rc = lib.prd_profile_kernel(name.encode(), ctypes.byref(d), ctypes.c_void_p(ws.data_ptr()),
+                                    ctypes.c_size_t(ws.numel()), ctypes.c_void_p(aux.data_ptr() if aux is not None else 0),
+                                    a.iters, ctypes.byref(ms), stream)
+        if rc != 0:
+            raise RuntimeError(_lib.last_error())
+        res[name] = round(ms.value, 4)
+    print(json.dumps({"B": a.B, "N": a.N, "ms": res, "env": {k: v for k, v in os.environ.items() if k.startswith("PRD_")}}))
+
+
+if __name__ == "__main__":
+    main()
