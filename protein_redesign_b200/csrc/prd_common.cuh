@@ -83,6 +83,44 @@ __device__ __forceinline__ uint32_t sw128_offset(uint32_t row, uint32_t chunk) {
   return row * 128u + ((chunk ^ (row & 7u)) << 4);
 }
 
+// Coalesced store of 32 rows of 128 bytes owned one-per-lane (v[c] = 16-byte chunk c of this lane's row;
+// row i of the warp goes to gbase + i * pitch_bytes).  A direct uint4 store per lane hits 32 different
+// lines with 16 bytes each per instruction (partial sectors, 32 requests); staged through a warp-private
+// 4 KB swizzled shared-memory slice, every store instruction writes four full 128-byte lines.
+// rows_valid: rows of this warp that exist (the rest is not written).
+__device__ __forceinline__ void warp_store_rows128(uint8_t* slice, int lane, const uint4 (&v)[8], void* gbase,
+                                                   long long pitch_bytes, int rows_valid) {
+  __syncwarp();  // the slice may still be read by the previous call
+#pragma unroll
+  for (int c = 0; c < 8; ++c) *reinterpret_cast<uint4*>(slice + lane * 128 + ((c ^ (lane & 7)) << 4)) = v[c];
+  __syncwarp();
+  uint8_t* gp = reinterpret_cast<uint8_t*>(gbase) + (lane & 7) * 16;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int row = i * 4 + (lane >> 3), c = lane & 7;
+    const uint4 o = *reinterpret_cast<const uint4*>(slice + row * 128 + ((c ^ (row & 7)) << 4));
+    if (row < rows_valid) *reinterpret_cast<uint4*>(gp + row * pitch_bytes) = o;
+  }
+}
+
+// The matching load: 32 rows of 128 bytes (row i at gbase + i * pitch_bytes) arrive one-per-lane in v[],
+// fetched with fully coalesced 16-byte loads.  Rows >= rows_valid read as zero.
+__device__ __forceinline__ void warp_load_rows128(uint8_t* slice, int lane, uint4 (&v)[8], const void* gbase,
+                                                  long long pitch_bytes, int rows_valid) {
+  __syncwarp();
+  const uint8_t* gp = reinterpret_cast<const uint8_t*>(gbase) + (lane & 7) * 16;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int row = i * 4 + (lane >> 3), c = lane & 7;
+    uint4 o = make_uint4(0, 0, 0, 0);
+    if (row < rows_valid) o = __ldg(reinterpret_cast<const uint4*>(gp + row * pitch_bytes));
+    *reinterpret_cast<uint4*>(slice + row * 128 + ((c ^ (row & 7)) << 4)) = o;
+  }
+  __syncwarp();
+#pragma unroll
+  for (int c = 0; c < 8; ++c) v[c] = *reinterpret_cast<const uint4*>(slice + lane * 128 + ((c ^ (lane & 7)) << 4));
+}
+
 // ---------------------------------------------------------------------------------------
 // mbarrier
 // ---------------------------------------------------------------------------------------
@@ -198,6 +236,13 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
   return d;
 }
 
+// One elected lane of a fully converged warp (warp-uniform control flow around it keeps UMMA / TMA operands
+// in uniform registers; an `if (lane == 0)` branch costs ~15 instructions per tcgen05.mma instead).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 // Instruction descriptor, kind::f16: fp16 A/B (format 0), fp32 accumulate (c_format 1), both
 // operands K-major, M = 128.  Layout: cute::UMMA::InstrDescriptor.
 __host__ __device__ constexpr uint32_t umma_idesc_f16(uint32_t M, uint32_t N) {

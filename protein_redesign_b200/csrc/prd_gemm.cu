@@ -18,7 +18,8 @@ struct GemmSmem {
   static constexpr int kABytes = 128 * 64 * 2;
   static constexpr int kBBytes = BN * 64 * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kTotal = STAGES * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kEpiBytes = 4 * 4096;  // one 4 KB store-coalescing slice per epilogue warp
+  static constexpr int kTotal = STAGES * kStageBytes + kEpiBytes + 1024 /*align slack*/ + 256 /*barriers*/;
   static constexpr int kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;  // two accumulators
 };
 
@@ -67,7 +68,8 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   using L = GemmSmem<BN, STAGES>;
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * L::kStageBytes);
+  uint8_t* epi = smem + STAGES * L::kStageBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(epi + L::kEpiBytes);
   uint64_t* full = bars;
   uint64_t* empty = bars + STAGES;
   uint64_t* tmem_full = bars + 2 * STAGES;       // [2]
@@ -151,9 +153,13 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
       const float* addp = ep.add ? ep.add + (long long)i1 * ep.add_bs1 + (long long)i2 * ep.add_bs2 + (long long)row * ep.ldadd : nullptr;
       const bool plain = ep.bias == nullptr && ep.act == 0 && ep.rowscale == nullptr && mulp == nullptr &&
                          addp == nullptr && ep.alpha == 1.0f;
+      // warp-uniform: fp32 C whose full tile width exists and whose rows are 16-byte aligned
+      const bool coalesce = !ep.c_fp16 && (n0 + BN <= ep.N) && ((ep.ldc & 3) == 0) &&
+                            ((reinterpret_cast<uintptr_t>(reinterpret_cast<float*>(ep.C) + boff_c + n0) & 15) == 0);
 #pragma unroll 1
       for (int c = 0; c < BN / 32; ++c) {
         uint32_t r[32];
+        uint4 ov[8];
         tmem_ld32(tmem + buf * BN + (static_cast<uint32_t>(q * 32) << 16) + c * 32, r);
         tmem_ld_wait();
         const int col0 = n0 + c * 32;
@@ -194,7 +200,7 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             } else {
               for (int j = 0; j < 32 && col0 + j < ep.N; ++j) cp[j] = __float2half_rn(v[j]);
             }
-          } else {
+          } else if (!coalesce) {
             float* cp = reinterpret_cast<float*>(ep.C) + boff_c + (long long)row * ep.ldc + col0;
             if (full_chunk && ((reinterpret_cast<uintptr_t>(cp) & 15) == 0)) {
 #pragma unroll
@@ -203,6 +209,17 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
               for (int j = 0; j < 32 && col0 + j < ep.N; ++j) cp[j] = v[j];
             }
           }
+          if (coalesce) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) ov[j] = make_uint4(__float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]),
+                                                           __float_as_uint(v[4 * j + 2]), __float_as_uint(v[4 * j + 3]));
+          }
+        }
+        if (coalesce && col0 < ep.N) {
+          // fp32 output, every 32-column chunk of the tile complete and 16-byte aligned (warp-uniform): the
+          // warp's 32 rows x 128 bytes leave as full lines
+          float* cb = reinterpret_cast<float*>(ep.C) + boff_c + (long long)(m0 + q * 32) * ep.ldc + col0;
+          warp_store_rows128(epi + q * 4096, lane, ov, cb, (long long)ep.ldc * 4, ep.M - (m0 + q * 32));
         }
       }
       // this thread's TMEM reads of the accumulator are complete: hand it back to the MMA warp

@@ -178,11 +178,14 @@ outer_linear_kernel(const __grid_constant__ CUtensorMap map_x, const float* pair
           *reinterpret_cast<uint4*>(sBs + sw128_offset(z, ch)) = o;
         }
         sync_before_mma();
-        if (t == 0) {
+        if (t < 32) {  // warp-uniform issue: UMMA operands stay in uniform registers
           tc_fence_after();
-          umma_kblock(tmem + (i & 1) * CZ, smem_u32(sA) + kb * 16384, smem_u32(sBs), umma_idesc_f16(128, CZ), kb > 0);
-          umma_commit(&ring_free[slot]);
-          if (kb == KBS - 1) umma_commit(&acc_full[i & 1]);
+          if (elect_one()) {
+            umma_kblock(tmem + (i & 1) * CZ, smem_u32(sA) + kb * 16384, smem_u32(sBs), umma_idesc_f16(128, CZ), kb > 0);
+            umma_commit(&ring_free[slot]);
+            if (kb == KBS - 1) umma_commit(&acc_full[i & 1]);
+          }
+          __syncwarp();
         }
       }
     }
@@ -336,14 +339,17 @@ pair_embed_kernel(const float* __restrict__ pstatic, float* __restrict__ pair, c
       store_a_cols32(sA2, t, k0, v);
     }
     sync_before_mma();
-    if (t == 0) {
+    if (t < 32) {  // warp-uniform issue: UMMA operands stay in uniform registers
       tc_fence_after();
-      if (with_dist) {
-        umma_multi(tmem, smem_u32(sA1), smem_u32(sW1), KBD, CZ * 128, umma_idesc_f16(128, CZ), false);
-        umma_multi(tmem, smem_u32(sA1), smem_u32(sW1 + KBD * CZ * 128), KBD, CZ * 128, umma_idesc_f16(128, CZ), true);
+      if (elect_one()) {
+        if (with_dist) {
+          umma_multi(tmem, smem_u32(sA1), smem_u32(sW1), KBD, CZ * 128, umma_idesc_f16(128, CZ), false);
+          umma_multi(tmem, smem_u32(sA1), smem_u32(sW1 + KBD * CZ * 128), KBD, CZ * 128, umma_idesc_f16(128, CZ), true);
+        }
+        umma_multi(tmem + CZ, smem_u32(sA2), smem_u32(sW2), KBO, CZ * 128, umma_idesc_f16(128, CZ), false);
+        umma_commit(mma_bar);
       }
-      umma_multi(tmem + CZ, smem_u32(sA2), smem_u32(sW2), KBO, CZ * 128, umma_idesc_f16(128, CZ), false);
-      umma_commit(mma_bar);
+      __syncwarp();
     }
     mbar_wait(full, it & 1);
     mbar_wait(mma_bar, mma_phase);
@@ -490,11 +496,14 @@ coord_head_kernel(const float* __restrict__ pair, const float* __restrict__ z, c
       store_a_row<CZ>(sA, t, x);
     }
     sync_before_mma();
-    if (t == 0) {
+    if (t < 32) {  // warp-uniform issue: UMMA operands stay in uniform registers
       tc_fence_after();
-      umma_multi(tmem, smem_u32(sA), smem_u32(sW), 1, CZ * 128, umma_idesc_f16(128, CZ), false);
-      umma_multi(tmem, smem_u32(sA), smem_u32(sW + CZ * 128), 1, CZ * 128, umma_idesc_f16(128, CZ), true);
-      umma_commit(mma_bar);
+      if (elect_one()) {
+        umma_multi(tmem, smem_u32(sA), smem_u32(sW), 1, CZ * 128, umma_idesc_f16(128, CZ), false);
+        umma_multi(tmem, smem_u32(sA), smem_u32(sW + CZ * 128), 1, CZ * 128, umma_idesc_f16(128, CZ), true);
+        umma_commit(mma_bar);
+      }
+      __syncwarp();
     }
     mbar_wait(mma_bar, mma_phase);
     mma_phase ^= 1;

@@ -141,11 +141,14 @@ pair_transition_kernel(const float* pair, float* dst, int residual, long long R,
     }
     bulk_wait_read0();  // previous tile's output rows (staged in sH) have been read by the bulk store
     sync_before_mma();
-    if (t == 0) {
+    if (t < 32) {  // warp-uniform issue: UMMA operands stay in uniform registers
       tc_fence_after();
-      umma_multi(tmem, smem_u32(sA), smem_u32(sW1), 1, HID * 128, umma_idesc_f16(128, HID), false);
-      umma_multi(tmem, smem_u32(sA), smem_u32(sW1 + HID * 128), 1, HID * 128, umma_idesc_f16(128, HID), true);
-      umma_commit(mma_bar);
+      if (elect_one()) {
+        umma_multi(tmem, smem_u32(sA), smem_u32(sW1), 1, HID * 128, umma_idesc_f16(128, HID), false);
+        umma_multi(tmem, smem_u32(sA), smem_u32(sW1 + HID * 128), 1, HID * 128, umma_idesc_f16(128, HID), true);
+        umma_commit(mma_bar);
+      }
+      __syncwarp();
     }
     mbar_wait(mma_bar, mma_phase);
     mma_phase ^= 1;
@@ -163,16 +166,19 @@ pair_transition_kernel(const float* pair, float* dst, int residual, long long R,
         store_a_cols32(sH, t, c * 32, v);
       }
       sync_before_mma();
-      if (t == 0) {
+      if (t < 32) {  // warp-uniform issue: UMMA operands stay in uniform registers
         tc_fence_after();
-        const uint32_t idesc = umma_idesc_f16(128, CZ);
-        for (int kb = 0; kb < L::KBHH; ++kb)
-          umma_kblock(tmem + tm_out, smem_u32(sH) + kb * 16384, smem_u32(sW2) + (half * L::KBHH + kb) * CZ * 128, idesc,
-                      half > 0 || kb > 0);
-        for (int kb = 0; kb < L::KBHH; ++kb)
-          umma_kblock(tmem + tm_out, smem_u32(sH) + kb * 16384,
-                      smem_u32(sW2) + (L::KBH + half * L::KBHH + kb) * CZ * 128, idesc, true);
-        umma_commit(mma_bar);
+        if (elect_one()) {
+          const uint32_t idesc = umma_idesc_f16(128, CZ);
+          for (int kb = 0; kb < L::KBHH; ++kb)
+            umma_kblock(tmem + tm_out, smem_u32(sH) + kb * 16384, smem_u32(sW2) + (half * L::KBHH + kb) * CZ * 128, idesc,
+                        half > 0 || kb > 0);
+          for (int kb = 0; kb < L::KBHH; ++kb)
+            umma_kblock(tmem + tm_out, smem_u32(sH) + kb * 16384,
+                        smem_u32(sW2) + (L::KBH + half * L::KBHH + kb) * CZ * 128, idesc, true);
+          umma_commit(mma_bar);
+        }
+        __syncwarp();
       }
       mbar_wait(mma_bar, mma_phase);  // the hidden tile is rewritten next: its UMMAs must be done
       mma_phase ^= 1;
@@ -311,11 +317,14 @@ trimul_in_kernel(const float* __restrict__ pair, const float* __restrict__ mask,
       store_a_row<CZ>(sA, t, x);
     }
     g.sync_before_mma();
-    if (t == 0) {
+    if (t < 32) {  // warp-uniform issue: UMMA operands stay in uniform registers
       tc_fence_after();
-      umma_multi(tmem, smem_u32(sA), smem_u32(sW), 1, NOUT * 128, umma_idesc_f16(128, NOUT), false);
-      umma_multi(tmem, smem_u32(sA), smem_u32(sWl), 1, NOUT * 128, umma_idesc_f16(128, NOUT), true);
-      umma_commit(mma_bar);
+      if (elect_one()) {
+        umma_multi(tmem, smem_u32(sA), smem_u32(sW), 1, NOUT * 128, umma_idesc_f16(128, NOUT), false);
+        umma_multi(tmem, smem_u32(sA), smem_u32(sWl), 1, NOUT * 128, umma_idesc_f16(128, NOUT), true);
+        umma_commit(mma_bar);
+      }
+      __syncwarp();
     }
     // mask_2d for the *source* element: m[b,i]*m[b,k] is symmetric, same for both modes
     const float m2 = valid ? mask[(long long)b * map.N + i] * mask[(long long)b * map.N + k] : 0.f;
@@ -353,12 +362,158 @@ trimul_in_kernel(const float* __restrict__ pair, const float* __restrict__ mask,
   if (threadIdx.x < 32) tmem_dealloc(*tmem_slot, 2 * NOUT);
 }
 
+// -----------------------------------------------------------------------------------------
+// pair_dim 64: the projections are computed TRANSPOSED, D^T[channel][k] = W[channel][:] . X[k][:]^T (the weight
+// tile is the UMMA A operand, the LayerNorm tile the B operand), so TMEM lane = output channel and a thread
+// owns 64 consecutive k of one channel plane: 128 contiguous bytes instead of 128 two-byte stores with a
+// plane stride.  A tile is 128 consecutive k of ONE (b, i) row; two threads per TMEM lane (Group2): half h
+// takes columns [64 h, 64 h + 64).  512 threads = two compute groups.
+// -----------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(512, 1)
+trimul_in_t_kernel(const float* __restrict__ pair, const float* __restrict__ mask, RowMap map, int B,
+                   const __half* __restrict__ w_in, const float* __restrict__ b_in, __half* __restrict__ ab, int Np) {
+  constexpr int CZ = 64, NOUT = 256;
+  extern __shared__ uint8_t raw[];
+  constexpr int kStage = (RowStage<CZ>::kBytes + 1023) / 1024 * 1024;
+  constexpr int kGroupBytes = 32768 + kStage;  // X tile (store slices of warps 0-3 afterwards), slices of warps 4-7, row stage
+  uint8_t* sm = smem_align1024(raw);
+  uint8_t* sW = sm;                  // hi: proj rows [0,128), gate rows [128,256): two [128 x 64] A tiles
+  uint8_t* sWl = sW + NOUT * 128;    // lo
+  uint8_t* sG = sWl + NOUT * 128;
+  float* sM2 = reinterpret_cast<float*>(sG + 2 * kGroupBytes);  // [2][128] mask product per tile row
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sM2 + 256);      // full[2], mma[2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+
+  const Group2 g;
+  uint8_t* sA = sG + g.grp * kGroupBytes;
+  uint8_t* sSl = sA + (g.half ? 16384 : 0) + g.warp * 4096;  // this warp's store slice
+  uint8_t* sSt = sA + 32768;
+  float* sMask = sM2 + g.grp * 128;
+  uint64_t* full = bars + g.grp;
+  uint64_t* mma_bar = bars + 2 + g.grp;
+  if (threadIdx.x == 0) {
+    mbar_init(&bars[0], kTileRows);
+    mbar_init(&bars[1], kTileRows);
+    mbar_init(&bars[2], 1);
+    mbar_init(&bars[3], 1);
+    fence_barrier_init();
+  }
+  if (threadIdx.x < 32) tmem_alloc(tmem_slot, 2 * NOUT);
+  load_weight_kblocks(sW, w_in, NOUT, CZ, CZ, threadIdx.x, 512);
+  load_weight_kblocks(sWl, w_in + NOUT * CZ, NOUT, CZ, CZ, threadIdx.x, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot + g.grp * NOUT;
+  const uint32_t tm_lane = tmem + (static_cast<uint32_t>(g.warp * 32) << 16);
+  const int t = g.t, half = g.half, lane = t & 31;
+  const int N = map.N;
+  // this thread's output channel: lane t = channel of [a | b]; biases in the exp2 / plain domain
+  const float bias_p = b_in[t];
+  const float bias_g = -1.4426950408889634f * b_in[2 * CZ + t];
+  const int tps = (N + kTileRows - 1) / kTileRows;  // k-tiles per (b, i) row
+  const long long num_tiles = (long long)B * N * tps;
+  const long long stride = (long long)gridDim.x * 2;
+  const long long plane = (long long)N * Np;
+  uint32_t mma_phase = 0;
+  long long tile = (long long)blockIdx.x * 2 + g.grp;
+  auto issue = [&](long long tl) {  // row (b, i, k = k0 + t), loaded by the half-0 thread of the pair
+    const long long bi = tl / tps;
+    const int k = static_cast<int>(tl - bi * tps) * kTileRows + t;
+    const int b = static_cast<int>(bi / N), i = static_cast<int>(bi - (long long)b * N);
+    issue_row_load<CZ>(sSt, t, pair + map.src_row(b, i, k < N ? k : 0) * CZ, k < N, full);
+  };
+  if (tile < num_tiles && half == 0) issue(tile);
+  for (int it = 0; tile < num_tiles; tile += stride, ++it) {
+    mbar_wait(full, it & 1);
+    const long long bi = tile / tps;
+    const int k0 = static_cast<int>(tile - bi * tps) * kTileRows;
+    const int b = static_cast<int>(bi / N), i = static_cast<int>(bi - (long long)b * N);
+    const bool valid = k0 + t < N;
+    {
+      float x[CZ];
+      if (valid) {
+        read_row<CZ>(stage_row<CZ>(sSt, t), x);
+      } else {
+#pragma unroll
+        for (int q = 0; q < CZ; ++q) x[q] = 0.f;
+      }
+      layernorm_inplace<CZ>(x);
+      store_a_half_row<CZ>(sA, t, half, x);
+      // mask_2d of the *source* element: m[b,i]*m[b,k] is symmetric, same for both modes
+      if (half == 0) sMask[t] = valid ? mask[(long long)b * N + i] * mask[(long long)b * N + k0 + t] : 0.f;
+    }
+    g.sync_before_mma();
+    if (half == 0 && tile + stride < num_tiles) issue(tile + stride);
+    if (g.tt < 32) {  // warp-uniform issue: UMMA operands stay in uniform registers
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t idesc = umma_idesc_f16(128, 128);
+        umma_kblock(tmem, smem_u32(sW), smem_u32(sA), idesc, false);                  // proj, hi
+        umma_kblock(tmem, smem_u32(sWl), smem_u32(sA), idesc, true);                  // proj, lo
+        umma_kblock(tmem + 128, smem_u32(sW) + 16384, smem_u32(sA), idesc, false);    // gate, hi
+        umma_kblock(tmem + 128, smem_u32(sWl) + 16384, smem_u32(sA), idesc, true);    // gate, lo
+        umma_commit(mma_bar);
+      }
+      __syncwarp();
+    }
+    mbar_wait(mma_bar, mma_phase);
+    mma_phase ^= 1;
+    tc_fence_after();
+    // ---- epilogue: channel t, columns k0 + 64 half + [0, 64)
+    uint4 ov[8];
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      uint32_t pr[32], ga[32];
+      tmem_ld32(tm_lane + half * 64 + c * 32, pr);
+      tmem_ld32(tm_lane + 128 + half * 64 + c * 32, ga);
+      tmem_ld_wait();
+      const float4* mp = reinterpret_cast<const float4*>(sMask + half * 64 + c * 32);
+#pragma unroll
+      for (int j = 0; j < 32; j += 8) {
+        const float4 m0 = mp[j >> 2], m1 = mp[(j >> 2) + 1];
+        const float mm[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+        float v[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float z = fmaf(__uint_as_float(ga[j + e]), -1.4426950408889634f, bias_g);
+          const float sg = __fdividef(mm[e], 1.0f + ex2_approx(z));  // m2 * sigmoid
+          v[e] = sg * (__uint_as_float(pr[j + e]) + bias_p);
+        }
+        ov[c * 4 + (j >> 3)] = make_uint4(pack_half2(v[0], v[1]), pack_half2(v[2], v[3]), pack_half2(v[4], v[5]),
+                                          pack_half2(v[6], v[7]));
+      }
+    }
+    tc_fence_before();
+    if (k0 + 64 * half < Np) {  // (warp-uniform) the 64-column half lies inside the padded plane row
+      // warp = 32 consecutive channels of tensor a (lanes 0-63) or b (lanes 64-127)
+      const int ch0 = g.warp * 32;
+      const long long pl0 = (ch0 < CZ) ? ch0 : (ch0 - CZ) + (long long)B * CZ;
+      __half* gb = ab + ((long long)b * CZ + pl0) * plane + (long long)i * Np + k0 + 64 * half;
+      warp_store_rows128(sSl, lane, ov, gb, plane * 2, 32);
+    }
+    g.bar();  // the X tile / store slices are rewritten by the next tile
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (threadIdx.x < 32) tmem_dealloc(*tmem_slot, 2 * NOUT);
+}
+
 template <int CZ>
 static int launch_trimul_in(const PairDims& d, const float* pair, const float* mask, int mode, const __half* w_in,
                             const float* b_in, __half* ab, cudaStream_t s) {
+  RowMap map{d.N, (long long)d.N * d.N, mode};
+  if (CZ == 64) {
+    const long long tiles = (long long)d.B * d.N * ((d.N + kTileRows - 1) / kTileRows);
+    constexpr int kStage = (RowStage<64>::kBytes + 1023) / 1024 * 1024;
+    constexpr int smem = 1024 + 2 * 256 * 128 + 2 * (32768 + kStage) + 256 * 4 + 64;
+    if (set_smem(trimul_in_t_kernel, smem)) return 1;
+    trimul_in_t_kernel<<<grid_for((tiles + 1) / 2, 1), 512, smem, s>>>(pair, mask, map, d.B, w_in, b_in, ab, plane_ld(d.N));
+    PRD_LAUNCHED();
+    return 0;
+  }
   const long long R = (long long)d.B * d.N * d.N;
   const long long tiles = (R + kTileRows - 1) / kTileRows;
-  RowMap map{d.N, (long long)d.N * d.N, mode};
   constexpr int kGroupBytes = 16384 + (RowStage<CZ>::kBytes + 1023) / 1024 * 1024;
   constexpr int smem = 1024 + 2 * 4 * CZ * 128 + 2 * kGroupBytes + 4 * CZ * 4 + 64;
   auto kern = trimul_in_kernel<CZ>;
@@ -483,13 +638,16 @@ trimul_out_kernel(const float* pair, float* dst, int residual, const float* __re
       store_a_row<CZ>(sAp, t, y);
     }
     g.sync_before_mma();
-    if (t == 0) {
+    if (t < 32) {  // warp-uniform issue: UMMA operands stay in uniform registers
       tc_fence_after();
-      umma_multi(tmem, smem_u32(sAp), smem_u32(sW), 1, CZ * 128, umma_idesc_f16(128, CZ), false);
-      umma_multi(tmem, smem_u32(sAp), smem_u32(sW + 2 * CZ * 128), 1, CZ * 128, umma_idesc_f16(128, CZ), true);
-      umma_multi(tmem + CZ, smem_u32(sAx), smem_u32(sW + CZ * 128), 1, CZ * 128, umma_idesc_f16(128, CZ), false);
-      umma_multi(tmem + CZ, smem_u32(sAx), smem_u32(sW + 3 * CZ * 128), 1, CZ * 128, umma_idesc_f16(128, CZ), true);
-      umma_commit(mma_bar);
+      if (elect_one()) {
+        umma_multi(tmem, smem_u32(sAp), smem_u32(sW), 1, CZ * 128, umma_idesc_f16(128, CZ), false);
+        umma_multi(tmem, smem_u32(sAp), smem_u32(sW + 2 * CZ * 128), 1, CZ * 128, umma_idesc_f16(128, CZ), true);
+        umma_multi(tmem + CZ, smem_u32(sAx), smem_u32(sW + CZ * 128), 1, CZ * 128, umma_idesc_f16(128, CZ), false);
+        umma_multi(tmem + CZ, smem_u32(sAx), smem_u32(sW + 3 * CZ * 128), 1, CZ * 128, umma_idesc_f16(128, CZ), true);
+        umma_commit(mma_bar);
+      }
+      __syncwarp();
     }
     mbar_wait(mma_bar, mma_phase);
     mma_phase ^= 1;
@@ -551,18 +709,22 @@ int trimul_out(const PairDims& d, const float* pair, float* dst, int residual, c
 // Triangle attention projections.  Logical row (b, seq, tok): "starting" reads pair[b,seq,tok],
 // "ending" reads pair[b,tok,seq].  w: fp16 pair [hi; lo], each [256 x CZ] with rows [0,64) q,
 // [64,128) k, [128,192) v, [192,256) gate.
-// Outputs (fp16): q (pre-scaled by log2(e)/sqrt(c): the flash kernel works in the exp2 domain), k, g = sigmoid(gate) as [rows][64];
+// Outputs (fp16): q (pre-scaled by log2(e)/sqrt(c): the flash kernel works in the exp2 domain), k,
+// g = sigmoid(gate) as [rows][64];
 // v transposed per sequence: vt[(b*N+seq)][h*16+c][tok] (tok contiguous, row stride plane_ld(N)),
-// i.e. the K-major B operand of the P.V product.  Two compute groups.
+// i.e. the K-major B operand of the P.V product.
+// A tile is 128 consecutive tokens of ONE sequence (ceil(N/128) tiles per sequence), so the v tile can be
+// transposed through shared memory (the A tile, idle after the UMMA) and leave as 256-byte rows with
+// 16-byte stores instead of 64 two-byte stores per thread.  Two compute groups.
 // =========================================================================================
 template <int CZ>
-__global__ void __launch_bounds__(256, 1)
-triattn_proj_kernel(const float* __restrict__ pair, RowMap map, long long R, const __half* __restrict__ w,
+__global__ void __launch_bounds__(512, 1)
+triattn_proj_kernel(const float* __restrict__ pair, RowMap map, int B, const __half* __restrict__ w,
                     const float* __restrict__ b_gate, __half* __restrict__ q, __half* __restrict__ k,
                     __half* __restrict__ gout, __half* __restrict__ vt, int Np) {
   extern __shared__ uint8_t raw[];
   constexpr int NOUT = 256;
-  constexpr int kGroupBytes = 16384 + (RowStage<CZ>::kBytes + 1023) / 1024 * 1024;
+  constexpr int kGroupBytes = 32768 + (RowStage<CZ>::kBytes + 1023) / 1024 * 1024;  // A tile, output stage, row stage
   uint8_t* sm = smem_align1024(raw);
   uint8_t* sW = sm;
   uint8_t* sWl = sW + NOUT * 128;
@@ -571,9 +733,10 @@ triattn_proj_kernel(const float* __restrict__ pair, RowMap map, long long R, con
   uint64_t* bars = reinterpret_cast<uint64_t*>(sB + 64);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
 
-  const Group g;
+  const Group2 g;
   uint8_t* sA = sG + g.grp * kGroupBytes;
-  uint8_t* sSt = sA + 16384;
+  uint8_t* sO = sA + 16384;  // gate rows (warp-private 4 KB slices), then the transposed v tile
+  uint8_t* sSt = sA + 32768;
   uint64_t* full = bars + g.grp;
   uint64_t* mma_bar = bars + 2 + g.grp;
   if (threadIdx.x == 0) {
@@ -584,31 +747,35 @@ triattn_proj_kernel(const float* __restrict__ pair, RowMap map, long long R, con
     fence_barrier_init();
   }
   if (threadIdx.x < 32) tmem_alloc(tmem_slot, 2 * NOUT);
-  load_weight_kblocks(sW, w, NOUT, CZ, CZ, threadIdx.x, 256);
-  load_weight_kblocks(sWl, w + NOUT * CZ, NOUT, CZ, CZ, threadIdx.x, 256);
-  if (threadIdx.x < 64) sB[threadIdx.x] = b_gate[threadIdx.x];
+  load_weight_kblocks(sW, w, NOUT, CZ, CZ, threadIdx.x, 512);
+  load_weight_kblocks(sWl, w + NOUT * CZ, NOUT, CZ, CZ, threadIdx.x, 512);
+  if (threadIdx.x < 64) sB[threadIdx.x] = -1.4426950408889634f * b_gate[threadIdx.x];
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot + g.grp * NOUT;
   const uint32_t tm_lane = tmem + (static_cast<uint32_t>(g.warp * 32) << 16);
-  const int t = g.t;
-
-  const long long num_tiles = (R + kTileRows - 1) / kTileRows;
+  const int t = g.t, half = g.half;
+  const int N = map.N;
+  const int tps = (N + kTileRows - 1) / kTileRows;  // tiles per sequence
+  const long long num_tiles = (long long)B * N * tps;
   const long long stride = (long long)gridDim.x * 2;
   uint32_t mma_phase = 0;
   long long tile = (long long)blockIdx.x * 2 + g.grp;
+  // tile -> (sequence = b * N + s, first token); the row of thread pair t is loaded by its half-0 thread
   auto issue = [&](long long tl) {
-    const long long r = tl * kTileRows + t;
-    int b = 0, s = 0, tk = 0;
-    if (r < R) map.decompose(r, b, s, tk);
-    issue_row_load<CZ>(sSt, t, pair + map.src_row(b, s, tk) * CZ, r < R, full);
+    const long long seq = tl / tps;
+    const int tok = static_cast<int>(tl - seq * tps) * kTileRows + t;
+    const int b = static_cast<int>(seq / N), s = static_cast<int>(seq - (long long)b * N);
+    issue_row_load<CZ>(sSt, t, pair + map.src_row(b, s, tok < N ? tok : 0) * CZ, tok < N, full);
   };
-  if (tile < num_tiles) issue(tile);
+  if (tile < num_tiles && half == 0) issue(tile);
   for (int it = 0; tile < num_tiles; tile += stride, ++it) {
     mbar_wait(full, it & 1);
-    const long long r = tile * kTileRows + t;
-    const bool valid = r < R;
+    const long long seq = tile / tps;
+    const int tok0 = static_cast<int>(tile - seq * tps) * kTileRows;
+    const bool valid = tok0 + t < N;
+    const long long r0 = seq * N + tok0;  // first row of the tile
     {
       float x[CZ];
       if (valid) {
@@ -617,59 +784,105 @@ triattn_proj_kernel(const float* __restrict__ pair, RowMap map, long long R, con
 #pragma unroll
         for (int i = 0; i < CZ; ++i) x[i] = 0.f;
       }
-      if (tile + stride < num_tiles) issue(tile + stride);
-      layernorm_inplace<CZ>(x);
-      store_a_row<CZ>(sA, t, x);
+      layernorm_inplace<CZ>(x);  // both threads of the row (the statistics are cheap), each stores its half
+      store_a_half_row<CZ>(sA, t, half, x);
     }
-    g.sync_before_mma();
-    if (t == 0) {
+    g.sync_before_mma();  // also: both threads have read the row, its stage slot may be refilled
+    if (half == 0 && tile + stride < num_tiles) issue(tile + stride);
+    if (g.tt < 32) {  // warp-uniform issue: UMMA operands stay in uniform registers
       tc_fence_after();
-      umma_multi(tmem, smem_u32(sA), smem_u32(sW), 1, NOUT * 128, umma_idesc_f16(128, NOUT), false);
-      umma_multi(tmem, smem_u32(sA), smem_u32(sWl), 1, NOUT * 128, umma_idesc_f16(128, NOUT), true);
-      umma_commit(mma_bar);
+      if (elect_one()) {
+        umma_multi(tmem, smem_u32(sA), smem_u32(sW), 1, NOUT * 128, umma_idesc_f16(128, NOUT), false);
+        umma_multi(tmem, smem_u32(sA), smem_u32(sWl), 1, NOUT * 128, umma_idesc_f16(128, NOUT), true);
+        umma_commit(mma_bar);
+      }
+      __syncwarp();
     }
-    int b = 0, s = 0, tk = 0;
-    if (valid) map.decompose(r, b, s, tk);
     mbar_wait(mma_bar, mma_phase);
     mma_phase ^= 1;
     tc_fence_after();
-#pragma unroll 1
-    for (int c = 0; c < 8; ++c) {
-      uint32_t acc[32];
-      tmem_ld32(tm_lane + c * 32, acc);
-      tmem_ld_wait();
-      if (!valid) continue;
-      const int part = c >> 1;       // 0 q, 1 k, 2 v, 3 gate
-      const int col0 = (c & 1) * 32;  // column inside the 64-wide part
-      if (part == 2) {
-        __half* vp = vt + (((long long)b * map.N + s) * 64 + col0) * Np + tk;
+    if (half == 0) {
+      // ---- q (scaled), k: row-major [rows][64]
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          *vp = __float2half_rn(__uint_as_float(acc[j]));
-          vp += Np;
-        }
-      } else {
-        float v[32];
+      for (int part = 0; part < 2; ++part) {
+        uint32_t acc[2][32];
+        tmem_ld32(tm_lane + part * 64, acc[0]);
+        tmem_ld32(tm_lane + part * 64 + 32, acc[1]);
+        tmem_ld_wait();
+        const float sc = part == 0 ? 0.25f * 1.4426950408889634f : 1.0f;
+        uint4 o[8];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          float a = __uint_as_float(acc[j]);
-          if (part == 0) a *= 0.25f * 1.4426950408889634f;
-          if (part == 3) a = sigmoidf_fast(a + sB[col0 + j]);
-          v[j] = a;
+        for (int j = 0; j < 8; ++j) {
+          const uint32_t* a = &acc[j >> 2][(j & 3) * 8];
+          o[j].x = pack_half2(__uint_as_float(a[0]) * sc, __uint_as_float(a[1]) * sc);
+          o[j].y = pack_half2(__uint_as_float(a[2]) * sc, __uint_as_float(a[3]) * sc);
+          o[j].z = pack_half2(__uint_as_float(a[4]) * sc, __uint_as_float(a[5]) * sc);
+          o[j].w = pack_half2(__uint_as_float(a[6]) * sc, __uint_as_float(a[7]) * sc);
         }
-        __half* dstp = (part == 0 ? q : (part == 1 ? k : gout)) + r * 64 + col0;
+        // the A tile is idle after the UMMA: warp-private 4 KB slices
+        warp_store_rows128(sA + g.warp * 4096, t & 31, o, (part == 0 ? q : k) + (r0 + g.warp * 32) * 64, 128,
+                           N - (tok0 + g.warp * 32));
+      }
+    } else {
+      // ---- gate: sigmoid(a + b) = 1 / (1 + exp2(-(a + b) log2 e)), row-major
+      {
+        uint32_t acc[2][32];
+        tmem_ld32(tm_lane + 192, acc[0]);
+        tmem_ld32(tm_lane + 224, acc[1]);
+        tmem_ld_wait();
+        uint4 o[8];
 #pragma unroll
-        for (int j = 0; j < 32; j += 8) {
-          uint4 o;
-          o.x = pack_half2(v[j], v[j + 1]);
-          o.y = pack_half2(v[j + 2], v[j + 3]);
-          o.z = pack_half2(v[j + 4], v[j + 5]);
-          o.w = pack_half2(v[j + 6], v[j + 7]);
-          *reinterpret_cast<uint4*>(dstp + j) = o;
+        for (int j = 0; j < 8; ++j) {
+          float gsig[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const int col = j * 8 + e;
+            const float z = fmaf(__uint_as_float(acc[col >> 5][col & 31]), -1.4426950408889634f, sB[col]);
+            gsig[e] = __fdividef(1.0f, 1.0f + ex2_approx(z));
+          }
+          o[j].x = pack_half2(gsig[0], gsig[1]);
+          o[j].y = pack_half2(gsig[2], gsig[3]);
+          o[j].z = pack_half2(gsig[4], gsig[5]);
+          o[j].w = pack_half2(gsig[6], gsig[7]);
         }
+        warp_store_rows128(sO + g.warp * 4096, t & 31, o, gout + (r0 + g.warp * 32) * 64, 128, N - (tok0 + g.warp * 32));
+      }
+      // ---- v: transpose through shared memory: sO[ch][tok] halves, 256 B per channel (the four gate warps
+      // are done with their slices of sO)
+      asm volatile("bar.sync %0, 128;" ::"r"(g.grp + 3) : "memory");
+      {
+        uint32_t acc[2][32];
+        tmem_ld32(tm_lane + 128, acc[0]);
+        tmem_ld32(tm_lane + 160, acc[1]);
+        tmem_ld_wait();
+        __half* sV = reinterpret_cast<__half*>(sO);
+#pragma unroll
+        for (int c = 0; c < 64; ++c) sV[c * kTileRows + t] = __float2half_rn(__uint_as_float(acc[c >> 5][c & 31]));
       }
     }
     tc_fence_before();
+    g.bar();
+    {
+      // thread -> 16-byte vector (tt & 15) of channel rows (tt >> 4) + 16 i: a warp writes two full 256-byte rows
+      const int vec = g.tt & 15;
+      __half* vrow = vt + seq * 64 * Np + tok0 + vec * 8;
+      const int n_ok = N - (tok0 + vec * 8);  // tokens of this vector that exist
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int ch = (g.tt >> 4) + 16 * i;
+        const uint4 v = *reinterpret_cast<const uint4*>(sO + ch * 256 + vec * 16);
+        __half* dp = vrow + (long long)ch * Np;
+        if (n_ok >= 8) {
+          *reinterpret_cast<uint4*>(dp) = v;
+        } else if (n_ok > 0) {  // ragged tail: static register indices (a dynamic one would spill v to local memory)
+          const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+          for (int e = 0; e < 8; ++e)
+            if (e < n_ok) reinterpret_cast<unsigned short*>(dp)[e] = static_cast<unsigned short>(w4[e >> 1] >> ((e & 1) * 16));
+        }
+      }
+    }
+    g.bar();  // the A tile and the output stage are rewritten by the next tile
   }
   tc_fence_before();
   __syncthreads();
@@ -679,14 +892,13 @@ triattn_proj_kernel(const float* __restrict__ pair, RowMap map, long long R, con
 template <int CZ>
 static int launch_triattn_proj(const PairDims& d, const float* pair, int mode, const __half* w_qkvg, const float* b_gate,
                                __half* q, __half* k, __half* g, __half* vt, cudaStream_t s) {
-  const long long R = (long long)d.B * d.N * d.N;
-  const long long tiles = (R + kTileRows - 1) / kTileRows;
+  const long long tiles = (long long)d.B * d.N * ((d.N + kTileRows - 1) / kTileRows);
   RowMap map{d.N, (long long)d.N * d.N, mode};
-  constexpr int kGroupBytes = 16384 + (RowStage<CZ>::kBytes + 1023) / 1024 * 1024;
+  constexpr int kGroupBytes = 32768 + (RowStage<CZ>::kBytes + 1023) / 1024 * 1024;  // A tile, output stage, row stage
   constexpr int smem = 1024 + 2 * 256 * 128 + 2 * kGroupBytes + 64 * 4 + 64;
   auto kern = triattn_proj_kernel<CZ>;
   if (set_smem(kern, smem)) return 1;
-  kern<<<grid_for((tiles + 1) / 2, 1), 256, smem, s>>>(pair, map, R, w_qkvg, b_gate, q, k, g, vt, plane_ld(d.N));
+  kern<<<grid_for((tiles + 1) / 2, 1), 512, smem, s>>>(pair, map, d.B, w_qkvg, b_gate, q, k, g, vt, plane_ld(d.N));
   PRD_LAUNCHED();
   return 0;
 }
@@ -766,11 +978,14 @@ triattn_out_kernel(const float* pair, float* dst, int residual, RowMap map, long
       }
     }
     g.sync_before_mma();
-    if (t == 0) {
+    if (t < 32) {  // warp-uniform issue: UMMA operands stay in uniform registers
       tc_fence_after();
-      umma_multi(tmem, smem_u32(sA), smem_u32(sW), 1, CZ * 128, umma_idesc_f16(128, CZ), false);
-      umma_multi(tmem, smem_u32(sA), smem_u32(sWl), 1, CZ * 128, umma_idesc_f16(128, CZ), true);
-      umma_commit(mma_bar);
+      if (elect_one()) {
+        umma_multi(tmem, smem_u32(sA), smem_u32(sW), 1, CZ * 128, umma_idesc_f16(128, CZ), false);
+        umma_multi(tmem, smem_u32(sA), smem_u32(sWl), 1, CZ * 128, umma_idesc_f16(128, CZ), true);
+        umma_commit(mma_bar);
+      }
+      __syncwarp();
     }
     mbar_wait(full, it & 1);
     mbar_wait(mma_bar, mma_phase);

@@ -62,19 +62,42 @@ __device__ __forceinline__ void write_row(float* row, const float (&x)[CZ]) {
 // In-place LayerNorm without affine (nn.LayerNorm(elementwise_affine=False), eps 1e-5).
 template <int CZ>
 __device__ __forceinline__ void layernorm_inplace(float (&x)[CZ]) {
-  float s = 0.f;
+  // four independent partial sums: a single 64-deep dependent FADD chain costs ~250 cycles of pure latency
+  float s4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-  for (int i = 0; i < CZ; ++i) s += x[i];
-  const float mean = s * (1.0f / CZ);
-  float v = 0.f;
+  for (int i = 0; i < CZ; ++i) s4[i & 3] += x[i];
+  const float mean = ((s4[0] + s4[1]) + (s4[2] + s4[3])) * (1.0f / CZ);
+  float v4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
   for (int i = 0; i < CZ; ++i) {
-    const float d = x[i] - mean;
-    v += d * d;
+    x[i] -= mean;
+    v4[i & 3] = fmaf(x[i], x[i], v4[i & 3]);
   }
-  const float rstd = rsqrtf(v * (1.0f / CZ) + kLnEps);
+  const float rstd = rsqrtf(((v4[0] + v4[1]) + (v4[2] + v4[3])) * (1.0f / CZ) + kLnEps);
 #pragma unroll
-  for (int i = 0; i < CZ; ++i) x[i] = (x[i] - mean) * rstd;
+  for (int i = 0; i < CZ; ++i) x[i] *= rstd;
+}
+
+// Write channels [32 half, 32 half + 32) of one row of a [128 x 64] fp16 K-block (two threads per row).
+template <int CZ>
+__device__ __forceinline__ void store_a_half_row(uint8_t* a_tile, int t, int half, const float (&y)[CZ]) {
+#pragma unroll
+  for (int c4 = 0; c4 < 4; ++c4) {
+    uint4 o = make_uint4(0, 0, 0, 0);
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh) {
+      if (hh == half) {
+        const int ch = hh * 4 + c4;
+        if (ch * 8 < CZ) {
+          o.x = pack_half2(y[ch * 8 + 0], y[ch * 8 + 1]);
+          o.y = pack_half2(y[ch * 8 + 2], y[ch * 8 + 3]);
+          o.z = pack_half2(y[ch * 8 + 4], y[ch * 8 + 5]);
+          o.w = pack_half2(y[ch * 8 + 6], y[ch * 8 + 7]);
+        }
+      }
+    }
+    *reinterpret_cast<uint4*>(a_tile + sw128_offset(t, half * 4 + c4)) = o;
+  }
 }
 
 // Write one row (CZ <= 64 values, zero padded to 64) of a [128 x 64] fp16 K-block.
@@ -177,6 +200,31 @@ struct Group {
   }
   __device__ __forceinline__ void bar() const { asm volatile("bar.sync %0, 128;" ::"r"(grp + 1) : "memory"); }
   // make generic-proxy smem writes visible to the tensor core, then sync the group
+  __device__ __forceinline__ void sync_before_mma() const {
+    fence_proxy_async_smem();
+    tc_fence_before();
+    bar();
+  }
+};
+
+// Two compute groups of 256 threads (warps 0-7 / 8-15), TWO threads per tile row: thread (row, half) with
+// row = TMEM lane, half = which half of the work of that row (channels of the LayerNorm output, columns of
+// the accumulator).  Warps w and w+4 of a group share a TMEM lane quarter, which tcgen05.ld allows (the
+// quarter is warp_id % 4).  Twice the warps per scheduler and half the serial work per thread of `Group`.
+struct Group2 {
+  int grp;   // 0 or 1
+  int tt;    // thread index inside the group, 0..255
+  int t;     // tile row = TMEM lane, 0..127
+  int half;  // 0 or 1
+  int warp;  // lane quarter, 0..3
+  __device__ __forceinline__ Group2() {
+    grp = threadIdx.x >> 8;
+    tt = threadIdx.x & 255;
+    t = tt & 127;
+    half = tt >> 7;
+    warp = t >> 5;
+  }
+  __device__ __forceinline__ void bar() const { asm volatile("bar.sync %0, 256;" ::"r"(grp + 1) : "memory"); }
   __device__ __forceinline__ void sync_before_mma() const {
     fence_proxy_async_smem();
     tc_fence_before();

@@ -103,13 +103,6 @@ __device__ __forceinline__ uint32_t cvt_f16x2(float lo, float hi) {
   asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(y) : "f"(hi), "f"(lo));
   return y;
 }
-// One elected lane of a fully converged warp (warp-uniform control flow around it keeps UMMA / TMA operands
-// in uniform registers; an `if (lane == 0)` branch costs ~15 instructions per tcgen05.mma instead).
-__device__ __forceinline__ bool elect_one() {
-  uint32_t pred;
-  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
-  return pred != 0;
-}
 __device__ __forceinline__ void tmem_ld_wait32(uint32_t (&r)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;"
                : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
@@ -586,14 +579,6 @@ triattn_flash_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
         }
       }
       // ---- unit epilogue: last O partial, normalise, gate, store
-      const int tok_i = qt * 128 + t;
-      const long long row = (long long)seq * N + tok_i;
-      uint4 gv[8];
-      if (tok_i < N) {
-        const uint4* gp = reinterpret_cast<const uint4*>(g_gate + row * 64);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) gv[i] = __ldg(gp + i);
-      }
       {
         mbar_wait(bar_pv, (G - 1) & 1);
         tc_fence_after();
@@ -606,24 +591,31 @@ triattn_flash_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
         for (int c = 0; c < 16; ++c) o[3][c] = fmaf(o[3][c], alpha[3], __uint_as_float(ov[c]));
       }
       FLASH_TRACE(30);
-      if (tok_i < N) {
-        uint4* op = reinterpret_cast<uint4*>(og + row * 64);
+      {
+        // rows [32 w, 32 w + 32) of P K-block 0 are private to this warp and idle (the last P.V is complete):
+        // 4 KB slice for the coalesced load of the gate rows / store of the output rows
+        uint8_t* slice = sP + w * 4096;
+        const int row0 = qt * 128 + w * 32;
+        const long long grow = ((long long)seq * N + row0) * 64;
+        uint4 gv[8];
+        warp_load_rows128(slice, lane, gv, g_gate + grow, 128, N - row0);
+        uint4 ovv[8];
 #pragma unroll
         for (int h = 0; h < 4; ++h) {
           const float inv = 1.0f / lrow[h];
 #pragma unroll
           for (int half = 0; half < 2; ++half) {
             const __half2* g2 = reinterpret_cast<const __half2*>(&gv[h * 2 + half]);
-            uint4 ovv;
-            uint32_t* o32 = reinterpret_cast<uint32_t*>(&ovv);
+            uint32_t* o32 = reinterpret_cast<uint32_t*>(&ovv[h * 2 + half]);
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               const float2 gf = __half22float2(g2[e]);
               o32[e] = pack_half2(o[h][half * 8 + 2 * e] * inv * gf.x, o[h][half * 8 + 2 * e + 1] * inv * gf.y);
             }
-            op[h * 2 + half] = ovv;
           }
         }
+        warp_store_rows128(slice, lane, ovv, og + grow, 128, N - row0);
+        __syncwarp();  // the slice is P again from here on
       }
       FLASH_TRACE(31);
     }

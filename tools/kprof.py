@@ -43,7 +43,34 @@ def main():
     stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
     lib.prd_profile_kernel.restype = ctypes.c_int
     res = {}
+    single = torch.randn(a.B, a.N, cfg.single_dim, generator=g).to(dev)
+    op_calls = {
+        "op_triattn_start": lambda: blk.pair_attn_starting.apply_(cfg, pair, mask),
+        "op_triattn_end": lambda: blk.pair_attn_ending.apply_(cfg, pair, mask),
+        "op_trimul_out": lambda: blk.pair_mul_outgoing.apply_(cfg, pair, mask),
+        "op_trimul_in": lambda: blk.pair_mul_incoming.apply_(cfg, pair, mask),
+        "op_pair_fc": lambda: ops.pair_transition(cfg, pair, blk.pair_fc.packed_pair(), pair),
+        "op_outer_linear": lambda: blk.outer_linear.apply_(cfg, single, pair),
+        "op_single_attn": lambda: ops.single_attention(cfg, single, pair, mask, blk.single_attn.packed_single(blk.attn_bias[1]), single),
+        "op_block": lambda: blk.forward_(cfg, single, pair, mask),
+    }
+    for name in list(a.kernels):
+        if name == "ops":
+            a.kernels.remove("ops")
+            a.kernels += [k for k in op_calls if k not in a.kernels]
     for name in a.kernels:
+        if name in op_calls:  # whole module-level op (several kernels), CUDA events on the current stream
+            f = op_calls[name]
+            f()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(a.iters):
+                f()
+            e1.record()
+            torch.cuda.synchronize()
+            res[name] = round(e0.elapsed_time(e1) / a.iters, 4)
+            continue
         if name == "triattn_flash":
             blk.pair_attn_starting.apply_(cfg, pair, mask)
             aux = mask
