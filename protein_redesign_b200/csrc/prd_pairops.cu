@@ -13,189 +13,213 @@ namespace prd {
 // =========================================================================================
 // OuterLinear:  dst[b,i,j,z] = [pair +] sum_d W1[z,d] x_i[d] x_j[d] + u[b,i,z] - u[b,j,z] + bias[z]
 // with x = LN(single), u = x W2^T (precomputed), W = [W1 | W2] = linear.weight[:, :c_s | c_s:].
-// CTA (256 threads) = (j-tile of 128 tokens, chunk of i, b).  A = x[b, j-tile, :] stays in shared
-// memory (c_s/64 K-blocks, TMA).  W1 lives in REGISTERS (each thread owns a fixed set of 16-byte
-// chunks), so for every i the B operand (W1 * x_i) is rebuilt with pure register x smem math;
-// c_s/16 UMMAs then produce one [128 x c_z] accumulator.  Two accumulators alternate: the UMMAs of
-// row i run while the epilogue of row i-1 (TMEM -> registers -> global) is in flight, and the
-// residual pair values of row i-1 are prefetched before the B operand is rebuilt.
+// CTA = (j-tile of 128 tokens, chunk of i, b); A = x[b, j-tile, :] stays in shared memory (c_s/64 K-blocks,
+// TMA).  Warp-specialised, no CTA-wide barrier in the row loop:
+//   warps 0-7   builders: W1 lives in their REGISTERS (each thread owns a fixed set of 16-byte chunks); for
+//               every i the B operand (W1 * x_i) is rebuilt K-block by K-block into a 4-slot ring
+//               (mbarriers full[] / empty[])
+//   warps 8-11  epilogue: thread = token j (TMEM lane): accumulator + u_i - u_j + bias + residual, pair rows
+//               loaded and stored as full lines through warp-private shared-memory slices
+//   warp 12     UMMA issue (c_s/16 UMMAs per row into one of two [128 x c_z] accumulators) and the A-tile TMA
+// The only per-row synchronisation of the builders is one named barrier (x_i staged in shared memory).
 // =========================================================================================
+constexpr int kOlThreads = 512;  // 4 warpgroups: builders, builders, epilogue, {UMMA/TMA warp + 3 idle warps that only donate registers}
+
 template <int CZ, int KBS>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(kOlThreads, 1)
 outer_linear_kernel(const __grid_constant__ CUtensorMap map_x, const float* pair, float* dst, int residual,
-                    const float* __restrict__ xn32, const __half* __restrict__ w1, const float* __restrict__ u,
+                    const __half* __restrict__ xn16, const __half* __restrict__ w1, const float* __restrict__ u,
                     const float* __restrict__ bias, int N, int ilen) {
   extern __shared__ uint8_t raw[];
   constexpr int CS = KBS * 64;
-  constexpr int NCH = KBS * CZ * 8 / 256;  // 16-byte W1 chunks per thread
+  constexpr int NCH = KBS * CZ * 8 / 256;  // 16-byte W1 chunks per builder thread
   constexpr int CPK = NCH / KBS;           // ... per K-block
-  constexpr int HC = CZ / 2;               // accumulator columns per thread (two warp groups split them)
   constexpr int RB = 4;                    // ring of B-operand K-blocks
+  constexpr int RP = CZ * 4 / 128;         // 128-byte pieces per pair row
   uint8_t* sm = smem_align1024(raw);
   uint8_t* sA = sm;                        // KBS x 16 KB
   uint8_t* sB = sA + KBS * 16384;          // RB x [CZ x 64]
-  float* sXi = reinterpret_cast<float*>(sB + RB * CZ * 128);
-  float* sUi = sXi + CS;                   // [2][CZ]
-  float* sBias = sUi + 2 * CZ;
+  uint8_t* sSl = sB + RB * CZ * 128;       // 4 epilogue warps x 4 KB
+  float* sXi = reinterpret_cast<float*>(sSl + 4 * 4096);  // [2][CS]
+  float* sUi = sXi + 2 * CS;               // [4][CZ]
+  float* sBias = sUi + 4 * CZ;
   uint64_t* bar_a = reinterpret_cast<uint64_t*>(sBias + CZ);
-  uint64_t* ring_free = bar_a + 1;         // [RB]
-  uint64_t* acc_full = ring_free + RB;     // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 2);
+  uint64_t* full = bar_a + 1;              // [RB] K-block built (256 builder arrivals)
+  uint64_t* empty = full + RB;             // [RB] K-block consumed (UMMA commit)
+  uint64_t* acc_full = empty + RB;         // [2]
+  uint64_t* acc_empty = acc_full + 2;      // [2] (128 epilogue arrivals)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
   constexpr int TCOLS = 2 * CZ < 32 ? 32 : 2 * CZ;
 
-  const int t = threadIdx.x, warp = t >> 5;
-  const int grp = warp >> 2;               // 0: columns [0, HC), 1: columns [HC, CZ)
-  const int lane_row = (warp & 3) * 32 + (t & 31);
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
   const int jt = blockIdx.x, b = blockIdx.z;
   const int i0 = blockIdx.y * ilen;
   const int i1 = min(N, i0 + ilen);
   if (t == 0) {
     mbar_init(bar_a, 1);
-    for (int q = 0; q < RB; ++q) mbar_init(&ring_free[q], 1);
-    mbar_init(&acc_full[0], 1);
-    mbar_init(&acc_full[1], 1);
+    for (int q = 0; q < RB; ++q) {
+      mbar_init(&full[q], 256);
+      mbar_init(&empty[q], 1);
+    }
+    for (int q = 0; q < 2; ++q) {
+      mbar_init(&acc_full[q], 1);
+      mbar_init(&acc_empty[q], 128);
+    }
     fence_barrier_init();
     tma_prefetch_desc(&map_x);
   }
   if (warp == 0) tmem_alloc(tmem_slot, TCOLS);
-  for (int i = t; i < CZ; i += 256) sBias[i] = bias[i];
+  for (int i = t; i < CZ; i += kOlThreads) sBias[i] = bias[i];
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  const uint32_t tm_lane = tmem + (static_cast<uint32_t>((warp & 3) * 32) << 16);
-  if (t == 0) {
-    mbar_expect_tx(bar_a, KBS * 16384);
-    for (int kb = 0; kb < KBS; ++kb) tma_load_3d(sA + kb * 16384, &map_x, bar_a, kb * 64, jt * 128, b);
-  }
-  // this thread's W1 chunks (fixed for the whole kernel): chunk n covers K-block n / CPK,
-  // row z = (t >> 3) + 32 * (n % CPK), 16-byte column chunk ch = t & 7
-  const int ch = t & 7;
-  uint4 wreg[NCH];
-#pragma unroll
-  for (int n = 0; n < NCH; ++n) {
-    const int kb = n / CPK, z = (t >> 3) + 32 * (n % CPK);
-    wreg[n] = __ldg(reinterpret_cast<const uint4*>(w1 + (long long)z * CS + kb * 64 + ch * 8));
-  }
-  const int j = jt * 128 + lane_row;
-  const bool valid = j < N;
-  float uj[HC];
-  if (valid) {
-    const float4* up = reinterpret_cast<const float4*>(u + ((long long)b * N + j) * CZ + grp * HC);
-#pragma unroll
-    for (int c = 0; c < HC / 4; ++c) {
-      const float4 v = __ldg(up + c);
-      uj[c * 4] = v.x; uj[c * 4 + 1] = v.y; uj[c * 4 + 2] = v.z; uj[c * 4 + 3] = v.w;
-    }
-  } else {
-#pragma unroll
-    for (int c = 0; c < HC; ++c) uj[c] = 0.f;
-  }
-  mbar_wait(bar_a, 0);
 
-  // epilogue of row `ie` from accumulator `ie & 1`; `res` holds the prefetched residual values
-  auto epilogue = [&](int ie, const float4 (&res)[HC / 4]) {
-    float* drow = dst + (((long long)b * N + ie) * N + j) * CZ + grp * HC;
-    const float* ui = sUi + (ie & 1) * CZ + grp * HC;
-    const float* bs = sBias + grp * HC;
+  if (warp < 8) {
+    // ------------------------------------------------------------------ builders
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 136;");  // 64 registers of W1 + working set
+    // this thread's W1 chunks (fixed for the whole kernel): chunk n covers K-block n / CPK,
+    // row z = (t >> 3) + 32 * (n % CPK), 16-byte column chunk ch = t & 7
+    const int ch = t & 7;
+    uint4 wreg[NCH];
 #pragma unroll
-    for (int c = 0; c < HC / 16; ++c) {
-      uint32_t acc[16];
-      tmem_ld16(tm_lane + (ie & 1) * CZ + grp * HC + c * 16, acc);
-      tmem_ld_wait();
-      if (valid) {
-#pragma unroll
-        for (int q = 0; q < 16; q += 4) {
-          float4 x = res[c * 4 + q / 4];
-          x.x += __uint_as_float(acc[q + 0]) + ui[c * 16 + q + 0] - uj[c * 16 + q + 0] + bs[c * 16 + q + 0];
-          x.y += __uint_as_float(acc[q + 1]) + ui[c * 16 + q + 1] - uj[c * 16 + q + 1] + bs[c * 16 + q + 1];
-          x.z += __uint_as_float(acc[q + 2]) + ui[c * 16 + q + 2] - uj[c * 16 + q + 2] + bs[c * 16 + q + 2];
-          x.w += __uint_as_float(acc[q + 3]) + ui[c * 16 + q + 3] - uj[c * 16 + q + 3] + bs[c * 16 + q + 3];
-          *reinterpret_cast<float4*>(drow + c * 16 + q) = x;
-        }
+    for (int n = 0; n < NCH; ++n) {
+      const int kb = n / CPK, z = (t >> 3) + 32 * (n % CPK);
+      wreg[n] = __ldg(reinterpret_cast<const uint4*>(w1 + (long long)z * CS + kb * 64 + ch * 8));
+    }
+    // x_i (fp16, the same rounding as the A operand x_j) / u_i are fetched one row ahead into registers so
+    // their global latency is off the critical path.  B' = W1 * x_i is formed with HMUL2 straight from the
+    // packed W1 registers: no fp32 temporaries (a loop-invariant half->float expansion of W1 would spill).
+    constexpr int XPT = CS / 512;  // half2 of x_i per thread
+    static_assert(XPT == 1 || CS == 256, "x_i staging assumes c_s in {256, 512}");
+    uint32_t xnext = 0;
+    float unext = 0.f;
+    auto fetch_row = [&](int i) {
+      if (i < i1) {
+        const uint32_t* xi = reinterpret_cast<const uint32_t*>(xn16 + ((long long)b * N + i) * CS);
+        if (t < CS / 2) xnext = __ldg(xi + t);
+        if (t < CZ) unext = __ldg(u + ((long long)b * N + i) * CZ + t);
       }
-    }
-  };
-
-  // x_i / u_i are fetched one row ahead into registers so their global latency is off the critical path
-  constexpr int XPT = CS / 256;  // floats of x_i per thread
-  float xnext[XPT];
-  float unext = 0.f;
-  auto fetch_row = [&](int i) {
-    if (i < i1) {
-      const float* xi = xn32 + ((long long)b * N + i) * CS;
-#pragma unroll
-      for (int q = 0; q < XPT; ++q) xnext[q] = __ldg(xi + t + 256 * q);
-      if (t < CZ) unext = __ldg(u + ((long long)b * N + i) * CZ + t);
-    }
-  };
-  fetch_row(i0);
-  uint32_t ring_it = 0;  // K-blocks generated so far (ring position)
-  for (int i = i0; i <= i1; ++i) {
-    // (1) prefetch the residual of row i-1 (consumed by its epilogue at the end of this iteration)
-    float4 res[HC / 4];
-#pragma unroll
-    for (int c = 0; c < HC / 4; ++c) res[c] = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (i > i0 && residual && valid) {
-      const float4* pr = reinterpret_cast<const float4*>(pair + (((long long)b * N + (i - 1)) * N + j) * CZ + grp * HC);
-#pragma unroll
-      for (int c = 0; c < HC / 4; ++c) res[c] = pr[c];
-    }
-    const float ucur = unext;
-    if (i < i1) {
-      // (2) x_i -> shared (registers filled one iteration ago); every thread finished reading the previous
-      // x in the K-block barriers of the previous row
-#pragma unroll
-      for (int q = 0; q < XPT; ++q) sXi[t + 256 * q] = xnext[q];
-      // u_i is read by the epilogue of row i (next iteration); its slot was last read by the epilogue of
-      // row i-2, i.e. before the barriers of row i-1
-      if (t < CZ) sUi[(i & 1) * CZ + t] = ucur;
-    }
-    fetch_row(i + 1);
-    __syncthreads();
-    if (i < i1) {
-      // (3) per K-block: B'[z][d] = W1[z][d] * x_i[d] into a ring slot, then its four UMMAs are issued while
-      // the next K-block is being built
+    };
+    fetch_row(i0);
+    uint32_t ring_it = 0;  // K-blocks generated so far (ring position)
+    for (int i = i0; i < i1; ++i) {
+      uint32_t* sx = reinterpret_cast<uint32_t*>(sXi) + (i & 1) * (CS / 2);
+      if (t < CS / 2) sx[t] = xnext;
+      if (t < CZ) sUi[(i & 3) * CZ + t] = unext;  // read by the epilogue of row i (ordered through full[] -> acc_full[])
+      fetch_row(i + 1);
+      asm volatile("bar.sync 1, 256;" ::: "memory");  // x_i complete; everyone is done with the buffer of row i-2
 #pragma unroll
       for (int kb = 0; kb < KBS; ++kb, ++ring_it) {
         const uint32_t slot = ring_it % RB;
-        if (ring_it >= RB) mbar_wait(&ring_free[slot], ((ring_it / RB) - 1) & 1);
-        const int d0 = kb * 64 + ch * 8;
-        const float4 xa = *reinterpret_cast<const float4*>(sXi + d0);
-        const float4 xb = *reinterpret_cast<const float4*>(sXi + d0 + 4);
+        if (ring_it >= RB) mbar_wait(&empty[slot], ((ring_it / RB) - 1) & 1);
+        const uint4 xv = *reinterpret_cast<const uint4*>(sx + (kb * 64 + ch * 8) / 2);
+        const __half2* x2 = reinterpret_cast<const __half2*>(&xv);
         uint8_t* sBs = sB + slot * (CZ * 128);
 #pragma unroll
         for (int n = 0; n < CPK; ++n) {
           const int z = (t >> 3) + 32 * n;
           const __half2* w2 = reinterpret_cast<const __half2*>(&wreg[kb * CPK + n]);
-          const float2 f0 = __half22float2(w2[0]), f1 = __half22float2(w2[1]);
-          const float2 f2 = __half22float2(w2[2]), f3 = __half22float2(w2[3]);
           uint4 o;
-          o.x = pack_half2(f0.x * xa.x, f0.y * xa.y);
-          o.y = pack_half2(f1.x * xa.z, f1.y * xa.w);
-          o.z = pack_half2(f2.x * xb.x, f2.y * xb.y);
-          o.w = pack_half2(f3.x * xb.z, f3.y * xb.w);
+          __half2* o2 = reinterpret_cast<__half2*>(&o);
+          o2[0] = __hmul2(w2[0], x2[0]);
+          o2[1] = __hmul2(w2[1], x2[1]);
+          o2[2] = __hmul2(w2[2], x2[2]);
+          o2[3] = __hmul2(w2[3], x2[3]);
           *reinterpret_cast<uint4*>(sBs + sw128_offset(z, ch)) = o;
         }
-        sync_before_mma();
-        if (t < 32) {  // warp-uniform issue: UMMA operands stay in uniform registers
-          tc_fence_after();
-          if (elect_one()) {
-            umma_kblock(tmem + (i & 1) * CZ, smem_u32(sA) + kb * 16384, smem_u32(sBs), umma_idesc_f16(128, CZ), kb > 0);
-            umma_commit(&ring_free[slot]);
-            if (kb == KBS - 1) umma_commit(&acc_full[i & 1]);
-          }
-          __syncwarp();
-        }
+        fence_proxy_async_smem();
+        mbar_arrive(&full[slot]);
       }
     }
-    // (4) epilogue of row i-1 while the UMMAs of row i drain
-    if (i > i0) {
-      mbar_wait(&acc_full[(i - 1) & 1], ((i - 1 - i0) >> 1) & 1);
-      tc_fence_after();
-      epilogue(i - 1, res);
+  } else if (warp < 12) {
+    // ------------------------------------------------------------------ epilogue
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 200;");
+    const int q4 = warp & 3;  // TMEM lane quarter
+    const int j0 = jt * 128 + q4 * 32;
+    const int j = j0 + lane;
+    const int rows_valid = N - j0;
+    const uint32_t tm_lane = tmem + (static_cast<uint32_t>(q4 * 32) << 16);
+    uint8_t* slice = sSl + q4 * 4096;
+    float ujb[CZ];  // bias - u_j
+    if (j < N) {
+      const float4* up = reinterpret_cast<const float4*>(u + ((long long)b * N + j) * CZ);
+#pragma unroll
+      for (int c = 0; c < CZ / 4; ++c) {
+        const float4 v = __ldg(up + c);
+        ujb[c * 4] = sBias[c * 4] - v.x;
+        ujb[c * 4 + 1] = sBias[c * 4 + 1] - v.y;
+        ujb[c * 4 + 2] = sBias[c * 4 + 2] - v.z;
+        ujb[c * 4 + 3] = sBias[c * 4 + 3] - v.w;
+      }
+    } else {
+#pragma unroll
+      for (int c = 0; c < CZ; ++c) ujb[c] = 0.f;
     }
-    tc_fence_before();
+    for (int i = i0; i < i1; ++i) {
+      const long long rowoff = (((long long)b * N + i) * N + j0) * CZ;  // first of this warp's 32 pair rows
+      uint4 res[RP][8];
+      if (residual) {
+#pragma unroll
+        for (int p = 0; p < RP; ++p) warp_load_rows128(slice, lane, res[p], pair + rowoff + p * 32, CZ * 4, rows_valid);
+      } else {
+#pragma unroll
+        for (int p = 0; p < RP; ++p)
+#pragma unroll
+          for (int c = 0; c < 8; ++c) res[p][c] = make_uint4(0, 0, 0, 0);
+      }
+      mbar_wait(&acc_full[i & 1], ((i - i0) >> 1) & 1);
+      tc_fence_after();
+      const float* ui = sUi + (i & 3) * CZ;
+#pragma unroll
+      for (int p = 0; p < RP; ++p) {
+        uint32_t acc[32];
+        tmem_ld32(tm_lane + (i & 1) * CZ + p * 32, acc);
+        tmem_ld_wait();
+        if (p == RP - 1) {  // all TMEM reads of this accumulator are done: hand it back
+          tc_fence_before();
+          mbar_arrive(&acc_empty[i & 1]);
+        }
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const float4 uv = *reinterpret_cast<const float4*>(ui + p * 32 + c * 4);
+          uint4& r = res[p][c];
+          r.x = __float_as_uint(__uint_as_float(r.x) + __uint_as_float(acc[c * 4 + 0]) + uv.x + ujb[p * 32 + c * 4 + 0]);
+          r.y = __float_as_uint(__uint_as_float(r.y) + __uint_as_float(acc[c * 4 + 1]) + uv.y + ujb[p * 32 + c * 4 + 1]);
+          r.z = __float_as_uint(__uint_as_float(r.z) + __uint_as_float(acc[c * 4 + 2]) + uv.z + ujb[p * 32 + c * 4 + 2]);
+          r.w = __float_as_uint(__uint_as_float(r.w) + __uint_as_float(acc[c * 4 + 3]) + uv.w + ujb[p * 32 + c * 4 + 3]);
+        }
+        warp_store_rows128(slice, lane, res[p], dst + rowoff + p * 32, CZ * 4, rows_valid);
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ TMA + UMMA warp (12); 13-15 idle
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");  // 8 x 136 + 4 x 200 + 4 x 24 <= 16 x 128
+    if (warp == 12) {
+    if (elect_one()) {
+      mbar_expect_tx(bar_a, KBS * 16384);
+      for (int kb = 0; kb < KBS; ++kb) tma_load_3d(sA + kb * 16384, &map_x, bar_a, kb * 64, jt * 128, b);
+    }
+    __syncwarp();
+    mbar_wait(bar_a, 0);
+    uint32_t ring_it = 0;
+    for (int i = i0; i < i1; ++i) {
+      const int buf = i & 1;
+      if (i - i0 >= 2) mbar_wait(&acc_empty[buf], (((i - i0) >> 1) - 1) & 1);  // epilogue of row i-2 drained it
+      for (int kb = 0; kb < KBS; ++kb, ++ring_it) {
+        const uint32_t slot = ring_it % RB;
+        mbar_wait(&full[slot], (ring_it / RB) & 1);
+        tc_fence_after();
+        if (elect_one()) {
+          umma_kblock(tmem + buf * CZ, smem_u32(sA) + kb * 16384, smem_u32(sB) + slot * (CZ * 128), umma_idesc_f16(128, CZ),
+                      kb > 0);
+          umma_commit(&empty[slot]);
+          if (kb == KBS - 1) umma_commit(&acc_full[buf]);
+        }
+        __syncwarp();
+      }
+    }
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -204,13 +228,13 @@ outer_linear_kernel(const __grid_constant__ CUtensorMap map_x, const float* pair
 
 template <int CZ, int KBS>
 static int launch_outer_linear(const CUtensorMap& mx, dim3 grid, const float* pair, float* dst, int residual,
-                               const float* xn32, const __half* w1, const float* u, const float* bias, int N, int ilen,
+                               const __half* xn16, const __half* w1, const float* u, const float* bias, int N, int ilen,
                                cudaStream_t s) {
-  constexpr int smem = 1024 + KBS * 16384 + 4 * CZ * 128 + (KBS * 64 + 3 * CZ) * 4 + 128;
+  constexpr int smem = 1024 + KBS * 16384 + 4 * CZ * 128 + 4 * 4096 + (2 * KBS * 64 + 5 * CZ) * 4 + 256;
   static_assert(smem <= 227 * 1024, "outer_linear shared memory budget");
   auto kern = outer_linear_kernel<CZ, KBS>;
   PRD_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  kern<<<grid, 256, smem, s>>>(mx, pair, dst, residual, xn32, w1, u, bias, N, ilen);
+  kern<<<grid, kOlThreads, smem, s>>>(mx, pair, dst, residual, xn16, w1, u, bias, N, ilen);
   PRD_LAUNCHED();
   return 0;
 }
@@ -227,17 +251,30 @@ int outer_linear(const PairDims& d, int CS, const float* pair, float* dst, int r
   t.box[0] = 64; t.box[1] = 128; t.box[2] = 1; t.box[3] = 1;
   if (make_tensor_map(&mx, xn16, 2, 3, t, true)) return 1;
   const int jtiles = (N + 127) / 128;
-  // enough CTAs for a few waves; every CTA re-uses its A tile and its W1 registers for `ilen` rows
-  int ichunks = (4 * kNumSMs + jtiles * d.B - 1) / (jtiles * d.B);
-  if (ichunks > N) ichunks = N;
-  if (ichunks < 1) ichunks = 1;
-  const int ilen = (N + ichunks - 1) / ichunks;
+  // every CTA re-uses its A tile and its W1 registers for `ilen` rows; one CTA per SM, so pick the number of
+  // i-chunks that fills whole waves (least idle SM time in the last wave), at least 8 rows per CTA
+  int ichunks = 1;
+  {
+    const long long per = (long long)jtiles * d.B;
+    double best = 1e30;
+    for (int c = 1; c <= (N + 7) / 8; ++c) {
+      const int len = (N + c - 1) / c;
+      const long long ctas = per * ((N + len - 1) / len);
+      const long long waves = (ctas + kNumSMs - 1) / kNumSMs;
+      const double cost = (double)waves * (len + 3.0);  // rows per wave + ~3 rows of prologue (A tile, W1)
+      if (cost < best - 1e-9) {
+        best = cost;
+        ichunks = c;
+      }
+    }
+  }
+  int ilen = (N + ichunks - 1) / ichunks;
   ichunks = (N + ilen - 1) / ilen;
   dim3 grid(jtiles, ichunks, d.B);
-  if (d.CZ == 64 && CS == 512) return launch_outer_linear<64, 8>(mx, grid, pair, dst, residual, xn32, w1, u, bias, N, ilen, s);
-  if (d.CZ == 64 && CS == 256) return launch_outer_linear<64, 4>(mx, grid, pair, dst, residual, xn32, w1, u, bias, N, ilen, s);
-  if (d.CZ == 32 && CS == 512) return launch_outer_linear<32, 8>(mx, grid, pair, dst, residual, xn32, w1, u, bias, N, ilen, s);
-  return launch_outer_linear<32, 4>(mx, grid, pair, dst, residual, xn32, w1, u, bias, N, ilen, s);
+  if (d.CZ == 64 && CS == 512) return launch_outer_linear<64, 8>(mx, grid, pair, dst, residual, xn16, w1, u, bias, N, ilen, s);
+  if (d.CZ == 64 && CS == 256) return launch_outer_linear<64, 4>(mx, grid, pair, dst, residual, xn16, w1, u, bias, N, ilen, s);
+  if (d.CZ == 32 && CS == 512) return launch_outer_linear<32, 8>(mx, grid, pair, dst, residual, xn16, w1, u, bias, N, ilen, s);
+  return launch_outer_linear<32, 4>(mx, grid, pair, dst, residual, xn16, w1, u, bias, N, ilen, s);
 }
 
 // =========================================================================================
