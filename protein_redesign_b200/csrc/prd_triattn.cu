@@ -38,7 +38,8 @@
 namespace prd {
 
 constexpr int kFlashThreads = 384;
-constexpr bool kFlashPolyHalf = true;  // every other column pair: exp2 on the FMA pipe (exp2_poly2)
+constexpr bool kFlashPolyHalf = true;  // every fourth column pair: exp2 on the FMA pipe (exp2_poly2); measured at B=8 N=512:
+                                       // none 1.86 ms, 1/8 1.81, 1/4 1.77 -> shipped, 1/2 1.90 (instruction bound)
 constexpr bool kFlashToken = false;  // strict per-scheduler MUFU ping-pong between the two groups; measured slower (2.32 vs 1.78 ms):
                                      // a lone warp in its exp2 pass is latency bound, two overlapping passes fill each other's bubbles
 constexpr float kLog2e = 1.4426950408889634f;
@@ -71,8 +72,8 @@ __device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) {
 // exp2 of two non-positive arguments on the FMA pipe (no MUFU): Cody-Waite split x = n + f, |f| <= 1/2,
 // degree-3 minimax polynomial for 2^f (max relative error 7.5e-5, well below the fp16 rounding of P that
 // follows), n added into the exponent field.  Arguments are clamped at -24 (2^-24 is below fp16 range).
-// Half of the exponentials of the all-valid path go through here: the MUFU pipe (16 exp2/clk/SM) is the
-// binding unit of this kernel, the FMA pipe has room.
+// A quarter of the exponentials of the all-valid path go through here: the MUFU pipe (16 exp2/clk/SM) is the
+// nominal bound of this kernel, the FMA pipe has room.
 __device__ __forceinline__ uint64_t exp2_poly2(uint64_t x) {
   float a, b;
   unpack_f2(x, a, b);
@@ -258,7 +259,7 @@ __device__ __forceinline__ float flash_row_exp(uint32_t tS, const float2* keyp, 
       FLASH_TRACE(40 + c);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        if (kFlashPolyHalf && (j & 1)) {
+        if (kFlashPolyHalf && (j & 3) == 3) {
           if (c + 1 < 8) x[(c + 1) % 3][j] = fadd2v(x[(c + 1) % 3][j], nm2);
           x[c % 3][j] = exp2_poly2(x[c % 3][j]);
         } else {
