@@ -231,9 +231,266 @@ static int launch_pair_transition(const PairDims& d, const float* pair, float* d
   return 0;
 }
 
+// -----------------------------------------------------------------------------------------
+// pair_dim 64 / hidden 256: warp-specialised pipeline (the kernel above serialises LayerNorm, two GEMMs and two
+// epilogues per tile on four warps).  Persistent CTA, one per SM, 16 warps:
+//   warps 0-3    row warps: thread = pair row.  Coalesced row load, LayerNorm -> A tile (2-slot ring); later
+//                the output epilogue of the same tile (accumulator + b2 + residual from registers), full-line
+//                stores.  LayerNorm of tile i+1 is done BEFORE the output of tile i, so the tensor core
+//                never waits for it.
+//   warps 4-11   mid warps: hidden quarter q (64 columns): D1_q + b1 -> ReLU -> fp16 -> H tile (2-slot ring);
+//                warps 4-7 take the even quarters, 8-11 the odd ones
+//   warps 12/13  UMMA issue of the first / second GEMM (M1_q: D1[q&1] = A W1_q^T, M2_q: D2 += H_q W2_q^T, hi and lo
+//                weight halves side by side along N), all hand-offs through mbarriers
+//   warps 14-15  idle (donate registers)
+// TMEM: D1 quarters 2 x 128 columns, D2 2 x 128 columns (hi | lo weight halves side by side).
+// -----------------------------------------------------------------------------------------
+namespace {
+constexpr int kPtThreads = 512;
+struct PtSmem {
+  static constexpr int kW1 = 0;                        // hi, lo: 2 x [256 x 64] = 64 KB
+  static constexpr int kW2 = kW1 + 2 * 256 * 128;      // hi, lo: 2 x 4 K-blocks of [64 x 64] = 64 KB
+  static constexpr int kA = kW2 + 2 * 4 * 64 * 128;    // 2 x 16 KB
+  static constexpr int kH = kA + 2 * 16384;            // 2 x 16 KB
+  static constexpr int kSl = kH + 2 * 16384;           // 4 row warps x 4 KB
+  static constexpr int kBias = kSl + 4 * 4096;         // b1[256], b2[64]
+  static constexpr int kBars = kBias + 320 * 4;
+  static constexpr int kTotal = kBars + 16 * 8 + 16 + 1024;
+};
+}  // namespace
+
+__global__ void __launch_bounds__(kPtThreads, 1)
+pair_transition_ws_kernel(const float* pair, float* dst, int residual, long long R, const __half* __restrict__ w1,
+                          const float* __restrict__ b1, const __half* __restrict__ w2, const float* __restrict__ b2) {
+  constexpr int CZ = 64, HID = 256;
+  extern __shared__ uint8_t raw[];
+  using L = PtSmem;
+  uint8_t* sm = smem_align1024(raw);
+  uint8_t* sW1 = sm + L::kW1;
+  uint8_t* sW2 = sm + L::kW2;
+  uint8_t* sA = sm + L::kA;
+  uint8_t* sH = sm + L::kH;
+  float* sB1 = reinterpret_cast<float*>(sm + L::kBias);
+  float* sB2 = sB1 + HID;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sm + L::kBars);
+  uint64_t* a_full = bars;        // [2] 128 row-thread arrivals
+  uint64_t* a_empty = bars + 2;   // [2] UMMA commit
+  uint64_t* d1_full = bars + 4;   // [2] UMMA commit
+  uint64_t* d1_empty = bars + 6;  // [2] 128 mid-thread arrivals (mid set Q&1)
+  uint64_t* h_full = bars + 8;    // [2] 128 mid-thread arrivals
+  uint64_t* h_empty = bars + 10;  // [2] UMMA commit
+  uint64_t* d2_full = bars + 12;  // [2] UMMA commit
+  uint64_t* d2_empty = bars + 14; // [2] 128 row-thread arrivals
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&a_full[i], 128);
+      mbar_init(&a_empty[i], 1);
+      mbar_init(&d1_full[i], 1);
+      mbar_init(&d1_empty[i], 128);
+      mbar_init(&h_full[i], 128);
+      mbar_init(&h_empty[i], 1);
+      mbar_init(&d2_full[i], 1);
+      mbar_init(&d2_empty[i], 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc(tmem_slot, 512);
+  // B operands of 128 rows per hidden quarter q: rows [0,64) = hi weights, [64,128) = lo weights, so one UMMA
+  // (N = 128) computes both halves; the epilogues add the two 64-column accumulator halves
+  for (int q = 0; q < 4; ++q) {
+    load_weight_kblocks(sW1 + q * 16384, w1 + q * 64 * CZ, 64, CZ, CZ, threadIdx.x, kPtThreads);
+    load_weight_kblocks(sW1 + q * 16384 + 8192, w1 + HID * CZ + q * 64 * CZ, 64, CZ, CZ, threadIdx.x, kPtThreads);
+    load_weight_kblocks(sW2 + q * 16384, w2 + q * 64, CZ, 64, HID, threadIdx.x, kPtThreads);
+    load_weight_kblocks(sW2 + q * 16384 + 8192, w2 + CZ * HID + q * 64, CZ, 64, HID, threadIdx.x, kPtThreads);
+  }
+  for (int i = threadIdx.x; i < HID; i += kPtThreads) sB1[i] = b1[i];
+  for (int i = threadIdx.x; i < CZ; i += kPtThreads) sB2[i] = b2[i];
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const long long num_tiles = (R + kTileRows - 1) / kTileRows;
+  const int my_tiles = (blockIdx.x < num_tiles) ? static_cast<int>((num_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0;
+
+  if (warp < 4) {
+    // ------------------------------------------------------------------ row warps
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 200;");
+    const int t = threadIdx.x;  // row of the tile = TMEM lane
+    uint8_t* slice = sm + L::kSl + warp * 4096;
+    const uint32_t tm_lane = tmem + (static_cast<uint32_t>(warp * 32) << 16);
+    float xc[CZ], xn[CZ];
+    auto load_ln = [&](int il, float (&x)[CZ]) {  // rows of local tile il -> x (kept for the residual), LN -> A slot
+      const long long row0 = ((long long)blockIdx.x + (long long)il * gridDim.x) * kTileRows + warp * 32;
+      const long long left = R - row0;
+      const int rows_valid = left > 32 ? 32 : (left < 0 ? 0 : static_cast<int>(left));
+#pragma unroll
+      for (int p = 0; p < 2; ++p) {
+        uint4 v[8];
+        warp_load_rows128(slice, lane, v, pair + row0 * CZ + p * 32, CZ * 4, rows_valid);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          x[p * 32 + 4 * c + 0] = __uint_as_float(v[c].x);
+          x[p * 32 + 4 * c + 1] = __uint_as_float(v[c].y);
+          x[p * 32 + 4 * c + 2] = __uint_as_float(v[c].z);
+          x[p * 32 + 4 * c + 3] = __uint_as_float(v[c].w);
+        }
+      }
+      // LayerNorm statistics (x itself is kept for the residual)
+      float s4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int i = 0; i < CZ; ++i) s4[i & 3] += x[i];
+      const float mean = ((s4[0] + s4[1]) + (s4[2] + s4[3])) * (1.0f / CZ);
+      float v4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int i = 0; i < CZ; ++i) {
+        const float dlt = x[i] - mean;
+        v4[i & 3] = fmaf(dlt, dlt, v4[i & 3]);
+      }
+      const float rstd = rsqrtf(((v4[0] + v4[1]) + (v4[2] + v4[3])) * (1.0f / CZ) + kLnEps);
+      const float nmr = -mean * rstd;
+      if (il >= 2) mbar_wait(&a_empty[il & 1], ((il >> 1) - 1) & 1);
+      uint8_t* a_tile = sA + (il & 1) * 16384;
+#pragma unroll
+      for (int ch = 0; ch < 8; ++ch) {
+        uint4 o;
+        o.x = pack_half2(fmaf(x[ch * 8 + 0], rstd, nmr), fmaf(x[ch * 8 + 1], rstd, nmr));
+        o.y = pack_half2(fmaf(x[ch * 8 + 2], rstd, nmr), fmaf(x[ch * 8 + 3], rstd, nmr));
+        o.z = pack_half2(fmaf(x[ch * 8 + 4], rstd, nmr), fmaf(x[ch * 8 + 5], rstd, nmr));
+        o.w = pack_half2(fmaf(x[ch * 8 + 6], rstd, nmr), fmaf(x[ch * 8 + 7], rstd, nmr));
+        *reinterpret_cast<uint4*>(a_tile + sw128_offset(t, ch)) = o;
+      }
+      fence_proxy_async_smem();
+      mbar_arrive(&a_full[il & 1]);
+    };
+    if (my_tiles > 0) load_ln(0, xc);
+    for (int il = 0; il < my_tiles; ++il) {
+      if (il + 1 < my_tiles) load_ln(il + 1, xn);
+      // output epilogue of tile il
+      const long long row0 = ((long long)blockIdx.x + (long long)il * gridDim.x) * kTileRows + warp * 32;
+      const long long left = R - row0;
+      const int rows_valid = left > 32 ? 32 : (left < 0 ? 0 : static_cast<int>(left));
+      mbar_wait(&d2_full[il & 1], (il >> 1) & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int p = 0; p < 2; ++p) {
+        uint32_t acc[32], acl[32];
+        tmem_ld32(tm_lane + 256 + (il & 1) * 128 + p * 32, acc);
+        tmem_ld32(tm_lane + 256 + (il & 1) * 128 + 64 + p * 32, acl);
+        tmem_ld_wait();
+        if (p == 1) {
+          tc_fence_before();
+          mbar_arrive(&d2_empty[il & 1]);
+        }
+        uint4 o[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          float v[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            v[e] = (__uint_as_float(acc[4 * c + e]) + __uint_as_float(acl[4 * c + e])) + sB2[p * 32 + 4 * c + e];
+            if (residual) v[e] += xc[p * 32 + 4 * c + e];
+          }
+          o[c] = make_uint4(__float_as_uint(v[0]), __float_as_uint(v[1]), __float_as_uint(v[2]), __float_as_uint(v[3]));
+        }
+        warp_store_rows128(slice, lane, o, dst + row0 * CZ + p * 32, CZ * 4, rows_valid);
+      }
+#pragma unroll
+      for (int i = 0; i < CZ; ++i) xc[i] = xn[i];
+    }
+  } else if (warp < 12) {
+    // ------------------------------------------------------------------ mid warps: set 0 (warps 4-7) takes the even
+    // hidden quarters, set 1 (warps 8-11) the odd ones, so two quarters are in flight at once
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 112;");
+    const int m = warp - 4;
+    const int t = (m & 3) * 32 + lane;  // tile row = TMEM lane
+    const int set = m >> 2;
+    const uint32_t tm_lane = tmem + (static_cast<uint32_t>((m & 3) * 32) << 16);
+    for (int il = 0; il < my_tiles; ++il) {
+#pragma unroll 1
+      for (int qq = 0; qq < 2; ++qq) {
+        const int q = 2 * qq + set, Q = 4 * il + q;  // Q & 1 == set
+        mbar_wait(&d1_full[set], (Q >> 1) & 1);
+        tc_fence_after();
+        if (Q >= 2) mbar_wait(&h_empty[set], ((Q >> 1) - 1) & 1);
+#pragma unroll 1
+        for (int hf = 0; hf < 2; ++hf) {
+          uint32_t acc[32], acl[32];
+          tmem_ld32(tm_lane + set * 128 + hf * 32, acc);
+          tmem_ld32(tm_lane + set * 128 + 64 + hf * 32, acl);
+          tmem_ld_wait();
+          if (hf == 1) {
+            tc_fence_before();
+            mbar_arrive(&d1_empty[set]);
+          }
+          float v[32];
+          const float* bq = sB1 + q * 64 + hf * 32;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = fmaxf((__uint_as_float(acc[j]) + __uint_as_float(acl[j])) + bq[j], 0.f);
+          store_a_cols32(sH + set * 16384, t, hf * 32, v);
+        }
+        fence_proxy_async_smem();
+        mbar_arrive(&h_full[set]);
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ UMMA warps: 12 issues the first GEMM (gated by
+    // A tiles and free D1 buffers), 13 the second (gated by H tiles and free D2 buffers); 14-15 idle
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+    const uint32_t idesc = umma_idesc_f16(128, 128);
+    if (warp == 12) {
+      int Q = 0;
+      for (int il = 0; il < my_tiles; ++il) {
+        mbar_wait(&a_full[il & 1], (il >> 1) & 1);
+        for (int q = 0; q < 4; ++q, ++Q) {
+          if (Q >= 2) mbar_wait(&d1_empty[Q & 1], ((Q >> 1) - 1) & 1);
+          tc_fence_after();
+          if (elect_one()) {
+            umma_kblock(tmem + (Q & 1) * 128, smem_u32(sA) + (il & 1) * 16384, smem_u32(sW1) + q * 16384, idesc, false);
+            umma_commit(&d1_full[Q & 1]);
+            if (q == 3) umma_commit(&a_empty[il & 1]);
+          }
+          __syncwarp();
+        }
+      }
+    } else if (warp == 13) {
+      int Q = 0;
+      for (int il = 0; il < my_tiles; ++il) {
+        if (il >= 2) mbar_wait(&d2_empty[il & 1], ((il >> 1) - 1) & 1);
+        for (int q = 0; q < 4; ++q, ++Q) {
+          mbar_wait(&h_full[Q & 1], (Q >> 1) & 1);
+          tc_fence_after();
+          if (elect_one()) {
+            umma_kblock(tmem + 256 + (il & 1) * 128, smem_u32(sH) + (Q & 1) * 16384, smem_u32(sW2) + q * 16384, idesc, q > 0);
+            umma_commit(&h_empty[Q & 1]);
+            if (q == 3) umma_commit(&d2_full[il & 1]);
+          }
+          __syncwarp();
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+static int launch_pair_transition_ws(const PairDims& d, const float* pair, float* dst, int residual, const __half* w1,
+                                     const float* b1, const __half* w2, const float* b2, cudaStream_t s) {
+  static_assert(PtSmem::kTotal <= 227 * 1024, "pair_fc shared memory budget");
+  if (set_smem(pair_transition_ws_kernel, PtSmem::kTotal)) return 1;
+  const long long R = (long long)d.B * d.N * d.N;
+  const long long tiles = (R + kTileRows - 1) / kTileRows;
+  pair_transition_ws_kernel<<<grid_for(tiles, 1), kPtThreads, PtSmem::kTotal, s>>>(pair, dst, residual, R, w1, b1, w2, b2);
+  PRD_LAUNCHED();
+  return 0;
+}
+
 int pair_transition(const PairDims& d, const float* pair, float* dst, int residual, const __half* w1, const float* b1,
                     const __half* w2, const float* b2, int hidden, cudaStream_t s) {
-  if (d.CZ == 64 && hidden == 256) return launch_pair_transition<64, 256>(d, pair, dst, residual, w1, b1, w2, b2, s);
+  if (d.CZ == 64 && hidden == 256) return launch_pair_transition_ws(d, pair, dst, residual, w1, b1, w2, b2, s);
   if (d.CZ == 32 && hidden == 128) return launch_pair_transition<32, 128>(d, pair, dst, residual, w1, b1, w2, b2, s);
   set_error("pair_transition: unsupported pair_dim %d / hidden %d (built: 64/256, 32/128)", d.CZ, hidden);
   return 1;
