@@ -327,10 +327,18 @@ CASES = {
     "trimul_outgoing": lambda: case_trimul(mode="outgoing"),
     "trimul_incoming": lambda: case_trimul(mode="incoming"),
     "trimul_readme": lambda: case_trimul(syn.README, 2, 40, "incoming"),
+    # N = 140: plane_ld = 192, the second 64-column half of the second k-tile lies outside the padded plane row
+    "trimul_n140": lambda: case_trimul(B=1, N=140, mode="incoming", pad=7),
+    "trimul_n300": lambda: case_trimul(B=1, N=300, mode="outgoing", pad=11),
     "triattn_starting": lambda: case_triattn(mode="starting"),
     "triattn_ending": lambda: case_triattn(mode="ending"),
     "triattn_n200": lambda: case_triattn(B=1, N=200, mode="ending", pad=9),
     "triattn_readme": lambda: case_triattn(syn.README, 2, 40, "starting"),
+    # N = 140: ragged 16-byte vectors in the transposed v tile, two query tiles, padded last key tile
+    "triattn_n140": lambda: case_triattn(B=1, N=140, mode="starting", pad=6),
+    "triattn_n300": lambda: case_triattn(B=1, N=300, mode="ending", pad=13),
+    "pair_transition_n140": lambda: case_pair_transition(syn.PAPER, 1, 140),
+    "outer_linear_n300": lambda: case_outer_linear(syn.PAPER, 1, 300),
     "outer_linear": lambda: case_outer_linear(),
     "outer_linear_readme": lambda: case_outer_linear(syn.README, 2, 140),
     "single_attention": lambda: case_single_attention(),
