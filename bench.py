@@ -325,30 +325,45 @@ def profile_dominant(lib, cfg, B, N, dev, mask, pair):
 
     P = 4.0 * B * N * N * cfg.pair_dim  # bytes of one fp32 pair tensor
     out = []
+    ncu = {}
+    tpath = os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")
+    if os.path.exists(tpath) and (B, N) == (BATCH, N_TOKENS):
+        with open(tpath) as f:
+            ncu = json.load(f)
+
+    def dram(key):  # dram bytes per launch from the committed ncu --set full capture (None at other sizes)
+        e = ncu.get(key)
+        return (e["read_bytes"] + e["write_bytes"]) if e else None
+
     # triangle-multiplication contraction: 2*B*N^3*c_z flop; a, b fp16 planes in, x fp32 planes out
     ms = time_kernel("trimul_gemm", None)
     flops = 2.0 * B * N ** 3 * cfg.pair_dim
     out.append({"kernel": "gemm_f16_kernel (tri-mul contraction)", "bound": "tensor", "achieved": flops / ms / 1e9,
-                "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": flops / ms / 1e9 / peaks["tflops"], "traffic": None,
+                "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": flops / ms / 1e9 / peaks["tflops"],
+                "traffic": dram("gemm_f16_kernel<256,4> (tri-mul contraction)"),
                 "ms_per_launch": ms, "hbm_floor_ms": (P + P) / peaks["hbm_gbs"] / 1e6,
                 "note": "HBM floor: 0.5 P (a) + 0.5 P (b) + 1 P (x fp32) = 2 P"})
     # pair-bias stream: reads P, writes P/16
     ms = time_kernel("pair_bias", pair)
     nbytes = P + P * 4 / cfg.pair_dim
     out.append({"kernel": "pair_bias_kernel (LN + c_z->4 bias stream)", "bound": "hbm", "achieved": nbytes / ms / 1e6,
-                "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": nbytes / ms / 1e6 / peaks["hbm_gbs"], "traffic": None,
+                "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": nbytes / ms / 1e6 / peaks["hbm_gbs"],
+                "traffic": dram("pair_bias_kernel"),
                 "ms_per_launch": ms})
     # triangle attention core (dominant): QK^T + PV flops; co-limited by 4*B*N^3 exp2 on the MUFU pipe
     ms = time_kernel("triattn_flash", mask)
     flops = 2.0 * 2.0 * B * N * cfg.num_heads * N * N * cfg.head_dim
     n_exp = float(B) * N * cfg.num_heads * N * N
     mufu_floor_ms = n_exp / (148 * 16 * 1.965e9) * 1e3
+    traffic = dram("triattn_flash_kernel")
     roof = {"kernel": "triattn_flash_kernel", "bound": "tensor", "achieved": flops / ms / 1e9, "peak": peaks["tflops"],
-            "unit": "TFLOP/s", "frac": flops / ms / 1e9 / peaks["tflops"], "traffic": None,
+            "unit": "TFLOP/s", "frac": flops / ms / 1e9 / peaks["tflops"], "traffic": traffic,
             "peak_source": peaks["source"], "ms_per_launch": ms, "mufu_floor_ms": mufu_floor_ms,
             "mufu_frac": mufu_floor_ms / ms,
-            "note": "K=16 attention: the binding unit is the MUFU exp2 pipe (%.2e exp2 per launch at 16/clk/SM), "
-                    "not the tensor pipe" % n_exp,
+            "hbm_achieved_gbs": (traffic / ms / 1e6) if traffic else None,
+            "note": "K=16 attention (head dim 16): 275 GFLOP on the tensor pipe against %.2e exp2 per launch; the binding "
+                    "unit is the exp2 path (MUFU 16/clk/SM, a quarter of the exp2 moved to an FMA-pipe polynomial), "
+                    "not the tensor pipe; mufu_frac = all-MUFU floor / measured (profiles/r01_flash_variants.md)" % n_exp,
             "others": out}
     return roof
 
