@@ -212,75 +212,51 @@ template <bool kAllValid, bool kTrace>
 __device__ __forceinline__ float flash_row_exp(uint32_t tS, const float2* keyp, float mx, uint8_t* sP, int t,
                                                uint64_t* bar_pr, uint32_t (&b0)[16], long long* tr, int& tr_n) {
   if (kAllValid) {
+    // straightforward per-chunk code (ptxas schedules it better than a hand-ordered volatile pipeline: 154 vs 195
+    // cycles per 16-column chunk for a lone warp, tools/micro/warps_scaling.cu); the TMEM load of chunk c+1 is in
+    // flight while chunk c is processed
     const uint64_t nm2 = pack_f2(-mx, -mx);
     uint64_t racc[4] = {0ull, 0ull, 0ull, 0ull};
     const uint32_t sP_row = smem_u32(sP) + t * 128;
-    uint32_t b1[16], b2[16];
-    uint64_t x[3][8];
-    uint32_t ph[2][8];
-    constexpr int kLag = 3;
-    auto pack_chunk = [&](int bi, const uint32_t(&s)[16]) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) x[bi][j] = pack_f2(__uint_as_float(s[2 * j]), __uint_as_float(s[2 * j + 1]));
-    };
-    auto consume = [&](int c, int i) {  // stage C of pair i of chunk c
-      float a, b;
-      unpack_f2(x[c % 3][i], a, b);
-      racc[i & 3] = fadd2v(racc[i & 3], x[c % 3][i]);
-      ph[c & 1][i] = cvt_f16x2v(a, b);
-      if ((i & 3) == 3) {
-        const int k0 = c * 16;
-        sts128v(sP_row + (k0 >> 6) * (kTileRows * 128) + (((((k0 & 63) >> 3) + (i >> 2)) ^ (t & 7)) << 4), ph[c & 1][i - 3],
-                ph[c & 1][i - 2], ph[c & 1][i - 1], ph[c & 1][i]);
-        if ((c == 3 || c == 7) && i == 7) {
-          tc_fence_before();  // all TMEM reads of this half of the S buffer are done (P.V overwrites columns 0-15)
-          fence_proxy_async_smem();
-          mbar_arrive(&bar_pr[c >> 2]);
-        }
-      }
-    };
-    tmem_ld_wait16(b0);
-    tmem_ld16(tS + 16, b1);
-    pack_chunk(0, b0);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) x[0][j] = fadd2v(x[0][j], nm2);
-#pragma unroll
-    for (int c = 0; c < 8; ++c) {
-      // chunk c+1 has landed; start the load of chunk c+2 (its buffer held chunk c-1, whose last kLag pairs are
-      // consumed just below: the register dependency orders the load behind them)
-      if (c + 1 < 8) {
-        if (c % 3 == 0) tmem_ld_wait16(b1);
-        if (c % 3 == 1) tmem_ld_wait16(b2);
-        if (c % 3 == 2) tmem_ld_wait16(b0);
-        if (c % 3 == 0) pack_chunk(1, b1);
-        if (c % 3 == 1) pack_chunk(2, b2);
-        if (c % 3 == 2) pack_chunk(0, b0);
-      }
-      FLASH_TRACE(40 + c);
+    uint32_t b1[16];
+    auto chunk = [&](const uint32_t(&s)[16], int c) {
+      uint32_t ph[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
+        uint64_t y = fadd2(pack_f2(__uint_as_float(s[2 * j]), __uint_as_float(s[2 * j + 1])), nm2);
         if (kFlashPolyHalf && (j & 3) == 3) {
-          if (c + 1 < 8) x[(c + 1) % 3][j] = fadd2v(x[(c + 1) % 3][j], nm2);
-          x[c % 3][j] = exp2_poly2(x[c % 3][j]);
+          y = exp2_poly2(y);
         } else {
-          float a, b;
-          unpack_f2(x[c % 3][j], a, b);
-          a = ex2v(a);
-          if (c + 1 < 8) x[(c + 1) % 3][j] = fadd2v(x[(c + 1) % 3][j], nm2);
-          b = ex2v(b);
-          x[c % 3][j] = pack_f2(a, b);
+          float ya, yb;
+          unpack_f2(y, ya, yb);
+          y = pack_f2(ex2_approx(ya), ex2_approx(yb));
         }
-        if (j >= kLag) consume(c, j - kLag);
-        else if (c > 0) consume(c - 1, j + 8 - kLag);
-        if (j == kLag - 1 && c + 2 < 8) {
-          if (c % 3 == 0) tmem_ld16(tS + (c + 2) * 16, b2);
-          if (c % 3 == 1) tmem_ld16(tS + (c + 2) * 16, b0);
-          if (c % 3 == 2) tmem_ld16(tS + (c + 2) * 16, b1);
-        }
+        racc[j & 3] = fadd2(racc[j & 3], y);
+        float ya, yb;
+        unpack_f2(y, ya, yb);
+        ph[j] = cvt_f16x2(ya, yb);
+      }
+      const int k0 = c * 16;
+      const uint32_t blk = sP_row + (k0 >> 6) * (kTileRows * 128);
+#pragma unroll
+      for (int q = 0; q < 2; ++q)
+        sts128v(blk + (((((k0 & 63) >> 3) + q) ^ (t & 7)) << 4), ph[4 * q], ph[4 * q + 1], ph[4 * q + 2], ph[4 * q + 3]);
+    };
+#pragma unroll
+    for (int c = 0; c < 8; c += 2) {
+      FLASH_TRACE(40 + c);
+      tmem_ld_wait16(b0);
+      tmem_ld16(tS + (c + 1) * 16, b1);
+      chunk(b0, c);
+      tmem_ld_wait16(b1);
+      if (c + 2 < 8) tmem_ld16(tS + (c + 2) * 16, b0);
+      chunk(b1, c + 1);
+      if (c == 2 || c == 6) {
+        tc_fence_before();  // all TMEM reads of this half of the S buffer are done (P.V overwrites columns 0-15)
+        fence_proxy_async_smem();
+        mbar_arrive(&bar_pr[c >> 2]);
       }
     }
-#pragma unroll
-    for (int i = 8 - kLag; i < 8; ++i) consume(7, i);
     float r0, r1, r2, r3;
     unpack_f2(fadd2(racc[0], racc[1]), r0, r1);
     unpack_f2(fadd2(racc[2], racc[3]), r2, r3);
