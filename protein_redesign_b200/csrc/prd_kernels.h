@@ -54,6 +54,8 @@ int trimul_out(const PairDims& d, const float* pair, float* dst, int residual, c
 // vt: [B*N][64][plane_ld(N)] fp16.
 int triattn_proj(const PairDims& d, const float* pair, int mode, const __half* w_qkvg, const float* b_gate, __half* q,
                  __half* k, __half* g, __half* vt, cudaStream_t s);
+int triattn_flash_g4(const PairDims& d, const float* mask, const __half* q, const __half* k, const __half* g,
+                     const __half* vt, __half* og, cudaStream_t s);  // four softmax groups per SM (prd_triattn4.cu)
 int triattn_flash(const PairDims& d, const float* mask, const __half* q, const __half* k, const __half* g,
                   const __half* vt, __half* og, cudaStream_t s);
 int triattn_out(const PairDims& d, const float* pair, float* dst, int residual, int mode, const __half* og,

@@ -1,0 +1,475 @@
+// Triangle attention core, four-group variant (same math and interface as prd_triattn.cu).
+//
+// The exp2 stream of the softmax is the binding resource; with two softmax groups per SM (prd_triattn.cu) every
+// item leaves the MUFU / FMA pipes idle while its rows wait for UMMAs and barriers (~35 % of the time, phase
+// trace in profiles/r01_flash_variants.md).  TMEM (512 columns) caps the groups per SM, so this variant shrinks
+// the per-group footprint to 128 columns and runs FOUR groups = 16 softmax warps per SM:
+//   * item = (64-key tile, head): S = Q_h K_h^T, one UMMA M=128 N=64 K=16 into the group's single S buffer
+//     (columns [0,64)); O_h += P V_h accumulates in TMEM (columns [64,128)) over all key tiles, nothing is
+//     read back until the unit ends; P goes through one 16 KB shared-memory tile per group
+//   * lazy running max: m_h is fixed by the first key tile; a later tile keeps it while no score exceeds it by
+//     2^14 (P still fits fp16), otherwise the exact path rescales O_h in TMEM
+//   * the four groups of a CTA take the q-tiles 4 r .. 4 r + 3 of ONE sequence: K / V tiles are loaded once per CTA
+//     into 3-slot rings shared by the groups (full / empty mbarriers, empty counts one arrival per group)
+//   * warps 0-15 softmax (thread = query row), 16-19 UMMA issue (one per group), 20 K/V TMA, 21 Q TMA, 22-23 idle
+// A group's S / P.V latency (single buffers) is hidden by the other three groups.  Measured at B=8 N=512: 1.56 ms against
+// 1.63 ms of the two-group kernel (softmax warps still wait ~27 % of the time for S / P.V of their own group; staggering
+// the groups' start does not change it).  Used when the number of query tiles per sequence is a multiple of four.
+#include "prd_kernels.h"
+#include "prd_rowtile.cuh"
+#include "prd_flash_math.cuh"
+
+#include <stdlib.h>
+
+#include <algorithm>
+
+namespace prd {
+
+namespace {
+
+constexpr int kG4Threads = 768;
+constexpr int kG4Ring = 3;
+constexpr float kG4LazyBound = 14.0f;  // log2: P <= 2^14 < fp16 max
+
+// exp2 of one 16-column chunk of scores (already in registers): running max tracking, P = exp2(s - m) (MUFU on 3/4 of
+// the pairs, FMA-pipe polynomial on 1/4), packed row sum, fp16 pack, two 16-byte stores into the P row.
+template <bool kPoly>
+__device__ __forceinline__ void g4_chunk(const uint32_t (&s)[16], uint64_t nm2, uint64_t (&racc)[2], float (&rm)[2],
+                                         uint32_t sP_row, int t, int c) {
+  uint32_t ph[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float a = __uint_as_float(s[2 * j]), b = __uint_as_float(s[2 * j + 1]);
+    rm[j & 1] = fmax3(rm[j & 1], a, b);
+    uint64_t y = fadd2(pack_f2(a, b), nm2);
+    if (kPoly && (j & 3) == 3) {
+      y = exp2_poly2(y);
+    } else {
+      float ya, yb;
+      unpack_f2(y, ya, yb);
+      y = pack_f2(ex2_approx(ya), ex2_approx(yb));
+    }
+    racc[j & 1] = fadd2(racc[j & 1], y);
+    float ya, yb;
+    unpack_f2(y, ya, yb);
+    ph[j] = cvt_f16x2(ya, yb);
+  }
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sP_row + (((2 * c + q) ^ (t & 7)) << 4)), "r"(ph[4 * q]),
+                 "r"(ph[4 * q + 1]), "r"(ph[4 * q + 2]), "r"(ph[4 * q + 3])
+                 : "memory");
+  }
+}
+
+// scores of chunk c with the key mask applied (masked key -> fill value, non-existent key -> -inf)
+__device__ __forceinline__ void g4_mask_chunk(uint32_t (&s)[16], const float* keyp, int c) {
+#pragma unroll
+  for (int j = 0; j < 16; j += 4) {
+    const float4 e = *reinterpret_cast<const float4*>(keyp + c * 16 + j);
+    if (e.x != 0.f) s[j] = __float_as_uint(e.x);
+    if (e.y != 0.f) s[j + 1] = __float_as_uint(e.y);
+    if (e.z != 0.f) s[j + 2] = __float_as_uint(e.z);
+    if (e.w != 0.f) s[j + 3] = __float_as_uint(e.w);
+  }
+}
+
+struct G4Smem {
+  static constexpr int kK = 0;                         // kG4Ring x 8 KB
+  static constexpr int kV = kK + kG4Ring * 8192;       // kG4Ring x 8 KB
+  static constexpr int kQ = kV + kG4Ring * 8192;       // 4 x 16 KB
+  static constexpr int kP = kQ + 4 * 16384;            // 4 x 16 KB
+  static constexpr int kKey = kP + 4 * 16384;          // 4 x (nkt * 64 floats + nkt * 16 bytes), sized at run time
+};
+
+__global__ void __launch_bounds__(kG4Threads, 1)
+triattn_flash_g4_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
+                        const __grid_constant__ CUtensorMap map_vt, const float* __restrict__ mask,
+                        const __half* __restrict__ g_gate, __half* __restrict__ og, int N, int nseq) {
+  extern __shared__ uint8_t raw[];
+  const int nqt = (N + 127) / 128;  // query tiles per sequence
+  const int nkt = (N + 63) / 64;    // 64-key tiles per sequence
+  const int nrr = (nqt + 3) / 4;    // rounds of four query tiles per sequence
+  const int n_items = nkt * 4;
+  const int key_bytes = (nkt * 64 * 4 + nkt * 16 + 127) & ~127;
+  uint8_t* sm = smem_align1024(raw);
+  uint8_t* sK = sm + G4Smem::kK;
+  uint8_t* sV = sm + G4Smem::kV;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sm + G4Smem::kKey + 4 * key_bytes);
+  uint64_t* k_full = bars;               // [ring]
+  uint64_t* k_empty = bars + kG4Ring;    // [ring] one arrival per group
+  uint64_t* v_full = bars + 2 * kG4Ring;
+  uint64_t* v_empty = bars + 3 * kG4Ring;
+  uint64_t* gb = bars + 4 * kG4Ring;     // per group: 8 barriers
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gb + 4 * 8);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kG4Ring; ++i) {
+      mbar_init(&k_full[i], 1);
+      mbar_init(&k_empty[i], 4);
+      mbar_init(&v_full[i], 1);
+      mbar_init(&v_empty[i], 4);
+    }
+    for (int g = 0; g < 4; ++g) {
+      uint64_t* b = gb + g * 8;
+      mbar_init(&b[0], 1);    // q_full
+      mbar_init(&b[1], 1);    // q_empty (UMMA commit after the unit's last S)
+      mbar_init(&b[2], 1);    // s_full
+      mbar_init(&b[3], 128);  // pr: P written, S consumed
+      mbar_init(&b[4], 1);    // pv: P.V complete, P free
+      mbar_init(&b[5], 128);  // o_read: O region free
+    }
+    fence_barrier_init();
+    tma_prefetch_desc(&map_q);
+    tma_prefetch_desc(&map_k);
+    tma_prefetch_desc(&map_vt);
+  }
+  if (warp == 0) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+
+  // sequences of this CTA: seq = blockIdx.x + k * gridDim.x; round R = k * nrr + rr; group g takes q-tile 4 rr + g
+  const int nseq_cta = ((int)blockIdx.x < nseq) ? (nseq - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+  const int total_rounds = nseq_cta * nrr;
+
+  if (warp < 16) {
+    // ------------------------------------------------------------------ softmax group g
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 96;");
+    const int g = warp >> 2, w = warp & 3, t = threadIdx.x & 127;
+    uint64_t* b = gb + g * 8;
+    uint64_t* s_full = &b[2];
+    uint64_t* pr = &b[3];
+    uint64_t* pv = &b[4];
+    uint64_t* o_read = &b[5];
+    const uint32_t tmem = *tmem_slot + g * 128;
+    const uint32_t tS = tmem + (static_cast<uint32_t>(w * 32) << 16);
+    const uint32_t tO = tS + 64;
+    uint8_t* sP = sm + G4Smem::kP + g * 16384;
+    const uint32_t sP_row = smem_u32(sP) + t * 128;
+    float* sKey = reinterpret_cast<float*>(sm + G4Smem::kKey + g * key_bytes);
+    int* sWarpValid = reinterpret_cast<int*>(sKey + nkt * 64);  // [ceil(nkt/2)][4]
+    int G = 0;  // items of this group so far (barrier parities)
+    int R = 0;
+    for (int ks = 0; ks < nseq_cta; ++ks) {
+      const int seq = (int)blockIdx.x + ks * (int)gridDim.x;
+      bool table = false;
+      for (int rr = 0; rr < nrr; ++rr, ++R) {
+        const int qt = rr * 4 + g;
+        if (qt >= nqt) continue;  // (uniform per group) no unit in this round
+        if (!table) {
+          // key mask = m[b,seq_pos] * m[b,key]; one private copy per group, rebuilt once per sequence.  Every thread
+          // of the group is past its last read of the previous table (the unit epilogue waits for the last P.V).
+          table = true;
+          const int bb = seq / N;
+          const float ms = mask[seq];
+          for (int i = 0; i * 128 < nkt * 64; ++i) {
+            const int j = i * 128 + t;
+            float e = 0.f;
+            if (j >= N) e = -INFINITY;
+            else if (ms * mask[(long long)bb * N + j] < 0.5f) e = kMaskFillLog2;
+            if (j < nkt * 64) sKey[j] = e;
+            const bool all = __all_sync(0xffffffffu, e == 0.f);
+            if (lane == 0) sWarpValid[i * 4 + w] = all ? 1 : 0;
+          }
+          asm volatile("bar.sync %0, 128;" ::"r"(g + 1) : "memory");
+        }
+        float mrow[4], lrow[4];
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+          mrow[h] = -INFINITY;
+          lrow[h] = 0.f;
+        }
+        for (int kt = 0; kt < nkt; ++kt) {
+          const int2 wv = *reinterpret_cast<const int2*>(sWarpValid + (kt >> 1) * 4 + (kt & 1) * 2);
+          const bool all_valid = (wv.x & wv.y) != 0;
+          const float* keyp = sKey + kt * 64;
+#pragma unroll
+          for (int h = 0; h < 4; ++h, ++G) {
+            mbar_wait(s_full, G & 1);
+            tc_fence_after();
+            bool exact = (kt == 0) || !all_valid;
+            if (!exact) {
+              // fast item: running max kept; chunk c+1 is loaded from TMEM while chunk c is processed
+              const uint64_t nm2 = pack_f2(-mrow[h], -mrow[h]);
+              uint64_t racc[2] = {0ull, 0ull};
+              float rm[2] = {-INFINITY, -INFINITY};
+              uint32_t sa[16], sb[16];
+              tmem_ld16(tS, sa);
+              if (G >= 1) mbar_wait(pv, (G - 1) & 1);  // the P tile is free (P.V of the previous item complete)
+              tmem_ld_wait16(sa);
+              tmem_ld16(tS + 16, sb);
+              g4_chunk<true>(sa, nm2, racc, rm, sP_row, t, 0);
+              tmem_ld_wait16(sb);
+              tmem_ld16(tS + 32, sa);
+              g4_chunk<true>(sb, nm2, racc, rm, sP_row, t, 1);
+              tmem_ld_wait16(sa);
+              tmem_ld16(tS + 48, sb);
+              g4_chunk<true>(sa, nm2, racc, rm, sP_row, t, 2);
+              tmem_ld_wait16(sb);
+              g4_chunk<true>(sb, nm2, racc, rm, sP_row, t, 3);
+              // a score that would push P past 2^14: redo the item on the exact path (warp-uniform: the TMEM rescale
+              // there is warp-collective; S is still in its buffer)
+              exact = __any_sync(0xffffffffu, fmaxf(rm[0], rm[1]) - mrow[h] > kG4LazyBound);
+              if (!exact) {
+                float r0, r1;
+                unpack_f2(fadd2(racc[0], racc[1]), r0, r1);
+                lrow[h] += r0 + r1;
+              }
+            } else if (G >= 1) {
+              mbar_wait(pv, (G - 1) & 1);
+            }
+            if (exact) {
+              // pass 1: row max of the (masked) scores
+              float tmax = -INFINITY;
+#pragma unroll 1
+              for (int c = 0; c < 4; ++c) {
+                uint32_t s[16];
+                tmem_ld16(tS + c * 16, s);
+                tmem_ld_wait16(s);
+                if (!all_valid) g4_mask_chunk(s, keyp, c);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) tmax = fmax3(tmax, __uint_as_float(s[2 * j]), __uint_as_float(s[2 * j + 1]));
+              }
+              const float m_new = fmaxf(mrow[h], tmax);
+              if (kt > 0) {
+                const float alpha = ex2_approx(mrow[h] - m_new);
+                lrow[h] *= alpha;
+                // O_h of this row lives in this thread's TMEM lane; every earlier P.V of this group is complete (see
+                // the wait on pv above)
+                uint32_t ov[16];
+                tmem_ld16(tO + h * 16, ov);
+                tmem_ld_wait16(ov);
+#pragma unroll
+                for (int c = 0; c < 16; ++c) ov[c] = __float_as_uint(__uint_as_float(ov[c]) * alpha);
+                tmem_st16(tO + h * 16, ov);
+                tmem_st_wait();
+              }
+              mrow[h] = m_new;
+              // pass 2: P = exp2(t - m_new) (MUFU only: the polynomial's clamp would weight masked keys with 2^-24)
+              const uint64_t nm2 = pack_f2(-m_new, -m_new);
+              uint64_t racc[2] = {0ull, 0ull};
+              float rm[2] = {-INFINITY, -INFINITY};
+#pragma unroll 1
+              for (int c = 0; c < 4; ++c) {
+                uint32_t s[16];
+                tmem_ld16(tS + c * 16, s);
+                tmem_ld_wait16(s);
+                if (!all_valid) g4_mask_chunk(s, keyp, c);
+                g4_chunk<false>(s, nm2, racc, rm, sP_row, t, c);
+              }
+              float r0, r1;
+              unpack_f2(fadd2(racc[0], racc[1]), r0, r1);
+              lrow[h] += r0 + r1;
+            }
+            tc_fence_before();  // S reads (and a possible O rescale) are done before the UMMA warp moves on
+            fence_proxy_async_smem();
+            mbar_arrive(pr);
+          }
+        }
+        // ---- unit epilogue: O (4 x 16 fp32, complete once the last P.V is), normalise, gate, store
+        mbar_wait(pv, (G - 1) & 1);
+        tc_fence_after();
+        {
+          // rows [32 w, 32 w + 32) of the P tile are private to this warp and idle: 4 KB slice for the coalesced load
+          // of the gate rows / store of the output rows
+          uint8_t* slice = sP + w * 4096;
+          const int row0 = qt * 128 + w * 32;
+          const long long grow = ((long long)seq * N + row0) * 64;
+          uint4 gv[8];
+          warp_load_rows128(slice, lane, gv, g_gate + grow, 128, N - row0);
+          uint4 ovv[8];
+#pragma unroll
+          for (int h = 0; h < 4; ++h) {
+            uint32_t ov[16];
+            tmem_ld16(tO + h * 16, ov);
+            tmem_ld_wait16(ov);
+            const float inv = 1.0f / lrow[h];
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+              const __half2* g2 = reinterpret_cast<const __half2*>(&gv[h * 2 + half]);
+              uint32_t* o32 = reinterpret_cast<uint32_t*>(&ovv[h * 2 + half]);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float2 gf = __half22float2(g2[e]);
+                o32[e] = pack_half2(__uint_as_float(ov[half * 8 + 2 * e]) * inv * gf.x,
+                                    __uint_as_float(ov[half * 8 + 2 * e + 1]) * inv * gf.y);
+              }
+            }
+          }
+          tc_fence_before();
+          mbar_arrive(o_read);  // the O region may be overwritten by the next unit
+          warp_store_rows128(slice, lane, ovv, og + grow, 128, N - row0);
+          __syncwarp();  // the slice is P again from here on
+        }
+      }
+    }
+  } else if (warp < 20) {
+    // ------------------------------------------------------------------ UMMA warp of group g
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+    const int g = warp - 16;
+    uint64_t* b = gb + g * 8;
+    uint64_t* q_full = &b[0];
+    uint64_t* q_empty = &b[1];
+    uint64_t* s_full = &b[2];
+    uint64_t* pr = &b[3];
+    uint64_t* pv = &b[4];
+    uint64_t* o_read = &b[5];
+    const uint32_t tmem = *tmem_slot + g * 128;
+    const uint64_t dq = umma_desc_sw128(smem_u32(sm + G4Smem::kQ + g * 16384));
+    const uint64_t dp = umma_desc_sw128(smem_u32(sm + G4Smem::kP + g * 16384));
+    const uint64_t dk0 = umma_desc_sw128(smem_u32(sK));
+    const uint64_t dv0 = umma_desc_sw128(smem_u32(sV));
+    const uint32_t idesc_s = umma_idesc_f16(128, 64), idesc_o = umma_idesc_f16(128, 16);
+    int G = 0, U = 0;  // items / units of this group so far
+    int R = 0;
+    for (int ks = 0; ks < nseq_cta; ++ks) {
+      for (int rr = 0; rr < nrr; ++rr, ++R) {
+        const int gt0 = R * nkt;
+        if (rr * 4 + g >= nqt) {
+          // no unit: still release the ring slots, paced by the loads (an arrival must land in the slot's current phase)
+          for (int kt = 0; kt < nkt; ++kt) {
+            const int gt = gt0 + kt, slot = gt % kG4Ring;
+            mbar_wait(&k_full[slot], (gt / kG4Ring) & 1);
+            mbar_wait(&v_full[slot], (gt / kG4Ring) & 1);
+            if (elect_one()) {
+              mbar_arrive(&k_empty[slot]);
+              mbar_arrive(&v_empty[slot]);
+            }
+            __syncwarp();
+          }
+          continue;
+        }
+        mbar_wait(q_full, U & 1);
+        // first S of the unit (its S buffer was released by the previous unit's last pass, or never used)
+        if (G >= 1) mbar_wait(pr, (G - 1) & 1);
+        mbar_wait(&k_full[gt0 % kG4Ring], (gt0 / kG4Ring) & 1);
+        tc_fence_after();
+        if (elect_one()) {
+          umma_f16(tmem, dq, dk0 + (gt0 % kG4Ring) * (8192 >> 4), idesc_s, 0u);
+          umma_commit(s_full);
+        }
+        __syncwarp();
+        for (int it = 0; it < n_items; ++it, ++G) {
+          const int h = it & 3, kt = it >> 2, gt = gt0 + kt, slot = gt % kG4Ring;
+          mbar_wait(pr, G & 1);  // P_G written, S_G consumed
+          tc_fence_after();
+          if (it + 1 < n_items) {
+            // S of the next item first: the softmax threads wait for it
+            const int h1 = (it + 1) & 3, gt1 = gt0 + ((it + 1) >> 2), slot1 = gt1 % kG4Ring;
+            if (h1 == 0) {
+              mbar_wait(&k_full[slot1], (gt1 / kG4Ring) & 1);
+              tc_fence_after();
+            }
+            if (elect_one()) {
+              umma_f16(tmem, dq + 2 * h1, dk0 + slot1 * (8192 >> 4) + 2 * h1, idesc_s, 0u);
+              umma_commit(s_full);
+              if (h1 == 3) umma_commit(&k_empty[slot1]);        // last read of this K tile by this group
+              if (it + 1 == n_items - 1) umma_commit(q_empty);  // last read of the Q tile
+            }
+            __syncwarp();
+          }
+          // O_h (+)= P_G V_h ; a unit's first tile overwrites the O region (every thread has read the previous unit's O)
+          if (it == 0 && U >= 1) mbar_wait(o_read, (U - 1) & 1);
+          if (h == 0) mbar_wait(&v_full[slot], (gt / kG4Ring) & 1);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint32_t tO = tmem + 64 + h * 16;
+            const uint64_t dv = dv0 + slot * (8192 >> 4) + h * (2048 >> 4);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_f16(tO, dp + 2 * k, dv + 2 * k, idesc_o, (kt > 0 || k > 0) ? 1u : 0u);
+            umma_commit(pv);
+            if (h == 3) umma_commit(&v_empty[slot]);
+          }
+          __syncwarp();
+        }
+        ++U;
+      }
+    }
+  } else if (warp == 20) {
+    // ------------------------------------------------------------------ K / V ring TMA warp
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+    int gt = 0;
+    for (int ks = 0; ks < nseq_cta; ++ks) {
+      const int seq = (int)blockIdx.x + ks * (int)gridDim.x;
+      for (int rr = 0; rr < nrr; ++rr) {
+        for (int kt = 0; kt < nkt; ++kt, ++gt) {
+          const int slot = gt % kG4Ring;
+          if (gt >= kG4Ring) {
+            mbar_wait(&k_empty[slot], ((gt / kG4Ring) - 1) & 1);
+            mbar_wait(&v_empty[slot], ((gt / kG4Ring) - 1) & 1);
+          }
+          if (elect_one()) {
+            mbar_expect_tx(&k_full[slot], 8192);
+            tma_load_3d(sK + slot * 8192, &map_k, &k_full[slot], 0, kt * 64, seq);
+            mbar_expect_tx(&v_full[slot], 8192);
+            tma_load_3d(sV + slot * 8192, &map_vt, &v_full[slot], kt * 64, 0, seq);
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else if (warp == 21) {
+    // ------------------------------------------------------------------ Q TMA warp (all four groups)
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+    int U[4] = {0, 0, 0, 0};
+    for (int ks = 0; ks < nseq_cta; ++ks) {
+      const int seq = (int)blockIdx.x + ks * (int)gridDim.x;
+      for (int rr = 0; rr < nrr; ++rr) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const int qt = rr * 4 + g;
+          if (qt >= nqt) continue;
+          uint64_t* b = gb + g * 8;
+          if (U[g] >= 1) mbar_wait(&b[1], (U[g] - 1) & 1);  // the previous unit's last S is complete
+          if (elect_one()) {
+            mbar_expect_tx(&b[0], 16384);
+            tma_load_3d(sm + G4Smem::kQ + g * 16384, &map_q, &b[0], 0, qt * 128, seq);
+          }
+          __syncwarp();
+          ++U[g];
+        }
+      }
+    }
+  } else {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(*tmem_slot, 512);
+}
+
+}  // namespace
+
+int triattn_flash_g4(const PairDims& d, const float* mask, const __half* q, const __half* k, const __half* g,
+                     const __half* vt, __half* og, cudaStream_t s) {
+  const int N = d.N, Np = plane_ld(N);
+  const long long nseq = (long long)d.B * N;
+  CUtensorMap mq, mk, mv;
+  TmaDims t;
+  // q: [seq][tok][64], box 128 tokens; k: box 64 keys
+  t.size[0] = 64; t.size[1] = (uint64_t)N; t.size[2] = (uint64_t)nseq; t.size[3] = 1;
+  t.stride[0] = 128; t.stride[1] = (uint64_t)N * 128; t.stride[2] = 0;
+  t.box[0] = 64; t.box[1] = 128; t.box[2] = 1; t.box[3] = 1;
+  if (make_tensor_map(&mq, q, 2, 3, t, true)) return 1;
+  t.box[1] = 64;
+  if (make_tensor_map(&mk, k, 2, 3, t, true)) return 1;
+  // vt: [seq][64 (h,c)][tok], tok contiguous, row stride Np; one box = all 64 rows x 64 keys
+  t.size[0] = (uint64_t)N; t.size[1] = 64; t.size[2] = (uint64_t)nseq;
+  t.stride[0] = (uint64_t)Np * 2; t.stride[1] = (uint64_t)Np * 2 * 64;
+  t.box[0] = 64; t.box[1] = 64; t.box[2] = 1;
+  if (make_tensor_map(&mv, vt, 2, 3, t, true)) return 1;
+  const int nkt = (N + 63) / 64;
+  const int key_bytes = (nkt * 64 * 4 + nkt * 16 + 127) & ~127;
+  const int smem = 1024 + G4Smem::kKey + 4 * key_bytes + (4 * kG4Ring + 32) * 8 + 16;
+  PRD_REQUIRE(smem <= 227 * 1024, "triattn_flash_g4: N=%d needs %d B of shared memory", N, smem);
+  PRD_REQUIRE(nseq <= 2147483647LL / 64, "triattn_flash_g4: too many sequences");
+  const int grid = (int)std::min<long long>(nseq, kNumSMs);
+  PRD_CUDA_OK(cudaFuncSetAttribute(triattn_flash_g4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  triattn_flash_g4_kernel<<<grid, kG4Threads, smem, s>>>(mq, mk, mv, mask, g, og, N, (int)nseq);
+  PRD_LAUNCHED();
+  return 0;
+}
+
+}  // namespace prd

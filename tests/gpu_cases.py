@@ -337,6 +337,8 @@ CASES = {
     # N = 140: ragged 16-byte vectors in the transposed v tile, two query tiles, padded last key tile
     "triattn_n140": lambda: case_triattn(B=1, N=140, mode="starting", pad=6),
     "triattn_n300": lambda: case_triattn(B=1, N=300, mode="ending", pad=13),
+    # N = 512: four query tiles per sequence -> the four-group kernel (prd_triattn4.cu), with masked key tiles
+    "triattn_n512": lambda: case_triattn(B=1, N=512, mode="starting", pad=70),
     "pair_transition_n140": lambda: case_pair_transition(syn.PAPER, 1, 140),
     "outer_linear_n300": lambda: case_outer_linear(syn.PAPER, 1, 300),
     "outer_linear": lambda: case_outer_linear(),
