@@ -284,7 +284,7 @@ int outer_linear(const PairDims& d, int CS, const float* pair, float* dst, int r
 // operand (dist_dim/64 K-blocks); a_i * b_j (opm_dim/64 K-blocks) likewise.  Two accumulators.
 // =========================================================================================
 template <int CZ>
-__global__ void __launch_bounds__(128, 1)
+__global__ void __launch_bounds__(256, 1)
 pair_embed_kernel(const float* __restrict__ pstatic, float* __restrict__ pair, const float* __restrict__ z,
                   const float* __restrict__ mask, const float* __restrict__ beta, const __half* __restrict__ w_dist,
                   int DD, const float* __restrict__ centers, float rbf_scale, const float* __restrict__ opm_a,
@@ -308,21 +308,23 @@ pair_embed_kernel(const float* __restrict__ pstatic, float* __restrict__ pair, c
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mma_bar + 1);
   constexpr int TCOLS = 2 * CZ;
 
-  const int t = threadIdx.x, warp = t >> 5;
-  if (t == 0) {
+  // two threads per row: thread (t, half) generates half of the radial-basis / outer-product columns of row t and
+  // handles half of the output channels (the kernel is instruction bound: ~1500 instructions per row)
+  const int tid = threadIdx.x, t = tid & 127, half = tid >> 7, warp = t >> 5;
+  if (tid == 0) {
     mbar_init(full, kTileRows);
     mbar_init(mma_bar, 1);
     fence_barrier_init();
   }
-  if (warp == 0) tmem_alloc(tmem_slot, TCOLS);
+  if (tid < 32) tmem_alloc(tmem_slot, TCOLS);
   if (with_dist) {
-    load_weight_kblocks(sW1, w_dist, CZ, DD, DD, t, 128);
-    load_weight_kblocks(sW1 + KBD * CZ * 128, w_dist + CZ * DD, CZ, DD, DD, t, 128);
+    load_weight_kblocks(sW1, w_dist, CZ, DD, DD, tid, 256);
+    load_weight_kblocks(sW1 + KBD * CZ * 128, w_dist + CZ * DD, CZ, DD, DD, tid, 256);
   }
-  load_weight_kblocks(sW2, w_opm, CZ, OD, OD, t, 128);
+  load_weight_kblocks(sW2, w_opm, CZ, OD, OD, tid, 256);
   if (with_dist)
-    for (int i = t; i < DD; i += 128) sC[i] = centers[i];
-  for (int i = t; i < CZ; i += 128) sBo[i] = b_opm[i];
+    for (int i = tid; i < DD; i += 256) sC[i] = centers[i];
+  for (int i = tid; i < CZ; i += 256) sBo[i] = b_opm[i];
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -336,8 +338,8 @@ pair_embed_kernel(const float* __restrict__ pstatic, float* __restrict__ pair, c
   for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
     const long long r = tile * kTileRows + t;
     const bool valid = r < R;
-    bulk_wait_read0();  // previous tile's bulk store has finished reading the stage
-    issue_row_load<CZ>(sSt, t, pstatic + r * CZ, valid && pstatic != nullptr, full);
+    if (half == 0) bulk_wait_read0();  // previous tile's bulk store has finished reading the stage
+    if (half == 0) issue_row_load<CZ>(sSt, t, pstatic + r * CZ, valid && pstatic != nullptr, full);
     int b = 0, i = 0, j = 0;
     if (valid) {
       b = static_cast<int>(r / NN);
@@ -352,7 +354,7 @@ pair_embed_kernel(const float* __restrict__ pstatic, float* __restrict__ pair, c
     const float m2 = valid ? mask[(long long)b * N + i] * mask[(long long)b * N + j] : 0.f;
     // radial basis -> A1
 #pragma unroll 1
-    for (int k0 = 0; k0 < KBD * 64; k0 += 32) {
+    for (int k0 = half * KBD * 32; k0 < (half + 1) * KBD * 32; k0 += 32) {
       float v[32];
 #pragma unroll
       for (int q = 0; q < 32; ++q) {
@@ -365,7 +367,7 @@ pair_embed_kernel(const float* __restrict__ pstatic, float* __restrict__ pair, c
     const float* ap = opm_a + ((long long)b * N + i) * OD;
     const float* bp = opm_b + ((long long)b * N + j) * OD;
 #pragma unroll 1
-    for (int k0 = 0; k0 < OD; k0 += 32) {
+    for (int k0 = half * (OD / 2); k0 < (half + 1) * (OD / 2); k0 += 32) {
       float v[32];
 #pragma unroll
       for (int q = 0; q < 32; q += 4) {
@@ -376,7 +378,7 @@ pair_embed_kernel(const float* __restrict__ pstatic, float* __restrict__ pair, c
       store_a_cols32(sA2, t, k0, v);
     }
     sync_before_mma();
-    if (t < 32) {  // warp-uniform issue: UMMA operands stay in uniform registers
+    if (tid < 32) {  // warp-uniform issue: UMMA operands stay in uniform registers
       tc_fence_after();
       if (elect_one()) {
         if (with_dist) {
@@ -397,8 +399,10 @@ pair_embed_kernel(const float* __restrict__ pstatic, float* __restrict__ pair, c
     const float inv_norm = 1.0f / (m2 + 1e-3f);
     const float m2o = (flags & 2) ? 1.0f : m2;
     const bool have_static = pstatic != nullptr;
+    // output channels [32 half, 32 half + 32) (pair_dim 64) / all channels by half 0 (pair_dim 32)
 #pragma unroll
     for (int c = 0; c < CZ / 32; ++c) {
+      if (CZ / 32 == 2 ? (c != half) : (half != 0)) continue;
       uint32_t a1[32], a2[32];
       tmem_ld32(tm_lane + c * 32, a1);
       tmem_ld32(tm_lane + CZ + c * 32, a2);
@@ -418,15 +422,17 @@ pair_embed_kernel(const float* __restrict__ pstatic, float* __restrict__ pair, c
       }
     }
     fence_proxy_async_smem();
-    if (valid) bulk_s2g(pair + r * CZ, my, CZ * 4);
-    bulk_commit();
     tc_fence_before();
-    __syncthreads();
+    __syncthreads();  // both halves of every row are staged; TMEM / A tiles are free for the next tile
+    if (half == 0) {
+      if (valid) bulk_s2g(pair + r * CZ, my, CZ * 4);
+      bulk_commit();
+    }
   }
   bulk_wait0();
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem, TCOLS);
+  if (tid < 32) tmem_dealloc(tmem, TCOLS);
 }
 
 int pair_embed_dynamic(const PairDims& d, const float* pair_static, float* pair, const float* z, const float* mask,
@@ -445,7 +451,7 @@ int pair_embed_dynamic(const PairDims& d, const float* pair_static, float* pair,
     PRD_REQUIRE(smem <= 227 * 1024, "pair_embed: shared memory %d B exceeds 227 KB", smem);
     auto kern = pair_embed_kernel<CZ>;
     PRD_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    kern<<<grid, 128, smem, s>>>(pair_static, pair, z, mask, beta, w_dist, dist_dim, centers, rbf_scale, opm_a, opm_b,
+    kern<<<grid, 256, smem, s>>>(pair_static, pair, z, mask, beta, w_dist, dist_dim, centers, rbf_scale, opm_a, opm_b,
                                  opm_dim, w_opm, b_opm, d.N, R, flags);
   } else if (d.CZ == 32) {
     constexpr int CZ = 32;
@@ -453,7 +459,7 @@ int pair_embed_dynamic(const PairDims& d, const float* pair_static, float* pair,
     PRD_REQUIRE(smem <= 227 * 1024, "pair_embed: shared memory %d B exceeds 227 KB", smem);
     auto kern = pair_embed_kernel<CZ>;
     PRD_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    kern<<<grid, 128, smem, s>>>(pair_static, pair, z, mask, beta, w_dist, dist_dim, centers, rbf_scale, opm_a, opm_b,
+    kern<<<grid, 256, smem, s>>>(pair_static, pair, z, mask, beta, w_dist, dist_dim, centers, rbf_scale, opm_a, opm_b,
                                  opm_dim, w_opm, b_opm, d.N, R, flags);
   } else {
     set_error("pair_embed: unsupported pair_dim %d", d.CZ);
