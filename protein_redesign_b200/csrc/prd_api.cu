@@ -409,6 +409,9 @@ int prd_triangle_attention_fwd(const PrdDims* d, const void* const* in, void* co
   cudaStream_t st = S(stream);
   const float* pair = in_ptr<float>(in, 0);
   if (triattn_proj(pd(d), pair, d->mode, in_ptr<__half>(w, 0), in_ptr<float>(w, 1), s.q, s.k, s.g, s.vt, st)) return 1;
+  if (d->c_z == 64 && triattn_flash_g4_applies(pd(d)))  // attention core + out_proj + residual in one kernel
+    return triattn_flash_out_g4(pd(d), in_ptr<float>(in, 1), s.q, s.k, s.g, s.vt, pair, out_ptr<float>(out, 0), d->residual,
+                                d->mode, in_ptr<__half>(w, 2), in_ptr<float>(w, 3), st);
   if (triattn_flash(pd(d), in_ptr<float>(in, 1), s.q, s.k, s.g, s.vt, s.og, st)) return 1;
   return triattn_out(pd(d), pair, out_ptr<float>(out, 0), d->residual, d->mode, s.og, in_ptr<__half>(w, 2),
                      in_ptr<float>(w, 3), st);

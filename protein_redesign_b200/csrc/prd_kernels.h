@@ -56,6 +56,10 @@ int triattn_proj(const PairDims& d, const float* pair, int mode, const __half* w
                  __half* k, __half* g, __half* vt, cudaStream_t s);
 int triattn_flash_g4(const PairDims& d, const float* mask, const __half* q, const __half* k, const __half* g,
                      const __half* vt, __half* og, cudaStream_t s);  // four softmax groups per SM (prd_triattn4.cu)
+int triattn_flash_out_g4(const PairDims& d, const float* mask, const __half* q, const __half* k, const __half* g,
+                         const __half* vt, const float* pair, float* dst, int residual, int mode, const __half* w_o,
+                         const float* b_o, cudaStream_t s);  // attention core + out_proj + residual fused
+bool triattn_flash_g4_applies(const PairDims& d);
 int triattn_flash(const PairDims& d, const float* mask, const __half* q, const __half* k, const __half* g,
                   const __half* vt, __half* og, cudaStream_t s);
 int triattn_out(const PairDims& d, const float* pair, float* dst, int residual, int mode, const __half* og,

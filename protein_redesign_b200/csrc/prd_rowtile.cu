@@ -1227,11 +1227,16 @@ triattn_out_kernel(const float* pair, float* dst, int residual, RowMap map, long
     bulk_wait_read0();  // this thread's previous output row has left the stage
     issue_row_load<CZ>(sSt, t, pair + src * CZ, valid && residual, full);
     {
-      const uint4* op = reinterpret_cast<const uint4*>(og + r * 64);
+      // og rows are contiguous in logical row order: the warp's 32 rows x 128 bytes are fetched with fully coalesced
+      // 16-byte loads (lane -> chunk (i*32 + lane) of the 4 KB block) and dropped straight into the swizzled A tile
+      const int lane = t & 31, w32 = (t >> 5) * 32;
+      const long long row0 = tile * kTileRows + w32;
+      const uint4* op = reinterpret_cast<const uint4*>(og + row0 * 64);
 #pragma unroll
-      for (int ch = 0; ch < 8; ++ch) {
-        const uint4 v = valid ? __ldg(op + ch) : make_uint4(0, 0, 0, 0);
-        *reinterpret_cast<uint4*>(sA + sw128_offset(t, ch)) = v;
+      for (int i = 0; i < 8; ++i) {
+        const int rr = i * 4 + (lane >> 3), ch = lane & 7;
+        const uint4 v = (row0 + rr < R) ? __ldg(op + i * 32 + lane) : make_uint4(0, 0, 0, 0);
+        *reinterpret_cast<uint4*>(sA + sw128_offset(w32 + rr, ch)) = v;
       }
     }
     g.sync_before_mma();

@@ -527,14 +527,7 @@ triattn_flash_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
 
 int triattn_flash(const PairDims& d, const float* mask, const __half* q, const __half* k, const __half* g,
                   const __half* vt, __half* og, cudaStream_t s) {
-  {
-    // four-group variant (prd_triattn4.cu) when its groups are all busy: query tiles per sequence a multiple of 4
-    // (N = 512, 1024, ...).  PRD_FLASH_G4=0/1 forces one of the two kernels (A/B timing).
-    const char* force = getenv("PRD_FLASH_G4");
-    const int nqt4 = (d.N + 127) / 128;
-    const bool g4 = force ? (force[0] == '1') : (nqt4 % 4 == 0 && d.N <= 2048);
-    if (g4) return triattn_flash_g4(d, mask, q, k, g, vt, og, s);
-  }
+  if (triattn_flash_g4_applies(d)) return triattn_flash_g4(d, mask, q, k, g, vt, og, s);
   const int N = d.N, Np = plane_ld(N);
   const long long nseq = (long long)d.B * N;
   CUtensorMap mq, mk, mv;

@@ -79,13 +79,30 @@ struct G4Smem {
   static constexpr int kV = kK + kG4Ring * 8192;       // kG4Ring x 8 KB
   static constexpr int kQ = kV + kG4Ring * 8192;       // 4 x 16 KB
   static constexpr int kP = kQ + 4 * 16384;            // 4 x 16 KB
-  static constexpr int kKey = kP + 4 * 16384;          // 4 x (nkt * 64 floats + nkt * 16 bytes), sized at run time
+  static constexpr int kWo = kP + 4 * 16384;           // fused out-projection: W_o hi, lo: 2 x [64 x 64] halves (1024-aligned)
+  static constexpr int kBo = kWo + 16384;              // b_o [64]
+  static constexpr int kKey = kBo + 256;               // 4 x (nkt * 64 floats + nkt * 16 bytes), sized at run time
 };
 
+// kFused: the output projection of the attention module (modules.py:222-225: out_proj, + residual) runs in the unit
+// epilogue: the gated rows become a [128 x 64] fp16 A tile (the idle P tile), one UMMA pair against W_o (hi + lo)
+// accumulates into the (already read) O columns, and the pair rows are updated in place with full-line loads /
+// stores.  The kernel is exp2 bound with HBM idle, so the 2 P of traffic of the former triattn_out kernel are free
+// here, and the og round trip (1 P) disappears.
+struct G4OutProj {
+  const float* pair;   // residual source (may equal dst)
+  float* dst;
+  const __half* w_o;   // fp16 pair [hi; lo], each [64 x 64]
+  const float* b_o;    // [64]
+  int residual;
+  int transposed;      // 0: row (b, seq, tok) = pair[b, seq, tok]; 1: pair[b, tok, seq]
+};
+
+template <bool kFused>
 __global__ void __launch_bounds__(kG4Threads, 1)
 triattn_flash_g4_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
                         const __grid_constant__ CUtensorMap map_vt, const float* __restrict__ mask,
-                        const __half* __restrict__ g_gate, __half* __restrict__ og, int N, int nseq) {
+                        const __half* __restrict__ g_gate, __half* __restrict__ og, int N, int nseq, G4OutProj op) {
   extern __shared__ uint8_t raw[];
   const int nqt = (N + 127) / 128;  // query tiles per sequence
   const int nkt = (N + 63) / 64;    // 64-key tiles per sequence
@@ -95,6 +112,8 @@ triattn_flash_g4_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_
   uint8_t* sm = smem_align1024(raw);
   uint8_t* sK = sm + G4Smem::kK;
   uint8_t* sV = sm + G4Smem::kV;
+  uint8_t* sWo = sm + G4Smem::kWo;
+  float* sBo = reinterpret_cast<float*>(sm + G4Smem::kBo);
   uint64_t* bars = reinterpret_cast<uint64_t*>(sm + G4Smem::kKey + 4 * key_bytes);
   uint64_t* k_full = bars;               // [ring]
   uint64_t* k_empty = bars + kG4Ring;    // [ring] one arrival per group
@@ -119,6 +138,7 @@ triattn_flash_g4_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_
       mbar_init(&b[3], 128);  // pr: P written, S consumed
       mbar_init(&b[4], 1);    // pv: P.V complete, P free
       mbar_init(&b[5], 128);  // o_read: O region free
+      mbar_init(&b[6], 1);    // proj: output projection complete (kFused)
     }
     fence_barrier_init();
     tma_prefetch_desc(&map_q);
@@ -126,6 +146,12 @@ triattn_flash_g4_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_
     tma_prefetch_desc(&map_vt);
   }
   if (warp == 0) tmem_alloc(tmem_slot, 512);
+  if (kFused) {
+    load_weight_kblocks(sWo, op.w_o, 64, 64, 64, threadIdx.x, kG4Threads);
+    load_weight_kblocks(sWo + 8192, op.w_o + 64 * 64, 64, 64, 64, threadIdx.x, kG4Threads);
+    if (threadIdx.x < 64) sBo[threadIdx.x] = op.b_o[threadIdx.x];
+    fence_proxy_async_smem();
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -152,6 +178,7 @@ triattn_flash_g4_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_
     int* sWarpValid = reinterpret_cast<int*>(sKey + nkt * 64);  // [ceil(nkt/2)][4]
     int G = 0;  // items of this group so far (barrier parities)
     int R = 0;
+    int Ug = 0;  // units of this group so far
     for (int ks = 0; ks < nseq_cta; ++ks) {
       const int seq = (int)blockIdx.x + ks * (int)gridDim.x;
       bool table = false;
@@ -298,9 +325,63 @@ triattn_flash_g4_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_
               }
             }
           }
-          tc_fence_before();
-          mbar_arrive(o_read);  // the O region may be overwritten by the next unit
-          warp_store_rows128(slice, lane, ovv, og + grow, 128, N - row0);
+          if (!kFused) {
+            tc_fence_before();
+            mbar_arrive(o_read);  // the O region may be overwritten by the next unit
+            warp_store_rows128(slice, lane, ovv, og + grow, 128, N - row0);
+          } else {
+            // gated rows -> A tile (this thread's row of the idle P tile), out-projection on the tensor core into the
+            // O columns (every thread of the group has read its O: group barrier), pair rows updated with full lines
+            __syncwarp();  // the slice (= this warp's rows of the P tile) is done as a load stage
+#pragma unroll
+            for (int c = 0; c < 8; ++c) *reinterpret_cast<uint4*>(sP + sw128_offset(t, c)) = ovv[c];
+            fence_proxy_async_smem();
+            tc_fence_before();
+            asm volatile("bar.sync %0, 128;" ::"r"(g + 1) : "memory");
+            if (w == 0) {
+              tc_fence_after();
+              if (elect_one()) {
+                const uint32_t idesc = umma_idesc_f16(128, 64);
+                umma_kblock(tmem + 64, smem_u32(sP), smem_u32(sWo), idesc, false);
+                umma_kblock(tmem + 64, smem_u32(sP), smem_u32(sWo) + 8192, idesc, true);
+                umma_commit(&b[6]);
+              }
+              __syncwarp();
+            }
+            // this warp's 32 pair rows (tokens row0 ..): contiguous rows in "starting" mode, stride N rows in "ending"
+            const int bb = seq / N, ss = seq - bb * N;
+            const long long prow = op.transposed ? (((long long)bb * N + row0) * N + ss) : ((long long)seq * N + row0);
+            const long long pitch = (op.transposed ? (long long)N : 1LL) * 64 * 4;
+            mbar_wait(&b[6], Ug & 1);
+            tc_fence_after();
+#pragma unroll
+            for (int p = 0; p < 2; ++p) {
+              uint4 res[8];
+              if (op.residual) {
+                warp_load_rows128(slice, lane, res, op.pair + prow * 64 + p * 32, pitch, N - row0);
+              } else {
+#pragma unroll
+                for (int c = 0; c < 8; ++c) res[c] = make_uint4(0, 0, 0, 0);
+              }
+              uint32_t acc[32];
+              tmem_ld32(tO + p * 32, acc);
+              tmem_ld_wait();
+              if (p == 1) {
+                tc_fence_before();
+                mbar_arrive(o_read);  // the O columns may be overwritten by the next unit
+              }
+#pragma unroll
+              for (int c = 0; c < 8; ++c) {
+                uint4& r = res[c];
+                r.x = __float_as_uint(__uint_as_float(r.x) + __uint_as_float(acc[4 * c + 0]) + sBo[p * 32 + 4 * c + 0]);
+                r.y = __float_as_uint(__uint_as_float(r.y) + __uint_as_float(acc[4 * c + 1]) + sBo[p * 32 + 4 * c + 1]);
+                r.z = __float_as_uint(__uint_as_float(r.z) + __uint_as_float(acc[4 * c + 2]) + sBo[p * 32 + 4 * c + 2]);
+                r.w = __float_as_uint(__uint_as_float(r.w) + __uint_as_float(acc[4 * c + 3]) + sBo[p * 32 + 4 * c + 3]);
+              }
+              warp_store_rows128(slice, lane, res, op.dst + prow * 64 + p * 32, pitch, N - row0);
+            }
+            ++Ug;
+          }
           __syncwarp();  // the slice is P again from here on
         }
       }
@@ -440,10 +521,8 @@ triattn_flash_g4_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_
   if (warp == 0) tmem_dealloc(*tmem_slot, 512);
 }
 
-}  // namespace
-
-int triattn_flash_g4(const PairDims& d, const float* mask, const __half* q, const __half* k, const __half* g,
-                     const __half* vt, __half* og, cudaStream_t s) {
+static int g4_launch(const PairDims& d, const float* mask, const __half* q, const __half* k, const __half* g,
+                     const __half* vt, __half* og, const G4OutProj* op, cudaStream_t s) {
   const int N = d.N, Np = plane_ld(N);
   const long long nseq = (long long)d.B * N;
   CUtensorMap mq, mk, mv;
@@ -466,10 +545,38 @@ int triattn_flash_g4(const PairDims& d, const float* mask, const __half* q, cons
   PRD_REQUIRE(smem <= 227 * 1024, "triattn_flash_g4: N=%d needs %d B of shared memory", N, smem);
   PRD_REQUIRE(nseq <= 2147483647LL / 64, "triattn_flash_g4: too many sequences");
   const int grid = (int)std::min<long long>(nseq, kNumSMs);
-  PRD_CUDA_OK(cudaFuncSetAttribute(triattn_flash_g4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  triattn_flash_g4_kernel<<<grid, kG4Threads, smem, s>>>(mq, mk, mv, mask, g, og, N, (int)nseq);
+  if (op) {
+    PRD_REQUIRE(d.CZ == 64, "triattn_flash_g4: fused output projection needs pair_dim 64");
+    PRD_CUDA_OK(cudaFuncSetAttribute(triattn_flash_g4_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    triattn_flash_g4_kernel<true><<<grid, kG4Threads, smem, s>>>(mq, mk, mv, mask, g, og, N, (int)nseq, *op);
+  } else {
+    PRD_CUDA_OK(cudaFuncSetAttribute(triattn_flash_g4_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    triattn_flash_g4_kernel<false><<<grid, kG4Threads, smem, s>>>(mq, mk, mv, mask, g, og, N, (int)nseq, G4OutProj{});
+  }
   PRD_LAUNCHED();
   return 0;
+}
+
+}  // namespace
+
+int triattn_flash_g4(const PairDims& d, const float* mask, const __half* q, const __half* k, const __half* g,
+                     const __half* vt, __half* og, cudaStream_t s) {
+  return g4_launch(d, mask, q, k, g, vt, og, nullptr, s);
+}
+
+// Attention core + output projection + residual in one kernel (replaces triattn_flash + triattn_out).
+int triattn_flash_out_g4(const PairDims& d, const float* mask, const __half* q, const __half* k, const __half* g,
+                         const __half* vt, const float* pair, float* dst, int residual, int mode, const __half* w_o,
+                         const float* b_o, cudaStream_t s) {
+  G4OutProj op{pair, dst, w_o, b_o, residual, mode};
+  return g4_launch(d, mask, q, k, g, vt, nullptr, &op, s);
+}
+
+// The four-group kernel keeps all groups busy when the query tiles per sequence are a multiple of four.
+bool triattn_flash_g4_applies(const PairDims& d) {
+  const char* force = getenv("PRD_FLASH_G4");
+  const int nqt = (d.N + 127) / 128;
+  return force ? (force[0] == '1') : (nqt % 4 == 0 && d.N <= 2048);
 }
 
 }  // namespace prd
