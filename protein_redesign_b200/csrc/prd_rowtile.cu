@@ -4,6 +4,7 @@
 //   triattn_proj/out  TriangleAttention q,k,v,gate / out_proj    (modules.py:185-225,236-243)
 // See prd_rowtile.cuh for the execution model.
 #include "prd_kernels.h"
+#include <string.h>
 #include "prd_rowtile.cuh"
 
 namespace prd {
@@ -35,6 +36,17 @@ struct RowMap {
 template <typename Kern>
 int set_smem(Kern k, int bytes) {
   return check_cuda(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes), "cudaFuncSetAttribute");
+}
+
+// Tensor map over the fp32 pair tensor [B][N][N][64] for tiles of 128 tokens of one sequence:
+//   mode 0 (row (b,s,tok) = pair[b,s,tok]): dims (c, tok, s, b), box (32, 128, 1, 1)  -> coords (32 h, tok0, s, b)
+//   mode 1 (row (b,s,tok) = pair[b,tok,s]): dims (c, s, tok, b), box (32, 1, 128, 1)  -> coords (32 h, s, tok0, b)
+inline int make_pair_tile_map(CUtensorMap* m, const float* pair, int B, int N, int mode) {
+  TmaDims t;
+  t.size[0] = 64; t.size[1] = (uint64_t)N; t.size[2] = (uint64_t)N; t.size[3] = (uint64_t)B;
+  t.stride[0] = 256; t.stride[1] = (uint64_t)N * 256; t.stride[2] = (uint64_t)N * N * 256;
+  t.box[0] = 32; t.box[1] = mode ? 1 : 128; t.box[2] = mode ? 128 : 1; t.box[3] = 1;
+  return make_tensor_map(m, pair, 4, 4, t, true);
 }
 
 inline int grid_for(long long tiles, int ctas_per_sm) {
@@ -627,7 +639,7 @@ trimul_in_kernel(const float* __restrict__ pair, const float* __restrict__ mask,
 // takes columns [64 h, 64 h + 64).  512 threads = two compute groups.
 // -----------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(512, 1)
-trimul_in_t_kernel(const float* __restrict__ pair, const float* __restrict__ mask, RowMap map, int B,
+trimul_in_t_kernel(const __grid_constant__ CUtensorMap map_pair, const float* __restrict__ mask, RowMap map, int B,
                    const __half* __restrict__ w_in, const float* __restrict__ b_in, __half* __restrict__ ab, int Np) {
   constexpr int CZ = 64, NOUT = 256;
   extern __shared__ uint8_t raw[];
@@ -649,8 +661,9 @@ trimul_in_t_kernel(const float* __restrict__ pair, const float* __restrict__ mas
   uint64_t* full = bars + g.grp;
   uint64_t* mma_bar = bars + 2 + g.grp;
   if (threadIdx.x == 0) {
-    mbar_init(&bars[0], kTileRows);
-    mbar_init(&bars[1], kTileRows);
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    tma_prefetch_desc(&map_pair);
     mbar_init(&bars[2], 1);
     mbar_init(&bars[3], 1);
     fence_barrier_init();
@@ -674,13 +687,18 @@ trimul_in_t_kernel(const float* __restrict__ pair, const float* __restrict__ mas
   const long long plane = (long long)N * Np;
   uint32_t mma_phase = 0;
   long long tile = (long long)blockIdx.x * 2 + g.grp;
-  auto issue = [&](long long tl) {  // row (b, i, k = k0 + t), loaded by the half-0 thread of the pair
+  auto issue = [&](long long tl) {  // rows (b, i, k0 .. k0 + 127): one TMA tile (rows past N are zero-filled)
+    if (g.tt != 0) return;
     const long long bi = tl / tps;
-    const int k = static_cast<int>(tl - bi * tps) * kTileRows + t;
+    const int kk0 = static_cast<int>(tl - bi * tps) * kTileRows;
     const int b = static_cast<int>(bi / N), i = static_cast<int>(bi - (long long)b * N);
-    issue_row_load<CZ>(sSt, t, pair + map.src_row(b, i, k < N ? k : 0) * CZ, k < N, full);
+    mbar_expect_tx(full, 32768);
+    for (int h = 0; h < 2; ++h) {
+      if (map.transposed) tma_load_4d(sSt + h * 16384, &map_pair, full, h * 32, i, kk0, b);
+      else tma_load_4d(sSt + h * 16384, &map_pair, full, h * 32, kk0, i, b);
+    }
   };
-  if (tile < num_tiles && half == 0) issue(tile);
+  if (tile < num_tiles) issue(tile);
   for (int it = 0; tile < num_tiles; tile += stride, ++it) {
     mbar_wait(full, it & 1);
     const long long bi = tile / tps;
@@ -689,19 +707,14 @@ trimul_in_t_kernel(const float* __restrict__ pair, const float* __restrict__ mas
     const bool valid = k0 + t < N;
     {
       float x[CZ];
-      if (valid) {
-        read_row<CZ>(stage_row<CZ>(sSt, t), x);
-      } else {
-#pragma unroll
-        for (int q = 0; q < CZ; ++q) x[q] = 0.f;
-      }
+      read_row_tma64(sSt, t, x);
       layernorm_inplace<CZ>(x);
       store_a_half_row<CZ>(sA, t, half, x);
       // mask_2d of the *source* element: m[b,i]*m[b,k] is symmetric, same for both modes
       if (half == 0) sMask[t] = valid ? mask[(long long)b * N + i] * mask[(long long)b * N + k0 + t] : 0.f;
     }
     g.sync_before_mma();
-    if (half == 0 && tile + stride < num_tiles) issue(tile + stride);
+    if (tile + stride < num_tiles) issue(tile + stride);
     if (g.tt < 32) {  // warp-uniform issue: UMMA operands stay in uniform registers
       tc_fence_after();
       if (elect_one()) {
@@ -765,7 +778,9 @@ static int launch_trimul_in(const PairDims& d, const float* pair, const float* m
     constexpr int kStage = (RowStage<64>::kBytes + 1023) / 1024 * 1024;
     constexpr int smem = 1024 + 2 * 256 * 128 + 2 * (32768 + kStage) + 256 * 4 + 64;
     if (set_smem(trimul_in_t_kernel, smem)) return 1;
-    trimul_in_t_kernel<<<grid_for((tiles + 1) / 2, 1), 512, smem, s>>>(pair, mask, map, d.B, w_in, b_in, ab, plane_ld(d.N));
+    CUtensorMap mp;
+    if (make_pair_tile_map(&mp, pair, d.B, d.N, mode)) return 1;
+    trimul_in_t_kernel<<<grid_for((tiles + 1) / 2, 1), 512, smem, s>>>(mp, mask, map, d.B, w_in, b_in, ab, plane_ld(d.N));
     PRD_LAUNCHED();
     return 0;
   }
@@ -976,11 +991,12 @@ int trimul_out(const PairDims& d, const float* pair, float* dst, int residual, c
 // =========================================================================================
 template <int CZ>
 __global__ void __launch_bounds__(512, 1)
-triattn_proj_kernel(const float* __restrict__ pair, RowMap map, int B, const __half* __restrict__ w,
+triattn_proj_kernel(const __grid_constant__ CUtensorMap map_pair, const float* __restrict__ pair, RowMap map, int B, const __half* __restrict__ w,
                     const float* __restrict__ b_gate, __half* __restrict__ q, __half* __restrict__ k,
                     __half* __restrict__ gout, __half* __restrict__ vt, int Np) {
   extern __shared__ uint8_t raw[];
   constexpr int NOUT = 256;
+  constexpr bool kTma = (CZ == 64);  // pair_dim 64: the row tile arrives by TMA (32 KB swizzled stage)
   constexpr int kGroupBytes = 32768 + (RowStage<CZ>::kBytes + 1023) / 1024 * 1024;  // A tile, output stage, row stage
   uint8_t* sm = smem_align1024(raw);
   uint8_t* sW = sm;
@@ -997,8 +1013,9 @@ triattn_proj_kernel(const float* __restrict__ pair, RowMap map, int B, const __h
   uint64_t* full = bars + g.grp;
   uint64_t* mma_bar = bars + 2 + g.grp;
   if (threadIdx.x == 0) {
-    mbar_init(&bars[0], kTileRows);
-    mbar_init(&bars[1], kTileRows);
+    mbar_init(&bars[0], kTma ? 1 : kTileRows);
+    mbar_init(&bars[1], kTma ? 1 : kTileRows);
+    if (kTma) tma_prefetch_desc(&map_pair);
     mbar_init(&bars[2], 1);
     mbar_init(&bars[3], 1);
     fence_barrier_init();
@@ -1022,11 +1039,22 @@ triattn_proj_kernel(const float* __restrict__ pair, RowMap map, int B, const __h
   // tile -> (sequence = b * N + s, first token); the row of thread pair t is loaded by its half-0 thread
   auto issue = [&](long long tl) {
     const long long seq = tl / tps;
-    const int tok = static_cast<int>(tl - seq * tps) * kTileRows + t;
+    const int tok0 = static_cast<int>(tl - seq * tps) * kTileRows;
     const int b = static_cast<int>(seq / N), s = static_cast<int>(seq - (long long)b * N);
-    issue_row_load<CZ>(sSt, t, pair + map.src_row(b, s, tok < N ? tok : 0) * CZ, tok < N, full);
+    if (kTma) {
+      if (g.tt == 0) {  // rows past N are zero-filled by the TMA unit
+        mbar_expect_tx(full, 32768);
+        for (int h = 0; h < 2; ++h) {
+          if (map.transposed) tma_load_4d(sSt + h * 16384, &map_pair, full, h * 32, s, tok0, b);
+          else tma_load_4d(sSt + h * 16384, &map_pair, full, h * 32, tok0, s, b);
+        }
+      }
+    } else if (half == 0) {
+      const int tok = tok0 + t;
+      issue_row_load<CZ>(sSt, t, pair + map.src_row(b, s, tok < N ? tok : 0) * CZ, tok < N, full);
+    }
   };
-  if (tile < num_tiles && half == 0) issue(tile);
+  if (tile < num_tiles) issue(tile);
   for (int it = 0; tile < num_tiles; tile += stride, ++it) {
     mbar_wait(full, it & 1);
     const long long seq = tile / tps;
@@ -1035,7 +1063,9 @@ triattn_proj_kernel(const float* __restrict__ pair, RowMap map, int B, const __h
     const long long r0 = seq * N + tok0;  // first row of the tile
     {
       float x[CZ];
-      if (valid) {
+      if (kTma) {
+        if constexpr (CZ == 64) read_row_tma64(sSt, t, x);
+      } else if (valid) {
         read_row<CZ>(stage_row<CZ>(sSt, t), x);
       } else {
 #pragma unroll
@@ -1045,7 +1075,7 @@ triattn_proj_kernel(const float* __restrict__ pair, RowMap map, int B, const __h
       store_a_half_row<CZ>(sA, t, half, x);
     }
     g.sync_before_mma();  // also: both threads have read the row, its stage slot may be refilled
-    if (half == 0 && tile + stride < num_tiles) issue(tile + stride);
+    if (tile + stride < num_tiles) issue(tile + stride);
     if (g.tt < 32) {  // warp-uniform issue: UMMA operands stay in uniform registers
       tc_fence_after();
       if (elect_one()) {
@@ -1151,11 +1181,18 @@ static int launch_triattn_proj(const PairDims& d, const float* pair, int mode, c
                                __half* q, __half* k, __half* g, __half* vt, cudaStream_t s) {
   const long long tiles = (long long)d.B * d.N * ((d.N + kTileRows - 1) / kTileRows);
   RowMap map{d.N, (long long)d.N * d.N, mode};
+  constexpr bool kTma = (CZ == 64);  // pair_dim 64: the row tile arrives by TMA (32 KB swizzled stage)
   constexpr int kGroupBytes = 32768 + (RowStage<CZ>::kBytes + 1023) / 1024 * 1024;  // A tile, output stage, row stage
   constexpr int smem = 1024 + 2 * 256 * 128 + 2 * kGroupBytes + 64 * 4 + 64;
   auto kern = triattn_proj_kernel<CZ>;
   if (set_smem(kern, smem)) return 1;
-  kern<<<grid_for((tiles + 1) / 2, 1), 512, smem, s>>>(pair, map, d.B, w_qkvg, b_gate, q, k, g, vt, plane_ld(d.N));
+  CUtensorMap mp;
+  if (CZ == 64) {
+    if (make_pair_tile_map(&mp, pair, d.B, d.N, mode)) return 1;
+  } else {
+    memset(&mp, 0, sizeof(mp));
+  }
+  kern<<<grid_for((tiles + 1) / 2, 1), 512, smem, s>>>(mp, pair, map, d.B, w_qkvg, b_gate, q, k, g, vt, plane_ld(d.N));
   PRD_LAUNCHED();
   return 0;
 }

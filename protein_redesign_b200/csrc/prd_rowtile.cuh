@@ -59,6 +59,21 @@ __device__ __forceinline__ void write_row(float* row, const float (&x)[CZ]) {
     *reinterpret_cast<float4*>(row + c * 4) = make_float4(x[c * 4], x[c * 4 + 1], x[c * 4 + 2], x[c * 4 + 3]);
 }
 
+// Pair-row tile staged by TMA: 128 rows x 64 fp32 as two SWIZZLE_128B boxes of [128 rows x 32 floats] (16 KB each).
+// Row t, 16-byte chunk cc (0..15) lives at  (cc >> 3) * 16384 + t * 128 + (((cc & 7) ^ (t & 7)) << 4): a thread reading
+// its own row is bank-conflict free, and ONE thread issues the whole tile (two cp.async.bulk.tensor) instead of 128
+// per-thread row copies (which serialise lane by lane on the uniform datapath, ~8 % of a row kernel's time).
+__device__ __forceinline__ void read_row_tma64(const uint8_t* stage, int t, float (&x)[64]) {
+#pragma unroll
+  for (int cc = 0; cc < 16; ++cc) {
+    const float4 v = *reinterpret_cast<const float4*>(stage + (cc >> 3) * 16384 + t * 128 + (((cc & 7) ^ (t & 7)) << 4));
+    x[cc * 4 + 0] = v.x;
+    x[cc * 4 + 1] = v.y;
+    x[cc * 4 + 2] = v.z;
+    x[cc * 4 + 3] = v.w;
+  }
+}
+
 // In-place LayerNorm without affine (nn.LayerNorm(elementwise_affine=False), eps 1e-5).
 template <int CZ>
 __device__ __forceinline__ void layernorm_inplace(float (&x)[CZ]) {
