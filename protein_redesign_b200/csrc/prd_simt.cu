@@ -230,15 +230,23 @@ single_attention_kernel(int N, int H, const float* __restrict__ qkvg, const floa
   for (int c = 0; c < C; ++c) o[c] = 0.f;
   const float* bias_bh = bias + ((long long)b * H + h) * N * N;
   const int warp = t >> 5, lane = t & 31;
-  for (int j0 = 0; j0 < N; j0 += 32) {
-    __syncthreads();
-    // stage bias[i0 .. i0+31][j0 .. j0+31]: warp w loads rows w, w+4, ...; lanes along j
-    for (int r = warp; r < QT; r += 4) {
-      const int ii = blockIdx.x * QT + r;
-      const int jj = j0 + lane;
-      sBias[r * 33 + lane] = (ii < N && jj < N) ? bias_bh[(long long)ii * N + jj] : 0.f;
+  // bias[i0 .. i0+31][j0 .. j0+31] is staged through shared memory one 32-key stage ahead: the global loads of stage
+  // s+1 are in flight (registers) while stage s is processed
+  float bnext[QT / 4];
+  auto fetch_bias = [&](int j0) {
+#pragma unroll
+    for (int k = 0; k < QT / 4; ++k) {
+      const int r = warp + 4 * k, ii = blockIdx.x * QT + r, jj = j0 + lane;
+      bnext[k] = (j0 < N && ii < N && jj < N) ? bias_bh[(long long)ii * N + jj] : 0.f;
     }
+  };
+  fetch_bias(0);
+  for (int j0 = 0; j0 < N; j0 += 32) {
+    __syncthreads();  // the previous stage's tile has been consumed (also covers the K / V staging the first time)
+#pragma unroll
+    for (int k = 0; k < QT / 4; ++k) sBias[(warp + 4 * k) * 33 + lane] = bnext[k];
     __syncthreads();
+    fetch_bias(j0 + 32);
     const int jn = min(32, N - j0);
     for (int jj = part; jj < jn; jj += 4) {
       const int j = j0 + jj;
