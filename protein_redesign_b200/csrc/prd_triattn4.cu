@@ -434,30 +434,28 @@ triattn_flash_g4_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_
         __syncwarp();
         for (int it = 0; it < n_items; ++it, ++G) {
           const int h = it & 3, kt = it >> 2, gt = gt0 + kt, slot = gt % kG4Ring;
-          mbar_wait(pr, G & 1);  // P_G written, S_G consumed
-          tc_fence_after();
-          if (it + 1 < n_items) {
-            // S of the next item first: the softmax threads wait for it
-            const int h1 = (it + 1) & 3, gt1 = gt0 + ((it + 1) >> 2), slot1 = gt1 % kG4Ring;
-            if (h1 == 0) {
-              mbar_wait(&k_full[slot1], (gt1 / kG4Ring) & 1);
-              tc_fence_after();
-            }
-            if (elect_one()) {
-              umma_f16(tmem, dq + 2 * h1, dk0 + slot1 * (8192 >> 4) + 2 * h1, idesc_s, 0u);
-              umma_commit(s_full);
-              if (h1 == 3) umma_commit(&k_empty[slot1]);        // last read of this K tile by this group
-              if (it + 1 == n_items - 1) umma_commit(q_empty);  // last read of the Q tile
-            }
-            __syncwarp();
-          }
-          // O_h (+)= P_G V_h ; a unit's first tile overwrites the O region (every thread has read the previous unit's O)
+          // ---- everything that does not depend on P_G is prepared BEFORE waiting for it: the softmax threads of this
+          // group stall from their last arrival until S_{G+1} / P.V_G are issued, so the path behind the wait is short
+          const bool have_next = it + 1 < n_items;
+          const int h1 = (it + 1) & 3, gt1 = gt0 + ((it + 1) >> 2), slot1 = gt1 % kG4Ring;
+          const uint64_t dq1 = dq + 2 * h1, dk1 = dk0 + slot1 * (8192 >> 4) + 2 * h1;
+          const uint32_t tO = tmem + 64 + h * 16;
+          const uint64_t dv = dv0 + slot * (8192 >> 4) + h * (2048 >> 4);
+          const bool last_s = (it + 1 == n_items - 1);
+          if (have_next && h1 == 0) mbar_wait(&k_full[slot1], (gt1 / kG4Ring) & 1);
+          // a unit's first tile overwrites the O region (every thread has read the previous unit's O)
           if (it == 0 && U >= 1) mbar_wait(o_read, (U - 1) & 1);
           if (h == 0) mbar_wait(&v_full[slot], (gt / kG4Ring) & 1);
+          mbar_wait(pr, G & 1);  // P_G written, S_G consumed
           tc_fence_after();
           if (elect_one()) {
-            const uint32_t tO = tmem + 64 + h * 16;
-            const uint64_t dv = dv0 + slot * (8192 >> 4) + h * (2048 >> 4);
+            if (have_next) {  // S of the next item first: the softmax threads wait for it
+              umma_f16(tmem, dq1, dk1, idesc_s, 0u);
+              umma_commit(s_full);
+              if (h1 == 3) umma_commit(&k_empty[slot1]);  // last read of this K tile by this group
+              if (last_s) umma_commit(q_empty);           // last read of the Q tile
+            }
+            // O_h (+)= P_G V_h
 #pragma unroll
             for (int k = 0; k < 4; ++k) umma_f16(tO, dp + 2 * k, dv + 2 * k, idesc_o, (kt > 0 || k > 0) ? 1u : 0u);
             umma_commit(pv);
