@@ -4,6 +4,7 @@
 #include "prd_common.cuh"
 #include "prd_embed.h"
 #include "prd_kernels.h"
+#include <stdlib.h>
 
 #include <string>
 
@@ -409,7 +410,10 @@ int prd_triangle_attention_fwd(const PrdDims* d, const void* const* in, void* co
   cudaStream_t st = S(stream);
   const float* pair = in_ptr<float>(in, 0);
   if (triattn_proj(pd(d), pair, d->mode, in_ptr<__half>(w, 0), in_ptr<float>(w, 1), s.q, s.k, s.g, s.vt, st)) return 1;
-  if (d->c_z == 64 && triattn_flash_g4_applies(pd(d)))  // attention core + out_proj + residual in one kernel
+  // the fused variant (out_proj + residual in the attention kernel's unit epilogue) measures 3 % slower than the core +
+  // triattn_out (its epilogue is a serial latency chain per unit): opt-in for A/B timing
+  static const bool fuse = getenv("PRD_FLASH_FUSE") && getenv("PRD_FLASH_FUSE")[0] == '1';
+  if (fuse && d->c_z == 64 && triattn_flash_g4_applies(pd(d)))  // attention core + out_proj + residual in one kernel
     return triattn_flash_out_g4(pd(d), in_ptr<float>(in, 1), s.q, s.k, s.g, s.vt, pair, out_ptr<float>(out, 0), d->residual,
                                 d->mode, in_ptr<__half>(w, 2), in_ptr<float>(w, 3), st);
   if (triattn_flash(pd(d), in_ptr<float>(in, 1), s.q, s.k, s.g, s.vt, s.og, st)) return 1;

@@ -35,7 +35,7 @@ constexpr float kG4LazyBound = 14.0f;  // log2: P <= 2^14 < fp16 max
 // the pairs, FMA-pipe polynomial on 1/4), packed row sum, fp16 pack, two 16-byte stores into the P row.
 template <bool kPoly>
 __device__ __forceinline__ void g4_chunk(const uint32_t (&s)[16], uint64_t nm2, uint64_t (&racc)[2], float (&rm)[2],
-                                         uint32_t sP_row, int t, int c) {
+                                         uint32_t sP_row, int t, int c, uint64_t* p_free = nullptr, uint32_t p_parity = 0) {
   uint32_t ph[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
@@ -54,6 +54,8 @@ __device__ __forceinline__ void g4_chunk(const uint32_t (&s)[16], uint64_t nm2, 
     unpack_f2(y, ya, yb);
     ph[j] = cvt_f16x2(ya, yb);
   }
+  // the P tile is free once P.V of the previous item is complete: waited for here, behind the chunk's arithmetic
+  if (p_free != nullptr) mbar_wait(p_free, p_parity);
 #pragma unroll
   for (int q = 0; q < 2; ++q) {
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sP_row + (((2 * c + q) ^ (t & 7)) << 4)), "r"(ph[4 * q]),
@@ -139,6 +141,7 @@ triattn_flash_g4_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_
       mbar_init(&b[4], 1);    // pv: P.V complete, P free
       mbar_init(&b[5], 128);  // o_read: O region free
       mbar_init(&b[6], 1);    // proj: output projection complete (kFused)
+      mbar_init(&b[7], 128);  // sc: S consumed (its TMEM buffer may be overwritten), ahead of pr
     }
     fence_barrier_init();
     tma_prefetch_desc(&map_q);
@@ -169,6 +172,7 @@ triattn_flash_g4_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_
     uint64_t* pr = &b[3];
     uint64_t* pv = &b[4];
     uint64_t* o_read = &b[5];
+    uint64_t* sc = &b[7];
     const uint32_t tmem = *tmem_slot + g * 128;
     const uint32_t tS = tmem + (static_cast<uint32_t>(w * 32) << 16);
     const uint32_t tO = tS + 64;
@@ -224,10 +228,9 @@ triattn_flash_g4_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_
               float rm[2] = {-INFINITY, -INFINITY};
               uint32_t sa[16], sb[16];
               tmem_ld16(tS, sa);
-              if (G >= 1) mbar_wait(pv, (G - 1) & 1);  // the P tile is free (P.V of the previous item complete)
               tmem_ld_wait16(sa);
               tmem_ld16(tS + 16, sb);
-              g4_chunk<true>(sa, nm2, racc, rm, sP_row, t, 0);
+              g4_chunk<true>(sa, nm2, racc, rm, sP_row, t, 0, G >= 1 ? pv : nullptr, (G - 1) & 1);
               tmem_ld_wait16(sb);
               tmem_ld16(tS + 32, sa);
               g4_chunk<true>(sb, nm2, racc, rm, sP_row, t, 1);
@@ -235,11 +238,19 @@ triattn_flash_g4_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_
               tmem_ld16(tS + 48, sb);
               g4_chunk<true>(sa, nm2, racc, rm, sP_row, t, 2);
               tmem_ld_wait16(sb);
-              g4_chunk<true>(sb, nm2, racc, rm, sP_row, t, 3);
-              // a score that would push P past 2^14: redo the item on the exact path (warp-uniform: the TMEM rescale
-              // there is warp-collective; S is still in its buffer)
-              exact = __any_sync(0xffffffffu, fmaxf(rm[0], rm[1]) - mrow[h] > kG4LazyBound);
+              // the last chunk is in registers: decide NOW whether a score would push P past 2^14 (then the item is
+              // redone on the exact path; warp-uniform, the TMEM rescale there is warp-collective) -- otherwise S is
+              // released a quarter of an item before P is complete, so S_{G+1} is ready when this item ends
+              {
+                float m3 = fmaxf(rm[0], rm[1]);
+#pragma unroll
+                for (int j = 0; j < 16; j += 2) m3 = fmax3(m3, __uint_as_float(sb[j]), __uint_as_float(sb[j + 1]));
+                exact = __any_sync(0xffffffffu, m3 - mrow[h] > kG4LazyBound);
+              }
               if (!exact) {
+                tc_fence_before();
+                mbar_arrive(sc);
+                g4_chunk<true>(sb, nm2, racc, rm, sP_row, t, 3);
                 float r0, r1;
                 unpack_f2(fadd2(racc[0], racc[1]), r0, r1);
                 lrow[h] += r0 + r1;
@@ -289,6 +300,8 @@ triattn_flash_g4_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_
               float r0, r1;
               unpack_f2(fadd2(racc[0], racc[1]), r0, r1);
               lrow[h] += r0 + r1;
+              tc_fence_before();
+              mbar_arrive(sc);
             }
             tc_fence_before();  // S reads (and a possible O rescale) are done before the UMMA warp moves on
             fence_proxy_async_smem();
@@ -397,6 +410,7 @@ triattn_flash_g4_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_
     uint64_t* pr = &b[3];
     uint64_t* pv = &b[4];
     uint64_t* o_read = &b[5];
+    uint64_t* sc = &b[7];
     const uint32_t tmem = *tmem_slot + g * 128;
     const uint64_t dq = umma_desc_sw128(smem_u32(sm + G4Smem::kQ + g * 16384));
     const uint64_t dp = umma_desc_sw128(smem_u32(sm + G4Smem::kP + g * 16384));
@@ -424,7 +438,7 @@ triattn_flash_g4_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_
         }
         mbar_wait(q_full, U & 1);
         // first S of the unit (its S buffer was released by the previous unit's last pass, or never used)
-        if (G >= 1) mbar_wait(pr, (G - 1) & 1);
+        if (G >= 1) mbar_wait(sc, (G - 1) & 1);
         mbar_wait(&k_full[gt0 % kG4Ring], (gt0 / kG4Ring) & 1);
         tc_fence_after();
         if (elect_one()) {
@@ -446,15 +460,18 @@ triattn_flash_g4_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_
           // a unit's first tile overwrites the O region (every thread has read the previous unit's O)
           if (it == 0 && U >= 1) mbar_wait(o_read, (U - 1) & 1);
           if (h == 0) mbar_wait(&v_full[slot], (gt / kG4Ring) & 1);
-          mbar_wait(pr, G & 1);  // P_G written, S_G consumed
+          mbar_wait(sc, G & 1);  // S_G consumed (a quarter of an item before P_G is complete)
+          tc_fence_after();
+          if (have_next && elect_one()) {  // S of the next item: ready when the softmax threads finish this one
+            umma_f16(tmem, dq1, dk1, idesc_s, 0u);
+            umma_commit(s_full);
+            if (h1 == 3) umma_commit(&k_empty[slot1]);  // last read of this K tile by this group
+            if (last_s) umma_commit(q_empty);           // last read of the Q tile
+          }
+          __syncwarp();
+          mbar_wait(pr, G & 1);  // P_G written
           tc_fence_after();
           if (elect_one()) {
-            if (have_next) {  // S of the next item first: the softmax threads wait for it
-              umma_f16(tmem, dq1, dk1, idesc_s, 0u);
-              umma_commit(s_full);
-              if (h1 == 3) umma_commit(&k_empty[slot1]);  // last read of this K tile by this group
-              if (last_s) umma_commit(q_empty);           // last read of the Q tile
-            }
             // O_h (+)= P_G V_h
 #pragma unroll
             for (int k = 0; k < 4; ++k) umma_f16(tO, dp + 2 * k, dv + 2 * k, idesc_o, (kt > 0 || k > 0) ? 1u : 0u);
