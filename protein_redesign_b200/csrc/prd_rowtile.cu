@@ -864,31 +864,28 @@ trimul_out_kernel(const float* pair, float* dst, int residual, const float* __re
     // the previous tile's output rows were staged over the A tiles: its bulk stores must have read them
     bulk_wait_read0();
     g.bar();
-    {
-      // contraction result for this (b,i,j): one value per channel plane, coalesced across lanes
-      float x[CZ];
-      if (valid) {
-        int b, rem;
-        if (r < 0x7fffffffLL && NN < 0x7fffffffLL) {
-          b = static_cast<int>(static_cast<unsigned>(r) / static_cast<unsigned>(NN));
-          rem = static_cast<int>(static_cast<unsigned>(r) - static_cast<unsigned>(b) * static_cast<unsigned>(NN));
-        } else {
-          b = static_cast<int>(r / NN);
-          rem = static_cast<int>(r - (long long)b * NN);
-        }
-        const int i = rem / N, j = rem - i * N;
-        const float* xp = xpl + (long long)b * CZ * xplane + (long long)i * Nx + j;
-#pragma unroll
-        for (int dch = 0; dch < CZ; ++dch) {
-          x[dch] = __ldg(xp);
-          xp += xplane;
-        }
+    // contraction result for this (b,i,j): one value per channel plane, coalesced across lanes.  The 64 loads are
+    // issued first and consumed last: their latency overlaps the pair-row LayerNorm below.
+    float x[CZ];
+    if (valid) {
+      int b, rem;
+      if (r < 0x7fffffffLL && NN < 0x7fffffffLL) {
+        b = static_cast<int>(static_cast<unsigned>(r) / static_cast<unsigned>(NN));
+        rem = static_cast<int>(static_cast<unsigned>(r) - static_cast<unsigned>(b) * static_cast<unsigned>(NN));
       } else {
-#pragma unroll
-        for (int q = 0; q < CZ; ++q) x[q] = 0.f;
+        b = static_cast<int>(r / NN);
+        rem = static_cast<int>(r - (long long)b * NN);
       }
-      layernorm_inplace<CZ>(x);
-      store_a_row<CZ>(sAx, t, x);
+      const int i = rem / N, j = rem - i * N;
+      const float* xp = xpl + (long long)b * CZ * xplane + (long long)i * Nx + j;
+#pragma unroll
+      for (int dch = 0; dch < CZ; ++dch) {
+        x[dch] = __ldg(xp);
+        xp += xplane;
+      }
+    } else {
+#pragma unroll
+      for (int q = 0; q < CZ; ++q) x[q] = 0.f;
     }
     mbar_wait(full, it & 1);
     float xr[CZ];
@@ -909,6 +906,8 @@ trimul_out_kernel(const float* pair, float* dst, int residual, const float* __re
       layernorm_inplace<CZ>(y);
       store_a_row<CZ>(sAp, t, y);
     }
+    layernorm_inplace<CZ>(x);
+    store_a_row<CZ>(sAx, t, x);
     g.sync_before_mma();
     if (t < 32) {  // warp-uniform issue: UMMA operands stay in uniform registers
       tc_fence_after();
