@@ -146,6 +146,21 @@ PRD_DECLARE_OP(remove_mean)
  * in: [noise_pred | seq_pred | noise f32 steps,B,N,3 | coef f32 T,3]  out: [z | seq_t | sampler_state int32[2]] */
 PRD_DECLARE_OP(sampler_update)
 
+/* --- training objective (model.py:471-549) ----------------------------------- */
+/* model.py:471-488 q(): z_t = sa[t] x + s1[t] noise_z; seq_t = keep*seq + drop*(sa[t] seq + s1[t] noise_seq);
+ * seq_t1 = sa[t1] seq + s1[t1] noise_seq with t1 = max(t-1, 0).  d->num_steps = rows of sched.
+ * in: [x f32 B,N,3 | seq (residue_one_hot) f32 B,N,21 | t i64 B | noise_z | noise_seq | keep (residue_extra_mask) B,N |
+ *      drop (residue_inv_extra_mask) B,N | sched f32 T,2 {sqrt_alphas_cumprod, sqrt_one_minus_alphas_cumprod}]
+ * out: [z_t | seq_t | seq_t1] */
+PRD_DECLARE_OP(diffusion_q)
+/* model.py:499-526 (the three loss terms after the network call) + :538-541 (loss = mean(diff_loss / num_nodes)),
+ * and d loss / d noise_pred, d loss / d seq_pred (what autograd hands to the network's backward).
+ * in: [noise_pred | seq_pred | noise_z | noise_seq | seq_t1 | mask (residue_and_atom_mask) | residue_mask |
+ *      residue_type i64 B,N | t i64 B | sched]
+ * out: [loss f32 1 | diff_loss f32 B | terms f32 B+2 {mse_b.., KL, CE} (or NULL) | d_noise_pred (or NULL) |
+ *       d_seq_pred (or NULL)] */
+PRD_DECLARE_OP(diffusion_loss)
+
 /* Profiling hook used by bench.py: average duration (ms) of ONE named kernel ("triattn_flash",
  * "trimul_gemm", "pair_bias") over `iters` launches on the data a previous full op left in the
  * workspace; CUDA events on `stream`.  aux: mask (triattn_flash) / pair (pair_bias). */

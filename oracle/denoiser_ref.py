@@ -394,3 +394,67 @@ def _with_steps(cfg, T):
     import dataclasses
 
     return dataclasses.replace(cfg, num_steps=T)
+
+
+# --------------------------------------------------------------------------------------
+# training objective
+# --------------------------------------------------------------------------------------
+def q_sample(tab: Dict[str, Tensor], x: Tensor, seq: Tensor, t: Tensor, noise_z: Tensor, noise_seq: Tensor,
+             keep: Tensor, drop: Tensor) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
+    """ProteinReDiffModel.q (model.py:471-488): forward noising of the coordinates and of the +-1 one-hot
+    sequence; known residues (``keep`` = residue_extra_mask) stay clean, ``drop`` rows are noised."""
+    sa, s1 = tab["sqrt_alphas_cumprod"], tab["sqrt_one_minus_alphas_cumprod"]
+    z_t = sa[t][:, None, None] * x + s1[t][:, None, None] * noise_z
+    seq_t = sa[t][:, None, None] * seq + s1[t][:, None, None] * noise_seq
+    seq_t = keep.unsqueeze(-1) * seq + drop.unsqueeze(-1) * seq_t
+    t1 = (t - 1).clamp(min=0)
+    seq_t1 = sa[t1][:, None, None] * seq + s1[t1][:, None, None] * noise_seq
+    return z_t, seq_t, seq_t1, t1
+
+
+def loss_from_outputs(tab: Dict[str, Tensor], batch: Dict[str, Tensor], noise_pred: Tensor, seq_pred: Tensor,
+                      noise_z: Tensor, noise_seq: Tensor, seq_t1: Tensor, t1: Tensor) -> Tensor:
+    """The three terms of ProteinReDiffModel.diffusion_loss after the network call (model.py:499-526):
+    per-row noise MSE (sum) + KL(softmax(seq_{t-1}) || softmax(seq_pred_{t-1})) + CE((seq_pred+1)/2, type;
+    ignore_index 0) * mask; the KL and CE terms are scalar sums added to every batch row (:512-525).
+    Returns diff_loss [B]."""
+    mask, residue_mask = batch["residue_and_atom_mask"], batch["residue_mask"]
+    sa, s1 = tab["sqrt_alphas_cumprod"], tab["sqrt_one_minus_alphas_cumprod"]
+    seq_pred_t1 = sa[t1][:, None, None] * seq_pred + s1[t1][:, None, None] * noise_seq
+    diff = (mask.unsqueeze(-1) * torch.square(noise_pred - noise_z)).sum(dim=(1, 2))
+    diff = diff + F.kl_div(torch.log_softmax(seq_pred_t1, dim=-1) * residue_mask.unsqueeze(-1),
+                           torch.softmax(seq_t1, dim=-1) * residue_mask.unsqueeze(-1), reduction="none").sum()
+    logits = (seq_pred + 1) / 2
+    ce = F.cross_entropy(logits.reshape(-1, 21), batch["residue_type"].reshape(-1), reduction="none", ignore_index=0)
+    return diff + (ce * mask.reshape(-1)).sum()
+
+
+def diffusion_loss(sd: SD, cfg, batch: Dict[str, Tensor], x: Tensor, mask: Tensor, t: Tensor,
+                   randn_like: Callable[[Tensor], Tensor] = torch.randn_like,
+                   outputs: Optional[list] = None) -> Tensor:
+    """ProteinReDiffModel.diffusion_loss (model.py:490-526) on a prepared batch; draw order: noise_z, noise_seq.
+    ``outputs`` (a list) receives (noise_pred, seq_pred) so that tests can differentiate with respect to them."""
+    tab = schedule_tables(cfg.num_steps, cfg.diffusion_schedule)
+    seq, residue_mask = batch["residue_one_hot"], batch["residue_mask"]
+    noise_z = remove_mean(randn_like(x), mask)
+    noise_seq = remove_mean(randn_like(seq), residue_mask)
+    z_t, seq_t, seq_t1, t1 = q_sample(tab, x, seq, t, noise_z, noise_seq, batch["residue_extra_mask"],
+                                      batch["residue_inv_extra_mask"])
+    noise_pred, seq_pred = denoiser_step(sd, cfg, batch, z_t, seq_t, mask, t)
+    if outputs is not None:
+        noise_pred, seq_pred = noise_pred.detach().requires_grad_(), seq_pred.detach().requires_grad_()
+        outputs.extend([noise_pred, seq_pred])
+    return loss_from_outputs(tab, batch, noise_pred, seq_pred, noise_z, noise_seq, seq_t1, t1)
+
+
+def training_loss(sd: SD, cfg, batch: Dict[str, Tensor], randn_like: Callable[[Tensor], Tensor] = torch.randn_like,
+                  outputs: Optional[list] = None) -> Tuple[Tensor, Tensor, Tensor]:
+    """ProteinReDiffModel.training_step (model.py:528-549) with training_mode=False: prepare_batch
+    (one CPU randperm), t ~ randint(0, T, (B,)) from the global CPU generator, loss = mean(diff_loss / num_nodes).
+    Returns (loss, diff_loss [B], t)."""
+    batch = prepare_batch(batch, cfg.mask_prob)
+    x, mask = batch["x"], batch["residue_and_atom_mask"]
+    num_nodes = (mask > 0.5).sum(dim=1)
+    t = torch.randint(0, cfg.num_steps, size=(x.shape[0],))
+    diff = diffusion_loss(sd, cfg, batch, x, mask, t, randn_like, outputs)
+    return torch.mean(diff / num_nodes), diff, t

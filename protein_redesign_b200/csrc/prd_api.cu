@@ -3,6 +3,7 @@
 #include "../../include/prd_denoiser.h"
 #include "prd_common.cuh"
 #include "prd_embed.h"
+#include "prd_loss.h"
 #include "prd_kernels.h"
 #include <stdlib.h>
 
@@ -547,6 +548,40 @@ int prd_sampler_update_fwd(const PrdDims* d, const void* const* in, void* const*
   return sampler_update(d->B, d->N, in_ptr<float>(in, 0), in_ptr<float>(in, 1), in_ptr<float>(in, 2),
                         in_ptr<float>(in, 3), static_cast<SamplerState*>(out[2]), out_ptr<float>(out, 0),
                         out_ptr<float>(out, 1), S(stream));
+}
+
+// ----------------------------------------------------------------------------- diffusion_q
+size_t prd_diffusion_q_workspace_bytes(const PrdDims*) { return 256; }
+int prd_diffusion_q_fwd(const PrdDims* d, const void* const* in, void* const* out, const void* const*, void*, size_t,
+                        void* stream) {
+  if (prd_device_check()) return 1;
+  PRD_REQUIRE(d->num_steps > 0, "diffusion_q: num_steps must be positive");
+  return diffusion_q(d->B, d->N, d->num_steps, in_ptr<float>(in, 0), in_ptr<float>(in, 1), in_ptr<int64_t>(in, 2),
+                     in_ptr<float>(in, 3), in_ptr<float>(in, 4), in_ptr<float>(in, 5), in_ptr<float>(in, 6),
+                     in_ptr<float>(in, 7), out_ptr<float>(out, 0), out_ptr<float>(out, 1), out_ptr<float>(out, 2),
+                     S(stream));
+}
+
+// -------------------------------------------------------------------------- diffusion_loss
+size_t prd_diffusion_loss_workspace_bytes(const PrdDims* d) {
+  Carver c(nullptr);
+  c.take<float>((size_t)d->B);
+  c.take<float>((size_t)d->B * d->N * 3);
+  return c.total();
+}
+int prd_diffusion_loss_fwd(const PrdDims* d, const void* const* in, void* const* out, const void* const*, void* workspace,
+                           size_t workspace_bytes, void* stream) {
+  if (prd_device_check()) return 1;
+  PRD_WS_CHECK(prd_diffusion_loss_workspace_bytes(d));
+  PRD_REQUIRE(d->num_steps > 0, "diffusion_loss: num_steps must be positive");
+  Carver c(workspace);
+  float* row_w = c.take<float>((size_t)d->B);
+  float* partial = c.take<float>((size_t)d->B * d->N * 3);
+  return diffusion_loss(d->B, d->N, d->num_steps, in_ptr<float>(in, 0), in_ptr<float>(in, 1), in_ptr<float>(in, 2),
+                        in_ptr<float>(in, 3), in_ptr<float>(in, 4), in_ptr<float>(in, 5), in_ptr<float>(in, 6),
+                        in_ptr<int64_t>(in, 7), in_ptr<int64_t>(in, 8), in_ptr<float>(in, 9), row_w, partial,
+                        out_ptr<float>(out, 0), out_ptr<float>(out, 1), out_ptr<float>(out, 2), out_ptr<float>(out, 3),
+                        out_ptr<float>(out, 4), S(stream));
 }
 
 }  // extern "C"

@@ -287,8 +287,64 @@ class ProteinReDiffModel(_Base):
         with self.ema.average_parameters():
             return self.sample(batch)
 
-    def training_step(self, batch, batch_idx):
-        raise NotImplementedError("training needs backward kernels, which are not part of this build (SURVEY §8f)")
+    # ---- training objective (reference model.py:471-549) ---------------------------
+    def _sched_table(self):
+        tab = getattr(self, "_sched", None)
+        if tab is None or tab.device != self._device or tab.shape[0] != self.num_steps:
+            self._sched = tab = torch.stack([self.sqrt_alphas_cumprod, self.sqrt_one_minus_alphas_cumprod], dim=1).contiguous()
+        return tab
+
+    def q(self, x, seq, t, noise_z, noise_seq, batch):
+        """Forward noising step (reference model.py:471-488) -> (z_t, seq_t, seq_t1, t1)."""
+        z_t, seq_t, seq_t1 = ops.diffusion_q(self.cfg, x.contiguous(), seq.contiguous(), t.contiguous(), noise_z.contiguous(),
+                                             noise_seq.contiguous(), batch["residue_extra_mask"].contiguous(),
+                                             batch["residue_inv_extra_mask"].contiguous(), self._sched_table())
+        return z_t, seq_t, seq_t1, (t - 1).clamp(min=0)
+
+    def diffusion_loss(self, batch, x, mask, t, noise: Optional[Dict[str, torch.Tensor]] = None, want_grads: bool = False,
+                       detail: Optional[dict] = None):
+        """reference model.py:490-526: draws noise_z / noise_seq (or takes raw N(0,1) draws from ``noise`` with keys
+        ``z`` [B,N,3] and ``seq`` [B,N,21]), removes their masked means, applies q(), evaluates the network and the three
+        loss terms, all on device.  Returns diff_loss [B]; ``detail`` (a dict) receives loss, terms, the network outputs
+        and, with ``want_grads``, d loss / d noise_pred and d loss / d seq_pred."""
+        seq, residue_mask = batch["residue_one_hot"].to(torch.float32).contiguous(), batch["residue_mask"].contiguous()
+        mask, x = mask.contiguous(), x.contiguous()
+        noise_z = (noise["z"].to(x.device, torch.float32).clone() if noise is not None else torch.randn_like(x)).contiguous()
+        noise_seq = (noise["seq"].to(x.device, torch.float32).clone() if noise is not None else torch.randn_like(seq)).contiguous()
+        ops.remove_mean(self.cfg, noise_z, mask)
+        ops.remove_mean(self.cfg, noise_seq, residue_mask)
+        z_t, seq_t, seq_t1, _ = self.q(x, seq, t, noise_z, noise_seq, batch)
+        noise_pred, seq_pred = self._denoise(batch, z_t, seq_t, mask, t.contiguous())
+        loss, diff, terms, d_noise, d_seq = ops.diffusion_loss(
+            self.cfg, noise_pred, seq_pred, noise_z, noise_seq, seq_t1, mask, residue_mask,
+            batch["residue_type"].contiguous(), t.contiguous(), self._sched_table(), want_grads=want_grads)
+        if detail is not None:
+            detail.update(loss=loss, terms=terms, noise_pred=noise_pred, seq_pred=seq_pred, z_t=z_t, seq_t=seq_t,
+                          d_noise_pred=d_noise, d_seq_pred=d_seq)
+        return diff
+
+    def training_step(self, batch, batch_idx, noise: Optional[Dict[str, torch.Tensor]] = None, detail: Optional[dict] = None):
+        """reference model.py:528-549: prepare_batch, t ~ randint(0, T) drawn on the CPU generator as the reference does,
+        loss = mean(diff_loss / num_nodes), evaluated by the CUDA kernels.  The objective and its gradient with respect
+        to the network outputs are built; the backward pass through the network is not, so the
+        returned loss carries no autograd graph and the call refuses to run with gradients enabled."""
+        if torch.is_grad_enabled():
+            raise NotImplementedError(
+                "training_step computes the loss forward (and d loss / d outputs) only: the network's backward kernels are "
+                "not part of this build (SURVEY §8f item 1); call it under torch.no_grad()")
+        if not self.setup_schedule:
+            self.run_setup_schedule()
+            self.setup_schedule = True
+        batch = self.prepare_batch(batch, batch_idx)
+        x, mask = batch["x"], batch["residue_and_atom_mask"]
+        t = torch.randint(0, self.num_steps, size=(x.size(0),)).to(x.device)
+        d = detail if detail is not None else {}
+        self.diffusion_loss(batch, x, mask, t, noise=noise, want_grads=detail is not None, detail=d)
+        d["t"] = t
+        loss = d["loss"].reshape(())
+        if hasattr(self, "log"):
+            self.log("train_loss", loss, on_step=True, on_epoch=True, sync_dist=True, batch_size=x.size(0))
+        return loss
 
     # ---- sampler (reference model.py:377-422) ------------------------------------------------
     @torch.inference_mode()

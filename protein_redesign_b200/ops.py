@@ -175,3 +175,37 @@ def sampler_update(cfg, noise_pred, seq_pred, noise, coef, z, seq_t, state):
     _chk([noise_pred, seq_pred, noise, coef, z, seq_t], [F32] * 6, ["noise_pred", "seq_pred", "noise", "coef", "z", "seq_t"])
     _lib.check_tensor(state, torch.int32, "sampler_state")
     _lib.call("sampler_update", make_dims(cfg, B, N), [noise_pred, seq_pred, noise, coef], [z, seq_t, state], [])
+
+
+def diffusion_q(cfg, x, seq, t, noise_z, noise_seq, keep, drop, sched):
+    """Forward noising (reference model.py:471-488).  sched: [T, 2] = {sqrt_alphas_cumprod, sqrt_one_minus_alphas_cumprod}."""
+    B, N, _ = x.shape
+    _chk([x, seq, t, noise_z, noise_seq, keep, drop, sched], [F32, F32, I64, F32, F32, F32, F32, F32],
+         ["x", "seq", "t", "noise_z", "noise_seq", "residue_extra_mask", "residue_inv_extra_mask", "sched"])
+    z_t, seq_t, seq_t1 = torch.empty_like(x), torch.empty_like(seq), torch.empty_like(seq)
+    d = make_dims(cfg, B, N)
+    d.num_steps = sched.shape[0]
+    _lib.call("diffusion_q", d, [x, seq, t, noise_z, noise_seq, keep, drop, sched], [z_t, seq_t, seq_t1], [])
+    return z_t, seq_t, seq_t1
+
+
+def diffusion_loss(cfg, noise_pred, seq_pred, noise_z, noise_seq, seq_t1, mask, residue_mask, residue_type, t, sched,
+                   want_grads: bool = False):
+    """Loss terms after the network call + loss = mean(diff_loss / num_nodes) (reference model.py:499-526, 538-541).
+    Returns (loss [1], diff_loss [B], terms [B+2] = per-row MSE | KL | CE, d_noise_pred, d_seq_pred); the gradients
+    are None unless ``want_grads``."""
+    B, N, _ = noise_pred.shape
+    _chk([noise_pred, seq_pred, noise_z, noise_seq, seq_t1, mask, residue_mask, residue_type, t, sched],
+         [F32, F32, F32, F32, F32, F32, F32, I64, I64, F32],
+         ["noise_pred", "seq_pred", "noise_z", "noise_seq", "seq_t1", "mask", "residue_mask", "residue_type", "t", "sched"])
+    dev = noise_pred.device
+    loss = torch.empty(1, dtype=F32, device=dev)
+    diff = torch.empty(B, dtype=F32, device=dev)
+    terms = torch.empty(B + 2, dtype=F32, device=dev)
+    d_noise = torch.empty_like(noise_pred) if want_grads else None
+    d_seq = torch.empty_like(seq_pred) if want_grads else None
+    d = make_dims(cfg, B, N)
+    d.num_steps = sched.shape[0]
+    _lib.call("diffusion_loss", d, [noise_pred, seq_pred, noise_z, noise_seq, seq_t1, mask, residue_mask, residue_type, t, sched],
+              [loss, diff, terms, d_noise, d_seq], [])
+    return loss, diff, terms, d_noise, d_seq

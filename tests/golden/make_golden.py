@@ -29,6 +29,11 @@ sys.path.insert(0, ROOT)
 from protein_redesign_b200 import synthetic as syn  # noqa: E402
 
 REFERENCE_ROOT = "/root/reference"
+ONLY_NEW = "--only-new" in sys.argv  # add missing fixtures without rewriting the existing ones
+
+
+def _skip(kind, tag):
+    return ONLY_NEW and os.path.exists(os.path.join(HERE, f"{kind}_{tag}.npz"))
 
 
 def install_stubs() -> None:
@@ -129,6 +134,8 @@ def capture_modules(model, names):
 
 
 def gen_step_case(tag, cfg, sizes, seed, n_total=None, two_chains=False, probes=False, out=None):
+    if _skip("step", tag):
+        return
     model, sd = load_reference_model(cfg, seed)
     batch = syn.make_batch(cfg, sizes, seed=seed, n_total=n_total, two_chains=two_chains)
     pb = ref_prepare(model, batch, torch_seed=seed)
@@ -171,6 +178,8 @@ def gen_step_case(tag, cfg, sizes, seed, n_total=None, two_chains=False, probes=
 def gen_sample_case(tag, cfg, sizes, seed, n_total=None):
     """Full sampler with injected noise: torch.randn_like is replaced by draws from a seeded
     generator, in the reference's own draw order."""
+    if _skip("sample", tag):
+        return
     model, sd = load_reference_model(cfg, seed)
     batch = syn.make_batch(cfg, sizes, seed=seed, n_total=n_total)
     g = torch.Generator().manual_seed(seed + 31337)
@@ -204,6 +213,66 @@ def gen_sample_case(tag, cfg, sizes, seed, n_total=None):
     print(f"{tag}: pos rms {pos.square().mean().sqrt():.3f} A -> {os.path.relpath(path, ROOT)}")
 
 
+def gen_loss_case(tag, cfg, sizes, seed, n_total=None, two_chains=False):
+    """training_step (model.py:528-549, training_mode=False: SURVEY N8) with injected randn_like draws; stores the
+    loss, diff_loss, t, the q() outputs, the network outputs and d loss / d (noise_pred, seq_pred) from autograd."""
+    if _skip("loss", tag):
+        return
+    model, sd = load_reference_model(cfg, seed)
+    batch = syn.make_batch(cfg, sizes, seed=seed, n_total=n_total, two_chains=two_chains, with_positions=True)
+    g = torch.Generator().manual_seed(seed + 4242)
+    cap = {}
+
+    def fake_randn_like(x, **kw):
+        return torch.randn(x.shape, generator=g, dtype=x.dtype)
+
+    fwd = model.forward
+
+    def spy_forward(b, z, seq_t, mask, t):
+        noise_pred, seq_pred = fwd(b, z, seq_t, mask, t)
+        noise_pred.retain_grad()
+        seq_pred.retain_grad()
+        cap.update(z_t=z.detach().clone(), seq_t=seq_t.detach().clone(), t=t.clone(), noise_pred=noise_pred,
+                   seq_pred=seq_pred)
+        return noise_pred, seq_pred
+
+    diff = {}
+    dl = model.diffusion_loss
+
+    def spy_loss(*a, **k):
+        out = dl(*a, **k)
+        diff["diff_loss"] = out.detach().clone()
+        return out
+
+    model.forward = spy_forward
+    model.diffusion_loss = spy_loss
+    orig = torch.randn_like
+    torch.randn_like = fake_randn_like
+    try:
+        torch.manual_seed(seed)
+        loss = model.training_step(clone_batch(batch), 0)
+        loss.backward()
+    finally:
+        torch.randn_like = orig
+    rec = {
+        "weights_checksum": syn.checksum(sd),
+        "batch_checksum": syn.checksum(batch),
+        "loss": loss.detach().numpy(),
+        "diff_loss": diff["diff_loss"].numpy(),
+        "t": cap["t"].numpy(),
+        "z_t": cap["z_t"].numpy(),
+        "seq_t": cap["seq_t"].numpy(),
+        "noise_pred": cap["noise_pred"].detach().numpy(),
+        "seq_pred": cap["seq_pred"].detach().numpy(),
+        "d_noise_pred": cap["noise_pred"].grad.numpy(),
+        "d_seq_pred": cap["seq_pred"].grad.numpy(),
+    }
+    path = os.path.join(HERE, f"loss_{tag}.npz")
+    np.savez_compressed(path, **rec)
+    print(f"{tag}: loss {float(loss):.5f} t {cap['t'].tolist()} -> {os.path.relpath(path, ROOT)}"
+          f" ({os.path.getsize(path) / 1024:.0f} KiB)")
+
+
 def main():
     torch.set_num_threads(os.cpu_count() or 1)
     # (1) tiny dims, every module probed, ragged batch with padding + two chains.
@@ -218,6 +287,14 @@ def main():
                     [(5, 14), (3, 9)], seed=5)
     gen_sample_case("tiny_T6_cos", syn.DenoiserConfig(**{**syn.TINY.__dict__, "num_steps": 6, "mask_prob": 1.0,
                                                          "diffusion_schedule": "cosine"}), [(4, 12)], seed=6)
+    # north_star: a 50-step fixed-noise trajectory
+    gen_sample_case("tiny_T50", syn.DenoiserConfig(**{**syn.TINY.__dict__, "num_steps": 50, "mask_prob": 0.3}),
+                    [(5, 14), (3, 9)], seed=8)
+    # (5) training objective (a18): q(), the three loss terms and the gradient with respect to the network outputs
+    gen_loss_case("tiny", syn.DenoiserConfig(**{**syn.TINY.__dict__, "mask_prob": 0.15}), [(5, 14), (3, 9)], seed=9,
+                  n_total=22, two_chains=True)
+    gen_loss_case("readme_n40", syn.DenoiserConfig(**{**syn.README.__dict__, "mask_prob": 0.15, "num_steps": 2000}),
+                  [(8, 32), (6, 27)], seed=10)
 
 
 if __name__ == "__main__":

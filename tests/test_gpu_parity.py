@@ -29,7 +29,7 @@ CASE_NAMES = [
     "trimul_readme", "trimul_n140", "trimul_n300", "triattn_starting", "triattn_ending", "triattn_n200", "triattn_n140",
     "triattn_n300", "triattn_n512", "triattn_readme", "outer_linear", "outer_linear_readme", "outer_linear_n300",
     "single_attention", "single_transition", "spattention", "opm", "embeddings", "embeddings_readme", "heads",
-    "pair_bias", "sample_eager", "sample_graph", "invariants",
+    "pair_bias", "sample_eager", "sample_graph", "invariants", "sample_graph_T50", "loss_paper_n72",
 ]
 
 
@@ -48,6 +48,28 @@ def test_step_vs_oracle_and_reference_golden(tag, cfg_name, sizes, seed):
     from protein_redesign_b200 import synthetic as syn
     gold = load_golden(f"step_{tag}.npz")
     _check(gc.case_step(getattr(syn, cfg_name), sizes, seed=seed, golden=gold, probes=(tag == "paper_n72")))
+
+
+@pytest.mark.parametrize("tag,cfg_name,over,sizes,seed,kw", [
+    ("readme_n40", "README", dict(mask_prob=0.15, num_steps=2000), ((8, 32), (6, 27)), 10, {}),
+])
+def test_training_objective_vs_oracle_and_reference_golden(tag, cfg_name, over, sizes, seed, kw):
+    import dataclasses
+    gc = _cases()
+    from protein_redesign_b200 import synthetic as syn
+    cfg = dataclasses.replace(getattr(syn, cfg_name), **over)
+    _check(gc.case_loss(cfg, sizes, seed, golden=load_golden(f"loss_{tag}.npz"), **kw))
+
+
+def test_training_step_refuses_autograd():
+    """The backward pass through the network is not built: training_step must say so instead of returning a loss that
+    silently has no graph."""
+    from protein_redesign_b200 import synthetic as syn
+    gc = _cases()
+    m, _ = gc._model(syn.README, 0)
+    batch = gc._to_dev(syn.make_batch(syn.README, [(4, 12)], seed=0, with_positions=True))
+    with torch.enable_grad(), pytest.raises(NotImplementedError):
+        m.training_step(batch, 0)
 
 
 def test_cpu_tensor_is_rejected():

@@ -107,6 +107,7 @@ def test_module_probes_match_reference():
 @pytest.mark.parametrize("tag,cfg_over,sizes,seed", [
     ("tiny_T8", dict(num_steps=8, mask_prob=0.3), [(5, 14), (3, 9)], 5),
     ("tiny_T6_cos", dict(num_steps=6, mask_prob=1.0, diffusion_schedule="cosine"), [(4, 12)], 6),
+    ("tiny_T50", dict(num_steps=50, mask_prob=0.3), [(5, 14), (3, 9)], 8),  # north_star: 50-step fixed-noise trajectory
 ])
 def test_sampler_matches_reference(tag, cfg_over, sizes, seed):
     cfg = dataclasses.replace(syn.TINY, **cfg_over)
@@ -131,6 +132,39 @@ def test_sampler_matches_reference(tag, cfg_over, sizes, seed):
     assert n_draws[0] == int(gold["num_draws"])
     assert rel_l2(pos, torch.from_numpy(gold["pos"])) < 1e-4
     assert rel_l2(logits, torch.from_numpy(gold["logits"])) < 1e-4
+    rmsd = float((pos - torch.from_numpy(gold["pos"])).square().sum(-1).mean().sqrt())
+    assert rmsd < 1e-3, rmsd  # Angstrom
+
+
+LOSS_CASES = {
+    "tiny": (dataclasses.replace(syn.TINY, mask_prob=0.15), [(5, 14), (3, 9)], 9, dict(n_total=22, two_chains=True)),
+    "readme_n40": (dataclasses.replace(syn.README, mask_prob=0.15, num_steps=2000), [(8, 32), (6, 27)], 10, {}),
+}
+
+
+@pytest.mark.parametrize("tag", list(LOSS_CASES))
+def test_training_loss_matches_reference(tag):
+    """a18: prepare_batch + randint + q() + the three loss terms vs the reference's training_step, and the gradient of
+    the loss with respect to the network outputs vs the reference's autograd."""
+    cfg, sizes, seed, kw = LOSS_CASES[tag]
+    gold = load_golden(f"loss_{tag}.npz")
+    sd = syn.make_state_dict(cfg, seed)
+    batch = syn.make_batch(cfg, sizes, seed=seed, with_positions=True, **kw)
+    assert syn.checksum(sd) == str(gold["weights_checksum"])
+    assert syn.checksum(batch) == str(gold["batch_checksum"])
+    g = torch.Generator().manual_seed(seed + 4242)
+    outs = []
+    torch.manual_seed(seed)
+    loss, diff, t = ref.training_loss(sd, cfg, batch, randn_like=lambda x: torch.randn(x.shape, generator=g, dtype=x.dtype),
+                                      outputs=outs)
+    assert np.array_equal(t.numpy(), gold["t"])  # index path: bit exact
+    assert rel_l2(outs[0], torch.from_numpy(gold["noise_pred"])) < 2e-5
+    assert rel_l2(outs[1], torch.from_numpy(gold["seq_pred"])) < 2e-5
+    assert rel_l2(diff, torch.from_numpy(gold["diff_loss"])) < 1e-5
+    assert abs(float(loss.detach()) - float(gold["loss"])) < 1e-5 * abs(float(gold["loss"]))
+    loss.backward()
+    assert rel_l2(outs[0].grad, torch.from_numpy(gold["d_noise_pred"])) < 1e-5
+    assert rel_l2(outs[1].grad, torch.from_numpy(gold["d_seq_pred"])) < 1e-5
 
 
 def test_oracle_invariants():
