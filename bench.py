@@ -121,6 +121,54 @@ def cpu_reference_step_time(steps: int, warmup: int, budget_s: float = 150.0):
     return sum(times) / len(times), len(times), cores
 
 
+def gpu_eager_step_time(dev, B: int, steps: int = 3, warmup: int = 1):
+    """Second baseline: the reference's algorithm as eager fp32 PyTorch (the oracle port, stock ATen /
+    cuBLAS kernels, torch's default matmul precision) on the SAME B200, timed with CUDA events.  Not the product path."""
+    from oracle import denoiser_ref as ref
+
+    cfg = syn.PAPER
+    sd = {k: v.to(dev) for k, v in syn.make_state_dict(cfg, 0).items()}
+    batch = syn.make_batch(cfg, [(N_ATOMS, N_TOKENS - N_ATOMS)] * B, seed=0)
+    z, seq_t, mask, t = syn.make_step_inputs(batch, cfg.num_steps, 0)
+    torch.manual_seed(0)
+    pb = {k: (v.to(dev) if isinstance(v, torch.Tensor) else v) for k, v in ref.prepare_batch(batch, cfg.mask_prob).items()}
+    z, seq_t, mask, t = z.to(dev), seq_t.to(dev), mask.to(dev), t.to(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.inference_mode():
+        for _ in range(warmup):
+            ref.denoiser_step(sd, cfg, pb, z, seq_t, mask, t)
+        torch.cuda.synchronize(dev)
+        e0.record()
+        for _ in range(steps):
+            ref.denoiser_step(sd, cfg, pb, z, seq_t, mask, t)
+        e1.record()
+        torch.cuda.synchronize(dev)
+    peak = torch.cuda.max_memory_allocated(dev)
+    return e0.elapsed_time(e1) / steps * 1e-3, peak
+
+
+def gpu_eager_baseline(dev):
+    torch.cuda.empty_cache()
+    torch.cuda.reset_peak_memory_stats(dev)
+    try:
+        try:
+            t_step, peak = gpu_eager_step_time(dev, BATCH)
+            rec = {"value": 1.0 / t_step, "sample": f"3 timed steps (1 warm-up) at B={BATCH}, N={N_TOKENS}"}
+        except torch.OutOfMemoryError:
+            torch.cuda.empty_cache()
+            t_step, peak = gpu_eager_step_time(dev, 1)
+            rec = {"value": 1.0 / (BATCH * t_step),
+                   "sample": f"3 timed steps (1 warm-up) at B=1, N={N_TOKENS} (B={BATCH} does not fit); value = 1 / ({BATCH} * {t_step * 1e3:.1f} ms)"}
+        rec.update({"unit": UNIT, "kind": "port", "device": torch.cuda.get_device_name(dev), "dtype": "f32 (torch defaults)",
+                    "peak_mem_gb": round(peak / 1e9, 1),
+                    "what": "eager PyTorch port of the reference forward (oracle/denoiser_ref.py) on the same GPU"})
+        return rec
+    except Exception as e:  # a baseline must never take the bench line down
+        return {"unavailable": f"{type(e).__name__}: {e}"[:200]}
+    finally:
+        torch.cuda.empty_cache()
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -292,6 +340,7 @@ def run_ours(args):
             cpu = {"value": 1.0 / (BATCH * t_step), "unit": UNIT, "cores": cores, "kind": "port",
                    "sample": f"{n} timed step (after 1 warm-up) of the CPU oracle on ONE complex (B=1) of the N=512 workload; "
                              f"value = 1 / (8 * {t_step:.2f} s)"}
+        eager = gpu_eager_baseline(dev) if world == 1 and not args.no_gpu_eager else None
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -306,6 +355,7 @@ def run_ours(args):
             "clocks": clocks,
             "roofline": roof,
             "cpu_baseline": cpu,
+            "gpu_eager_baseline": eager,
             "flops_per_step": 6730.6e9,
             "achieved_tflops_step": 6730.6e9 / (ms_per_step * 1e-3) / 1e12,
         }
@@ -387,6 +437,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gpu-eager", action="store_true", help="skip the eager-PyTorch-on-the-same-GPU baseline")
     ap.add_argument("--profile-eager", action="store_true",
                     help="run the steps eagerly (no CUDA graph, no e2e / CPU legs): for ncu launch lists")
     args = ap.parse_args()

@@ -8,7 +8,9 @@ kernels through libprd_sm100 (include/prd_denoiser.h); ``sample`` captures one r
 step as a CUDA graph and replays it ``num_steps`` times with the schedule, the noise and the
 step counter resident on the device.
 
-Not in this build: the backward pass (``training_step`` raises), ESM loading, Lightning hooks.
+``q``, ``diffusion_loss``, ``validation_step`` and the forward half of ``training_step`` (reference model.py:471-549,
+226-247) run on the loss kernels (csrc/prd_loss.cu).  Not in this build: the backward pass through the network
+(``training_step`` refuses to run with autograd enabled), ESM loading.
 """
 from __future__ import annotations
 
@@ -323,28 +325,76 @@ class ProteinReDiffModel(_Base):
                           d_noise_pred=d_noise, d_seq_pred=d_seq)
         return diff
 
-    def training_step(self, batch, batch_idx, noise: Optional[Dict[str, torch.Tensor]] = None, detail: Optional[dict] = None):
-        """reference model.py:528-549: prepare_batch, t ~ randint(0, T) drawn on the CPU generator as the reference does,
-        loss = mean(diff_loss / num_nodes), evaluated by the CUDA kernels.  The objective and its gradient with respect
-        to the network outputs are built; the backward pass through the network is not, so the
-        returned loss carries no autograd graph and the call refuses to run with gradients enabled."""
-        if torch.is_grad_enabled():
-            raise NotImplementedError(
-                "training_step computes the loss forward (and d loss / d outputs) only: the network's backward kernels are "
-                "not part of this build (SURVEY §8f item 1); call it under torch.no_grad()")
+    def _objective(self, batch, batch_idx, noise, detail, want_grads):
+        """Shared by training_step / validation_step (reference model.py:528-541 / :226-240)."""
         if not self.setup_schedule:
             self.run_setup_schedule()
             self.setup_schedule = True
         batch = self.prepare_batch(batch, batch_idx)
         x, mask = batch["x"], batch["residue_and_atom_mask"]
-        t = torch.randint(0, self.num_steps, size=(x.size(0),)).to(x.device)
+        t = torch.randint(0, self.num_steps, size=(x.size(0),)).to(x.device)  # CPU generator, as the reference
         d = detail if detail is not None else {}
-        self.diffusion_loss(batch, x, mask, t, noise=noise, want_grads=detail is not None, detail=d)
+        self.diffusion_loss(batch, x, mask, t, noise=noise, want_grads=want_grads, detail=d)
         d["t"] = t
-        loss = d["loss"].reshape(())
+        return d["loss"].reshape(()), x.size(0)
+
+    def training_step(self, batch, batch_idx, noise: Optional[Dict[str, torch.Tensor]] = None, detail: Optional[dict] = None):
+        """reference model.py:528-549: prepare_batch, t ~ randint(0, T), loss = mean(diff_loss / num_nodes), evaluated by
+        the CUDA kernels.  The objective and its gradient with respect to the network outputs (``detail``) are built; the
+        backward pass through the network is not, so the returned loss carries no autograd graph and
+        the call refuses to run with gradients enabled instead of returning a loss that silently cannot train."""
+        if torch.is_grad_enabled():
+            raise NotImplementedError(
+                "training_step computes the loss forward (and d loss / d outputs) only: the network's backward kernels are "
+                "not part of this build (SURVEY §8f item 1); call it under torch.no_grad(), or use validation_step")
+        loss, bs = self._objective(batch, batch_idx, noise, detail, want_grads=detail is not None)
         if hasattr(self, "log"):
-            self.log("train_loss", loss, on_step=True, on_epoch=True, sync_dist=True, batch_size=x.size(0))
+            self.log("train_loss", loss, on_step=True, on_epoch=True, sync_dist=True, batch_size=bs)
         return loss
+
+    @torch.no_grad()
+    def validation_step(self, batch, batch_idx, noise: Optional[Dict[str, torch.Tensor]] = None, detail: Optional[dict] = None):
+        """reference model.py:226-247: the same objective under the EMA weights, logged as ``val_loss`` (the reference
+        returns None; the loss is returned here as well)."""
+        with self.ema.average_parameters():
+            loss, bs = self._objective(batch, batch_idx, noise, detail, want_grads=False)
+        if hasattr(self, "log"):
+            self.log("val_loss", loss, on_epoch=True, sync_dist=True, batch_size=bs)
+        return loss
+
+    # ---- checkpoint / optimiser glue (reference model.py:192-217; host side, not on the hot path) ----------
+    def to(self, *args, **kwargs):
+        out = torch._C._nn._parse_to(*args, **kwargs)
+        self.ema.to(device=out[0], dtype=out[1])
+        return super().to(*args, **kwargs)
+
+    def on_save_checkpoint(self, checkpoint):
+        checkpoint["ema_state_dict"] = self.ema.state_dict()
+
+    def on_load_checkpoint(self, checkpoint):
+        self.ema.load_state_dict(checkpoint["ema_state_dict"])
+
+    def configure_optimizers(self):
+        optimizer = torch.optim.Adam(self.parameters(), lr=self.learning_rate)
+        scheduler = torch.optim.lr_scheduler.LinearLR(optimizer, start_factor=1.0 / self.warmup_steps,
+                                                      total_iters=self.warmup_steps - 1)
+        return {"optimizer": optimizer, "lr_scheduler": {"scheduler": scheduler, "interval": "step"}}
+
+    if _Base is nn.Module:  # Lightning provides this otherwise
+        @classmethod
+        def load_from_checkpoint(cls, checkpoint_path, map_location=None, strict: bool = True, **overrides):
+            """Lightning-free reader of a Lightning checkpoint of the reference model (generate.py:103-107):
+            ``hyper_parameters`` (+ keyword overrides such as num_steps / mask_prob) -> constructor, ``state_dict`` loaded
+            strictly, ``ema_state_dict`` handed to on_load_checkpoint."""
+            ckpt = torch.load(checkpoint_path, map_location=map_location or "cpu", weights_only=False)
+            hp = ckpt.get("hyper_parameters", {})
+            hp = dict(vars(hp)) if isinstance(hp, Namespace) else dict(hp)
+            hp.update(overrides)
+            model = cls(Namespace(**hp))
+            model.load_state_dict(ckpt["state_dict"], strict=strict)
+            if "ema_state_dict" in ckpt:
+                model.on_load_checkpoint(ckpt)
+            return model
 
     # ---- sampler (reference model.py:377-422) ------------------------------------------------
     @torch.inference_mode()

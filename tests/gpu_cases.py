@@ -368,8 +368,11 @@ def case_loss(cfg, sizes, seed, golden=None, **batch_kw):
     torch.manual_seed(seed)
     with torch.no_grad():
         loss = m.training_step(_to_dev(batch), 0, noise=draws, detail=detail)
+    torch.manual_seed(seed)
+    vloss = m.validation_step(_to_dev(batch), 0, noise=draws)  # reference model.py:226-247: same objective, no graph
     torch.cuda.synchronize()
     out = {"t_exact": (float((detail["t"].cpu() - want_t).abs().max()), 0.0),
+           "validation_step": (abs(float(vloss) - float(loss)), 0.0),
            "loss": (abs(float(loss) - float(want_loss.detach())) / abs(float(want_loss.detach())), STEP_TOL),
            "noise_pred": (rel(detail["noise_pred"], outs[0]), STEP_TOL),
            "seq_pred": (rel(detail["seq_pred"], outs[1]), STEP_TOL),

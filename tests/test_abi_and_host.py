@@ -102,3 +102,41 @@ def test_schedule_tables_match_reference_golden(tag, over):
         assert np.array_equal(getattr(model, k).numpy(), gold["sched:" + k]), k
     coef = model._coef.numpy()
     assert np.array_equal(coef[:, 2], gold["sched:sqrt_betas"])
+
+
+def test_checkpoint_round_trip_and_optimizer_glue(tmp_path):
+    """Lightning-free load_from_checkpoint (generate.py:103-107): hyper-parameters + overrides -> constructor, strict
+    state-dict, EMA hook; configure_optimizers mirrors reference model.py:203-213."""
+    import torch
+    from protein_redesign_b200 import synthetic as syn
+    from protein_redesign_b200.model import ProteinReDiffModel
+    cfg = syn.TINY
+    m = ProteinReDiffModel(cfg)
+    m.load_state_dict(syn.make_state_dict(cfg, 3), strict=True)
+    ckpt = {"state_dict": m.state_dict(), "hyper_parameters": vars(cfg.to_namespace())}
+    m.on_save_checkpoint(ckpt)
+    assert "ema_state_dict" in ckpt
+    path = tmp_path / "model.ckpt"
+    torch.save(ckpt, path)
+    m2 = ProteinReDiffModel.load_from_checkpoint(str(path), num_steps=20, mask_prob=0.5)
+    assert (m2.num_steps, m2.mask_prob) == (20, 0.5)
+    for (k, a), b in zip(m.state_dict().items(), m2.state_dict().values()):
+        assert torch.equal(a, b), k
+    opt = m2.configure_optimizers()
+    assert isinstance(opt["optimizer"], torch.optim.Adam) and opt["lr_scheduler"]["interval"] == "step"
+    assert abs(opt["optimizer"].param_groups[0]["lr"] - m2.learning_rate / m2.warmup_steps) < 1e-12
+
+
+def test_training_step_needs_no_grad_and_cuda():
+    """No CPU fallback and no silent graph-less loss: training_step refuses autograd; under no_grad on CPU tensors the
+    CUDA-only ops raise."""
+    import pytest
+    import torch
+    from protein_redesign_b200 import synthetic as syn
+    from protein_redesign_b200.model import ProteinReDiffModel
+    m = ProteinReDiffModel(syn.TINY)
+    batch = syn.make_batch(syn.TINY, [(3, 9)], seed=0, with_positions=True)
+    with pytest.raises(NotImplementedError):
+        m.training_step(dict(batch), 0)
+    with torch.no_grad(), pytest.raises(RuntimeError):
+        m.training_step(dict(batch), 0)
