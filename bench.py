@@ -325,7 +325,7 @@ def run_ours(args):
         # ---- dominant kernel alone (roofline) ------------------------------------------------------
         roof = None
         if rank == 0 and hasattr(lib, "prd_profile_kernel"):
-            roof = profile_dominant(lib, cfg, B, N, dev, mask, bufs["pair"])
+            roof = profile_dominant(lib, cfg, B, N, dev, mask, bufs["pair"], model)
 
     if world > 1:
         t_all = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
@@ -364,7 +364,7 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-def profile_dominant(lib, cfg, B, N, dev, mask, pair):
+def profile_dominant(lib, cfg, B, N, dev, mask, pair, model):
     """Average duration of individual kernels, each timed alone (CUDA events on the launch stream) on the
     data the last step left in the workspace.  Returns the roofline object of the dominant kernel (the
     triangle-attention core) and a list for the other kernels north_star names."""
@@ -397,7 +397,12 @@ def profile_dominant(lib, cfg, B, N, dev, mask, pair):
         e = ncu.get(key)
         return (e["read_bytes"] + e["write_bytes"]) if e else None
 
+    # each kernel is timed on the operands its own op leaves in the (shared) workspace: run that op first, on a copy of
+    # the last step's pair tensor -- the attention core's lazy-rescale path would otherwise run on another op's bytes
+    blk = model.Denoiser.folding_blocks[0]
+    scratch = pair.clone()
     # triangle-multiplication contraction: 2*B*N^3*c_z flop; a, b fp16 planes in, x fp32 planes out
+    blk.pair_mul_outgoing.apply_(cfg, scratch, mask)
     ms = time_kernel("trimul_gemm", None)
     flops = 2.0 * B * N ** 3 * cfg.pair_dim
     out.append({"kernel": "gemm_f16_kernel (tri-mul contraction)", "bound": "tensor", "achieved": flops / ms / 1e9,
@@ -413,12 +418,14 @@ def profile_dominant(lib, cfg, B, N, dev, mask, pair):
                 "traffic": dram("pair_bias_kernel"),
                 "ms_per_launch": ms})
     # triangle attention core (dominant): QK^T + PV flops; co-limited by 4*B*N^3 exp2 on the MUFU pipe
+    blk.pair_attn_starting.apply_(cfg, scratch, mask)
     ms = time_kernel("triattn_flash", mask)
+    del scratch
     flops = 2.0 * 2.0 * B * N * cfg.num_heads * N * N * cfg.head_dim
     n_exp = float(B) * N * cfg.num_heads * N * N
     mufu_floor_ms = n_exp / (148 * 16 * 1.965e9) * 1e3
     traffic = dram("triattn_flash_kernel")
-    roof = {"kernel": "triattn_flash_kernel", "bound": "tensor", "achieved": flops / ms / 1e9, "peak": peaks["tflops"],
+    roof = {"kernel": "triattn_flash_g4_kernel", "bound": "tensor", "achieved": flops / ms / 1e9, "peak": peaks["tflops"],
             "unit": "TFLOP/s", "frac": flops / ms / 1e9 / peaks["tflops"], "traffic": traffic,
             "peak_source": peaks["source"], "ms_per_launch": ms, "mufu_floor_ms": mufu_floor_ms,
             "mufu_frac": mufu_floor_ms / ms,

@@ -352,12 +352,12 @@ int prd_outer_linear_fwd(const PrdDims* d, const void* const* in, void* const* o
 
 // ----------------------------------------------------------------- triangle_multiplication
 namespace {
-struct TmWs { __half* ab; float* x; size_t total; };
+struct TmWs { __half* ab; __half* x; size_t total; };
 TmWs tm_carve(const PrdDims* d, void* ws) {
   Carver c(ws);
   TmWs s;
   s.ab = c.take<__half>((size_t)2 * d->B * d->c_z * d->N * plane_ld(d->N));
-  s.x = c.take<float>((size_t)d->B * d->c_z * d->N * xplane_ld(d->N));
+  s.x = c.take<__half>((size_t)d->B * d->c_z * d->N * xplane_ld(d->N));
   s.total = c.total();
   return s;
 }
@@ -379,7 +379,7 @@ int prd_triangle_multiplication_fwd(const PrdDims* d, const void* const* in, voi
   g.M = N; g.N = N; g.K = N; g.nb1 = d->B * d->c_z;
   g.A = s.ab; g.lda = Np; g.a_bs1 = (long long)N * Np;
   g.B = s.ab + (size_t)d->B * d->c_z * N * Np; g.ldb = Np; g.b_bs1 = (long long)N * Np;
-  g.C = s.x; g.ldc = Nx; g.c_bs1 = (long long)N * Nx;
+  g.C = s.x; g.ldc = Nx; g.c_bs1 = (long long)N * Nx; g.c_fp16 = 1;
   if (gemm_f16(g, st)) return 1;
   return trimul_out(pd(d), pair, out_ptr<float>(out, 0), d->residual, s.x, in_ptr<__half>(w, 2), in_ptr<float>(w, 3), st);
 }
@@ -450,7 +450,7 @@ int prd_profile_kernel(const char* name, const PrdDims* d, void* workspace, size
       g.M = N; g.N = N; g.K = N; g.nb1 = d->B * d->c_z;
       g.A = s.ab; g.lda = Np; g.a_bs1 = (long long)N * Np;
       g.B = s.ab + (size_t)d->B * d->c_z * N * Np; g.ldb = Np; g.b_bs1 = (long long)N * Np;
-      g.C = s.x; g.ldc = Nx; g.c_bs1 = (long long)N * Nx;
+      g.C = s.x; g.ldc = Nx; g.c_bs1 = (long long)N * Nx; g.c_fp16 = 1;
       return gemm_f16(g, st);
     }
     if (n == "pair_bias") {

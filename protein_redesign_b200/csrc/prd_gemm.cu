@@ -156,6 +156,36 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
       // warp-uniform: fp32 C whose full tile width exists and whose rows are 16-byte aligned
       const bool coalesce = !ep.c_fp16 && (n0 + BN <= ep.N) && ((ep.ldc & 3) == 0) &&
                             ((reinterpret_cast<uintptr_t>(reinterpret_cast<float*>(ep.C) + boff_c + n0) & 15) == 0);
+      // warp-uniform: plain fp16 C (the tri-mul contraction result), full tile width, 16-byte aligned rows: 64-column chunks
+      // (128 bytes per row) leave as full lines
+      const bool coalesce16 = ep.c_fp16 && plain && BN >= 64 && (n0 + BN <= ep.N) && ((ep.ldc & 7) == 0) && (m0 + 128 <= ep.M) &&
+                              ((reinterpret_cast<uintptr_t>(reinterpret_cast<__half*>(ep.C) + boff_c + n0) & 15) == 0);
+      if (coalesce16) {
+#pragma unroll 1
+        for (int c = 0; c < BN / 64; ++c) {
+          uint32_t r0[32], r1[32];
+          uint4 ov[8];
+          tmem_ld32(tmem + buf * BN + (static_cast<uint32_t>(q * 32) << 16) + c * 64, r0);
+          tmem_ld32(tmem + buf * BN + (static_cast<uint32_t>(q * 32) << 16) + c * 64 + 32, r1);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            ov[j] = make_uint4(pack_half2(__uint_as_float(r0[8 * j]), __uint_as_float(r0[8 * j + 1])),
+                               pack_half2(__uint_as_float(r0[8 * j + 2]), __uint_as_float(r0[8 * j + 3])),
+                               pack_half2(__uint_as_float(r0[8 * j + 4]), __uint_as_float(r0[8 * j + 5])),
+                               pack_half2(__uint_as_float(r0[8 * j + 6]), __uint_as_float(r0[8 * j + 7])));
+            ov[4 + j] = make_uint4(pack_half2(__uint_as_float(r1[8 * j]), __uint_as_float(r1[8 * j + 1])),
+                                   pack_half2(__uint_as_float(r1[8 * j + 2]), __uint_as_float(r1[8 * j + 3])),
+                                   pack_half2(__uint_as_float(r1[8 * j + 4]), __uint_as_float(r1[8 * j + 5])),
+                                   pack_half2(__uint_as_float(r1[8 * j + 6]), __uint_as_float(r1[8 * j + 7])));
+          }
+          __half* cb = reinterpret_cast<__half*>(ep.C) + boff_c + (long long)(m0 + q * 32) * ep.ldc + n0 + c * 64;
+          warp_store_rows128(epi + q * 4096, lane, ov, cb, (long long)ep.ldc * 2, 32);
+        }
+        tc_fence_before();
+        mbar_arrive(&tmem_empty[buf]);
+        continue;
+      }
 #pragma unroll 1
       for (int c = 0; c < BN / 32; ++c) {
         uint32_t r[32];

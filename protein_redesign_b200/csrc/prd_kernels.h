@@ -39,7 +39,7 @@ struct PairDims {
 };
 inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 inline int plane_ld(int N) { return round_up(N, 64); }  // row stride (halves) of fp16 channel planes
-inline int xplane_ld(int N) { return round_up(N, 4); }  // row stride (floats) of fp32 result planes
+inline int xplane_ld(int N) { return round_up(N, 8); }  // row stride (halves) of the fp16 contraction-result planes
 
 // All residual ops: dst = (residual ? src : 0) + update; dst may alias src.
 int pair_transition(const PairDims& d, const float* pair, float* dst, int residual, const __half* w1, const float* b1,
@@ -47,8 +47,8 @@ int pair_transition(const PairDims& d, const float* pair, float* dst, int residu
 // mode 0 = outgoing, 1 = incoming.  ab: [2][B][CZ][N][plane_ld(N)] fp16 channel planes.
 int trimul_in(const PairDims& d, const float* pair, const float* mask, int mode, const __half* w_in, const float* b_in,
               __half* ab, cudaStream_t s);
-// x: [B][CZ][N][xplane_ld(N)] fp32 contraction result.
-int trimul_out(const PairDims& d, const float* pair, float* dst, int residual, const float* x, const __half* w_out,
+// x: [B][CZ][N][xplane_ld(N)] fp16 contraction result.
+int trimul_out(const PairDims& d, const float* pair, float* dst, int residual, const __half* x, const __half* w_out,
                const float* b_out, cudaStream_t s);
 // mode 0 = starting, 1 = ending.  q,k,g: [B*N*N][64] fp16 (logical row = (b, seq, tok));
 // vt: [B*N][64][plane_ld(N)] fp16.

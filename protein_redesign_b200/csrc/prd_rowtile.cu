@@ -805,37 +805,44 @@ int trimul_in(const PairDims& d, const float* pair, const float* mask, int mode,
 
 // =========================================================================================
 // Triangle multiplication, output side: dst = [pair +] sigmoid(Go p + bgo) * (Wo LN(x) + bo)
-// x: fp32 planes [B][CZ][N][Nx] from the contraction GEMM.  w_out: fp16 pair, four [CZ x CZ] tiles
+// x: fp16 planes [B][CZ][N][Nx] from the contraction GEMM (fp32 accumulate, one rounding).  w_out: fp16 pair, four [CZ x CZ] tiles
 // in the order out_gate_hi, out_proj_hi, out_gate_lo, out_proj_lo.  Two compute groups; the pair row
 // stays in registers for the residual, the output is staged over the (then idle) A tiles.
 // =========================================================================================
 template <int CZ>
 __global__ void __launch_bounds__(256, 1)
-trimul_out_kernel(const float* pair, float* dst, int residual, const float* __restrict__ xpl, int N, int Nx, long long R,
+trimul_out_kernel(const float* pair, float* dst, int residual, const __half* __restrict__ xpl,
+                  const __grid_constant__ CUtensorMap map_x, int use_tma, int N, int Nx, long long R,
                   const __half* __restrict__ w_out, const float* __restrict__ b_out) {
   extern __shared__ uint8_t raw[];
   constexpr int kStage = (RowStage<CZ>::kBytes + 1023) / 1024 * 1024;
   constexpr int kAO = kStage > 32768 ? kStage : 32768;  // A_p | A_x, re-used as the output stage
-  constexpr int kGroupBytes = kAO + kStage;
+  constexpr int kXBytes = CZ * kTileRows * 2;           // contraction-result tile [CZ planes][128 j] fp16
+  constexpr int kGroupBytes = kAO + kStage + kXBytes;
   uint8_t* sm = smem_align1024(raw);
   uint8_t* sW = sm;  // four B tiles of [CZ x 64]
   uint8_t* sG = sW + 4 * CZ * 128;
   float* sB = reinterpret_cast<float*>(sG + 2 * kGroupBytes);
   uint64_t* bars = reinterpret_cast<uint64_t*>(sB + 2 * CZ);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
   constexpr int TCOLS = 2 * CZ;
 
   const Group g;
   uint8_t* sAp = sG + g.grp * kGroupBytes;
   uint8_t* sAx = sAp + 16384;
   uint8_t* sSt = sAp + kAO;
+  const __half* sX = reinterpret_cast<const __half*>(sSt + kStage);
   uint64_t* full = bars + g.grp;
   uint64_t* mma_bar = bars + 2 + g.grp;
+  uint64_t* xfull = bars + 4 + g.grp;
   if (threadIdx.x == 0) {
     mbar_init(&bars[0], kTileRows);
     mbar_init(&bars[1], kTileRows);
     mbar_init(&bars[2], 1);
     mbar_init(&bars[3], 1);
+    mbar_init(&bars[4], 1);
+    mbar_init(&bars[5], 1);
+    if (use_tma) tma_prefetch_desc(&map_x);
     fence_barrier_init();
   }
   if (threadIdx.x < 32) tmem_alloc(tmem_slot, 2 * TCOLS);
@@ -854,9 +861,20 @@ trimul_out_kernel(const float* pair, float* dst, int residual, const float* __re
   const long long stride = (long long)gridDim.x * 2;
   uint32_t mma_phase = 0;
   long long tile = (long long)blockIdx.x * 2 + g.grp;
+  // N % 128 == 0: a tile is 128 consecutive j of one (b, i) row, so its contraction results are ONE TMA box
+  // [CZ planes][128 j] fetched a tile ahead by one thread (the per-thread 64-plane gather was this kernel's top stall)
+  const int tiles_per_row = N / kTileRows;
+  auto issue_x = [&](long long tl) {
+    const long long bi = tl / tiles_per_row;
+    const int j0 = static_cast<int>(tl - bi * tiles_per_row) * kTileRows;
+    const int b = static_cast<int>(bi / N), i = static_cast<int>(bi - (long long)b * N);
+    mbar_expect_tx(xfull, kXBytes);
+    tma_load_4d(const_cast<__half*>(sX), &map_x, xfull, j0, i, 0, b);
+  };
   if (tile < num_tiles) {
     const long long r = tile * kTileRows + t;
     issue_row_load<CZ>(sSt, t, pair + r * CZ, r < R, full);
+    if (use_tma && t == 0) issue_x(tile);
   }
   for (int it = 0; tile < num_tiles; tile += stride, ++it) {
     const long long r = tile * kTileRows + t;
@@ -864,10 +882,14 @@ trimul_out_kernel(const float* pair, float* dst, int residual, const float* __re
     // the previous tile's output rows were staged over the A tiles: its bulk stores must have read them
     bulk_wait_read0();
     g.bar();
-    // contraction result for this (b,i,j): one value per channel plane, coalesced across lanes.  The 64 loads are
-    // issued first and consumed last: their latency overlaps the pair-row LayerNorm below.
+    // contraction result for this (b,i,j): one value per channel plane.  TMA path: column t of the staged tile;
+    // otherwise a gather, coalesced across lanes, issued first and consumed last.
     float x[CZ];
-    if (valid) {
+    if (use_tma) {
+      mbar_wait(xfull, it & 1);
+#pragma unroll
+      for (int dch = 0; dch < CZ; ++dch) x[dch] = __half2float(sX[dch * kTileRows + t]);
+    } else if (valid) {
       int b, rem;
       if (r < 0x7fffffffLL && NN < 0x7fffffffLL) {
         b = static_cast<int>(static_cast<unsigned>(r) / static_cast<unsigned>(NN));
@@ -877,10 +899,10 @@ trimul_out_kernel(const float* pair, float* dst, int residual, const float* __re
         rem = static_cast<int>(r - (long long)b * NN);
       }
       const int i = rem / N, j = rem - i * N;
-      const float* xp = xpl + (long long)b * CZ * xplane + (long long)i * Nx + j;
+      const __half* xp = xpl + (long long)b * CZ * xplane + (long long)i * Nx + j;
 #pragma unroll
       for (int dch = 0; dch < CZ; ++dch) {
-        x[dch] = __ldg(xp);
+        x[dch] = __half2float(__ldg(xp));
         xp += xplane;
       }
     } else {
@@ -909,6 +931,7 @@ trimul_out_kernel(const float* pair, float* dst, int residual, const float* __re
     layernorm_inplace<CZ>(x);
     store_a_row<CZ>(sAx, t, x);
     g.sync_before_mma();
+    if (use_tma && t == 64 && tile + stride < num_tiles) issue_x(tile + stride);  // every thread has read the x tile
     if (t < 32) {  // warp-uniform issue: UMMA operands stay in uniform registers
       tc_fence_after();
       if (elect_one()) {
@@ -954,21 +977,32 @@ trimul_out_kernel(const float* pair, float* dst, int residual, const float* __re
 }
 
 template <int CZ>
-static int launch_trimul_out(const PairDims& d, const float* pair, float* dst, int residual, const float* x,
+static int launch_trimul_out(const PairDims& d, const float* pair, float* dst, int residual, const __half* x,
                              const __half* w_out, const float* b_out, cudaStream_t s) {
   const long long R = (long long)d.B * d.N * d.N;
   const long long tiles = (R + kTileRows - 1) / kTileRows;
   constexpr int kStage = (RowStage<CZ>::kBytes + 1023) / 1024 * 1024;
   constexpr int kAO = kStage > 32768 ? kStage : 32768;
-  constexpr int smem = 1024 + 4 * CZ * 128 + 2 * (kAO + kStage) + 2 * CZ * 4 + 64;
+  constexpr int smem = 1024 + 4 * CZ * 128 + 2 * (kAO + kStage + CZ * kTileRows * 2) + 2 * CZ * 4 + 64;
   auto kern = trimul_out_kernel<CZ>;
   if (set_smem(kern, smem)) return 1;
-  kern<<<grid_for((tiles + 1) / 2, 1), 256, smem, s>>>(pair, dst, residual, x, d.N, xplane_ld(d.N), R, w_out, b_out);
+  // x planes [B][CZ][N][Nx] fp16 as a 4-D map (j, i, channel, b); box = [128 j][1][CZ][1]
+  const int Nx = xplane_ld(d.N);
+  const int use_tma = (d.N % kTileRows == 0) ? 1 : 0;
+  CUtensorMap mx;
+  {
+    TmaDims t;
+    t.size[0] = (uint64_t)d.N; t.size[1] = (uint64_t)d.N; t.size[2] = (uint64_t)CZ; t.size[3] = (uint64_t)d.B;
+    t.stride[0] = (uint64_t)Nx * 2; t.stride[1] = (uint64_t)d.N * Nx * 2; t.stride[2] = (uint64_t)CZ * d.N * Nx * 2;
+    t.box[0] = use_tma ? kTileRows : 8; t.box[1] = 1; t.box[2] = CZ; t.box[3] = 1;
+    if (make_tensor_map(&mx, x, 2, 4, t, false)) return 1;
+  }
+  kern<<<grid_for((tiles + 1) / 2, 1), 256, smem, s>>>(pair, dst, residual, x, mx, use_tma, d.N, Nx, R, w_out, b_out);
   PRD_LAUNCHED();
   return 0;
 }
 
-int trimul_out(const PairDims& d, const float* pair, float* dst, int residual, const float* x, const __half* w_out,
+int trimul_out(const PairDims& d, const float* pair, float* dst, int residual, const __half* x, const __half* w_out,
                const float* b_out, cudaStream_t s) {
   if (d.CZ == 64) return launch_trimul_out<64>(d, pair, dst, residual, x, w_out, b_out, s);
   if (d.CZ == 32) return launch_trimul_out<32>(d, pair, dst, residual, x, w_out, b_out, s);
