@@ -159,6 +159,20 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// Lean wait for hot single-warp issue loops: the watchdog version costs ~10 registers and a printf call site per use,
+// which makes a 40-register UMMA warp spill.  Use only where the same protocol is already covered by mbar_wait elsewhere.
+__device__ __forceinline__ void mbar_wait_spin(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "SPIN_WAIT:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra SPIN_DONE;\n\t"
+      "bra SPIN_WAIT;\n\t"
+      "SPIN_DONE:\n\t}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+
 // generic-proxy writes (st.shared) -> visible to the async proxy (TMA store / UMMA operand reads)
 __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");

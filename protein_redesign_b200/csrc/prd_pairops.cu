@@ -23,23 +23,36 @@ namespace prd {
 //   warp 12     UMMA issue (c_s/16 UMMAs per row into one of two [128 x c_z] accumulators) and the A-tile TMA
 // The only per-row synchronisation of the builders is one named barrier (x_i staged in shared memory).
 // =========================================================================================
+// Shared-memory split per configuration: the B-operand ring depth and whether the residual rows get a TMA stage.
+// ncu: the builders wait for free ring slots 70 % of the time with a 4-slot ring (a slot is free only when the UMMAs
+// that read it have COMPLETED, ~1000 cycles after issue), so depth goes first.
+template <int CZ, int KBS>
+struct OlCfg {
+  static constexpr int kRing = 4;
+  static constexpr bool kResTma = true;
+  static constexpr int kSmem = 1024 + KBS * 16384 + kRing * CZ * 128 + (kResTma ? (CZ * 4 / 128) * 16384 : 0) + 4 * 4096 +
+                               (2 * KBS * 64 + 5 * CZ) * 4 + 256;
+};
 constexpr int kOlThreads = 512;  // 4 warpgroups: builders, builders, epilogue, {UMMA/TMA warp + 3 idle warps that only donate registers}
 
 template <int CZ, int KBS>
 __global__ void __launch_bounds__(kOlThreads, 1)
-outer_linear_kernel(const __grid_constant__ CUtensorMap map_x, const float* pair, float* dst, int residual,
+outer_linear_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_pair, const float* pair,
+                    float* dst, int residual,
                     const __half* __restrict__ xn16, const __half* __restrict__ w1, const float* __restrict__ u,
                     const float* __restrict__ bias, int N, int ilen) {
   extern __shared__ uint8_t raw[];
   constexpr int CS = KBS * 64;
   constexpr int NCH = KBS * CZ * 8 / 256;  // 16-byte W1 chunks per builder thread
   constexpr int CPK = NCH / KBS;           // ... per K-block
-  constexpr int RB = 4;                    // ring of B-operand K-blocks
+  constexpr int RB = OlCfg<CZ, KBS>::kRing;        // ring of B-operand K-blocks
+  constexpr bool kResTma = OlCfg<CZ, KBS>::kResTma;  // residual rows prefetched by TMA (when shared memory allows)
   constexpr int RP = CZ * 4 / 128;         // 128-byte pieces per pair row
   uint8_t* sm = smem_align1024(raw);
   uint8_t* sA = sm;                        // KBS x 16 KB
   uint8_t* sB = sA + KBS * 16384;          // RB x [CZ x 64]
-  uint8_t* sSl = sB + RB * CZ * 128;       // 4 epilogue warps x 4 KB
+  uint8_t* sRes = sB + RB * CZ * 128;      // residual pair rows of the next i: RP swizzled TMA boxes [128 j x 32 floats]
+  uint8_t* sSl = sRes + (kResTma ? RP * 16384 : 0);  // 4 epilogue warps x 4 KB
   float* sXi = reinterpret_cast<float*>(sSl + 4 * 4096);  // [2][CS]
   float* sUi = sXi + 2 * CS;               // [4][CZ]
   float* sBias = sUi + 4 * CZ;
@@ -48,7 +61,9 @@ outer_linear_kernel(const __grid_constant__ CUtensorMap map_x, const float* pair
   uint64_t* empty = full + RB;             // [RB] K-block consumed (UMMA commit)
   uint64_t* acc_full = empty + RB;         // [2]
   uint64_t* acc_empty = acc_full + 2;      // [2] (128 epilogue arrivals)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  uint64_t* res_full = acc_empty + 2;      // residual rows of row i landed (TMA transaction bytes)
+  uint64_t* res_empty = res_full + 1;      // ... and were copied to registers (128 epilogue arrivals)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_empty + 1);
   constexpr int TCOLS = 2 * CZ < 32 ? 32 : 2 * CZ;
 
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
@@ -65,8 +80,11 @@ outer_linear_kernel(const __grid_constant__ CUtensorMap map_x, const float* pair
       mbar_init(&acc_full[q], 1);
       mbar_init(&acc_empty[q], 128);
     }
+    mbar_init(res_full, 1);
+    mbar_init(res_empty, 128);
     fence_barrier_init();
     tma_prefetch_desc(&map_x);
+    tma_prefetch_desc(&map_pair);
   }
   if (warp == 0) tmem_alloc(tmem_slot, TCOLS);
   for (int i = t; i < CZ; i += kOlThreads) sBias[i] = bias[i];
@@ -77,7 +95,8 @@ outer_linear_kernel(const __grid_constant__ CUtensorMap map_x, const float* pair
 
   if (warp < 8) {
     // ------------------------------------------------------------------ builders
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 136;");  // 64 registers of W1 + working set
+    // 64 registers of W1 + working set: stays at the launch allocation of 128 (these warps wait for ring slots most
+    // of the time; the registers go to the UMMA warp, whose issue loop is the critical path)
     // this thread's W1 chunks (fixed for the whole kernel): chunk n covers K-block n / CPK,
     // row z = (t >> 3) + 32 * (n % CPK), 16-byte column chunk ch = t & 7
     const int ch = t & 7;
@@ -159,9 +178,20 @@ outer_linear_kernel(const __grid_constant__ CUtensorMap map_x, const float* pair
     for (int i = i0; i < i1; ++i) {
       const long long rowoff = (((long long)b * N + i) * N + j0) * CZ;  // first of this warp's 32 pair rows
       uint4 res[RP][8];
-      if (residual) {
+      if (residual && !kResTma) {
 #pragma unroll
         for (int p = 0; p < RP; ++p) warp_load_rows128(slice, lane, res[p], pair + rowoff + p * 32, CZ * 4, rows_valid);
+      } else if (residual) {
+        // this row's residual tile was fetched by the loader warp while the previous row was in flight (a synchronous
+        // load here left one row of HBM latency exposed per i: long-scoreboard was 7 of 13 stall cycles per issue)
+        mbar_wait(res_full, (i - i0) & 1);
+        const int tl = q4 * 32 + lane;
+#pragma unroll
+        for (int p = 0; p < RP; ++p)
+#pragma unroll
+          for (int c = 0; c < 8; ++c)
+            res[p][c] = *reinterpret_cast<const uint4*>(sRes + p * 16384 + tl * 128 + ((c ^ (tl & 7)) << 4));
+        mbar_arrive(res_empty);
       } else {
 #pragma unroll
         for (int p = 0; p < RP; ++p)
@@ -193,32 +223,60 @@ outer_linear_kernel(const __grid_constant__ CUtensorMap map_x, const float* pair
       }
     }
   } else {
-    // ------------------------------------------------------------------ TMA + UMMA warp (12); 13-15 idle
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");  // 8 x 136 + 4 x 200 + 4 x 24 <= 16 x 128
-    if (warp == 12) {
-    if (elect_one()) {
-      mbar_expect_tx(bar_a, KBS * 16384);
-      for (int kb = 0; kb < KBS; ++kb) tma_load_3d(sA + kb * 16384, &map_x, bar_a, kb * 64, jt * 128, b);
-    }
-    __syncwarp();
-    mbar_wait(bar_a, 0);
-    uint32_t ring_it = 0;
-    for (int i = i0; i < i1; ++i) {
-      const int buf = i & 1;
-      if (i - i0 >= 2) mbar_wait(&acc_empty[buf], (((i - i0) >> 1) - 1) & 1);  // epilogue of row i-2 drained it
-      for (int kb = 0; kb < KBS; ++kb, ++ring_it) {
-        const uint32_t slot = ring_it % RB;
-        mbar_wait(&full[slot], (ring_it / RB) & 1);
-        tc_fence_after();
+    // ------------------------------------------------------------------ TMA + UMMA warp (12), residual loader (13); 14-15 idle
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");  // 8 x 128 + 4 x 200 + 4 x 56 = 16 x 128 (24 made the issue loop spill)
+    if (kResTma && warp == 13 && residual) {
+      for (int i = i0; i < i1; ++i) {
+        if (i > i0) mbar_wait(res_empty, (i - i0 - 1) & 1);  // the epilogue holds row i-1 in registers
         if (elect_one()) {
-          umma_kblock(tmem + buf * CZ, smem_u32(sA) + kb * 16384, smem_u32(sB) + slot * (CZ * 128), umma_idesc_f16(128, CZ),
-                      kb > 0);
-          umma_commit(&empty[slot]);
-          if (kb == KBS - 1) umma_commit(&acc_full[buf]);
+          mbar_expect_tx(res_full, RP * 16384);
+          for (int p = 0; p < RP; ++p) tma_load_4d(sRes + p * 16384, &map_pair, res_full, p * 32, jt * 128, i, b);
         }
         __syncwarp();
       }
     }
+    if (warp == 12) {
+      if (elect_one()) {
+        mbar_expect_tx(bar_a, KBS * 16384);
+        for (int kb = 0; kb < KBS; ++kb) tma_load_3d(sA + kb * 16384, &map_x, bar_a, kb * 64, jt * 128, b);
+      }
+      __syncwarp();
+      mbar_wait(bar_a, 0);
+      // The issue loop is this kernel's critical path (ncu: the warp is never parked, ~90 dependent instructions and
+      // three local-memory reloads per K-block = 940 cycles against 290 of tensor time).  K-blocks fully unrolled: the
+      // ring slot (kb % RB) and, for KBS a multiple of 2 RB, the ring phase are compile-time, the descriptors are
+      // base + constant in uniform registers.
+      static_assert(KBS % RB == 0, "ring slots must be compile-time per K-block");
+      const uint64_t da0 = umma_desc_sw128(smem_u32(sA));
+      const uint64_t db0 = umma_desc_sw128(smem_u32(sB));
+      const uint32_t idesc = umma_idesc_f16(128, CZ);
+      uint32_t ring_round = 0;  // completed passes over the RB-slot ring
+      for (int i = i0; i < i1; ++i) {
+        const int buf = i & 1;
+        const uint32_t tacc = tmem + buf * CZ;
+        if (i - i0 >= 2) mbar_wait(&acc_empty[buf], (((i - i0) >> 1) - 1) & 1);  // epilogue of row i-2 drained it
+#pragma unroll 1
+        for (int round = 0; round < KBS / RB; ++round) {
+          const uint32_t ph = (ring_round + round) & 1;
+          const uint64_t da_r = da0 + static_cast<uint64_t>(round * RB * (16384 >> 4));
+#pragma unroll
+          for (int slot = 0; slot < RB; ++slot) {
+            mbar_wait_spin(&full[slot], ph);
+            tc_fence_after();
+            if (elect_one()) {
+              const uint64_t da = da_r + static_cast<uint64_t>(slot * (16384 >> 4));
+              const uint64_t db = db0 + static_cast<uint64_t>(slot * ((CZ * 128) >> 4));
+#pragma unroll
+              for (uint32_t k = 0; k < 4; ++k)
+                umma_f16(tacc, da + 2 * k, db + 2 * k, idesc, (round > 0 || slot > 0 || k > 0) ? 1u : 0u);
+              umma_commit(&empty[slot]);
+              if (round == KBS / RB - 1 && slot == RB - 1) umma_commit(&acc_full[buf]);
+            }
+            __syncwarp();
+          }
+        }
+        ring_round += KBS / RB;
+      }
     }
   }
   tc_fence_before();
@@ -227,14 +285,14 @@ outer_linear_kernel(const __grid_constant__ CUtensorMap map_x, const float* pair
 }
 
 template <int CZ, int KBS>
-static int launch_outer_linear(const CUtensorMap& mx, dim3 grid, const float* pair, float* dst, int residual,
+static int launch_outer_linear(const CUtensorMap& mx, const CUtensorMap& mp, dim3 grid, const float* pair, float* dst, int residual,
                                const __half* xn16, const __half* w1, const float* u, const float* bias, int N, int ilen,
                                cudaStream_t s) {
-  constexpr int smem = 1024 + KBS * 16384 + 4 * CZ * 128 + 4 * 4096 + (2 * KBS * 64 + 5 * CZ) * 4 + 256;
+  constexpr int smem = OlCfg<CZ, KBS>::kSmem;
   static_assert(smem <= 227 * 1024, "outer_linear shared memory budget");
   auto kern = outer_linear_kernel<CZ, KBS>;
   PRD_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  kern<<<grid, kOlThreads, smem, s>>>(mx, pair, dst, residual, xn16, w1, u, bias, N, ilen);
+  kern<<<grid, kOlThreads, smem, s>>>(mx, mp, pair, dst, residual, xn16, w1, u, bias, N, ilen);
   PRD_LAUNCHED();
   return 0;
 }
@@ -250,6 +308,15 @@ int outer_linear(const PairDims& d, int CS, const float* pair, float* dst, int r
   t.stride[0] = (uint64_t)CS * 2; t.stride[1] = (uint64_t)N * CS * 2; t.stride[2] = 0;
   t.box[0] = 64; t.box[1] = 128; t.box[2] = 1; t.box[3] = 1;
   if (make_tensor_map(&mx, xn16, 2, 3, t, true)) return 1;
+  // residual rows: pair [B][N][N][CZ] fp32 as (c, j, i, b); one box = [128 j x 32 floats] (128-byte swizzle rows)
+  CUtensorMap mp;
+  {
+    TmaDims r;
+    r.size[0] = (uint64_t)d.CZ; r.size[1] = (uint64_t)N; r.size[2] = (uint64_t)N; r.size[3] = (uint64_t)d.B;
+    r.stride[0] = (uint64_t)d.CZ * 4; r.stride[1] = (uint64_t)N * d.CZ * 4; r.stride[2] = (uint64_t)N * N * d.CZ * 4;
+    r.box[0] = 32; r.box[1] = 128; r.box[2] = 1; r.box[3] = 1;
+    if (make_tensor_map(&mp, (residual && pair) ? pair : dst, 4, 4, r, true)) return 1;  // unused without the residual
+  }
   const int jtiles = (N + 127) / 128;
   // every CTA re-uses its A tile and its W1 registers for `ilen` rows; one CTA per SM, so pick the number of
   // i-chunks that fills whole waves (least idle SM time in the last wave), at least 8 rows per CTA
@@ -271,10 +338,10 @@ int outer_linear(const PairDims& d, int CS, const float* pair, float* dst, int r
   int ilen = (N + ichunks - 1) / ichunks;
   ichunks = (N + ilen - 1) / ilen;
   dim3 grid(jtiles, ichunks, d.B);
-  if (d.CZ == 64 && CS == 512) return launch_outer_linear<64, 8>(mx, grid, pair, dst, residual, xn16, w1, u, bias, N, ilen, s);
-  if (d.CZ == 64 && CS == 256) return launch_outer_linear<64, 4>(mx, grid, pair, dst, residual, xn16, w1, u, bias, N, ilen, s);
-  if (d.CZ == 32 && CS == 512) return launch_outer_linear<32, 8>(mx, grid, pair, dst, residual, xn16, w1, u, bias, N, ilen, s);
-  return launch_outer_linear<32, 4>(mx, grid, pair, dst, residual, xn16, w1, u, bias, N, ilen, s);
+  if (d.CZ == 64 && CS == 512) return launch_outer_linear<64, 8>(mx, mp, grid, pair, dst, residual, xn16, w1, u, bias, N, ilen, s);
+  if (d.CZ == 64 && CS == 256) return launch_outer_linear<64, 4>(mx, mp, grid, pair, dst, residual, xn16, w1, u, bias, N, ilen, s);
+  if (d.CZ == 32 && CS == 512) return launch_outer_linear<32, 8>(mx, mp, grid, pair, dst, residual, xn16, w1, u, bias, N, ilen, s);
+  return launch_outer_linear<32, 4>(mx, mp, grid, pair, dst, residual, xn16, w1, u, bias, N, ilen, s);
 }
 
 // =========================================================================================
