@@ -449,6 +449,9 @@ CASES = {
     # N = 140: plane_ld = 192, the second 64-column half of the second k-tile lies outside the padded plane row
     "trimul_n140": lambda: case_trimul(B=1, N=140, mode="incoming", pad=7),
     "trimul_n300": lambda: case_trimul(B=1, N=300, mode="outgoing", pad=11),
+    # N % 128 == 0: TMA-staged contraction-result tiles and the two-threads-per-row output kernel
+    "trimul_n256": lambda: case_trimul(B=2, N=256, mode="incoming", pad=9),
+    "trimul_n128": lambda: case_trimul(B=1, N=128, mode="outgoing", pad=3),
     "triattn_starting": lambda: case_triattn(mode="starting"),
     "triattn_ending": lambda: case_triattn(mode="ending"),
     "triattn_n200": lambda: case_triattn(B=1, N=200, mode="ending", pad=9),
