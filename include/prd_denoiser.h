@@ -101,8 +101,17 @@ PRD_DECLARE_OP(opm_project)
  * in: [pair_static (NULL = zeros) | z f32 B,N,3 | mask | t i64 B (or NULL with sampler_state) | opm_a | opm_b | sampler_state]
  * d->mode bit 0: OuterProductUpdate term only (Denoiser.forward's `pair += mask_2d * opm(...)`, modules.py:395-397);
  *         bit 1: OPM term not multiplied by mask_2d (stand-alone OuterProductUpdate.forward, AF2_modules.py:503-545).
- * out: [pair]   weights: [freq | w_beta f32 c_z x time | w_dist_h c_z x dist | centers | w_opm_h c_z x c_s/4 | b_opm] */
+ * out: [pair]   weights: [freq | w_beta f32 c_z x time | w_dist_h c_z x dist | centers | w_opm_h c_z x c_s/4 | b_opm |
+ *                        rbf_lut f32 (or NULL)]  -- ALWAYS seven entries.
+ * rbf_lut (built by prd_rbf_lut_build): W_dist rbf(d) is a function of one scalar, so it may be tabulated once per weight
+ * version (fp32, PRD_RBF_LUT_POINTS + 1 rows over [0, d_max]) and interpolated linearly (3e-6 relative) instead of being
+ * rebuilt per pair as dist_dim exponentials + a K = dist_dim GEMM; NULL keeps the GEMM form (modules.py:73-82 literally). */
 PRD_DECLARE_OP(pair_embed)
+#define PRD_RBF_LUT_POINTS 8192
+size_t prd_rbf_lut_floats(const PrdDims* d); /* (PRD_RBF_LUT_POINTS + 2) * c_z: header row {1/h, M} + table rows */
+/* w_dist f32 [c_z x dist_dim] (embed_dist.1.weight), centers f32 [dist_dim] (embed_dist.0.center); d_max: distances
+ * beyond it embed to zero (use max center + 0.52 nm: every term is below 1e-15 there). */
+int prd_rbf_lut_build(const PrdDims* d, const float* w_dist, const float* centers, float d_max, float* lut, void* stream);
 
 /* --- Denoiser trunk (modules.py:391-404) ------------------------------------------------- */
 /* AF2_modules.py:421-473 SPAttention (+ :251-367, :613-627): single <- LN_a(single) + mha(...).

@@ -160,7 +160,15 @@ int prd_pair_embed_fwd(const PrdDims* d, const void* const* in, void* const* out
   return pair_embed_dynamic(pd(d), in_ptr<float>(in, 0), out_ptr<float>(out, 0), in_ptr<float>(in, 1),
                             in_ptr<float>(in, 2), beta, in_ptr<__half>(w, 2), d->dist_dim, in_ptr<float>(w, 3),
                             rbf_scale, in_ptr<float>(in, 4), in_ptr<float>(in, 5), d->c_s / 4, in_ptr<__half>(w, 4),
-                            in_ptr<float>(w, 5), flags, S(stream));
+                            in_ptr<float>(w, 5), flags, in_ptr<float>(w, 6), S(stream));
+}
+
+// Table for the distance embedding (optional 7th weight of pair_embed): see include/prd_denoiser.h
+size_t prd_rbf_lut_floats(const PrdDims* d) { return (size_t)(PRD_RBF_LUT_POINTS + 2) * d->c_z; }
+int prd_rbf_lut_build(const PrdDims* d, const float* w_dist, const float* centers, float d_max, float* lut, void* stream) {
+  if (prd_device_check()) return 1;
+  const float rbf_scale = (d->dist_dim - 1) / 2.0f;
+  return rbf_lut_build(d->c_z, d->dist_dim, w_dist, centers, rbf_scale, d_max, PRD_RBF_LUT_POINTS, lut, S(stream));
 }
 
 // ----------------------------------------------------------------------------- spattention

@@ -71,7 +71,10 @@ int coord_head(const PairDims& d, const float* pair, const float* z, const float
 int pair_embed_dynamic(const PairDims& d, const float* pair_static, float* pair, const float* z, const float* mask,
                        const float* beta, const __half* w_dist, int dist_dim, const float* centers, float rbf_scale,
                        const float* opm_a, const float* opm_b, int opm_dim, const __half* w_opm, const float* b_opm,
-                       int flags, cudaStream_t s);
+                       int flags, const float* rbf_lut, cudaStream_t s);
+// rbf_lut: [(M + 2)][CZ] floats = header row {1/h, M} + M + 1 table rows of d -> W_dist rbf(d) at d = m h, h = d_max / M
+int rbf_lut_build(int CZ, int DD, const float* w_dist, const float* centers, float scale, float d_max, int M, float* lut,
+                  cudaStream_t s);
 // pair[b,i,j,:] += W1 . (x_i * x_j) + u_i - u_j + bias   (OuterLinear, bilinear form)
 int outer_linear(const PairDims& d, int CS, const float* pair, float* dst, int residual, const __half* xn16,
                  const float* xn32, const __half* w1, const float* u, const float* bias, cudaStream_t s);

@@ -352,18 +352,23 @@ int outer_linear(const PairDims& d, int CS, const float* pair, float* dst, int r
 // rbf_k(d) = exp(-scale (d - center_k)^2) is generated thread-locally straight into the fp16 A
 // operand (dist_dim/64 K-blocks); a_i * b_j (opm_dim/64 K-blocks) likewise.  Two accumulators.
 // =========================================================================================
-template <int CZ>
-__global__ void __launch_bounds__(256, 1)
+template <int CZ, bool LUT>
+__global__ void __launch_bounds__(256, LUT ? 2 : 1)
 pair_embed_kernel(const float* __restrict__ pstatic, float* __restrict__ pair, const float* __restrict__ z,
                   const float* __restrict__ mask, const float* __restrict__ beta, const __half* __restrict__ w_dist,
                   int DD, const float* __restrict__ centers, float rbf_scale, const float* __restrict__ opm_a,
                   const float* __restrict__ opm_b, int OD, const __half* __restrict__ w_opm,
-                  const float* __restrict__ b_opm, int N, long long R, int flags) {
+                  const float* __restrict__ b_opm, int N, long long R, int flags, const float* __restrict__ lut) {
   // flags: 1 = OuterProductUpdate term only (no distance / time embedding); 2 = do not multiply the
   // OPM term by mask_2d (stand-alone OuterProductUpdate.forward).  pstatic may be NULL (= zeros).
+  // lut != NULL: the distance embedding d -> W_dist rbf(d) (a smooth function of ONE scalar) is read from a table
+  // (rbf_lut_kernel) and interpolated linearly instead of being rebuilt as 256 exponentials + a K = 256 GEMM per row.
   extern __shared__ uint8_t raw[];
   const bool with_dist = (flags & 1) == 0;
-  const int KBD = with_dist ? DD / 64 : 0, KBO = OD / 64;
+  const bool use_lut = LUT && with_dist && lut != nullptr;  // LUT variant: ~85 KB of shared memory, two CTAs per SM
+  const int KBD = (with_dist && !use_lut) ? DD / 64 : 0, KBO = OD / 64;
+  const float lut_inv_h = use_lut ? lut[0] : 0.f;
+  const float lut_m = use_lut ? lut[1] : 0.f;
   uint8_t* sm = smem_align1024(raw);
   uint8_t* sA1 = sm;                         // rbf, KBD x 16 KB
   uint8_t* sA2 = sA1 + KBD * 16384;          // a_i*b_j, KBO x 16 KB
@@ -386,12 +391,12 @@ pair_embed_kernel(const float* __restrict__ pstatic, float* __restrict__ pair, c
     fence_barrier_init();
   }
   if (tid < 32) tmem_alloc(tmem_slot, TCOLS);
-  if (with_dist) {
+  if (KBD > 0) {
     load_weight_kblocks(sW1, w_dist, CZ, DD, DD, tid, 256);
     load_weight_kblocks(sW1 + KBD * CZ * 128, w_dist + CZ * DD, CZ, DD, DD, tid, 256);
   }
   load_weight_kblocks(sW2, w_opm, CZ, OD, OD, tid, 256);
-  if (with_dist)
+  if (KBD > 0)
     for (int i = tid; i < DD; i += 256) sC[i] = centers[i];
   for (int i = tid; i < CZ; i += 256) sBo[i] = b_opm[i];
   tc_fence_before();
@@ -421,6 +426,24 @@ pair_embed_kernel(const float* __restrict__ pstatic, float* __restrict__ pair, c
     const float dx = zi[0] - zj[0], dy = zi[1] - zj[1], dz = zi[2] - zj[2];
     const float dist = sqrtf(dx * dx + dy * dy + dz * dz);
     const float m2 = valid ? mask[(long long)b * N + i] * mask[(long long)b * N + j] : 0.f;
+    // table rows m, m+1 around dist / h (this thread's 32 output channels); issued now, interpolated in the epilogue
+    const bool my_out = (CZ / 32 == 2) || (half == 0);
+    float lv[LUT ? 32 : 1];
+    if (LUT && use_lut && my_out) {
+      const float u = fminf(dist * lut_inv_h, lut_m);
+      const int mi = min(static_cast<int>(u), static_cast<int>(lut_m) - 1);
+      const float lfrac = u - static_cast<float>(mi);
+      const float4* r0 = reinterpret_cast<const float4*>(lut + (long long)(mi + 1) * CZ + (CZ / 32 == 2 ? 32 * half : 0));
+      const float4* r1 = r0 + CZ / 4;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const float4 a = __ldg(r0 + q), c = __ldg(r1 + q);
+        lv[4 * q + 0] = fmaf(lfrac, c.x - a.x, a.x);
+        lv[4 * q + 1] = fmaf(lfrac, c.y - a.y, a.y);
+        lv[4 * q + 2] = fmaf(lfrac, c.z - a.z, a.z);
+        lv[4 * q + 3] = fmaf(lfrac, c.w - a.w, a.w);
+      }
+    }
     // radial basis -> A1
 #pragma unroll 1
     for (int k0 = half * KBD * 32; k0 < (half + 1) * KBD * 32; k0 += 32) {
@@ -450,7 +473,7 @@ pair_embed_kernel(const float* __restrict__ pstatic, float* __restrict__ pair, c
     if (tid < 32) {  // warp-uniform issue: UMMA operands stay in uniform registers
       tc_fence_after();
       if (elect_one()) {
-        if (with_dist) {
+        if (KBD > 0) {
           umma_multi(tmem, smem_u32(sA1), smem_u32(sW1), KBD, CZ * 128, umma_idesc_f16(128, CZ), false);
           umma_multi(tmem, smem_u32(sA1), smem_u32(sW1 + KBD * CZ * 128), KBD, CZ * 128, umma_idesc_f16(128, CZ), true);
         }
@@ -473,9 +496,13 @@ pair_embed_kernel(const float* __restrict__ pstatic, float* __restrict__ pair, c
     for (int c = 0; c < CZ / 32; ++c) {
       if (CZ / 32 == 2 ? (c != half) : (half != 0)) continue;
       uint32_t a1[32], a2[32];
-      tmem_ld32(tm_lane + c * 32, a1);
+      if (KBD > 0) tmem_ld32(tm_lane + c * 32, a1);
       tmem_ld32(tm_lane + CZ + c * 32, a2);
       tmem_ld_wait();
+      if (LUT && use_lut) {
+#pragma unroll
+        for (int q = 0; q < 32; ++q) a1[q] = __float_as_uint(lv[LUT ? q : 0]);
+      }
 #pragma unroll
       for (int q = 0; q < 32; q += 4) {
         float4 x = have_static ? *reinterpret_cast<float4*>(my + c * 32 + q) : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -507,33 +534,65 @@ pair_embed_kernel(const float* __restrict__ pstatic, float* __restrict__ pair, c
 int pair_embed_dynamic(const PairDims& d, const float* pair_static, float* pair, const float* z, const float* mask,
                        const float* beta, const __half* w_dist, int dist_dim, const float* centers, float rbf_scale,
                        const float* opm_a, const float* opm_b, int opm_dim, const __half* w_opm, const float* b_opm,
-                       int flags, cudaStream_t s) {
+                       int flags, const float* lut, cudaStream_t s) {
   PRD_REQUIRE(dist_dim % 64 == 0 && opm_dim % 64 == 0, "pair_embed: dist_dim %d / opm hidden %d must be multiples of 64",
               dist_dim, opm_dim);
   const long long R = (long long)d.B * d.N * d.N;
   const long long tiles = (R + kTileRows - 1) / kTileRows;
-  const int KBD = dist_dim / 64, KBO = opm_dim / 64;
+  const int KBD = ((flags & 1) == 0 && lut == nullptr) ? dist_dim / 64 : 0, KBO = opm_dim / 64;
   const int grid = (int)(tiles < kNumSMs ? tiles : kNumSMs);
   if (d.CZ == 64) {
     constexpr int CZ = 64;
     const int smem = 1024 + (KBD + KBO) * 16384 + (2 * KBD + KBO) * CZ * 128 + RowStage<CZ>::kBytes + (dist_dim + CZ) * 4 + 64;
     PRD_REQUIRE(smem <= 227 * 1024, "pair_embed: shared memory %d B exceeds 227 KB", smem);
-    auto kern = pair_embed_kernel<CZ>;
+    const bool lut_variant = (flags & 1) == 0 && lut != nullptr;
+    auto kern = lut_variant ? pair_embed_kernel<CZ, true> : pair_embed_kernel<CZ, false>;
     PRD_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    kern<<<grid, 256, smem, s>>>(pair_static, pair, z, mask, beta, w_dist, dist_dim, centers, rbf_scale, opm_a, opm_b,
-                                 opm_dim, w_opm, b_opm, d.N, R, flags);
+    kern<<<lut_variant ? (int)(tiles < 2 * kNumSMs ? tiles : 2 * kNumSMs) : grid, 256, smem, s>>>(pair_static, pair, z, mask, beta, w_dist, dist_dim, centers, rbf_scale, opm_a, opm_b,
+                                 opm_dim, w_opm, b_opm, d.N, R, flags, lut);
   } else if (d.CZ == 32) {
     constexpr int CZ = 32;
     const int smem = 1024 + (KBD + KBO) * 16384 + (2 * KBD + KBO) * CZ * 128 + RowStage<CZ>::kBytes + (dist_dim + CZ) * 4 + 64;
     PRD_REQUIRE(smem <= 227 * 1024, "pair_embed: shared memory %d B exceeds 227 KB", smem);
-    auto kern = pair_embed_kernel<CZ>;
+    const bool lut_variant = (flags & 1) == 0 && lut != nullptr;
+    auto kern = lut_variant ? pair_embed_kernel<CZ, true> : pair_embed_kernel<CZ, false>;
     PRD_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    kern<<<grid, 256, smem, s>>>(pair_static, pair, z, mask, beta, w_dist, dist_dim, centers, rbf_scale, opm_a, opm_b,
-                                 opm_dim, w_opm, b_opm, d.N, R, flags);
+    kern<<<lut_variant ? (int)(tiles < 2 * kNumSMs ? tiles : 2 * kNumSMs) : grid, 256, smem, s>>>(pair_static, pair, z, mask, beta, w_dist, dist_dim, centers, rbf_scale, opm_a, opm_b,
+                                 opm_dim, w_opm, b_opm, d.N, R, flags, lut);
   } else {
     set_error("pair_embed: unsupported pair_dim %d", d.CZ);
     return 1;
   }
+  PRD_LAUNCHED();
+  return 0;
+}
+
+// Table of the distance embedding: lut[(1 + m) * CZ + c] = sum_k W_dist[c][k] exp(-scale (m h - center_k)^2), m = 0 .. M, in
+// fp32 from the fp32 weights; header row: lut[0] = 1 / h, lut[1] = M.  Linear interpolation between rows is exact to
+// h^2 / 8 * |f''| ~ 3e-6 relative at M = 8192 over [0, max center + 0.52] (beyond that every term is below 1e-15).
+__global__ void rbf_lut_kernel(const float* __restrict__ w_dist, const float* __restrict__ centers, float scale, int CZ,
+                               int DD, float h, int M, float* __restrict__ lut) {
+  extern __shared__ float sE[];  // [DD]
+  const int m = blockIdx.x;
+  const float d = h * static_cast<float>(m);
+  for (int k = threadIdx.x; k < DD; k += blockDim.x) {
+    const float dd = d - centers[k];
+    sE[k] = expf(-scale * dd * dd);
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < CZ; c += blockDim.x) {
+    const float* wr = w_dist + (long long)c * DD;
+    float acc = 0.f;
+    for (int k = 0; k < DD; ++k) acc = fmaf(wr[k], sE[k], acc);
+    lut[(long long)(1 + m) * CZ + c] = acc;
+    if (m == 0) lut[c] = c == 0 ? 1.0f / h : (c == 1 ? static_cast<float>(M) : 0.f);
+  }
+}
+
+int rbf_lut_build(int CZ, int DD, const float* w_dist, const float* centers, float scale, float d_max, int M, float* lut,
+                  cudaStream_t s) {
+  PRD_REQUIRE(M >= 2 && d_max > 0.f && CZ >= 2, "rbf_lut_build: bad arguments");
+  rbf_lut_kernel<<<M + 1, 64, DD * sizeof(float), s>>>(w_dist, centers, scale, CZ, DD, d_max / M, M, lut);
   PRD_LAUNCHED();
   return 0;
 }

@@ -28,6 +28,10 @@ from ._packing import PackCache, f32, half, split_k, split_rows, tensor_version
 from .modules import AtomEmbedding, BondEmbedding, Denoiser, Linear, RadialBasisProjection, SinusoidalProjection
 from .synthetic import NUM_RESIDUE_CLASSES, DenoiserConfig
 
+import os as _os
+
+_USE_RBF_LUT = _os.environ.get("PRD_RBF_LUT", "1") != "0"
+
 try:  # the reference derives from LightningModule; keep that when Lightning is installed
     import pytorch_lightning as _pl
 
@@ -210,6 +214,8 @@ class ProteinReDiffModel(_Base):
                 "esm": [split_k(srcs[0])],
                 "w_type": f32(srcs[1]),
                 "pair_dyn": [f32(srcs[2]), f32(srcs[3]), split_rows(srcs[5]), f32(srcs[4])],
+                # d -> W_dist rbf(d) tabulated once per weight version (PRD_RBF_LUT=0 keeps the per-pair RBF GEMM)
+                "rbf_lut": ops.rbf_lut_build(self.cfg, f32(srcs[5]), f32(srcs[4])) if _USE_RBF_LUT and srcs[5].is_cuda else None,
                 "bdist": f32(srcs[6]), "relpos": f32(srcs[7]),
                 "coord": [split_rows(srcs[8]), f32(srcs[9]), f32(srcs[10]).reshape(-1).contiguous()],
                 "seq": [split_k(srcs[11]), f32(srcs[12]), split_k(srcs[13])],
@@ -270,7 +276,7 @@ class ProteinReDiffModel(_Base):
         if pair is None:
             pair = torch.empty(B, N, N, cfg.pair_dim, dtype=torch.float32, device=z.device)
         ops.pair_embed(cfg, pair_static, z.contiguous(), mask, None if sampler_state is not None else t.contiguous(),
-                       a, b, w["pair_dyn"] + [w_o, b_o], pair, sampler_state=sampler_state)
+                       a, b, w["pair_dyn"] + [w_o, b_o], pair, sampler_state=sampler_state, rbf_lut=w["rbf_lut"])
         rec("Denoiser.opm", pair)
         single, pair = self.Denoiser.trunk_(single, pair, mask, probe=probe)
         noise_pred = ops.coord_head(cfg, pair, z.contiguous(), mask, w["coord"], out=bufs.get("noise_pred"))

@@ -78,13 +78,38 @@ def opm_project(cfg, single, mask, weights, out_a=None, out_b=None):
     return out_a, out_b
 
 
-def pair_embed(cfg, pair_static, z, mask, t, opm_a, opm_b, weights, out, sampler_state=None, flags: int = 0):
+def pair_embed(cfg, pair_static, z, mask, t, opm_a, opm_b, weights, out, sampler_state=None, flags: int = 0, rbf_lut=None):
+    """``weights``: the six tensors of include/prd_denoiser.h; ``rbf_lut`` (from :func:`rbf_lut_build`) switches the distance
+    embedding from the per-pair RBF GEMM to the interpolated table."""
     B, N = mask.shape
-    _chk([pair_static, z, mask, t, opm_a, opm_b, out], [F32, F32, F32, I64, F32, F32, F32],
-         ["pair_static", "z", "mask", "t", "opm_a", "opm_b", "pair"])
+    _chk([pair_static, z, mask, t, opm_a, opm_b, out, rbf_lut], [F32, F32, F32, I64, F32, F32, F32, F32],
+         ["pair_static", "z", "mask", "t", "opm_a", "opm_b", "pair", "rbf_lut"])
+    weights = list(weights)[:6]
+    weights += [None] * (6 - len(weights)) + [rbf_lut]  # the C side always reads seven entries
     _lib.call("pair_embed", make_dims(cfg, B, N, mode=flags), [pair_static, z, mask, t, opm_a, opm_b, sampler_state],
               [out], weights)
     return out
+
+
+def rbf_lut_build(cfg, w_dist, centers):
+    """Tabulate d -> W_dist rbf(d) (reference modules.py:73-82 followed by embed_dist's Linear, model.py:360) on the device:
+    fp32 weights, PRD_RBF_LUT_POINTS + 1 rows over [0, max center + 0.52 nm]."""
+    import ctypes
+    _chk([w_dist, centers], [F32, F32], ["w_dist", "centers"])
+    lib = _lib.load()
+    d = make_dims(cfg, 1, 1)
+    lib.prd_rbf_lut_floats.restype = ctypes.c_size_t
+    lib.prd_rbf_lut_floats.argtypes = [ctypes.POINTER(PrdDims)]
+    lib.prd_rbf_lut_build.restype = ctypes.c_int
+    lib.prd_rbf_lut_build.argtypes = [ctypes.POINTER(PrdDims), ctypes.c_void_p, ctypes.c_void_p, ctypes.c_float,
+                                      ctypes.c_void_p, ctypes.c_void_p]
+    lut = torch.empty(int(lib.prd_rbf_lut_floats(ctypes.byref(d))), dtype=F32, device=w_dist.device)
+    d_max = float(centers.max()) + 0.52
+    rc = lib.prd_rbf_lut_build(ctypes.byref(d), w_dist.data_ptr(), centers.data_ptr(), ctypes.c_float(d_max), lut.data_ptr(),
+                               ctypes.c_void_p(torch.cuda.current_stream(w_dist.device).cuda_stream))
+    if rc != 0:
+        raise RuntimeError(f"prd_rbf_lut_build failed: {_lib.last_error()}")
+    return lut
 
 
 def spattention(cfg, single, pair, weights, out=None):

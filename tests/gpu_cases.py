@@ -198,9 +198,27 @@ def case_embeddings(cfg=syn.PAPER, sizes=((9, 50), (12, 60)), seed=0):
     _, (w_o, b_o) = m.Denoiser.opm.packed_weights()
     pair = torch.empty_like(pair_static)
     ops.pair_embed(cfg, pair_static, z.to(DEV), mask.to(DEV), t.to(DEV), a, b, w["pair_dyn"] + [w_o, b_o], pair)
+    # the same with the distance embedding read from the interpolated table instead of the per-pair RBF GEMM
+    pair_lut = torch.empty_like(pair_static)
+    ops.pair_embed(cfg, pair_static, z.to(DEV), mask.to(DEV), t.to(DEV), a, b, w["pair_dyn"] + [w_o, b_o], pair_lut,
+                   rbf_lut=w["rbf_lut"])
     torch.cuda.synchronize()
+    # the table itself against the reference's RadialBasisProjection + Linear in fp64 at off-grid distances
+    lut = w["rbf_lut"].cpu().double()
+    cz = cfg.pair_dim
+    inv_h, M = float(lut[0]), int(lut[1])
+    dq = torch.linspace(0.0, 2.7, 4001, dtype=torch.float64)
+    u = torch.clamp(dq * inv_h, max=float(M))
+    mi = torch.clamp(u.floor().long(), max=M - 1)
+    fr = (u - mi).unsqueeze(-1)
+    rows = lut[cz:].view(M + 1, cz)
+    got_tab = rows[mi] * (1 - fr) + rows[mi + 1] * fr
+    cen = sd["embed_dist.0.center"].double()
+    scale = (cfg.dist_dim - 1) / 2.0
+    want_tab = torch.exp(-scale * (dq.unsqueeze(-1) - cen) ** 2) @ sd["embed_dist.1.weight"].double().t()
     return {"single": (rel(single, want_single), OP_TOL), "pair_static": (rel(pair_static, want_static), 1e-6),
-            "pair": (rel(pair, want_pair_opm), OP_TOL)}
+            "pair": (rel(pair, want_pair_opm), OP_TOL), "pair_rbf_lut": (rel(pair_lut, want_pair_opm), OP_TOL),
+            "rbf_lut_table": (rel(got_tab, want_tab), 2e-5)}
 
 
 def case_heads(cfg=syn.PAPER, B=2, N=72, seed=0, pad=5):

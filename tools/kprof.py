@@ -54,6 +54,16 @@ def main():
         "op_single_attn": lambda: ops.single_attention(cfg, single, pair, mask, blk.single_attn.packed_single(blk.attn_bias[1]), single),
         "op_block": lambda: blk.forward_(cfg, single, pair, mask),
     }
+    # per-step pair embedding (RBF + time + OPM) with / without the interpolated distance table
+    zc = torch.randn(a.B, a.N, 3, generator=g).to(dev)
+    tt = torch.full((a.B,), 17, dtype=torch.int64, device=dev)
+    w = m._weights()
+    oa, ob = m.Denoiser.opm.project(cfg, single, mask)
+    _, (w_o, b_o) = m.Denoiser.opm.packed_weights()
+    pe_out = torch.empty_like(pair)
+    op_calls["op_pair_embed_lut"] = lambda: ops.pair_embed(cfg, pair, zc, mask, tt, oa, ob, w["pair_dyn"] + [w_o, b_o], pe_out,
+                                                           rbf_lut=w["rbf_lut"])
+    op_calls["op_pair_embed_gemm"] = lambda: ops.pair_embed(cfg, pair, zc, mask, tt, oa, ob, w["pair_dyn"] + [w_o, b_o], pe_out)
     for name in list(a.kernels):
         if name == "ops":
             a.kernels.remove("ops")
