@@ -191,6 +191,9 @@ outer_linear_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
 #pragma unroll
           for (int c = 0; c < 8; ++c)
             res[p][c] = *reinterpret_cast<const uint4*>(sRes + p * 16384 + tl * 128 + ((c ^ (tl & 7)) << 4));
+        // generic-proxy reads of the stage must be ordered before the async-proxy (TMA) write that refills it: without
+        // this fence a few rows per launch picked up the NEXT row's residual (seen only with a warm allocator / L2)
+        fence_proxy_async_smem();
         mbar_arrive(res_empty);
       } else {
 #pragma unroll
