@@ -6,6 +6,7 @@
 //                       (AF2_modules.py:519-543, modules.py:395-397)
 //   coord_head          symmetrise (modules.py:403) + weight_radial + equivariant sum (model.py:364-372)
 #include "prd_kernels.h"
+#include <stdlib.h>
 #include "prd_rowtile.cuh"
 
 namespace prd {
@@ -534,6 +535,182 @@ pair_embed_kernel(const float* __restrict__ pstatic, float* __restrict__ pair, c
   if (tid < 32) tmem_dealloc(tmem, TCOLS);
 }
 
+// -----------------------------------------------------------------------------------------
+// pair_dim 64, OPM hidden 128, N % 128 == 0, table-driven distance embedding: the remaining cost of the kernel above is load
+// latency (ncu: issue slots 20 % busy, long-scoreboard 12 cycles per issue on the per-thread opm_a / opm_b / z / table loads).
+// Here a tile is 128 consecutive j of one (b, i) row and a CTA keeps seeing the SAME (b, j-tile) for long runs (tiles are
+// strided by the grid size), so the opm_b rows of the j-tile (64 KB fp32, four swizzled TMA boxes), z_j and mask_j are kept
+// resident and re-fetched only when (b, j-tile) changes; a_i of the NEXT tile arrives by a 512-byte bulk copy a tile ahead;
+// the table rows are requested at tile start and consumed in the epilogue.  One accumulator (OPM), 256 threads = two per row.
+// -----------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256, 1)
+pair_embed_lut_kernel(const __grid_constant__ CUtensorMap map_b, const float* __restrict__ pstatic, float* __restrict__ pair,
+                      const float* __restrict__ z, const float* __restrict__ mask, const float* __restrict__ beta,
+                      const float* __restrict__ opm_a, const __half* __restrict__ w_opm, const float* __restrict__ b_opm,
+                      int N, long long num_tiles, const float* __restrict__ lut) {
+  constexpr int CZ = 64, OD = 128, KBO = 2;
+  extern __shared__ uint8_t raw[];
+  uint8_t* sm = smem_align1024(raw);
+  uint8_t* sA2 = sm;                         // a_i * b_j, 2 x 16 KB
+  uint8_t* sBt = sA2 + KBO * 16384;          // opm_b rows of the j-tile: 4 swizzled boxes [128 x 32 floats]
+  uint8_t* sW2 = sBt + 4 * 16384;            // W_opm, 2 x [CZ x 64]
+  uint8_t* sSt = sW2 + KBO * CZ * 128;       // padded row stage (static rows in, output rows out)
+  float* sAi = reinterpret_cast<float*>(sSt + RowStage<CZ>::kBytes);  // [2][OD]
+  float* sBo = sAi + 2 * OD;                                          // b_opm [CZ]
+  uint64_t* full = reinterpret_cast<uint64_t*>(sBo + CZ);
+  uint64_t* mma_bar = full + 1;
+  uint64_t* bt_bar = full + 2;
+  uint64_t* ai_bar = full + 3;  // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(full + 5);
+
+  const int tid = threadIdx.x, t = tid & 127, half = tid >> 7, warp = t >> 5;
+  if (tid == 0) {
+    mbar_init(full, kTileRows);
+    mbar_init(mma_bar, 1);
+    mbar_init(bt_bar, 1);
+    mbar_init(&ai_bar[0], 1);
+    mbar_init(&ai_bar[1], 1);
+    tma_prefetch_desc(&map_b);
+    fence_barrier_init();
+  }
+  if (tid < 32) tmem_alloc(tmem_slot, CZ);
+  load_weight_kblocks(sW2, w_opm, CZ, OD, OD, tid, 256);
+  for (int i = tid; i < CZ; i += 256) sBo[i] = b_opm[i];
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t tm_lane = tmem + (static_cast<uint32_t>(warp * 32) << 16);
+  const float lut_inv_h = lut[0], lut_m = lut[1];
+  const int tpr = N / kTileRows;  // tiles per (b, i) row
+  auto decode = [&](long long tl, int& b, int& i, int& jt) {
+    const long long bi = tl / tpr;
+    jt = static_cast<int>(tl - bi * tpr);
+    b = static_cast<int>(bi / N);
+    i = static_cast<int>(bi - (long long)b * N);
+  };
+  int cur_b = -1, cur_jt = -1;
+  uint32_t bt_phase = 0, mma_phase = 0;
+  float zj0 = 0.f, zj1 = 0.f, zj2 = 0.f, mj = 0.f;
+  int it = 0;
+  if (blockIdx.x < num_tiles && tid == 0) {  // a_i of the first tile
+    int b, i, jt;
+    decode(blockIdx.x, b, i, jt);
+    mbar_expect_tx(&ai_bar[0], OD * 4);
+    bulk_g2s(sAi, opm_a + ((long long)b * N + i) * OD, OD * 4, &ai_bar[0]);
+  }
+  for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+    int b, i, jt;
+    decode(tile, b, i, jt);
+    const long long r = tile * kTileRows + t;
+    if (half == 0) {
+      bulk_wait_read0();  // previous tile's bulk store has finished reading the stage
+      issue_row_load<CZ>(sSt, t, pstatic + r * CZ, pstatic != nullptr, full);
+    }
+    if (tid == 0 && tile + gridDim.x < num_tiles) {  // a_i of the next tile (its buffer was last read two tiles ago)
+      int nb, ni, njt;
+      decode(tile + gridDim.x, nb, ni, njt);
+      mbar_expect_tx(&ai_bar[(it + 1) & 1], OD * 4);
+      bulk_g2s(sAi + ((it + 1) & 1) * OD, opm_a + ((long long)nb * N + ni) * OD, OD * 4, &ai_bar[(it + 1) & 1]);
+    }
+    if (b != cur_b || jt != cur_jt) {  // CTA-uniform: new j-tile -> resident operands (rare)
+      cur_b = b;
+      cur_jt = jt;
+      // every thread is past the previous tile's reads of sBt (end-of-tile barrier, which follows a proxy fence)
+      if (tid == 0) {
+        mbar_expect_tx(bt_bar, 4 * 16384);
+        for (int q = 0; q < 4; ++q) tma_load_3d(sBt + q * 16384, &map_b, bt_bar, q * 32, jt * kTileRows, b);
+      }
+      const float* zj = z + ((long long)b * N + jt * kTileRows + t) * 3;
+      zj0 = zj[0];
+      zj1 = zj[1];
+      zj2 = zj[2];
+      mj = mask[(long long)b * N + jt * kTileRows + t];
+      mbar_wait(bt_bar, bt_phase);
+      bt_phase ^= 1;
+    }
+    const float* zi = z + ((long long)b * N + i) * 3;
+    const float dx = __ldg(zi) - zj0, dy = __ldg(zi + 1) - zj1, dz = __ldg(zi + 2) - zj2;
+    const float dist = sqrtf(dx * dx + dy * dy + dz * dz);
+    const float m2 = __ldg(mask + (long long)b * N + i) * mj;
+    // table rows around dist / h for this thread's 32 output channels: requested now, interpolated in the epilogue
+    float4 l0[8], l1[8];
+    const float u = fminf(dist * lut_inv_h, lut_m);
+    const int mi = min(static_cast<int>(u), static_cast<int>(lut_m) - 1);
+    const float lfrac = u - static_cast<float>(mi);
+    {
+      const float4* r0 = reinterpret_cast<const float4*>(lut + (long long)(mi + 1) * CZ + 32 * half);
+      const float4* r1 = r0 + CZ / 4;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        l0[q] = __ldg(r0 + q);
+        l1[q] = __ldg(r1 + q);
+      }
+    }
+    // outer product a_i * b_j -> A2: this thread's K-block (= half): 64 products
+    mbar_wait(&ai_bar[it & 1], (it >> 1) & 1);
+    {
+      const float* ai = sAi + (it & 1) * OD + half * 64;
+#pragma unroll
+      for (int k0 = 0; k0 < 64; k0 += 32) {
+        float v[32];
+        const uint8_t* box = sBt + (half * 2 + (k0 >> 5)) * 16384 + t * 128;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const float4 bv = *reinterpret_cast<const float4*>(box + ((c ^ (t & 7)) << 4));
+          const float4 av = *reinterpret_cast<const float4*>(ai + k0 + 4 * c);
+          v[4 * c] = av.x * bv.x; v[4 * c + 1] = av.y * bv.y; v[4 * c + 2] = av.z * bv.z; v[4 * c + 3] = av.w * bv.w;
+        }
+        store_a_cols32(sA2, t, half * 64 + k0, v);
+      }
+    }
+    sync_before_mma();
+    if (tid < 32) {  // warp-uniform issue: UMMA operands stay in uniform registers
+      tc_fence_after();
+      if (elect_one()) {
+        umma_multi(tmem, smem_u32(sA2), smem_u32(sW2), KBO, CZ * 128, umma_idesc_f16(128, CZ), false);
+        umma_commit(mma_bar);
+      }
+      __syncwarp();
+    }
+    mbar_wait(full, it & 1);
+    mbar_wait(mma_bar, mma_phase);
+    mma_phase ^= 1;
+    tc_fence_after();
+    float* my = stage_row<CZ>(sSt, t) + 32 * half;
+    const float* bt = beta + (long long)b * CZ + 32 * half;
+    const float* bo = sBo + 32 * half;
+    const float inv_norm = m2 / (m2 + 1e-3f);  // mask_2d * (.) / (mask_2d + 1e-3)  (AF2_modules.py:539-543, modules.py:395)
+    const bool have_static = pstatic != nullptr;
+    {
+      uint32_t a2[32];
+      tmem_ld32(tm_lane + 32 * half, a2);
+      tmem_ld_wait();
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        float4 x = have_static ? *reinterpret_cast<float4*>(my + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 be = __ldg(reinterpret_cast<const float4*>(bt + 4 * q));
+        x.x += (__uint_as_float(a2[4 * q + 0]) + bo[4 * q + 0]) * inv_norm + m2 * (fmaf(lfrac, l1[q].x - l0[q].x, l0[q].x) + be.x);
+        x.y += (__uint_as_float(a2[4 * q + 1]) + bo[4 * q + 1]) * inv_norm + m2 * (fmaf(lfrac, l1[q].y - l0[q].y, l0[q].y) + be.y);
+        x.z += (__uint_as_float(a2[4 * q + 2]) + bo[4 * q + 2]) * inv_norm + m2 * (fmaf(lfrac, l1[q].z - l0[q].z, l0[q].z) + be.z);
+        x.w += (__uint_as_float(a2[4 * q + 3]) + bo[4 * q + 3]) * inv_norm + m2 * (fmaf(lfrac, l1[q].w - l0[q].w, l0[q].w) + be.w);
+        *reinterpret_cast<float4*>(my + 4 * q) = x;
+      }
+    }
+    fence_proxy_async_smem();  // output rows -> bulk store; also orders this tile's reads of sAi / sBt before later refills
+    tc_fence_before();
+    __syncthreads();  // both halves of every row are staged; TMEM / A tiles are free for the next tile
+    if (half == 0) {
+      bulk_s2g(pair + r * CZ, stage_row<CZ>(sSt, t), CZ * 4);
+      bulk_commit();
+    }
+  }
+  bulk_wait0();
+  tc_fence_before();
+  __syncthreads();
+  if (tid < 32) tmem_dealloc(tmem, CZ);
+}
+
 int pair_embed_dynamic(const PairDims& d, const float* pair_static, float* pair, const float* z, const float* mask,
                        const float* beta, const __half* w_dist, int dist_dim, const float* centers, float rbf_scale,
                        const float* opm_a, const float* opm_b, int opm_dim, const __half* w_opm, const float* b_opm,
@@ -544,6 +721,21 @@ int pair_embed_dynamic(const PairDims& d, const float* pair_static, float* pair,
   const long long tiles = (R + kTileRows - 1) / kTileRows;
   const int KBD = ((flags & 1) == 0 && lut == nullptr) ? dist_dim / 64 : 0, KBO = opm_dim / 64;
   const int grid = (int)(tiles < kNumSMs ? tiles : kNumSMs);
+  static const bool resident_off = getenv("PRD_PAIR_EMBED_RESIDENT") && getenv("PRD_PAIR_EMBED_RESIDENT")[0] == '0';  // A/B timing
+  if (d.CZ == 64 && opm_dim == 128 && flags == 0 && lut != nullptr && d.N % kTileRows == 0 && !resident_off) {
+    // resident-operand kernel: opm_b [B][N][128] fp32 as (k, j, b); box = [32 k][128 j] with the 128-byte swizzle
+    CUtensorMap mb;
+    TmaDims t;
+    t.size[0] = 128; t.size[1] = (uint64_t)d.N; t.size[2] = (uint64_t)d.B; t.size[3] = 1;
+    t.stride[0] = 128 * 4; t.stride[1] = (uint64_t)d.N * 128 * 4; t.stride[2] = 0;
+    t.box[0] = 32; t.box[1] = 128; t.box[2] = 1; t.box[3] = 1;
+    if (make_tensor_map(&mb, opm_b, 4, 3, t, true)) return 1;
+    constexpr int smem = 1024 + 2 * 16384 + 4 * 16384 + 2 * 64 * 128 + RowStage<64>::kBytes + (2 * 128 + 64) * 4 + 64;
+    PRD_CUDA_OK(cudaFuncSetAttribute(pair_embed_lut_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    pair_embed_lut_kernel<<<grid, 256, smem, s>>>(mb, pair_static, pair, z, mask, beta, opm_a, w_opm, b_opm, d.N, tiles, lut);
+    PRD_LAUNCHED();
+    return 0;
+  }
   if (d.CZ == 64) {
     constexpr int CZ = 64;
     const int smem = 1024 + (KBD + KBO) * 16384 + (2 * KBD + KBO) * CZ * 128 + RowStage<CZ>::kBytes + (dist_dim + CZ) * 4 + 64;

@@ -489,6 +489,9 @@ CASES = {
     "opm": lambda: case_opm(),
     "embeddings": lambda: case_embeddings(),
     "embeddings_readme": lambda: case_embeddings(syn.README),
+    # N % 128 == 0 with padding: the resident-operand table kernel (pair_embed_lut_kernel)
+    "embeddings_n128": lambda: case_embeddings(sizes=((16, 112), (12, 100)), seed=3),
+    "embeddings_n256": lambda: case_embeddings(sizes=((30, 226),), seed=4),
     "heads": lambda: case_heads(),
     "pair_bias": lambda: case_pair_bias(),
     "step_paper_n72": lambda: case_step(probes=True),
