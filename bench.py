@@ -401,15 +401,17 @@ def profile_dominant(lib, cfg, B, N, dev, mask, pair, model):
     # the last step's pair tensor -- the attention core's lazy-rescale path would otherwise run on another op's bytes
     blk = model.Denoiser.folding_blocks[0]
     scratch = pair.clone()
-    # triangle-multiplication contraction: 2*B*N^3*c_z flop; a, b fp16 planes in, x fp32 planes out
+    # triangle-multiplication contraction: 2*B*N^3*c_z flop; a, b fp16 planes in, x fp16 planes out (fp32 accumulate)
     blk.pair_mul_outgoing.apply_(cfg, scratch, mask)
     ms = time_kernel("trimul_gemm", None)
     flops = 2.0 * B * N ** 3 * cfg.pair_dim
     out.append({"kernel": "gemm_f16_kernel (tri-mul contraction)", "bound": "tensor", "achieved": flops / ms / 1e9,
                 "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": flops / ms / 1e9 / peaks["tflops"],
                 "traffic": dram("gemm_f16_kernel<256,4> (tri-mul contraction)"),
-                "ms_per_launch": ms, "hbm_floor_ms": (P + P) / peaks["hbm_gbs"] / 1e6,
-                "note": "HBM floor: 0.5 P (a) + 0.5 P (b) + 1 P (x fp32) = 2 P"})
+                "ms_per_launch": ms, "hbm_floor_ms": 1.5 * P / peaks["hbm_gbs"] / 1e6,
+                "hbm_frac": 1.5 * P / ms / 1e6 / peaks["hbm_gbs"],
+                "note": "HBM floor: 0.5 P (a) + 0.5 P (b) + 0.5 P (x as fp16 planes) = 1.5 P; ncu tensor-pipe active 49.5 % "
+                        "(profiles/r01_ncu_traffic.json)"})
     # pair-bias stream: reads P, writes P/16
     ms = time_kernel("pair_bias", pair)
     nbytes = P + P * 4 / cfg.pair_dim

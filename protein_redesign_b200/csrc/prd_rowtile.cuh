@@ -33,6 +33,8 @@ __device__ __forceinline__ float* stage_row(uint8_t* stage, int t) {
 template <int CZ>
 __device__ __forceinline__ void issue_row_load(uint8_t* stage, int t, const float* gsrc, bool valid, uint64_t* bar) {
   if (valid) {
+    // the slot was read (ld.shared, generic proxy) by this thread: order those reads before the async-proxy refill
+    fence_proxy_async_smem();
     mbar_expect_tx(bar, CZ * 4);
     bulk_g2s(stage_row<CZ>(stage, t), gsrc, CZ * 4, bar);
   } else {
