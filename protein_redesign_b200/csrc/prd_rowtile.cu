@@ -1245,29 +1245,33 @@ int triattn_proj(const PairDims& d, const float* pair, int mode, const __half* w
 // =========================================================================================
 template <int CZ>
 __global__ void __launch_bounds__(256, 1)
-triattn_out_kernel(const float* pair, float* dst, int residual, RowMap map, long long R, const __half* __restrict__ og,
-                   const __half* __restrict__ w_o, const float* __restrict__ b_o) {
+triattn_out_kernel(const __grid_constant__ CUtensorMap map_og, const float* pair, float* dst, int residual, RowMap map,
+                   long long R, const __half* __restrict__ w_o, const float* __restrict__ b_o) {
+  // Both inputs of a tile are in flight a tile ahead: the og tile [128 rows x 64 halves] is one swizzled TMA box that IS the
+  // UMMA A operand (issued as soon as the previous tile's UMMAs have completed), the residual rows go to the other of two row
+  // stages (the stage a tile was read from also carries its output rows to the bulk store).
   extern __shared__ uint8_t raw[];
-  constexpr int kGroupBytes = 16384 + (RowStage<CZ>::kBytes + 1023) / 1024 * 1024;
+  constexpr int kStage = (RowStage<CZ>::kBytes + 1023) / 1024 * 1024;
+  constexpr int kGroupBytes = 16384 + 2 * kStage;
   uint8_t* sm = smem_align1024(raw);
   uint8_t* sW = sm;
   uint8_t* sWl = sW + CZ * 128;
   uint8_t* sG = sm + ((2 * CZ * 128 + 1023) / 1024) * 1024;
   float* sB = reinterpret_cast<float*>(sG + 2 * kGroupBytes);
   uint64_t* bars = reinterpret_cast<uint64_t*>(sB + CZ);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
   constexpr int TCOLS = CZ < 32 ? 32 : CZ;
 
   const Group g;
   uint8_t* sA = sG + g.grp * kGroupBytes;
-  uint8_t* sSt = sA + 16384;
-  uint64_t* full = bars + g.grp;
-  uint64_t* mma_bar = bars + 2 + g.grp;
+  uint8_t* sSt = sA + 16384;  // two stages, kStage apart
+  uint64_t* full = bars + g.grp * 2;  // [2]
+  uint64_t* mma_bar = bars + 4 + g.grp;
+  uint64_t* afull = bars + 6 + g.grp;
   if (threadIdx.x == 0) {
-    mbar_init(&bars[0], kTileRows);
-    mbar_init(&bars[1], kTileRows);
-    mbar_init(&bars[2], 1);
-    mbar_init(&bars[3], 1);
+    for (int q = 0; q < 4; ++q) mbar_init(&bars[q], kTileRows);
+    for (int q = 4; q < 8; ++q) mbar_init(&bars[q], 1);
+    tma_prefetch_desc(&map_og);
     fence_barrier_init();
   }
   if (threadIdx.x < 32) tmem_alloc(tmem_slot, 2 * TCOLS);
@@ -1285,32 +1289,44 @@ triattn_out_kernel(const float* pair, float* dst, int residual, RowMap map, long
   const long long stride = (long long)gridDim.x * 2;
   uint32_t mma_phase = 0;
   long long tile = (long long)blockIdx.x * 2 + g.grp;
-  for (int it = 0; tile < num_tiles; tile += stride, ++it) {
-    const long long r = tile * kTileRows + t;
-    const bool valid = r < R;
+  auto src_of = [&](long long tl, bool& valid) {
+    const long long r = tl * kTileRows + t;
+    valid = r < R;
     long long src = 0;
     if (valid) {
       int b, s, tk;
       map.decompose(r, b, s, tk);
       src = map.src_row(b, s, tk);
     }
-    bulk_wait_read0();  // this thread's previous output row has left the stage
+    return src;
+  };
+  auto issue_og = [&](long long tl) {  // one thread; rows past R are zero-filled by the TMA unit
+    mbar_expect_tx(afull, 16384);
+    tma_load_3d(sA, &map_og, afull, 0, static_cast<int>(tl * kTileRows), 0);
+  };
+  bool valid = false;
+  long long src = 0;
+  if (tile < num_tiles) {
+    src = src_of(tile, valid);
     issue_row_load<CZ>(sSt, t, pair + src * CZ, valid && residual, full);
-    {
-      // og rows are contiguous in logical row order: the warp's 32 rows x 128 bytes are fetched with fully coalesced
-      // 16-byte loads (lane -> chunk (i*32 + lane) of the 4 KB block) and dropped straight into the swizzled A tile
-      const int lane = t & 31, w32 = (t >> 5) * 32;
-      const long long row0 = tile * kTileRows + w32;
-      const uint4* op = reinterpret_cast<const uint4*>(og + row0 * 64);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int rr = i * 4 + (lane >> 3), ch = lane & 7;
-        const uint4 v = (row0 + rr < R) ? __ldg(op + i * 32 + lane) : make_uint4(0, 0, 0, 0);
-        *reinterpret_cast<uint4*>(sA + sw128_offset(w32 + rr, ch)) = v;
-      }
+    if (t == 0) issue_og(tile);
+  }
+  for (int it = 0; tile < num_tiles; tile += stride, ++it) {
+    const int cur = it & 1;
+    const bool has_next = tile + stride < num_tiles;
+    bool valid_n = false;
+    long long src_n = 0;
+    // the other stage carried the previous tile's output row of this thread: its bulk store must have read it
+    bulk_wait_read0();
+    if (has_next) {
+      src_n = src_of(tile + stride, valid_n);
+      issue_row_load<CZ>(sSt + (cur ^ 1) * kStage, t, pair + src_n * CZ, valid_n && residual, full + (cur ^ 1));
     }
-    g.sync_before_mma();
+    // every thread of the group has finished the previous tile's TMEM reads
+    tc_fence_before();
+    g.bar();
     if (t < 32) {  // warp-uniform issue: UMMA operands stay in uniform registers
+      mbar_wait(afull, it & 1);
       tc_fence_after();
       if (elect_one()) {
         umma_multi(tmem, smem_u32(sA), smem_u32(sW), 1, CZ * 128, umma_idesc_f16(128, CZ), false);
@@ -1319,11 +1335,12 @@ triattn_out_kernel(const float* pair, float* dst, int residual, RowMap map, long
       }
       __syncwarp();
     }
-    mbar_wait(full, it & 1);
+    mbar_wait(full + cur, (it >> 1) & 1);
     mbar_wait(mma_bar, mma_phase);
     mma_phase ^= 1;
     tc_fence_after();
-    float* my = stage_row<CZ>(sSt, t);
+    if (t == 64 && has_next) issue_og(tile + stride);  // the A tile is free: this tile's UMMAs have completed
+    float* my = stage_row<CZ>(sSt + cur * kStage, t);
 #pragma unroll
     for (int c = 0; c < CZ / 32; ++c) {
       uint32_t acc[32];
@@ -1342,7 +1359,8 @@ triattn_out_kernel(const float* pair, float* dst, int residual, RowMap map, long
     fence_proxy_async_smem();
     if (valid) bulk_s2g(dst + src * CZ, my, CZ * 4);
     bulk_commit();
-    tc_fence_before();
+    valid = valid_n;
+    src = src_n;
   }
   bulk_wait0();
   tc_fence_before();
@@ -1356,11 +1374,21 @@ static int launch_triattn_out(const PairDims& d, const float* pair, float* dst, 
   const long long R = (long long)d.B * d.N * d.N;
   const long long tiles = (R + kTileRows - 1) / kTileRows;
   RowMap map{d.N, (long long)d.N * d.N, mode};
-  constexpr int kGroupBytes = 16384 + (RowStage<CZ>::kBytes + 1023) / 1024 * 1024;
-  constexpr int smem = 1024 + ((2 * CZ * 128 + 1023) / 1024) * 1024 + 2 * kGroupBytes + CZ * 4 + 64;
+  constexpr int kStage = (RowStage<CZ>::kBytes + 1023) / 1024 * 1024;
+  constexpr int kGroupBytes = 16384 + 2 * kStage;
+  constexpr int smem = 1024 + ((2 * CZ * 128 + 1023) / 1024) * 1024 + 2 * kGroupBytes + CZ * 4 + 128;
   auto kern = triattn_out_kernel<CZ>;
   if (set_smem(kern, smem)) return 1;
-  kern<<<grid_for((tiles + 1) / 2, 1), 256, smem, s>>>(pair, dst, residual, map, R, og, w_o, b_o);
+  // og [R rows][64 halves] as (channel, row, 1); box = [64][128 rows] with the 128-byte swizzle = one UMMA A K-block
+  CUtensorMap mo;
+  {
+    TmaDims t;
+    t.size[0] = 64; t.size[1] = (uint64_t)R; t.size[2] = 1; t.size[3] = 1;
+    t.stride[0] = 128; t.stride[1] = (uint64_t)R * 128; t.stride[2] = 0;
+    t.box[0] = 64; t.box[1] = 128; t.box[2] = 1; t.box[3] = 1;
+    if (make_tensor_map(&mo, og, 2, 3, t, true)) return 1;
+  }
+  kern<<<grid_for((tiles + 1) / 2, 1), 256, smem, s>>>(mo, pair, dst, residual, map, R, w_o, b_o);
   PRD_LAUNCHED();
   return 0;
 }
