@@ -189,11 +189,13 @@ int softmax_rows(float* logits, __half* probs, long long rows, int n, int ld_in,
 }
 
 // -----------------------------------------------------------------------------------------
-// FoldingBlock.single_attn core (modules.py:185-225 with attn_bias): head_dim 16, 4 heads.
-// CTA = (32 queries, h, b), 128 threads: thread (query q = t / 4, part = t % 4) runs the online softmax over the
-// keys j = part (mod 4); the four partial states of a query are merged with shuffles.  K/V of (b,h) in shared
-// memory; the bias tile is staged through shared memory so the [B,H,N,N] bias is read with coalesced lines.
-// (One thread per query over all N keys left 128 CTAs x 4 warps for the whole GPU: 0.165 ms; now 512 CTAs.)
+// FoldingBlock.single_attn core (modules.py:185-225): CTA = 32 queries of one (b, head); warp w takes a quarter of the keys
+// for ALL 32 queries (lane = query), so every K / V row is a warp-uniform shared-memory read (one broadcast wavefront;
+// with four threads per query the four key rows of a warp conflicted and short-scoreboard was 5.7 cycles per issue).  Scores
+// of 8 keys at a time (independent dot products), one running-max update per 8 keys; the bias row of a query is read
+// straight from global memory (row-contiguous: 32 bytes per lane per 8 keys, the next 8 prefetched).  The four partial
+// softmax states of a query are merged through shared memory; each thread then writes 4 of the 16 gated channels.
+// K/V of (b,h) in shared memory.  qkvg [B*N, 4*H*16] fp32 (q|k|v|gate pre-activation), bias [B,H,N,N], mask [B,N].
 // -----------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128)
 single_attention_kernel(int N, int H, const float* __restrict__ qkvg, const float* __restrict__ bias,
@@ -203,24 +205,28 @@ single_attention_kernel(int N, int H, const float* __restrict__ qkvg, const floa
   float* sK = sm;               // [N][16]
   float* sV = sK + (size_t)N * C;
   float* sMask = sV + (size_t)N * C;  // [N]
-  float* sBias = sMask + N;           // [32][33]
+  float* sPart = sMask + ((N + 3) & ~3);  // [4 warps][32 queries][18]: m, l, o[16]
   const int t = threadIdx.x;
   const int h = blockIdx.y, b = blockIdx.z;
-  const int qi = t >> 2, part = t & 3;
-  const int i = blockIdx.x * QT + qi;
+  const int warp = t >> 5, lane = t & 31;
+  const int i = blockIdx.x * QT + lane;
   const int ld = 4 * H * C;
-  for (int idx = t; idx < N * C; idx += 128) {
-    const int j = idx / C, c = idx % C;
-    const float* row = qkvg + ((long long)b * N + j) * ld;
-    sK[idx] = row[H * C + h * C + c];
-    sV[idx] = row[2 * H * C + h * C + c];
+  // K / V of this (b, head): 16 floats per token and tensor, staged with 16-byte loads (4 per row and tensor)
+  for (int idx = t; idx < N * (C / 4); idx += 128) {
+    const int j = idx >> 2, c4 = idx & 3;
+    const float* row = qkvg + ((long long)b * N + j) * ld + h * C + c4 * 4;
+    reinterpret_cast<float4*>(sK)[idx] = __ldg(reinterpret_cast<const float4*>(row + H * C));
+    reinterpret_cast<float4*>(sV)[idx] = __ldg(reinterpret_cast<const float4*>(row + 2 * H * C));
   }
   for (int j = t; j < N; j += 128) sMask[j] = mask[(long long)b * N + j];
   float q[C];
   if (i < N) {
-    const float* row = qkvg + ((long long)b * N + i) * ld;
+    const float4* row = reinterpret_cast<const float4*>(qkvg + ((long long)b * N + i) * ld + h * C);
 #pragma unroll
-    for (int c = 0; c < C; ++c) q[c] = 0.25f * row[h * C + c];
+    for (int c4 = 0; c4 < 4; ++c4) {
+      const float4 v = __ldg(row + c4);
+      q[4 * c4] = 0.25f * v.x; q[4 * c4 + 1] = 0.25f * v.y; q[4 * c4 + 2] = 0.25f * v.z; q[4 * c4 + 3] = 0.25f * v.w;
+    }
   } else {
 #pragma unroll
     for (int c = 0; c < C; ++c) q[c] = 0.f;
@@ -228,69 +234,99 @@ single_attention_kernel(int N, int H, const float* __restrict__ qkvg, const floa
   float m = -INFINITY, l = 0.f, o[C];
 #pragma unroll
   for (int c = 0; c < C; ++c) o[c] = 0.f;
-  const float* bias_bh = bias + ((long long)b * H + h) * N * N;
-  const int warp = t >> 5, lane = t & 31;
-  // bias[i0 .. i0+31][j0 .. j0+31] is staged through shared memory one 32-key stage ahead: the global loads of stage
-  // s+1 are in flight (registers) while stage s is processed
-  float bnext[QT / 4];
+  // this warp's key range: a quarter of the keys, in whole groups of 8
+  const int chunk = (((N + 3) / 4) + 7) & ~7;
+  const int jbeg = warp * chunk, jend = min(N, jbeg + chunk);
+  const float* brow = bias + (((long long)b * H + h) * N + min(i, N - 1)) * N;
+  const bool vec = (N & 3) == 0;  // 16-byte aligned bias rows
+  float bn[8];
   auto fetch_bias = [&](int j0) {
+    if (vec && j0 + 8 <= jend) {
+      const float4 x0 = __ldg(reinterpret_cast<const float4*>(brow + j0)), x1 = __ldg(reinterpret_cast<const float4*>(brow + j0 + 4));
+      bn[0] = x0.x; bn[1] = x0.y; bn[2] = x0.z; bn[3] = x0.w; bn[4] = x1.x; bn[5] = x1.y; bn[6] = x1.z; bn[7] = x1.w;
+    } else {
 #pragma unroll
-    for (int k = 0; k < QT / 4; ++k) {
-      const int r = warp + 4 * k, ii = blockIdx.x * QT + r, jj = j0 + lane;
-      bnext[k] = (j0 < N && ii < N && jj < N) ? bias_bh[(long long)ii * N + jj] : 0.f;
+      for (int e = 0; e < 8; ++e) bn[e] = (j0 + e < jend) ? __ldg(brow + j0 + e) : 0.f;
     }
   };
-  fetch_bias(0);
-  for (int j0 = 0; j0 < N; j0 += 32) {
-    __syncthreads();  // the previous stage's tile has been consumed (also covers the K / V staging the first time)
+  if (jbeg < jend) fetch_bias(jbeg);
+  __syncthreads();  // K / V / mask staged
+  for (int j0 = jbeg; j0 < jend; j0 += 8) {
+    float bc[8];
 #pragma unroll
-    for (int k = 0; k < QT / 4; ++k) sBias[(warp + 4 * k) * 33 + lane] = bnext[k];
-    __syncthreads();
-    fetch_bias(j0 + 32);
-    const int jn = min(32, N - j0);
-    for (int jj = part; jj < jn; jj += 4) {
-      const int j = j0 + jj;
-      const float* kr = sK + j * C;
-      float s = 0.f;
+    for (int e = 0; e < 8; ++e) bc[e] = bn[e];
+    if (j0 + 8 < jend) fetch_bias(j0 + 8);
+    float sc[8];
 #pragma unroll
-      for (int c = 0; c < C; ++c) s += q[c] * kr[c];
-      s += sBias[qi * 33 + jj];
-      if (sMask[j] < 0.5f) s = -32768.0f;
-      const float mn = fmaxf(m, s);
-      const float a = __expf(m - mn), p = __expf(s - mn);
-      l = l * a + p;
-      const float* vr = sV + j * C;
-#pragma unroll
-      for (int c = 0; c < C; ++c) o[c] = o[c] * a + p * vr[c];
-      m = mn;
+    for (int e = 0; e < 8; ++e) {
+      const int j = j0 + e;
+      if (j < jend) {  // warp-uniform
+        const float4* kr = reinterpret_cast<const float4*>(sK + j * C);
+        const float4 k0 = kr[0], k1 = kr[1], k2 = kr[2], k3 = kr[3];
+        const float p0 = q[0] * k0.x + q[1] * k0.y + q[2] * k0.z + q[3] * k0.w;
+        const float p1 = q[4] * k1.x + q[5] * k1.y + q[6] * k1.z + q[7] * k1.w;
+        const float p2 = q[8] * k2.x + q[9] * k2.y + q[10] * k2.z + q[11] * k2.w;
+        const float p3 = q[12] * k3.x + q[13] * k3.y + q[14] * k3.z + q[15] * k3.w;
+        float sv = ((p0 + p1) + (p2 + p3)) + bc[e];
+        if (sMask[j] < 0.5f) sv = -32768.0f;
+        sc[e] = sv;
+      } else {
+        sc[e] = -INFINITY;
+      }
     }
-  }
-  // merge the four partial softmax states of the query (lanes 4 q .. 4 q + 3)
+    float mn = m;
 #pragma unroll
-  for (int off = 1; off <= 2; off <<= 1) {
-    const float m2 = __shfl_xor_sync(0xffffffffu, m, off);
-    const float l2 = __shfl_xor_sync(0xffffffffu, l, off);
-    const float mn = fmaxf(m, m2);
-    const float a = (m == -INFINITY) ? 0.f : __expf(m - mn), a2 = (m2 == -INFINITY) ? 0.f : __expf(m2 - mn);
-    l = l * a + l2 * a2;
+    for (int e = 0; e < 8; ++e) mn = fmaxf(mn, sc[e]);
+    const float a = __expf(m - mn);  // m = -inf (first group) -> 0; mn is finite: the group holds at least one key
+    l *= a;
 #pragma unroll
-    for (int c = 0; c < C; ++c) {
-      const float o2 = __shfl_xor_sync(0xffffffffu, o[c], off);
-      o[c] = o[c] * a + o2 * a2;
+    for (int c = 0; c < C; ++c) o[c] *= a;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int j = j0 + e;
+      if (j < jend) {
+        const float pe = __expf(sc[e] - mn);
+        l += pe;
+        const float4* vr = reinterpret_cast<const float4*>(sV + j * C);
+        const float4 v0 = vr[0], v1 = vr[1], v2 = vr[2], v3 = vr[3];
+        o[0] += pe * v0.x; o[1] += pe * v0.y; o[2] += pe * v0.z; o[3] += pe * v0.w;
+        o[4] += pe * v1.x; o[5] += pe * v1.y; o[6] += pe * v1.z; o[7] += pe * v1.w;
+        o[8] += pe * v2.x; o[9] += pe * v2.y; o[10] += pe * v2.z; o[11] += pe * v2.w;
+        o[12] += pe * v3.x; o[13] += pe * v3.y; o[14] += pe * v3.z; o[15] += pe * v3.w;
+      }
     }
     m = mn;
   }
-  if (i < N) {
-    // each of the four threads of a query writes four of its 16 gated channels
-    const float inv = 1.0f / l;
-    const float* row = qkvg + ((long long)b * N + i) * ld + 3 * H * C + h * C;
-    __half* dst = og + ((long long)b * N + i) * (H * C) + h * C;
+  // partial state of (warp, query) -> shared memory; thread (w, lane) then merges the four states of query `lane` and
+  // writes channels [4 w, 4 w + 4)
+  {
+    float* p = sPart + (warp * QT + lane) * 18;
+    p[0] = m;
+    p[1] = l;
 #pragma unroll
-    for (int c = 0; c < C; ++c) {
-      if ((c >> 2) == part) {
-        const float gate = 1.0f / (1.0f + __expf(-row[c]));
-        dst[c] = __float2half_rn(gate * o[c] * inv);
-      }
+    for (int c = 0; c < C; ++c) p[2 + c] = o[c];
+  }
+  __syncthreads();
+  if (i < N) {
+    float mm = -INFINITY;
+#pragma unroll
+    for (int w = 0; w < 4; ++w) mm = fmaxf(mm, sPart[(w * QT + lane) * 18]);
+    float lsum = 0.f, acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+      const float* p = sPart + (w * QT + lane) * 18;
+      const float sc = (p[0] == -INFINITY) ? 0.f : __expf(p[0] - mm);
+      lsum += p[1] * sc;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[e] += p[2 + 4 * warp + e] * sc;
+    }
+    const float inv = 1.0f / lsum;
+    const float* row = qkvg + ((long long)b * N + i) * ld + 3 * H * C + h * C + 4 * warp;
+    __half* dst = og + ((long long)b * N + i) * (H * C) + h * C + 4 * warp;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float gate = 1.0f / (1.0f + __expf(-row[e]));
+      dst[e] = __float2half_rn(gate * acc[e] * inv);
     }
   }
 }
@@ -298,7 +334,7 @@ single_attention_kernel(int N, int H, const float* __restrict__ qkvg, const floa
 int single_attention(int B, int N, int H, int c, const float* qkvg, const float* bias, const float* mask, __half* og,
                      cudaStream_t s) {
   PRD_REQUIRE(c == 16, "single_attention: head_dim %d unsupported (built for 16)", c);
-  const int smem = (2 * N * 16 + N + 32 * 33) * 4;
+  const int smem = (2 * N * 16 + ((N + 3) & ~3) + 4 * 32 * 18) * 4;
   PRD_REQUIRE(smem <= 227 * 1024, "single_attention: N=%d needs %d B of shared memory", N, smem);
   PRD_CUDA_OK(cudaFuncSetAttribute(single_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   dim3 grid((N + 31) / 32, H, B);
