@@ -158,7 +158,9 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                             ((reinterpret_cast<uintptr_t>(reinterpret_cast<float*>(ep.C) + boff_c + n0) & 15) == 0);
       // warp-uniform: plain fp16 C (the tri-mul contraction result), full tile width, 16-byte aligned rows: 64-column chunks
       // (128 bytes per row) leave as full lines
-      const bool coalesce16 = ep.c_fp16 && plain && BN >= 64 && (n0 + BN <= ep.N) && ((ep.ldc & 7) == 0) && (m0 + 128 <= ep.M) &&
+      // (bias / activation / alpha are applied in registers; row scale, mul and add operands keep the general path)
+      const bool simple = ep.rowscale == nullptr && mulp == nullptr && addp == nullptr;
+      const bool coalesce16 = ep.c_fp16 && simple && BN >= 64 && (n0 + BN <= ep.N) && ((ep.ldc & 7) == 0) && (m0 + 128 <= ep.M) &&
                               ((reinterpret_cast<uintptr_t>(reinterpret_cast<__half*>(ep.C) + boff_c + n0) & 15) == 0);
       if (coalesce16) {
 #pragma unroll 1
@@ -168,6 +170,38 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
           tmem_ld32(tmem + buf * BN + (static_cast<uint32_t>(q * 32) << 16) + c * 64, r0);
           tmem_ld32(tmem + buf * BN + (static_cast<uint32_t>(q * 32) << 16) + c * 64 + 32, r1);
           tmem_ld_wait();
+          if (!plain) {
+            const int colb = n0 + c * 64;
+            const bool bvec = ep.bias != nullptr && ((reinterpret_cast<uintptr_t>(ep.bias + colb) & 15) == 0);
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4) {
+              float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
+              if (bvec) {
+                b0 = __ldg(reinterpret_cast<const float4*>(ep.bias + colb) + j4);
+                b1 = __ldg(reinterpret_cast<const float4*>(ep.bias + colb + 32) + j4);
+              } else if (ep.bias != nullptr) {
+                b0 = make_float4(__ldg(ep.bias + colb + 4 * j4), __ldg(ep.bias + colb + 4 * j4 + 1), __ldg(ep.bias + colb + 4 * j4 + 2),
+                                 __ldg(ep.bias + colb + 4 * j4 + 3));
+                b1 = make_float4(__ldg(ep.bias + colb + 32 + 4 * j4), __ldg(ep.bias + colb + 32 + 4 * j4 + 1),
+                                 __ldg(ep.bias + colb + 32 + 4 * j4 + 2), __ldg(ep.bias + colb + 32 + 4 * j4 + 3));
+              }
+              const float bb0[4] = {b0.x, b0.y, b0.z, b0.w}, bb1[4] = {b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const int j = 4 * j4 + e;
+                float x0 = fmaf(ep.alpha, __uint_as_float(r0[j]), bb0[e]), x1 = fmaf(ep.alpha, __uint_as_float(r1[j]), bb1[e]);
+                if (ep.act == 1) {
+                  x0 = fmaxf(x0, 0.0f);
+                  x1 = fmaxf(x1, 0.0f);
+                } else if (ep.act == 2) {
+                  x0 = 1.0f / (1.0f + __expf(-x0));
+                  x1 = 1.0f / (1.0f + __expf(-x1));
+                }
+                r0[j] = __float_as_uint(x0);
+                r1[j] = __float_as_uint(x1);
+              }
+            }
+          }
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             ov[j] = make_uint4(pack_half2(__uint_as_float(r0[8 * j]), __uint_as_float(r0[8 * j + 1])),
@@ -193,27 +227,76 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         tmem_ld32(tmem + buf * BN + (static_cast<uint32_t>(q * 32) << 16) + c * 32, r);
         tmem_ld_wait();
         const int col0 = n0 + c * 32;
-        if (row < ep.M && col0 < ep.N) {
-          float v[32];
-          if (plain) {
+        // Epilogue operands: per-element scalar loads (32 bias loads and, per lane, 32 strided mul / add loads per chunk) made
+        // the four epilogue warps the bottleneck of every single-representation GEMM (ncu: tensor pipe 3-7 % on the
+        // SPAttention logits / PV / gate GEMMs).  Full chunks now take the bias as 8 broadcast float4 loads and the
+        // [M, N] operands as coalesced 128-byte rows through the warp's slice.
+        const bool chunk_full = (col0 + 32 <= ep.N);  // warp-uniform
+        const bool active = row < ep.M && col0 < ep.N;
+        float v[32];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        if (!plain) {
+          const bool bias_vec = ep.bias != nullptr && chunk_full && ((reinterpret_cast<uintptr_t>(ep.bias + col0) & 15) == 0);
+          if (bias_vec) {
+            const float4* b4 = reinterpret_cast<const float4*>(ep.bias + col0);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 bb = __ldg(b4 + j);
+              v[4 * j] = fmaf(ep.alpha, v[4 * j], bb.x);
+              v[4 * j + 1] = fmaf(ep.alpha, v[4 * j + 1], bb.y);
+              v[4 * j + 2] = fmaf(ep.alpha, v[4 * j + 2], bb.z);
+              v[4 * j + 3] = fmaf(ep.alpha, v[4 * j + 3], bb.w);
+            }
           } else {
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
-              const int col = col0 + j;
-              float x = ep.alpha * __uint_as_float(r[j]);
-              if (col < ep.N) {
-                if (ep.bias) x += __ldg(ep.bias + col);
-                if (ep.act == 1) x = fmaxf(x, 0.0f);
-                else if (ep.act == 2) x = 1.0f / (1.0f + __expf(-x));
-                x *= rs;
-                if (mulp) x *= mulp[col];
-                if (addp) x += addp[col];
-              }
-              v[j] = x;
+              v[j] *= ep.alpha;
+              if (ep.bias != nullptr && col0 + j < ep.N) v[j] += __ldg(ep.bias + col0 + j);
             }
           }
+          if (ep.act == 1) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
+          } else if (ep.act == 2) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = 1.0f / (1.0f + __expf(-v[j]));
+          }
+          if (ep.rowscale != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] *= rs;
+          }
+          const int rows_left = ep.M - (m0 + q * 32);
+          if (ep.mul != nullptr) {
+            const float* mb = ep.mul + (long long)i1 * ep.mul_bs1 + (long long)i2 * ep.mul_bs2 + (long long)(m0 + q * 32) * ep.ldmul + col0;
+            if (chunk_full && ((ep.ldmul & 3) == 0) && ((reinterpret_cast<uintptr_t>(mb) & 15) == 0)) {
+              uint4 t4[8];
+              warp_load_rows128(epi + q * 4096, lane, t4, mb, (long long)ep.ldmul * 4, rows_left);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                v[4 * j] *= __uint_as_float(t4[j].x); v[4 * j + 1] *= __uint_as_float(t4[j].y);
+                v[4 * j + 2] *= __uint_as_float(t4[j].z); v[4 * j + 3] *= __uint_as_float(t4[j].w);
+              }
+            } else if (active) {
+              for (int j = 0; j < 32 && col0 + j < ep.N; ++j) v[j] *= mulp[col0 + j];
+            }
+          }
+          if (ep.add != nullptr) {
+            const float* ab = ep.add + (long long)i1 * ep.add_bs1 + (long long)i2 * ep.add_bs2 + (long long)(m0 + q * 32) * ep.ldadd + col0;
+            if (chunk_full && ((ep.ldadd & 3) == 0) && ((reinterpret_cast<uintptr_t>(ab) & 15) == 0)) {
+              uint4 t4[8];
+              warp_load_rows128(epi + q * 4096, lane, t4, ab, (long long)ep.ldadd * 4, rows_left);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                v[4 * j] += __uint_as_float(t4[j].x); v[4 * j + 1] += __uint_as_float(t4[j].y);
+                v[4 * j + 2] += __uint_as_float(t4[j].z); v[4 * j + 3] += __uint_as_float(t4[j].w);
+              }
+            } else if (active) {
+              for (int j = 0; j < 32 && col0 + j < ep.N; ++j) v[j] += addp[col0 + j];
+            }
+          }
+        }
+        if (active) {
           const bool full_chunk = (col0 + 32 <= ep.N);
           if (ep.c_fp16) {
             __half* cp = reinterpret_cast<__half*>(ep.C) + boff_c + (long long)row * ep.ldc + col0;

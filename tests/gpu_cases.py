@@ -58,7 +58,7 @@ def _pair_inputs(cfg, B, N, seed, pad=0):
 # ------------------------------------------------------------------------------------------
 # tcgen05 + TMA machinery
 # ------------------------------------------------------------------------------------------
-def case_gemm(M=256, N=128, K=64, nb1=1, nb2=1, epilogue=False, out_fp16=False, seed=0):
+def case_gemm(M=256, N=128, K=64, nb1=1, nb2=1, epilogue=False, out_fp16=False, seed=0, bias_act=0):
     g = torch.Generator().manual_seed(seed)
     a = (torch.randn(nb2, nb1, M, K, generator=g)).half()
     b = (torch.randn(nb2, nb1, N, K, generator=g)).half()
@@ -72,6 +72,11 @@ def case_gemm(M=256, N=128, K=64, nb1=1, nb2=1, epilogue=False, out_fp16=False, 
         want = torch.relu(0.5 * want + bias) * rowscale.unsqueeze(-1) * mul + add
         kw = dict(alpha=0.5, bias=bias.to(DEV), act=1, rowscale=rowscale.to(DEV).contiguous(),
                   mul=mul.to(DEV).contiguous(), add=add.to(DEV).contiguous())
+    if bias_act:  # alpha + bias + activation only: the full-line fp16 store path of the single-representation projections
+        bias = torch.randn(N, generator=g)
+        want = 0.25 * want + bias
+        want = torch.relu(want) if bias_act == 1 else torch.sigmoid(want)
+        kw = dict(alpha=0.25, bias=bias.to(DEV), act=bias_act)
     out = torch.full((nb2, nb1, M, N), float("nan"), dtype=torch.float16 if out_fp16 else torch.float32, device=DEV)
     _lib.gemm_f16(a.to(DEV).contiguous(), b.to(DEV).contiguous(), out, **kw)
     torch.cuda.synchronize()
@@ -459,6 +464,8 @@ CASES = {
     "gemm_batch": lambda: case_gemm(128, 128, 128, nb1=3, nb2=2),
     "gemm_epilogue": lambda: case_gemm(200, 136, 128, nb1=2, epilogue=True),
     "gemm_fp16_out": lambda: case_gemm(256, 128, 256, out_fp16=True),
+    "gemm_fp16_relu": lambda: case_gemm(384, 512, 128, out_fp16=True, bias_act=1),
+    "gemm_fp16_sigmoid": lambda: case_gemm(256, 256, 64, nb1=2, out_fp16=True, bias_act=2),
     "pair_transition": lambda: case_pair_transition(),
     "pair_transition_readme": lambda: case_pair_transition(syn.README, 2, 40),
     "trimul_outgoing": lambda: case_trimul(mode="outgoing"),

@@ -24,7 +24,7 @@ def _need_gpu(cuda_device):
 
 
 CASE_NAMES = [
-    "gemm_basic", "gemm_k512", "gemm_tails", "gemm_n48", "gemm_batch", "gemm_epilogue", "gemm_fp16_out",
+    "gemm_basic", "gemm_k512", "gemm_tails", "gemm_n48", "gemm_batch", "gemm_epilogue", "gemm_fp16_out", "gemm_fp16_relu", "gemm_fp16_sigmoid",
     "pair_transition", "pair_transition_readme", "pair_transition_n140", "trimul_outgoing", "trimul_incoming",
     "trimul_readme", "trimul_n140", "trimul_n300", "trimul_n256", "trimul_n128", "triattn_starting", "triattn_ending", "triattn_n200", "triattn_n140",
     "triattn_n300", "triattn_n512", "triattn_readme", "outer_linear", "outer_linear_readme", "outer_linear_n300",

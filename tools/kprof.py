@@ -53,6 +53,8 @@ def main():
         "op_outer_linear": lambda: blk.outer_linear.apply_(cfg, single, pair),
         "op_single_attn": lambda: ops.single_attention(cfg, single, pair, mask, blk.single_attn.packed_single(blk.attn_bias[1]), single),
         "op_block": lambda: blk.forward_(cfg, single, pair, mask),
+        "op_single_fc": lambda: ops.single_transition(cfg, single, blk.single_fc.packed_single(), single),
+        "op_spattention": lambda: ops.spattention(cfg, single, pair, m.Denoiser.SPAAttnBlock.packed_weights(), out=single),
     }
     # per-step pair embedding (RBF + time + OPM) with / without the interpolated distance table
     zc = torch.randn(a.B, a.N, 3, generator=g).to(dev)
