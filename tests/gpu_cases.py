@@ -507,6 +507,11 @@ CASES = {
     "sample_eager": lambda: case_sample(graph=False),
     "sample_graph": lambda: case_sample(graph=True),
     "invariants": lambda: case_invariants(),
+    # BASELINE.json's full sizes, through size-independent properties (no oracle at these sizes): config 2 (~300 tokens),
+    # config 3 (batch of 8 x 512 tokens), config 5 (1024 tokens = 1023 residues + 1 dummy atom)
+    "invariants_n300": lambda: case_invariants(syn.PAPER, sizes=((30, 270),), seed=8),
+    "invariants_n512_b8": lambda: case_invariants(syn.PAPER, sizes=((32, 480),) * 8, seed=9),
+    "invariants_n1024": lambda: case_invariants(syn.PAPER, sizes=((1, 1023),), seed=10),
     "sample_graph_T50": lambda: case_sample_T50(),
     "loss_paper_n72": lambda: case_loss(dataclasses.replace(syn.PAPER, mask_prob=0.15, num_steps=2000),
                                         ((12, 60), (9, 50)), seed=11),

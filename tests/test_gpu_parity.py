@@ -29,7 +29,7 @@ CASE_NAMES = [
     "trimul_readme", "trimul_n140", "trimul_n300", "trimul_n256", "trimul_n128", "triattn_starting", "triattn_ending", "triattn_n200", "triattn_n140",
     "triattn_n300", "triattn_n512", "triattn_readme", "outer_linear", "outer_linear_readme", "outer_linear_n300",
     "single_attention", "single_transition", "spattention", "opm", "embeddings", "embeddings_readme", "embeddings_n128", "embeddings_n256", "heads",
-    "pair_bias", "sample_eager", "sample_graph", "invariants", "sample_graph_T50", "loss_paper_n72",
+    "pair_bias", "sample_eager", "sample_graph", "invariants", "invariants_n300", "invariants_n512_b8", "invariants_n1024", "sample_graph_T50", "loss_paper_n72",
 ]
 
 
