@@ -254,9 +254,23 @@ def gen_loss_case(tag, cfg, sizes, seed, n_total=None, two_chains=False):
         loss.backward()
     finally:
         torch.randn_like = orig
+    # parameter gradients of the reference's backward (through per-block checkpointing, modules.py:399): per parameter the
+    # L2 norm and the projection on a seeded random direction (2 numbers instead of the full tensor)
+    gp = torch.Generator().manual_seed(seed + 777)
+    names, norms, projs = [], [], []
+    for n, prm in model.named_parameters():
+        if prm.grad is None:
+            continue
+        d = torch.randn(prm.shape, generator=gp)
+        names.append(n)
+        norms.append(float(prm.grad.norm()))
+        projs.append(float((prm.grad * d).sum()))
     rec = {
         "weights_checksum": syn.checksum(sd),
         "batch_checksum": syn.checksum(batch),
+        "grad_names": np.array(names),
+        "grad_norms": np.array(norms, dtype=np.float64),
+        "grad_projs": np.array(projs, dtype=np.float64),
         "loss": loss.detach().numpy(),
         "diff_loss": diff["diff_loss"].numpy(),
         "t": cap["t"].numpy(),

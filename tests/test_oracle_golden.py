@@ -184,3 +184,30 @@ def test_oracle_invariants():
     assert rel_l2(s1, s0) < 1e-4
     mean = (mask.unsqueeze(-1) * n0).sum(1) / mask.sum(1, keepdim=True)
     assert float(mean.abs().max()) < 1e-6
+
+
+@pytest.mark.parametrize("tag", list(LOSS_CASES))
+def test_backward_matches_reference(tag):
+    """Ground truth for the backward pass (built next): autograd through the oracle reproduces the
+    parameter gradients of the reference's training_step (through its per-block checkpointing) -- per parameter the L2
+    norm and the projection on a seeded random direction."""
+    cfg, sizes, seed, kw = LOSS_CASES[tag]
+    gold = load_golden(f"loss_{tag}.npz")
+    sd = {k: (v.clone().requires_grad_() if v.is_floating_point() else v) for k, v in syn.make_state_dict(cfg, seed).items()}
+    batch = syn.make_batch(cfg, sizes, seed=seed, with_positions=True, **kw)
+    g = torch.Generator().manual_seed(seed + 4242)
+    torch.manual_seed(seed)
+    loss, _, _ = ref.training_loss(sd, cfg, batch, randn_like=lambda x: torch.randn(x.shape, generator=g, dtype=x.dtype))
+    loss.backward()
+    gp = torch.Generator().manual_seed(seed + 777)
+    names = [str(n) for n in gold["grad_names"]]
+    assert len(names) >= 100
+    worst = 0.0
+    for n, want_norm, want_proj in zip(names, gold["grad_norms"], gold["grad_projs"]):
+        grad = sd[n].grad
+        assert grad is not None, n
+        d = torch.randn(grad.shape, generator=gp)
+        scale = max(float(want_norm), 1e-12)
+        worst = max(worst, abs(float(grad.norm()) - float(want_norm)) / scale,
+                    abs(float((grad * d).sum()) - float(want_proj)) / (scale * float(d.norm())))
+    assert worst < 1e-3, worst
