@@ -33,7 +33,7 @@ constexpr float kG4LazyBound = 14.0f;  // log2: P <= 2^14 < fp16 max
 
 // exp2 of one 16-column chunk of scores (already in registers): running max tracking, P = exp2(s - m) (MUFU on 3/4 of
 // the pairs, FMA-pipe polynomial on 1/4), packed row sum, fp16 pack, two 16-byte stores into the P row.
-template <bool kPoly>
+template <int kPolyMask>  // bit j set: pair j of the chunk (0..7) takes the FMA-pipe polynomial instead of MUFU
 __device__ __forceinline__ void g4_chunk(const uint32_t (&s)[16], uint64_t nm2, uint64_t (&racc)[2], float (&rm)[2],
                                          uint32_t sP_row, int t, int c, uint64_t* p_free = nullptr, uint32_t p_parity = 0) {
   uint32_t ph[8];
@@ -42,7 +42,7 @@ __device__ __forceinline__ void g4_chunk(const uint32_t (&s)[16], uint64_t nm2, 
     const float a = __uint_as_float(s[2 * j]), b = __uint_as_float(s[2 * j + 1]);
     rm[j & 1] = fmax3(rm[j & 1], a, b);
     uint64_t y = fadd2(pack_f2(a, b), nm2);
-    if (kPoly && (j & 3) == 3) {
+    if ((kPolyMask >> j) & 1) {
       y = exp2_poly2(y);
     } else {
       float ya, yb;
@@ -100,7 +100,7 @@ struct G4OutProj {
   int transposed;      // 0: row (b, seq, tok) = pair[b, seq, tok]; 1: pair[b, tok, seq]
 };
 
-template <bool kFused>
+template <bool kFused, int kPM = 0x88>
 __global__ void __launch_bounds__(kG4Threads, 1)
 triattn_flash_g4_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
                         const __grid_constant__ CUtensorMap map_vt, const float* __restrict__ mask,
@@ -230,13 +230,13 @@ triattn_flash_g4_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_
               tmem_ld16(tS, sa);
               tmem_ld_wait16(sa);
               tmem_ld16(tS + 16, sb);
-              g4_chunk<true>(sa, nm2, racc, rm, sP_row, t, 0, G >= 1 ? pv : nullptr, (G - 1) & 1);
+              g4_chunk<kPM>(sa, nm2, racc, rm, sP_row, t, 0, G >= 1 ? pv : nullptr, (G - 1) & 1);
               tmem_ld_wait16(sb);
               tmem_ld16(tS + 32, sa);
-              g4_chunk<true>(sb, nm2, racc, rm, sP_row, t, 1);
+              g4_chunk<kPM>(sb, nm2, racc, rm, sP_row, t, 1);
               tmem_ld_wait16(sa);
               tmem_ld16(tS + 48, sb);
-              g4_chunk<true>(sa, nm2, racc, rm, sP_row, t, 2);
+              g4_chunk<kPM>(sa, nm2, racc, rm, sP_row, t, 2);
               tmem_ld_wait16(sb);
               // the last chunk is in registers: decide NOW whether a score would push P past 2^14 (then the item is
               // redone on the exact path; warp-uniform, the TMEM rescale there is warp-collective) -- otherwise S is
@@ -250,7 +250,7 @@ triattn_flash_g4_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_
               if (!exact) {
                 tc_fence_before();
                 mbar_arrive(sc);
-                g4_chunk<true>(sb, nm2, racc, rm, sP_row, t, 3);
+                g4_chunk<kPM>(sb, nm2, racc, rm, sP_row, t, 3);
                 float r0, r1;
                 unpack_f2(fadd2(racc[0], racc[1]), r0, r1);
                 lrow[h] += r0 + r1;
@@ -295,7 +295,7 @@ triattn_flash_g4_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_
                 tmem_ld16(tS + c * 16, s);
                 tmem_ld_wait16(s);
                 if (!all_valid) g4_mask_chunk(s, keyp, c);
-                g4_chunk<false>(s, nm2, racc, rm, sP_row, t, c);
+                g4_chunk<0>(s, nm2, racc, rm, sP_row, t, c);
               }
               float r0, r1;
               unpack_f2(fadd2(racc[0], racc[1]), r0, r1);
@@ -565,8 +565,12 @@ static int g4_launch(const PairDims& d, const float* mask, const __half* q, cons
     PRD_CUDA_OK(cudaFuncSetAttribute(triattn_flash_g4_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     triattn_flash_g4_kernel<true><<<grid, kG4Threads, smem, s>>>(mq, mk, mv, mask, g, og, N, (int)nseq, *op);
   } else {
-    PRD_CUDA_OK(cudaFuncSetAttribute(triattn_flash_g4_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    triattn_flash_g4_kernel<false><<<grid, kG4Threads, smem, s>>>(mq, mk, mv, mask, g, og, N, (int)nseq, G4OutProj{});
+    // share of the exponentials on the FMA-pipe polynomial: 1/4 (default), PRD_FLASH_POLY=1 -> 3/8, =2 -> 1/2 (A/B timing)
+    static const int poly = getenv("PRD_FLASH_POLY") ? atoi(getenv("PRD_FLASH_POLY")) : 0;
+    auto kern = poly == 1 ? triattn_flash_g4_kernel<false, 0xA8> : poly == 2 ? triattn_flash_g4_kernel<false, 0xAA>
+                                                                             : triattn_flash_g4_kernel<false, 0x88>;
+    PRD_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    kern<<<grid, kG4Threads, smem, s>>>(mq, mk, mv, mask, g, og, N, (int)nseq, G4OutProj{});
   }
   PRD_LAUNCHED();
   return 0;
