@@ -16,6 +16,9 @@ roofline the dominant kernel (triangle-attention core), timed alone inside this 
 cpu_baseline / --impl reference
          the CPU oracle (a port of the reference's PyTorch forward, oracle/denoiser_ref.py) on the
          host cores, on a bounded sample: one complex (B=1) of the same N=512 workload.
+gpu_eager_baseline
+         the same port run as eager fp32 PyTorch (stock ATen / cuBLAS kernels) on the same GPU at the full
+         batch of 8 (SURVEY §8d's second baseline; N=1 only, --no-gpu-eager skips it).
 """
 from __future__ import annotations
 
