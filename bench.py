@@ -271,6 +271,7 @@ def run_ours(args):
         side.wait_stream(torch.cuda.current_stream(dev))
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.stream(side):
+            graph_ws = ops.reserve_workspace(cfg, B, N, dev)  # the capture stream's scratch: kept alive with the graph
             with torch.cuda.graph(graph, stream=side):
                 one_step()
         launches_per_step = int(lib.prd_launch_count() - c0)

@@ -24,6 +24,9 @@ Tensor = torch.Tensor
 SD = Dict[str, Tensor]
 LN_EPS = 1e-5  # nn.LayerNorm default, used everywhere
 MASK_FILL = -(2.0 ** 15)  # ProteinReDiff/modules.py:177,220
+# Memory knob for the large parity cases (N = 1024: the eager logits alone are 17 GB): when set, the row-independent
+# ops (triangle attention, OuterLinear) are evaluated ROW_CHUNK pair rows at a time.  Same arithmetic per row.
+ROW_CHUNK: Optional[int] = None
 
 
 def _ln(x: Tensor, w: Optional[Tensor] = None, b: Optional[Tensor] = None) -> Tensor:
@@ -244,9 +247,15 @@ def transition(sd: SD, prefix: str, x: Tensor) -> Tensor:
 def outer_linear(sd: SD, prefix: str, single: Tensor) -> Tensor:
     """modules.OuterLinear.forward (modules.py:283-287)."""
     x = _ln(single)
-    xi, xj = x.unsqueeze(-2), x.unsqueeze(-3)
-    return F.linear(torch.cat([xi * xj, (xi - xj).expand(*xi.shape[:-3], xi.shape[-3], xj.shape[-2], -1)], dim=-1),
-                    sd[prefix + "linear.weight"], sd[prefix + "linear.bias"])
+    xj = x.unsqueeze(-3)
+    n = x.shape[-2]
+    step = ROW_CHUNK or n
+    outs = []
+    for r0 in range(0, n, step):
+        xi = x[..., r0:r0 + step, :].unsqueeze(-2)
+        outs.append(F.linear(torch.cat([xi * xj, (xi - xj).expand(*xi.shape[:-3], xi.shape[-3], xj.shape[-2], -1)], dim=-1),
+                             sd[prefix + "linear.weight"], sd[prefix + "linear.bias"]))
+    return outs[0] if len(outs) == 1 else torch.cat(outs, dim=-3)
 
 
 def triangle_multiplication(sd: SD, prefix: str, pair: Tensor, mask_2d: Tensor, mode: str) -> Tensor:
@@ -272,7 +281,11 @@ def triangle_attention(sd: SD, prefix: str, pair: Tensor, mask_2d: Tensor, num_h
         pair, mask_2d = pair.transpose(1, 2), mask_2d.transpose(1, 2)
     elif mode != "starting":
         raise ValueError(f"Invalid mode: {mode}")
-    out = gated_attention(sd, prefix + "attn.", pair, mask_2d, num_heads)
+    n = pair.shape[1]
+    step = ROW_CHUNK or n
+    outs = [gated_attention(sd, prefix + "attn.", pair[:, r0:r0 + step], mask_2d[:, r0:r0 + step], num_heads)
+            for r0 in range(0, n, step)]
+    out = outs[0] if len(outs) == 1 else torch.cat(outs, dim=1)
     return out.transpose(1, 2) if mode == "ending" else out
 
 

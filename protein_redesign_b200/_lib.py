@@ -50,6 +50,24 @@ _lib: Optional[ctypes.CDLL] = None
 _lock = threading.Lock()
 
 
+def source_hash() -> Optional[str]:
+    """Hash of the CUDA sources beside this file, computed exactly like csrc/build.sh does (None if they are absent)."""
+    import glob
+    import hashlib
+
+    csrc = os.path.join(_HERE, "csrc")
+    inc = os.path.join(_HERE, "..", "include", "prd_denoiser.h")
+    files = sorted(glob.glob(os.path.join(csrc, "*.cu"))) + sorted(glob.glob(os.path.join(csrc, "*.cuh"))) + \
+        sorted(glob.glob(os.path.join(csrc, "*.h"))) + [inc]
+    if not os.path.exists(inc) or not glob.glob(os.path.join(csrc, "*.cu")):
+        return None
+    h = hashlib.sha256()
+    for f in files:
+        with open(f, "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()[:16]
+
+
 def load() -> ctypes.CDLL:
     """Load the shared library (once) and declare every prototype of include/prd_denoiser.h."""
     global _lib
@@ -61,6 +79,12 @@ def load() -> ctypes.CDLL:
                 f"{LIB_PATH} not found: the CUDA extension is not built and there is no CPU fallback. "
                 "Run protein_redesign_b200/csrc/build.sh (needs nvcc with sm_100a support).")
         lib = ctypes.CDLL(LIB_PATH)
+        lib.prd_source_hash.restype = ctypes.c_char_p
+        built, have = lib.prd_source_hash().decode(), source_hash()
+        if have is not None and built != have and os.environ.get("PRD_ALLOW_STALE_LIB") != "1":
+            raise RuntimeError(
+                f"{LIB_PATH} was built from other sources (library {built}, tree {have}): rebuild with "
+                "protein_redesign_b200/csrc/build.sh -- a stale kernel must never be tested or benchmarked")
         lib.prd_version.restype = ctypes.c_int
         lib.prd_last_error.restype = ctypes.c_char_p
         lib.prd_device_check.restype = ctypes.c_int
@@ -101,21 +125,35 @@ def check_tensor(t: torch.Tensor, dtype: torch.dtype, name: str) -> torch.Tensor
     return t
 
 
-# One grow-only workspace per device.  It must be sized before a CUDA-graph capture starts
-# (Workspace.reserve); growing it during capture would allocate.
+# One grow-only workspace per (device, stream): ops enqueued on different streams of one device never share scratch
+# memory.  It must be sized before a CUDA-graph capture starts (Workspace.reserve on the capture stream); growing it
+# during capture would allocate.  Growing replaces the buffer object: whoever replays a captured graph keeps the
+# tensor returned by reserve() / current() alive next to the graph (ProteinReDiffModel.sample, bench.py do).
 class Workspace:
-    _buffers: Dict[int, torch.Tensor] = {}
+    _buffers: Dict[tuple, torch.Tensor] = {}
+    _guard = threading.Lock()
+
+    @staticmethod
+    def _key(device: torch.device):
+        idx = device.index if device.index is not None else torch.cuda.current_device()
+        return idx, int(torch.cuda.current_stream(device).cuda_stream)
 
     @classmethod
     def reserve(cls, device: torch.device, nbytes: int) -> torch.Tensor:
-        idx = device.index if device.index is not None else torch.cuda.current_device()
-        buf = cls._buffers.get(idx)
-        if buf is None or buf.numel() < nbytes:
-            if torch.cuda.is_current_stream_capturing():
-                raise RuntimeError("prd workspace must be reserved before CUDA-graph capture")
-            buf = torch.empty(int(nbytes) + 256, dtype=torch.uint8, device=device)
-            cls._buffers[idx] = buf
-        return buf
+        key = cls._key(device)
+        with cls._guard:
+            buf = cls._buffers.get(key)
+            if buf is None or buf.numel() < nbytes:
+                if torch.cuda.is_current_stream_capturing():
+                    raise RuntimeError("prd workspace must be reserved (on the capture stream) before CUDA-graph capture")
+                buf = torch.empty(int(nbytes) + 256, dtype=torch.uint8, device=device)
+                cls._buffers[key] = buf
+            return buf
+
+    @classmethod
+    def current(cls, device: torch.device) -> Optional[torch.Tensor]:
+        """The buffer the ops enqueued on the current stream of ``device`` use right now (None before the first call)."""
+        return cls._buffers.get(cls._key(device))
 
 
 def workspace_bytes(op: str, dims: PrdDims) -> int:

@@ -2,7 +2,8 @@
 
 The reference overwrites parameters in place between calls (EMA weight swap around
 ``predict_step``, model.py:249-252), so packed copies are keyed on every source tensor's
-``data_ptr`` and in-place ``_version`` and rebuilt when either changes.
+``data_ptr``, its in-place ``_version`` and a process-wide weights epoch (bumped around every EMA
+swap, because writes through ``param.data`` leave ``_version`` untouched) and rebuilt when any changes.
 """
 from __future__ import annotations
 
@@ -27,13 +28,31 @@ def tensor_version(t: torch.Tensor) -> int:
         return -1
 
 
+# Process-wide "weights epoch".  ``Parameter._version`` does not see writes that go through ``param.data`` (its own
+# version counter) -- which is exactly how torch_ema's ``average_parameters()`` swaps the EMA weights in and out
+# (``copy_to`` / ``restore`` use ``param.data.copy_``).  Every code path of this package that lets such a writer run
+# (the EMA contexts of predict_step / validation_step) bumps the epoch on entry and exit; callers that overwrite
+# ``param.data`` themselves call :func:`invalidate_packed_weights`.  The epoch is part of every PackCache key.
+_weights_epoch = 0
+
+
+def weights_epoch() -> int:
+    return _weights_epoch
+
+
+def invalidate_packed_weights() -> None:
+    """Force every packed fp16 weight copy (and everything derived from them) to be rebuilt on next use."""
+    global _weights_epoch
+    _weights_epoch += 1
+
+
 class PackCache:
     def __init__(self):
         self._key = None
         self._value = None
 
     def get(self, sources: Sequence[torch.Tensor], build: Callable[[], object]):
-        key = tuple((t.data_ptr(), tensor_version(t), t.device) for t in sources)
+        key = tuple((t.data_ptr(), tensor_version(t), t.device) for t in sources) + (_weights_epoch,)
         if key != self._key:
             for t in sources:
                 if not t.is_cuda:

@@ -553,7 +553,8 @@ size_t prd_sampler_update_workspace_bytes(const PrdDims*) { return 256; }
 int prd_sampler_update_fwd(const PrdDims* d, const void* const* in, void* const* out, const void* const*, void*,
                            size_t, void* stream) {
   if (prd_device_check()) return 1;
-  return sampler_update(d->B, d->N, in_ptr<float>(in, 0), in_ptr<float>(in, 1), in_ptr<float>(in, 2),
+  PRD_REQUIRE(d->num_steps > 0, "sampler_update: num_steps must be positive");
+  return sampler_update(d->B, d->N, d->num_steps, in_ptr<float>(in, 0), in_ptr<float>(in, 1), in_ptr<float>(in, 2),
                         in_ptr<float>(in, 3), static_cast<SamplerState*>(out[2]), out_ptr<float>(out, 0),
                         out_ptr<float>(out, 1), S(stream));
 }

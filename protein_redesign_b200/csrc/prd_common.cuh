@@ -16,6 +16,8 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <atomic>
+
 namespace prd {
 
 // ---------------------------------------------------------------------------------------
@@ -37,7 +39,7 @@ int check_cuda(cudaError_t e, const char* what);
   } while (0)
 
 // count of kernels launched by this library in this process (prd_launch_count())
-extern long long g_launches;
+extern std::atomic<long long> g_launches;
 #define PRD_LAUNCHED()                       \
   do {                                       \
     ++::prd::g_launches;                     \

@@ -18,7 +18,13 @@ single_embed_kernel(int CS, const int64_t* __restrict__ atom_feats, const float*
   __shared__ long long sIdx[9];
   const long long tok = blockIdx.x;
   const int t = threadIdx.x;
-  if (t < 9) sIdx[t] = atom_feats[tok * 9 + t];
+  // nn.Embedding raises on an out-of-range index; a kernel cannot, so indices are clamped into the table
+  // (features.py:31-60 vocabulary sizes) instead of reading out of bounds
+  constexpr int kVocab[9] = {119, 4, 12, 12, 10, 6, 6, 2, 2};
+  if (t < 9) {
+    const long long v = atom_feats[tok * 9 + t];
+    sIdx[t] = v < 0 ? 0 : (v >= kVocab[t] ? kVocab[t] - 1 : v);
+  }
   if (t == 0) {
     const float* s = seq_t + tok * 21;
     float mean = 0.f;
@@ -60,7 +66,8 @@ __global__ void time_embed_kernel(int CZ, int TD, const int64_t* __restrict__ t,
                                   float* __restrict__ beta) {
   extern __shared__ float sF[];  // [TD]
   const int b = blockIdx.x;
-  const long long tb = st ? (long long)st->t_cur : t[b];
+  long long tb = st ? (long long)st->t_cur : t[b];
+  tb = tb < 0 ? 0 : (tb >= num_steps ? num_steps - 1 : tb);  // a stale / over-replayed state must not index out of range
   const float scaled = static_cast<float>(tb) / static_cast<float>(num_steps);
   const int half = TD / 2;
   for (int k = threadIdx.x; k < half; k += blockDim.x) {
@@ -93,18 +100,20 @@ int time_embed(int B, int CZ, int TD, const int64_t* t, const SamplerState* st, 
 // and the step counter live in *st (device memory) so that one captured CUDA graph serves every
 // step; noise is the pre-generated, mean-removed tensor [steps][B*N][3] indexed by st->step.
 // A second one-thread kernel advances the state after every block has read it.
-__global__ void sampler_update_kernel(long long n_tok, const float* __restrict__ eps, const float* __restrict__ seq_pred,
+__global__ void sampler_update_kernel(long long n_tok, int T, const float* __restrict__ eps, const float* __restrict__ seq_pred,
                                       const float* __restrict__ noise, const float* __restrict__ coef,
                                       const SamplerState* __restrict__ st, float* __restrict__ z,
                                       float* __restrict__ seq_t) {
   const long long tok = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (tok >= n_tok) return;
-  const int tc = st->t_cur;
+  // clamped: replaying the captured step more than T times must not read past coef[T][3] / noise[T-1][..]
+  const int tc = min(max(st->t_cur, 0), T - 1);
+  const int sidx = min(max(st->step, 0), max(T - 2, 0));
   const float c1 = coef[tc * 3 + 0], c2 = coef[tc * 3 + 1], sd = coef[tc * 3 + 2];
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
     const float mean = c1 * (z[tok * 3 + k] - c2 * eps[tok * 3 + k]);
-    z[tok * 3 + k] = (tc == 0) ? mean : mean + sd * noise[((long long)st->step * n_tok + tok) * 3 + k];
+    z[tok * 3 + k] = (tc == 0) ? mean : mean + sd * noise[((long long)sidx * n_tok + tok) * 3 + k];
   }
   const float* sp = seq_pred + tok * 21;
   float m = -INFINITY;
@@ -121,19 +130,26 @@ __global__ void sampler_update_kernel(long long n_tok, const float* __restrict__
   for (int k = 0; k < 21; ++k) seq_t[tok * 21 + k] = e[k] * inv * 2.0f - 1.0f;
 }
 
-__global__ void sampler_advance_kernel(SamplerState* st) {
+// After the last step (t_cur == 0) the state wraps to the start of a new trajectory, so a replay loop of any length
+// (bench.py) stays inside the schedule and the noise tensor.
+__global__ void sampler_advance_kernel(SamplerState* st, int T) {
   if (threadIdx.x == 0 && blockIdx.x == 0) {
-    st->t_cur -= 1;
-    st->step += 1;
+    if (st->t_cur <= 0) {
+      st->t_cur = T - 1;
+      st->step = 0;
+    } else {
+      st->t_cur -= 1;
+      st->step += 1;
+    }
   }
 }
 
-int sampler_update(int B, int N, const float* eps, const float* seq_pred, const float* noise, const float* coef,
+int sampler_update(int B, int N, int T, const float* eps, const float* seq_pred, const float* noise, const float* coef,
                    SamplerState* st, float* z, float* seq_t, cudaStream_t s) {
   const long long n_tok = (long long)B * N;
-  sampler_update_kernel<<<(unsigned)((n_tok + 127) / 128), 128, 0, s>>>(n_tok, eps, seq_pred, noise, coef, st, z, seq_t);
+  sampler_update_kernel<<<(unsigned)((n_tok + 127) / 128), 128, 0, s>>>(n_tok, T, eps, seq_pred, noise, coef, st, z, seq_t);
   PRD_LAUNCHED();
-  sampler_advance_kernel<<<1, 32, 0, s>>>(st);
+  sampler_advance_kernel<<<1, 32, 0, s>>>(st, T);
   PRD_LAUNCHED();
   return 0;
 }

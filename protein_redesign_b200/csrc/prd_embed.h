@@ -20,7 +20,7 @@ int single_embed(int B, int N, int CS, const int64_t* atom_feats, const float* a
                  cudaStream_t s);
 int time_embed(int B, int CZ, int TD, const int64_t* t, const SamplerState* st, int num_steps, const float* freq,
                const float* w_beta, float* beta, cudaStream_t s);
-int sampler_update(int B, int N, const float* eps, const float* seq_pred, const float* noise, const float* coef,
+int sampler_update(int B, int N, int T, const float* eps, const float* seq_pred, const float* noise, const float* coef,
                    SamplerState* st, float* z, float* seq_t, cudaStream_t s);
 
 }  // namespace prd

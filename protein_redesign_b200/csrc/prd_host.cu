@@ -2,6 +2,8 @@
 // and TMA tensor-map construction through the driver entry point (resolved at run time with
 // cudaGetDriverEntryPoint, so the library has no link-time dependency on libcuda).
 #include <stdarg.h>
+#include <atomic>
+#include <mutex>
 #include <stdio.h>
 #include <string.h>
 
@@ -11,7 +13,7 @@
 namespace prd {
 
 static thread_local char g_error[512] = "";
-long long g_launches = 0;
+std::atomic<long long> g_launches{0};
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -32,16 +34,15 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 
 static EncodeTiledFn get_encode_fn() {
   static EncodeTiledFn fn = nullptr;
-  static bool tried = false;
-  if (!tried) {
-    tried = true;
+  static std::once_flag once;
+  std::call_once(once, [] {
     void* p = nullptr;
     cudaDriverEntryPointQueryResult q;
     if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
         q == cudaDriverEntryPointSuccess) {
       fn = reinterpret_cast<EncodeTiledFn>(p);
     }
-  }
+  });
   return fn;
 }
 
@@ -83,10 +84,10 @@ int prd_version(void) { return PRD_VERSION; }
 
 const char* prd_last_error(void) { return prd::g_error; }
 
-long long prd_launch_count(void) { return prd::g_launches; }
+long long prd_launch_count(void) { return prd::g_launches.load(); }
 
 int prd_device_check(void) {
-  static int cached[64] = {0};  // per device: 0 unknown, 1 ok, 2 wrong architecture
+  static std::atomic<int> cached[64];  // per device: 0 unknown, 1 ok (zero-initialised: static storage)
   int dev = 0;
   if (prd::check_cuda(cudaGetDevice(&dev), "cudaGetDevice")) return 1;
   if (dev >= 0 && dev < 64 && cached[dev] == 1) return 0;

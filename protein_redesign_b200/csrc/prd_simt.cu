@@ -444,12 +444,17 @@ __global__ void embed_pair_static_kernel(int N, int CZ4, long long total, const 
     float4 bond = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int f = 0; f < 3; ++f) {
-      const float4 v = row4(bt.t[f], bond_feats[e * 3 + f]);
+      // nn.Embedding raises on an out-of-range index; the kernel clamps into the table (features.py:52-60 vocabularies)
+      constexpr int kBondVocab[3] = {5, 6, 2};
+      long long bf = bond_feats[e * 3 + f];
+      bf = bf < 0 ? 0 : (bf >= kBondVocab[f] ? kBondVocab[f] - 1 : bf);
+      const float4 v = row4(bt.t[f], bf);
       bond.x += scale * v.x; bond.y += scale * v.y; bond.z += scale * v.z; bond.w += scale * v.w;
     }
     const float bm = bond_mask[e];
     long long bd = bond_distance[e];
     if (bd > max_bd) bd = max_bd;
+    if (bd < 0) bd = 0;
     const float4 dv = row4(bdist_table, bd);
     acc.x = am2 * (bm * bond.x + dv.x); acc.y = am2 * (bm * bond.y + dv.y);
     acc.z = am2 * (bm * bond.z + dv.z); acc.w = am2 * (bm * bond.w + dv.w);

@@ -24,7 +24,8 @@ import torch.nn.functional as F
 from torch import nn
 
 from . import ops
-from ._packing import PackCache, f32, half, split_k, split_rows, tensor_version
+from ._packing import (PackCache, f32, half, invalidate_packed_weights, split_k, split_rows, tensor_version,
+                       weights_epoch)
 from .modules import AtomEmbedding, BondEmbedding, Denoiser, Linear, RadialBasisProjection, SinusoidalProjection
 from .synthetic import NUM_RESIDUE_CLASSES, DenoiserConfig
 
@@ -246,18 +247,37 @@ class ProteinReDiffModel(_Base):
         return batch
 
     # ---- step-invariant embeddings, cached per batch ---------------------------------------------
+    _STATIC_KEYS = ("residue_esm", "bond_feats", "bond_mask", "bond_distance", "residue_index", "residue_chain_index",
+                    "atom_mask", "residue_mask")
+
     def _static_embeddings(self, batch):
-        keys = ("residue_esm", "bond_feats", "bond_mask", "bond_distance", "residue_index", "residue_chain_index",
-                "atom_mask", "residue_mask")
-        key = tuple((batch[k].data_ptr(), tensor_version(batch[k])) for k in keys) + (id(self._weights()),)
-        if key != self._static_key:
-            w = self._weights()
-            b = {k: batch[k].contiguous() for k in keys}
+        """ESM projection and the bond / relpos pair terms do not depend on the diffusion step.  The cache is keyed on the
+        IDENTITY of the batch tensors, which it keeps alive: a raw data_ptr of a tensor nobody holds can be handed out again
+        by the caching allocator for the next same-shape batch (and inference tensors carry no version counter), which
+        would silently reuse another complex's embeddings."""
+        w = self._weights()
+        held = self._static_key
+        fresh = held is None or held[2] is not w or held[3] != weights_epoch() or any(
+            batch[k] is not t or tensor_version(batch[k]) != v for k, t, v in zip(self._STATIC_KEYS, held[0], held[1]))
+        if fresh:
+            b = {k: batch[k].contiguous() for k in self._STATIC_KEYS}
             esm_emb = ops.esm_embed(self.cfg, b["residue_esm"], w["esm"][0])
             pair_static = ops.pair_embed_static(self.cfg, b, w["bond_tabs"], w["bdist"], w["relpos"])
             self._static = (esm_emb, pair_static)
-            self._static_key = key
+            self._static_key = (tuple(batch[k] for k in self._STATIC_KEYS),
+                                tuple(tensor_version(batch[k]) for k in self._STATIC_KEYS), w, weights_epoch())
         return self._static
+
+    @contextlib.contextmanager
+    def _ema_weights(self):
+        """``with self.ema.average_parameters()`` (reference model.py:227,250) plus invalidation of every packed weight
+        copy: torch_ema swaps through ``param.data.copy_``, which no version counter sees."""
+        try:
+            with self.ema.average_parameters():
+                invalidate_packed_weights()
+                yield
+        finally:
+            invalidate_packed_weights()
 
     def _denoise(self, batch, z, seq_t, mask, t, bufs=None, sampler_state=None, probe=None):
         """One network evaluation (reference model.py:318-375).  `bufs` lets the sampler reuse storage."""
@@ -291,9 +311,10 @@ class ProteinReDiffModel(_Base):
     def sample_step(self, batch, z, seq_t, mask, t):
         return self._denoise(batch, z, seq_t, mask.contiguous(), t)
 
-    def predict_step(self, batch, batch_idx):
-        with self.ema.average_parameters():
-            return self.sample(batch)
+    def predict_step(self, batch, batch_idx, noise: Optional[Dict[str, torch.Tensor]] = None):
+        """reference model.py:249-252: sample under the EMA weights (``noise``: optional injected draws, see sample)."""
+        with self._ema_weights():
+            return self.sample(batch, noise=noise)
 
     # ---- training objective (reference model.py:471-549; SURVEY §8 a18) ---------------------------
     def _sched_table(self):
@@ -362,7 +383,7 @@ class ProteinReDiffModel(_Base):
     def validation_step(self, batch, batch_idx, noise: Optional[Dict[str, torch.Tensor]] = None, detail: Optional[dict] = None):
         """reference model.py:226-247: the same objective under the EMA weights, logged as ``val_loss`` (the reference
         returns None; the loss is returned here as well)."""
-        with self.ema.average_parameters():
+        with self._ema_weights():
             loss, bs = self._objective(batch, batch_idx, noise, detail, want_grads=False)
         if hasattr(self, "log"):
             self.log("val_loss", loss, on_epoch=True, sync_dist=True, batch_size=bs)
@@ -405,14 +426,16 @@ class ProteinReDiffModel(_Base):
     # ---- sampler (reference model.py:377-422) ------------------------------------------------
     @torch.inference_mode()
     def sample(self, batch, noise: Optional[Dict[str, torch.Tensor]] = None, use_cuda_graph: bool = True,
-               trace: Optional[list] = None):
+               trace: Optional[list] = None, prepared: bool = False):
         """DDPM ancestral sampling.  `noise` may inject pre-generated draws (keys ``z_T`` [B,N,3],
         ``seq_T`` [B,N,21], ``steps`` [T-1,B,N,3], raw N(0,1), in the reference's draw order); otherwise
-        they come from torch's CUDA generator."""
+        they come from torch's CUDA generator.  ``prepared=True``: ``batch`` already went through prepare_batch (the
+        sample-parallel driver masks the FULL batch jointly before sharding it, sampling.py) and must not be masked again."""
         if not self.setup_schedule:
             self.run_setup_schedule()
             self.setup_schedule = True
-        batch = self.prepare_batch(batch)
+        if not prepared:
+            batch = self.prepare_batch(batch)
         cfg = self.cfg
         x, mask = batch["x"], batch["residue_and_atom_mask"].contiguous()
         residue_mask, seq = batch["residue_mask"].contiguous(), batch["residue_one_hot"]
@@ -456,6 +479,7 @@ class ProteinReDiffModel(_Base):
             side.wait_stream(torch.cuda.current_stream(dev))
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.stream(side):
+                graph_ws = ops.reserve_workspace(cfg, B, N, dev)  # the capture stream's own scratch, held with the graph
                 with torch.cuda.graph(graph, stream=side):
                     one_step()
             torch.cuda.current_stream(dev).wait_stream(side)
@@ -468,4 +492,5 @@ class ProteinReDiffModel(_Base):
             if trace is not None:
                 trace.append((z.clone(), bufs["seq_pred"].clone(), bufs["noise_pred"].clone()))
         pos = 10.0 * z
+        del graph  # before its workspace reference (graph_ws) goes out of scope
         return pos, residue_mask.unsqueeze(-1) * bufs["seq_pred"]

@@ -25,11 +25,12 @@ def make_dims(cfg, B: int, N: int, mode: int = 0, residual: int = 1) -> PrdDims:
     return d
 
 
-def reserve_workspace(cfg, B: int, N: int, device) -> None:
-    """Size the per-device workspace for every op at (B, N) -- call before CUDA-graph capture."""
+def reserve_workspace(cfg, B: int, N: int, device):
+    """Size the workspace of the CURRENT stream of ``device`` for every op at (B, N) -- call on the capture stream before
+    a CUDA-graph capture.  Returns the buffer: keep it alive for as long as a graph captured against it is replayed."""
     d = make_dims(cfg, B, N)
     need = max(_lib.workspace_bytes(op, d) for op in _lib.OPS)
-    _lib.Workspace.reserve(torch.device(device), need)
+    return _lib.Workspace.reserve(torch.device(device), need)
 
 
 def _chk(ts: Sequence[Optional[torch.Tensor]], dtypes, names):

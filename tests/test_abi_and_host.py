@@ -52,7 +52,7 @@ def test_workspace_queries_run_without_gpu():
 def test_state_dict_contract(cfg):
     model = ProteinReDiffModel(cfg)
     sd = syn.make_state_dict(cfg, 0)
-    assert list(model.state_dict().keys()).sort() == list(sd.keys()).sort()
+    assert sorted(model.state_dict().keys()) == sorted(sd.keys())
     model.load_state_dict(sd, strict=True)
     assert {k: tuple(v.shape) for k, v in model.state_dict().items()} == {k: tuple(v.shape) for k, v in sd.items()}
     # Denoiser accepts a Mapping like the reference (modules.py:353)
