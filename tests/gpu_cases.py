@@ -265,16 +265,21 @@ def case_pair_bias(cfg=syn.PAPER, B=2, N=72, seed=0):
 # ------------------------------------------------------------------------------------------
 # whole step / sampler
 # ------------------------------------------------------------------------------------------
-def case_step(cfg=syn.PAPER, sizes=((12, 60), (9, 50)), seed=3, n_total=None, golden=None, probes=False):
+def case_step(cfg=syn.PAPER, sizes=((12, 60), (9, 50)), seed=3, n_total=None, golden=None, probes=False, row_chunk=None):
+    """``row_chunk``: evaluate the oracle's row-independent ops that many pair rows at a time (host memory at N = 1024)."""
     m, sd = _model(cfg, seed)
     batch = syn.make_batch(cfg, list(sizes), seed=seed, n_total=n_total)
     z, seq_t, mask, t = syn.make_step_inputs(batch, cfg.num_steps, seed)
     torch.manual_seed(seed)
     pb = ref.prepare_batch(batch, cfg.mask_prob)
     want_probes = {}
-    with torch.inference_mode():
-        want_noise, want_seq = ref.denoiser_step(sd, cfg, pb, z, seq_t, mask, t,
-                                                 probe=(lambda n, v: want_probes.__setitem__(n, v.clone())) if probes else None)
+    ref.ROW_CHUNK = row_chunk
+    try:
+        with torch.inference_mode():
+            want_noise, want_seq = ref.denoiser_step(sd, cfg, pb, z, seq_t, mask, t,
+                                                     probe=(lambda n, v: want_probes.__setitem__(n, v.clone())) if probes else None)
+    finally:
+        ref.ROW_CHUNK = None
     torch.manual_seed(seed)
     db = m.prepare_batch(_to_dev(batch))
     got_probes = {}
@@ -456,6 +461,141 @@ def case_invariants(cfg=syn.PAPER, sizes=((10, 54),), seed=7):
             "zero_mean": (float(mean.abs().max()), 1e-5)}
 
 
+def case_batch_rows(cfg=syn.PAPER, sizes=((32, 480), (20, 400), (25, 487), (10, 380), (32, 480), (8, 300), (30, 482), (16, 430)),
+                    seed=21, oracle_row=3, check_rows=(0, 3, 7)):
+    """The benchmarked shape (B = 8, N = 512), ragged: row k of the batched output must equal the B = 1 output of complex k
+    (the network never mixes batch rows), and one padded row is compared with the oracle directly -- so the B = 8
+    run inherits the B = 1 oracle checks."""
+    m, sd = _model(cfg, seed)
+    batch = syn.make_batch(cfg, list(sizes), seed=seed, n_total=512)
+    z, seq_t, mask, t = syn.make_step_inputs(batch, cfg.num_steps, seed)
+    torch.manual_seed(seed)
+    pb = ref.prepare_batch(batch, cfg.mask_prob)
+    db = _to_dev(pb)
+    with torch.inference_mode():
+        n8, s8 = m._denoise(db, z.to(DEV), seq_t.to(DEV), mask.to(DEV), t.to(DEV))
+        n8, s8 = n8.clone(), s8.clone()
+        worst_n = worst_s = 0.0
+        for k in check_rows:
+            row = {key: (v[k:k + 1].contiguous() if isinstance(v, torch.Tensor) and v.dim() >= 1 else v) for key, v in db.items()}
+            n1, s1 = m._denoise(row, z[k:k + 1].to(DEV), seq_t[k:k + 1].to(DEV), mask[k:k + 1].to(DEV), t[k:k + 1].to(DEV))
+            worst_n = max(worst_n, rel(n8[k:k + 1], n1))
+            worst_s = max(worst_s, rel(s8[k:k + 1], s1))
+        k = oracle_row
+        prow = {key: (v[k:k + 1] if isinstance(v, torch.Tensor) and v.dim() >= 1 else v) for key, v in pb.items()}
+        want_n, want_s = ref.denoiser_step(sd, cfg, prow, z[k:k + 1], seq_t[k:k + 1], mask[k:k + 1], t[k:k + 1])
+    torch.cuda.synchronize()
+    return {"row_independence_noise": (worst_n, 1e-5), "row_independence_seq": (worst_s, 1e-5),
+            "b8_row_vs_oracle_noise": (rel(n8[k:k + 1], want_n), STEP_TOL), "b8_row_vs_oracle_seq": (rel(s8[k:k + 1], want_s), STEP_TOL),
+            "pad_noise": (float((n8.cpu() * (1 - mask).unsqueeze(-1)).abs().max()), 0.0)}
+
+
+def case_denoiser_forward(cfg=syn.PAPER, B=2, N=72, seed=13, pad=5):
+    """The public entry modules.Denoiser.forward(batch, z, t, single, pair, cache) (reference modules.py:391-404): OPM
+    added to the caller's pair in place, SPAttention, the folding blocks, symmetrisation."""
+    m, sd = _model(cfg, seed)
+    single, pair, mask = _pair_inputs(cfg, B, N, seed, pad)
+    with torch.inference_mode():
+        want_single, want_pair = ref.denoiser_trunk(sd, cfg, single, pair, mask)
+        p = pair.to(DEV).contiguous()
+        got_single, got_pair, cache = m.Denoiser({"residue_and_atom_mask": mask.to(DEV)}, None, None, single.to(DEV), p, "cache")
+    torch.cuda.synchronize()
+    return {"single": (rel(got_single, want_single), STEP_TOL), "pair": (rel(got_pair, want_pair), STEP_TOL),
+            "in_place": (0.0 if got_pair.data_ptr() == p.data_ptr() and cache == "cache" else 1.0, 0.0)}
+
+
+def case_folding_block_forward(cfg=syn.PAPER, B=2, N=72, seed=14, pad=5):
+    """modules.FoldingBlock.forward(single, pair, mask) (reference modules.py:328-343) returns NEW tensors."""
+    m, sd = _model(cfg, seed)
+    single, pair, mask = _pair_inputs(cfg, B, N, seed, pad)
+    with torch.inference_mode():
+        want_single, want_pair = ref.folding_block(sd, 1, single, pair, mask, cfg.num_heads)
+        s_in, p_in = single.to(DEV), pair.to(DEV)
+        got_single, got_pair = m.Denoiser.folding_blocks[1](s_in, p_in, mask.to(DEV))
+    torch.cuda.synchronize()
+    return {"single": (rel(got_single, want_single), OP_TOL), "pair": (rel(got_pair, want_pair), OP_TOL),
+            "inputs_untouched": (float((p_in.cpu() - pair).abs().max() + (s_in.cpu() - single).abs().max()), 0.0)}
+
+
+class _ShadowEMA:
+    """torch_ema.ExponentialMovingAverage's weight swap, restated: average_parameters() copies the shadow weights in
+    through ``param.data.copy_`` (no version counter sees it) and restores the originals on exit."""
+
+    def __init__(self, params, shadow):
+        self.params, self.shadow = list(params), [s.clone() for s in shadow]
+
+    def average_parameters(self):
+        import contextlib
+
+        @contextlib.contextmanager
+        def ctx():
+            saved = [p.data.clone() for p in self.params]
+            for p, s in zip(self.params, self.shadow):
+                p.data.copy_(s)
+            try:
+                yield
+            finally:
+                for p, s in zip(self.params, saved):
+                    p.data.copy_(s)
+        return ctx()
+
+
+def case_predict_step(seed=6, T=6, sizes=((8, 32), (6, 27))):
+    """predict_step (reference model.py:249-252) = sample() under the EMA weights: checked against the oracle run with the
+    SHADOW weights, then sample() again must be back on the raw weights (packed fp16 copies invalidated both ways)."""
+    cfg = dataclasses.replace(syn.README, num_steps=T, mask_prob=0.3)
+    m, sd = _model(cfg, seed)
+    sd_ema = syn.make_state_dict(cfg, seed + 100)
+    batch = syn.make_batch(cfg, list(sizes), seed=seed)
+    B, N = batch["atom_mask"].shape
+    g = torch.Generator().manual_seed(seed + 31337)
+    draws = {"z_T": torch.randn(B, N, 3, generator=g), "seq_T": torch.randn(B, N, 21, generator=g),
+             "steps": torch.randn(T - 1, B, N, 3, generator=g)}
+
+    def oracle(weights):
+        it = iter([draws["z_T"], draws["seq_T"]] + [draws["steps"][i] for i in range(T - 1)])
+        torch.manual_seed(seed)
+        with torch.inference_mode():
+            return ref.sample(weights, cfg, batch, randn_like=lambda x: next(it).clone())
+
+    want_raw, want_ema = oracle(sd), oracle(sd_ema)
+    torch.manual_seed(seed)
+    pos_a, log_a = m.sample(_to_dev(batch), noise=draws)  # first pack happens on the RAW weights
+    names = [n for n, _ in m.named_parameters()]
+    m.ema = _ShadowEMA([p for _, p in m.named_parameters()], [sd_ema[n].to(DEV) for n in names])
+    torch.manual_seed(seed)
+    pos_b, log_b = m.predict_step(_to_dev(batch), 0, noise=draws)
+    torch.manual_seed(seed)
+    pos_c, log_c = m.sample(_to_dev(batch), noise=draws)
+    torch.cuda.synchronize()
+    return {"raw_pos": (rel(pos_a, want_raw[0]), 5e-3), "raw_logits": (rel(log_a, want_raw[1]), 5e-3),
+            "ema_pos": (rel(pos_b, want_ema[0]), 5e-3), "ema_logits": (rel(log_b, want_ema[1]), 5e-3),
+            "restored_pos": (rel(pos_c, pos_a), 0.0), "restored_logits": (rel(log_c, log_a), 0.0)}
+
+
+def case_back_to_back_batches(cfg=syn.README, sizes=((8, 32), (6, 27)), seed=15):
+    """Two DIFFERENT same-shape batches through one model, the first one freed before the second is created (so the
+    caching allocator hands the same addresses out again): each must match the oracle (the step-invariant
+    embedding cache was keyed on raw data_ptr values)."""
+    m, sd = _model(cfg, seed)
+    out = {}
+    for tag, bseed in (("first", seed), ("second", seed + 1)):
+        batch = syn.make_batch(cfg, list(sizes), seed=bseed)
+        z, seq_t, mask, t = syn.make_step_inputs(batch, cfg.num_steps, bseed)
+        torch.manual_seed(bseed)
+        pb = ref.prepare_batch(batch, cfg.mask_prob)
+        with torch.inference_mode():
+            want_n, want_s = ref.denoiser_step(sd, cfg, pb, z, seq_t, mask, t)
+            torch.manual_seed(bseed)
+            db = m.prepare_batch(_to_dev(batch))
+            n, s_ = m.sample_step(db, z.to(DEV), seq_t.to(DEV), mask.to(DEV), t.to(DEV))
+            out[tag + "_noise"] = (rel(n, want_n), STEP_TOL)
+            out[tag + "_seq"] = (rel(s_, want_s), STEP_TOL)
+        del db, n, s_
+        torch.cuda.synchronize()
+    return out
+
+
 CASES = {
     "gemm_basic": lambda: case_gemm(256, 128, 64),
     "gemm_k512": lambda: case_gemm(384, 256, 512),
@@ -513,6 +653,23 @@ CASES = {
     "invariants_n512_b8": lambda: case_invariants(syn.PAPER, sizes=((32, 480),) * 8, seed=9),
     "invariants_n1024": lambda: case_invariants(syn.PAPER, sizes=((1, 1023),), seed=10),
     "sample_graph_T50": lambda: case_sample_T50(),
+    # ---- round 2: oracle parity at BASELINE.json's sizes ----
+    "step_n512": lambda: case_step(syn.PAPER, ((32, 480),), seed=31),                                  # config 3, one complex
+    "step_n512_b2_ragged": lambda: case_step(syn.PAPER, ((32, 430), (20, 371)), seed=32, n_total=512),   # masked key tiles of the g4 core
+    "step_n300": lambda: case_step(syn.PAPER, ((30, 270),), seed=33),                                  # config 2
+    "step_n1024": lambda: case_step(syn.PAPER, ((1, 1023),), seed=34, row_chunk=64),                   # config 5
+    "batch_rows_b8_n512": lambda: case_batch_rows(),
+    "trimul_n512_outgoing": lambda: case_trimul(B=1, N=512, mode="outgoing", pad=37),
+    "trimul_n512_incoming": lambda: case_trimul(B=1, N=512, mode="incoming", pad=37),
+    "triattn_n512_ending": lambda: case_triattn(B=1, N=512, mode="ending", pad=70),
+    "outer_linear_n512": lambda: case_outer_linear(syn.PAPER, 1, 512),
+    "pair_transition_n512": lambda: case_pair_transition(syn.PAPER, 1, 512),
+    "heads_n512": lambda: case_heads(syn.PAPER, 1, 512, seed=3, pad=41),
+    "embeddings_n512": lambda: case_embeddings(sizes=((32, 450), (20, 492)), seed=5),
+    "denoiser_forward": lambda: case_denoiser_forward(),
+    "folding_block_forward": lambda: case_folding_block_forward(),
+    "predict_step_ema": lambda: case_predict_step(),
+    "back_to_back_batches": lambda: case_back_to_back_batches(),
     "loss_paper_n72": lambda: case_loss(dataclasses.replace(syn.PAPER, mask_prob=0.15, num_steps=2000),
                                         ((12, 60), (9, 50)), seed=11),
 }

@@ -30,6 +30,10 @@ CASE_NAMES = [
     "triattn_n300", "triattn_n512", "triattn_readme", "outer_linear", "outer_linear_readme", "outer_linear_n300",
     "single_attention", "single_transition", "spattention", "opm", "embeddings", "embeddings_readme", "embeddings_n128", "embeddings_n256", "heads",
     "pair_bias", "sample_eager", "sample_graph", "invariants", "invariants_n300", "invariants_n512_b8", "invariants_n1024", "sample_graph_T50", "loss_paper_n72",
+    # round 2: oracle parity at BASELINE.json's sizes, public module entry points, advisor regressions
+    "step_n512", "step_n512_b2_ragged", "step_n300", "step_n1024", "batch_rows_b8_n512", "trimul_n512_outgoing", "trimul_n512_incoming",
+    "triattn_n512_ending", "outer_linear_n512", "pair_transition_n512", "heads_n512", "embeddings_n512", "denoiser_forward",
+    "folding_block_forward", "predict_step_ema", "back_to_back_batches",
 ]
 
 

@@ -30,7 +30,7 @@ def main():
     out = open(os.path.join(ROOT, "gpurun_out", "diag.jsonl"), "a")
     for n in names:
         try:
-            p = subprocess.run([sys.executable, __file__, "--one", n], capture_output=True, text=True, timeout=300)
+            p = subprocess.run([sys.executable, __file__, "--one", n], capture_output=True, text=True, timeout=900)
             line = [l for l in p.stdout.splitlines() if l.startswith("{")]
             if p.returncode == 0 and line:
                 rec = line[-1]
