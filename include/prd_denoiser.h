@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define PRD_VERSION 1
+#define PRD_VERSION 2
 
 typedef struct PrdDims {
   int32_t B;                 /* batch rows                                  */
@@ -70,6 +70,9 @@ typedef struct PrdGemm {
   const float* mul; int64_t ldmul, mul_bs1, mul_bs2;
   const float* add; int64_t ldadd, add_bs1, add_bs2;
   void* C; int64_t ldc, c_bs1, c_bs2; int32_t c_fp16;
+  int32_t tf32;       /* 1: A, B are fp32 in memory and multiplied on kind::tf32 (lda / ldb / strides in floats); C fp32 */
+  int32_t mul_step;   /* 1: `mul` gates instead of scaling: v = mul > 0 ? v : 0 (ReLU backward) */
+  int32_t round_tf32; /* 1: fp32 result rounded to nearest tf32 (it is the operand of a following tf32 GEMM) */
 } PrdGemm;
 int prd_gemm_f16(const PrdGemm* g, void* stream);
 
@@ -169,6 +172,35 @@ PRD_DECLARE_OP(diffusion_q)
  * out: [loss f32 1 | diff_loss f32 B | terms f32 B+2 {mse_b.., KL, CE} (or NULL) | d_noise_pred (or NULL) |
  *       d_seq_pred (or NULL)] */
 PRD_DECLARE_OP(diffusion_loss)
+
+/* --- backward pass (reference: Lightning's backward through model.py:528-549 with per-block
+ * checkpointing, modules.py:399-401) --------------------------------------------------------------------------
+ * One prd_<op>_bwd per forward op, same uniform signature.  Conventions (csrc/prd_bwd_api.cu):
+ *   - `in`  : the op's forward INPUTS (the op recomputes its intermediates: nothing else is stored by the forward);
+ *   - `out` : out[0] is the gradient buffer of the op's main operand, IN/OUT for the residual ops (d output on entry,
+ *             d input on exit, may not alias `in`); further gradient buffers marked (+=) are accumulated; weight
+ *             gradients are fp32 buffers shaped like the REFERENCE parameters and are accumulated (+=);
+ *   - `weights` : the RAW fp32 reference parameters (nn.Linear layout [out, in]), not the packed fp16 forward copies;
+ *   - arithmetic: fp32 activations, products on kind::tf32 tensor cores (operands rounded to nearest), weight gradients
+ *     as exact fp32 reductions.  Pointer orders are documented above each op in csrc/prd_bwd_api.cu. */
+#define PRD_DECLARE_BWD(name)                                                                     \
+  int prd_##name##_bwd(const PrdDims* d, const void* const* in, void* const* out,                 \
+                       const void* const* weights, void* workspace, size_t workspace_bytes,       \
+                       void* stream);                                                             \
+  size_t prd_##name##_bwd_workspace_bytes(const PrdDims* d);
+PRD_DECLARE_BWD(pair_transition)          /* modules.py:321-326,342 */
+PRD_DECLARE_BWD(single_transition)        /* modules.py:306-311,336 */
+PRD_DECLARE_BWD(seq_head)                 /* model.py:374 */
+PRD_DECLARE_BWD(coord_head)               /* model.py:364-373 + modules.py:403 */
+PRD_DECLARE_BWD(triangle_attention)       /* modules.py:236-243 */
+PRD_DECLARE_BWD(triangle_multiplication)  /* modules.py:262-274 */
+PRD_DECLARE_BWD(outer_linear)             /* modules.py:283-287 */
+PRD_DECLARE_BWD(single_attention)         /* modules.py:300-304,185-225 */
+PRD_DECLARE_BWD(spattention)              /* AF2_modules.py:421-473 */
+PRD_DECLARE_BWD(opm_project)              /* AF2_modules.py:519-530 */
+PRD_DECLARE_BWD(pair_embed)               /* model.py:348-361, AF2_modules.py:532-543 */
+PRD_DECLARE_BWD(single_embed)             /* model.py:342-346,99-102 */
+#undef PRD_DECLARE_BWD
 
 /* Profiling hook used by bench.py: average duration (ms) of ONE named kernel ("triattn_flash",
  * "trimul_gemm", "pair_bias") over `iters` launches on the data a previous full op left in the

@@ -24,6 +24,12 @@ OPS = (
 )
 
 
+OPS_BWD = (
+    "pair_transition", "single_transition", "seq_head", "coord_head", "triangle_attention", "triangle_multiplication",
+    "outer_linear", "single_attention", "spattention", "opm_project", "pair_embed", "single_embed",
+)
+
+
 class PrdDims(ctypes.Structure):
     _fields_ = [(n, ctypes.c_int32) for n in (
         "B", "N", "c_s", "c_z", "H", "c", "tf", "esm_dim", "time_dim", "dist_dim",
@@ -42,7 +48,7 @@ class PrdGemm(ctypes.Structure):
         ("mul", ctypes.c_void_p), ("ldmul", ctypes.c_int64), ("mul_bs1", ctypes.c_int64), ("mul_bs2", ctypes.c_int64),
         ("add", ctypes.c_void_p), ("ldadd", ctypes.c_int64), ("add_bs1", ctypes.c_int64), ("add_bs2", ctypes.c_int64),
         ("C", ctypes.c_void_p), ("ldc", ctypes.c_int64), ("c_bs1", ctypes.c_int64), ("c_bs2", ctypes.c_int64),
-        ("c_fp16", ctypes.c_int32),
+        ("c_fp16", ctypes.c_int32), ("tf32", ctypes.c_int32), ("mul_step", ctypes.c_int32), ("round_tf32", ctypes.c_int32),
     ]
 
 
@@ -96,6 +102,13 @@ def load() -> ctypes.CDLL:
             f.restype = ctypes.c_int
             f.argtypes = [ctypes.POINTER(PrdDims), vpp, vpp, vpp, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]
             w = getattr(lib, f"prd_{op}_workspace_bytes")
+            w.restype = ctypes.c_size_t
+            w.argtypes = [ctypes.POINTER(PrdDims)]
+        for op in OPS_BWD:
+            f = getattr(lib, f"prd_{op}_bwd")
+            f.restype = ctypes.c_int
+            f.argtypes = [ctypes.POINTER(PrdDims), vpp, vpp, vpp, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]
+            w = getattr(lib, f"prd_{op}_bwd_workspace_bytes")
             w.restype = ctypes.c_size_t
             w.argtypes = [ctypes.POINTER(PrdDims)]
         _lib = lib
@@ -183,13 +196,39 @@ def call(op: str, dims: PrdDims, ins: Sequence[Optional[torch.Tensor]], outs: Se
         raise RuntimeError(f"prd_{op}_fwd failed: {last_error()}")
 
 
-def gemm_f16(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, *, alpha: float = 1.0, bias=None, act: int = 0,
-             rowscale=None, mul=None, add=None) -> torch.Tensor:
-    """out[..., M, N] = epilogue(alpha * a[..., M, K] @ b[..., N, K]^T); a, b fp16; up to two batch dims
-    (b may omit them = shared weight).  Test hook for the tcgen05 + TMA machinery."""
+def call_bwd(op: str, dims: PrdDims, ins: Sequence[Optional[torch.Tensor]], outs: Sequence[Optional[torch.Tensor]],
+             weights: Sequence[Optional[torch.Tensor]]) -> None:
+    """Enqueue prd_<op>_bwd on the current torch CUDA stream (same conventions as :func:`call`)."""
     lib = load()
-    check_tensor(a, torch.float16, "a")
-    check_tensor(b, torch.float16, "b")
+    dev = None
+    for t in list(ins) + list(outs) + list(weights):
+        if t is not None:
+            if not t.is_cuda:
+                raise RuntimeError(f"prd_{op}_bwd: tensor on {t.device}; CUDA sm_100 only (no CPU fallback)")
+            if not t.is_contiguous():
+                raise ValueError(f"prd_{op}_bwd: every tensor must be contiguous")
+            dev = t.device
+    if dev is None:
+        raise RuntimeError(f"prd_{op}_bwd: no tensors given")
+    need = int(getattr(lib, f"prd_{op}_bwd_workspace_bytes")(ctypes.byref(dims)))
+    ws = Workspace.reserve(dev, need)
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    rc = getattr(lib, f"prd_{op}_bwd")(ctypes.byref(dims), _ptr_array(ins), _ptr_array(outs), _ptr_array(weights),
+                                       ctypes.c_void_p(ws.data_ptr()), ctypes.c_size_t(ws.numel()),
+                                       ctypes.c_void_p(stream))
+    if rc != 0:
+        raise RuntimeError(f"prd_{op}_bwd failed: {last_error()}")
+
+
+def gemm_f16(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, *, alpha: float = 1.0, bias=None, act: int = 0,
+             rowscale=None, mul=None, add=None, mul_step: bool = False, round_tf32: bool = False) -> torch.Tensor:
+    """out[..., M, N] = epilogue(alpha * a[..., M, K] @ b[..., N, K]^T); a, b fp16 -- or both fp32, multiplied on
+    kind::tf32 (the backward pass's operand type); up to two batch dims (b may omit them = shared weight).  Test hook
+    for the tcgen05 + TMA machinery."""
+    lib = load()
+    tf32 = a.dtype == torch.float32
+    check_tensor(a, torch.float32 if tf32 else torch.float16, "a")
+    check_tensor(b, torch.float32 if tf32 else torch.float16, "b")
     M, K = a.shape[-2:]
     N = b.shape[-2]
     batch = list(a.shape[:-2])
@@ -212,6 +251,7 @@ def gemm_f16(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, *, alpha: floa
         g.add, g.ldadd, g.add_bs1, g.add_bs2 = add.data_ptr(), N, M * N, nb1 * M * N
     g.C, g.ldc, g.c_bs1, g.c_bs2 = out.data_ptr(), N, M * N, nb1 * M * N
     g.c_fp16 = 1 if out.dtype == torch.float16 else 0
+    g.tf32, g.mul_step, g.round_tf32 = int(tf32), int(mul_step), int(round_tf32)
     rc = lib.prd_gemm_f16(ctypes.byref(g), ctypes.c_void_p(torch.cuda.current_stream(a.device).cuda_stream))
     if rc != 0:
         raise RuntimeError(f"prd_gemm_f16 failed: {last_error()}")

@@ -1,0 +1,265 @@
+"""Backward pass of the denoiser on the CUDA kernels (reference: Lightning's ``loss.backward()`` through
+``ProteinReDiffModel.training_step`` model.py:528-549 with per-block checkpointing, modules.py:399-401).
+
+Structure
+* forward: the fused inference kernels, keeping only block-boundary checkpoints (single, pair before every FoldingBlock,
+  the embedding outputs and the OuterProductUpdate operands);
+* backward: per block, the forward of the block is re-run once to recover the input of each of its eight residual
+  updates, then ``prd_<op>_bwd`` (include/prd_denoiser.h) is called in reverse order; each of those recomputes its own
+  intermediates from its input, so nothing else is ever stored;
+* parameter gradients are fp32 tensors shaped like the reference parameters, accumulated by the kernels and handed to
+  autograd by :class:`DenoiserFunction` -- ``loss.backward()``, optimisers and gradient all-reduce work unchanged.
+
+Nothing here computes in PyTorch: the functions pack pointers and call the C ABI.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Tuple
+
+import torch
+
+from . import _lib, ops
+from .ops import make_dims
+
+
+def _bwd(op, dims, ins, outs, weights):
+    _lib.call_bwd(op, dims, ins, outs, weights)
+
+
+# --------------------------------------------------------------------------------------------------------------
+# per-op launchers.  P: name -> fp32 parameter (contiguous, CUDA), G: name -> fp32 gradient buffer (accumulated)
+# --------------------------------------------------------------------------------------------------------------
+def _names(prefix: str, *suffixes: str) -> List[str]:
+    return [prefix + s for s in suffixes]
+
+
+def transition_bwd(cfg, P, G, prefix: str, x_in: torch.Tensor, d_io: torch.Tensor) -> None:
+    """single_fc / pair_fc (reference modules.py:306-311, 321-326); ``d_io``: d out -> d in."""
+    n = _names(prefix, "1.weight", "1.bias", "3.weight", "3.bias")
+    op = "single_transition" if x_in.dim() == 3 else "pair_transition"
+    B, N = x_in.shape[:2]
+    _bwd(op, make_dims(cfg, B, N), [x_in], [d_io] + [G[k] for k in n], [P[k] for k in n])
+
+
+def seq_head_bwd(cfg, P, G, single: torch.Tensor, d_seq_pred: torch.Tensor, d_single: torch.Tensor) -> None:
+    """seq_mlp (reference model.py:374); ``d_single`` is written."""
+    n = ["seq_mlp.1.weight", "seq_mlp.1.bias", "seq_mlp.3.weight"]
+    B, N = single.shape[:2]
+    _bwd("seq_head", make_dims(cfg, B, N), [single, d_seq_pred], [d_single] + [G[k] for k in n], [P[k] for k in n])
+
+
+def coord_head_bwd(cfg, P, G, pair, z, mask, d_noise_pred, d_pair) -> None:
+    """weight_radial + equivariant sum + remove_mean + the trunk's symmetrisation (reference model.py:364-373,
+    modules.py:403); ``pair`` is the tensor BEFORE symmetrisation, ``d_pair`` is written."""
+    n = ["weight_radial.1.weight", "weight_radial.1.bias", "weight_radial.3.weight"]
+    B, N = mask.shape
+    _bwd("coord_head", make_dims(cfg, B, N), [pair, z, mask, d_noise_pred], [d_pair] + [G[k] for k in n], [P[k] for k in n])
+
+
+_ATTN = ("q_proj.weight", "k_proj.weight", "v_proj.weight", "gate_proj.weight", "gate_proj.bias", "out_proj.weight", "out_proj.bias")
+
+
+def triangle_attention_bwd(cfg, P, G, prefix: str, mode: int, pair_in, mask, d_pair) -> None:
+    """reference modules.py:236-243 (``prefix`` ends with ``attn.``)."""
+    n = _names(prefix, *_ATTN)
+    B, N = mask.shape
+    _bwd("triangle_attention", make_dims(cfg, B, N, mode=mode), [pair_in, mask], [d_pair] + [G[k] for k in n], [P[k] for k in n])
+
+
+def single_attention_bwd(cfg, P, G, block_prefix: str, single_in, pair, mask, d_single, d_pair) -> None:
+    """attn_bias + single_attn of a FoldingBlock (reference modules.py:300-304, 185-225, 335)."""
+    n = _names(block_prefix, "attn_bias.1.weight", "attn_bias.1.bias") + _names(block_prefix + "single_attn.", *_ATTN)
+    B, N = mask.shape
+    _bwd("single_attention", make_dims(cfg, B, N), [single_in, pair, mask], [d_single, d_pair] + [G[k] for k in n], [P[k] for k in n])
+
+
+def triangle_multiplication_bwd(cfg, P, G, prefix: str, mode: int, pair_in, mask, d_pair) -> None:
+    """reference modules.py:262-274."""
+    n = _names(prefix, "ab_proj.weight", "ab_proj.bias", "ab_gate.weight", "ab_gate.bias", "out_proj.weight", "out_proj.bias",
+               "out_gate.weight", "out_gate.bias")
+    B, N = mask.shape
+    _bwd("triangle_multiplication", make_dims(cfg, B, N, mode=mode), [pair_in, mask], [d_pair] + [G[k] for k in n],
+         [P[k] for k in n])
+
+
+def outer_linear_bwd(cfg, P, G, prefix: str, single_in, d_pair, d_single) -> None:
+    """reference modules.py:283-287; ``d_pair`` is read only (the residual passes through), ``d_single`` accumulates."""
+    n = _names(prefix, "linear.weight", "linear.bias")
+    B, N = single_in.shape[:2]
+    _bwd("outer_linear", make_dims(cfg, B, N), [single_in, d_pair], [d_single, G[n[0]], G[n[1]]], [P[n[0]]])
+
+
+_SPA = ("layer_norm_m.weight", "layer_norm_m.bias", "linear_z.0.weight", "linear_z.0.bias", "linear_z.1.weight",
+        "mha.linear_q.weight", "mha.linear_k.weight", "mha.linear_v.weight", "mha.linear_g.weight", "mha.linear_g.bias",
+        "mha.linear_o.weight", "mha.linear_o.bias")
+
+
+def spattention_bwd(cfg, P, G, single_in, pair, d_single, d_pair, prefix: str = "Denoiser.SPAAttnBlock.") -> None:
+    """reference AF2_modules.py:421-473; ``d_single``: d out -> d in, ``d_pair`` accumulates."""
+    n = _names(prefix, *_SPA)
+    B, N = single_in.shape[:2]
+    _bwd("spattention", make_dims(cfg, B, N), [single_in, pair], [d_single, d_pair] + [G[k] for k in n], [P[k] for k in n])
+
+
+def opm_project_bwd(cfg, P, G, single_in, mask, d_a, d_b, d_single, prefix: str = "Denoiser.opm.") -> None:
+    """reference AF2_modules.py:519-530; ``d_single`` accumulates."""
+    n = _names(prefix, "layer_norm.weight", "layer_norm.bias", "linear_1.weight", "linear_1.bias", "linear_2.weight", "linear_2.bias")
+    B, N = mask.shape
+    _bwd("opm_project", make_dims(cfg, B, N), [single_in, mask, d_a, d_b], [d_single] + [G[k] for k in n], [P[k] for k in n])
+
+
+def pair_embed_bwd(cfg, P, G, batch, d_pair, z, mask, t, opm_a, opm_b) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Everything that wrote the initial pair tensor (reference model.py:348-361, AF2_modules.py:532-543,
+    modules.py:395-397).  Returns (d_opm_a, d_opm_b)."""
+    B, N = mask.shape
+    d_a, d_b = torch.empty_like(opm_a), torch.empty_like(opm_b)
+    outs = [d_a, d_b, G["Denoiser.opm.linear_out.weight"], G["Denoiser.opm.linear_out.bias"], G["embed_dist.1.weight"],
+            G["embed_beta.1.weight"], G["embed_bond_feats.embeddings.0.weight"], G["embed_bond_feats.embeddings.1.weight"],
+            G["embed_bond_feats.embeddings.2.weight"], G["embed_bond_distance.weight"], G["embed_relpos.weight"]]
+    ins = [d_pair, z, mask, t, opm_a, opm_b, batch["atom_mask"], batch["residue_mask"], batch["bond_mask"], batch["bond_feats"],
+           batch["bond_distance"], batch["residue_index"], batch["residue_chain_index"]]
+    _bwd("pair_embed", make_dims(cfg, B, N), [x.contiguous() for x in ins], outs,
+         [P["Denoiser.opm.linear_out.weight"], P["embed_dist.0.center"], P["embed_beta.0.weight"]])
+    return d_a, d_b
+
+
+def single_embed_bwd(cfg, P, G, batch, seq_t, d_single) -> None:
+    """reference model.py:342-346 (+ :99-102)."""
+    B, N = seq_t.shape[:2]
+    outs = [G[f"embed_atom_feats.embeddings.{f}.weight"] for f in range(9)] + [G["embed_residue_type.1.weight"],
+                                                                               G["embed_residue_esm.1.weight"]]
+    ins = [d_single, batch["atom_feats"], batch["atom_mask"], batch["residue_mask"], seq_t, batch["residue_esm"]]
+    _bwd("single_embed", make_dims(cfg, B, N), [x.contiguous() for x in ins], outs, [P["embed_residue_type.1.weight"]])
+
+
+# --------------------------------------------------------------------------------------------------------------
+# the whole network
+# --------------------------------------------------------------------------------------------------------------
+class DenoiserTape:
+    """Checkpoints of one forward evaluation (what the reference's per-block ``checkpoint`` keeps)."""
+
+    __slots__ = ("batch", "z", "seq_t", "mask", "t", "single0", "opm_a", "opm_b", "pair1", "blocks", "single_out", "pair_out")
+
+
+def forward_with_checkpoints(model, batch, z, seq_t, mask, t) -> Tuple[torch.Tensor, torch.Tensor, DenoiserTape]:
+    """The same kernels as ``ProteinReDiffModel._denoise`` (reference model.py:318-375), keeping the block-boundary
+    activations."""
+    cfg, w = model.cfg, model._weights()
+    den = model.Denoiser
+    tape = DenoiserTape()
+    tape.batch, tape.z, tape.seq_t, tape.mask, tape.t = batch, z.contiguous(), seq_t.contiguous(), mask.contiguous(), t.contiguous()
+    esm_emb, pair_static = model._static_embeddings(batch)
+    single = ops.single_embed(cfg, batch["atom_feats"].contiguous(), batch["atom_mask"].contiguous(),
+                              batch["residue_mask"].contiguous(), tape.seq_t, esm_emb, w["atom_tabs"], w["w_type"])
+    tape.single0 = single.clone()
+    tape.opm_a, tape.opm_b = den.opm.project(cfg, single, tape.mask)
+    _, (w_o, b_o) = den.opm.packed_weights()
+    pair = torch.empty(mask.shape[0], mask.shape[1], mask.shape[1], cfg.pair_dim, dtype=torch.float32, device=z.device)
+    ops.pair_embed(cfg, pair_static, tape.z, tape.mask, tape.t, tape.opm_a, tape.opm_b, w["pair_dyn"] + [w_o, b_o], pair,
+                   rbf_lut=w["rbf_lut"])
+    tape.pair1 = pair.clone()
+    den.SPAAttnBlock(single, pair, tape.mask, cfg=cfg, out=single)
+    tape.blocks = []
+    for block in den.folding_blocks:
+        tape.blocks.append((single.clone(), pair.clone()))
+        block.forward_(cfg, single, pair, tape.mask)
+    tape.single_out, tape.pair_out = single, pair
+    noise_pred = ops.coord_head(cfg, pair, tape.z, tape.mask, w["coord"])
+    seq_pred = ops.seq_head(cfg, single, w["seq"])
+    return noise_pred, seq_pred, tape
+
+
+def backward_from_checkpoints(model, tape: DenoiserTape, d_noise_pred: torch.Tensor, d_seq_pred: torch.Tensor,
+                              P: Dict[str, torch.Tensor], G: Dict[str, torch.Tensor]) -> None:
+    """Accumulates d loss / d parameter into ``G`` for every trainable parameter of the model."""
+    cfg, den, mask = model.cfg, model.Denoiser, tape.mask
+    d_single = torch.empty_like(tape.single_out)
+    d_pair = torch.empty_like(tape.pair_out)
+    seq_head_bwd(cfg, P, G, tape.single_out, d_seq_pred.contiguous(), d_single)
+    coord_head_bwd(cfg, P, G, tape.pair_out, tape.z, mask, d_noise_pred.contiguous(), d_pair)
+    tape.single_out = tape.pair_out = None
+    for k in reversed(range(len(den.folding_blocks))):
+        block, bp = den.folding_blocks[k], f"Denoiser.folding_blocks.{k}."
+        s0, p0 = tape.blocks.pop()
+        # re-run the block once, keeping the input of each residual update (reference order modules.py:335-342)
+        s1 = s0.clone()
+        ops.single_attention(cfg, s1, p0, mask, block.single_attn.packed_single(block.attn_bias[1]), s1)
+        s2 = s1.clone()
+        ops.single_transition(cfg, s2, block.single_fc.packed_single(), s2)
+        p1 = p0.clone()
+        block.outer_linear.apply_(cfg, s2, p1)
+        p2 = p1.clone()
+        block.pair_mul_outgoing.apply_(cfg, p2, mask)
+        p3 = p2.clone()
+        block.pair_mul_incoming.apply_(cfg, p3, mask)
+        p4 = p3.clone()
+        block.pair_attn_starting.apply_(cfg, p4, mask)
+        p5 = p4.clone()
+        block.pair_attn_ending.apply_(cfg, p5, mask)
+        transition_bwd(cfg, P, G, bp + "pair_fc.", p5, d_pair)
+        del p5
+        triangle_attention_bwd(cfg, P, G, bp + "pair_attn_ending.attn.", 1, p4, mask, d_pair)
+        del p4
+        triangle_attention_bwd(cfg, P, G, bp + "pair_attn_starting.attn.", 0, p3, mask, d_pair)
+        del p3
+        triangle_multiplication_bwd(cfg, P, G, bp + "pair_mul_incoming.", 1, p2, mask, d_pair)
+        del p2
+        triangle_multiplication_bwd(cfg, P, G, bp + "pair_mul_outgoing.", 0, p1, mask, d_pair)
+        del p1
+        outer_linear_bwd(cfg, P, G, bp + "outer_linear.", s2, d_pair, d_single)
+        transition_bwd(cfg, P, G, bp + "single_fc.", s1, d_single)
+        single_attention_bwd(cfg, P, G, bp, s0, p0, mask, d_single, d_pair)
+    spattention_bwd(cfg, P, G, tape.single0, tape.pair1, d_single, d_pair)
+    d_a, d_b = pair_embed_bwd(cfg, P, G, tape.batch, d_pair, tape.z, mask, tape.t, tape.opm_a, tape.opm_b)
+    opm_project_bwd(cfg, P, G, tape.single0, mask, d_a, d_b, d_single)
+    single_embed_bwd(cfg, P, G, tape.batch, tape.seq_t, d_single)
+
+
+def trainable_parameters(model) -> List[Tuple[str, torch.nn.Parameter]]:
+    return [(n, p) for n, p in model.named_parameters() if p.requires_grad]
+
+
+class DenoiserFunction(torch.autograd.Function):
+    """(noise_pred, seq_pred) = network(z, seq_t, t | batch) as one autograd node over every trainable parameter."""
+
+    @staticmethod
+    def forward(ctx, model, batch, z, seq_t, mask, t, *params):
+        with torch.no_grad():
+            noise_pred, seq_pred, tape = forward_with_checkpoints(model, batch, z, seq_t, mask, t)
+        ctx.model, ctx.tape = model, tape
+        return noise_pred, seq_pred
+
+    @staticmethod
+    def backward(ctx, d_noise_pred, d_seq_pred):
+        model, tape = ctx.model, ctx.tape
+        named = trainable_parameters(model)
+        P = {n: p.detach().contiguous() for n, p in model.named_parameters()}
+        flat = torch.zeros(sum(p.numel() for _, p in named), dtype=torch.float32, device=tape.z.device)
+        G, off = {}, 0
+        for n, p in named:
+            G[n] = flat[off:off + p.numel()].view(p.shape)
+            off += p.numel()
+        with torch.no_grad():
+            backward_from_checkpoints(model, tape, d_noise_pred, d_seq_pred, P, G)
+        ctx.tape = None
+        return (None,) * 6 + tuple(G[n] for n, _ in named)
+
+
+class LossFunction(torch.autograd.Function):
+    """loss = mean(diff_loss / num_nodes) (reference model.py:499-526, 538-541) with the gradient the loss kernels
+    already produce (d loss / d noise_pred, d loss / d seq_pred)."""
+
+    @staticmethod
+    def forward(ctx, noise_pred, seq_pred, cfg, noise_z, noise_seq, seq_t1, mask, residue_mask, residue_type, t, sched, detail):
+        loss, diff, terms, d_noise, d_seq = ops.diffusion_loss(cfg, noise_pred.contiguous(), seq_pred.contiguous(), noise_z,
+                                                               noise_seq, seq_t1, mask, residue_mask, residue_type, t, sched,
+                                                               want_grads=True)
+        ctx.save_for_backward(d_noise, d_seq)
+        if detail is not None:
+            detail.update(loss=loss, diff_loss=diff, terms=terms, d_noise_pred=d_noise, d_seq_pred=d_seq)
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, g):
+        d_noise, d_seq = ctx.saved_tensors
+        return (g * d_noise, g * d_seq) + (None,) * 10

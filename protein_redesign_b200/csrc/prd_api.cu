@@ -59,13 +59,14 @@ int prd_gemm_f16(const PrdGemm* p, void* stream) {
   if (prd_device_check()) return 1;
   GemmArgs g;
   g.M = p->M; g.N = p->N; g.K = p->K; g.nb1 = p->nb1; g.nb2 = p->nb2;
-  g.A = static_cast<const __half*>(p->A); g.lda = p->lda; g.a_bs1 = p->a_bs1; g.a_bs2 = p->a_bs2;
-  g.B = static_cast<const __half*>(p->B); g.ldb = p->ldb; g.b_bs1 = p->b_bs1; g.b_bs2 = p->b_bs2;
+  g.A = p->A; g.lda = p->lda; g.a_bs1 = p->a_bs1; g.a_bs2 = p->a_bs2;
+  g.B = p->B; g.ldb = p->ldb; g.b_bs1 = p->b_bs1; g.b_bs2 = p->b_bs2;
   g.alpha = p->alpha; g.act = p->act; g.bias = p->bias;
   g.rowscale = p->rowscale; g.rs_bs1 = p->rs_bs1; g.rs_bs2 = p->rs_bs2;
   g.mul = p->mul; g.ldmul = p->ldmul; g.mul_bs1 = p->mul_bs1; g.mul_bs2 = p->mul_bs2;
   g.add = p->add; g.ldadd = p->ldadd; g.add_bs1 = p->add_bs1; g.add_bs2 = p->add_bs2;
   g.C = p->C; g.ldc = p->ldc; g.c_bs1 = p->c_bs1; g.c_bs2 = p->c_bs2; g.c_fp16 = p->c_fp16;
+  g.tf32 = p->tf32; g.mul_step = p->mul_step; g.round_tf32 = p->round_tf32;
   return gemm_f16(g, S(stream));
 }
 

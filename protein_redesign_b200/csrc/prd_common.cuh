@@ -265,6 +265,17 @@ __host__ __device__ constexpr uint32_t umma_idesc_f16(uint32_t M, uint32_t N) {
   return (1u << 4) | (0u << 7) | (0u << 10) | (0u << 15) | (0u << 16) | ((N >> 3) << 17) | ((M >> 4) << 24);
 }
 
+// kind::tf32: fp32 words in shared memory, of which the tensor core reads sign + exponent + 10 mantissa bits (format 2).
+__host__ __device__ constexpr uint32_t umma_idesc_tf32(uint32_t M, uint32_t N) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | (0u << 15) | (0u << 16) | ((N >> 3) << 17) | ((M >> 4) << 24);
+}
+// Round to nearest tf32 (the tensor core truncates: an unrounded operand carries a systematic -2^-11 bias).
+__device__ __forceinline__ float round_tf32(float x) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+  return __uint_as_float(u);
+}
+
 // D[tmem] (+)= A[smem] * B[smem]^T, one UMMA (K = 16 halves); issued by ONE thread.
 __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
                                          uint32_t accumulate) {
@@ -292,6 +303,24 @@ __device__ __forceinline__ void umma_kblock(uint32_t tmem_d, uint32_t a_smem, ui
     // advancing 16 halves (32 B) along K inside the 128 B swizzle row = +2 in the (addr >> 4) field
     umma_f16(tmem_d, da + 2 * k, db + 2 * k, idesc, (accumulate_first || k > 0) ? 1u : 0u);
   }
+}
+
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// One [128 x 32] fp32 K-block of A against one [N x 32] K-block of B: four UMMAs of K = 8 (32 bytes each).
+__device__ __forceinline__ void umma_kblock_tf32(uint32_t tmem_d, uint32_t a_smem, uint32_t b_smem, uint32_t idesc,
+                                                 bool accumulate_first) {
+  const uint64_t da = umma_desc_sw128(a_smem);
+  const uint64_t db = umma_desc_sw128(b_smem);
+#pragma unroll
+  for (uint32_t k = 0; k < 4; ++k) umma_tf32(tmem_d, da + 2 * k, db + 2 * k, idesc, (accumulate_first || k > 0) ? 1u : 0u);
 }
 
 // TMEM -> registers: 32 lanes (this warp's quarter) x 32 consecutive 32-bit columns.

@@ -37,6 +37,8 @@ struct GemmEpilogue {
   void* C;
   long long ldc, c_bs1, c_bs2;
   int c_fp16;
+  int mul_step;   // the mul operand gates instead of scaling: v = mul > 0 ? v : 0 (ReLU backward)
+  int round_tf32; // fp32 C rounded to nearest tf32 (the result feeds another tf32 GEMM as an operand)
 };
 
 struct GemmTiling {
@@ -57,10 +59,12 @@ struct GemmTiling {
 // Persistent: every CTA walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...  The accumulator is
 // double buffered in TMEM, so the epilogue of tile i (TMEM -> registers -> global) overlaps the
 // TMA / UMMA main loop of tile i+1.
-template <int BN, int STAGES>
+template <int BN, int STAGES, bool TF32>
 __global__ void __launch_bounds__(192, 1)
 gemm_f16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, int num_kb,
                 int a_wrap, int b_wrap, GemmTiling tl, int a_b1, int a_b2, int b_b1, int b_b2, GemmEpilogue ep) {
+  // TF32: operands are fp32 in memory (kind::tf32 reads the upper 19 bits: producers round to nearest first), one K-block =
+  // 32 elements = the same 128-byte swizzle row, one UMMA = K 8 = the same 32-byte descriptor step as 16 halves.
   // a_wrap / b_wrap: K-blocks after which that operand's K coordinate wraps to 0.  With a weight
   // stored as [hi | lo] along K (fp16 pair, removes the systematic weight rounding) the activation
   // operand is simply read twice: sum_k x_k (w_hi + w_lo)_k.
@@ -108,14 +112,15 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
           mbar_wait(&empty[s], ph ^ 1);
           mbar_expect_tx(&full[s], L::kStageBytes);
           uint8_t* sa = smem + s * L::kStageBytes;
-          tma_load_4d(sa, &map_a, &full[s], (kb % a_wrap) * 64, m0, i1 * a_b1, i2 * a_b2);
-          tma_load_4d(sa + L::kABytes, &map_b, &full[s], (kb % b_wrap) * 64, n0, i1 * b_b1, i2 * b_b2);
+          constexpr int kKbElems = TF32 ? 32 : 64;
+          tma_load_4d(sa, &map_a, &full[s], (kb % a_wrap) * kKbElems, m0, i1 * a_b1, i2 * a_b2);
+          tma_load_4d(sa + L::kABytes, &map_b, &full[s], (kb % b_wrap) * kKbElems, n0, i1 * b_b1, i2 * b_b2);
         }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_f16(128, BN);
+      constexpr uint32_t idesc = TF32 ? umma_idesc_tf32(128, BN) : umma_idesc_f16(128, BN);
       long long it = 0;
       int lt = 0;  // local tile counter
       for (long long tile = blockIdx.x; tile < tl.total; tile += gridDim.x, ++lt) {
@@ -128,7 +133,8 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
           mbar_wait(&full[s], ph);
           tc_fence_after();
           const uint32_t sa = base + s * L::kStageBytes;
-          umma_kblock(tmem + buf * BN, sa, sa + L::kABytes, idesc, kb > 0);
+          if constexpr (TF32) umma_kblock_tf32(tmem + buf * BN, sa, sa + L::kABytes, idesc, kb > 0);
+          else umma_kblock(tmem + buf * BN, sa, sa + L::kABytes, idesc, kb > 0);
           umma_commit(&empty[s]);
         }
         umma_commit(&tmem_full[buf]);
@@ -272,13 +278,21 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             if (chunk_full && ((ep.ldmul & 3) == 0) && ((reinterpret_cast<uintptr_t>(mb) & 15) == 0)) {
               uint4 t4[8];
               warp_load_rows128(epi + q * 4096, lane, t4, mb, (long long)ep.ldmul * 4, rows_left);
+              if (ep.mul_step) {
 #pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                v[4 * j] *= __uint_as_float(t4[j].x); v[4 * j + 1] *= __uint_as_float(t4[j].y);
-                v[4 * j + 2] *= __uint_as_float(t4[j].z); v[4 * j + 3] *= __uint_as_float(t4[j].w);
+                for (int j = 0; j < 8; ++j) {
+                  v[4 * j] = __uint_as_float(t4[j].x) > 0.f ? v[4 * j] : 0.f; v[4 * j + 1] = __uint_as_float(t4[j].y) > 0.f ? v[4 * j + 1] : 0.f;
+                  v[4 * j + 2] = __uint_as_float(t4[j].z) > 0.f ? v[4 * j + 2] : 0.f; v[4 * j + 3] = __uint_as_float(t4[j].w) > 0.f ? v[4 * j + 3] : 0.f;
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  v[4 * j] *= __uint_as_float(t4[j].x); v[4 * j + 1] *= __uint_as_float(t4[j].y);
+                  v[4 * j + 2] *= __uint_as_float(t4[j].z); v[4 * j + 3] *= __uint_as_float(t4[j].w);
+                }
               }
             } else if (active) {
-              for (int j = 0; j < 32 && col0 + j < ep.N; ++j) v[j] *= mulp[col0 + j];
+              for (int j = 0; j < 32 && col0 + j < ep.N; ++j) v[j] = ep.mul_step ? (mulp[col0 + j] > 0.f ? v[j] : 0.f) : v[j] * mulp[col0 + j];
             }
           }
           if (ep.add != nullptr) {
@@ -295,6 +309,10 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
               for (int j = 0; j < 32 && col0 + j < ep.N; ++j) v[j] += addp[col0 + j];
             }
           }
+        }
+        if (ep.round_tf32) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = round_tf32(v[j]);
         }
         if (active) {
           const bool full_chunk = (col0 + 32 <= ep.N);
@@ -345,44 +363,49 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   if (warp == 0) tmem_dealloc(tmem, L::kTmemCols);
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, bool TF32>
 static int launch_gemm(const GemmArgs& g, cudaStream_t stream) {
   using L = GemmSmem<BN, STAGES>;
   CUtensorMap map_a, map_b;
   TmaDims da, db;
+  constexpr int kEl = TF32 ? 4 : 2;          // operand element bytes
+  constexpr int kKb = TF32 ? 32 : 64;        // elements per 128-byte K-block
+  constexpr int kAl = 16 / kEl;              // elements per 16 bytes (TMA stride granularity)
   const int nb1 = g.nb1 > 0 ? g.nb1 : 1, nb2 = g.nb2 > 0 ? g.nb2 : 1;
-  const int kb_half = (g.K + 63) / 64;
-  if (g.split != 0) PRD_REQUIRE(g.K % 64 == 0, "gemm: split weights need K %% 64 == 0 (K=%d)", g.K);
+  const int kb_half = (g.K + kKb - 1) / kKb;
+  if (g.split != 0) PRD_REQUIRE(g.K % kKb == 0, "gemm: split weights need K %% %d == 0 (K=%d)", kKb, g.K);
+  PRD_REQUIRE(!(TF32 && g.c_fp16), "gemm: tf32 operands write fp32 results");
   auto fill = [&](TmaDims& d, long long rows, long long ld, long long bs1, long long bs2, int box_rows, bool is_split) {
     d.size[0] = (uint64_t)(is_split ? 2 * g.K : g.K);
     d.size[1] = (uint64_t)rows;
     d.size[2] = bs1 != 0 ? (uint64_t)nb1 : 1;
     d.size[3] = bs2 != 0 ? (uint64_t)nb2 : 1;
-    d.stride[0] = (uint64_t)ld * 2;
-    d.stride[1] = (uint64_t)(bs1 != 0 ? bs1 : ld * rows) * 2;
-    d.stride[2] = (uint64_t)(bs2 != 0 ? bs2 : ld * rows) * 2;
+    d.stride[0] = (uint64_t)ld * kEl;
+    d.stride[1] = (uint64_t)(bs1 != 0 ? bs1 : ld * rows) * kEl;
+    d.stride[2] = (uint64_t)(bs2 != 0 ? bs2 : ld * rows) * kEl;
     // dims of size 1 still need a 16-byte-multiple stride
     d.stride[1] = (d.stride[1] + 15) & ~15ull;
     d.stride[2] = (d.stride[2] + 15) & ~15ull;
-    d.box[0] = 64;
+    d.box[0] = kKb;
     d.box[1] = (uint32_t)box_rows;
     d.box[2] = 1;
     d.box[3] = 1;
   };
   PRD_REQUIRE(g.M > 0 && g.N > 0 && g.K > 0, "gemm: empty problem M=%d N=%d K=%d", g.M, g.N, g.K);
-  PRD_REQUIRE(g.lda % 8 == 0 && g.ldb % 8 == 0, "gemm: lda/ldb must be multiples of 8 halves (lda=%lld ldb=%lld)", g.lda, g.ldb);
-  PRD_REQUIRE((g.a_bs1 % 8 == 0) && (g.a_bs2 % 8 == 0) && (g.b_bs1 % 8 == 0) && (g.b_bs2 % 8 == 0), "gemm: batch strides must be multiples of 8 halves");
+  PRD_REQUIRE(g.lda % kAl == 0 && g.ldb % kAl == 0, "gemm: lda/ldb must be multiples of 16 bytes (lda=%lld ldb=%lld)", g.lda, g.ldb);
+  PRD_REQUIRE((g.a_bs1 % kAl == 0) && (g.a_bs2 % kAl == 0) && (g.b_bs1 % kAl == 0) && (g.b_bs2 % kAl == 0), "gemm: batch strides must be multiples of 16 bytes");
   fill(da, g.M, g.lda, g.a_bs1, g.a_bs2, 128, g.split == 2);
   fill(db, g.N, g.ldb, g.b_bs1, g.b_bs2, BN, g.split == 1);
-  if (make_tensor_map(&map_a, g.A, 2, 4, da, true)) return 1;
-  if (make_tensor_map(&map_b, g.B, 2, 4, db, true)) return 1;
+  if (make_tensor_map(&map_a, g.A, kEl, 4, da, true)) return 1;
+  if (make_tensor_map(&map_b, g.B, kEl, 4, db, true)) return 1;
   GemmEpilogue ep;
   ep.M = g.M; ep.N = g.N; ep.alpha = g.alpha; ep.bias = g.bias; ep.act = g.act;
   ep.rowscale = g.rowscale; ep.rs_bs1 = g.rs_bs1; ep.rs_bs2 = g.rs_bs2;
   ep.mul = g.mul; ep.ldmul = g.ldmul; ep.mul_bs1 = g.mul_bs1; ep.mul_bs2 = g.mul_bs2;
   ep.add = g.add; ep.ldadd = g.ldadd; ep.add_bs1 = g.add_bs1; ep.add_bs2 = g.add_bs2;
   ep.C = g.C; ep.ldc = g.ldc; ep.c_bs1 = g.c_bs1; ep.c_bs2 = g.c_bs2; ep.c_fp16 = g.c_fp16;
-  auto kern = gemm_f16_kernel<BN, STAGES>;
+  ep.mul_step = g.mul_step; ep.round_tf32 = g.round_tf32;
+  auto kern = gemm_f16_kernel<BN, STAGES, TF32>;
   static bool attr_set = false;
   if (!attr_set) {
     PRD_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
@@ -404,10 +427,14 @@ static int launch_gemm(const GemmArgs& g, cudaStream_t stream) {
 }
 
 int gemm_f16(const GemmArgs& g, cudaStream_t stream) {
-  if (g.N <= 64) return launch_gemm<64, 6>(g, stream);
+  if (g.tf32) {  // fp32 operands on kind::tf32 (the backward pass): same tiles, same pipeline
+    if (g.N <= 64) return launch_gemm<64, 6, true>(g, stream);
+    return launch_gemm<128, 5, true>(g, stream);
+  }
+  if (g.N <= 64) return launch_gemm<64, 6, false>(g, stream);
   if (g.N % 256 == 0 && (long long)((g.M + 127) / 128) * (g.N / 256) * (g.nb1 > 0 ? g.nb1 : 1) * (g.nb2 > 0 ? g.nb2 : 1) >= kNumSMs)
-    return launch_gemm<256, 4>(g, stream);
-  return launch_gemm<128, 5>(g, stream);
+    return launch_gemm<256, 4, false>(g, stream);
+  return launch_gemm<128, 5, false>(g, stream);
 }
 
 }  // namespace prd

@@ -11,9 +11,9 @@ namespace prd {
 struct GemmArgs {
   int M = 0, N = 0, K = 0;
   int nb1 = 1, nb2 = 1;  // two batch levels; blockIdx.z = i2 * nb1 + i1
-  const __half* A = nullptr;  // [M, K] row-major (K contiguous), leading dim lda (halves)
-  long long lda = 0, a_bs1 = 0, a_bs2 = 0;  // batch strides in halves; 0 = broadcast
-  const __half* B = nullptr;  // [N, K] row-major ("weight" layout)
+  const void* A = nullptr;  // [M, K] row-major (K contiguous), leading dim lda (elements: halves, or floats with tf32)
+  long long lda = 0, a_bs1 = 0, a_bs2 = 0;  // batch strides in elements; 0 = broadcast
+  const void* B = nullptr;  // [N, K] row-major ("weight" layout)
   long long ldb = 0, b_bs1 = 0, b_bs2 = 0;
   float alpha = 1.0f;
   const float* bias = nullptr;      // [N]
@@ -29,6 +29,9 @@ struct GemmArgs {
   int c_fp16 = 0;
   // 0: plain.  1: B is a weight stored as [hi | lo] along K (ldb >= 2K).  2: same for A.
   int split = 0;
+  int tf32 = 0;        // A, B are fp32 in memory, multiplied on kind::tf32 (producers round to nearest tf32); C fp32
+  int mul_step = 0;    // `mul` gates instead of scaling: v = mul > 0 ? v : 0
+  int round_tf32 = 0;  // round the fp32 result to nearest tf32 (it becomes a tf32 operand next)
 };
 // v = alpha*acc (+bias) -> act -> *rowscale -> *mul -> +add
 int gemm_f16(const GemmArgs& g, cudaStream_t stream);

@@ -8,9 +8,9 @@ kernels through libprd_sm100 (include/prd_denoiser.h); ``sample`` captures one r
 step as a CUDA graph and replays it ``num_steps`` times with the schedule, the noise and the
 step counter resident on the device.
 
-``q``, ``diffusion_loss``, ``validation_step`` and the forward half of ``training_step`` (reference model.py:471-549,
-226-247) run on the loss kernels (csrc/prd_loss.cu).  Not in this build: the backward pass through the network
-(``training_step`` refuses to run with autograd enabled), ESM loading.
+``q``, ``diffusion_loss``, ``validation_step`` and ``training_step`` (reference model.py:471-549, 226-247) run on the loss
+kernels (csrc/prd_loss.cu); with autograd enabled ``training_step`` returns a loss whose backward runs on the backward
+kernels (autograd.py, csrc/prd_bwd*.cu).  Not in this build: ESM loading (training_mode masking).
 """
 from __future__ import annotations
 
@@ -304,8 +304,16 @@ class ProteinReDiffModel(_Base):
         return noise_pred, seq_pred
 
     def forward(self, batch, z, seq_t, mask, t):
-        if torch.is_grad_enabled() and (z.requires_grad or seq_t.requires_grad):
-            raise NotImplementedError("backward kernels are not part of this build (SURVEY §8f item 1)")
+        """reference model.py:254-316.  With autograd enabled the evaluation is one autograd node over every trainable
+        parameter (autograd.DenoiserFunction: fused forward kernels + block checkpoints, prd_<op>_bwd kernels backward);
+        gradients with respect to z / seq_t are not produced (the reference's training never asks for them)."""
+        if torch.is_grad_enabled():
+            from .autograd import DenoiserFunction, trainable_parameters
+            params = [p for _, p in trainable_parameters(self)]
+            if params:
+                if z.requires_grad or seq_t.requires_grad:
+                    raise NotImplementedError("gradients with respect to z / seq_t are not part of this build")
+                return DenoiserFunction.apply(self, batch, z, seq_t, mask.contiguous(), t, *params)
         return self._denoise(batch, z, seq_t, mask.contiguous(), t)
 
     def sample_step(self, batch, z, seq_t, mask, t):
@@ -343,6 +351,16 @@ class ProteinReDiffModel(_Base):
         ops.remove_mean(self.cfg, noise_z, mask)
         ops.remove_mean(self.cfg, noise_seq, residue_mask)
         z_t, seq_t, seq_t1, _ = self.q(x, seq, t, noise_z, noise_seq, batch)
+        if torch.is_grad_enabled():
+            # training: (noise_pred, seq_pred) and the loss are autograd nodes backed by the backward kernels
+            from .autograd import LossFunction
+            noise_pred, seq_pred = self.forward(batch, z_t, seq_t, mask, t.contiguous())
+            d = detail if detail is not None else {}
+            loss = LossFunction.apply(noise_pred, seq_pred, self.cfg, noise_z, noise_seq, seq_t1, mask, residue_mask,
+                                      batch["residue_type"].contiguous(), t.contiguous(), self._sched_table(), d)
+            d.update(noise_pred=noise_pred, seq_pred=seq_pred, z_t=z_t, seq_t=seq_t, loss_graph=loss)
+            self._last_loss = loss
+            return d["diff_loss"]
         noise_pred, seq_pred = self._denoise(batch, z_t, seq_t, mask, t.contiguous())
         loss, diff, terms, d_noise, d_seq = ops.diffusion_loss(
             self.cfg, noise_pred, seq_pred, noise_z, noise_seq, seq_t1, mask, residue_mask,
@@ -363,17 +381,13 @@ class ProteinReDiffModel(_Base):
         d = detail if detail is not None else {}
         self.diffusion_loss(batch, x, mask, t, noise=noise, want_grads=want_grads, detail=d)
         d["t"] = t
-        return d["loss"].reshape(()), x.size(0)
+        return d.get("loss_graph", d["loss"].reshape(())), x.size(0)
 
     def training_step(self, batch, batch_idx, noise: Optional[Dict[str, torch.Tensor]] = None, detail: Optional[dict] = None):
-        """reference model.py:528-549: prepare_batch, t ~ randint(0, T), loss = mean(diff_loss / num_nodes), evaluated by
-        the CUDA kernels.  The objective and its gradient with respect to the network outputs (``detail``) are built; the
-        backward pass through the network is not, so the returned loss carries no autograd graph and
-        the call refuses to run with gradients enabled instead of returning a loss that silently cannot train."""
-        if torch.is_grad_enabled():
-            raise NotImplementedError(
-                "training_step computes the loss forward (and d loss / d outputs) only: the network's backward kernels are "
-                "not part of this build (SURVEY §8f item 1); call it under torch.no_grad(), or use validation_step")
+        """reference model.py:528-549: prepare_batch, t ~ randint(0, T), loss = mean(diff_loss / num_nodes).  With autograd
+        enabled the returned loss carries a graph whose backward runs on the prd_<op>_bwd kernels (autograd.py), so
+        ``loss.backward()`` fills ``.grad`` of every trainable parameter exactly like Lightning's backward does for the
+        reference; under ``torch.no_grad()`` only the objective (and, through ``detail``, d loss / d outputs) is evaluated."""
         loss, bs = self._objective(batch, batch_idx, noise, detail, want_grads=detail is not None)
         if hasattr(self, "log"):
             self.log("train_loss", loss, on_step=True, on_epoch=True, sync_dist=True, batch_size=bs)

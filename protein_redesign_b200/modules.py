@@ -398,8 +398,9 @@ class Denoiser(nn.Module):
 
     def forward(self, batch, z, t, single, pair, cache):
         """Same contract as the reference: `pair` is updated in place, z / t / cache pass through."""
-        if pair.requires_grad or single.requires_grad:
-            raise NotImplementedError("backward kernels are not part of this build (SURVEY §8f item 1)")
+        if torch.is_grad_enabled() and (pair.requires_grad or single.requires_grad):
+            raise NotImplementedError("Denoiser.forward is the inference entry; training differentiates the whole step "
+                                      "through ProteinReDiffModel.forward (autograd.DenoiserFunction)")
         mask = batch["residue_and_atom_mask"].contiguous()
         single = single.contiguous().clone()
         if not pair.is_contiguous():

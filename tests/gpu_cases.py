@@ -673,3 +673,293 @@ CASES = {
     "loss_paper_n72": lambda: case_loss(dataclasses.replace(syn.PAPER, mask_prob=0.15, num_steps=2000),
                                         ((12, 60), (9, 50)), seed=11),
 }
+
+
+# ------------------------------------------------------------------------------------------
+# backward pass: every prd_<op>_bwd against autograd through the oracle, then the whole training step
+# ------------------------------------------------------------------------------------------
+BWD_TOL = 3e-3   # per-tensor relative L2 of a gradient (tf32 operand products, fp32 accumulation and reductions)
+
+
+def _bwd_setup(cfg, seed, names_prefixes):
+    """(model on the GPU, P, G, oracle state-dict whose tensors under the given prefixes require grad)."""
+    from protein_redesign_b200 import autograd as ag  # noqa: F401
+    m, sd = _model(cfg, seed)
+    sd = {k: v.clone() for k, v in sd.items()}
+    for k in sd:
+        if any(k.startswith(p) for p in names_prefixes) and sd[k].is_floating_point() and k not in ("embed_beta.0.weight", "embed_dist.0.center"):
+            sd[k].requires_grad_()
+    P = {n: p.detach().contiguous() for n, p in m.named_parameters()}
+    G = {n: torch.zeros_like(p) for n, p in P.items()}
+    return m, sd, P, G
+
+
+ZERO_GRAD_FLOOR = 1e-4  # see _grad_rel
+
+
+def _grad_rel(got, want, global_norm):
+    """Relative L2 error of one gradient tensor.  Five tensors of the model have an analytically ZERO gradient (a constant
+    shift of attention logits along the key axis cancels in the softmax: FoldingBlock.attn_bias.1.bias x4,
+    SPAttention.linear_z.0.bias): what any implementation returns for them is rounding noise, so the denominator is
+    floored at ZERO_GRAD_FLOOR of the norm of the whole gradient."""
+    got, want = got.detach().double().cpu(), want.detach().double().cpu()
+    return float((got - want).norm() / max(float(want.norm()), ZERO_GRAD_FLOOR * global_norm, 1e-30))
+
+
+def _param_metrics(out, sd, G, tol=BWD_TOL):
+    req = {k: v for k, v in sd.items() if v.requires_grad}
+    for k, v in req.items():
+        assert v.grad is not None, k
+    gn = math.sqrt(sum(float(v.grad.double().norm()) ** 2 for v in req.values()))
+    for k, v in req.items():
+        out["dW:" + k] = (_grad_rel(G[k], v.grad, gn), tol)
+    return out
+
+
+def _rand_like(x, seed):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(x.shape, generator=g)
+
+
+def case_bwd_transition(cfg=syn.PAPER, B=2, N=40, seed=40, which="pair_fc"):
+    from protein_redesign_b200 import autograd as ag
+    prefix = _block_prefix() + which + "."
+    m, sd, P, G = _bwd_setup(cfg, seed, [prefix])
+    single, pair, _ = _pair_inputs(cfg, B, N, seed)
+    x = (pair if which == "pair_fc" else single).clone().requires_grad_()
+    out = x + ref.transition(sd, prefix, x)
+    dy = _rand_like(out, seed + 1)
+    out.backward(dy)
+    d = dy.to(DEV).contiguous()
+    ag.transition_bwd(cfg, P, G, prefix, x.detach().to(DEV).contiguous(), d)
+    torch.cuda.synchronize()
+    return _param_metrics({"dx": (rel(d, x.grad), BWD_TOL)}, sd, G)
+
+
+def case_bwd_triattn(cfg=syn.PAPER, B=2, N=40, mode="starting", seed=41, pad=5):
+    from protein_redesign_b200 import autograd as ag
+    prefix = _block_prefix() + f"pair_attn_{mode}."
+    m, sd, P, G = _bwd_setup(cfg, seed, [prefix])
+    _, pair, mask = _pair_inputs(cfg, B, N, seed, pad)
+    m2 = mask.unsqueeze(-1) * mask.unsqueeze(-2)
+    x = pair.clone().requires_grad_()
+    out = x + ref.triangle_attention(sd, prefix, x, m2, cfg.num_heads, mode)
+    dy = _rand_like(out, seed + 1)
+    out.backward(dy)
+    d = dy.to(DEV).contiguous()
+    ag.triangle_attention_bwd(cfg, P, G, prefix + "attn.", 1 if mode == "ending" else 0, pair.to(DEV).contiguous(), mask.to(DEV), d)
+    torch.cuda.synchronize()
+    return _param_metrics({"dx": (rel(d, x.grad), BWD_TOL)}, sd, G)
+
+
+def case_bwd_trimul(cfg=syn.PAPER, B=2, N=40, mode="outgoing", seed=42, pad=5):
+    from protein_redesign_b200 import autograd as ag
+    prefix = _block_prefix() + f"pair_mul_{mode}."
+    m, sd, P, G = _bwd_setup(cfg, seed, [prefix])
+    _, pair, mask = _pair_inputs(cfg, B, N, seed, pad)
+    m2 = mask.unsqueeze(-1) * mask.unsqueeze(-2)
+    x = pair.clone().requires_grad_()
+    out = x + ref.triangle_multiplication(sd, prefix, x, m2, mode)
+    dy = _rand_like(out, seed + 1)
+    out.backward(dy)
+    d = dy.to(DEV).contiguous()
+    ag.triangle_multiplication_bwd(cfg, P, G, prefix, 1 if mode == "incoming" else 0, pair.to(DEV).contiguous(), mask.to(DEV), d)
+    torch.cuda.synchronize()
+    return _param_metrics({"dx": (rel(d, x.grad), BWD_TOL)}, sd, G)
+
+
+def case_bwd_outer_linear(cfg=syn.PAPER, B=2, N=40, seed=43):
+    from protein_redesign_b200 import autograd as ag
+    prefix = _block_prefix() + "outer_linear."
+    m, sd, P, G = _bwd_setup(cfg, seed, [prefix])
+    single, pair, _ = _pair_inputs(cfg, B, N, seed)
+    s = single.clone().requires_grad_()
+    out = ref.outer_linear(sd, prefix, s)
+    dy = _rand_like(out, seed + 1)
+    out.backward(dy)
+    d_single = torch.zeros(B, N, cfg.single_dim, device=DEV)
+    ag.outer_linear_bwd(cfg, P, G, prefix, single.to(DEV).contiguous(), dy.to(DEV).contiguous(), d_single)
+    torch.cuda.synchronize()
+    return _param_metrics({"d_single": (rel(d_single, s.grad), BWD_TOL)}, sd, G)
+
+
+def case_bwd_single_attention(cfg=syn.PAPER, B=2, N=40, seed=44, pad=5):
+    from protein_redesign_b200 import autograd as ag
+    p = _block_prefix()
+    m, sd, P, G = _bwd_setup(cfg, seed, [p + "single_attn.", p + "attn_bias."])
+    single, pair, mask = _pair_inputs(cfg, B, N, seed, pad)
+    s, pr = single.clone().requires_grad_(), pair.clone().requires_grad_()
+    out = s + ref.gated_attention(sd, p + "single_attn.", s, mask, cfg.num_heads, ref.attn_bias_from_pair(sd, p, pr))
+    dy = _rand_like(out, seed + 1)
+    out.backward(dy)
+    d_single = dy.to(DEV).contiguous()
+    d_pair = torch.zeros_like(pair, device=DEV)
+    ag.single_attention_bwd(cfg, P, G, p, single.to(DEV).contiguous(), pair.to(DEV).contiguous(), mask.to(DEV), d_single, d_pair)
+    torch.cuda.synchronize()
+    return _param_metrics({"d_single": (rel(d_single, s.grad), BWD_TOL), "d_pair": (rel(d_pair, pr.grad), BWD_TOL)}, sd, G)
+
+
+def case_bwd_spattention(cfg=syn.PAPER, B=2, N=40, seed=45):
+    from protein_redesign_b200 import autograd as ag
+    m, sd, P, G = _bwd_setup(cfg, seed, ["Denoiser.SPAAttnBlock."])
+    single, pair, mask = _pair_inputs(cfg, B, N, seed)
+    s, pr = single.clone().requires_grad_(), pair.clone().requires_grad_()
+    out = ref.single_pair_attention(sd, s, pr, cfg.num_heads)
+    dy = _rand_like(out, seed + 1)
+    out.backward(dy)
+    d_single = dy.to(DEV).contiguous()
+    d_pair = torch.zeros_like(pair, device=DEV)
+    ag.spattention_bwd(cfg, P, G, single.to(DEV).contiguous(), pair.to(DEV).contiguous(), d_single, d_pair)
+    torch.cuda.synchronize()
+    return _param_metrics({"d_single": (rel(d_single, s.grad), BWD_TOL), "d_pair": (rel(d_pair, pr.grad), BWD_TOL)}, sd, G)
+
+
+def case_bwd_heads(cfg=syn.PAPER, B=2, N=40, seed=46, pad=5):
+    from protein_redesign_b200 import autograd as ag
+    m, sd, P, G = _bwd_setup(cfg, seed, ["weight_radial.", "seq_mlp."])
+    single, pair, mask = _pair_inputs(cfg, B, N, seed, pad)
+    z = _rand_like(torch.empty(B, N, 3), seed + 2)
+    s, pr = single.clone().requires_grad_(), pair.clone().requires_grad_()
+    noise = ref.coord_head(sd, 0.5 * (pr + pr.transpose(1, 2)), z, mask)
+    seq = ref.seq_head(sd, s)
+    dn, dsq = _rand_like(noise, seed + 3), _rand_like(seq, seed + 4)
+    (noise * dn).sum().backward()
+    (seq * dsq).sum().backward()
+    d_single = torch.empty(B, N, cfg.single_dim, device=DEV)
+    d_pair = torch.empty_like(pair, device=DEV)
+    ag.seq_head_bwd(cfg, P, G, single.to(DEV).contiguous(), dsq.to(DEV).contiguous(), d_single)
+    ag.coord_head_bwd(cfg, P, G, pair.to(DEV).contiguous(), z.to(DEV), mask.to(DEV), dn.to(DEV).contiguous(), d_pair)
+    torch.cuda.synchronize()
+    return _param_metrics({"d_single": (rel(d_single, s.grad), BWD_TOL), "d_pair": (rel(d_pair, pr.grad), BWD_TOL)}, sd, G)
+
+
+def case_bwd_embeddings(cfg=syn.PAPER, sizes=((9, 30), (12, 26)), seed=47):
+    """pair_embed_bwd + opm_project_bwd + single_embed_bwd: everything upstream of the trunk (reference model.py:332-361,
+    modules.py:391-397)."""
+    from protein_redesign_b200 import autograd as ag
+    m, sd, P, G = _bwd_setup(cfg, seed, ["Denoiser.opm.", "embed_"])
+    batch = syn.make_batch(cfg, list(sizes), seed=seed, two_chains=True)
+    z, seq_t, mask, t = syn.make_step_inputs(batch, cfg.num_steps, seed)
+    torch.manual_seed(seed)
+    pb = ref.prepare_batch(batch, cfg.mask_prob)
+    single = ref.embed_single(sd, pb, seq_t)
+    m2 = mask.unsqueeze(-1) * mask.unsqueeze(-2)
+    pair = ref.embed_pair_static(sd, pb, cfg.max_bond_distance, cfg.max_relpos) + ref.embed_pair_dynamic(sd, z, t, mask, cfg.num_steps) \
+        + m2.unsqueeze(-1) * ref.outer_product_update(sd, single, mask)
+    dp, ds = _rand_like(pair, seed + 1), _rand_like(single, seed + 2)
+    ((pair * dp).sum() + (single * ds).sum()).backward()
+    db = _to_dev(pb)
+    w = m._weights()
+    esm_emb, _ = m._static_embeddings(db)
+    single_dev = ops.single_embed(cfg, db["atom_feats"], db["atom_mask"], db["residue_mask"], seq_t.to(DEV), esm_emb, w["atom_tabs"], w["w_type"])
+    a, b = m.Denoiser.opm.project(cfg, single_dev, mask.to(DEV))
+    d_single = ds.to(DEV).contiguous()
+    d_a, d_b = ag.pair_embed_bwd(cfg, P, G, db, dp.to(DEV).contiguous(), z.to(DEV), mask.to(DEV), t.to(DEV), a, b)
+    ag.opm_project_bwd(cfg, P, G, single_dev, mask.to(DEV), d_a, d_b, d_single)
+    ag.single_embed_bwd(cfg, P, G, db, seq_t.to(DEV), d_single)
+    torch.cuda.synchronize()
+    return _param_metrics({}, sd, G)
+
+
+STEP_GRAD_TOL = 3e-2     # worst per-tensor relative L2 of a parameter gradient through the whole step (see case_train_step)
+STEP_GRAD_MEDIAN = 3e-3  # median over the 240 tensors
+
+
+def case_train_step(cfg, sizes, seed, golden=None, tol=STEP_GRAD_TOL, top=4, **batch_kw):
+    """training_step under autograd: loss.backward() through the CUDA backward kernels; every parameter gradient against
+    autograd through the oracle (per-tensor relative L2) and against the REFERENCE's gradient fingerprints (norm +
+    seeded random projection of all 240 tensors, tests/golden/loss_*.npz; bound 1e-3, the acceptance criterion).
+
+    Why the per-tensor L2 bound through the whole step is 3e-2 while every op's own backward meets 3e-3 (bwd_* cases): the
+    network has ReLU layers (single_fc, pair_fc, seq_mlp, weight_radial).  The forward activations differ from the fp32
+    oracle's by eps ~ 1e-4 (the step tolerance), so a fraction ~0.8 eps of the ReLU pre-activations has the other sign, and
+    each flipped element carries a full-size error in d(hidden): relative L2 ~ sqrt(0.8 eps) ~ 1e-2 on those layers'
+    gradients and, diluted, on everything upstream.  The errors are sparse and random-signed, so they vanish in the
+    fingerprints (norm, projection) and in any sum over rows; the reference's own training runs fp16 AMP (train.py:37),
+    whose eps ~ 1e-3 puts it at ~3e-2 by the same argument."""
+    m, sd = _model(cfg, seed)
+    m.train()
+    sdg = {k: (v.clone().requires_grad_() if v.is_floating_point() and k not in ("embed_beta.0.weight", "embed_dist.0.center") else v)
+           for k, v in sd.items()}
+    batch = syn.make_batch(cfg, list(sizes), seed=seed, with_positions=True, **batch_kw)
+    B, N = batch["atom_mask"].shape
+    g = torch.Generator().manual_seed(seed + 4242)
+    draws = {"z": torch.randn(B, N, 3, generator=g), "seq": torch.randn(B, N, 21, generator=g)}
+    it = iter([draws["z"], draws["seq"]])
+    torch.manual_seed(seed)
+    want_loss, _, _ = ref.training_loss(sdg, cfg, batch, randn_like=lambda x: next(it).clone())
+    want_loss.backward()
+    torch.manual_seed(seed)
+    with torch.enable_grad():
+        loss = m.training_step(_to_dev(batch), 0, noise=draws)
+        loss.backward()
+    torch.cuda.synchronize()
+    out = {"loss": (abs(float(loss) - float(want_loss.detach())) / abs(float(want_loss.detach())), STEP_TOL)}
+    grads = {n: p.grad for n, p in m.named_parameters() if p.requires_grad}
+    req = {k: v for k, v in sdg.items() if v.requires_grad}
+    gn = math.sqrt(sum(float(v.grad.double().norm()) ** 2 for v in req.values()))
+    errs = []
+    for k, v in req.items():
+        assert grads.get(k) is not None, f"no gradient for {k}"
+        errs.append((_grad_rel(grads[k], v.grad, gn), k))
+    errs.sort(reverse=True)
+    for e, k in errs[:top]:
+        out[f"grad_rel_l2[{k}]"] = (e, tol)
+    out["median_grad_rel_l2"] = (errs[len(errs) // 2][0], STEP_GRAD_MEDIAN)
+    out["tensors_without_grad"] = (float(240 - len(errs)), 0.0)
+    if golden is not None:
+        gp = torch.Generator().manual_seed(seed + 777)
+        gnorm = math.sqrt(sum(float(x) ** 2 for x in golden["grad_norms"]))
+        fw, fname = 0.0, ""
+        for n, want_norm, want_proj in zip([str(x) for x in golden["grad_names"]], golden["grad_norms"], golden["grad_projs"]):
+            grad = grads[n].detach().cpu()
+            dvec = torch.randn(grad.shape, generator=gp)
+            scale = max(float(want_norm), ZERO_GRAD_FLOOR * gnorm, 1e-12)
+            e = max(abs(float(grad.norm()) - float(want_norm)) / scale,
+                    abs(float((grad * dvec).sum()) - float(want_proj)) / (scale * float(dvec.norm())))
+            if e > fw:
+                fw, fname = e, n
+        out[f"reference_gradient_fingerprints[worst: {fname}]"] = (fw, 1e-3)
+    return out
+
+
+CASES.update({
+    "gemm_tf32": lambda: case_gemm_tf32(),
+    "gemm_tf32_batch_tails": lambda: case_gemm_tf32(200, 72, 100, nb1=3),
+    "bwd_pair_fc": lambda: case_bwd_transition(which="pair_fc"),
+    "bwd_single_fc": lambda: case_bwd_transition(which="single_fc"),
+    "bwd_triattn_starting": lambda: case_bwd_triattn(mode="starting"),
+    "bwd_triattn_ending": lambda: case_bwd_triattn(mode="ending"),
+    "bwd_triattn_n140": lambda: case_bwd_triattn(B=1, N=140, mode="ending", pad=9),
+    "bwd_trimul_outgoing": lambda: case_bwd_trimul(mode="outgoing"),
+    "bwd_trimul_incoming": lambda: case_bwd_trimul(mode="incoming"),
+    "bwd_trimul_n75": lambda: case_bwd_trimul(B=1, N=75, mode="incoming", pad=4),
+    "bwd_outer_linear": lambda: case_bwd_outer_linear(),
+    "bwd_single_attention": lambda: case_bwd_single_attention(),
+    "bwd_spattention": lambda: case_bwd_spattention(),
+    "bwd_heads": lambda: case_bwd_heads(),
+    "bwd_embeddings": lambda: case_bwd_embeddings(),
+    "bwd_embeddings_readme": lambda: case_bwd_embeddings(syn.README),
+    "train_step_readme_n40": lambda: case_train_step(dataclasses.replace(syn.README, mask_prob=0.15, num_steps=2000),
+                                                     ((8, 32), (6, 27)), 10),
+    "train_step_paper_n72": lambda: case_train_step(dataclasses.replace(syn.PAPER, mask_prob=0.15, num_steps=2000),
+                                                    ((12, 60), (9, 50)), 11),
+})
+
+
+def case_gemm_tf32(M=256, N=128, K=64, nb1=1, seed=0):
+    """fp32 operands on kind::tf32: operands pre-rounded to tf32 make every product exact, so only the fp32 accumulation
+    order differs from the float64 reference."""
+    g = torch.Generator().manual_seed(seed)
+
+    def r_tf32(x):  # round to nearest, ties away (cvt.rna): add half an ulp of the 10-bit mantissa, clear 13 bits
+        i = x.view(torch.int32)
+        return ((i + 0x1000) & ~0x1FFF).view(torch.float32)
+
+    a = r_tf32(torch.randn(1, nb1, M, K, generator=g))
+    b = r_tf32(torch.randn(1, nb1, N, K, generator=g))
+    want = torch.matmul(a.double(), b.double().transpose(-1, -2))
+    out = torch.full((1, nb1, M, N), float("nan"), dtype=torch.float32, device=DEV)
+    _lib.gemm_f16(a.to(DEV).contiguous(), b.to(DEV).contiguous(), out)
+    torch.cuda.synchronize()
+    return {"rel": (rel(out, want), 2e-6)}

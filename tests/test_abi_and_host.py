@@ -34,7 +34,7 @@ def test_library_exports_every_declared_symbol():
     missing = [s for s in sorted(syms) if not hasattr(lib, s)]
     assert not missing, missing
     assert sorted(header_ops) == sorted(_lib.OPS)
-    assert lib.prd_version() == 1
+    assert lib.prd_version() == 2
 
 
 def test_workspace_queries_run_without_gpu():
@@ -127,16 +127,15 @@ def test_checkpoint_round_trip_and_optimizer_glue(tmp_path):
     assert abs(opt["optimizer"].param_groups[0]["lr"] - m2.learning_rate / m2.warmup_steps) < 1e-12
 
 
-def test_training_step_needs_no_grad_and_cuda():
-    """No CPU fallback and no silent graph-less loss: training_step refuses autograd; under no_grad on CPU tensors the
-    CUDA-only ops raise."""
+def test_training_step_has_no_cpu_fallback():
+    """No CPU fallback: with or without autograd, training_step on CPU tensors fails loudly in the CUDA-only ops."""
     import pytest
     import torch
     from protein_redesign_b200 import synthetic as syn
     from protein_redesign_b200.model import ProteinReDiffModel
     m = ProteinReDiffModel(syn.TINY)
     batch = syn.make_batch(syn.TINY, [(3, 9)], seed=0, with_positions=True)
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(RuntimeError):
         m.training_step(dict(batch), 0)
     with torch.no_grad(), pytest.raises(RuntimeError):
         m.training_step(dict(batch), 0)

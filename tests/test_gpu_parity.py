@@ -34,6 +34,10 @@ CASE_NAMES = [
     "step_n512", "step_n512_b2_ragged", "step_n300", "step_n1024", "batch_rows_b8_n512", "trimul_n512_outgoing", "trimul_n512_incoming",
     "triattn_n512_ending", "outer_linear_n512", "pair_transition_n512", "heads_n512", "embeddings_n512", "denoiser_forward",
     "folding_block_forward", "predict_step_ema", "back_to_back_batches",
+    # round 2: backward pass (every prd_<op>_bwd vs autograd through the oracle)
+    "gemm_tf32", "gemm_tf32_batch_tails", "bwd_pair_fc", "bwd_single_fc", "bwd_triattn_starting", "bwd_triattn_ending", "bwd_triattn_n140",
+    "bwd_trimul_outgoing", "bwd_trimul_incoming", "bwd_trimul_n75", "bwd_outer_linear", "bwd_single_attention", "bwd_spattention",
+    "bwd_heads", "bwd_embeddings", "bwd_embeddings_readme", "train_step_paper_n72",
 ]
 
 
@@ -65,15 +69,14 @@ def test_training_objective_vs_oracle_and_reference_golden(tag, cfg_name, over, 
     _check(gc.case_loss(cfg, sizes, seed, golden=load_golden(f"loss_{tag}.npz"), **kw))
 
 
-def test_training_step_refuses_autograd():
-    """The backward pass through the network is not built: training_step must say so instead of returning a loss that
-    silently has no graph."""
-    from protein_redesign_b200 import synthetic as syn
+def test_training_step_gradients_vs_oracle_and_reference_fingerprints():
+    """loss.backward() through the CUDA backward kernels: all 240 parameter gradients against autograd through the oracle
+    and against the unmodified reference's gradient fingerprints (tests/golden/loss_readme_n40.npz)."""
+    import dataclasses
     gc = _cases()
-    m, _ = gc._model(syn.README, 0)
-    batch = gc._to_dev(syn.make_batch(syn.README, [(4, 12)], seed=0, with_positions=True))
-    with torch.enable_grad(), pytest.raises(NotImplementedError):
-        m.training_step(batch, 0)
+    from protein_redesign_b200 import synthetic as syn
+    cfg = dataclasses.replace(syn.README, mask_prob=0.15, num_steps=2000)
+    _check(gc.case_train_step(cfg, ((8, 32), (6, 27)), 10, golden=load_golden("loss_readme_n40.npz")))
 
 
 def test_cpu_tensor_is_rejected():
