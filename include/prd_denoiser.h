@@ -173,6 +173,16 @@ PRD_DECLARE_OP(diffusion_q)
  *       d_seq_pred (or NULL)] */
 PRD_DECLARE_OP(diffusion_loss)
 
+/* --- output post-processing -------------------------------------------------------- */
+/* generate.py:76-91 predict_seq / update_seq: tokens = argmax softmax(logits) (0 = 'X' at masked positions).
+ * in: [logits f32 B,N,21 | residue_mask B,N (or NULL)]   out: [tokens i64 B,N] */
+PRD_DECLARE_OP(decode_argmax)
+/* generate.py:176-195 + tmalign.py:23-49: rigid superposition of every sample onto a reference (d->mode = rows of the
+ * reference: 1 or B), RMSD and TM-score (normalised by the reference length) under the identity residue correspondence,
+ * for the sample and for its mirror image; aligned = t + pos @ R as in the reference.
+ * in: [pos f32 B,N,3 | ref f32 (1|B),N,3 | mask B,N]   out: [tm f32 B,2 | rmsd f32 B,2 | R f32 B,2,3,3 | t f32 B,2,3] */
+PRD_DECLARE_OP(kabsch)
+
 /* --- backward pass (reference: Lightning's backward through model.py:528-549 with per-block
  * checkpointing, modules.py:399-401) --------------------------------------------------------------------------
  * One prd_<op>_bwd per forward op, same uniform signature.  Conventions (csrc/prd_bwd_api.cu):

@@ -20,7 +20,7 @@ OPS = (
     "esm_embed", "single_embed", "pair_embed_static", "opm_project", "pair_embed", "spattention",
     "single_attention", "single_transition", "outer_linear", "triangle_multiplication",
     "triangle_attention", "pair_transition", "symmetrize", "coord_head", "seq_head", "remove_mean",
-    "sampler_update", "diffusion_q", "diffusion_loss",
+    "sampler_update", "diffusion_q", "diffusion_loss", "decode_argmax", "kabsch",
 )
 
 

@@ -286,6 +286,29 @@ def make_batch(
     return b
 
 
+def make_complex(cfg: DenoiserConfig, num_atoms: int, num_residues: int, seed: int = 0) -> Dict[str, object]:
+    """One featurised complex as ``ligand_to_data`` + ``protein_to_data`` return it (reference data.py:28-77): the
+    per-item input of ``collate_fn``.  ``residue_type`` is 0..19 here (collate_fn adds 1); the ``*_mol`` entries are
+    placeholders (RDKit objects in the reference)."""
+    g = torch.Generator().manual_seed(seed)
+    na, nr = num_atoms, num_residues
+    bm = torch.triu((torch.rand(na, na, generator=g) < 0.2).float(), 1)
+    bm = bm + bm.T
+    bf = torch.stack([torch.randint(0, v, (na, na), generator=g) for v in BOND_VOCAB], -1) * bm.long().unsqueeze(-1)
+    bd = torch.triu(torch.randint(0, 12, (na, na), generator=g), 1)
+    return {
+        "ligand_mol": f"ligand-{seed}", "num_atoms": na,
+        "atom_feats": torch.stack([torch.randint(0, v, (na,), generator=g) for v in ATOM_VOCAB], -1),
+        "atom_pos": torch.randn(na, 3, generator=g), "atom_mask": torch.ones(na),
+        "bond_feats": bf, "bond_mask": bm, "bond_distance": bd + bd.T,
+        "protein_mol": f"protein-{seed}", "num_residues": nr,
+        "residue_type": torch.randint(0, NUM_RESIDUE_CLASSES - 1, (nr,), generator=g), "residue_mask": torch.ones(nr),
+        "residue_chain_index": torch.zeros(nr, dtype=torch.int64), "residue_index": torch.arange(nr),
+        "residue_atom_pos": torch.randn(nr, 37, 3, generator=g), "residue_atom_mask": (torch.rand(nr, 37, generator=g) < 0.5).float(),
+        "residue_esm": torch.randn(nr, cfg.esm_dim, generator=g),
+    }
+
+
 def make_step_inputs(batch: Dict[str, torch.Tensor], num_steps: int, seed: int = 0):
     """Seeded (z, seq_t, mask, t) for one denoiser step.
 

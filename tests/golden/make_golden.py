@@ -51,6 +51,7 @@ def install_stubs() -> None:
             pass
 
     pl.LightningModule = LightningModule
+    pl.LightningDataModule = type("LightningDataModule", (), {})  # data.py:172 derives from it (never instantiated here)
     sys.modules["pytorch_lightning"] = pl
 
     te = types.ModuleType("torch_ema")
@@ -287,8 +288,26 @@ def gen_loss_case(tag, cfg, sizes, seed, n_total=None, two_chains=False):
           f" ({os.path.getsize(path) / 1024:.0f} KiB)")
 
 
+def gen_collate_case():
+    """collate_fn (data.py:80-142) on three synthetic complexes of different sizes: every tensor of the batch."""
+    if ONLY_NEW and os.path.exists(os.path.join(HERE, "collate.npz")):
+        return
+    install_stubs()
+    if REFERENCE_ROOT not in sys.path:
+        sys.path.insert(0, REFERENCE_ROOT)
+    from ProteinReDiff.data import collate_fn  # type: ignore
+
+    items = [syn.make_complex(syn.TINY, na, nr, seed=60 + i) for i, (na, nr) in enumerate([(5, 9), (3, 14), (7, 4)])]
+    batch = collate_fn(items)
+    out = {k: v.numpy() for k, v in batch.items() if isinstance(v, torch.Tensor)}
+    out["mol_lists"] = np.array([",".join(batch["ligand_mol"]), ",".join(batch["protein_mol"])])
+    np.savez_compressed(os.path.join(HERE, "collate.npz"), **out)
+    print("collate:", {k: v.shape for k, v in out.items()})
+
+
 def main():
     torch.set_num_threads(os.cpu_count() or 1)
+    gen_collate_case()
     # (1) tiny dims, every module probed, ragged batch with padding + two chains.
     gen_step_case("tiny_probes", syn.TINY, [(5, 14), (3, 9)], seed=1, n_total=22, two_chains=True, probes=True)
     # (2) README dims (BASELINE config 1 shape family), one ragged batch.

@@ -694,7 +694,7 @@ def _bwd_setup(cfg, seed, names_prefixes):
     return m, sd, P, G
 
 
-ZERO_GRAD_FLOOR = 1e-4  # see _grad_rel
+ZERO_GRAD_FLOOR = 1e-3  # see _grad_rel
 
 
 def _grad_rel(got, want, global_norm):
@@ -963,3 +963,111 @@ def case_gemm_tf32(M=256, N=128, K=64, nb1=1, seed=0):
     _lib.gemm_f16(a.to(DEV).contiguous(), b.to(DEV).contiguous(), out)
     torch.cuda.synchronize()
     return {"rel": (rel(out, want), 2e-6)}
+
+
+# ------------------------------------------------------------------------------------------
+# Lightning-free predict loop, GPU post-processing
+# ------------------------------------------------------------------------------------------
+def _kabsch_np(P, Q):
+    """float64 SVD Kabsch (row convention: aligned = t + P @ R) -> (R, t, rmsd)."""
+    import numpy as np
+    cp, cq = P.mean(0), Q.mean(0)
+    H = (P - cp).T @ (Q - cq)
+    U, S, Vt = np.linalg.svd(H)
+    d = np.sign(np.linalg.det(U @ Vt))
+    D = np.diag([1.0, 1.0, d])
+    R = U @ D @ Vt
+    t = cq - cp @ R
+    diff = t + P @ R - Q
+    return R, t, float(np.sqrt((diff ** 2).sum(-1).mean()))
+
+
+def case_postprocess(B=5, N=150, seed=50):
+    import numpy as np
+    from protein_redesign_b200 import postprocess as post
+    g = torch.Generator().manual_seed(seed)
+    out = {}
+    # ---- decode (reference generate.py:76-91) ----
+    logits = torch.randn(B, N, 21, generator=g)
+    rmask = torch.ones(B, N)
+    rmask[:, :7] = 0
+    rmask[1, N - 20:] = 0
+    tokens = post.decode_tokens(logits.to(DEV), rmask.to(DEV)).cpu()
+    want_tok = torch.argmax(torch.softmax(logits, dim=-1), dim=-1) * rmask.long()
+    out["tokens_exact"] = (float((tokens != want_tok).sum()), 0.0)
+    letters = ["X"] + post.RESIDUE_TYPES
+    want_seq = ["".join(letters[i] for i in row).lstrip("X").rstrip("X") for row in want_tok.tolist()]
+    out["sequences_exact"] = (float(sum(a != b for a, b in zip(post.trimmed_sequence(logits.to(DEV), rmask.to(DEV)), want_seq))), 0.0)
+    out["predict_seq_exact"] = (float(post.predict_seq(logits.to(DEV)) != [[letters[i] for i in row] for row in
+                                                                            torch.argmax(logits, -1).tolist()]), 0.0)
+    # ---- superposition (generate.py:176-195, tmalign.py:23-49) ----
+    ref = 10.0 * torch.randn(N, 3, generator=g, dtype=torch.float64)
+    mask = torch.ones(B, N)
+    mask[:, :7] = 0  # ligand tokens do not take part
+    mask[2, N - 30:] = 0
+    pos = torch.empty(B, N, 3, dtype=torch.float64)
+    for b in range(B):
+        q, _ = torch.linalg.qr(torch.randn(3, 3, generator=g, dtype=torch.float64))
+        if torch.det(q) < 0:
+            q[:, 0] = -q[:, 0]
+        pos[b] = (ref + (0.5 + b) * torch.randn(N, 3, generator=g, dtype=torch.float64)) @ q + 5.0 * torch.randn(1, 3, generator=g, dtype=torch.float64)
+    pos[3, :, 2] = -pos[3, :, 2]  # a mirror image: only the mirrored superposition can fit it
+    tm, rmsd, t, R, mirrored = post.superpose(pos.float().to(DEV), ref.float().to(DEV), mask.to(DEV))
+    torch.cuda.synchronize()
+    worst_r = worst_R = worst_tm = worst_fit = 0.0
+    for b in range(B):
+        sel = mask[b] > 0.5
+        P = pos[b][sel].numpy().copy()
+        Q = ref[sel].numpy()
+        if bool(mirrored[b]):
+            P[:, 2] = -P[:, 2]
+        Rw, tw, rw = _kabsch_np(P, Q)
+        L = int(sel.sum())
+        d0 = max(0.5, 1.24 * (L - 15) ** (1.0 / 3.0) - 1.8)
+        d2 = ((tw + P @ Rw - Q) ** 2).sum(-1)
+        tmw = float((1.0 / (1.0 + d2 / d0 ** 2)).sum() / L)
+        Rg = R[b].double().cpu().numpy()
+        if bool(mirrored[b]):
+            Rg = np.diag([1.0, 1.0, -1.0]) @ Rg  # back to the rotation that acts on the mirrored sample
+        worst_r = max(worst_r, abs(float(rmsd[b]) - rw) / rw)
+        worst_R = max(worst_R, float(np.abs(Rg - Rw).max()))
+        worst_tm = max(worst_tm, abs(float(tm[b]) - tmw))
+        # the returned (t, R) act on the ORIGINAL sample: aligned = t + pos @ R (generate.py:186)
+        al = t[b].double().cpu().numpy() + pos[b][sel].numpy() @ R[b].double().cpu().numpy()
+        worst_fit = max(worst_fit, abs(float(np.sqrt(((al - Q) ** 2).sum(-1).mean())) - rw) / rw)
+    out.update({"rmsd_rel": (worst_r, 1e-4), "rotation_maxabs": (worst_R, 1e-4), "tm_abs": (worst_tm, 1e-4),
+                "aligned_rmsd_rel": (worst_fit, 1e-4), "mirror_detected": (0.0 if bool(mirrored[3]) and not bool(mirrored[0]) else 1.0, 0.0)})
+    return out
+
+
+def case_predict_loop(seed=52, T=4):
+    """predict(model, dataloader) == Trainer.predict for generate.py:145-159: RepeatDataset + collate_fn + predict_step under
+    no_grad; the result of every batch equals a direct predict_step call with the same generator state."""
+    from torch.utils.data import DataLoader
+    from protein_redesign_b200.predict import RepeatDataset, collate_fn, predict
+    from protein_redesign_b200 import postprocess as post
+    cfg = dataclasses.replace(syn.README, num_steps=T, mask_prob=0.3)
+    m, sd = _model(cfg, seed)
+    item = syn.make_complex(cfg, 6, 26, seed=seed)
+    dl = DataLoader(RepeatDataset(item, 5), batch_size=2, collate_fn=collate_fn)
+    torch.manual_seed(seed)
+    torch.cuda.manual_seed(seed)
+    res = predict(m, dl)
+    torch.manual_seed(seed)
+    torch.cuda.manual_seed(seed)
+    direct = [m.predict_step({k: (v.to(DEV) if isinstance(v, torch.Tensor) else v) for k, v in b.items()}, i) for i, b in enumerate(dl)]
+    torch.cuda.synchronize()
+    same = all(torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) for a, b in zip(res, direct))
+    shapes = [tuple(p.shape) for p, _ in res] == [(2, 32, 3), (2, 32, 3), (1, 32, 3)]
+    finite = all(bool(torch.isfinite(p).all()) and bool(torch.isfinite(l).all()) for p, l in res)
+    pos = torch.cat([p for p, _ in res])
+    logits = torch.cat([l for _, l in res])
+    rmask = torch.cat([torch.zeros(5, 6), torch.ones(5, 26)], 1).to(DEV)
+    seqs = post.trimmed_sequence(logits, rmask)
+    tm, rmsd, t, R, mir = post.superpose(pos, pos[0], rmask)  # generate.py:171-175: the first sample as the reference
+    return {"equals_direct_predict_step": (0.0 if same else 1.0, 0.0), "shapes": (0.0 if shapes else 1.0, 0.0),
+            "finite": (0.0 if finite else 1.0, 0.0), "sequence_lengths": (float(sum(len(s) > 26 for s in seqs)), 0.0),
+            "self_tm_is_one": (abs(float(tm[0]) - 1.0), 1e-5), "self_rmsd_is_zero": (float(rmsd[0]), 1e-3)}
+
+
+CASES.update({"postprocess": lambda: case_postprocess(), "predict_loop": lambda: case_predict_loop()})

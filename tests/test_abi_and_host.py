@@ -139,3 +139,22 @@ def test_training_step_has_no_cpu_fallback():
         m.training_step(dict(batch), 0)
     with torch.no_grad(), pytest.raises(RuntimeError):
         m.training_step(dict(batch), 0)
+
+
+def test_collate_fn_matches_reference_golden():
+    """predict.collate_fn (reference data.py:80-142) bit-exactly against the unmodified reference (tests/golden/collate.npz,
+    generated by make_golden.py)."""
+    from protein_redesign_b200.predict import InferenceDataset, RepeatDataset, collate_fn
+    gold = load_golden("collate.npz")
+    items = [syn.make_complex(syn.TINY, na, nr, seed=60 + i) for i, (na, nr) in enumerate([(5, 9), (3, 14), (7, 4)])]
+    batch = collate_fn(items)
+    tensors = {k: v for k, v in batch.items() if isinstance(v, torch.Tensor)}
+    assert sorted(tensors) == sorted(k for k in gold if k != "mol_lists")
+    for k, v in tensors.items():
+        assert v.dtype == torch.from_numpy(gold[k]).dtype, k
+        assert np.array_equal(v.numpy(), gold[k]), k
+    assert ",".join(batch["ligand_mol"]) == str(gold["mol_lists"][0]) and ",".join(batch["protein_mol"]) == str(gold["mol_lists"][1])
+    # token order: ligand atoms, residues, padding; residue types shifted by +1
+    assert int(batch["residue_type"].min()) == 0 and int(batch["residue_type"].max()) <= 20
+    assert len(RepeatDataset(items[0], 5)) == 5 and RepeatDataset(items[0], 5)[3] is items[0]
+    assert len(InferenceDataset(items, 0)) == 3 and InferenceDataset(items, 0)[1] is items[1]

@@ -38,6 +38,8 @@ CASE_NAMES = [
     "gemm_tf32", "gemm_tf32_batch_tails", "bwd_pair_fc", "bwd_single_fc", "bwd_triattn_starting", "bwd_triattn_ending", "bwd_triattn_n140",
     "bwd_trimul_outgoing", "bwd_trimul_incoming", "bwd_trimul_n75", "bwd_outer_linear", "bwd_single_attention", "bwd_spattention",
     "bwd_heads", "bwd_embeddings", "bwd_embeddings_readme", "train_step_paper_n72",
+    # round 2: Lightning-free predict loop and GPU post-processing
+    "postprocess", "predict_loop",
 ]
 
 
