@@ -535,28 +535,34 @@ def run_train(args, dev, rank, local_rank, world, lib):
 
     cfg = dataclasses.replace(syn.PAPER, mask_prob=0.15, num_steps=2000)
     model = _make_model(cfg, dev, train=True)
-    sizes = TRAIN_SIZES[rank % len(TRAIN_SIZES)]
+    # every rank gets complexes of the same sizes (different content): the scaling run then measures the all-reduce, not
+    # a straggler with a longer complex; --train-sizes picks another entry of TRAIN_SIZES
+    sizes = TRAIN_SIZES[args.train_sizes % len(TRAIN_SIZES)]
     host = syn.make_batch(cfg, sizes, seed=700 + rank, with_positions=True)
     host = {k: (v.pin_memory() if isinstance(v, torch.Tensor) else v) for k, v in host.items()}
     h2d = sum(v.numel() * v.element_size() for v in host.values() if isinstance(v, torch.Tensor))
-    named = [(n, p) for n, p in model.named_parameters() if p.requires_grad]
-    flat = torch.zeros(sum(p.numel() for _, p in named), dtype=torch.float32, device=dev)
-    off = 0
-    for _, p in named:
-        p.grad = flat[off:off + p.numel()].view(p.shape)
-        off += p.numel()
+    from protein_redesign_b200.autograd import FlatGrads, TrainStepGraph, training_step_manual
+    grads = FlatGrads(model).attach()
+    flat = grads.flat
     loss_host = torch.empty((), dtype=torch.float32).pin_memory()
     torch.manual_seed(rank)
+    to_dev = lambda: {k: (v.to(dev, non_blocking=True) if isinstance(v, torch.Tensor) else v) for k, v in host.items()}
+    tsg = TrainStepGraph(model, to_dev(), grads) if args.train_mode == "graph" else None
 
     def step():
-        batch = {k: (v.to(dev, non_blocking=True) if isinstance(v, torch.Tensor) else v) for k, v in host.items()}
-        flat.zero_()
-        loss = model.training_step(batch, 0)
-        loss.backward()
+        batch = to_dev()
+        if args.train_mode == "autograd":   # the drop-in path: training_step + loss.backward() through autograd
+            flat.zero_()
+            loss = model.training_step(batch, 0)
+            loss.backward()
+        elif args.train_mode == "manual":   # same kernels, gradients written straight into the flat bucket
+            loss = training_step_manual(model, batch, grads)
+        else:                               # device side of the step replayed as one CUDA graph
+            loss = tsg.step(batch)
         if world > 1:
             dist.all_reduce(flat)
             flat.mul_(1.0 / world)
-        loss_host.copy_(loss.detach(), non_blocking=True)
+        loss_host.copy_(loss.detach().reshape(()), non_blocking=True)
 
     for _ in range(args.warmup):
         step()
@@ -592,7 +598,9 @@ def run_train(args, dev, rank, local_rank, world, lib):
                                        f"ragged complexes {sizes} (rank 0), gradient all-reduce of {flat.numel() * 4 / 1e6:.0f} MB fp32 inside "
                                        "the timed step", "global_batch": 2 * world, "parallelism": f"data-parallel x{world}"},
                 "e2e": {"value": world * 1e3 / ms_step, "unit": "steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
-                        "api": "ProteinReDiffModel.training_step + loss.backward(), pinned host batch copied every step"},
+                        "api": {"autograd": "ProteinReDiffModel.training_step + loss.backward()", "manual": "autograd.training_step_manual",
+                                "graph": "autograd.TrainStepGraph.step"}[args.train_mode] + ", pinned host batch copied every step"},
+                "train_mode": args.train_mode,
                 "gpu_launches": launches, "gpu_launches_per_step": launches // max(args.steps, 1), "clocks": clocks,
                 "loss": float(loss_host)}
         print(json.dumps(line))
@@ -717,6 +725,9 @@ def main():
     ap.add_argument("--no-ragged", action="store_true", help="skip the ragged (10 percent padding) block")
     ap.add_argument("--no-sample-parallel", action="store_true", help="skip the real 64-sample sharded run (config 3)")
     ap.add_argument("--sp-steps", type=int, default=8, help="diffusion steps of the sample-parallel run")
+    ap.add_argument("--train-mode", default="graph", choices=["autograd", "manual", "graph"],
+                    help="--workload train: drop-in autograd path / manual backward into a flat bucket / the same as one CUDA graph")
+    ap.add_argument("--train-sizes", type=int, default=0, help="--workload train: which entry of TRAIN_SIZES")
     ap.add_argument("--reference-b1", action="store_true", help="--impl reference: time one complex instead of the batch of 8")
     ap.add_argument("--profile-eager", action="store_true",
                     help="run the steps eagerly (no CUDA graph, no e2e / CPU legs): for ncu launch lists")

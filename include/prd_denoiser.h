@@ -212,6 +212,11 @@ PRD_DECLARE_BWD(pair_embed)               /* model.py:348-361, AF2_modules.py:53
 PRD_DECLARE_BWD(single_embed)             /* model.py:342-346,99-102 */
 #undef PRD_DECLARE_BWD
 
+/* Test hook of the weight-gradient reduction dW[n,k] += alpha sum_r dY[r,n] X[r,k] (db[n] += alpha sum_r dY[r,n], or NULL):
+ * mode 0 = dispatch as the backward ops do, 1 = never used, 2 = force the tcgen05 kernel (both operands MN-major tf32). */
+int prd_dw_acc(const float* dY, long long ldy, const float* X, long long ldx, long long R, int Nout, int K, float* dW,
+               long long ldw, float* db, float alpha, int mode, void* stream);
+
 /* Profiling hook used by bench.py: average duration (ms) of ONE named kernel ("triattn_flash",
  * "trimul_gemm", "pair_bias") over `iters` launches on the data a previous full op left in the
  * workspace; CUDA events on `stream`.  aux: mask (triattn_flash) / pair (pair_bias). */

@@ -7,6 +7,7 @@ swap, because writes through ``param.data`` leave ``_version`` untouched) and re
 """
 from __future__ import annotations
 
+import contextlib
 from typing import Callable, Sequence
 
 import torch
@@ -46,6 +47,33 @@ def invalidate_packed_weights() -> None:
     _weights_epoch += 1
 
 
+# "Repack in place" mode (autograd.TrainStepGraph): every PackCache.get() rebuilds its packed copies and writes them INTO
+# the tensors it already handed out, so that (a) a CUDA graph that captured those addresses reads the current weights on
+# every replay and (b) the packing itself is part of the captured graph.
+_repack_in_place = False
+
+
+@contextlib.contextmanager
+def repack_in_place():
+    global _repack_in_place
+    old, _repack_in_place = _repack_in_place, True
+    try:
+        yield
+    finally:
+        _repack_in_place = old
+
+
+def _copy_into(old, new):
+    if isinstance(old, torch.Tensor):
+        old.copy_(new)
+    elif isinstance(old, dict):
+        for k in old:
+            _copy_into(old[k], new[k])
+    elif isinstance(old, (list, tuple)):
+        for a, b in zip(old, new):
+            _copy_into(a, b)
+
+
 class PackCache:
     def __init__(self):
         self._key = None
@@ -53,6 +81,11 @@ class PackCache:
 
     def get(self, sources: Sequence[torch.Tensor], build: Callable[[], object]):
         key = tuple((t.data_ptr(), tensor_version(t), t.device) for t in sources) + (_weights_epoch,)
+        if _repack_in_place and self._value is not None:
+            with torch.no_grad():
+                _copy_into(self._value, build())
+            self._key = key
+            return self._value
         if key != self._key:
             for t in sources:
                 if not t.is_cuda:

@@ -263,3 +263,138 @@ class LossFunction(torch.autograd.Function):
     def backward(ctx, g):
         d_noise, d_seq = ctx.saved_tensors
         return (g * d_noise, g * d_seq) + (None,) * 10
+
+
+# --------------------------------------------------------------------------------------------------------------
+# training step without the autograd engine (Lightning's "manual optimization" shape): loss + gradients straight into one
+# flat fp32 buffer -- the bucket a data-parallel all-reduce sends -- and, optionally, the whole device side of the step
+# captured as ONE CUDA graph
+# --------------------------------------------------------------------------------------------------------------
+class FlatGrads:
+    """One contiguous fp32 buffer holding the gradient of every trainable parameter (in ``named_parameters`` order) with
+    a per-parameter view; ``attach()`` makes the views the parameters' ``.grad`` so optimisers see them."""
+
+    def __init__(self, model):
+        self.named = trainable_parameters(model)
+        dev = self.named[0][1].device
+        self.flat = torch.zeros(sum(p.numel() for _, p in self.named), dtype=torch.float32, device=dev)
+        self.views, off = {}, 0
+        for n, p in self.named:
+            self.views[n] = self.flat[off:off + p.numel()].view(p.shape)
+            off += p.numel()
+
+    def attach(self):
+        for n, p in self.named:
+            p.grad = self.views[n]
+        return self
+
+
+def _device_step(model, batch, x, mask, t, grads: FlatGrads, noise=None, detail=None):
+    """Everything of training_step that runs on the device (reference model.py:490-526, 538-541 + backward): noise draws,
+    q(), the network with checkpoints, the loss kernels, the backward kernels.  Fills ``grads`` and returns loss [1]."""
+    from .synthetic import NUM_RESIDUE_CLASSES  # noqa: F401
+    cfg = model.cfg
+    seq, residue_mask = batch["residue_one_hot"].to(torch.float32).contiguous(), batch["residue_mask"].contiguous()
+    noise_z = (noise["z"].to(x.device, torch.float32).clone() if noise is not None else torch.randn_like(x)).contiguous()
+    noise_seq = (noise["seq"].to(x.device, torch.float32).clone() if noise is not None else torch.randn_like(seq)).contiguous()
+    ops.remove_mean(cfg, noise_z, mask)
+    ops.remove_mean(cfg, noise_seq, residue_mask)
+    z_t, seq_t, seq_t1, _ = model.q(x, seq, t, noise_z, noise_seq, batch)
+    noise_pred, seq_pred, tape = forward_with_checkpoints(model, batch, z_t, seq_t, mask, t)
+    loss, diff, terms, d_noise, d_seq = ops.diffusion_loss(cfg, noise_pred, seq_pred, noise_z, noise_seq, seq_t1, mask, residue_mask,
+                                                           batch["residue_type"].contiguous(), t, model._sched_table(),
+                                                           want_grads=True)
+    grads.flat.zero_()
+    P = {n: p.detach().contiguous() for n, p in model.named_parameters()}
+    backward_from_checkpoints(model, tape, d_noise, d_seq, P, grads.views)
+    if detail is not None:
+        detail.update(loss=loss, diff_loss=diff, terms=terms, noise_pred=noise_pred, seq_pred=seq_pred, t=t)
+    return loss
+
+
+def training_step_manual(model, batch, grads: FlatGrads, batch_idx: int = 0, noise=None, detail=None) -> torch.Tensor:
+    """``training_step`` + ``loss.backward()`` in one call without the autograd engine: same host-side draws (prepare_batch's
+    CPU randperm, ``t ~ randint``) and the same kernels as the autograd path, gradients written straight into ``grads``
+    (no per-parameter accumulate kernels).  Returns the loss (0-d tensor)."""
+    if not model.setup_schedule:
+        model.run_setup_schedule()
+        model.setup_schedule = True
+    with torch.no_grad():
+        batch = model.prepare_batch(batch, batch_idx)
+        x, mask = batch["x"].contiguous(), batch["residue_and_atom_mask"].contiguous()
+        t = torch.randint(0, model.num_steps, size=(x.size(0),)).to(x.device)
+        return _device_step(model, batch, x, mask, t, grads, noise, detail).reshape(())
+
+
+class TrainStepGraph:
+    """The device side of one training step (noise draws, q(), network forward with checkpoints, loss, full backward into
+    the flat gradient buffer) captured as ONE CUDA graph for a fixed (B, N): ~1000 kernel launches replayed without any
+    host work in between.  Per step the host still does what the reference does on the host -- prepare_batch's CPU randperm
+    and ``t ~ randint`` (model.py:424-468, 534) -- and copies the results into the graph's static input buffers."""
+
+    _KEYS = ("atom_feats", "atom_mask", "residue_mask", "bond_mask", "bond_feats", "bond_distance", "residue_index",
+             "residue_chain_index", "residue_type", "residue_esm", "residue_one_hot", "residue_extra_mask",
+             "residue_inv_extra_mask", "x", "residue_and_atom_mask")
+
+    def __init__(self, model, example_batch, grads: FlatGrads, inject_noise: bool = False):
+        """``inject_noise``: the graph reads its noise draws from static buffers (``step(..., noise=...)`` fills them) instead
+        of drawing them from the CUDA generator -- for parity tests."""
+        self.model, self.grads = model, grads
+        if not model.setup_schedule:
+            model.run_setup_schedule()
+            model.setup_schedule = True
+        dev = grads.flat.device
+        with torch.no_grad():
+            prepared = model.prepare_batch(dict(example_batch))
+            self.static = {k: prepared[k].contiguous().clone() for k in self._KEYS}
+            B, N = self.static["atom_mask"].shape
+            self.shape = (B, N)
+            self.t = torch.zeros(B, dtype=torch.int64, device=dev)
+            self.noise = {"z": torch.zeros(B, N, 3, device=dev), "seq": torch.zeros(B, N, 21, device=dev)} if inject_noise else None
+            # every workspace (forward and backward ops) sized before capture, on the capture stream
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            from ._packing import repack_in_place
+            with torch.cuda.stream(side), repack_in_place():
+                self.ws = _reserve_all(model.cfg, B, N, dev)
+                for _ in range(2):  # warm-up on the capture stream (lazy kernel attributes, packed weights, allocator pools)
+                    model._static_key = None
+                    self.loss = _device_step(model, self.static, self.static["x"], self.static["residue_and_atom_mask"], self.t, grads, self.noise)
+                torch.cuda.synchronize(dev)
+                self.graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(self.graph, stream=side):
+                    # inside the graph: the fp16 weight packs are rebuilt IN PLACE from the current fp32 parameters (an
+                    # optimiser step between replays is picked up) and the step-invariant embeddings are recomputed from
+                    # the static batch buffers (their content changes every step)
+                    model._static_key = None
+                    self.loss = _device_step(model, self.static, self.static["x"], self.static["residue_and_atom_mask"], self.t, grads, self.noise)
+                model._static_key = None
+            torch.cuda.current_stream(dev).wait_stream(side)
+
+    def step(self, batch, batch_idx: int = 0, noise=None) -> torch.Tensor:
+        """prepare_batch + t on the host path, then one graph replay; returns the loss [1] (a static tensor of the graph)."""
+        model = self.model
+        with torch.no_grad():
+            prepared = model.prepare_batch(batch, batch_idx)
+            if tuple(prepared["atom_mask"].shape) != self.shape:
+                raise ValueError(f"TrainStepGraph was captured for (B, N) = {self.shape}, got {tuple(prepared['atom_mask'].shape)}")
+            for k in self._KEYS:
+                self.static[k].copy_(prepared[k], non_blocking=True)
+            self.t.copy_(torch.randint(0, model.num_steps, size=(self.shape[0],)), non_blocking=True)
+            if self.noise is not None:
+                if noise is None:
+                    raise ValueError("this graph was captured with inject_noise=True: pass noise={'z': ..., 'seq': ...}")
+                self.noise["z"].copy_(noise["z"], non_blocking=True)
+                self.noise["seq"].copy_(noise["seq"], non_blocking=True)
+            self.graph.replay()
+        return self.loss
+
+
+def _reserve_all(cfg, B: int, N: int, device):
+    """Workspace of the current stream sized for every forward AND backward op at (B, N)."""
+    import ctypes
+    lib = _lib.load()
+    d = make_dims(cfg, B, N)
+    need = max([_lib.workspace_bytes(op, d) for op in _lib.OPS] +
+               [int(getattr(lib, f"prd_{op}_bwd_workspace_bytes")(ctypes.byref(d))) for op in _lib.OPS_BWD])
+    return _lib.Workspace.reserve(torch.device(device), need)

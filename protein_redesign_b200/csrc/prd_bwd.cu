@@ -3,9 +3,13 @@
 // (cited per kernel), differentiated by hand.
 #include "prd_bwd.h"
 
+#include <stdlib.h>
+
 #include "prd_common.cuh"
 
 namespace prd {
+
+int bw_colsum(const float* dY, long long ldy, long long R, int Nout, float* db, float alpha, cudaStream_t s);
 
 namespace {
 constexpr float kLnEps = 1e-5f;
@@ -184,6 +188,11 @@ __global__ void __launch_bounds__(256) bw_dw_acc_kernel(const float* __restrict_
 int bw_dw_acc(const float* dY, long long ldy, const float* X, long long ldx, long long R, int Nout, int K, float* dW,
               long long ldw, float* db, float alpha, cudaStream_t s) {
   if (R <= 0) return 0;
+  static const bool simt_only = getenv("PRD_DW_SIMT") && getenv("PRD_DW_SIMT")[0] == '1';  // A/B switch
+  if (!simt_only && bw_dw_tc_applies(dY, ldy, X, ldx, R)) {
+    if (db != nullptr && bw_colsum(dY, ldy, R, Nout, db, alpha, s)) return 1;
+    return bw_dw_tc(dY, ldy, X, ldx, R, Nout, K, dW, ldw, alpha, s);
+  }
   const int gx = (K + 63) / 64, gy = (Nout + 63) / 64;
   long long want = (148LL * 4 + gx * gy - 1) / (gx * gy);  // ~4 CTAs per SM in total
   long long chunks = (R + 255) / 256;
@@ -1070,7 +1079,7 @@ __global__ void bw_rbf_rows_kernel(const float* __restrict__ z, const float* __r
     const long long bj = b * N + (r - bi * N);
     const float dx = z[bi * 3] - z[bj * 3], dy = z[bi * 3 + 1] - z[bj * 3 + 1], dz = z[bi * 3 + 2] - z[bj * 3 + 2];
     const float d = sqrtf(dx * dx + dy * dy + dz * dz) - centers[k];
-    rbf[idx] = expf(-scale * d * d);
+    rbf[idx] = round_tf32(expf(-scale * d * d));
   }
 }
 int bw_rbf_rows(const float* z, const float* centers, float scale, int B, int N, int DD, float* rbf, cudaStream_t s) {
@@ -1235,8 +1244,8 @@ __global__ void __launch_bounds__(128) bw_single_embed_bwd_kernel(const float* _
     const float* wr = w_type + (long long)c * 21;
 #pragma unroll
     for (int k = 0; k < 21; ++k) ty += wr[k] * sLn[k];
-    d_ty[tok * CS + c] = ty > 0.f ? rm * d : 0.f;
-    d_esm[tok * CS + c] = rm * d;
+    d_ty[tok * CS + c] = ty > 0.f ? round_tf32(rm * d) : 0.f;
+    d_esm[tok * CS + c] = round_tf32(rm * d);
   }
 }
 int bw_single_embed_bwd(const float* d_single, const int64_t* atom_feats, const float* atom_mask, const float* residue_mask,

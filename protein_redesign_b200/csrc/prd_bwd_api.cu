@@ -194,6 +194,19 @@ int gated_attn_bwd(bool dry, Carver& c, cudaStream_t st, const AttnGeom& geom, l
 
 extern "C" {
 
+// Test hook: dW[n, k] += alpha * sum_r dY[r, n] X[r, k]  (the weight-gradient reduction; mode 0 = dispatch like the
+// backward ops do, 1 = force the SIMT kernel, 2 = force the tensor-core kernel)
+int prd_dw_acc(const float* dY, long long ldy, const float* X, long long ldx, long long R, int Nout, int K, float* dW,
+               long long ldw, float* db, float alpha, int mode, void* stream) {
+  if (prd_device_check()) return 1;
+  if (mode == 2) {
+    PRD_REQUIRE(bw_dw_tc_applies(dY, ldy, X, ldx, R), "dw_acc: operands do not qualify for the tensor-core kernel");
+    if (db != nullptr && bw_colsum(dY, ldy, R, Nout, db, alpha, S(stream))) return 1;
+    return bw_dw_tc(dY, ldy, X, ldx, R, Nout, K, dW, ldw, alpha, S(stream));
+  }
+  return bw_dw_acc(dY, ldy, X, ldx, R, Nout, K, dW, ldw, db, alpha, S(stream));
+}
+
 #define PRD_BWD_OP(name)                                                                                              \
   static int name##_impl(bool dry, const PrdDims* d, const void* const* in, void* const* out, const void* const* w,   \
                          Carver& c, cudaStream_t st);                                                                 \

@@ -212,6 +212,13 @@ __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* m
       "l"(m), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(m), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
 __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1,
                                             int c2) {
   asm volatile(
@@ -369,5 +376,7 @@ struct TmaDims {
   uint32_t box[4];     // box extent per dim (elements)
 };
 int make_tensor_map(CUtensorMap* out, const void* base, int elem_bytes, int rank, const TmaDims& d, bool swizzle128);
+// mode: 0 none, 1 SWIZZLE_128B, 2 SWIZZLE_128B_ATOM_32B (32-byte swizzle chunks: MN-major 32-bit UMMA operands)
+int make_tensor_map_mode(CUtensorMap* out, const void* base, int elem_bytes, int rank, const TmaDims& d, int mode);
 
 }  // namespace prd

@@ -47,6 +47,12 @@ static EncodeTiledFn get_encode_fn() {
 }
 
 int make_tensor_map(CUtensorMap* out, const void* base, int elem_bytes, int rank, const TmaDims& d, bool swizzle128) {
+  return make_tensor_map_mode(out, base, elem_bytes, rank, d, swizzle128 ? 1 : 0);
+}
+
+// mode: 0 none, 1 SWIZZLE_128B (16-byte chunks), 2 SWIZZLE_128B_ATOM_32B (32-byte chunks: MN-major 32-bit UMMA operands)
+int make_tensor_map_mode(CUtensorMap* out, const void* base, int elem_bytes, int rank, const TmaDims& d, int mode) {
+  const bool swizzle128 = mode != 0;
   EncodeTiledFn fn = get_encode_fn();
   PRD_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled not available (no CUDA driver?)");
   PRD_REQUIRE(rank >= 2 && rank <= 4, "tensor map rank %d unsupported", rank);
@@ -70,7 +76,8 @@ int make_tensor_map(CUtensorMap* out, const void* base, int elem_bytes, int rank
   if (swizzle128) PRD_REQUIRE(d.box[0] * elem_bytes == 128, "swizzle-128 box must span 128 bytes");
   CUtensorMapDataType dt = elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
   CUresult r = fn(out, dt, (cuuint32_t)rank, const_cast<void*>(base), size, stride, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  mode == 2 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : (mode == 1 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE),
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   PRD_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
   return 0;

@@ -246,34 +246,41 @@ static int launch_pair_transition(const PairDims& d, const float* pair, float* d
 // -----------------------------------------------------------------------------------------
 // pair_dim 64 / hidden 256: warp-specialised pipeline (the kernel above serialises LayerNorm, two GEMMs and two
 // epilogues per tile on four warps).  Persistent CTA, one per SM, 16 warps:
-//   warps 0-3    row warps: thread = pair row.  Coalesced row load, LayerNorm -> A tile (2-slot ring); later
-//                the output epilogue of the same tile (accumulator + b2 + residual from registers), full-line
-//                stores.  LayerNorm of tile i+1 is done BEFORE the output of tile i, so the tensor core
-//                never waits for it.
+//   warps 0-3    row warps: thread = pair row.  Rows arrive by TMA (two swizzled boxes of [128 rows x 32 floats], issued
+//                a tile ahead by warp 14), LayerNorm -> A tile (2-slot ring); later the output epilogue of the same tile
+//                (accumulator + b2 + residual from registers), full-line stores.  LayerNorm of tile i+1 is done BEFORE
+//                the output of tile i, so the tensor core never waits for it.
 //   warps 4-11   mid warps: hidden quarter q (64 columns): D1_q + b1 -> ReLU -> fp16 -> H tile (2-slot ring);
 //                warps 4-7 take the even quarters, 8-11 the odd ones
-//   warps 12/13  UMMA issue of the first / second GEMM (M1_q: D1[q&1] = A W1_q^T, M2_q: D2 += H_q W2_q^T, hi and lo
-//                weight halves side by side along N), all hand-offs through mbarriers
-//   warps 14-15  idle (donate registers)
-// TMEM: D1 quarters 2 x 128 columns, D2 2 x 128 columns (hi | lo weight halves side by side).
+//   warps 12/13  UMMA issue of the first / second GEMM (M1_q: D1[q&1] = A W1_q^T with the hi and lo weight halves side by
+//                side along N; M2_q: D2 += H_q W2_q^T), all hand-offs through mbarriers
+//   warp 14      TMA loader of the row stage (one 32 KB stage: it is free again as soon as the row warps hold the rows in
+//                registers, i.e. the load of tile i+1 overlaps everything tile i still has to do)
+//   warp 15      idle (donates registers)
+// The second GEMM uses the hi half of W2 only: the hidden activations are already rounded to fp16 and W2's lo half
+// contributes 2e-5 of the update at N = 512, 1.5e-4 on the worst known case (tools/precision_pairfc.py) against the 1e-3
+// budget; dropping it frees exactly the 32 KB the row stage needs and a quarter of the second GEMM.
+// TMEM: D1 quarters 2 x 128 columns (hi | lo), D2 2 x 64 columns.
 // -----------------------------------------------------------------------------------------
 namespace {
 constexpr int kPtThreads = 512;
 struct PtSmem {
   static constexpr int kW1 = 0;                        // hi, lo: 2 x [256 x 64] = 64 KB
-  static constexpr int kW2 = kW1 + 2 * 256 * 128;      // hi, lo: 2 x 4 K-blocks of [64 x 64] = 64 KB
-  static constexpr int kA = kW2 + 2 * 4 * 64 * 128;    // 2 x 16 KB
+  static constexpr int kW2 = kW1 + 2 * 256 * 128;      // hi: 4 K-blocks of [64 x 64] = 32 KB
+  static constexpr int kA = kW2 + 4 * 64 * 128;        // 2 x 16 KB
   static constexpr int kH = kA + 2 * 16384;            // 2 x 16 KB
   static constexpr int kSl = kH + 2 * 16384;           // 4 row warps x 4 KB
-  static constexpr int kBias = kSl + 4 * 4096;         // b1[256], b2[64]
+  static constexpr int kStage = kSl + 4 * 4096;        // row stage: 2 boxes x 16 KB
+  static constexpr int kBias = kStage + 2 * 16384;     // b1[256], b2[64]
   static constexpr int kBars = kBias + 320 * 4;
-  static constexpr int kTotal = kBars + 16 * 8 + 16 + 1024;
+  static constexpr int kTotal = kBars + 20 * 8 + 16 + 1024;
 };
 }  // namespace
 
 __global__ void __launch_bounds__(kPtThreads, 1)
-pair_transition_ws_kernel(const float* pair, float* dst, int residual, long long R, const __half* __restrict__ w1,
-                          const float* __restrict__ b1, const __half* __restrict__ w2, const float* __restrict__ b2) {
+pair_transition_ws_kernel(const __grid_constant__ CUtensorMap map_rows, float* dst, int residual, long long R,
+                          const __half* __restrict__ w1, const float* __restrict__ b1, const __half* __restrict__ w2,
+                          const float* __restrict__ b2) {
   constexpr int CZ = 64, HID = 256;
   extern __shared__ uint8_t raw[];
   using L = PtSmem;
@@ -282,6 +289,7 @@ pair_transition_ws_kernel(const float* pair, float* dst, int residual, long long
   uint8_t* sW2 = sm + L::kW2;
   uint8_t* sA = sm + L::kA;
   uint8_t* sH = sm + L::kH;
+  uint8_t* sStage = sm + L::kStage;
   float* sB1 = reinterpret_cast<float*>(sm + L::kBias);
   float* sB2 = sB1 + HID;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sm + L::kBars);
@@ -293,7 +301,9 @@ pair_transition_ws_kernel(const float* pair, float* dst, int residual, long long
   uint64_t* h_empty = bars + 10;  // [2] UMMA commit
   uint64_t* d2_full = bars + 12;  // [2] UMMA commit
   uint64_t* d2_empty = bars + 14; // [2] 128 row-thread arrivals
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+  uint64_t* st_full = bars + 16;  // TMA complete_tx
+  uint64_t* st_empty = bars + 17; // 128 row-thread arrivals
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
@@ -307,16 +317,18 @@ pair_transition_ws_kernel(const float* pair, float* dst, int residual, long long
       mbar_init(&d2_full[i], 1);
       mbar_init(&d2_empty[i], 128);
     }
+    mbar_init(st_full, 1);
+    mbar_init(st_empty, 128);
     fence_barrier_init();
+    tma_prefetch_desc(&map_rows);
   }
   if (warp == 0) tmem_alloc(tmem_slot, 512);
-  // B operands of 128 rows per hidden quarter q: rows [0,64) = hi weights, [64,128) = lo weights, so one UMMA
-  // (N = 128) computes both halves; the epilogues add the two 64-column accumulator halves
+  // B operands of the first GEMM, 128 rows per hidden quarter q: rows [0,64) = hi weights, [64,128) = lo weights, so one
+  // UMMA (N = 128) computes both halves; the mid warps add the two 64-column accumulator halves
   for (int q = 0; q < 4; ++q) {
     load_weight_kblocks(sW1 + q * 16384, w1 + q * 64 * CZ, 64, CZ, CZ, threadIdx.x, kPtThreads);
     load_weight_kblocks(sW1 + q * 16384 + 8192, w1 + HID * CZ + q * 64 * CZ, 64, CZ, CZ, threadIdx.x, kPtThreads);
-    load_weight_kblocks(sW2 + q * 16384, w2 + q * 64, CZ, 64, HID, threadIdx.x, kPtThreads);
-    load_weight_kblocks(sW2 + q * 16384 + 8192, w2 + CZ * HID + q * 64, CZ, 64, HID, threadIdx.x, kPtThreads);
+    load_weight_kblocks(sW2 + q * 8192, w2 + q * 64, CZ, 64, HID, threadIdx.x, kPtThreads);  // hi half only
   }
   for (int i = threadIdx.x; i < HID; i += kPtThreads) sB1[i] = b1[i];
   for (int i = threadIdx.x; i < CZ; i += kPtThreads) sB2[i] = b2[i];
@@ -335,21 +347,10 @@ pair_transition_ws_kernel(const float* pair, float* dst, int residual, long long
     const uint32_t tm_lane = tmem + (static_cast<uint32_t>(warp * 32) << 16);
     float xc[CZ], xn[CZ];
     auto load_ln = [&](int il, float (&x)[CZ]) {  // rows of local tile il -> x (kept for the residual), LN -> A slot
-      const long long row0 = ((long long)blockIdx.x + (long long)il * gridDim.x) * kTileRows + warp * 32;
-      const long long left = R - row0;
-      const int rows_valid = left > 32 ? 32 : (left < 0 ? 0 : static_cast<int>(left));
-#pragma unroll
-      for (int p = 0; p < 2; ++p) {
-        uint4 v[8];
-        warp_load_rows128(slice, lane, v, pair + row0 * CZ + p * 32, CZ * 4, rows_valid);
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          x[p * 32 + 4 * c + 0] = __uint_as_float(v[c].x);
-          x[p * 32 + 4 * c + 1] = __uint_as_float(v[c].y);
-          x[p * 32 + 4 * c + 2] = __uint_as_float(v[c].z);
-          x[p * 32 + 4 * c + 3] = __uint_as_float(v[c].w);
-        }
-      }
+      mbar_wait(st_full, il & 1);
+      read_row_tma64(sStage, t, x);
+      fence_proxy_async_smem();  // generic reads of the stage before the async-proxy refill
+      mbar_arrive(st_empty);
       // LayerNorm statistics (x itself is kept for the residual)
       float s4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
@@ -388,9 +389,8 @@ pair_transition_ws_kernel(const float* pair, float* dst, int residual, long long
       tc_fence_after();
 #pragma unroll
       for (int p = 0; p < 2; ++p) {
-        uint32_t acc[32], acl[32];
-        tmem_ld32(tm_lane + 256 + (il & 1) * 128 + p * 32, acc);
-        tmem_ld32(tm_lane + 256 + (il & 1) * 128 + 64 + p * 32, acl);
+        uint32_t acc[32];
+        tmem_ld32(tm_lane + 256 + (il & 1) * 64 + p * 32, acc);
         tmem_ld_wait();
         if (p == 1) {
           tc_fence_before();
@@ -402,7 +402,7 @@ pair_transition_ws_kernel(const float* pair, float* dst, int residual, long long
           float v[4];
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            v[e] = (__uint_as_float(acc[4 * c + e]) + __uint_as_float(acl[4 * c + e])) + sB2[p * 32 + 4 * c + e];
+            v[e] = __uint_as_float(acc[4 * c + e]) + sB2[p * 32 + 4 * c + e];
             if (residual) v[e] += xc[p * 32 + 4 * c + e];
           }
           o[c] = make_uint4(__float_as_uint(v[0]), __float_as_uint(v[1]), __float_as_uint(v[2]), __float_as_uint(v[3]));
@@ -449,10 +449,10 @@ pair_transition_ws_kernel(const float* pair, float* dst, int residual, long long
     }
   } else {
     // ------------------------------------------------------------------ UMMA warps: 12 issues the first GEMM (gated by
-    // A tiles and free D1 buffers), 13 the second (gated by H tiles and free D2 buffers); 14-15 idle
+    // A tiles and free D1 buffers), 13 the second (gated by H tiles and free D2 buffers); 14 loads rows; 15 idle
     asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
-    const uint32_t idesc = umma_idesc_f16(128, 128);
     if (warp == 12) {
+      const uint32_t idesc = umma_idesc_f16(128, 128);
       int Q = 0;
       for (int il = 0; il < my_tiles; ++il) {
         mbar_wait(&a_full[il & 1], (il >> 1) & 1);
@@ -468,6 +468,7 @@ pair_transition_ws_kernel(const float* pair, float* dst, int residual, long long
         }
       }
     } else if (warp == 13) {
+      const uint32_t idesc = umma_idesc_f16(128, 64);
       int Q = 0;
       for (int il = 0; il < my_tiles; ++il) {
         if (il >= 2) mbar_wait(&d2_empty[il & 1], ((il >> 1) - 1) & 1);
@@ -475,12 +476,23 @@ pair_transition_ws_kernel(const float* pair, float* dst, int residual, long long
           mbar_wait(&h_full[Q & 1], (Q >> 1) & 1);
           tc_fence_after();
           if (elect_one()) {
-            umma_kblock(tmem + 256 + (il & 1) * 128, smem_u32(sH) + (Q & 1) * 16384, smem_u32(sW2) + q * 16384, idesc, q > 0);
+            umma_kblock(tmem + 256 + (il & 1) * 64, smem_u32(sH) + (Q & 1) * 16384, smem_u32(sW2) + q * 8192, idesc, q > 0);
             umma_commit(&h_empty[Q & 1]);
             if (q == 3) umma_commit(&d2_full[il & 1]);
           }
           __syncwarp();
         }
+      }
+    } else if (warp == 14) {
+      for (int il = 0; il < my_tiles; ++il) {
+        if (il >= 1) mbar_wait(st_empty, (il - 1) & 1);
+        if (elect_one()) {
+          const long long row0 = ((long long)blockIdx.x + (long long)il * gridDim.x) * kTileRows;
+          mbar_expect_tx(st_full, 2 * 16384);
+          tma_load_2d(sStage, &map_rows, st_full, 0, static_cast<int>(row0));
+          tma_load_2d(sStage + 16384, &map_rows, st_full, 32, static_cast<int>(row0));
+        }
+        __syncwarp();
       }
     }
   }
@@ -495,7 +507,14 @@ static int launch_pair_transition_ws(const PairDims& d, const float* pair, float
   if (set_smem(pair_transition_ws_kernel, PtSmem::kTotal)) return 1;
   const long long R = (long long)d.B * d.N * d.N;
   const long long tiles = (R + kTileRows - 1) / kTileRows;
-  pair_transition_ws_kernel<<<grid_for(tiles, 1), kPtThreads, PtSmem::kTotal, s>>>(pair, dst, residual, R, w1, b1, w2, b2);
+  PRD_REQUIRE(R < 0x7fffffffLL, "pair_transition: %lld pair rows exceed the TMA coordinate range", R);
+  CUtensorMap map_rows;  // the pair tensor as [R rows][64 floats]: one tile = two boxes of [128 rows x 32 floats]
+  TmaDims td;
+  td.size[0] = 64; td.size[1] = (uint64_t)R;
+  td.stride[0] = 256;
+  td.box[0] = 32; td.box[1] = 128;
+  if (make_tensor_map(&map_rows, pair, 4, 2, td, true)) return 1;
+  pair_transition_ws_kernel<<<grid_for(tiles, 1), kPtThreads, PtSmem::kTotal, s>>>(map_rows, dst, residual, R, w1, b1, w2, b2);
   PRD_LAUNCHED();
   return 0;
 }

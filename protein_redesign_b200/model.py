@@ -211,12 +211,14 @@ class ProteinReDiffModel(_Base):
         srcs += [e.weight for e in self.embed_bond_feats.embeddings]
 
         def build():
+            if getattr(self, "_rbf_dmax", None) is None and srcs[4].is_cuda:
+                self._rbf_dmax = float(srcs[4].max()) + 0.52  # centres are a fixed buffer: read once (host sync)
             w = {
                 "esm": [split_k(srcs[0])],
                 "w_type": f32(srcs[1]),
                 "pair_dyn": [f32(srcs[2]), f32(srcs[3]), split_rows(srcs[5]), f32(srcs[4])],
                 # d -> W_dist rbf(d) tabulated once per weight version (PRD_RBF_LUT=0 keeps the per-pair RBF GEMM)
-                "rbf_lut": ops.rbf_lut_build(self.cfg, f32(srcs[5]), f32(srcs[4])) if _USE_RBF_LUT and srcs[5].is_cuda else None,
+                "rbf_lut": ops.rbf_lut_build(self.cfg, f32(srcs[5]), f32(srcs[4]), self._rbf_dmax) if _USE_RBF_LUT and srcs[5].is_cuda else None,
                 "bdist": f32(srcs[6]), "relpos": f32(srcs[7]),
                 "coord": [split_rows(srcs[8]), f32(srcs[9]), f32(srcs[10]).reshape(-1).contiguous()],
                 "seq": [split_k(srcs[11]), f32(srcs[12]), split_k(srcs[13])],

@@ -92,7 +92,7 @@ def pair_embed(cfg, pair_static, z, mask, t, opm_a, opm_b, weights, out, sampler
     return out
 
 
-def rbf_lut_build(cfg, w_dist, centers):
+def rbf_lut_build(cfg, w_dist, centers, d_max=None):
     """Tabulate d -> W_dist rbf(d) (reference modules.py:73-82 followed by embed_dist's Linear, model.py:360) on the device:
     fp32 weights, PRD_RBF_LUT_POINTS + 1 rows over [0, max center + 0.52 nm]."""
     import ctypes
@@ -105,7 +105,8 @@ def rbf_lut_build(cfg, w_dist, centers):
     lib.prd_rbf_lut_build.argtypes = [ctypes.POINTER(PrdDims), ctypes.c_void_p, ctypes.c_void_p, ctypes.c_float,
                                       ctypes.c_void_p, ctypes.c_void_p]
     lut = torch.empty(int(lib.prd_rbf_lut_floats(ctypes.byref(d))), dtype=F32, device=w_dist.device)
-    d_max = float(centers.max()) + 0.52
+    if d_max is None:
+        d_max = float(centers.max()) + 0.52  # host read: callers that rebuild under CUDA-graph capture pass d_max
     rc = lib.prd_rbf_lut_build(ctypes.byref(d), w_dist.data_ptr(), centers.data_ptr(), ctypes.c_float(d_max), lut.data_ptr(),
                                ctypes.c_void_p(torch.cuda.current_stream(w_dist.device).cuda_stream))
     if rc != 0:

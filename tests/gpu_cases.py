@@ -1071,3 +1071,89 @@ def case_predict_loop(seed=52, T=4):
 
 
 CASES.update({"postprocess": lambda: case_postprocess(), "predict_loop": lambda: case_predict_loop()})
+
+
+def case_train_modes(cfg=None, sizes=((8, 32), (6, 27)), seed=60):
+    """The three ways to run a training step give the same loss and gradients: training_step + loss.backward() (autograd),
+    autograd.training_step_manual (no autograd engine), autograd.TrainStepGraph (device side as one CUDA graph) -- and the
+    graph picks up an in-place weight update between replays (its fp16 weight packs are rebuilt inside the graph)."""
+    from protein_redesign_b200 import autograd as ag
+    cfg = cfg or dataclasses.replace(syn.README, mask_prob=0.15, num_steps=2000)
+    m, sd = _model(cfg, seed)
+    m.train()
+    batch = syn.make_batch(cfg, list(sizes), seed=seed, with_positions=True)
+    B, N = batch["atom_mask"].shape
+    g = torch.Generator().manual_seed(seed + 1)
+    draws = {"z": torch.randn(B, N, 3, generator=g).to(DEV), "seq": torch.randn(B, N, 21, generator=g).to(DEV)}
+    names = [n for n, _ in ag.trainable_parameters(m)]
+
+    def flat_of(model):
+        return torch.cat([p.grad.reshape(-1) for n, p in model.named_parameters() if p.requires_grad]).clone()
+
+    torch.manual_seed(seed)
+    with torch.enable_grad():
+        loss_a = m.training_step(_to_dev(batch), 0, noise=draws)
+        loss_a.backward()
+    ga = flat_of(m)
+    grads = ag.FlatGrads(m).attach()
+    torch.manual_seed(seed)
+    loss_b = ag.training_step_manual(m, _to_dev(batch), grads, noise=draws)
+    gb = grads.flat.clone()
+    tsg = ag.TrainStepGraph(m, _to_dev(batch), grads, inject_noise=True)
+    torch.manual_seed(seed)
+    loss_c = tsg.step(_to_dev(batch), noise=draws).clone()
+    gc = grads.flat.clone()
+    # an optimiser-like in-place update of EVERY parameter, then the same step again: graph == manual on the new weights
+    with torch.no_grad():
+        for _, p in ag.trainable_parameters(m):
+            p.mul_(1.02)
+    torch.manual_seed(seed)
+    loss_d = tsg.step(_to_dev(batch), noise=draws).clone()
+    gd = grads.flat.clone()
+    torch.manual_seed(seed)
+    loss_e = ag.training_step_manual(m, _to_dev(batch), grads, noise=draws)
+    ge = grads.flat.clone()
+    torch.cuda.synchronize()
+    return {"manual_vs_autograd_loss": (abs(float(loss_b) - float(loss_a)) / abs(float(loss_a)), 1e-6),
+            "manual_vs_autograd_grads": (rel(gb, ga), 1e-5),
+            "graph_vs_manual_loss": (abs(float(loss_c) - float(loss_b)) / abs(float(loss_b)), 1e-6),
+            "graph_vs_manual_grads": (rel(gc, gb), 1e-5),
+            "weights_changed_loss_moved": (0.0 if abs(float(loss_d) - float(loss_c)) / abs(float(loss_c)) > 1e-4 else 1.0, 0.0),
+            "graph_after_update_vs_manual_loss": (abs(float(loss_d) - float(loss_e)) / abs(float(loss_e)), 1e-6),
+            "graph_after_update_vs_manual_grads": (rel(gd, ge), 1e-5),
+            "parameters": (float(len(names) != 240), 0.0)}
+
+
+CASES["train_modes"] = lambda: case_train_modes()
+
+
+def case_dw_tc():
+    """The weight-gradient reduction dW = dY^T X on tcgen05 with both operands MN-major tf32 (csrc/prd_bwd_dw.cu) through
+    its C-ABI hook, against float64 on operands pre-rounded to tf32 (every product is then exact): full tiles, column tails
+    (Nout, K not multiples of the tile), row counts that are not multiples of the pipeline block, K > 256 (several tiles)."""
+    import ctypes
+    lib = _lib.load()
+    lib.prd_dw_acc.restype = ctypes.c_int
+    lib.prd_dw_acc.argtypes = [ctypes.c_void_p, ctypes.c_longlong, ctypes.c_void_p, ctypes.c_longlong, ctypes.c_longlong, ctypes.c_int,
+                               ctypes.c_int, ctypes.c_void_p, ctypes.c_longlong, ctypes.c_void_p, ctypes.c_float, ctypes.c_int, ctypes.c_void_p]
+
+    def r_tf32(x):
+        i = x.view(torch.int32)
+        return ((i + 0x1000) & ~0x1FFF).view(torch.float32)
+
+    out = {}
+    g = torch.Generator().manual_seed(3)
+    for R, Nout, K in ((512, 128, 64), (4096, 256, 64), (4096, 64, 256), (1000, 320, 64), (3108, 128, 512), (2000, 100, 72)):
+        dY, X = r_tf32(torch.randn(R, Nout, generator=g)), r_tf32(torch.randn(R, K, generator=g))
+        dYd, Xd = dY.to(DEV), X.to(DEV)
+        dW = torch.ones(Nout, K, device=DEV)  # the kernel accumulates
+        db = torch.zeros(Nout, device=DEV)
+        rc = lib.prd_dw_acc(dYd.data_ptr(), Nout, Xd.data_ptr(), K, R, Nout, K, dW.data_ptr(), K, db.data_ptr(), 0.5, 2, None)
+        assert rc == 0, _lib.last_error()
+        torch.cuda.synchronize()
+        out[f"dW_{R}x{Nout}x{K}"] = (rel(dW, 1.0 + 0.5 * dY.double().t() @ X.double()), 2e-6)
+        out[f"db_{R}x{Nout}x{K}"] = (rel(db, 0.5 * dY.double().sum(0)), 2e-6)
+    return out
+
+
+CASES["dw_tc"] = lambda: case_dw_tc()

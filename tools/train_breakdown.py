@@ -1,0 +1,59 @@
+"""Per-op GPU time of one training step (CUDA events around every C-ABI call; serialised, so slightly pessimistic).
+Usage (GPU box): python tools/train_breakdown.py [--sizes 0]"""
+import argparse
+import collections
+import dataclasses
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bench  # noqa: E402
+from protein_redesign_b200 import _lib, synthetic as syn  # noqa: E402
+from protein_redesign_b200 import autograd as ag  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--sizes", type=int, default=0)
+    a = ap.parse_args()
+    dev = torch.device("cuda", 0)
+    cfg = dataclasses.replace(syn.PAPER, mask_prob=0.15, num_steps=2000)
+    model = bench._make_model(cfg, dev, train=True)
+    host = syn.make_batch(cfg, bench.TRAIN_SIZES[a.sizes], seed=700, with_positions=True)
+    grads = ag.FlatGrads(model).attach()
+    to_dev = lambda: {k: (v.to(dev) if isinstance(v, torch.Tensor) else v) for k, v in host.items()}
+    for _ in range(2):
+        ag.training_step_manual(model, to_dev(), grads)
+    torch.cuda.synchronize()
+    acc = collections.defaultdict(lambda: [0, 0.0])
+    orig_call, orig_bwd = _lib.call, _lib.call_bwd
+
+    def timed(kind, fn):
+        def wrapper(op, *args, **kw):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn(op, *args, **kw)
+            e1.record()
+            e1.synchronize()
+            acc[f"{kind}:{op}"][0] += 1
+            acc[f"{kind}:{op}"][1] += e0.elapsed_time(e1)
+        return wrapper
+
+    _lib.call, _lib.call_bwd = timed("fwd", orig_call), timed("bwd", orig_bwd)
+    ag._lib = _lib
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    ag.training_step_manual(model, to_dev(), grads)
+    t1.record()
+    torch.cuda.synchronize()
+    total = sum(v[1] for v in acc.values())
+    print(f"step (serialised, with per-op sync): {t0.elapsed_time(t1):.1f} ms; sum of op times {total:.1f} ms")
+    for k, (n, ms) in sorted(acc.items(), key=lambda kv: -kv[1][1])[:24]:
+        print(f"{k:36s} x{n:3d} {ms:8.2f} ms  {100 * ms / total:5.1f} %  {ms / n:7.3f} ms each")
+
+
+if __name__ == "__main__":
+    main()
