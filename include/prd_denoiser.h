@@ -19,7 +19,14 @@
  *                        void* stream);
  *       size_t prd_<op>_workspace_bytes(const PrdDims*);
  *     the pointer-array order is documented per function;
- *   - there is no CPU fallback: without an sm_100 device every op fails (prd_device_check()).
+ *   - there is no CPU fallback: without an sm_100 device every op fails (prd_device_check());
+ *   - contract limits (the reference's defaults; anything else returns an error, never a silent fallback):
+ *       attention heads are H = 4 heads of c = 16 channels (modules.py:148-149 defaults) in triangle_attention and
+ *       single_attention; pair_dim c_z is 64 or 32; single_dim c_s is a multiple of 64; SPAttention uses c_hidden = c_s
+ *       (modules.py:366-371) and OuterProductUpdate c_hidden = c_s / 4 (modules.py:372-374); RadialBasisProjection spans
+ *       [0, 2] nm (modules.py:73-82);
+ *     pair masks: the pair-stack ops take the TOKEN mask m [B, N]; the reference's mask_2d is always m (x) m
+ *     (modules.py:334,393) and the Python mirror rejects any other [B, N, N] mask (modules._mask_from_2d).
  */
 #ifndef PRD_DENOISER_H_
 #define PRD_DENOISER_H_

@@ -49,6 +49,32 @@ extern std::atomic<long long> g_launches;
 constexpr int kNumSMs = 148;
 
 // ---------------------------------------------------------------------------------------
+// Programmatic dependent launch (PDL).  A kernel launched through launch_pdl() may start while its predecessor in the
+// stream is still draining: its CTAs become resident as the predecessor's CTAs exit, run their prologue (barrier init,
+// TMEM allocation, weight tiles -> shared memory: nothing the predecessor produces) and then block in pdl_wait() until
+// the predecessor has completed and its writes are visible.  Every kernel launched this way calls pdl_trigger() first
+// (lets ITS successor do the same) and pdl_wait() before the first access to anything a previous kernel wrote; both are
+// no-ops for an ordinary launch.  PRD_PDL=0 turns the launch attribute off (A/B timing).
+// ---------------------------------------------------------------------------------------
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+// ---------------------------------------------------------------------------------------
 // small device helpers
 // ---------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {

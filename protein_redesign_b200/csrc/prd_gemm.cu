@@ -69,6 +69,7 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   // stored as [hi | lo] along K (fp16 pair, removes the systematic weight rounding) the activation
   // operand is simply read twice: sum_k x_k (w_hi + w_lo)_k.
   extern __shared__ uint8_t smem_raw[];
+  pdl_trigger();
   using L = GemmSmem<BN, STAGES>;
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
@@ -98,6 +99,7 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();  // everything above touched only weights / shared memory; the predecessor's output is read below
   const uint32_t tmem = *tmem_slot;
 
   if (warp == 0) {
@@ -420,8 +422,8 @@ static int launch_gemm(const GemmArgs& g, cudaStream_t stream) {
   const int num_kb = g.split != 0 ? 2 * kb_half : kb_half;
   const int a_wrap = g.split == 1 ? kb_half : num_kb;
   const int b_wrap = g.split == 2 ? kb_half : num_kb;
-  kern<<<grid, 192, L::kTotal, stream>>>(map_a, map_b, num_kb, a_wrap, b_wrap, tl, g.a_bs1 != 0 ? 1 : 0,
-                                         g.a_bs2 != 0 ? 1 : 0, g.b_bs1 != 0 ? 1 : 0, g.b_bs2 != 0 ? 1 : 0, ep);
+  PRD_CUDA_OK(launch_pdl(kern, grid, 192, L::kTotal, stream, map_a, map_b, num_kb, a_wrap, b_wrap, tl, g.a_bs1 != 0 ? 1 : 0,
+                         g.a_bs2 != 0 ? 1 : 0, g.b_bs1 != 0 ? 1 : 0, g.b_bs2 != 0 ? 1 : 0, ep));
   PRD_LAUNCHED();
   return 0;
 }

@@ -5,6 +5,7 @@
 #include <atomic>
 #include <mutex>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "../../include/prd_denoiser.h"
@@ -20,6 +21,11 @@ void set_error(const char* fmt, ...) {
   va_start(ap, fmt);
   vsnprintf(g_error, sizeof(g_error), fmt, ap);
   va_end(ap);
+}
+
+bool pdl_enabled() {
+  static const bool on = getenv("PRD_PDL") && getenv("PRD_PDL")[0] == '1';  // measured: no gain under graph replay (profiles/r02_pdl.md), so opt-in
+  return on;
 }
 
 int check_cuda(cudaError_t e, const char* what) {

@@ -43,6 +43,7 @@ outer_linear_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
                     const __half* __restrict__ xn16, const __half* __restrict__ w1, const float* __restrict__ u,
                     const float* __restrict__ bias, int N, int ilen) {
   extern __shared__ uint8_t raw[];
+  pdl_trigger();
   constexpr int CS = KBS * 64;
   constexpr int NCH = KBS * CZ * 8 / 256;  // 16-byte W1 chunks per builder thread
   constexpr int CPK = NCH / KBS;           // ... per K-block
@@ -92,6 +93,7 @@ outer_linear_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();  // everything above touched only weights / shared memory; the predecessor's output is read below
   const uint32_t tmem = *tmem_slot;
 
   if (warp < 8) {
@@ -298,7 +300,7 @@ static int launch_outer_linear(const CUtensorMap& mx, const CUtensorMap& mp, dim
   static_assert(smem <= 227 * 1024, "outer_linear shared memory budget");
   auto kern = outer_linear_kernel<CZ, KBS>;
   PRD_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  kern<<<grid, kOlThreads, smem, s>>>(mx, mp, pair, dst, residual, xn16, w1, u, bias, N, ilen);
+  PRD_CUDA_OK(launch_pdl(kern, grid, kOlThreads, smem, s, mx, mp, pair, dst, residual, xn16, w1, u, bias, N, ilen));
   PRD_LAUNCHED();
   return 0;
 }

@@ -283,6 +283,7 @@ pair_transition_ws_kernel(const __grid_constant__ CUtensorMap map_rows, float* d
                           const float* __restrict__ b2) {
   constexpr int CZ = 64, HID = 256;
   extern __shared__ uint8_t raw[];
+  pdl_trigger();
   using L = PtSmem;
   uint8_t* sm = smem_align1024(raw);
   uint8_t* sW1 = sm + L::kW1;
@@ -335,6 +336,7 @@ pair_transition_ws_kernel(const __grid_constant__ CUtensorMap map_rows, float* d
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();  // everything above touched only weights / shared memory; the predecessor's output is read below
   const uint32_t tmem = *tmem_slot;
   const long long num_tiles = (R + kTileRows - 1) / kTileRows;
   const int my_tiles = (blockIdx.x < num_tiles) ? static_cast<int>((num_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0;
@@ -514,7 +516,8 @@ static int launch_pair_transition_ws(const PairDims& d, const float* pair, float
   td.stride[0] = 256;
   td.box[0] = 32; td.box[1] = 128;
   if (make_tensor_map(&map_rows, pair, 4, 2, td, true)) return 1;
-  pair_transition_ws_kernel<<<grid_for(tiles, 1), kPtThreads, PtSmem::kTotal, s>>>(map_rows, dst, residual, R, w1, b1, w2, b2);
+  PRD_CUDA_OK(launch_pdl(pair_transition_ws_kernel, grid_for(tiles, 1), kPtThreads, PtSmem::kTotal, s, map_rows, dst, residual, R, w1, b1,
+                         w2, b2));
   PRD_LAUNCHED();
   return 0;
 }
@@ -662,6 +665,7 @@ trimul_in_t_kernel(const __grid_constant__ CUtensorMap map_pair, const float* __
                    const __half* __restrict__ w_in, const float* __restrict__ b_in, __half* __restrict__ ab, int Np) {
   constexpr int CZ = 64, NOUT = 256;
   extern __shared__ uint8_t raw[];
+  pdl_trigger();
   constexpr int kStage = (RowStage<CZ>::kBytes + 1023) / 1024 * 1024;
   constexpr int kGroupBytes = 32768 + kStage;  // X tile (store slices of warps 0-3 afterwards), slices of warps 4-7, row stage
   uint8_t* sm = smem_align1024(raw);
@@ -693,6 +697,7 @@ trimul_in_t_kernel(const __grid_constant__ CUtensorMap map_pair, const float* __
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();  // everything above touched only weights / shared memory; the predecessor's output is read below
   const uint32_t tmem = *tmem_slot + g.grp * NOUT;
   const uint32_t tm_lane = tmem + (static_cast<uint32_t>(g.warp * 32) << 16);
   const int t = g.t, half = g.half, lane = t & 31;
@@ -799,7 +804,7 @@ static int launch_trimul_in(const PairDims& d, const float* pair, const float* m
     if (set_smem(trimul_in_t_kernel, smem)) return 1;
     CUtensorMap mp;
     if (make_pair_tile_map(&mp, pair, d.B, d.N, mode)) return 1;
-    trimul_in_t_kernel<<<grid_for((tiles + 1) / 2, 1), 512, smem, s>>>(mp, mask, map, d.B, w_in, b_in, ab, plane_ld(d.N));
+    PRD_CUDA_OK(launch_pdl(trimul_in_t_kernel, grid_for((tiles + 1) / 2, 1), 512, smem, s, mp, mask, map, d.B, w_in, b_in, ab, plane_ld(d.N)));
     PRD_LAUNCHED();
     return 0;
   }
@@ -834,6 +839,7 @@ trimul_out_kernel(const float* pair, float* dst, int residual, const __half* __r
                   const __grid_constant__ CUtensorMap map_x, int use_tma, int N, int Nx, long long R,
                   const __half* __restrict__ w_out, const float* __restrict__ b_out) {
   extern __shared__ uint8_t raw[];
+  pdl_trigger();
   constexpr int kStage = (RowStage<CZ>::kBytes + 1023) / 1024 * 1024;
   constexpr int kAO = kStage > 32768 ? kStage : 32768;  // A_p | A_x, re-used as the output stage
   constexpr int kXBytes = CZ * kTileRows * 2;           // contraction-result tile [CZ planes][128 j] fp16
@@ -870,6 +876,7 @@ trimul_out_kernel(const float* pair, float* dst, int residual, const __half* __r
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();  // everything above touched only weights / shared memory; the predecessor's output is read below
   const uint32_t tmem = *tmem_slot + g.grp * TCOLS;
   const uint32_t tm_lane = tmem + (static_cast<uint32_t>(g.warp * 32) << 16);
   const long long NN = (long long)N * N;
@@ -1016,7 +1023,7 @@ static int launch_trimul_out(const PairDims& d, const float* pair, float* dst, i
     t.box[0] = use_tma ? kTileRows : 8; t.box[1] = 1; t.box[2] = CZ; t.box[3] = 1;
     if (make_tensor_map(&mx, x, 2, 4, t, false)) return 1;
   }
-  kern<<<grid_for((tiles + 1) / 2, 1), 256, smem, s>>>(pair, dst, residual, x, mx, use_tma, d.N, Nx, R, w_out, b_out);
+  PRD_CUDA_OK(launch_pdl(kern, grid_for((tiles + 1) / 2, 1), 256, smem, s, pair, dst, residual, x, mx, use_tma, d.N, Nx, R, w_out, b_out));
   PRD_LAUNCHED();
   return 0;
 }
@@ -1047,6 +1054,7 @@ triattn_proj_kernel(const __grid_constant__ CUtensorMap map_pair, const float* _
                     const float* __restrict__ b_gate, __half* __restrict__ q, __half* __restrict__ k,
                     __half* __restrict__ gout, __half* __restrict__ vt, int Np) {
   extern __shared__ uint8_t raw[];
+  pdl_trigger();
   constexpr int NOUT = 256;
   constexpr bool kTma = (CZ == 64);  // pair_dim 64: the row tile arrives by TMA (32 KB swizzled stage)
   constexpr int kGroupBytes = 32768 + (RowStage<CZ>::kBytes + 1023) / 1024 * 1024;  // A tile, output stage, row stage
@@ -1079,6 +1087,7 @@ triattn_proj_kernel(const __grid_constant__ CUtensorMap map_pair, const float* _
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();  // everything above touched only weights / shared memory; the predecessor's output is read below
   const uint32_t tmem = *tmem_slot + g.grp * NOUT;
   const uint32_t tm_lane = tmem + (static_cast<uint32_t>(g.warp * 32) << 16);
   const int t = g.t, half = g.half;
@@ -1244,7 +1253,7 @@ static int launch_triattn_proj(const PairDims& d, const float* pair, int mode, c
   } else {
     memset(&mp, 0, sizeof(mp));
   }
-  kern<<<grid_for((tiles + 1) / 2, 1), 512, smem, s>>>(mp, pair, map, d.B, w_qkvg, b_gate, q, k, g, vt, plane_ld(d.N));
+  PRD_CUDA_OK(launch_pdl(kern, grid_for((tiles + 1) / 2, 1), 512, smem, s, mp, pair, map, d.B, w_qkvg, b_gate, q, k, g, vt, plane_ld(d.N)));
   PRD_LAUNCHED();
   return 0;
 }
@@ -1270,6 +1279,7 @@ triattn_out_kernel(const __grid_constant__ CUtensorMap map_og, const float* pair
   // UMMA A operand (issued as soon as the previous tile's UMMAs have completed), the residual rows go to the other of two row
   // stages (the stage a tile was read from also carries its output rows to the bulk store).
   extern __shared__ uint8_t raw[];
+  pdl_trigger();
   constexpr int kStage = (RowStage<CZ>::kBytes + 1023) / 1024 * 1024;
   constexpr int kGroupBytes = 16384 + 2 * kStage;
   uint8_t* sm = smem_align1024(raw);
@@ -1300,6 +1310,7 @@ triattn_out_kernel(const __grid_constant__ CUtensorMap map_og, const float* pair
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();  // everything above touched only weights / shared memory; the predecessor's output is read below
   const uint32_t tmem = *tmem_slot + g.grp * TCOLS;
   const uint32_t tm_lane = tmem + (static_cast<uint32_t>(g.warp * 32) << 16);
   const int t = g.t;
@@ -1407,7 +1418,7 @@ static int launch_triattn_out(const PairDims& d, const float* pair, float* dst, 
     t.box[0] = 64; t.box[1] = 128; t.box[2] = 1; t.box[3] = 1;
     if (make_tensor_map(&mo, og, 2, 3, t, true)) return 1;
   }
-  kern<<<grid_for((tiles + 1) / 2, 1), 256, smem, s>>>(mo, pair, dst, residual, map, R, w_o, b_o);
+  PRD_CUDA_OK(launch_pdl(kern, grid_for((tiles + 1) / 2, 1), 256, smem, s, mo, pair, dst, residual, map, R, w_o, b_o));
   PRD_LAUNCHED();
   return 0;
 }

@@ -64,6 +64,7 @@ pair_bias_kernel(const float* __restrict__ pair, long long R, long long NN, cons
   float* sW = reinterpret_cast<float*>(smem_pb + STAGES * kStageBytes);  // [4][CZ] folded weights, [4] folded bias (16-byte aligned)
   uint64_t* full = reinterpret_cast<uint64_t*>(sW + 4 * CZ + 4);
   const int t = threadIdx.x;
+  pdl_trigger();
   // fold the affine LayerNorm into the projection:  (y*g + b) . w_h = y . (g*w_h) + b . w_h
   for (int i = t; i < 4 * CZ; i += 256) sW[i] = w[i] * (ln_w ? ln_w[i % CZ] : 1.0f);
   if (t < 4) {
@@ -77,6 +78,7 @@ pair_bias_kernel(const float* __restrict__ pair, long long R, long long NN, cons
     fence_barrier_init();
   }
   __syncthreads();
+  pdl_wait();  // everything above touched only weights / shared memory; the predecessor's output is read below
   const long long nchunks = (R + ROWS - 1) / ROWS;
   auto load = [&](long long chunk, int s) {
     const long long e = chunk * ROWS + t;
@@ -147,11 +149,11 @@ int pair_bias_proj(const PairDims& d, int H, const float* pair, const float* ln_
   if (d.CZ == 64) {
     constexpr int smem = 3 * 256 * (64 * 4 + 16) + 64 + (4 * 64 + 4) * 4;
     PRD_CUDA_OK(cudaFuncSetAttribute(pair_bias_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    pair_bias_kernel<64><<<blocks, 256, smem, s>>>(pair, R, NN, ln_w, ln_b, w, bvec, bias_out);
+    PRD_CUDA_OK(launch_pdl(pair_bias_kernel<64>, blocks, 256, smem, s, pair, R, NN, ln_w, ln_b, w, bvec, bias_out));
   } else if (d.CZ == 32) {
     constexpr int smem = 3 * 256 * (32 * 4 + 16) + 64 + (4 * 32 + 4) * 4;
     PRD_CUDA_OK(cudaFuncSetAttribute(pair_bias_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    pair_bias_kernel<32><<<blocks, 256, smem, s>>>(pair, R, NN, ln_w, ln_b, w, bvec, bias_out);
+    PRD_CUDA_OK(launch_pdl(pair_bias_kernel<32>, blocks, 256, smem, s, pair, R, NN, ln_w, ln_b, w, bvec, bias_out));
   } else {
     set_error("pair_bias_proj: unsupported pair_dim %d", d.CZ);
     return 1;

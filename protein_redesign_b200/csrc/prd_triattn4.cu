@@ -98,7 +98,30 @@ struct G4OutProj {
   const float* b_o;    // [64]
   int residual;
   int transposed;      // 0: row (b, seq, tok) = pair[b, seq, tok]; 1: pair[b, tok, seq]
+  int ragged_opt = 1;  // skip trailing all-masked key tiles / fast path for padded sequences (PRD_FLASH_RAGGED=0: off, A/B)
 };
+
+// Key tiles of a sequence that can contribute to its softmax.  The last valid key depends on the batch row only, so every
+// CTA tabulates it once per launch (sNkEff, one warp per batch row) instead of scanning the mask per sequence.  Ragged batches:
+//   * a VALID sequence (m_s = 1): keys of a padded token carry the logit -2^15, i.e. exp2(fill - max) == 0 exactly in fp32
+//     next to at least one valid key, so every 64-key tile AFTER the last valid key adds exactly nothing to P, l and O and
+//     is skipped by all roles (K / V loads, both UMMAs, the softmax pass);
+//   * a PADDED sequence (m_s = 0): every logit is the same constant, the softmax is uniform over all N tokens.  The same
+//     result comes out of the fast path when Q is zero (S = 0, P = exp2(0) = 1, l = N, O = sum_k V / N): the Q loader
+//     zero-fills the tile instead of fetching it and the key table stays all-valid, so a padded sequence costs what a
+//     valid one costs instead of taking the two-pass masked path on every tile.
+// Both are exact restatements of the reference's masked_fill(-2^15) + softmax (modules.py:216-222).
+constexpr int kG4MaxBatch = 256;  // batch rows whose effective tile count is tabulated (beyond that: no tile skipping)
+__device__ __forceinline__ int g4_eff_tiles(const float* __restrict__ mask, const int* sNkEff, int seq, int N, int nkt,
+                                            bool& padded_seq) {
+  if (sNkEff == nullptr) {  // optimisation switched off: every tile of every sequence takes the general path
+    padded_seq = false;
+    return nkt;
+  }
+  padded_seq = mask[seq] < 0.5f;
+  const int bb = seq / N;
+  return (padded_seq || bb >= kG4MaxBatch) ? nkt : sNkEff[bb];
+}
 
 template <bool kFused, int kPM = 0x88>
 __global__ void __launch_bounds__(kG4Threads, 1)
@@ -106,6 +129,7 @@ triattn_flash_g4_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_
                         const __grid_constant__ CUtensorMap map_vt, const float* __restrict__ mask,
                         const __half* __restrict__ g_gate, __half* __restrict__ og, int N, int nseq, G4OutProj op) {
   extern __shared__ uint8_t raw[];
+  pdl_trigger();
   const int nqt = (N + 127) / 128;  // query tiles per sequence
   const int nkt = (N + 63) / 64;    // 64-key tiles per sequence
   const int nrr = (nqt + 3) / 4;    // rounds of four query tiles per sequence
@@ -155,9 +179,34 @@ triattn_flash_g4_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_
     if (threadIdx.x < 64) sBo[threadIdx.x] = op.b_o[threadIdx.x];
     fence_proxy_async_smem();
   }
+  // effective key tiles per batch row (see g4_eff_tiles): tiles up to the last valid key; the token mask is an input of
+  // the whole step, not a product of the previous kernel
+  __shared__ int sNkEffBuf[kG4MaxBatch];
+  const int* sNkEff = op.ragged_opt ? sNkEffBuf : nullptr;
+  if (op.ragged_opt) {
+    const int nb = nseq / N < kG4MaxBatch ? nseq / N : kG4MaxBatch;
+    for (int bb = warp; bb < nb; bb += kG4Threads / 32) {
+      int last = -1;
+      for (int j0 = 0; j0 < N; j0 += 32 * 8) {
+        float mv[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int j = j0 + u * 32 + lane;
+          mv[u] = j < N ? mask[(long long)bb * N + j] : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+          if (mv[u] >= 0.5f) last = j0 + u * 32 + lane;
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) last = max(last, __shfl_xor_sync(0xffffffffu, last, o));
+      if (lane == 0) sNkEffBuf[bb] = last < 0 ? nkt : (last >> 6) + 1;
+    }
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();  // everything above touched only weights / shared memory; the predecessor's output is read below
 
   // sequences of this CTA: seq = blockIdx.x + k * gridDim.x; round R = k * nrr + rr; group g takes q-tile 4 rr + g
   const int nseq_cta = ((int)blockIdx.x < nseq) ? (nseq - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
@@ -186,6 +235,8 @@ triattn_flash_g4_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_
     for (int ks = 0; ks < nseq_cta; ++ks) {
       const int seq = (int)blockIdx.x + ks * (int)gridDim.x;
       bool table = false;
+      bool padded_seq;
+      const int nkt_s = g4_eff_tiles(mask, sNkEff, seq, N, nkt, padded_seq);
       for (int rr = 0; rr < nrr; ++rr, ++R) {
         const int qt = rr * 4 + g;
         if (qt >= nqt) continue;  // (uniform per group) no unit in this round
@@ -199,7 +250,7 @@ triattn_flash_g4_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_
             const int j = i * 128 + t;
             float e = 0.f;
             if (j >= N) e = -INFINITY;
-            else if (ms * mask[(long long)bb * N + j] < 0.5f) e = kMaskFillLog2;
+            else if (!padded_seq && ms * mask[(long long)bb * N + j] < 0.5f) e = kMaskFillLog2;
             if (j < nkt * 64) sKey[j] = e;
             const bool all = __all_sync(0xffffffffu, e == 0.f);
             if (lane == 0) sWarpValid[i * 4 + w] = all ? 1 : 0;
@@ -212,7 +263,7 @@ triattn_flash_g4_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_
           mrow[h] = -INFINITY;
           lrow[h] = 0.f;
         }
-        for (int kt = 0; kt < nkt; ++kt) {
+        for (int kt = 0; kt < nkt_s; ++kt) {
           const int2 wv = *reinterpret_cast<const int2*>(sWarpValid + (kt >> 1) * 4 + (kt & 1) * 2);
           const bool all_valid = (wv.x & wv.y) != 0;
           const float* keyp = sKey + kt * 64;
@@ -418,13 +469,16 @@ triattn_flash_g4_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_
     const uint64_t dv0 = umma_desc_sw128(smem_u32(sV));
     const uint32_t idesc_s = umma_idesc_f16(128, 64), idesc_o = umma_idesc_f16(128, 16);
     int G = 0, U = 0;  // items / units of this group so far
-    int R = 0;
+    int gt_base = 0;   // K / V tiles loaded before this round (the ring position)
     for (int ks = 0; ks < nseq_cta; ++ks) {
-      for (int rr = 0; rr < nrr; ++rr, ++R) {
-        const int gt0 = R * nkt;
+      bool padded_seq;
+      const int nkt_s = g4_eff_tiles(mask, sNkEff, (int)blockIdx.x + ks * (int)gridDim.x, N, nkt, padded_seq);
+      const int n_items_s = nkt_s * 4;
+      for (int rr = 0; rr < nrr; ++rr, gt_base += nkt_s) {
+        const int gt0 = gt_base;
         if (rr * 4 + g >= nqt) {
           // no unit: still release the ring slots, paced by the loads (an arrival must land in the slot's current phase)
-          for (int kt = 0; kt < nkt; ++kt) {
+          for (int kt = 0; kt < nkt_s; ++kt) {
             const int gt = gt0 + kt, slot = gt % kG4Ring;
             mbar_wait(&k_full[slot], (gt / kG4Ring) & 1);
             mbar_wait(&v_full[slot], (gt / kG4Ring) & 1);
@@ -446,16 +500,16 @@ triattn_flash_g4_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_
           umma_commit(s_full);
         }
         __syncwarp();
-        for (int it = 0; it < n_items; ++it, ++G) {
+        for (int it = 0; it < n_items_s; ++it, ++G) {
           const int h = it & 3, kt = it >> 2, gt = gt0 + kt, slot = gt % kG4Ring;
           // ---- everything that does not depend on P_G is prepared BEFORE waiting for it: the softmax threads of this
           // group stall from their last arrival until S_{G+1} / P.V_G are issued, so the path behind the wait is short
-          const bool have_next = it + 1 < n_items;
+          const bool have_next = it + 1 < n_items_s;
           const int h1 = (it + 1) & 3, gt1 = gt0 + ((it + 1) >> 2), slot1 = gt1 % kG4Ring;
           const uint64_t dq1 = dq + 2 * h1, dk1 = dk0 + slot1 * (8192 >> 4) + 2 * h1;
           const uint32_t tO = tmem + 64 + h * 16;
           const uint64_t dv = dv0 + slot * (8192 >> 4) + h * (2048 >> 4);
-          const bool last_s = (it + 1 == n_items - 1);
+          const bool last_s = (it + 1 == n_items_s - 1);
           if (have_next && h1 == 0) mbar_wait(&k_full[slot1], (gt1 / kG4Ring) & 1);
           // a unit's first tile overwrites the O region (every thread has read the previous unit's O)
           if (it == 0 && U >= 1) mbar_wait(o_read, (U - 1) & 1);
@@ -489,8 +543,10 @@ triattn_flash_g4_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_
     int gt = 0;
     for (int ks = 0; ks < nseq_cta; ++ks) {
       const int seq = (int)blockIdx.x + ks * (int)gridDim.x;
+      bool padded_seq;
+      const int nkt_s = g4_eff_tiles(mask, sNkEff, seq, N, nkt, padded_seq);
       for (int rr = 0; rr < nrr; ++rr) {
-        for (int kt = 0; kt < nkt; ++kt, ++gt) {
+        for (int kt = 0; kt < nkt_s; ++kt, ++gt) {
           const int slot = gt % kG4Ring;
           if (gt >= kG4Ring) {
             mbar_wait(&k_empty[slot], ((gt / kG4Ring) - 1) & 1);
@@ -512,6 +568,7 @@ triattn_flash_g4_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_
     int U[4] = {0, 0, 0, 0};
     for (int ks = 0; ks < nseq_cta; ++ks) {
       const int seq = (int)blockIdx.x + ks * (int)gridDim.x;
+      const bool padded_seq = op.ragged_opt && mask[seq] < 0.5f;
       for (int rr = 0; rr < nrr; ++rr) {
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
@@ -519,7 +576,14 @@ triattn_flash_g4_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_
           if (qt >= nqt) continue;
           uint64_t* b = gb + g * 8;
           if (U[g] >= 1) mbar_wait(&b[1], (U[g] - 1) & 1);  // the previous unit's last S is complete
-          if (elect_one()) {
+          if (padded_seq) {
+            // uniform softmax of a padded sequence = the fast path on Q = 0 (see g4_eff_tiles): zero the tile by hand
+            uint4* qz = reinterpret_cast<uint4*>(sm + G4Smem::kQ + g * 16384);
+            for (int i = lane; i < 1024; i += 32) qz[i] = make_uint4(0, 0, 0, 0);
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (elect_one()) mbar_arrive(&b[0]);
+          } else if (elect_one()) {
             mbar_expect_tx(&b[0], 16384);
             tma_load_3d(sm + G4Smem::kQ + g * 16384, &map_q, &b[0], 0, qt * 128, seq);
           }
@@ -570,7 +634,10 @@ static int g4_launch(const PairDims& d, const float* mask, const __half* q, cons
     auto kern = poly == 1 ? triattn_flash_g4_kernel<false, 0xA8> : poly == 2 ? triattn_flash_g4_kernel<false, 0xAA>
                                                                              : triattn_flash_g4_kernel<false, 0x88>;
     PRD_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    kern<<<grid, kG4Threads, smem, s>>>(mq, mk, mv, mask, g, og, N, (int)nseq, G4OutProj{});
+    static const int ragged_opt = !(getenv("PRD_FLASH_RAGGED") && getenv("PRD_FLASH_RAGGED")[0] == '0');
+    G4OutProj none{};
+    none.ragged_opt = ragged_opt;
+    PRD_CUDA_OK(launch_pdl(kern, grid, kG4Threads, smem, s, mq, mk, mv, mask, g, og, N, (int)nseq, none));
   }
   PRD_LAUNCHED();
   return 0;

@@ -130,9 +130,16 @@ class Linear(nn.Linear):
 
 
 def _mask_from_2d(mask_2d: torch.Tensor) -> torch.Tensor:
-    """The reference builds mask_2d = mask (x) mask from a 0/1 token mask (modules.py:334,393); the
-    kernels take the token mask, recovered here as the diagonal."""
-    return torch.diagonal(mask_2d, dim1=-2, dim2=-1).contiguous()
+    """The reference builds mask_2d = mask (x) mask from a 0/1 token mask (modules.py:334,393) and that is the only form
+    its callers ever pass; the kernels take the token mask, recovered here as the diagonal.  The stand-alone module entry
+    points (TriangleAttention / TriangleMultiplication / Attention ``.forward(pair, mask_2d)``) therefore accept exactly
+    the masks of that form and REFUSE any other one (one device comparison + host read: these entry points are the
+    drop-in surface, not the hot path, which passes the token mask directly)."""
+    mask = torch.diagonal(mask_2d, dim1=-2, dim2=-1).contiguous()
+    if not torch.equal(mask_2d, mask.unsqueeze(-1) * mask.unsqueeze(-2)):
+        raise ValueError("the B200 pair-stack kernels take masks of the form mask_2d = m (x) m with a 0/1 token mask m "
+                         "(what modules.py:334,393 builds); a general [B, N, N] mask is outside the contract")
+    return mask
 
 
 class Attention(nn.Module):
