@@ -141,7 +141,9 @@ PRD_DECLARE_OP(outer_linear)
  * in: [pair | mask]  out: [pair_out]
  * weights: [w_in_h 4c_z x c_z (ab_proj ; ab_gate) | b_in | w_out_h 2c_z x c_z (out_gate ; out_proj) | b_out] */
 PRD_DECLARE_OP(triangle_multiplication)
-/* modules.py:236-243 (+185-225),340-341 TriangleAttention + residual (d->mode: 0 starting, 1 ending).
+/* modules.py:236-243 (+185-225),340-341 TriangleAttention + residual (d->mode bit 0: 0 starting, 1 ending; bit 1: the
+ * caller promises that the token mask is all ones -- a performance hint that selects the attention core without the
+ * per-sequence handling of ragged batches; results are identical either way).
  * in: [pair | mask]  out: [pair_out]
  * weights: [w_qkvg_h 4Hc x c_z (q;k;v;gate) | b_gate f32 Hc | w_o_h c_z x Hc | b_o] */
 PRD_DECLARE_OP(triangle_attention)

@@ -162,7 +162,7 @@ def forward_with_checkpoints(model, batch, z, seq_t, mask, t) -> Tuple[torch.Ten
     tape.blocks = []
     for block in den.folding_blocks:
         tape.blocks.append((single.clone(), pair.clone()))
-        block.forward_(cfg, single, pair, tape.mask)
+        block.forward_(cfg, single, pair, tape.mask, all_valid=bool(batch.get("_all_valid", False)))
     tape.single_out, tape.pair_out = single, pair
     noise_pred = ops.coord_head(cfg, pair, tape.z, tape.mask, w["coord"])
     seq_pred = ops.seq_head(cfg, single, w["seq"])
@@ -192,10 +192,11 @@ def backward_from_checkpoints(model, tape: DenoiserTape, d_noise_pred: torch.Ten
         block.pair_mul_outgoing.apply_(cfg, p2, mask)
         p3 = p2.clone()
         block.pair_mul_incoming.apply_(cfg, p3, mask)
+        all_valid = bool(tape.batch.get("_all_valid", False))
         p4 = p3.clone()
-        block.pair_attn_starting.apply_(cfg, p4, mask)
+        block.pair_attn_starting.apply_(cfg, p4, mask, all_valid=all_valid)
         p5 = p4.clone()
-        block.pair_attn_ending.apply_(cfg, p5, mask)
+        block.pair_attn_ending.apply_(cfg, p5, mask, all_valid=all_valid)
         transition_bwd(cfg, P, G, bp + "pair_fc.", p5, d_pair)
         del p5
         triangle_attention_bwd(cfg, P, G, bp + "pair_attn_ending.attn.", 1, p4, mask, d_pair)

@@ -415,19 +415,23 @@ int prd_triangle_attention_fwd(const PrdDims* d, const void* const* in, void* co
   if (prd_device_check()) return 1;
   PRD_WS_CHECK(prd_triangle_attention_workspace_bytes(d));
   PRD_REQUIRE(d->H == 4 && d->c == 16, "triangle_attention: built for 4 heads x 16 channels (got %d x %d)", d->H, d->c);
-  PRD_REQUIRE(d->mode == 0 || d->mode == 1, "triangle_attention: invalid mode %d", d->mode);
+  // d->mode bit 0: 0 starting / 1 ending; bit 1: the caller promises an all-valid token mask (performance hint only)
+  PRD_REQUIRE(d->mode >= 0 && d->mode <= 3, "triangle_attention: invalid mode %d", d->mode);
+  const int mode = d->mode & 1;
+  PairDims pdm = pd(d);
+  pdm.all_valid = (d->mode >> 1) & 1;
   TaWs s = ta_carve(d, workspace);
   cudaStream_t st = S(stream);
   const float* pair = in_ptr<float>(in, 0);
-  if (triattn_proj(pd(d), pair, d->mode, in_ptr<__half>(w, 0), in_ptr<float>(w, 1), s.q, s.k, s.g, s.vt, st)) return 1;
+  if (triattn_proj(pdm, pair, mode, in_ptr<__half>(w, 0), in_ptr<float>(w, 1), s.q, s.k, s.g, s.vt, st)) return 1;
   // the fused variant (out_proj + residual in the attention kernel's unit epilogue) measures 3 % slower than the core +
   // triattn_out (its epilogue is a serial latency chain per unit): opt-in for A/B timing
   static const bool fuse = getenv("PRD_FLASH_FUSE") && getenv("PRD_FLASH_FUSE")[0] == '1';
-  if (fuse && d->c_z == 64 && triattn_flash_g4_applies(pd(d)))  // attention core + out_proj + residual in one kernel
-    return triattn_flash_out_g4(pd(d), in_ptr<float>(in, 1), s.q, s.k, s.g, s.vt, pair, out_ptr<float>(out, 0), d->residual,
-                                d->mode, in_ptr<__half>(w, 2), in_ptr<float>(w, 3), st);
-  if (triattn_flash(pd(d), in_ptr<float>(in, 1), s.q, s.k, s.g, s.vt, s.og, st)) return 1;
-  return triattn_out(pd(d), pair, out_ptr<float>(out, 0), d->residual, d->mode, s.og, in_ptr<__half>(w, 2),
+  if (fuse && d->c_z == 64 && triattn_flash_g4_applies(pdm))  // attention core + out_proj + residual in one kernel
+    return triattn_flash_out_g4(pdm, in_ptr<float>(in, 1), s.q, s.k, s.g, s.vt, pair, out_ptr<float>(out, 0), d->residual,
+                                mode, in_ptr<__half>(w, 2), in_ptr<float>(w, 3), st);
+  if (triattn_flash(pdm, in_ptr<float>(in, 1), s.q, s.k, s.g, s.vt, s.og, st)) return 1;
+  return triattn_out(pdm, pair, out_ptr<float>(out, 0), d->residual, mode, s.og, in_ptr<__half>(w, 2),
                      in_ptr<float>(w, 3), st);
 }
 
@@ -449,7 +453,9 @@ int prd_profile_kernel(const char* name, const PrdDims* d, void* workspace, size
     if (n == "triattn_flash") {
       PRD_WS_CHECK(prd_triangle_attention_workspace_bytes(d));
       TaWs s = ta_carve(d, workspace);
-      return triattn_flash(pd(d), static_cast<const float*>(aux), s.q, s.k, s.g, s.vt, s.og, st);
+      PairDims pdm = pd(d);
+      pdm.all_valid = (d->mode >> 1) & 1;  // same hint as prd_triangle_attention_fwd
+      return triattn_flash(pdm, static_cast<const float*>(aux), s.q, s.k, s.g, s.vt, s.og, st);
     }
     if (n == "trimul_gemm") {
       PRD_WS_CHECK(prd_triangle_multiplication_workspace_bytes(d));

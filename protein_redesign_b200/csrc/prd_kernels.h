@@ -39,6 +39,8 @@ int gemm_f16(const GemmArgs& g, cudaStream_t stream);
 // ---- pair-row tile kernels (prd_rowtile.cu): 128 pair elements per tile, thread per row ----
 struct PairDims {
   int B, N, CZ;
+  int all_valid = 0;  // caller's promise that every token of the batch is valid (mask all ones): selects the attention core
+                      // without per-sequence ragged handling; 0 = unknown (always correct)
 };
 inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 inline int plane_ld(int N) { return round_up(N, 64); }  // row stride (halves) of fp16 channel planes

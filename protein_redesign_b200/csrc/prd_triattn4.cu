@@ -98,7 +98,6 @@ struct G4OutProj {
   const float* b_o;    // [64]
   int residual;
   int transposed;      // 0: row (b, seq, tok) = pair[b, seq, tok]; 1: pair[b, tok, seq]
-  int ragged_opt = 1;  // skip trailing all-masked key tiles / fast path for padded sequences (PRD_FLASH_RAGGED=0: off, A/B)
 };
 
 // Key tiles of a sequence that can contribute to its softmax.  The last valid key depends on the batch row only, so every
@@ -112,9 +111,10 @@ struct G4OutProj {
 //     valid one costs instead of taking the two-pass masked path on every tile.
 // Both are exact restatements of the reference's masked_fill(-2^15) + softmax (modules.py:216-222).
 constexpr int kG4MaxBatch = 256;  // batch rows whose effective tile count is tabulated (beyond that: no tile skipping)
+template <bool kRagged>
 __device__ __forceinline__ int g4_eff_tiles(const float* __restrict__ mask, const int* sNkEff, int seq, int N, int nkt,
                                             bool& padded_seq) {
-  if (sNkEff == nullptr) {  // optimisation switched off: every tile of every sequence takes the general path
+  if (!kRagged) {  // all-valid variant: the tile count is the launch constant, nothing is read per sequence
     padded_seq = false;
     return nkt;
   }
@@ -123,7 +123,7 @@ __device__ __forceinline__ int g4_eff_tiles(const float* __restrict__ mask, cons
   return (padded_seq || bb >= kG4MaxBatch) ? nkt : sNkEff[bb];
 }
 
-template <bool kFused, int kPM = 0x88>
+template <bool kFused, int kPM = 0x88, bool kRagged = true>
 __global__ void __launch_bounds__(kG4Threads, 1)
 triattn_flash_g4_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
                         const __grid_constant__ CUtensorMap map_vt, const float* __restrict__ mask,
@@ -182,8 +182,8 @@ triattn_flash_g4_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_
   // effective key tiles per batch row (see g4_eff_tiles): tiles up to the last valid key; the token mask is an input of
   // the whole step, not a product of the previous kernel
   __shared__ int sNkEffBuf[kG4MaxBatch];
-  const int* sNkEff = op.ragged_opt ? sNkEffBuf : nullptr;
-  if (op.ragged_opt) {
+  const int* sNkEff = sNkEffBuf;
+  if (kRagged) {
     const int nb = nseq / N < kG4MaxBatch ? nseq / N : kG4MaxBatch;
     for (int bb = warp; bb < nb; bb += kG4Threads / 32) {
       int last = -1;
@@ -236,7 +236,7 @@ triattn_flash_g4_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_
       const int seq = (int)blockIdx.x + ks * (int)gridDim.x;
       bool table = false;
       bool padded_seq;
-      const int nkt_s = g4_eff_tiles(mask, sNkEff, seq, N, nkt, padded_seq);
+      const int nkt_s = g4_eff_tiles<kRagged>(mask, sNkEff, seq, N, nkt, padded_seq);
       for (int rr = 0; rr < nrr; ++rr, ++R) {
         const int qt = rr * 4 + g;
         if (qt >= nqt) continue;  // (uniform per group) no unit in this round
@@ -472,7 +472,7 @@ triattn_flash_g4_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_
     int gt_base = 0;   // K / V tiles loaded before this round (the ring position)
     for (int ks = 0; ks < nseq_cta; ++ks) {
       bool padded_seq;
-      const int nkt_s = g4_eff_tiles(mask, sNkEff, (int)blockIdx.x + ks * (int)gridDim.x, N, nkt, padded_seq);
+      const int nkt_s = g4_eff_tiles<kRagged>(mask, sNkEff, (int)blockIdx.x + ks * (int)gridDim.x, N, nkt, padded_seq);
       const int n_items_s = nkt_s * 4;
       for (int rr = 0; rr < nrr; ++rr, gt_base += nkt_s) {
         const int gt0 = gt_base;
@@ -544,7 +544,7 @@ triattn_flash_g4_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_
     for (int ks = 0; ks < nseq_cta; ++ks) {
       const int seq = (int)blockIdx.x + ks * (int)gridDim.x;
       bool padded_seq;
-      const int nkt_s = g4_eff_tiles(mask, sNkEff, seq, N, nkt, padded_seq);
+      const int nkt_s = g4_eff_tiles<kRagged>(mask, sNkEff, seq, N, nkt, padded_seq);
       for (int rr = 0; rr < nrr; ++rr) {
         for (int kt = 0; kt < nkt_s; ++kt, ++gt) {
           const int slot = gt % kG4Ring;
@@ -568,7 +568,7 @@ triattn_flash_g4_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_
     int U[4] = {0, 0, 0, 0};
     for (int ks = 0; ks < nseq_cta; ++ks) {
       const int seq = (int)blockIdx.x + ks * (int)gridDim.x;
-      const bool padded_seq = op.ragged_opt && mask[seq] < 0.5f;
+      const bool padded_seq = kRagged && mask[seq] < 0.5f;
       for (int rr = 0; rr < nrr; ++rr) {
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
@@ -634,10 +634,16 @@ static int g4_launch(const PairDims& d, const float* mask, const __half* q, cons
     auto kern = poly == 1 ? triattn_flash_g4_kernel<false, 0xA8> : poly == 2 ? triattn_flash_g4_kernel<false, 0xAA>
                                                                              : triattn_flash_g4_kernel<false, 0x88>;
     PRD_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    static const int ragged_opt = !(getenv("PRD_FLASH_RAGGED") && getenv("PRD_FLASH_RAGGED")[0] == '0');
-    G4OutProj none{};
-    none.ragged_opt = ragged_opt;
-    PRD_CUDA_OK(launch_pdl(kern, grid, kG4Threads, smem, s, mq, mk, mv, mask, g, og, N, (int)nseq, none));
+    // kRagged = false: the variant without per-sequence tile counts (all-valid batches; correct for any mask, it just
+    // takes the general masked path on every tile of a ragged one).  PRD_FLASH_RAGGED=0 forces it (A/B timing).
+    static const int ragged_env = !(getenv("PRD_FLASH_RAGGED") && getenv("PRD_FLASH_RAGGED")[0] == '0');
+    if (!ragged_env || d.all_valid) {
+      auto kern0 = triattn_flash_g4_kernel<false, 0x88, false>;
+      PRD_CUDA_OK(cudaFuncSetAttribute(kern0, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      PRD_CUDA_OK(launch_pdl(kern0, grid, kG4Threads, smem, s, mq, mk, mv, mask, g, og, N, (int)nseq, G4OutProj{}));
+    } else {
+      PRD_CUDA_OK(launch_pdl(kern, grid, kG4Threads, smem, s, mq, mk, mv, mask, g, og, N, (int)nseq, G4OutProj{}));
+    }
   }
   PRD_LAUNCHED();
   return 0;

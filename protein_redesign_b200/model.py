@@ -246,6 +246,9 @@ class ProteinReDiffModel(_Base):
         batch["residue_inv_extra_mask"] = drop
         batch["x"] = 0.1 * pos
         batch["residue_and_atom_mask"] = atom_mask + residue_mask
+        # not in the reference: whether the batch has any padding at all (one more host read next to the masking module's own
+        # .item()): a pure performance hint for the triangle-attention core, see ops.triangle_attention
+        batch["_all_valid"] = bool((batch["residue_and_atom_mask"] > 0.5).all())
         return batch
 
     # ---- step-invariant embeddings, cached per batch ---------------------------------------------
@@ -300,7 +303,7 @@ class ProteinReDiffModel(_Base):
         ops.pair_embed(cfg, pair_static, z.contiguous(), mask, None if sampler_state is not None else t.contiguous(),
                        a, b, w["pair_dyn"] + [w_o, b_o], pair, sampler_state=sampler_state, rbf_lut=w["rbf_lut"])
         rec("Denoiser.opm", pair)
-        single, pair = self.Denoiser.trunk_(single, pair, mask, probe=probe)
+        single, pair = self.Denoiser.trunk_(single, pair, mask, probe=probe, all_valid=bool(batch.get("_all_valid", False)))
         noise_pred = ops.coord_head(cfg, pair, z.contiguous(), mask, w["coord"], out=bufs.get("noise_pred"))
         seq_pred = ops.seq_head(cfg, single, w["seq"], out=bufs.get("seq_pred"))
         return noise_pred, seq_pred

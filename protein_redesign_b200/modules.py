@@ -217,10 +217,10 @@ class TriangleAttention(nn.Module):
         self.mode = mode
         self.pair_dim = pair_dim
 
-    def apply_(self, cfg, pair, mask, out=None, residual=1):
+    def apply_(self, cfg, pair, mask, out=None, residual=1, all_valid=False):
         out = pair if out is None else out
         return ops.triangle_attention(cfg, pair, mask, 1 if self.mode == "ending" else 0, self.attn.packed_pair(), out,
-                                      residual=residual)
+                                      residual=residual, all_valid=all_valid)
 
     def forward(self, pair: torch.Tensor, mask_2d: torch.Tensor) -> torch.Tensor:
         cfg = AF2_modules._MiniCfg(512, self.pair_dim, self.attn.num_heads, self.attn.head_dim)
@@ -343,8 +343,9 @@ class FoldingBlock(nn.Module):
         self.pair_attn_ending = TriangleAttention(pair_dim, head_dim, num_heads, "ending")
         self.pair_fc = _Transition(pair_dim, transition_factor)
 
-    def forward_(self, cfg, single: torch.Tensor, pair: torch.Tensor, mask: torch.Tensor, probe=None):
-        """In-place form used by Denoiser: updates `single` and `pair` and returns them."""
+    def forward_(self, cfg, single: torch.Tensor, pair: torch.Tensor, mask: torch.Tensor, probe=None, all_valid=False):
+        """In-place form used by Denoiser: updates `single` and `pair` and returns them.  ``all_valid``: every token of the
+        batch is valid (known from prepare_batch): a performance hint for the attention core."""
         rec = probe or (lambda n, t: None)
         ops.single_attention(cfg, single, pair, mask, self.single_attn.packed_single(self.attn_bias[1]), single)
         rec("single_attn", single)
@@ -356,9 +357,9 @@ class FoldingBlock(nn.Module):
         rec("pair_mul_outgoing", pair)
         self.pair_mul_incoming.apply_(cfg, pair, mask)
         rec("pair_mul_incoming", pair)
-        self.pair_attn_starting.apply_(cfg, pair, mask)
+        self.pair_attn_starting.apply_(cfg, pair, mask, all_valid=all_valid)
         rec("pair_attn_starting", pair)
-        self.pair_attn_ending.apply_(cfg, pair, mask)
+        self.pair_attn_ending.apply_(cfg, pair, mask, all_valid=all_valid)
         rec("pair_attn_ending", pair)
         ops.pair_transition(cfg, pair, self.pair_fc.packed_pair(), pair)
         rec("pair_fc", pair)
@@ -393,14 +394,15 @@ class Denoiser(nn.Module):
             FoldingBlock(self.single_dim, self.pair_dim, self.head_dim, self.num_heads, self.transition_factor)
             for _ in range(self.num_blocks)])
 
-    def trunk_(self, single, pair, mask, probe=None):
+    def trunk_(self, single, pair, mask, probe=None, all_valid=False):
         """Everything after the outer-product update, in place: SPAttention, then the folding blocks."""
         rec = probe or (lambda n, t: None)
         self.SPAAttnBlock(single, pair, mask, cfg=self.cfg, out=single)
         rec("Denoiser.SPAAttnBlock", single)
         for k, block in enumerate(self.folding_blocks):
             block.forward_(self.cfg, single, pair, mask,
-                           probe=None if probe is None else (lambda n, t, k=k: probe(f"Denoiser.folding_blocks.{k}.{n}", t)))
+                           probe=None if probe is None else (lambda n, t, k=k: probe(f"Denoiser.folding_blocks.{k}.{n}", t)),
+                           all_valid=all_valid)
         return single, pair
 
     def forward(self, batch, z, t, single, pair, cache):

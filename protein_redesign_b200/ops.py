@@ -150,10 +150,13 @@ def triangle_multiplication(cfg, pair, mask, mode, weights, out, residual=1):
     return out
 
 
-def triangle_attention(cfg, pair, mask, mode, weights, out, residual=1):
+def triangle_attention(cfg, pair, mask, mode, weights, out, residual=1, all_valid: bool = False):
+    """``all_valid``: the caller's promise that ``mask`` is all ones (bit 1 of PrdDims.mode): a pure performance hint, it
+    selects the attention core without the per-sequence handling of ragged batches."""
     B, N = mask.shape
     _chk([pair, mask, out], [F32, F32, F32], ["pair", "mask", "out"])
-    _lib.call("triangle_attention", make_dims(cfg, B, N, mode=mode, residual=residual), [pair, mask], [out], weights)
+    _lib.call("triangle_attention", make_dims(cfg, B, N, mode=(mode & 1) | (2 if all_valid else 0), residual=residual),
+              [pair, mask], [out], weights)
     return out
 
 
