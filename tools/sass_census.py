@@ -19,7 +19,8 @@ def main():
         m = re.match(r"\s*Function : (\S+)", line)
         if m:
             cur = subprocess.run(["c++filt", m.group(1)], capture_output=True, text=True).stdout.strip()
-            cur = re.sub(r"\(.*", "", cur).replace("prd::", "").replace("(anonymous namespace)::", "")
+            cur = cur.replace("(anonymous namespace)::", "").replace("prd::", "")
+            cur = re.sub(r"\(.*", "", cur)
             counts[cur] = collections.Counter()
             continue
         if cur is None:
