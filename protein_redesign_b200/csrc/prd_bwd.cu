@@ -422,14 +422,14 @@ __global__ void __launch_bounds__(128) bw_attn_fwd_kernel(AttnDev a, const float
         }
       }
       const float mnew = fmaxf(m, cmax);
-      const float corr = expf(m - mnew);  // m = -inf on the first group: exp(-inf) = 0
+      const float corr = __expf(m - mnew);  // m = -inf on the first group: exp(-inf) = 0
       l *= corr;
 #pragma unroll
       for (int c = 0; c < 16; ++c) acc[c] *= corr;
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
         if (kk + u < kn) {
-          const float p = expf(sc[u] - mnew);
+          const float p = __expf(sc[u] - mnew);
           l += p;
 #pragma unroll
           for (int c = 0; c < 16; ++c) acc[c] = fmaf(p, sV[kk + u][c], acc[c]);
@@ -505,7 +505,7 @@ __global__ void __launch_bounds__(128) bw_attn_dq_kernel(AttnDev a, const float*
       }
       if (a.bias) d += a.bias[boff + k0 + kk];
       const bool valid = sValid[kk] > 0.5f;
-      const float p = expf((valid ? d : kMaskFill) - L);
+      const float p = __expf((valid ? d : kMaskFill) - L);
       const float ds = valid ? p * (dp - D) : 0.f;  // masked_fill cuts the gradient (modules.py:220)
 #pragma unroll
       for (int c = 0; c < 16; ++c) dq[c] = fmaf(ds, sK[kk][c], dq[c]);
@@ -576,7 +576,7 @@ __global__ void __launch_bounds__(128) bw_attn_dkv_kernel(AttnDev a, const float
         dp = fmaf(sdO[qq][c], v[c], dp);
       }
       if (a.bias) d += a.bias[((b * a.H + h) * a.N + q0 + qq) * (long long)a.N + ki];
-      const float p = expf((valid ? d : kMaskFill) - sL[qq]);
+      const float p = __expf((valid ? d : kMaskFill) - sL[qq]);
 #pragma unroll
       for (int c = 0; c < 16; ++c) dv[c] = fmaf(p, sdO[qq][c], dv[c]);
       if (valid) {

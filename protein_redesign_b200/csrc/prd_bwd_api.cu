@@ -181,8 +181,16 @@ int gated_attn_bwd(bool dry, Carver& c, cudaStream_t st, const AttnGeom& geom, l
   if (bw_gate_bwd(d_og, 64, qkvg + 192, 256, O, 64, dO, 64, dqkvg + 192, 256, R, 64, st)) return 1;
   if (bw_attn_bwd(geom, qkvg, 256, O, lse, dO, Dbuf, dqkvg, 256, dbias, st)) return 1;
   float* dws[4] = {w.dWq, w.dWk, w.dWv, w.dWg};
-  for (int k = 0; k < 4; ++k)
-    if (bw_dw_acc(dqkvg + 64 * k, 256, xh, Cin, R, 64, Cin, dws[k], Cin, k == 3 ? w.dbg : nullptr, 1.f, st)) return 1;
+  const size_t wsz = (size_t)64 * Cin;
+  if (w.dWk == w.dWq + wsz && w.dWv == w.dWq + 2 * wsz && w.dWg == w.dWq + 3 * wsz) {
+    // the four gradients are adjacent (one flat gradient bucket in parameter order, autograd.FlatGrads): one reduction
+    // [R, 256]^T [R, Cin] instead of four that each re-read xh
+    if (bw_dw_acc(dqkvg, 256, xh, Cin, R, 256, Cin, w.dWq, Cin, nullptr, 1.f, st)) return 1;
+    if (bw_colsum(dqkvg + 192, 256, R, 64, w.dbg, 1.f, st)) return 1;
+  } else {
+    for (int k = 0; k < 4; ++k)
+      if (bw_dw_acc(dqkvg + 64 * k, 256, xh, Cin, R, 64, Cin, dws[k], Cin, k == 3 ? w.dbg : nullptr, 1.f, st)) return 1;
+  }
   {
     GemmArgs g = tfg((int)R, Cin, 256, dqkvg, 256, WcatT, 256, dxh, Cin);
     if (gemm_f16(g, st)) return 1;
