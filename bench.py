@@ -11,7 +11,7 @@ value    whole-job steps/sec, inputs resident in HBM, the captured CUDA graph re
          batch of 8, sample-parallel -- no data-path collective).
 e2e      the same metric through the public API (model.sample_step) with HOST buffers: pinned
          host -> device copies of (z, seq_t, mask, t) and device -> host reads of
-         (noise_pred, seq_pred) inside the timed region, eager launches (no graph).
+         (noise_pred, seq_pred) inside the timed region (sample_step replays its own cached graph).
 roofline the dominant kernel (triangle-attention core), timed alone inside this script.
 cpu_baseline / --impl reference
          the CPU oracle (a port of the reference's PyTorch forward, oracle/denoiser_ref.py) on the
@@ -437,7 +437,7 @@ def run_ours(args):
                        "l2": "per-step working set ~3 GB (pair tensor 537 MB fp32 + workspaces) >> 126 MB L2, no flush needed",
                        "timed": "CUDA-graph replay of one full sampling step (network + DDPM update)"},
             "e2e": {"value": world * 1e3 / ms_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": ms_e2e, "api": "ProteinReDiffModel.sample_step, pinned host buffers, eager launches"},
+                    "ms_per_step": ms_e2e, "api": "ProteinReDiffModel.sample_step (graph-cached per prepared batch), pinned host buffers"},
             "gpu_launches": launches_per_step * args.steps,
             "gpu_launches_per_step": launches_per_step,
             "clocks": clocks,

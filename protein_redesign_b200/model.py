@@ -32,6 +32,7 @@ from .synthetic import NUM_RESIDUE_CLASSES, DenoiserConfig
 import os as _os
 
 _USE_RBF_LUT = _os.environ.get("PRD_RBF_LUT", "1") != "0"
+_STEP_GRAPH = _os.environ.get("PRD_STEP_GRAPH", "1") != "0"
 
 try:  # the reference derives from LightningModule; keep that when Lightning is installed
     import pytorch_lightning as _pl
@@ -160,6 +161,7 @@ class ProteinReDiffModel(_Base):
         self._pack = PackCache()
         self._static_key = None
         self._static = None
+        self._step_graph = None
 
     # ---- argparse surface (reference model.py:129-170) ---------------------------------------
     @staticmethod
@@ -322,7 +324,49 @@ class ProteinReDiffModel(_Base):
         return self._denoise(batch, z, seq_t, mask.contiguous(), t)
 
     def sample_step(self, batch, z, seq_t, mask, t):
+        """reference model.py:318-375.  Repeated calls on the same prepared batch (what a sampling loop does) replay ONE
+        captured CUDA graph of the 119 kernels: the four inputs are copied into the graph's static buffers, the outputs are
+        returned as fresh tensors.  ``PRD_STEP_GRAPH=0`` (or autograd / a CPU tensor) takes the eager path."""
+        if _STEP_GRAPH and z.is_cuda and not torch.is_grad_enabled():
+            return self._sample_step_graph(batch, z, seq_t, mask, t)
         return self._denoise(batch, z, seq_t, mask.contiguous(), t)
+
+    def _sample_step_graph(self, batch, z, seq_t, mask, t):
+        w = self._weights()
+        keys = self._STATIC_KEYS + ("atom_feats",)
+        sg = self._step_graph
+        # every parameter's storage and in-place version (the graph baked the packed copies of ALL of them in)
+        wsig = (sum(p.data_ptr() for p in self.parameters()), sum(tensor_version(p) for p in self.parameters()))
+        stale = sg is None or sg["w"] is not w or sg["wsig"] != wsig or sg["epoch"] != weights_epoch() or tuple(z.shape) != sg["shape"] or any(
+            batch[k] is not tns or tensor_version(batch[k]) != v for k, tns, v in zip(keys, sg["tensors"], sg["versions"]))
+        if stale:
+            self._step_graph = None  # frees the previous graph's pool before the new capture
+            dev = z.device
+            B, N = mask.shape
+            st = {"z": torch.empty(B, N, 3, device=dev), "seq_t": torch.empty(B, N, NUM_RESIDUE_CLASSES, device=dev),
+                  "mask": torch.empty(B, N, device=dev), "t": torch.empty(B, dtype=torch.int64, device=dev)}
+            for k, v in (("z", z), ("seq_t", seq_t), ("mask", mask), ("t", t)):
+                st[k].copy_(v)
+            self._static_embeddings(batch)
+            self._denoise(batch, st["z"], st["seq_t"], st["mask"], st["t"])  # eager warm-up: packs, lazy kernel attributes
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.stream(side):
+                ws = ops.reserve_workspace(self.cfg, B, N, dev)
+                with torch.cuda.graph(graph, stream=side):
+                    out = self._denoise(batch, st["z"], st["seq_t"], st["mask"], st["t"])
+            torch.cuda.current_stream(dev).wait_stream(side)
+            sg = self._step_graph = {"w": w, "wsig": wsig, "epoch": weights_epoch(), "shape": tuple(z.shape), "static": st, "out": out, "graph": graph,
+                                     "ws": ws, "tensors": tuple(batch[k] for k in keys),
+                                     "versions": tuple(tensor_version(batch[k]) for k in keys)}
+        st = sg["static"]
+        st["z"].copy_(z, non_blocking=True)
+        st["seq_t"].copy_(seq_t, non_blocking=True)
+        st["mask"].copy_(mask, non_blocking=True)
+        st["t"].copy_(t, non_blocking=True)
+        sg["graph"].replay()
+        return sg["out"][0].clone(), sg["out"][1].clone()
 
     def predict_step(self, batch, batch_idx, noise: Optional[Dict[str, torch.Tensor]] = None):
         """reference model.py:249-252: sample under the EMA weights (``noise``: optional injected draws, see sample)."""
