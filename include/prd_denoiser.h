@@ -124,8 +124,16 @@ size_t prd_rbf_lut_floats(const PrdDims* d); /* (PRD_RBF_LUT_POINTS + 2) * c_z: 
 int prd_rbf_lut_build(const PrdDims* d, const float* w_dist, const float* centers, float d_max, float* lut, void* stream);
 
 /* --- Denoiser trunk (modules.py:391-404) ------------------------------------------------- */
+/* The pair-bias projections of the single-representation attentions as ONE stream over the pair tensor:
+ * bias_a[b,h,i,j] = (LN(pair[b,i,j,:]) * ln_w_a + ln_b_a) . w_a[h,:] + bvec_a[h]  (SPAttention.linear_z, AF2_modules.py:454-459) and,
+ * optionally, bias_b likewise (the first FoldingBlock's attn_bias, modules.py:300-304: both read the pair tensor the embedding
+ * leaves, SPAttention only updates the single representation).  NULL affine / bias vectors mean identity / zero.
+ * in: [pair]   out: [bias_a f32 B,H,N,N | bias_b (or NULL)]
+ * weights: [ln_w_a | ln_b_a | w_a f32 H x c_z | bvec_a | ln_w_b | ln_b_b | w_b | bvec_b]  -- ALWAYS eight entries */
+PRD_DECLARE_OP(pair_bias)
 /* AF2_modules.py:421-473 SPAttention (+ :251-367, :613-627): single <- LN_a(single) + mha(...).
- * in: [single | pair]  out: [single_out (may alias single)]
+ * in: [single | pair | bias f32 B,H,N,N precomputed by prd_pair_bias_fwd (or NULL: projected here)] -- ALWAYS three entries
+ * out: [single_out (may alias single)]
  * weights: [ln_m_w | ln_m_b | ln_z_w | ln_z_b | w_z f32 H x c_z | w_q_h | w_k_h | w_v_h | w_g_h | b_g | w_o_h | b_o] */
 PRD_DECLARE_OP(spattention)
 /* modules.py:300-304 attn_bias + modules.py:185-225 Attention on the single rep + residual (:335).
@@ -147,7 +155,11 @@ PRD_DECLARE_OP(triangle_multiplication)
  * in: [pair | mask]  out: [pair_out]
  * weights: [w_qkvg_h 4Hc x c_z (q;k;v;gate) | b_gate f32 Hc | w_o_h c_z x Hc | b_o] */
 PRD_DECLARE_OP(triangle_attention)
-/* modules.py:321-326,342 pair_fc + residual.  in: [pair]  out: [pair_out]  weights: [w1_h | b1 | w2_h | b2] */
+/* modules.py:321-326,342 pair_fc + residual.  in: [pair]
+ * out: [pair_out | bias_next f32 B,H,N,N (or NULL)] -- ALWAYS two entries; bias_next = the NEXT FoldingBlock's attn_bias
+ *      (modules.py:300-304) of the updated rows, emitted from the output epilogue (pair_dim 64) so that the pair tensor is not read
+ *      again for it; pass it to prd_single_attention_fwd as in[3] with pair = NULL
+ * weights: [w1_h | b1 | w2_h | b2 | w_bias f32 H x c_z (or NULL) | b_bias f32 H (or NULL)] -- ALWAYS six entries */
 PRD_DECLARE_OP(pair_transition)
 /* modules.py:403  pair <- 0.5 (pair + pair^T).  out: [pair] */
 PRD_DECLARE_OP(symmetrize)

@@ -17,7 +17,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libprd_sm100.so")
 
 OPS = (
-    "esm_embed", "single_embed", "pair_embed_static", "opm_project", "pair_embed", "spattention",
+    "esm_embed", "single_embed", "pair_embed_static", "opm_project", "pair_embed", "pair_bias", "spattention",
     "single_attention", "single_transition", "outer_linear", "triangle_multiplication",
     "triangle_attention", "pair_transition", "symmetrize", "coord_head", "seq_head", "remove_mean",
     "sampler_update", "diffusion_q", "diffusion_loss", "decode_argmax", "kabsch",

@@ -205,10 +205,14 @@ int prd_spattention_fwd(const PrdDims* d, const void* const* in, void* const* ou
   const int B = d->B, N = d->N, CS = d->c_s, H = d->H, M = B * N, HC = H * CS, Np = plane_ld(N);
   const float* single_src = in_ptr<float>(in, 0);
   float* single = out_ptr<float>(out, 0);
-  // pair bias: LN_affine(pair) . w_z  -> [B,H,N,N]
-  if (pair_bias_proj(pd(d), H, in_ptr<float>(in, 1), in_ptr<float>(w, 2), in_ptr<float>(w, 3), in_ptr<float>(w, 4),
-                     nullptr, s.bias, st))
-    return 1;
+  // pair bias: LN_affine(pair) . w_z  -> [B,H,N,N]   (or precomputed by prd_pair_bias_fwd: in[2])
+  const float* bias_in = in_ptr<float>(in, 2);
+  if (bias_in == nullptr) {
+    if (pair_bias_proj(pd(d), H, in_ptr<float>(in, 1), in_ptr<float>(w, 2), in_ptr<float>(w, 3), in_ptr<float>(w, 4),
+                       nullptr, s.bias, st))
+      return 1;
+    bias_in = s.bias;
+  }
   if (layernorm_rows(single_src, M, CS, in_ptr<float>(w, 0), in_ptr<float>(w, 1), s.xn16, s.xn32, st)) return 1;
   {  // q, k  [M, H*CS] fp16
     GemmArgs g = linear_args(M, HC, CS, s.xn16, in_ptr<__half>(w, 5), s.q, 1);
@@ -236,7 +240,7 @@ int prd_spattention_fwd(const PrdDims* d, const void* const* in, void* const* ou
     g.A = s.q; g.lda = HC; g.a_bs1 = CS; g.a_bs2 = (long long)N * HC;
     g.B = s.k; g.ldb = HC; g.b_bs1 = CS; g.b_bs2 = (long long)N * HC;
     g.alpha = 1.0f / sqrtf((float)CS);
-    g.add = s.bias; g.ldadd = N; g.add_bs1 = (long long)N * N; g.add_bs2 = (long long)H * N * N;
+    g.add = bias_in; g.ldadd = N; g.add_bs1 = (long long)N * N; g.add_bs2 = (long long)H * N * N;
     g.C = s.bias; g.ldc = N; g.c_bs1 = (long long)N * N; g.c_bs2 = (long long)H * N * N;
     if (gemm_f16(g, st)) return 1;
   }
@@ -257,6 +261,18 @@ int prd_spattention_fwd(const PrdDims* d, const void* const* in, void* const* ou
     if (gemm_f16(g, st)) return 1;
   }
   return 0;
+}
+
+// -------------------------------------------------------------------------------- pair_bias
+size_t prd_pair_bias_workspace_bytes(const PrdDims*) { return 256; }
+int prd_pair_bias_fwd(const PrdDims* d, const void* const* in, void* const* out, const void* const* w, void*, size_t,
+                      void* stream) {
+  if (prd_device_check()) return 1;
+  PRD_REQUIRE(out[0] != nullptr && w[2] != nullptr, "pair_bias: the first projection is mandatory");
+  PRD_REQUIRE(out[1] == nullptr || w[6] != nullptr, "pair_bias: second output without second weight");
+  return pair_bias_proj2(pd(d), d->H, in_ptr<float>(in, 0), in_ptr<float>(w, 0), in_ptr<float>(w, 1), in_ptr<float>(w, 2),
+                         in_ptr<float>(w, 3), out_ptr<float>(out, 0), in_ptr<float>(w, 4), in_ptr<float>(w, 5), in_ptr<float>(w, 6),
+                         in_ptr<float>(w, 7), out_ptr<float>(out, 1), S(stream));
 }
 
 // ------------------------------------------------------------------------ single_attention
@@ -499,8 +515,12 @@ size_t prd_pair_transition_workspace_bytes(const PrdDims*) { return 256; }
 int prd_pair_transition_fwd(const PrdDims* d, const void* const* in, void* const* out, const void* const* w, void*,
                             size_t, void* stream) {
   if (prd_device_check()) return 1;
+  // out[1] (optional): the next FoldingBlock's attn_bias [B,H,N,N] of the updated pair (weights[4], [5] = its W, b)
+  float* bias_out = out_ptr<float>(out, 1);
+  PRD_REQUIRE(bias_out == nullptr || (d->H == 4 && w[4] != nullptr), "pair_transition: fused attn_bias needs 4 heads and its weight");
   return pair_transition(pd(d), in_ptr<float>(in, 0), out_ptr<float>(out, 0), d->residual, in_ptr<__half>(w, 0), in_ptr<float>(w, 1),
-                         in_ptr<__half>(w, 2), in_ptr<float>(w, 3), d->c_z * d->tf, S(stream));
+                         in_ptr<__half>(w, 2), in_ptr<float>(w, 3), d->c_z * d->tf, in_ptr<float>(w, 4), in_ptr<float>(w, 5), bias_out,
+                         S(stream));
 }
 
 // ------------------------------------------------------------------------------ symmetrize

@@ -47,8 +47,11 @@ inline int plane_ld(int N) { return round_up(N, 64); }  // row stride (halves) o
 inline int xplane_ld(int N) { return round_up(N, 8); }  // row stride (halves) of the fp16 contraction-result planes
 
 // All residual ops: dst = (residual ? src : 0) + update; dst may alias src.
+// bias_out (optional, [B,4,N,N]): the NEXT block's attention bias of the updated rows, LN(dst row) . w_bias^T + b_bias
+// (modules.py:300-304), emitted from the output epilogue so that the pair tensor is not read again for it
 int pair_transition(const PairDims& d, const float* pair, float* dst, int residual, const __half* w1, const float* b1,
-                    const __half* w2, const float* b2, int hidden, cudaStream_t s);
+                    const __half* w2, const float* b2, int hidden, const float* w_bias, const float* b_bias, float* bias_out,
+                    cudaStream_t s);
 // mode 0 = outgoing, 1 = incoming.  ab: [2][B][CZ][N][plane_ld(N)] fp16 channel planes.
 int trimul_in(const PairDims& d, const float* pair, const float* mask, int mode, const __half* w_in, const float* b_in,
               __half* ab, cudaStream_t s);
@@ -90,6 +93,10 @@ int layernorm_rows(const float* x, int rows, int C, const float* gamma, const fl
 // bias_out[b,h,i,j] = (LN(pair[b,i,j,:]) (affine optional)) . w[h,:] + bvec[h]
 int pair_bias_proj(const PairDims& d, int H, const float* pair, const float* ln_w, const float* ln_b, const float* w,
                    const float* bvec, float* bias_out, cudaStream_t s);
+// the same with an optional second projection of the same rows (bias_out2 NULL = one projection)
+int pair_bias_proj2(const PairDims& d, int H, const float* pair, const float* ln_w, const float* ln_b, const float* w,
+                    const float* bvec, float* bias_out, const float* ln_w2, const float* ln_b2, const float* w2,
+                    const float* bvec2, float* bias_out2, cudaStream_t s);
 int softmax_rows(float* logits, __half* probs, long long rows, int n, int ld_in, int ld_out, cudaStream_t s);
 // FoldingBlock.single_attn core: qkvg [B*N, 4*H*c] fp32 (q|k|v|gate pre-activation, gate bias added),
 // bias [B,H,N,N], mask [B,N] -> og [B*N, H*c] fp16 (gated attention output)

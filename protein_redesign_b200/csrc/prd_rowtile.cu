@@ -272,7 +272,8 @@ struct PtSmem {
   static constexpr int kSl = kH + 2 * 16384;           // 4 row warps x 4 KB
   static constexpr int kStage = kSl + 4 * 4096;        // row stage: 2 boxes x 16 KB
   static constexpr int kBias = kStage + 2 * 16384;     // b1[256], b2[64]
-  static constexpr int kBars = kBias + 320 * 4;
+  static constexpr int kWb = kBias + 320 * 4;          // fused attn_bias: W_b [4][64], {sum_c W_b[h][c]}[4], b_b[4]
+  static constexpr int kBars = kWb + (4 * 64 + 8) * 4;
   static constexpr int kTotal = kBars + 20 * 8 + 16 + 1024;
 };
 }  // namespace
@@ -280,7 +281,8 @@ struct PtSmem {
 __global__ void __launch_bounds__(kPtThreads, 1)
 pair_transition_ws_kernel(const __grid_constant__ CUtensorMap map_rows, float* dst, int residual, long long R,
                           const __half* __restrict__ w1, const float* __restrict__ b1, const __half* __restrict__ w2,
-                          const float* __restrict__ b2) {
+                          const float* __restrict__ b2, const float* __restrict__ w_bias, const float* __restrict__ b_bias,
+                          float* __restrict__ bias_out, unsigned NN) {
   constexpr int CZ = 64, HID = 256;
   extern __shared__ uint8_t raw[];
   pdl_trigger();
@@ -293,6 +295,7 @@ pair_transition_ws_kernel(const __grid_constant__ CUtensorMap map_rows, float* d
   uint8_t* sStage = sm + L::kStage;
   float* sB1 = reinterpret_cast<float*>(sm + L::kBias);
   float* sB2 = sB1 + HID;
+  float* sWb = reinterpret_cast<float*>(sm + L::kWb);
   uint64_t* bars = reinterpret_cast<uint64_t*>(sm + L::kBars);
   uint64_t* a_full = bars;        // [2] 128 row-thread arrivals
   uint64_t* a_empty = bars + 2;   // [2] UMMA commit
@@ -333,6 +336,15 @@ pair_transition_ws_kernel(const __grid_constant__ CUtensorMap map_rows, float* d
   }
   for (int i = threadIdx.x; i < HID; i += kPtThreads) sB1[i] = b1[i];
   for (int i = threadIdx.x; i < CZ; i += kPtThreads) sB2[i] = b2[i];
+  if (bias_out != nullptr) {
+    for (int i = threadIdx.x; i < 4 * CZ; i += kPtThreads) sWb[i] = w_bias[i];
+    if (threadIdx.x < 4) {
+      float sw = 0.f;
+      for (int c = 0; c < CZ; ++c) sw += w_bias[threadIdx.x * CZ + c];
+      sWb[4 * CZ + threadIdx.x] = sw;
+      sWb[4 * CZ + 4 + threadIdx.x] = b_bias ? b_bias[threadIdx.x] : 0.f;
+    }
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -406,10 +418,43 @@ pair_transition_ws_kernel(const __grid_constant__ CUtensorMap map_rows, float* d
           for (int e = 0; e < 4; ++e) {
             v[e] = __uint_as_float(acc[4 * c + e]) + sB2[p * 32 + 4 * c + e];
             if (residual) v[e] += xc[p * 32 + 4 * c + e];
+            xc[p * 32 + 4 * c + e] = v[e];  // the updated row (the input row is not needed any more)
           }
           o[c] = make_uint4(__float_as_uint(v[0]), __float_as_uint(v[1]), __float_as_uint(v[2]), __float_as_uint(v[3]));
         }
         warp_store_rows128(slice, lane, o, dst + row0 * CZ + p * 32, CZ * 4, rows_valid);
+      }
+      if (bias_out != nullptr) {
+        // the NEXT block's attention bias of this row (FoldingBlock.attn_bias, modules.py:300-304): LayerNorm without
+        // affine + H x c_z projection, from the updated row in registers -- the pair tensor is not read again for it.
+        // bias_h = rstd (W_h . x - mean sum(W_h)) + b_h
+        float s4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int i = 0; i < CZ; ++i) s4[i & 3] += xc[i];
+        const float mean = ((s4[0] + s4[1]) + (s4[2] + s4[3])) * (1.0f / CZ);
+        float v4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int i = 0; i < CZ; ++i) {
+          const float dlt = xc[i] - mean;
+          v4[i & 3] = fmaf(dlt, dlt, v4[i & 3]);
+        }
+        const float rstd = rsqrtf(((v4[0] + v4[1]) + (v4[2] + v4[3])) * (1.0f / CZ) + kLnEps);
+        float hb[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int c = 0; c < CZ; c += 4) {
+#pragma unroll
+          for (int h = 0; h < 4; ++h) {
+            const float4 wv = *reinterpret_cast<const float4*>(sWb + h * CZ + c);  // broadcast
+            hb[h] = fmaf(xc[c], wv.x, fmaf(xc[c + 1], wv.y, fmaf(xc[c + 2], wv.z, fmaf(xc[c + 3], wv.w, hb[h]))));
+          }
+        }
+        if (lane < rows_valid) {
+          const unsigned r = static_cast<unsigned>(row0) + lane;
+          const unsigned b = r / NN, ij = r - b * NN;
+#pragma unroll
+          for (int h = 0; h < 4; ++h)
+            bias_out[(static_cast<size_t>(b) * 4 + h) * NN + ij] = rstd * (hb[h] - mean * sWb[4 * CZ + h]) + sWb[4 * CZ + 4 + h];
+        }
       }
 #pragma unroll
       for (int i = 0; i < CZ; ++i) xc[i] = xn[i];
@@ -504,7 +549,8 @@ pair_transition_ws_kernel(const __grid_constant__ CUtensorMap map_rows, float* d
 }
 
 static int launch_pair_transition_ws(const PairDims& d, const float* pair, float* dst, int residual, const __half* w1,
-                                     const float* b1, const __half* w2, const float* b2, cudaStream_t s) {
+                                     const float* b1, const __half* w2, const float* b2, const float* w_bias,
+                                     const float* b_bias, float* bias_out, cudaStream_t s) {
   static_assert(PtSmem::kTotal <= 227 * 1024, "pair_fc shared memory budget");
   if (set_smem(pair_transition_ws_kernel, PtSmem::kTotal)) return 1;
   const long long R = (long long)d.B * d.N * d.N;
@@ -517,15 +563,21 @@ static int launch_pair_transition_ws(const PairDims& d, const float* pair, float
   td.box[0] = 32; td.box[1] = 128;
   if (make_tensor_map(&map_rows, pair, 4, 2, td, true)) return 1;
   PRD_CUDA_OK(launch_pdl(pair_transition_ws_kernel, grid_for(tiles, 1), kPtThreads, PtSmem::kTotal, s, map_rows, dst, residual, R, w1, b1,
-                         w2, b2));
+                         w2, b2, w_bias, b_bias, bias_out, (unsigned)((long long)d.N * d.N)));
   PRD_LAUNCHED();
   return 0;
 }
 
 int pair_transition(const PairDims& d, const float* pair, float* dst, int residual, const __half* w1, const float* b1,
-                    const __half* w2, const float* b2, int hidden, cudaStream_t s) {
-  if (d.CZ == 64 && hidden == 256) return launch_pair_transition_ws(d, pair, dst, residual, w1, b1, w2, b2, s);
-  if (d.CZ == 32 && hidden == 128) return launch_pair_transition<32, 128>(d, pair, dst, residual, w1, b1, w2, b2, s);
+                    const __half* w2, const float* b2, int hidden, const float* w_bias, const float* b_bias, float* bias_out,
+                    cudaStream_t s) {
+  if (d.CZ == 64 && hidden == 256)
+    return launch_pair_transition_ws(d, pair, dst, residual, w1, b1, w2, b2, w_bias, b_bias, bias_out, s);
+  if (d.CZ == 32 && hidden == 128) {
+    if (launch_pair_transition<32, 128>(d, pair, dst, residual, w1, b1, w2, b2, s)) return 1;
+    // the narrow variant has no fused bias epilogue: separate stream kernel on the updated rows
+    return bias_out ? pair_bias_proj(d, 4, dst, nullptr, nullptr, w_bias, b_bias, bias_out, s) : 0;
+  }
   set_error("pair_transition: unsupported pair_dim %d / hidden %d (built: 64/256, 32/128)", d.CZ, hidden);
   return 1;
 }

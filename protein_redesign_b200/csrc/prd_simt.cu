@@ -51,18 +51,23 @@ int layernorm_rows(const float* x, int rows, int C, const float* gamma, const fl
 // thread (~200 KB per SM) are in flight no matter what the warps are doing; LayerNorm and the four
 // head dot products then run thread-locally in registers (no shuffles), and consecutive threads
 // write consecutive positions of the four head planes (full 128-byte lines).
-template <int CZ>
+// kTwo: a second projection (own LayerNorm affine, weights, bias) of the SAME rows in the same pass: SPAttention's bias and
+// the first FoldingBlock's attn_bias are both functions of the pair tensor the embedding leaves (SPAttention only updates
+// the single representation), so one read of P serves both.
+template <int CZ, bool kTwo>
 __global__ void __launch_bounds__(256, 1)
 pair_bias_kernel(const float* __restrict__ pair, long long R, long long NN, const float* __restrict__ ln_w,
                  const float* __restrict__ ln_b, const float* __restrict__ w, const float* __restrict__ bvec,
-                 float* __restrict__ out) {
+                 float* __restrict__ out, const float* __restrict__ ln_w2, const float* __restrict__ ln_b2,
+                 const float* __restrict__ w2, const float* __restrict__ bvec2, float* __restrict__ out2) {
   constexpr int ROWS = 256;                 // elements per stage = threads per CTA
   constexpr int STAGES = 3;
   constexpr int kRowBytes = CZ * 4 + 16;    // padded: same-column reads of 32 lanes hit distinct banks
   constexpr int kStageBytes = ROWS * kRowBytes;
   extern __shared__ __align__(128) uint8_t smem_pb[];
   float* sW = reinterpret_cast<float*>(smem_pb + STAGES * kStageBytes);  // [4][CZ] folded weights, [4] folded bias (16-byte aligned)
-  uint64_t* full = reinterpret_cast<uint64_t*>(sW + 4 * CZ + 4);
+  float* sW2 = sW + 4 * CZ + 4;                                          // the same for the second projection
+  uint64_t* full = reinterpret_cast<uint64_t*>(sW2 + 4 * CZ + 4);
   const int t = threadIdx.x;
   pdl_trigger();
   // fold the affine LayerNorm into the projection:  (y*g + b) . w_h = y . (g*w_h) + b . w_h
@@ -72,6 +77,15 @@ pair_bias_kernel(const float* __restrict__ pair, long long R, long long NN, cons
     if (ln_b)
       for (int c = 0; c < CZ; ++c) acc += ln_b[c] * w[t * CZ + c];
     sW[4 * CZ + t] = acc;
+  }
+  if (kTwo) {
+    for (int i = t; i < 4 * CZ; i += 256) sW2[i] = w2[i] * (ln_w2 ? ln_w2[i % CZ] : 1.0f);
+    if (t < 4) {
+      float acc = bvec2 ? bvec2[t] : 0.f;
+      if (ln_b2)
+        for (int c = 0; c < CZ; ++c) acc += ln_b2[c] * w2[t * CZ + c];
+      sW2[4 * CZ + t] = acc;
+    }
   }
   if (t == 0) {
     for (int s = 0; s < STAGES; ++s) mbar_init(&full[s], ROWS);
@@ -130,36 +144,59 @@ pair_bias_kernel(const float* __restrict__ pair, long long R, long long NN, cons
         acc[h] += x[c] * wv.x + x[c + 1] * wv.y + x[c + 2] * wv.z + x[c + 3] * wv.w;
       }
     }
+    float acc2[4] = {0.f, 0.f, 0.f, 0.f};
+    if (kTwo) {
+#pragma unroll
+      for (int c = 0; c < CZ; c += 4) {
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+          const float4 wv = *reinterpret_cast<const float4*>(sW2 + h * CZ + c);  // broadcast
+          acc2[h] += x[c] * wv.x + x[c + 1] * wv.y + x[c + 2] * wv.z + x[c + 3] * wv.w;
+        }
+      }
+    }
     const long long e = chunk * ROWS + t;
     if (e < R) {
       const long long b = e / NN;
       const long long ij = e - b * NN;
 #pragma unroll
       for (int h = 0; h < 4; ++h) out[(b * 4 + h) * NN + ij] = acc[h] * rstd + sW[4 * CZ + h];
+      if (kTwo) {
+#pragma unroll
+        for (int h = 0; h < 4; ++h) out2[(b * 4 + h) * NN + ij] = acc2[h] * rstd + sW2[4 * CZ + h];
+      }
     }
   }
 }
 
-int pair_bias_proj(const PairDims& d, int H, const float* pair, const float* ln_w, const float* ln_b, const float* w,
-                   const float* bvec, float* bias_out, cudaStream_t s) {
+int pair_bias_proj2(const PairDims& d, int H, const float* pair, const float* ln_w, const float* ln_b, const float* w,
+                    const float* bvec, float* bias_out, const float* ln_w2, const float* ln_b2, const float* w2,
+                    const float* bvec2, float* bias_out2, cudaStream_t s) {
   PRD_REQUIRE(H == 4, "pair_bias_proj: num_heads %d unsupported (built for 4)", H);
   const long long NN = (long long)d.N * d.N, R = NN * d.B;
   const long long nchunks = (R + 255) / 256;
   const int blocks = (int)(nchunks < kNumSMs ? nchunks : kNumSMs);
+  const bool two = bias_out2 != nullptr;
   if (d.CZ == 64) {
-    constexpr int smem = 3 * 256 * (64 * 4 + 16) + 64 + (4 * 64 + 4) * 4;
-    PRD_CUDA_OK(cudaFuncSetAttribute(pair_bias_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    PRD_CUDA_OK(launch_pdl(pair_bias_kernel<64>, blocks, 256, smem, s, pair, R, NN, ln_w, ln_b, w, bvec, bias_out));
+    constexpr int smem = 3 * 256 * (64 * 4 + 16) + 64 + 2 * (4 * 64 + 4) * 4;
+    auto kern = two ? pair_bias_kernel<64, true> : pair_bias_kernel<64, false>;
+    PRD_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    PRD_CUDA_OK(launch_pdl(kern, blocks, 256, smem, s, pair, R, NN, ln_w, ln_b, w, bvec, bias_out, ln_w2, ln_b2, w2, bvec2, bias_out2));
   } else if (d.CZ == 32) {
-    constexpr int smem = 3 * 256 * (32 * 4 + 16) + 64 + (4 * 32 + 4) * 4;
-    PRD_CUDA_OK(cudaFuncSetAttribute(pair_bias_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    PRD_CUDA_OK(launch_pdl(pair_bias_kernel<32>, blocks, 256, smem, s, pair, R, NN, ln_w, ln_b, w, bvec, bias_out));
+    constexpr int smem = 3 * 256 * (32 * 4 + 16) + 64 + 2 * (4 * 32 + 4) * 4;
+    auto kern = two ? pair_bias_kernel<32, true> : pair_bias_kernel<32, false>;
+    PRD_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    PRD_CUDA_OK(launch_pdl(kern, blocks, 256, smem, s, pair, R, NN, ln_w, ln_b, w, bvec, bias_out, ln_w2, ln_b2, w2, bvec2, bias_out2));
   } else {
     set_error("pair_bias_proj: unsupported pair_dim %d", d.CZ);
     return 1;
   }
   PRD_LAUNCHED();
   return 0;
+}
+int pair_bias_proj(const PairDims& d, int H, const float* pair, const float* ln_w, const float* ln_b, const float* w,
+                   const float* bvec, float* bias_out, cudaStream_t s) {
+  return pair_bias_proj2(d, H, pair, ln_w, ln_b, w, bvec, bias_out, nullptr, nullptr, nullptr, nullptr, nullptr, s);
 }
 
 // -----------------------------------------------------------------------------------------

@@ -33,14 +33,17 @@ constexpr float kG4LazyBound = 14.0f;  // log2: P <= 2^14 < fp16 max
 
 // exp2 of one 16-column chunk of scores (already in registers): running max tracking, P = exp2(s - m) (MUFU on 3/4 of
 // the pairs, FMA-pipe polynomial on 1/4), packed row sum, fp16 pack, two 16-byte stores into the P row.
-template <int kPolyMask>  // bit j set: pair j of the chunk (0..7) takes the FMA-pipe polynomial instead of MUFU
+// kTrackMax: keep the running maximum of the scores in rm (the exact path needs it; the fast path detects an overflow of
+// the lazy bound through the row SUM instead -- any P > 2^14 makes the fp32 sum exceed 2^14 -- which removes one FMNMX3
+// per pair, ~12 % of the fast path's instructions, from a loop that is issue bound)
+template <int kPolyMask, bool kTrackMax = true>  // bit j set: pair j of the chunk (0..7) takes the FMA-pipe polynomial instead of MUFU
 __device__ __forceinline__ void g4_chunk(const uint32_t (&s)[16], uint64_t nm2, uint64_t (&racc)[2], float (&rm)[2],
                                          uint32_t sP_row, int t, int c, uint64_t* p_free = nullptr, uint32_t p_parity = 0) {
   uint32_t ph[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const float a = __uint_as_float(s[2 * j]), b = __uint_as_float(s[2 * j + 1]);
-    rm[j & 1] = fmax3(rm[j & 1], a, b);
+    if (kTrackMax) rm[j & 1] = fmax3(rm[j & 1], a, b);
     uint64_t y = fadd2(pack_f2(a, b), nm2);
     if ((kPolyMask >> j) & 1) {
       y = exp2_poly2(y);
@@ -123,7 +126,7 @@ __device__ __forceinline__ int g4_eff_tiles(const float* __restrict__ mask, cons
   return (padded_seq || bb >= kG4MaxBatch) ? nkt : sNkEff[bb];
 }
 
-template <bool kFused, int kPM = 0x88, bool kRagged = true>
+template <bool kFused, int kPM = 0x88, bool kRagged = true, bool kSumCheck = true>
 __global__ void __launch_bounds__(kG4Threads, 1)
 triattn_flash_g4_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
                         const __grid_constant__ CUtensorMap map_vt, const float* __restrict__ mask,
@@ -293,27 +296,30 @@ triattn_flash_g4_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_
               tmem_ld16(tS, sa);
               tmem_ld_wait16(sa);
               tmem_ld16(tS + 16, sb);
-              g4_chunk<kPM>(sa, nm2, racc, rm, sP_row, t, 0, G >= 1 ? pv : nullptr, (G - 1) & 1);
+              g4_chunk<kPM, !kSumCheck>(sa, nm2, racc, rm, sP_row, t, 0, G >= 1 ? pv : nullptr, (G - 1) & 1);
               tmem_ld_wait16(sb);
               tmem_ld16(tS + 32, sa);
-              g4_chunk<kPM>(sb, nm2, racc, rm, sP_row, t, 1);
+              g4_chunk<kPM, !kSumCheck>(sb, nm2, racc, rm, sP_row, t, 1);
               tmem_ld_wait16(sa);
               tmem_ld16(tS + 48, sb);
-              g4_chunk<kPM>(sa, nm2, racc, rm, sP_row, t, 2);
+              g4_chunk<kPM, !kSumCheck>(sa, nm2, racc, rm, sP_row, t, 2);
               tmem_ld_wait16(sb);
-              // the last chunk is in registers: decide NOW whether a score would push P past 2^14 (then the item is
-              // redone on the exact path; warp-uniform, the TMEM rescale there is warp-collective) -- otherwise S is
-              // released a quarter of an item before P is complete, so S_{G+1} is ready when this item ends
+              // the last chunk is in registers: decide NOW whether a score pushes P past 2^14 (then the item is redone on
+              // the exact path; warp-uniform, the TMEM rescale there is warp-collective) -- otherwise S is released a
+              // quarter of an item before P is complete, so S_{G+1} is ready when this item ends.  Chunks 0-2: through
+              // their row sum (a P above 2^14 makes the sum exceed it); last chunk: through its raw scores.
               {
-                float m3 = fmaxf(rm[0], rm[1]);
+                float p0, p1;
+                unpack_f2(fadd2(racc[0], racc[1]), p0, p1);
+                float m3 = kSumCheck ? -INFINITY : fmaxf(rm[0], rm[1]);
 #pragma unroll
                 for (int j = 0; j < 16; j += 2) m3 = fmax3(m3, __uint_as_float(sb[j]), __uint_as_float(sb[j + 1]));
-                exact = __any_sync(0xffffffffu, m3 - mrow[h] > kG4LazyBound);
+                exact = __any_sync(0xffffffffu, (m3 - mrow[h] > kG4LazyBound) || (kSumCheck && !(p0 + p1 <= 16384.0f)));
               }
               if (!exact) {
                 tc_fence_before();
                 mbar_arrive(sc);
-                g4_chunk<kPM>(sb, nm2, racc, rm, sP_row, t, 3);
+                g4_chunk<kPM, !kSumCheck>(sb, nm2, racc, rm, sP_row, t, 3);
                 float r0, r1;
                 unpack_f2(fadd2(racc[0], racc[1]), r0, r1);
                 lrow[h] += r0 + r1;
@@ -649,7 +655,12 @@ static int g4_launch(const PairDims& d, const float* mask, const __half* q, cons
     // kRagged = false: the variant without per-sequence tile counts (all-valid batches; correct for any mask, it just
     // takes the general masked path on every tile of a ragged one).  PRD_FLASH_RAGGED=0 forces it (A/B timing).
     static const int ragged_env = !(getenv("PRD_FLASH_RAGGED") && getenv("PRD_FLASH_RAGGED")[0] == '0');
-    if (!ragged_env || d.all_valid) {
+    static const int sumcheck = !(getenv("PRD_FLASH_SUMCHECK") && getenv("PRD_FLASH_SUMCHECK")[0] == '0');
+    if ((!ragged_env || d.all_valid) && !sumcheck) {
+      auto kern0 = triattn_flash_g4_kernel<false, 0x88, false, false>;
+      PRD_CUDA_OK(cudaFuncSetAttribute(kern0, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      PRD_CUDA_OK(launch_pdl(kern0, grid, kG4Threads, smem, s, mq, mk, mv, mask, g, og, N, (int)nseq, G4OutProj{}));
+    } else if (!ragged_env || d.all_valid) {
       auto kern0 = triattn_flash_g4_kernel<false, 0x88, false>;
       PRD_CUDA_OK(cudaFuncSetAttribute(kern0, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
       PRD_CUDA_OK(launch_pdl(kern0, grid, kG4Threads, smem, s, mq, mk, mv, mask, g, og, N, (int)nseq, G4OutProj{}));

@@ -110,12 +110,17 @@ class SPAttention(nn.Module):
 
         return self._pack.get(srcs, build)
 
+    def bias_projection(self):
+        """(ln_weight, ln_bias, w_z, None) of linear_z for ops.pair_bias."""
+        w = self.packed_weights()
+        return (w[2], w[3], w[4], None)
+
     def forward(self, m: torch.Tensor, z: Optional[torch.Tensor] = None, mask: Optional[torch.Tensor] = None,
-                cfg=None, out: Optional[torch.Tensor] = None):
+                cfg=None, out: Optional[torch.Tensor] = None, bias: Optional[torch.Tensor] = None):
         if z is None:
             raise ValueError("pair embedding z is required")
         cfg = cfg if cfg is not None else _MiniCfg(self.c_in, self.c_z, self.no_heads)
-        return ops.spattention(cfg, m.contiguous(), z.contiguous(), self.packed_weights(), out=out)
+        return ops.spattention(cfg, m.contiguous(), z.contiguous(), self.packed_weights(), out=out, bias=bias)
 
 
 class OuterProductUpdate(nn.Module):

@@ -22,6 +22,11 @@ from ._packing import PackCache, f32, half, split_k, split_rows
 from .models import AF2_modules
 from .synthetic import ATOM_VOCAB, BOND_VOCAB, DenoiserConfig
 
+import os as _os
+
+# PRD_FUSE_BIAS=0: every attention bias gets its own pass over the pair tensor again (A/B timing)
+_FUSE_BIAS = _os.environ.get("PRD_FUSE_BIAS", "1") != "0"
+
 
 class _FusedOnly(nn.Module):
     """Parameter holder whose arithmetic lives inside a fused kernel."""
@@ -343,11 +348,24 @@ class FoldingBlock(nn.Module):
         self.pair_attn_ending = TriangleAttention(pair_dim, head_dim, num_heads, "ending")
         self.pair_fc = _Transition(pair_dim, transition_factor)
 
-    def forward_(self, cfg, single: torch.Tensor, pair: torch.Tensor, mask: torch.Tensor, probe=None, all_valid=False):
+    def bias_projection(self):
+        """(None, None, w, b) of attn_bias (LayerNorm without affine) for ops.pair_bias / ops.pair_transition."""
+        w = self.single_attn.packed_single(self.attn_bias[1])
+        return (None, None, w[0], w[1])
+
+    def forward_(self, cfg, single: torch.Tensor, pair: torch.Tensor, mask: torch.Tensor, probe=None, all_valid=False,
+                 attn_bias=None, next_block=None):
         """In-place form used by Denoiser: updates `single` and `pair` and returns them.  ``all_valid``: every token of the
-        batch is valid (known from prepare_batch): a performance hint for the attention core."""
+        batch is valid (known from prepare_batch): a performance hint for the attention core.  ``attn_bias``: this block's
+        [B, H, N, N] bias already projected from the incoming pair tensor (by the previous block's pair_fc epilogue or by
+        ops.pair_bias); ``next_block``: emit the next block's bias from this block's pair_fc -- the call then returns
+        (single, pair, bias_next)."""
         rec = probe or (lambda n, t: None)
-        ops.single_attention(cfg, single, pair, mask, self.single_attn.packed_single(self.attn_bias[1]), single)
+        if attn_bias is not None:
+            ops.single_attention(cfg, single, None, mask, self.single_attn.packed_single(self.attn_bias[1]), single,
+                                 attn_bias=attn_bias)
+        else:
+            ops.single_attention(cfg, single, pair, mask, self.single_attn.packed_single(self.attn_bias[1]), single)
         rec("single_attn", single)
         ops.single_transition(cfg, single, self.single_fc.packed_single(), single)
         rec("single_fc", single)
@@ -361,6 +379,11 @@ class FoldingBlock(nn.Module):
         rec("pair_attn_starting", pair)
         self.pair_attn_ending.apply_(cfg, pair, mask, all_valid=all_valid)
         rec("pair_attn_ending", pair)
+        if next_block is not None:
+            proj = next_block.bias_projection()
+            _, bias_next = ops.pair_transition(cfg, pair, self.pair_fc.packed_pair(), pair, next_bias=(proj[2], proj[3]))
+            rec("pair_fc", pair)
+            return single, pair, bias_next
         ops.pair_transition(cfg, pair, self.pair_fc.packed_pair(), pair)
         rec("pair_fc", pair)
         return single, pair
@@ -397,12 +420,26 @@ class Denoiser(nn.Module):
     def trunk_(self, single, pair, mask, probe=None, all_valid=False):
         """Everything after the outer-product update, in place: SPAttention, then the folding blocks."""
         rec = probe or (lambda n, t: None)
-        self.SPAAttnBlock(single, pair, mask, cfg=self.cfg, out=single)
+        blocks = list(self.folding_blocks)
+        if not _FUSE_BIAS or not blocks:
+            self.SPAAttnBlock(single, pair, mask, cfg=self.cfg, out=single)
+            rec("Denoiser.SPAAttnBlock", single)
+            for k, block in enumerate(blocks):
+                block.forward_(self.cfg, single, pair, mask,
+                               probe=None if probe is None else (lambda n, t, k=k: probe(f"Denoiser.folding_blocks.{k}.{n}", t)),
+                               all_valid=all_valid)
+            return single, pair
+        # the pair-bias projections never get their own pass over the pair tensor: SPAttention's and the first block's come
+        # out of ONE stream (SPAttention does not touch the pair tensor), block k + 1's out of block k's pair_fc epilogue
+        bias_spa, bias = ops.pair_bias(self.cfg, pair, self.SPAAttnBlock.bias_projection(), blocks[0].bias_projection())
+        self.SPAAttnBlock(single, pair, mask, cfg=self.cfg, out=single, bias=bias_spa)
         rec("Denoiser.SPAAttnBlock", single)
-        for k, block in enumerate(self.folding_blocks):
-            block.forward_(self.cfg, single, pair, mask,
-                           probe=None if probe is None else (lambda n, t, k=k: probe(f"Denoiser.folding_blocks.{k}.{n}", t)),
-                           all_valid=all_valid)
+        for k, block in enumerate(blocks):
+            nxt = blocks[k + 1] if k + 1 < len(blocks) else None
+            res = block.forward_(self.cfg, single, pair, mask,
+                                 probe=None if probe is None else (lambda n, t, k=k: probe(f"Denoiser.folding_blocks.{k}.{n}", t)),
+                                 all_valid=all_valid, attn_bias=bias, next_block=nxt)
+            bias = res[2] if nxt is not None else None
         return single, pair
 
     def forward(self, batch, z, t, single, pair, cache):

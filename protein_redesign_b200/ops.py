@@ -114,11 +114,26 @@ def rbf_lut_build(cfg, w_dist, centers, d_max=None):
     return lut
 
 
-def spattention(cfg, single, pair, weights, out=None):
+def pair_bias(cfg, pair, proj_a, proj_b=None):
+    """The pair-bias projections of the single-representation attentions in ONE pass over the pair tensor.  ``proj_*`` =
+    (ln_weight or None, ln_bias or None, w [H, c_z], bias [H] or None), fp32.  Returns (bias_a, bias_b or None), each
+    [B, H, N, N]."""
+    B, N = pair.shape[:2]
+    _chk([pair], [F32], ["pair"])
+    H = proj_a[2].shape[0]
+    bias_a = torch.empty(B, H, N, N, dtype=F32, device=pair.device)
+    bias_b = torch.empty(B, H, N, N, dtype=F32, device=pair.device) if proj_b is not None else None
+    weights = list(proj_a) + (list(proj_b) if proj_b is not None else [None] * 4)
+    _lib.call("pair_bias", make_dims(cfg, B, N), [pair], [bias_a, bias_b], weights)
+    return bias_a, bias_b
+
+
+def spattention(cfg, single, pair, weights, out=None, bias=None):
+    """``bias``: the [B, H, N, N] pair bias precomputed by :func:`pair_bias` (None: projected inside the op)."""
     B, N, _ = single.shape
-    _chk([single, pair], [F32, F32], ["single", "pair"])
+    _chk([single, pair, bias], [F32, F32, F32], ["single", "pair", "bias"])
     out = torch.empty_like(single) if out is None else out
-    _lib.call("spattention", make_dims(cfg, B, N), [single, pair], [out], weights)
+    _lib.call("spattention", make_dims(cfg, B, N), [single, pair, bias], [out], weights)
     return out
 
 
@@ -160,11 +175,18 @@ def triangle_attention(cfg, pair, mask, mode, weights, out, residual=1, all_vali
     return out
 
 
-def pair_transition(cfg, pair, weights, out, residual=1):
+def pair_transition(cfg, pair, weights, out, residual=1, next_bias=None):
+    """``next_bias`` = (w [H, c_z], b [H]) of the NEXT FoldingBlock's attn_bias: its [B, H, N, N] bias of the updated pair is
+    emitted from the same kernel and returned as the second value (None otherwise)."""
     B, N = pair.shape[:2]
     _chk([pair, out], [F32, F32], ["pair", "out"])
-    _lib.call("pair_transition", make_dims(cfg, B, N, residual=residual), [pair], [out], weights)
-    return out
+    bias_out, extra = None, [None, None]
+    if next_bias is not None:
+        _chk(list(next_bias), [F32, F32], ["w_bias", "b_bias"])
+        bias_out = torch.empty(B, next_bias[0].shape[0], N, N, dtype=F32, device=pair.device)
+        extra = list(next_bias)
+    _lib.call("pair_transition", make_dims(cfg, B, N, residual=residual), [pair], [out, bias_out], list(weights)[:4] + extra)
+    return out if next_bias is None else (out, bias_out)
 
 
 def symmetrize(cfg, pair):

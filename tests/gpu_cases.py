@@ -1179,3 +1179,31 @@ def case_mask_contract(cfg=syn.PAPER, B=1, N=40, seed=61):
 
 
 CASES["mask_contract"] = lambda: case_mask_contract()
+
+
+def case_fused_bias(cfg=syn.PAPER, B=2, N=72, seed=62):
+    """The pair-bias projections that no longer get their own pass over the pair tensor: ops.pair_bias (SPAttention's
+    linear_z and the first block's attn_bias in one stream) and the next block's attn_bias out of pair_fc's epilogue."""
+    m, sd = _model(cfg, seed)
+    _, pair, _ = _pair_inputs(cfg, B, N, seed)
+    den = m.Denoiser
+    p_spa = "Denoiser.SPAAttnBlock."
+    want_spa = F.linear(ref._ln(pair, sd[p_spa + "linear_z.0.weight"], sd[p_spa + "linear_z.0.bias"]),
+                        sd[p_spa + "linear_z.1.weight"]).permute(0, 3, 1, 2)
+    want_b0 = ref.attn_bias_from_pair(sd, _block_prefix(0), pair)
+    got_spa, got_b0 = ops.pair_bias(cfg, pair.to(DEV).contiguous(), den.SPAAttnBlock.bias_projection(),
+                                    den.folding_blocks[0].bias_projection())
+    only_spa, none = ops.pair_bias(cfg, pair.to(DEV).contiguous(), den.SPAAttnBlock.bias_projection())
+    updated = pair + ref.transition(sd, _block_prefix(0) + "pair_fc.", pair)
+    want_b1 = ref.attn_bias_from_pair(sd, _block_prefix(1), updated)
+    proj = den.folding_blocks[1].bias_projection()
+    p = pair.to(DEV).contiguous()
+    _, got_b1 = ops.pair_transition(cfg, p, den.folding_blocks[0].pair_fc.packed_pair(), p, next_bias=(proj[2], proj[3]))
+    torch.cuda.synchronize()
+    return {"spa_bias": (rel(got_spa, want_spa), 1e-5), "block0_bias": (rel(got_b0, want_b0), 1e-5),
+            "single_projection": (rel(only_spa, want_spa) + (0.0 if none is None else 1.0), 1e-5),
+            "pair_fc_rows": (rel(p, updated), OP_TOL), "next_block_bias": (rel(got_b1, want_b1), OP_TOL)}
+
+
+CASES["fused_bias"] = lambda: case_fused_bias()
+CASES["fused_bias_readme"] = lambda: case_fused_bias(syn.README, 2, 40)

@@ -39,7 +39,7 @@ CASE_NAMES = [
     "bwd_trimul_outgoing", "bwd_trimul_incoming", "bwd_trimul_n75", "bwd_outer_linear", "bwd_single_attention", "bwd_spattention",
     "bwd_heads", "bwd_embeddings", "bwd_embeddings_readme", "train_step_paper_n72",
     # round 2: Lightning-free predict loop and GPU post-processing
-    "postprocess", "predict_loop", "train_modes", "dw_tc", "mask_contract",
+    "postprocess", "predict_loop", "train_modes", "dw_tc", "mask_contract", "fused_bias", "fused_bias_readme",
 ]
 
 
