@@ -22,6 +22,7 @@
 #include <stdlib.h>
 
 #include <algorithm>
+#include <type_traits>
 
 namespace prd {
 
@@ -274,59 +275,66 @@ triattn_flash_g4_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_
           for (int h = 0; h < 4; ++h, ++G) {
             mbar_wait(s_full, G & 1);
             tc_fence_after();
-            bool exact = !all_valid;
-            if (kt == 0 && all_valid) {
-              // first tile of a unit: the reference max of the lazy scheme comes from the row's first 16 scores instead
-              // of a full max pass (the two-pass exact path cost ~1.5 fast items on 4 of the 32 items of a unit); a row
-              // whose later scores exceed it by more than the lazy bound is redone exactly, like on any other tile
-              uint32_t s0[16];
-              tmem_ld16(tS, s0);
-              tmem_ld_wait16(s0);
-              float m0 = -INFINITY;
-#pragma unroll
-              for (int j = 0; j < 16; j += 2) m0 = fmax3(m0, __uint_as_float(s0[j]), __uint_as_float(s0[j + 1]));
-              mrow[h] = m0;
-            }
-            if (!exact) {
-              // fast item: running max kept; chunk c+1 is loaded from TMEM while chunk c is processed
-              const uint64_t nm2 = pack_f2(-mrow[h], -mrow[h]);
-              uint64_t racc[2] = {0ull, 0ull};
-              float rm[2] = {-INFINITY, -INFINITY};
+            // Every item starts on the fast path (one pass over the scores against a lazily kept reference max); tiles with
+            // masked keys apply the key table to each chunk first and keep all their exponentials on MUFU (the polynomial's
+            // clamp at -24 would weight a masked key with 2^-24 instead of 0).  The two-pass exact path is the fallback for
+            // a row whose scores outgrow the reference max by more than the lazy bound.
+            bool exact = false;
+            auto fast_item = [&](auto masked_c) {
+              constexpr bool kMasked = decltype(masked_c)::value;
+              constexpr int PM = kMasked ? 0 : kPM;
               uint32_t sa[16], sb[16];
               tmem_ld16(tS, sa);
               tmem_ld_wait16(sa);
               tmem_ld16(tS + 16, sb);
-              g4_chunk<kPM, !kSumCheck>(sa, nm2, racc, rm, sP_row, t, 0, G >= 1 ? pv : nullptr, (G - 1) & 1);
+              if (kMasked) g4_mask_chunk(sa, keyp, 0);
+              if (kt == 0) {
+                // first tile of a unit: the reference max comes from the row's first 16 scores instead of a full max pass
+                // (the exact path cost ~1.5 fast items on 4 of the 32 items of a unit)
+                float m0 = -INFINITY;
+#pragma unroll
+                for (int j = 0; j < 16; j += 2) m0 = fmax3(m0, __uint_as_float(sa[j]), __uint_as_float(sa[j + 1]));
+                mrow[h] = m0;
+              }
+              const uint64_t nm2 = pack_f2(-mrow[h], -mrow[h]);
+              uint64_t racc[2] = {0ull, 0ull};
+              float rm[2] = {-INFINITY, -INFINITY};
+              g4_chunk<PM, !kSumCheck>(sa, nm2, racc, rm, sP_row, t, 0, G >= 1 ? pv : nullptr, (G - 1) & 1);
               tmem_ld_wait16(sb);
               tmem_ld16(tS + 32, sa);
-              g4_chunk<kPM, !kSumCheck>(sb, nm2, racc, rm, sP_row, t, 1);
+              if (kMasked) g4_mask_chunk(sb, keyp, 1);
+              g4_chunk<PM, !kSumCheck>(sb, nm2, racc, rm, sP_row, t, 1);
               tmem_ld_wait16(sa);
               tmem_ld16(tS + 48, sb);
-              g4_chunk<kPM, !kSumCheck>(sa, nm2, racc, rm, sP_row, t, 2);
+              if (kMasked) g4_mask_chunk(sa, keyp, 2);
+              g4_chunk<PM, !kSumCheck>(sa, nm2, racc, rm, sP_row, t, 2);
               tmem_ld_wait16(sb);
+              if (kMasked) g4_mask_chunk(sb, keyp, 3);
               // the last chunk is in registers: decide NOW whether a score pushes P past 2^14 (then the item is redone on
               // the exact path; warp-uniform, the TMEM rescale there is warp-collective) -- otherwise S is released a
               // quarter of an item before P is complete, so S_{G+1} is ready when this item ends.  Chunks 0-2: through
               // their row sum (a P above 2^14 makes the sum exceed it); last chunk: through its raw scores.
+              bool redo;
               {
                 float p0, p1;
                 unpack_f2(fadd2(racc[0], racc[1]), p0, p1);
                 float m3 = kSumCheck ? -INFINITY : fmaxf(rm[0], rm[1]);
 #pragma unroll
                 for (int j = 0; j < 16; j += 2) m3 = fmax3(m3, __uint_as_float(sb[j]), __uint_as_float(sb[j + 1]));
-                exact = __any_sync(0xffffffffu, (m3 - mrow[h] > kG4LazyBound) || (kSumCheck && !(p0 + p1 <= 16384.0f)));
+                redo = __any_sync(0xffffffffu, (m3 - mrow[h] > kG4LazyBound) || (kSumCheck && !(p0 + p1 <= 16384.0f)));
               }
-              if (!exact) {
+              if (!redo) {
                 tc_fence_before();
                 mbar_arrive(sc);
-                g4_chunk<kPM, !kSumCheck>(sb, nm2, racc, rm, sP_row, t, 3);
+                g4_chunk<PM, !kSumCheck>(sb, nm2, racc, rm, sP_row, t, 3);
                 float r0, r1;
                 unpack_f2(fadd2(racc[0], racc[1]), r0, r1);
                 lrow[h] += r0 + r1;
               }
-            } else if (G >= 1) {
-              mbar_wait(pv, (G - 1) & 1);
-            }
+              return redo;
+            };
+            if (all_valid) exact = fast_item(std::false_type{});
+            else exact = fast_item(std::true_type{});
             if (exact) {
               // pass 1: row max of the (masked) scores
               float tmax = -INFINITY;
