@@ -660,10 +660,12 @@ def profile_dominant(lib, cfg, B, N, dev, mask, pair, model):
     P = 4.0 * B * N * N * cfg.pair_dim  # bytes of one fp32 pair tensor
     out = []
     ncu = {}
-    tpath = os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")
-    if os.path.exists(tpath) and (B, N) == (BATCH, N_TOKENS):
-        with open(tpath) as f:
-            ncu = json.load(f)
+    if (B, N) == (BATCH, N_TOKENS):  # round 1's captures, overridden by this round's for the kernels that changed
+        for name in ("r01_ncu_traffic.json", "r02_ncu_traffic.json"):
+            tpath = os.path.join(ROOT, "profiles", name)
+            if os.path.exists(tpath):
+                with open(tpath) as f:
+                    ncu.update(json.load(f))
 
     def dram(key):  # dram bytes per launch from the committed ncu --set full capture (None at other sizes)
         e = ncu.get(key)
@@ -683,7 +685,7 @@ def profile_dominant(lib, cfg, B, N, dev, mask, pair, model):
                 "ms_per_launch": ms, "hbm_floor_ms": 1.5 * P / peaks["hbm_gbs"] / 1e6,
                 "hbm_frac": 1.5 * P / ms / 1e6 / peaks["hbm_gbs"],
                 "note": "HBM floor: 0.5 P (a) + 0.5 P (b) + 0.5 P (x as fp16 planes) = 1.5 P; ncu tensor-pipe active 49.5 % "
-                        "(profiles/r01_ncu_traffic.json)"})
+                        "(profiles/r01_ncu_traffic.json: the kernel is unchanged since round 1)"})
     # pair-bias stream: reads P, writes P/16
     ms = time_kernel("pair_bias", pair)
     nbytes = P + P * 4 / cfg.pair_dim
@@ -706,7 +708,7 @@ def profile_dominant(lib, cfg, B, N, dev, mask, pair, model):
             "hbm_achieved_gbs": (traffic / ms / 1e6) if traffic else None,
             "note": "K=16 attention (head dim 16): 275 GFLOP on the tensor pipe against %.2e exp2 per launch; the binding "
                     "unit is the exp2 path (MUFU 16/clk/SM, a quarter of the exp2 moved to an FMA-pipe polynomial), "
-                    "not the tensor pipe; mufu_frac = all-MUFU floor / measured (profiles/r01_flash_variants.md)" % n_exp,
+                    "not the tensor pipe; mufu_frac = all-MUFU floor / measured (profiles/r01_flash_variants.md, profiles/r02_launches.md)" % n_exp,
             "others": out}
     return roof
 
