@@ -695,11 +695,12 @@ int triattn_flash_out_g4(const PairDims& d, const float* mask, const __half* q, 
   return g4_launch(d, mask, q, k, g, vt, nullptr, &op, s);
 }
 
-// The four-group kernel keeps all groups busy when the query tiles per sequence are a multiple of four.
+// The four-group kernel keeps all groups busy when the query tiles per sequence are a multiple of four, but since its
+// first-tile / masked-tile fast paths (round 2) it also beats the two-group kernel when one or two groups idle: N = 300
+// 3.01 -> 2.72 ms per step, N = 140 (README dims) 1.91 -> 1.77 ms (bench.py --workload config2 / config1, PRD_FLASH_G4=0 A/B).
 bool triattn_flash_g4_applies(const PairDims& d) {
   const char* force = getenv("PRD_FLASH_G4");
-  const int nqt = (d.N + 127) / 128;
-  return force ? (force[0] == '1') : (nqt % 4 == 0 && d.N <= 2048);
+  return force ? (force[0] == '1') : d.N <= 2048;
 }
 
 }  // namespace prd
