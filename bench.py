@@ -584,6 +584,8 @@ def run_train(args, dev, rank, local_rank, world, lib):
     clocks = sampler.stop() if sampler else None
     ms = e0.elapsed_time(e1)
     launches = int(lib.prd_launch_count() - c0)
+    if tsg is not None:   # replays do not pass through the library's launch counter: count what the capture recorded
+        launches = tsg.launches_per_step * args.steps
     if world > 1:
         tt = torch.tensor([ms], device=dev, dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)

@@ -92,6 +92,7 @@ def load() -> ctypes.CDLL:
                 f"{LIB_PATH} was built from other sources (library {built}, tree {have}): rebuild with "
                 "protein_redesign_b200/csrc/build.sh -- a stale kernel must never be tested or benchmarked")
         lib.prd_version.restype = ctypes.c_int
+        lib.prd_launch_count.restype = ctypes.c_longlong
         lib.prd_last_error.restype = ctypes.c_char_p
         lib.prd_device_check.restype = ctypes.c_int
         lib.prd_gemm_f16.restype = ctypes.c_int

@@ -363,6 +363,8 @@ class TrainStepGraph:
                     self.loss = _device_step(model, self.static, self.static["x"], self.static["residue_and_atom_mask"], self.t, grads, self.noise)
                 torch.cuda.synchronize(dev)
                 self.graph = torch.cuda.CUDAGraph()
+                lib = _lib.load()
+                c0 = int(lib.prd_launch_count())
                 with torch.cuda.graph(self.graph, stream=side):
                     # inside the graph: the fp16 weight packs are rebuilt IN PLACE from the current fp32 parameters (an
                     # optimiser step between replays is picked up) and the step-invariant embeddings are recomputed from
@@ -370,6 +372,8 @@ class TrainStepGraph:
                     model._static_key = None
                     self.loss = _device_step(model, self.static, self.static["x"], self.static["residue_and_atom_mask"], self.t, grads, self.noise)
                 model._static_key = None
+                #: kernels of libprd_sm100.so inside the captured step (what one replay launches)
+                self.launches_per_step = int(lib.prd_launch_count()) - c0
             torch.cuda.current_stream(dev).wait_stream(side)
 
     def step(self, batch, batch_idx: int = 0, noise=None) -> torch.Tensor:

@@ -600,6 +600,7 @@ static AttnDev attn_dev(const AttnGeom& g) { return AttnDev{g.B, g.N, g.H, g.mod
 static long long attn_nseq(const AttnGeom& g) { return g.mode == 2 ? g.B : (long long)g.B * g.N; }
 
 int bw_attn_fwd(const AttnGeom& g, const float* qkvg, long long ld, float* O, float* lse, cudaStream_t s) {
+  if (bw_attn_tc_enabled()) return bw_attn_tc_fwd(g, qkvg, ld, O, lse, s);
   PRD_REQUIRE(ld % 4 == 0, "attn: row stride must be a multiple of 4 floats");
   const long long nsh = attn_nseq(g) * g.H;
   PRD_REQUIRE(nsh < 2147483647LL, "attn: too many (sequence, head) pairs");
@@ -609,6 +610,7 @@ int bw_attn_fwd(const AttnGeom& g, const float* qkvg, long long ld, float* O, fl
 }
 int bw_attn_bwd(const AttnGeom& g, const float* qkvg, long long ld, const float* O, const float* lse, const float* dO,
                 float* Dbuf, float* dqkvg, long long ldd, float* dbias, cudaStream_t s) {
+  if (bw_attn_tc_enabled()) return bw_attn_tc_bwd(g, qkvg, ld, O, lse, dO, Dbuf, dqkvg, ldd, dbias, s);
   PRD_REQUIRE(ld % 4 == 0, "attn: row stride must be a multiple of 4 floats");
   const long long nsh = attn_nseq(g) * g.H;
   const dim3 grid((unsigned)nsh, (g.N + 127) / 128);

@@ -63,6 +63,13 @@ int bw_attn_fwd(const AttnGeom& g, const float* qkvg, long long ld, float* O, fl
 int bw_attn_bwd(const AttnGeom& g, const float* qkvg, long long ld, const float* O, const float* lse, const float* dO,
                 float* Dbuf, float* dqkvg, long long ldd, float* dbias, cudaStream_t s);
 
+// the same two steps on the warp-level tensor cores (prd_bwd_attn.cu: mma.sync tf32, operands rounded to nearest);
+// bw_attn_fwd / bw_attn_bwd dispatch to them unless PRD_ATTN_SIMT=1 (then: exact fp32 on the FFMA pipe)
+bool bw_attn_tc_enabled();
+int bw_attn_tc_fwd(const AttnGeom& g, const float* qkvg, long long ld, float* O, float* lse, cudaStream_t s);
+int bw_attn_tc_bwd(const AttnGeom& g, const float* qkvg, long long ld, const float* O, const float* lse, const float* dO,
+                   float* Dbuf, float* dqkvg, long long ldd, float* dbias, cudaStream_t s);
+
 // ---- pair-bias projection backward (FoldingBlock.attn_bias, SPAttention.linear_z) ---------------------------------
 // bias[b,h,i,j] = sum_c W[h,c] (LN(pair[b,i,j,:]) gamma + beta)_c (+ bvec[h]).  d_pair += dLN(...), dW, dbvec, dgamma, dbeta +=
 // dbias[((b*H + h)*N + i)*ldb + j]
