@@ -149,6 +149,31 @@ __device__ __forceinline__ void warp_load_rows128(uint8_t* slice, int lane, uint
   for (int c = 0; c < 8; ++c) v[c] = *reinterpret_cast<const uint4*>(slice + lane * 128 + ((c ^ (lane & 7)) << 4));
 }
 
+// The same load in two halves, so that the global loads can be in flight while the caller waits for something else
+// (the GEMM epilogue issues them before tcgen05.wait::ld): issue = coalesced 16-byte loads into registers,
+// finish = transpose through the slice into one row per lane.
+__device__ __forceinline__ void warp_load_rows128_issue(int lane, uint4 (&t)[8], const void* gbase, long long pitch_bytes,
+                                                        int rows_valid) {
+  const uint8_t* gp = reinterpret_cast<const uint8_t*>(gbase) + (lane & 7) * 16;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int row = i * 4 + (lane >> 3);
+    t[i] = make_uint4(0, 0, 0, 0);
+    if (row < rows_valid) t[i] = __ldg(reinterpret_cast<const uint4*>(gp + row * pitch_bytes));
+  }
+}
+__device__ __forceinline__ void warp_load_rows128_finish(uint8_t* slice, int lane, const uint4 (&t)[8], uint4 (&v)[8]) {
+  __syncwarp();
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int row = i * 4 + (lane >> 3), c = lane & 7;
+    *reinterpret_cast<uint4*>(slice + row * 128 + ((c ^ (row & 7)) << 4)) = t[i];
+  }
+  __syncwarp();
+#pragma unroll
+  for (int c = 0; c < 8; ++c) v[c] = *reinterpret_cast<const uint4*>(slice + lane * 128 + ((c ^ (lane & 7)) << 4));
+}
+
 // ---------------------------------------------------------------------------------------
 // mbarrier
 // ---------------------------------------------------------------------------------------
@@ -238,6 +263,12 @@ __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* m
       "l"(m), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
+// shared -> global tile store (bulk async group; the box is clipped at the tensor's bounds)
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, const void* smem_src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(m),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
 __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1) {
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
@@ -303,10 +334,11 @@ __host__ __device__ constexpr uint32_t umma_idesc_tf32(uint32_t M, uint32_t N) {
   return (1u << 4) | (2u << 7) | (2u << 10) | (0u << 15) | (0u << 16) | ((N >> 3) << 17) | ((M >> 4) << 24);
 }
 // Round to nearest tf32 (the tensor core truncates: an unrounded operand carries a systematic -2^-11 bias).
+// cvt.rna.tf32.f32 (nearest, ties away from zero) is emulated on sm_100a with ~6 instructions (SASS: FSETP |x| < inf,
+// LOP3, IADD3, select); the same result for every finite input in two: add half an ulp of the 10-bit mantissa to the
+// magnitude, clear the 13 low bits (inf stays inf, NaN stays NaN).
 __device__ __forceinline__ float round_tf32(float x) {
-  uint32_t u;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
-  return __uint_as_float(u);
+  return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
 }
 
 // D[tmem] (+)= A[smem] * B[smem]^T, one UMMA (K = 16 halves); issued by ONE thread.

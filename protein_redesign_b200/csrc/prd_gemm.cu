@@ -3,11 +3,15 @@
 //   C[b][m][n] = epilogue( alpha * sum_k A[b][m][k] * B[b][n][k] )        (both operands K-major)
 //
 // One CTA computes one 128 x BN output tile: warp 0 = TMA producer, warp 1 = UMMA issuer,
-// warps 2..5 = epilogue (TMEM -> registers -> global).  Operand tiles are [rows x 64] halves
+// warps 2..3 idle (they only complete the first warpgroup, which gives its registers away), warps 4..11 = epilogue
+// (TMEM -> registers -> global; two warps per TMEM lane quarter, alternating 32-column chunks; fp32 results leave as
+// TMA tile stores when the C layout allows a tensor map).  Operand tiles are [rows x 64] halves
 // in SWIZZLE_128B shared memory, STAGES-deep mbarrier ring; the accumulator lives in TMEM.
 //
 // Used for: the triangle-multiplication contraction (per (b, channel) NxNxN GEMMs), every
 // single-representation linear layer, SPAttention logits / PV.  See prd_denoiser.h.
+#include <stdlib.h>
+
 #include "prd_common.cuh"
 #include "prd_kernels.h"
 
@@ -18,7 +22,7 @@ struct GemmSmem {
   static constexpr int kABytes = 128 * 64 * 2;
   static constexpr int kBBytes = BN * 64 * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kEpiBytes = 4 * 4096;  // one 4 KB store-coalescing slice per epilogue warp
+  static constexpr int kEpiBytes = 8 * 4096;  // one 4 KB store-coalescing slice per epilogue warp
   static constexpr int kTotal = STAGES * kStageBytes + kEpiBytes + 1024 /*align slack*/ + 256 /*barriers*/;
   static constexpr int kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;  // two accumulators
 };
@@ -39,6 +43,8 @@ struct GemmEpilogue {
   int c_fp16;
   int mul_step;   // the mul operand gates instead of scaling: v = mul > 0 ? v : 0 (ReLU backward)
   int round_tf32; // fp32 C rounded to nearest tf32 (the result feeds another tf32 GEMM as an operand)
+  int c_tma;      // fp32 C with 16-byte aligned rows / batches: 32 x 32 boxes leave through map_c (clipped at M, N)
+  int c_b1, c_b2; // 1 when that batch index is a coordinate of map_c
 };
 
 struct GemmTiling {
@@ -60,8 +66,9 @@ struct GemmTiling {
 // double buffered in TMEM, so the epilogue of tile i (TMEM -> registers -> global) overlaps the
 // TMA / UMMA main loop of tile i+1.
 template <int BN, int STAGES, bool TF32>
-__global__ void __launch_bounds__(192, 1)
-gemm_f16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, int num_kb,
+__global__ void __launch_bounds__(384, 1)
+gemm_f16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                const __grid_constant__ CUtensorMap map_c, int num_kb,
                 int a_wrap, int b_wrap, GemmTiling tl, int a_b1, int a_b2, int b_b1, int b_b2, GemmEpilogue ep) {
   // TF32: operands are fp32 in memory (kind::tf32 reads the upper 19 bits: producers round to nearest first), one K-block =
   // 32 elements = the same 128-byte swizzle row, one UMMA = K 8 = the same 32-byte descriptor step as 16 halves.
@@ -89,11 +96,12 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tmem_full[b], 1);
-      mbar_init(&tmem_empty[b], 128);
+      mbar_init(&tmem_empty[b], 256);
     }
     fence_barrier_init();
     tma_prefetch_desc(&map_a);
     tma_prefetch_desc(&map_b);
+    if (ep.c_tma) tma_prefetch_desc(&map_c);
   }
   if (warp == 0) tmem_alloc(tmem_slot, L::kTmemCols);
   tc_fence_before();
@@ -101,8 +109,12 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   tc_fence_after();
   pdl_wait();  // everything above touched only weights / shared memory; the predecessor's output is read below
   const uint32_t tmem = *tmem_slot;
+  // 384 threads x 168 registers = 128 x 56 + 256 x 224: the epilogue keeps a chunk of the accumulator and of both [M, N]
+  // epilogue operands in registers
+  // (setmaxnreg at the head of each role's branch)
 
   if (warp == 0) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
     if (lane == 0) {
       long long it = 0;  // running k-block counter across tiles
       for (long long tile = blockIdx.x; tile < tl.total; tile += gridDim.x) {
@@ -121,6 +133,7 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
       }
     }
   } else if (warp == 1) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
     if (lane == 0) {
       constexpr uint32_t idesc = TF32 ? umma_idesc_tf32(128, BN) : umma_idesc_f16(128, BN);
       long long it = 0;
@@ -142,9 +155,15 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         umma_commit(&tmem_full[buf]);
       }
     }
+  } else if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
   } else {
-    // epilogue: warp w may only touch TMEM lanes [32*(w%4), 32*(w%4)+32)
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
+    // epilogue: warp w may only touch TMEM lanes [32*(w%4), 32*(w%4)+32); the two warps of a lane quarter take
+    // alternating column chunks
     const int q = warp & 3;
+    const int half = (warp - 4) >> 2;
+    uint8_t* slice = epi + (warp - 4) * 4096;
     int lt = 0;
     for (long long tile = blockIdx.x; tile < tl.total; tile += gridDim.x, ++lt) {
       int n0, m0, i1, i2;
@@ -172,7 +191,7 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                               ((reinterpret_cast<uintptr_t>(reinterpret_cast<__half*>(ep.C) + boff_c + n0) & 15) == 0);
       if (coalesce16) {
 #pragma unroll 1
-        for (int c = 0; c < BN / 64; ++c) {
+        for (int c = half; c < BN / 64; c += 2) {
           uint32_t r0[32], r1[32];
           uint4 ov[8];
           tmem_ld32(tmem + buf * BN + (static_cast<uint32_t>(q * 32) << 16) + c * 64, r0);
@@ -222,19 +241,32 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                                    pack_half2(__uint_as_float(r1[8 * j + 6]), __uint_as_float(r1[8 * j + 7])));
           }
           __half* cb = reinterpret_cast<__half*>(ep.C) + boff_c + (long long)(m0 + q * 32) * ep.ldc + n0 + c * 64;
-          warp_store_rows128(epi + q * 4096, lane, ov, cb, (long long)ep.ldc * 2, 32);
+          warp_store_rows128(slice, lane, ov, cb, (long long)ep.ldc * 2, 32);
         }
         tc_fence_before();
         mbar_arrive(&tmem_empty[buf]);
         continue;
       }
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int c = half; c < BN / 32; c += 2) {
         uint32_t r[32];
         uint4 ov[8];
         tmem_ld32(tmem + buf * BN + (static_cast<uint32_t>(q * 32) << 16) + c * 32, r);
-        tmem_ld_wait();
         const int col0 = n0 + c * 32;
+        const int rows_left = ep.M - (m0 + q * 32);
+        // the [M, N] epilogue operands of this chunk: coalesced loads issued before the wait on the accumulator
+        const float* mb = ep.mul ? ep.mul + (long long)i1 * ep.mul_bs1 + (long long)i2 * ep.mul_bs2 + (long long)(m0 + q * 32) * ep.ldmul + col0 : nullptr;
+        const float* ab = ep.add ? ep.add + (long long)i1 * ep.add_bs1 + (long long)i2 * ep.add_bs2 + (long long)(m0 + q * 32) * ep.ldadd + col0 : nullptr;
+        const bool mul_fast = mb != nullptr && (col0 + 32 <= ep.N) && ((ep.ldmul & 3) == 0) && ((reinterpret_cast<uintptr_t>(mb) & 15) == 0);
+        const bool add_fast = ab != nullptr && (col0 + 32 <= ep.N) && ((ep.ldadd & 3) == 0) && ((reinterpret_cast<uintptr_t>(ab) & 15) == 0);
+        uint4 mreg[8], areg[8];
+        if (mul_fast) warp_load_rows128_issue(lane, mreg, mb, (long long)ep.ldmul * 4, rows_left);
+        if (add_fast) warp_load_rows128_issue(lane, areg, ab, (long long)ep.ldadd * 4, rows_left);
+        tmem_ld_wait();
+        if (ep.c_tma && (mul_fast || add_fast)) {  // the slice may still be read by this warp's previous tile store
+          if (lane == 0) bulk_wait_read0();
+          __syncwarp();
+        }
         // Epilogue operands: per-element scalar loads (32 bias loads and, per lane, 32 strided mul / add loads per chunk) made
         // the four epilogue warps the bottleneck of every single-representation GEMM (ncu: tensor pipe 3-7 % on the
         // SPAttention logits / PV / gate GEMMs).  Full chunks now take the bias as 8 broadcast float4 loads and the
@@ -274,12 +306,10 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] *= rs;
           }
-          const int rows_left = ep.M - (m0 + q * 32);
           if (ep.mul != nullptr) {
-            const float* mb = ep.mul + (long long)i1 * ep.mul_bs1 + (long long)i2 * ep.mul_bs2 + (long long)(m0 + q * 32) * ep.ldmul + col0;
-            if (chunk_full && ((ep.ldmul & 3) == 0) && ((reinterpret_cast<uintptr_t>(mb) & 15) == 0)) {
+            if (mul_fast) {
               uint4 t4[8];
-              warp_load_rows128(epi + q * 4096, lane, t4, mb, (long long)ep.ldmul * 4, rows_left);
+              warp_load_rows128_finish(slice, lane, mreg, t4);
               if (ep.mul_step) {
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
@@ -294,27 +324,50 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                 }
               }
             } else if (active) {
-              for (int j = 0; j < 32 && col0 + j < ep.N; ++j) v[j] = ep.mul_step ? (mulp[col0 + j] > 0.f ? v[j] : 0.f) : v[j] * mulp[col0 + j];
+              // (static indices only: a dynamically indexed v[] would live in local memory for the whole epilogue)
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (col0 + j < ep.N) v[j] = ep.mul_step ? (mulp[col0 + j] > 0.f ? v[j] : 0.f) : v[j] * mulp[col0 + j];
             }
           }
           if (ep.add != nullptr) {
-            const float* ab = ep.add + (long long)i1 * ep.add_bs1 + (long long)i2 * ep.add_bs2 + (long long)(m0 + q * 32) * ep.ldadd + col0;
-            if (chunk_full && ((ep.ldadd & 3) == 0) && ((reinterpret_cast<uintptr_t>(ab) & 15) == 0)) {
+            if (add_fast) {
               uint4 t4[8];
-              warp_load_rows128(epi + q * 4096, lane, t4, ab, (long long)ep.ldadd * 4, rows_left);
+              warp_load_rows128_finish(slice, lane, areg, t4);
 #pragma unroll
               for (int j = 0; j < 8; ++j) {
                 v[4 * j] += __uint_as_float(t4[j].x); v[4 * j + 1] += __uint_as_float(t4[j].y);
                 v[4 * j + 2] += __uint_as_float(t4[j].z); v[4 * j + 3] += __uint_as_float(t4[j].w);
               }
             } else if (active) {
-              for (int j = 0; j < 32 && col0 + j < ep.N; ++j) v[j] += addp[col0 + j];
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (col0 + j < ep.N) v[j] += addp[col0 + j];
             }
           }
         }
         if (ep.round_tf32) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = round_tf32(v[j]);
+        }
+        if (ep.c_tma) {
+          // fp32 C through the tensor map: the warp's 32 x 32 box goes to its swizzled slice and leaves as one tile store
+          // (rows past M / columns past N are clipped by the TMA unit)
+          if (rows_left > 0 && col0 < ep.N) {  // warp-uniform
+            if (lane == 0) bulk_wait_read0();  // the previous box of this warp has been read out of the slice
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              *reinterpret_cast<uint4*>(slice + lane * 128 + ((j ^ (lane & 7)) << 4)) =
+                  make_uint4(__float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]), __float_as_uint(v[4 * j + 2]), __float_as_uint(v[4 * j + 3]));
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_4d(&map_c, slice, col0, m0 + q * 32, i1 * ep.c_b1, i2 * ep.c_b2);
+              bulk_commit();
+            }
+          }
+          continue;
         }
         if (active) {
           const bool full_chunk = (col0 + 32 <= ep.N);
@@ -331,7 +384,9 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                 *reinterpret_cast<uint4*>(cp + j) = o;
               }
             } else {
-              for (int j = 0; j < 32 && col0 + j < ep.N; ++j) cp[j] = __float2half_rn(v[j]);
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (col0 + j < ep.N) cp[j] = __float2half_rn(v[j]);
             }
           } else if (!coalesce) {
             float* cp = reinterpret_cast<float*>(ep.C) + boff_c + (long long)row * ep.ldc + col0;
@@ -339,7 +394,9 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
 #pragma unroll
               for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(cp + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
             } else {
-              for (int j = 0; j < 32 && col0 + j < ep.N; ++j) cp[j] = v[j];
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (col0 + j < ep.N) cp[j] = v[j];
             }
           }
           if (coalesce) {
@@ -352,13 +409,14 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
           // fp32 output, every 32-column chunk of the tile complete and 16-byte aligned (warp-uniform): the
           // warp's 32 rows x 128 bytes leave as full lines
           float* cb = reinterpret_cast<float*>(ep.C) + boff_c + (long long)(m0 + q * 32) * ep.ldc + col0;
-          warp_store_rows128(epi + q * 4096, lane, ov, cb, (long long)ep.ldc * 4, ep.M - (m0 + q * 32));
+          warp_store_rows128(slice, lane, ov, cb, (long long)ep.ldc * 4, ep.M - (m0 + q * 32));
         }
       }
       // this thread's TMEM reads of the accumulator are complete: hand it back to the MMA warp
       tc_fence_before();
       mbar_arrive(&tmem_empty[buf]);
     }
+    if (ep.c_tma && lane == 0) bulk_wait_read0();  // shared memory must outlive the last tile store's read
   }
   tc_fence_before();
   __syncthreads();
@@ -407,6 +465,22 @@ static int launch_gemm(const GemmArgs& g, cudaStream_t stream) {
   ep.add = g.add; ep.ldadd = g.ldadd; ep.add_bs1 = g.add_bs1; ep.add_bs2 = g.add_bs2;
   ep.C = g.C; ep.ldc = g.ldc; ep.c_bs1 = g.c_bs1; ep.c_bs2 = g.c_bs2; ep.c_fp16 = g.c_fp16;
   ep.mul_step = g.mul_step; ep.round_tf32 = g.round_tf32;
+  // fp32 C whose rows and batch strides are 16-byte multiples: tile stores through a tensor map (PRD_GEMM_TMA_STORE=0: off)
+  static const bool tma_store_on = !(getenv("PRD_GEMM_TMA_STORE") && getenv("PRD_GEMM_TMA_STORE")[0] == '0');
+  CUtensorMap map_c = map_a;
+  ep.c_tma = 0; ep.c_b1 = g.c_bs1 != 0 ? 1 : 0; ep.c_b2 = g.c_bs2 != 0 ? 1 : 0;
+  if (tma_store_on && !g.c_fp16 && g.ldc % 4 == 0 && g.c_bs1 % 4 == 0 && g.c_bs2 % 4 == 0 &&
+      (reinterpret_cast<uintptr_t>(g.C) & 15) == 0) {
+    TmaDims dc;
+    dc.size[0] = (uint64_t)g.N; dc.size[1] = (uint64_t)g.M;
+    dc.size[2] = g.c_bs1 != 0 ? (uint64_t)nb1 : 1; dc.size[3] = g.c_bs2 != 0 ? (uint64_t)nb2 : 1;
+    dc.stride[0] = (uint64_t)g.ldc * 4;
+    dc.stride[1] = ((uint64_t)(g.c_bs1 != 0 ? g.c_bs1 : g.ldc * (long long)g.M) * 4 + 15) & ~15ull;
+    dc.stride[2] = ((uint64_t)(g.c_bs2 != 0 ? g.c_bs2 : g.ldc * (long long)g.M) * 4 + 15) & ~15ull;
+    dc.box[0] = 32; dc.box[1] = 32; dc.box[2] = 1; dc.box[3] = 1;
+    if (make_tensor_map(&map_c, g.C, 4, 4, dc, true)) return 1;
+    ep.c_tma = 1;
+  }
   auto kern = gemm_f16_kernel<BN, STAGES, TF32>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -422,7 +496,7 @@ static int launch_gemm(const GemmArgs& g, cudaStream_t stream) {
   const int num_kb = g.split != 0 ? 2 * kb_half : kb_half;
   const int a_wrap = g.split == 1 ? kb_half : num_kb;
   const int b_wrap = g.split == 2 ? kb_half : num_kb;
-  PRD_CUDA_OK(launch_pdl(kern, grid, 192, L::kTotal, stream, map_a, map_b, num_kb, a_wrap, b_wrap, tl, g.a_bs1 != 0 ? 1 : 0,
+  PRD_CUDA_OK(launch_pdl(kern, grid, 384, L::kTotal, stream, map_a, map_b, map_c, num_kb, a_wrap, b_wrap, tl, g.a_bs1 != 0 ? 1 : 0,
                          g.a_bs2 != 0 ? 1 : 0, g.b_bs1 != 0 ? 1 : 0, g.b_bs2 != 0 ? 1 : 0, ep));
   PRD_LAUNCHED();
   return 0;

@@ -18,6 +18,7 @@ from protein_redesign_b200 import autograd as ag  # noqa: E402
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--sizes", type=int, default=0)
+    ap.add_argument("--kernels", action="store_true", help="per-kernel table of one step (torch.profiler / CUPTI) instead")
     a = ap.parse_args()
     dev = torch.device("cuda", 0)
     cfg = dataclasses.replace(syn.PAPER, mask_prob=0.15, num_steps=2000)
@@ -28,6 +29,21 @@ def main():
     for _ in range(2):
         ag.training_step_manual(model, to_dev(), grads)
     torch.cuda.synchronize()
+    if a.kernels:
+        from torch.profiler import ProfilerActivity, profile
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            ag.training_step_manual(model, to_dev(), grads)
+            torch.cuda.synchronize()
+        rows = collections.defaultdict(lambda: [0, 0.0])
+        for ev in prof.events():
+            if ev.device_type == torch.autograd.DeviceType.CUDA:
+                rows[ev.name][0] += 1
+                rows[ev.name][1] += ev.device_time / 1e3
+        total = sum(v[1] for v in rows.values())
+        print(f"kernels of one training step: {sum(v[0] for v in rows.values())} launches, {total:.1f} ms of GPU time")
+        for k, (n, ms) in sorted(rows.items(), key=lambda kv: -kv[1][1])[:40]:
+            print(f"{k[:110]:110s} x{n:4d} {ms:8.2f} ms {100 * ms / total:5.1f} % {ms / n:7.3f}")
+        return
     acc = collections.defaultdict(lambda: [0, 0.0])
     orig_call, orig_bwd = _lib.call, _lib.call_bwd
 
