@@ -14,6 +14,12 @@
 //   dq kernel (CTA = 128 queries, loops over keys):   dP = dO v^T, dS = P (dP - D), dq = dS k / 4, optional dbias = dS
 //   dkv kernel (CTA = 128 keys, loops over queries):  the same tiles transposed (S^T = k q^T), dv = P^T dO, dk = dS^T q / 4
 //
+// Scores are kept in log2 units (q carries scale * log2 e, the bias is multiplied by log2 e on the fly, lse is stored as
+// log2 sum 2^s): one FADD + one ex2 per probability.  Operands produced in registers (P, dS) are rounded to nearest by
+// adding half a tf32 ulp to the bit pattern -- the tensor core drops the 13 low bits itself.  A key's state is one float
+// (+inf valid, -32768 log2 e masked_fill, -inf beyond the sequence): min(score, state) applies masked_fill and the
+// padding in one instruction.
+//
 // Shared-memory rows are 16 floats at a stride of 20: both fragment access patterns ((g, t) and (2t, g)) then touch 32
 // distinct banks.
 #include "prd_bwd.h"
@@ -25,7 +31,8 @@
 namespace prd {
 
 namespace {
-constexpr float kMaskFill = -32768.0f;  // modules.py:177,220
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kMaskFill2 = -32768.0f * kLog2e;  // modules.py:177,220 in log2 units
 constexpr int kLd = 20;                 // shared-memory row stride (floats)
 constexpr int kChunk = 128;             // keys (queries) staged per pass
 
@@ -45,10 +52,16 @@ __device__ __forceinline__ long long attn_row(const AttnDev& a, long long s, int
 __device__ __forceinline__ float attn_seq_mask(const AttnDev& a, long long s) { return a.mode == 2 ? 1.0f : a.mask[s]; }
 __device__ __forceinline__ long long attn_batch(const AttnDev& a, long long s) { return a.mode == 2 ? s : s / a.N; }
 
-__device__ __forceinline__ uint32_t tf32_bits(float x) {
-  uint32_t u;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
-  return u;
+// operand bits of a tf32 MMA, rounded to nearest once the tensor core has dropped the 13 low bits
+__device__ __forceinline__ uint32_t tf32_bits(float x) { return __float_as_uint(x) + 0x1000u; }
+__device__ __forceinline__ float ex2f(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// state of key kt of sequence s (see the header)
+__device__ __forceinline__ float key_state(const AttnDev& a, long long b, float ms, int kt) {
+  return kt < a.N ? ((ms * a.mask[b * a.N + kt] >= 0.5f) ? INFINITY : kMaskFill2) : -INFINITY;
 }
 // d += a (16 x 8, row) * b (8 x 8, col)
 __device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
@@ -77,8 +90,8 @@ __device__ __forceinline__ void load_a_frag(const AttnDev& a, long long s, int r
     const float* p = r < a.N ? base + attn_row(a, s, r) * ld + col0 : nullptr;
 #pragma unroll
     for (int ks = 0; ks < 2; ++ks) {
-      frag[ks][hf] = tf32_bits(p ? p[8 * ks + t] * mul : 0.f);
-      frag[ks][2 + hf] = tf32_bits(p ? p[8 * ks + t + 4] * mul : 0.f);
+      frag[ks][hf] = __float_as_uint(round_tf32(p ? p[8 * ks + t] * mul : 0.f));
+      frag[ks][2 + hf] = __float_as_uint(round_tf32(p ? p[8 * ks + t + 4] * mul : 0.f));
     }
   }
 }
@@ -103,9 +116,6 @@ __device__ __forceinline__ void stage_row(const AttnDev& a, long long s, int r, 
   }
 }
 
-// score of a key with flag f (1 valid, 0 masked_fill, -1 beyond the sequence)
-__device__ __forceinline__ float flagged(float sc, float f) { return f > 0.5f ? sc : (f < -0.5f ? -INFINITY : kMaskFill); }
-
 // -----------------------------------------------------------------------------------------------------------------
 // forward: grid (nseq * H, ceil(N / 128)), 4 warps x 32 queries
 // -----------------------------------------------------------------------------------------------------------------
@@ -126,7 +136,7 @@ __global__ void __launch_bounds__(128) attn_tc_fwd_kernel(AttnDev a, const float
   float acc[2][2][4], m[2][2], l[2][2];
 #pragma unroll
   for (int mt = 0; mt < 2; ++mt) {
-    load_a_frag(a, s, q0 + 16 * mt, qkvg, ld, h * 16, a.scale, g, t, qa[mt]);
+    load_a_frag(a, s, q0 + 16 * mt, qkvg, ld, h * 16, a.scale * kLog2e, g, t, qa[mt]);
 #pragma unroll
     for (int hf = 0; hf < 2; ++hf) {
       m[mt][hf] = -INFINITY;
@@ -143,7 +153,7 @@ __global__ void __launch_bounds__(128) attn_tc_fwd_kernel(AttnDev a, const float
       const int kt = k0 + threadIdx.x;
       stage_row(a, s, kt, qkvg, ld, 64 + h * 16, 1.f, sK + threadIdx.x * kLd);
       stage_row(a, s, kt, qkvg, ld, 128 + h * 16, 1.f, sV + threadIdx.x * kLd);
-      sFlag[threadIdx.x] = kt < a.N ? ((ms * a.mask[b * a.N + kt] >= 0.5f) ? 1.f : 0.f) : -1.f;
+      sFlag[threadIdx.x] = key_state(a, b, ms, kt);
     }
     __syncthreads();
     if (!active) continue;
@@ -169,15 +179,15 @@ __global__ void __launch_bounds__(128) attn_tc_fwd_kernel(AttnDev a, const float
               const int q = q0 + 16 * mt + g + 8 * hf;
               if (q < a.N) {
                 const float* bp = a.bias + ((b * a.H + h) * a.N + q) * (long long)a.N + k0 + key + 2 * t;
-                if (k0 + key + 2 * t < a.N) sc[mt][nt][2 * hf] += bp[0];
-                if (k0 + key + 2 * t + 1 < a.N) sc[mt][nt][2 * hf + 1] += bp[1];
+                if (k0 + key + 2 * t < a.N) sc[mt][nt][2 * hf] = fmaf(bp[0], kLog2e, sc[mt][nt][2 * hf]);
+                if (k0 + key + 2 * t + 1 < a.N) sc[mt][nt][2 * hf + 1] = fmaf(bp[1], kLog2e, sc[mt][nt][2 * hf + 1]);
               }
             }
           }
-          sc[mt][nt][0] = flagged(sc[mt][nt][0], f0);
-          sc[mt][nt][1] = flagged(sc[mt][nt][1], f1);
-          sc[mt][nt][2] = flagged(sc[mt][nt][2], f0);
-          sc[mt][nt][3] = flagged(sc[mt][nt][3], f1);
+          sc[mt][nt][0] = fminf(sc[mt][nt][0], f0);
+          sc[mt][nt][1] = fminf(sc[mt][nt][1], f1);
+          sc[mt][nt][2] = fminf(sc[mt][nt][2], f0);
+          sc[mt][nt][3] = fminf(sc[mt][nt][3], f1);
         }
       }
       // online softmax: rows (mt, hf) = q0 + 16 mt + g + 8 hf; the first key of every group is a real key, so the
@@ -191,12 +201,12 @@ __global__ void __launch_bounds__(128) attn_tc_fwd_kernel(AttnDev a, const float
           for (int nt = 0; nt < 4; ++nt) mx = fmaxf(mx, fmaxf(sc[mt][nt][2 * hf], sc[mt][nt][2 * hf + 1]));
           mx = quad_max(mx);
           const float mnew = fmaxf(m[mt][hf], mx);
-          const float corr = __expf(m[mt][hf] - mnew);
+          const float corr = ex2f(m[mt][hf] - mnew);
           m[mt][hf] = mnew;
           float part = 0.f;
 #pragma unroll
           for (int nt = 0; nt < 4; ++nt) {
-            const float p0 = __expf(sc[mt][nt][2 * hf] - mnew), p1 = __expf(sc[mt][nt][2 * hf + 1] - mnew);
+            const float p0 = ex2f(sc[mt][nt][2 * hf] - mnew), p1 = ex2f(sc[mt][nt][2 * hf + 1] - mnew);
             part += p0 + p1;
             sc[mt][nt][2 * hf] = p0;
             sc[mt][nt][2 * hf + 1] = p1;
@@ -237,7 +247,7 @@ __global__ void __launch_bounds__(128) attn_tc_fwd_kernel(AttnDev a, const float
 #pragma unroll
       for (int nt = 0; nt < 2; ++nt)
         *reinterpret_cast<float2*>(op + 8 * nt) = make_float2(acc[mt][nt][2 * hf] * inv, acc[mt][nt][2 * hf + 1] * inv);
-      if (t == 0) lse[(s * a.H + h) * a.N + q] = m[mt][hf] + logf(lt);
+      if (t == 0) lse[(s * a.H + h) * a.N + q] = m[mt][hf] + log2f(lt);  // log2 units
     }
   }
 }
@@ -264,7 +274,7 @@ __global__ void __launch_bounds__(128) attn_tc_dq_kernel(AttnDev a, const float*
   float dq[2][2][4], L[2][2], D[2][2];
 #pragma unroll
   for (int mt = 0; mt < 2; ++mt) {
-    load_a_frag(a, s, q0 + 16 * mt, qkvg, ld, h * 16, a.scale, g, t, qa[mt]);
+    load_a_frag(a, s, q0 + 16 * mt, qkvg, ld, h * 16, a.scale * kLog2e, g, t, qa[mt]);
     load_a_frag(a, s, q0 + 16 * mt, dO, 64, h * 16, 1.f, g, t, da[mt]);
 #pragma unroll
     for (int hf = 0; hf < 2; ++hf) {
@@ -294,7 +304,7 @@ __global__ void __launch_bounds__(128) attn_tc_dq_kernel(AttnDev a, const float*
       const int kt = k0 + threadIdx.x;
       stage_row(a, s, kt, qkvg, ld, 64 + h * 16, 1.f, sK + threadIdx.x * kLd);
       stage_row(a, s, kt, qkvg, ld, 128 + h * 16, 1.f, sV + threadIdx.x * kLd);
-      sFlag[threadIdx.x] = kt < a.N ? ((ms * a.mask[b * a.N + kt] >= 0.5f) ? 1.f : 0.f) : -1.f;
+      sFlag[threadIdx.x] = key_state(a, b, ms, kt);
     }
     __syncthreads();
     if (!active) continue;
@@ -310,7 +320,8 @@ __global__ void __launch_bounds__(128) attn_tc_dq_kernel(AttnDev a, const float*
       const float* k2 = sK + (key + 2 * t) * kLd + g;
       const uint32_t kc00 = __float_as_uint(k2[0]), kc01 = __float_as_uint(k2[kLd]);
       const uint32_t kc10 = __float_as_uint(k2[8]), kc11 = __float_as_uint(k2[kLd + 8]);
-      const float f0 = sFlag[key + 2 * t], f1 = sFlag[key + 2 * t + 1];
+      // only valid keys carry a gradient: masked_fill cuts it (modules.py:220), keys past the sequence do not exist
+      const bool v0 = sFlag[key + 2 * t] > 0.f, v1 = sFlag[key + 2 * t + 1] > 0.f;
 #pragma unroll
       for (int mt = 0; mt < 2; ++mt) {
         float sc[4] = {0.f, 0.f, 0.f, 0.f}, dp[4] = {0.f, 0.f, 0.f, 0.f};
@@ -322,14 +333,13 @@ __global__ void __launch_bounds__(128) attn_tc_dq_kernel(AttnDev a, const float*
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const int hf = e >> 1;
-          const float f = (e & 1) ? f1 : f0;
           float x = sc[e];
           if (kBias) {
             const int q = q0 + 16 * mt + g + 8 * hf, kk = k0 + key + 2 * t + (e & 1);
-            if (q < a.N && kk < a.N) x += a.bias[((b * a.H + h) * a.N + q) * (long long)a.N + kk];
+            if (q < a.N && kk < a.N) x = fmaf(a.bias[((b * a.H + h) * a.N + q) * (long long)a.N + kk], kLog2e, x);
           }
-          const float p = __expf(flagged(x, f) - L[mt][hf]);
-          ds[e] = f > 0.5f ? p * (dp[e] - D[mt][hf]) : 0.f;  // masked_fill cuts the gradient (modules.py:220)
+          const float p = ex2f(x - L[mt][hf]);
+          ds[e] = ((e & 1) ? v1 : v0) ? p * (dp[e] - D[mt][hf]) : 0.f;
           if (kBias) {
             const int q = q0 + 16 * mt + g + 8 * hf, kk = k0 + key + 2 * t + (e & 1);
             if (dbias != nullptr && q < a.N && kk < a.N) dbias[((b * a.H + h) * a.N + q) * (long long)a.N + kk] = ds[e];
@@ -383,8 +393,8 @@ __global__ void __launch_bounds__(128) attn_tc_dkv_kernel(AttnDev a, const float
     load_a_frag(a, s, kw0 + 16 * mt, qkvg, ld, 128 + h * 16, 1.f, g, t, va[mt]);
 #pragma unroll
     for (int hf = 0; hf < 2; ++hf) {
-      const int kt = kw0 + 16 * mt + g + 8 * hf;
-      kf[mt][hf] = kt < a.N ? ((ms * a.mask[b * a.N + kt] >= 0.5f) ? 1.f : 0.f) : -1.f;
+      // rows past the sequence are never stored, so only valid / masked_fill matters here
+      kf[mt][hf] = key_state(a, b, ms, kw0 + 16 * mt + g + 8 * hf);
     }
 #pragma unroll
     for (int nt = 0; nt < 2; ++nt)
@@ -395,7 +405,7 @@ __global__ void __launch_bounds__(128) attn_tc_dkv_kernel(AttnDev a, const float
     __syncthreads();
     {
       const int qt = qc + threadIdx.x;
-      stage_row(a, s, qt, qkvg, ld, h * 16, a.scale, sQ + threadIdx.x * kLd);
+      stage_row(a, s, qt, qkvg, ld, h * 16, a.scale * kLog2e, sQ + threadIdx.x * kLd);
       stage_row(a, s, qt, dO, 64, h * 16, 1.f, sdO + threadIdx.x * kLd);
       // queries past N: exp(score - inf) = 0
       sL[threadIdx.x] = qt < a.N ? lse[(s * a.H + h) * a.N + qt] : INFINITY;
@@ -435,16 +445,16 @@ __global__ void __launch_bounds__(128) attn_tc_dkv_kernel(AttnDev a, const float
           float x = sc[e];
           if (kBias) {
             const int qq = qc + q + 2 * t + (e & 1), kt = kw0 + 16 * mt + g + 8 * hf;
-            if (qq < a.N && kt < a.N) x += a.bias[((b * a.H + h) * a.N + qq) * (long long)a.N + kt];
+            if (qq < a.N && kt < a.N) x = fmaf(a.bias[((b * a.H + h) * a.N + qq) * (long long)a.N + kt], kLog2e, x);
           }
-          p[e] = __expf(flagged(x, f) - ((e & 1) ? L1 : L0));
-          ds[e] = f > 0.5f ? p[e] * (dp[e] - ((e & 1) ? D1 : D0)) : 0.f;
+          p[e] = ex2f(fminf(x, f) - ((e & 1) ? L1 : L0));
+          ds[e] = f > 0.f ? p[e] * (dp[e] - ((e & 1) ? D1 : D0)) : 0.f;
         }
         const uint32_t pa[4] = {tf32_bits(p[0]), tf32_bits(p[2]), tf32_bits(p[1]), tf32_bits(p[3])};
         const uint32_t sa[4] = {tf32_bits(ds[0]), tf32_bits(ds[2]), tf32_bits(ds[1]), tf32_bits(ds[3])};
         mma_tf32(dv[mt][0], pa, dc00, dc01);
         mma_tf32(dv[mt][1], pa, dc10, dc11);
-        mma_tf32(dk[mt][0], sa, qc00, qc01);  // sQ carries the 1 / 4 already
+        mma_tf32(dk[mt][0], sa, qc00, qc01);  // sQ carries scale * log2 e
         mma_tf32(dk[mt][1], sa, qc10, qc11);
       }
     }
@@ -459,7 +469,8 @@ __global__ void __launch_bounds__(128) attn_tc_dkv_kernel(AttnDev a, const float
       float* o = dqkvg + attn_row(a, s, kt) * ldd + h * 16 + 2 * t;
 #pragma unroll
       for (int nt = 0; nt < 2; ++nt) {
-        *reinterpret_cast<float2*>(o + 64 + 8 * nt) = make_float2(round_tf32(dk[mt][nt][2 * hf]), round_tf32(dk[mt][nt][2 * hf + 1]));
+        *reinterpret_cast<float2*>(o + 64 + 8 * nt) =
+            make_float2(round_tf32(dk[mt][nt][2 * hf] * (1.0f / kLog2e)), round_tf32(dk[mt][nt][2 * hf + 1] * (1.0f / kLog2e)));
         *reinterpret_cast<float2*>(o + 128 + 8 * nt) = make_float2(round_tf32(dv[mt][nt][2 * hf]), round_tf32(dv[mt][nt][2 * hf + 1]));
       }
     }
