@@ -5,6 +5,8 @@
 
 #include <stdlib.h>
 
+#include <initializer_list>
+
 #include "prd_common.cuh"
 
 namespace prd {
@@ -16,6 +18,19 @@ constexpr float kLnEps = 1e-5f;
 constexpr float kMaskFill = -32768.0f;  // modules.py:177,220
 
 __device__ __forceinline__ float sigmoid_acc(float x) { return 1.0f / (1.0f + expf(-x)); }
+// 2 ulp of ex2.approx and of the approximate division: far below the tf32 rounding (2^-11) every user applies next
+__device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+__device__ __forceinline__ float4 round4(float4 v) { return make_float4(round_tf32(v.x), round_tf32(v.y), round_tf32(v.z), round_tf32(v.w)); }
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+// sum over the LPR-lane group this lane belongs to (LPR a power of two, groups aligned)
+template <int LPR>
+__device__ __forceinline__ float group_sum(float v) {
+#pragma unroll
+  for (int o = LPR / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
 inline unsigned grid_for(long long n, int per_block, long long cap = 148LL * 32) {
   long long g = (n + per_block - 1) / per_block;
   if (g > cap) g = cap;
@@ -53,8 +68,59 @@ __global__ void __launch_bounds__(256) bw_ln_fwd_kernel(const float* __restrict_
     }
   }
 }
+// Rows of C = 4 * LPR floats (32 / 64 / 128: every pair-side LayerNorm): LPR lanes x float4 per row, 32 / LPR rows per warp
+// and load instruction, two such row groups in flight per warp.  The one-warp-per-row kernel above keeps a single 256-byte
+// row in flight per warp and reached 2.1 TB/s.
+template <int LPR>
+__global__ void __launch_bounds__(256) bw_ln_fwd_vec_kernel(const float* __restrict__ x, long long R,
+                                                            const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                            float* __restrict__ out, float* __restrict__ out_lo) {
+  constexpr int C = 4 * LPR, RPW = 32 / LPR, U = 2;
+  const int lane = threadIdx.x & 31, sub = lane / LPR, l = lane % LPR;
+  const long long warp0 = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long long nw = (long long)gridDim.x * (blockDim.x >> 5);
+  float4 gm = make_float4(1.f, 1.f, 1.f, 1.f), bt = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (gamma) gm = ld4(gamma + 4 * l);
+  if (gamma && beta) bt = ld4(beta + 4 * l);
+  for (long long r0 = warp0 * (RPW * U); r0 < R; r0 += nw * (RPW * U)) {
+    float4 v[U];
+    long long r[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      r[u] = r0 + u * RPW + sub;
+      v[u] = r[u] < R ? ld4(x + r[u] * C + 4 * l) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const float mean = group_sum<LPR>(v[u].x + v[u].y + v[u].z + v[u].w) * (1.0f / C);
+      const float4 d = make_float4(v[u].x - mean, v[u].y - mean, v[u].z - mean, v[u].w - mean);
+      const float rstd = rsqrtf(group_sum<LPR>(d.x * d.x + d.y * d.y + d.z * d.z + d.w * d.w) * (1.0f / C) + kLnEps);
+      const float4 y = make_float4(fmaf(d.x * rstd, gm.x, bt.x), fmaf(d.y * rstd, gm.y, bt.y), fmaf(d.z * rstd, gm.z, bt.z),
+                                   fmaf(d.w * rstd, gm.w, bt.w));
+      const float4 hi = round4(y);
+      if (r[u] < R) {
+        st4(out + r[u] * C + 4 * l, hi);
+        if (out_lo) st4(out_lo + r[u] * C + 4 * l, round4(make_float4(y.x - hi.x, y.y - hi.y, y.z - hi.z, y.w - hi.w)));
+      }
+    }
+  }
+}
+template <int LPR>
+static void launch_ln_fwd_vec(const float* x, long long R, const float* gamma, const float* beta, float* out, float* out_lo,
+                              cudaStream_t s) {
+  bw_ln_fwd_vec_kernel<LPR><<<grid_for(R, 8 * (32 / LPR) * 2), 256, 0, s>>>(x, R, gamma, beta, out, out_lo);
+}
 int bw_ln_fwd(const float* x, long long R, int C, const float* gamma, const float* beta, float* out, cudaStream_t s,
               float* out_lo) {
+  const bool vec = aligned16(x) && aligned16(out) && (out_lo == nullptr || aligned16(out_lo)) &&
+                   (gamma == nullptr || aligned16(gamma)) && (beta == nullptr || aligned16(beta));
+  if (vec && (C == 32 || C == 64 || C == 128)) {
+    if (C == 32) launch_ln_fwd_vec<8>(x, R, gamma, beta, out, out_lo, s);
+    else if (C == 64) launch_ln_fwd_vec<16>(x, R, gamma, beta, out, out_lo, s);
+    else launch_ln_fwd_vec<32>(x, R, gamma, beta, out, out_lo, s);
+    PRD_LAUNCHED();
+    return 0;
+  }
   bw_ln_fwd_kernel<<<grid_for(R, 8), 256, 0, s>>>(x, R, C, gamma, beta, out, out_lo);
   PRD_LAUNCHED();
   return 0;
@@ -116,8 +182,50 @@ __global__ void __launch_bounds__(256) bw_ln_bwd_kernel(const float* __restrict_
     }
   }
 }
+// The non-affine backward on rows of C = 4 * LPR floats, laid out like bw_ln_fwd_vec_kernel.
+template <int LPR>
+__global__ void __launch_bounds__(256) bw_ln_bwd_vec_kernel(const float* __restrict__ x, const float* __restrict__ g, long long R,
+                                                            float* __restrict__ dx_io, int accumulate) {
+  constexpr int C = 4 * LPR, RPW = 32 / LPR, U = 2;
+  const int lane = threadIdx.x & 31, sub = lane / LPR, l = lane % LPR;
+  const long long warp0 = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long long nw = (long long)gridDim.x * (blockDim.x >> 5);
+  for (long long r0 = warp0 * (RPW * U); r0 < R; r0 += nw * (RPW * U)) {
+    float4 v[U], gy[U], acc[U];
+    long long r[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      r[u] = r0 + u * RPW + sub;
+      const bool ok = r[u] < R;
+      const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+      v[u] = ok ? ld4(x + r[u] * C + 4 * l) : z;
+      gy[u] = ok ? ld4(g + r[u] * C + 4 * l) : z;
+      acc[u] = (ok && accumulate) ? ld4(dx_io + r[u] * C + 4 * l) : z;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const float mean = group_sum<LPR>(v[u].x + v[u].y + v[u].z + v[u].w) * (1.0f / C);
+      const float4 d = make_float4(v[u].x - mean, v[u].y - mean, v[u].z - mean, v[u].w - mean);
+      const float rstd = rsqrtf(group_sum<LPR>(d.x * d.x + d.y * d.y + d.z * d.z + d.w * d.w) * (1.0f / C) + kLnEps);
+      const float4 xh = make_float4(d.x * rstd, d.y * rstd, d.z * rstd, d.w * rstd);
+      const float m1 = group_sum<LPR>(gy[u].x + gy[u].y + gy[u].z + gy[u].w) * (1.0f / C);
+      const float m2 = group_sum<LPR>(gy[u].x * xh.x + gy[u].y * xh.y + gy[u].z * xh.z + gy[u].w * xh.w) * (1.0f / C);
+      const float4 o = make_float4(acc[u].x + rstd * (gy[u].x - m1 - xh.x * m2), acc[u].y + rstd * (gy[u].y - m1 - xh.y * m2),
+                                   acc[u].z + rstd * (gy[u].z - m1 - xh.z * m2), acc[u].w + rstd * (gy[u].w - m1 - xh.w * m2));
+      if (r[u] < R) st4(dx_io + r[u] * C + 4 * l, round4(o));
+    }
+  }
+}
 int bw_ln_bwd(const float* x, const float* g, long long R, int C, const float* gamma, float* dx_io, int accumulate,
               float* dgamma, float* dbeta, cudaStream_t s) {
+  if (!dgamma && !dbeta && !gamma && (C == 32 || C == 64 || C == 128) && aligned16(x) && aligned16(g) && aligned16(dx_io)) {
+    const unsigned grid = grid_for(R, 8 * (128 / C) * 2);
+    if (C == 32) bw_ln_bwd_vec_kernel<8><<<grid, 256, 0, s>>>(x, g, R, dx_io, accumulate);
+    else if (C == 64) bw_ln_bwd_vec_kernel<16><<<grid, 256, 0, s>>>(x, g, R, dx_io, accumulate);
+    else bw_ln_bwd_vec_kernel<32><<<grid, 256, 0, s>>>(x, g, R, dx_io, accumulate);
+    PRD_LAUNCHED();
+    return 0;
+  }
   if (dgamma || dbeta) {
     PRD_REQUIRE(C <= 1024, "ln_bwd: affine LayerNorm wider than 1024 (%d)", C);
     bw_ln_bwd_kernel<32><<<grid_for(R, 8, 148 * 4), 256, 0, s>>>(x, g, R, C, gamma, dx_io, accumulate, dgamma, dbeta);
@@ -298,7 +406,18 @@ __global__ void bw_relu_kernel(float* x, long long n) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     x[i] = round_tf32(fmaxf(x[i], 0.f));
 }
+__global__ void bw_relu_vec_kernel(float* x, long long n4) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 v = ld4(x + 4 * i);
+    st4(x + 4 * i, round4(make_float4(fmaxf(v.x, 0.f), fmaxf(v.y, 0.f), fmaxf(v.z, 0.f), fmaxf(v.w, 0.f))));
+  }
+}
 int bw_relu_inplace(float* x, long long n, cudaStream_t s) {
+  if (n % 4 == 0 && aligned16(x)) {
+    bw_relu_vec_kernel<<<grid_for(n / 4, 256), 256, 0, s>>>(x, n / 4);
+    PRD_LAUNCHED();
+    return 0;
+  }
   bw_relu_kernel<<<grid_for(n, 256), 256, 0, s>>>(x, n);
   PRD_LAUNCHED();
   return 0;
@@ -317,8 +436,44 @@ __global__ void bw_gate_fwd_kernel(const float* __restrict__ gpre, long long ldg
     og[r * ldog + c] = round_tf32(sigmoid_acc(gpre[r * ldg + c]) * o[r * ldo + c]);
   }
 }
+// float4 versions of the gating kernels (rows of W floats, W % 4 == 0, fewer than 2^32 float4 groups): one 32-bit
+// division per four elements instead of a 64-bit one per element, which made the scalar kernels instruction bound
+__global__ void bw_gate_fwd_vec_kernel(const float* __restrict__ gpre, long long ldg, const float* __restrict__ o, long long ldo,
+                                       float* __restrict__ og, long long ldog, unsigned total, unsigned W4) {
+  for (unsigned q = blockIdx.x * blockDim.x + threadIdx.x; q < total; q += gridDim.x * blockDim.x) {
+    const unsigned r = q / W4, c = (q - r * W4) * 4;
+    const float4 gp = ld4(gpre + (long long)r * ldg + c), ov = ld4(o + (long long)r * ldo + c);
+    st4(og + (long long)r * ldog + c, round4(make_float4(sigmoid_fast(gp.x) * ov.x, sigmoid_fast(gp.y) * ov.y,
+                                                        sigmoid_fast(gp.z) * ov.z, sigmoid_fast(gp.w) * ov.w)));
+  }
+}
+__global__ void bw_gate_bwd_vec_kernel(const float* __restrict__ d_og, long long ld1, const float* __restrict__ gpre, long long ldg,
+                                       const float* __restrict__ o, long long ldo, float* __restrict__ d_o, long long ld2,
+                                       float* __restrict__ d_gpre, long long ld3, unsigned total, unsigned W4) {
+  for (unsigned q = blockIdx.x * blockDim.x + threadIdx.x; q < total; q += gridDim.x * blockDim.x) {
+    const unsigned r = q / W4, c = (q - r * W4) * 4;
+    const float4 gp = ld4(gpre + (long long)r * ldg + c), d = ld4(d_og + (long long)r * ld1 + c), ov = ld4(o + (long long)r * ldo + c);
+    const float4 g = make_float4(sigmoid_fast(gp.x), sigmoid_fast(gp.y), sigmoid_fast(gp.z), sigmoid_fast(gp.w));
+    st4(d_o + (long long)r * ld2 + c, round4(make_float4(d.x * g.x, d.y * g.y, d.z * g.z, d.w * g.w)));
+    st4(d_gpre + (long long)r * ld3 + c, round4(make_float4(d.x * ov.x * g.x * (1.f - g.x), d.y * ov.y * g.y * (1.f - g.y),
+                                                           d.z * ov.z * g.z * (1.f - g.z), d.w * ov.w * g.w * (1.f - g.w))));
+  }
+}
+static bool vec_rows_ok(long long R, int W, std::initializer_list<const void*> ptrs, std::initializer_list<long long> lds) {
+  if (W % 4 != 0 || R * (W / 4) >= 4294967295LL || R >= 4294967295LL) return false;
+  for (const void* p : ptrs)
+    if (!aligned16(p)) return false;
+  for (long long l : lds)
+    if (l % 4 != 0) return false;
+  return true;
+}
 int bw_gate_fwd(const float* gpre, long long ldg, const float* o, long long ldo, float* og, long long ldog, long long R, int W,
                 cudaStream_t s) {
+  if (vec_rows_ok(R, W, {gpre, o, og}, {ldg, ldo, ldog})) {
+    bw_gate_fwd_vec_kernel<<<grid_for(R * (W / 4), 256), 256, 0, s>>>(gpre, ldg, o, ldo, og, ldog, (unsigned)(R * (W / 4)), (unsigned)(W / 4));
+    PRD_LAUNCHED();
+    return 0;
+  }
   bw_gate_fwd_kernel<<<grid_for(R * W, 256), 256, 0, s>>>(gpre, ldg, o, ldo, og, ldog, R, W);
   PRD_LAUNCHED();
   return 0;
@@ -339,6 +494,12 @@ __global__ void bw_gate_bwd_kernel(const float* __restrict__ d_og, long long ld1
 }
 int bw_gate_bwd(const float* d_og, long long ld1, const float* gpre, long long ldg, const float* o, long long ldo, float* d_o,
                 long long ld2, float* d_gpre, long long ld3, long long R, int W, cudaStream_t s) {
+  if (vec_rows_ok(R, W, {d_og, gpre, o, d_o, d_gpre}, {ld1, ldg, ldo, ld2, ld3})) {
+    bw_gate_bwd_vec_kernel<<<grid_for(R * (W / 4), 256), 256, 0, s>>>(d_og, ld1, gpre, ldg, o, ldo, d_o, ld2, d_gpre, ld3,
+                                                                      (unsigned)(R * (W / 4)), (unsigned)(W / 4));
+    PRD_LAUNCHED();
+    return 0;
+  }
   bw_gate_bwd_kernel<<<grid_for(R * W, 256), 256, 0, s>>>(d_og, ld1, gpre, ldg, o, ldo, d_o, ld2, d_gpre, ld3, R, W);
   PRD_LAUNCHED();
   return 0;
@@ -723,15 +884,18 @@ int bw_pair_bias_bwd(int B, int N, int CZ, int H, const float* pair, const float
 // ------------------------------------------------------------------------------------------------------------
 // rows <-> channel planes: per (b, i) a [N tokens, C channels] <-> [C, N] transpose through shared memory
 // ------------------------------------------------------------------------------------------------------------
+// transposed: planes[(b, c)][j][i] instead of [i][j] -- the block then walks i for a fixed j (rows N * ld apart, still one
+// full 128-byte line per row), so the transposed planes need no second pass over the natural ones
 __global__ void bw_rows_to_planes_kernel(const float* __restrict__ rows, long long ld, int col0, int N, int C, int Np,
-                                         float* __restrict__ planes) {
+                                         float* __restrict__ planes, int transposed) {
   __shared__ float tile[32][33];
-  const long long bi = blockIdx.z;  // b * N + i
+  const long long bi = blockIdx.z;  // b * N + i  (transposed: b * N + j)
   const long long b = bi / N, i = bi - b * N;
   const int j0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
   for (int t = threadIdx.y; t < 32; t += 8) {
     const int j = j0 + t, c = c0 + threadIdx.x;
-    tile[t][threadIdx.x] = (j < N && c < C) ? rows[(bi * N + j) * ld + col0 + c] : 0.f;
+    const long long row = transposed ? (b * N + j) * N + i : bi * N + j;
+    tile[t][threadIdx.x] = (j < N && c < C) ? rows[row * ld + col0 + c] : 0.f;
   }
   __syncthreads();
   for (int t = threadIdx.y; t < 32; t += 8) {
@@ -755,9 +919,10 @@ __global__ void bw_planes_to_rows_kernel(const float* __restrict__ planes, int N
     if (j < N && c < C) rows[(bi * N + j) * ld + col0 + c] = round_tf32(tile[threadIdx.x][t]);
   }
 }
-int bw_rows_to_planes(const float* rows, long long ld, int col0, int B, int N, int C, int Np, float* planes, cudaStream_t s) {
+int bw_rows_to_planes(const float* rows, long long ld, int col0, int B, int N, int C, int Np, float* planes, cudaStream_t s,
+                      int transposed) {
   PRD_REQUIRE((long long)B * N <= 65535, "rows_to_planes: B*N = %lld exceeds the grid limit", (long long)B * N);
-  bw_rows_to_planes_kernel<<<dim3((N + 31) / 32, (C + 31) / 32, B * N), dim3(32, 8), 0, s>>>(rows, ld, col0, N, C, Np, planes);
+  bw_rows_to_planes_kernel<<<dim3((N + 31) / 32, (C + 31) / 32, B * N), dim3(32, 8), 0, s>>>(rows, ld, col0, N, C, Np, planes, transposed);
   PRD_LAUNCHED();
   return 0;
 }
@@ -781,8 +946,42 @@ __global__ void bw_trimul_ab_kernel(const float* __restrict__ pre, long long ld,
     ab[idx] = round_tf32(m2 * sigmoid_acc(pre[r * ld + C2 + c]) * pre[r * ld + c]);
   }
 }
+__global__ void bw_trimul_ab_vec_kernel(const float* __restrict__ pre, long long ld, const float* __restrict__ mask, unsigned N,
+                                        unsigned C2, unsigned total, float* __restrict__ ab) {
+  const unsigned W4 = C2 / 4;
+  for (unsigned q = blockIdx.x * blockDim.x + threadIdx.x; q < total; q += gridDim.x * blockDim.x) {
+    const unsigned r = q / W4, c = (q - r * W4) * 4;
+    const unsigned bi = r / N, j = r - bi * N, b = bi / N;
+    const float m2 = mask[bi] * mask[b * N + j];
+    const float4 p = ld4(pre + (long long)r * ld + c), gp = ld4(pre + (long long)r * ld + C2 + c);
+    st4(ab + (long long)r * C2 + c, round4(make_float4(m2 * sigmoid_fast(gp.x) * p.x, m2 * sigmoid_fast(gp.y) * p.y,
+                                                      m2 * sigmoid_fast(gp.z) * p.z, m2 * sigmoid_fast(gp.w) * p.w)));
+  }
+}
+__global__ void bw_trimul_ab_bwd_vec_kernel(const float* __restrict__ pre, long long ld, const float* __restrict__ mask, unsigned N,
+                                            unsigned C2, unsigned total, const float* __restrict__ dab, float* __restrict__ dpre,
+                                            long long ldd) {
+  const unsigned W4 = C2 / 4;
+  for (unsigned q = blockIdx.x * blockDim.x + threadIdx.x; q < total; q += gridDim.x * blockDim.x) {
+    const unsigned r = q / W4, c = (q - r * W4) * 4;
+    const unsigned bi = r / N, j = r - bi * N, b = bi / N;
+    const float m2 = mask[bi] * mask[b * N + j];
+    const float4 p = ld4(pre + (long long)r * ld + c), gp = ld4(pre + (long long)r * ld + C2 + c);
+    const float4 dd = ld4(dab + (long long)r * C2 + c);
+    const float4 g = make_float4(sigmoid_fast(gp.x), sigmoid_fast(gp.y), sigmoid_fast(gp.z), sigmoid_fast(gp.w));
+    const float4 d = make_float4(dd.x * m2, dd.y * m2, dd.z * m2, dd.w * m2);
+    st4(dpre + (long long)r * ldd + c, round4(make_float4(d.x * g.x, d.y * g.y, d.z * g.z, d.w * g.w)));
+    st4(dpre + (long long)r * ldd + C2 + c, round4(make_float4(d.x * p.x * g.x * (1.f - g.x), d.y * p.y * g.y * (1.f - g.y),
+                                                               d.z * p.z * g.z * (1.f - g.z), d.w * p.w * g.w * (1.f - g.w))));
+  }
+}
 int bw_trimul_ab(const float* pre, long long ld, const float* mask, int B, int N, int C2, float* ab, cudaStream_t s) {
   const long long R = (long long)B * N * N;
+  if (vec_rows_ok(R, C2, {pre, ab}, {ld})) {
+    bw_trimul_ab_vec_kernel<<<grid_for(R * (C2 / 4), 256), 256, 0, s>>>(pre, ld, mask, (unsigned)N, (unsigned)C2, (unsigned)(R * (C2 / 4)), ab);
+    PRD_LAUNCHED();
+    return 0;
+  }
   bw_trimul_ab_kernel<<<grid_for(R * C2, 256), 256, 0, s>>>(pre, ld, mask, N, C2, R, ab);
   PRD_LAUNCHED();
   return 0;
@@ -808,6 +1007,12 @@ __global__ void bw_trimul_ab_bwd_kernel(const float* __restrict__ pre, long long
 int bw_trimul_ab_bwd(const float* pre, long long ld, const float* mask, int B, int N, int C2, const float* dab, float* dpre,
                      long long ldd, cudaStream_t s) {
   const long long R = (long long)B * N * N;
+  if (vec_rows_ok(R, C2, {pre, dab, dpre}, {ld, ldd})) {
+    bw_trimul_ab_bwd_vec_kernel<<<grid_for(R * (C2 / 4), 256), 256, 0, s>>>(pre, ld, mask, (unsigned)N, (unsigned)C2,
+                                                                            (unsigned)(R * (C2 / 4)), dab, dpre, ldd);
+    PRD_LAUNCHED();
+    return 0;
+  }
   bw_trimul_ab_bwd_kernel<<<grid_for(R * C2, 256), 256, 0, s>>>(pre, ld, mask, N, C2, R, dab, dpre, ldd);
   PRD_LAUNCHED();
   return 0;

@@ -78,7 +78,9 @@ int bw_pair_bias_bwd(int B, int N, int CZ, int H, const float* pair, const float
 
 // ---- channel-last rows <-> channel planes (triangle multiplication) -----------------------------------------------
 // rows [B*N*N, ld] (channel c at column col0 + c) -> planes[(b*C + c)][i][j] with row stride Np (natural orientation), rounded
-int bw_rows_to_planes(const float* rows, long long ld, int col0, int B, int N, int C, int Np, float* planes, cudaStream_t s);
+// transposed = 1: planes[(b*C + c)][j][i] (the planes of the transposed pair tensor) straight from the rows
+int bw_rows_to_planes(const float* rows, long long ld, int col0, int B, int N, int C, int Np, float* planes, cudaStream_t s,
+                      int transposed = 0);
 int bw_planes_to_rows(const float* planes, int B, int N, int C, int Np, float* rows, long long ld, int col0, cudaStream_t s);
 // ab[r, 0:2C] = round(m_i m_j sigmoid(pre[r, 2C + c]) pre[r, c])          (pre: [R, ld], proj at 0, gate at 2C)
 int bw_trimul_ab(const float* pre, long long ld, const float* mask, int B, int N, int C2, float* ab, cudaStream_t s);

@@ -347,8 +347,8 @@ PRD_BWD_OP(triangle_multiplication) {
   if (bw_rows_to_planes(ab, C2, 0, B, N, CZ, Np, pa, st)) return 1;
   if (bw_rows_to_planes(ab, C2, CZ, B, N, CZ, Np, pb, st)) return 1;
   const long long ps = (long long)N * Np;  // plane stride
-  if (bw_transpose(pa, Np, ps, paT, Np, ps, N, N, B * CZ, 1.f, st)) return 1;
-  if (bw_transpose(pb, Np, ps, pbT, Np, ps, N, N, B * CZ, 1.f, st)) return 1;
+  if (bw_rows_to_planes(ab, C2, 0, B, N, CZ, Np, paT, st, 1)) return 1;
+  if (bw_rows_to_planes(ab, C2, CZ, B, N, CZ, Np, pbT, st, 1)) return 1;
   auto plane_gemm = [&](const float* A, const float* Bm, float* C) {
     GemmArgs g = tfg(N, N, N, A, Np, Bm, Np, C, Np);
     g.nb1 = B * CZ; g.a_bs1 = ps; g.b_bs1 = ps; g.c_bs1 = ps;
@@ -372,7 +372,7 @@ PRD_BWD_OP(triangle_multiplication) {
   }
   if (bw_ln_bwd(xc, dxn, R, CZ, nullptr, dxc, 0, nullptr, nullptr, st)) return 1;
   if (bw_rows_to_planes(dxc, CZ, 0, B, N, CZ, Np, dxp, st)) return 1;
-  if (bw_transpose(dxp, Np, ps, dxpT, Np, ps, N, N, B * CZ, 1.f, st)) return 1;
+  if (bw_rows_to_planes(dxc, CZ, 0, B, N, CZ, Np, dxpT, st, 1)) return 1;
   if (d->mode == 0) {
     // da[i][k] = sum_j dx[i][j] b[j][k] = dx . (bT)^T ;  db[j][k] = sum_i dx[i][j] a[i][k] = dxT . (aT)^T
     if (plane_gemm(dxp, pbT, dap)) return 1;

@@ -19,6 +19,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--sizes", type=int, default=0)
     ap.add_argument("--kernels", action="store_true", help="per-kernel table of one step (torch.profiler / CUPTI) instead")
+    ap.add_argument("--op-kernels", default=None, help="ordered kernel list of the first backward call of this op, e.g. triangle_multiplication")
     a = ap.parse_args()
     dev = torch.device("cuda", 0)
     cfg = dataclasses.replace(syn.PAPER, mask_prob=0.15, num_steps=2000)
@@ -29,6 +30,29 @@ def main():
     for _ in range(2):
         ag.training_step_manual(model, to_dev(), grads)
     torch.cuda.synchronize()
+    if a.op_kernels:
+        from torch.profiler import ProfilerActivity, profile
+        orig_bwd = _lib.call_bwd
+        seen = []
+
+        def traced(op, *args, **kw):
+            if op != a.op_kernels or seen:
+                return orig_bwd(op, *args, **kw)
+            seen.append(1)
+            torch.cuda.synchronize()
+            with profile(activities=[ProfilerActivity.CUDA]) as prof:
+                orig_bwd(op, *args, **kw)
+                torch.cuda.synchronize()
+            evs = sorted((e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA), key=lambda e: e.time_range.start)
+            print(f"kernels of one {op} backward call: {len(evs)} launches, {sum(e.device_time for e in evs) / 1e3:.3f} ms")
+            for e in evs:
+                print(f"  {e.device_time:8.1f} us  {e.name[:120]}")
+
+        _lib.call_bwd = traced
+        ag._lib = _lib
+        ag.training_step_manual(model, to_dev(), grads)
+        torch.cuda.synchronize()
+        return
     if a.kernels:
         from torch.profiler import ProfilerActivity, profile
         with profile(activities=[ProfilerActivity.CUDA]) as prof:
