@@ -550,7 +550,7 @@ def run_train(args, dev, rank, local_rank, world, lib):
     tsg = TrainStepGraph(model, to_dev(), grads) if args.train_mode == "graph" else None
 
     def step():
-        batch = to_dev()
+        batch = to_dev() if tsg is None else host   # the graph path copies the pinned batch itself, on its side stream
         if args.train_mode == "autograd":   # the drop-in path: training_step + loss.backward() through autograd
             flat.zero_()
             loss = model.training_step(batch, 0)

@@ -352,6 +352,7 @@ class TrainStepGraph:
             self.shape = (B, N)
             self.t = torch.zeros(B, dtype=torch.int64, device=dev)
             self.noise = {"z": torch.zeros(B, N, 3, device=dev), "seq": torch.zeros(B, N, 21, device=dev)} if inject_noise else None
+            self.prep = torch.cuda.Stream(device=dev)  # host -> device copies and prepare_batch of the NEXT step
             # every workspace (forward and backward ops) sized before capture, on the capture stream
             side = torch.cuda.Stream(device=dev)
             side.wait_stream(torch.cuda.current_stream(dev))
@@ -377,15 +378,32 @@ class TrainStepGraph:
             torch.cuda.current_stream(dev).wait_stream(side)
 
     def step(self, batch, batch_idx: int = 0, noise=None) -> torch.Tensor:
-        """prepare_batch + t on the host path, then one graph replay; returns the loss [1] (a static tensor of the graph)."""
+        """prepare_batch + t on the host path, then one graph replay; returns the loss [1] (a static tensor of the graph).
+
+        ``batch`` may live on the host (pinned): it is copied to the device here.  The copy and prepare_batch run on a side
+        stream: prepare_batch reads masks back to the host (the reference's masking module calls ``.item()``), and on the
+        main stream that read would wait for the previous step's whole graph -- with the side stream the host prepares
+        step k + 1 while the device runs step k.  The copies into the graph's static buffers are ordered after the previous
+        replay on the main stream."""
         model = self.model
+        dev = self.grads.flat.device
+        main = torch.cuda.current_stream(dev)
         with torch.no_grad():
-            prepared = model.prepare_batch(batch, batch_idx)
+            if any(isinstance(v, torch.Tensor) and v.is_cuda for v in batch.values()):
+                self.prep.wait_stream(main)  # device inputs were produced on the caller's stream (no overlap then)
+            with torch.cuda.stream(self.prep):
+                batch = {k: (v.to(dev, non_blocking=True) if isinstance(v, torch.Tensor) and v.device != dev else v)
+                         for k, v in batch.items()}
+                prepared = model.prepare_batch(batch, batch_idx)
+                t_dev = torch.randint(0, model.num_steps, size=(self.shape[0],)).to(dev, non_blocking=True)
             if tuple(prepared["atom_mask"].shape) != self.shape:
                 raise ValueError(f"TrainStepGraph was captured for (B, N) = {self.shape}, got {tuple(prepared['atom_mask'].shape)}")
+            main.wait_stream(self.prep)
             for k in self._KEYS:
                 self.static[k].copy_(prepared[k], non_blocking=True)
-            self.t.copy_(torch.randint(0, model.num_steps, size=(self.shape[0],)), non_blocking=True)
+                prepared[k].record_stream(main)  # allocated on the side stream, read on the main one
+            self.t.copy_(t_dev, non_blocking=True)
+            t_dev.record_stream(main)
             if self.noise is not None:
                 if noise is None:
                     raise ValueError("this graph was captured with inject_noise=True: pass noise={'z': ..., 'seq': ...}")

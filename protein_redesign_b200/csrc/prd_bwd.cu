@@ -402,6 +402,33 @@ int bw_split2d(const float* src, long long lds, float* hi, float* lo, long long 
   PRD_LAUNCHED();
   return 0;
 }
+struct PrepJobs {
+  PrepJob j[PrepBatch::kMax];
+};
+__global__ void __launch_bounds__(256) bw_prep_kernel(const __grid_constant__ PrepJobs jobs) {
+  const PrepJob& jb = jobs.j[blockIdx.y];
+  const int total = jb.drows * jb.dcols;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const int i = idx / jb.dcols, j = idx - i * jb.dcols;
+    const int sr = jb.transpose ? j : i, sc = jb.transpose ? i : j;
+    float v = 0.f;
+    if (jb.src != nullptr && sr < jb.rows && sc < jb.cols) v = jb.alpha * jb.src[(long long)sr * jb.lds + sc];
+    const float hi = jb.round ? round_tf32(v) : v;
+    jb.dst[(long long)i * jb.ldd + j] = hi;
+    if (jb.dst_lo != nullptr) jb.dst_lo[(long long)i * jb.ldd + j] = round_tf32(v - hi);
+  }
+}
+int bw_prep(const PrepBatch& b, cudaStream_t s) {
+  PRD_REQUIRE(b.err == 0, "prep: more than %d jobs in one batch", PrepBatch::kMax);
+  if (b.n == 0) return 0;
+  PrepJobs jobs;
+  for (int i = 0; i < b.n; ++i) jobs.j[i] = b.jobs[i];
+  for (int i = b.n; i < PrepBatch::kMax; ++i) jobs.j[i] = PrepJob{nullptr, nullptr, nullptr, 0, 0, 0, 0, 0, 0, 0, 0, 0.f};
+  bw_prep_kernel<<<dim3(16, b.n), 256, 0, s>>>(jobs);
+  PRD_LAUNCHED();
+  return 0;
+}
+
 __global__ void bw_relu_kernel(float* x, long long n) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     x[i] = round_tf32(fmaxf(x[i], 0.f));

@@ -33,6 +33,43 @@ int bw_transpose(const float* src, long long lds, long long src_bs, float* dst, 
                  int cols, int batch, float alpha, cudaStream_t s);
 // dst[r, dcol + c] = round_tf32(src[r, scol + c]) for c < cols (strided 2-D copy, also used to pack weights row-wise)
 int bw_copy2d(const float* src, long long lds, float* dst, long long ldd, long long R, int cols, cudaStream_t s);
+// Several small weight-preparation jobs (rounded copies / transposes / zero fills / hi-lo splits of matrices of a few
+// hundred rows) in ONE launch: every backward op starts with 4 - 9 of them, and a step is ~1000 dependent launches whose
+// gaps (2 - 3 us each, also inside a CUDA graph) are not free.  A job is defined on its DESTINATION [drows, dcols]:
+// element (i, j) = src(i, j) (copy) or src(j, i) (transpose) where that lies inside the source [rows, cols], else 0 --
+// zero padding needs no separate fill, and jobs of one batch must write disjoint memory.
+struct PrepJob {
+  const float* src;  // NULL: zero fill
+  float* dst;
+  float* dst_lo;     // split: dst = round(src), dst_lo = round(src - dst)
+  long long lds, ldd;
+  int rows, cols;    // source extent
+  int drows, dcols;  // destination extent
+  int transpose, round;
+  float alpha;
+};
+struct PrepBatch {
+  static constexpr int kMax = 12;
+  PrepJob jobs[kMax];
+  int n = 0;
+  int err = 0;
+  void add(const PrepJob& j) {
+    if (n < kMax) jobs[n++] = j;
+    else err = 1;
+  }
+  void copy(const float* src, long long lds, float* dst, long long ldd, int rows, int cols, int round = 1) {
+    add(PrepJob{src, dst, nullptr, lds, ldd, rows, cols, rows, cols, 0, round, 1.f});
+  }
+  // dst [cols (padded to dcols rows... ), ldd]: dst[c][r] = alpha * src[r][c]; the destination extent may exceed the source (zeros)
+  void transpose(const float* src, long long lds, float* dst, long long ldd, int rows, int cols, int drows, int dcols, float alpha = 1.f) {
+    add(PrepJob{src, dst, nullptr, lds, ldd, rows, cols, drows, dcols, 1, 1, alpha});
+  }
+  void zero(float* dst, int n_) { add(PrepJob{nullptr, dst, nullptr, 0, n_, 0, 0, 1, n_, 0, 0, 0.f}); }
+  void split(const float* src, long long lds, float* hi, float* lo, long long ldd, int rows, int cols) {
+    add(PrepJob{src, hi, lo, lds, ldd, rows, cols, rows, cols, 0, 1, 1.f});
+  }
+};
+int bw_prep(const PrepBatch& b, cudaStream_t s);
 // hi = round_tf32(src), lo = round_tf32(src - hi)
 int bw_split2d(const float* src, long long lds, float* hi, float* lo, long long ldd, long long R, int cols, cudaStream_t s);
 // x = round_tf32(max(x, 0))

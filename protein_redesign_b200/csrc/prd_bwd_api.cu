@@ -67,14 +67,18 @@ float* transposed(bool dry, Carver& c, cudaStream_t st, const float* W, int rows
 // backward pass must agree with an fp32 evaluation -- with single tf32 operands ~3e-4 of the pre-activations change sign,
 // and every flipped element costs a full-size error in dh (relative L2 of dW ~ sqrt(3e-4) = 1.7e-2, measured 1.3e-2).
 // xh receives LN(x) rounded (the operand of the weight-gradient reductions).
+// prep: jobs of the caller that go into the same weight-preparation launch as the hi / lo split of W
 int relu_layer_fwd(bool dry, Carver& c, cudaStream_t st, long long R, int Cin, int Chid, const float* x, const float* W,
-                   const float* b, float* xh, float* h) {
+                   const float* b, float* xh, float* h, PrepBatch* prep = nullptr) {
   float* xlo = c.take((size_t)R * Cin);
   float* Whi = c.take((size_t)Chid * Cin);
   float* Wlo = c.take((size_t)Chid * Cin);
   if (dry) return 0;
+  PrepBatch own;
+  PrepBatch& pb = prep ? *prep : own;
+  pb.split(W, Cin, Whi, Wlo, Cin, Chid, Cin);
+  if (bw_prep(pb, st)) return 1;
   if (bw_ln_fwd(x, R, Cin, nullptr, nullptr, xh, st, xlo)) return 1;
-  if (bw_split2d(W, Cin, Whi, Wlo, Cin, Chid, Cin, st)) return 1;
   GemmArgs g = tfg((int)R, Chid, Cin, xlo, Cin, Whi, Cin, h, Chid);
   g.round_tf32 = 0;
   if (gemm_f16(g, st)) return 1;
@@ -100,16 +104,19 @@ int mlp_bwd(bool dry, Carver& c, cudaStream_t st, long long R, int Cin, int Chid
   float* h = c.take((size_t)R * Chid);
   float* dh = c.take((size_t)R * Chid);
   float* dxh = c.take((size_t)R * Cin);
-  if (relu_layer_fwd(dry, c, st, R, Cin, Chid, x, W1, b1, xh, h)) return 1;
-  float* W1T = transposed(dry, c, st, W1, Chid, Cin, Cin, &rc);   // [Cin, Chid]
+  float* W1T = c.take((size_t)Cin * up4(Chid));                   // [Cin, Chid]
   float* W2T = c.take((size_t)Chid * Cop);                        // [Chid, Cop] (zero padded)
+  PrepBatch pb;
+  if (!dry) {
+    pb.transpose(W1, Cin, W1T, up4(Chid), Chid, Cin, Cin, Chid);
+    pb.transpose(W2, Chid, W2T, Cop, Cout, Chid, Chid, Cop);
+  }
+  if (relu_layer_fwd(dry, c, st, R, Cin, Chid, x, W1, b1, xh, h, &pb)) return 1;
   const float* dyop = dy;
   float* dypad = nullptr;
   if (Cop != Cout) dypad = c.take((size_t)R * Cop);
   if (dry) return 0;
   if (rc) return 1;
-  if (bw_zero(W2T, (long long)Chid * Cop, st)) return 1;
-  if (bw_transpose(W2, Chid, 0, W2T, Cop, 0, Cout, Chid, 1, 1.f, st)) return 1;
   if (dypad) {
     if (bw_zero(dypad, R * Cop, st)) return 1;
     if (bw_copy2d(dy, Cout, dypad, Cop, R, Cout, st)) return 1;
@@ -157,13 +164,18 @@ int gated_attn_bwd(bool dry, Carver& c, cudaStream_t st, const AttnGeom& geom, l
   float* WoT = c.take((size_t)64 * Cin);
   if (dry) return 0;
   (void)rc;
-  const float* ws[4] = {w.Wq, w.Wk, w.Wv, w.Wg};
-  for (int k = 0; k < 4; ++k)
-    if (bw_copy2d(ws[k], Cin, Wcat + (size_t)k * 64 * Cin, Cin, 64, Cin, st)) return 1;
-  if (bw_zero(bcat, 256, st)) return 1;
-  PRD_CUDA_OK(cudaMemcpyAsync(bcat + 192, w.bg, 64 * sizeof(float), cudaMemcpyDeviceToDevice, st));
-  if (bw_transpose(Wcat, Cin, 0, WcatT, 256, 0, 256, Cin, 1, 1.f, st)) return 1;   // [Cin, 256]
-  if (bw_transpose(w.Wo, 64, 0, WoT, Cin, 0, Cin, 64, 1, 1.f, st)) return 1;       // Wo [Cin, 64] -> [64, Cin]
+  {
+    const float* ws[4] = {w.Wq, w.Wk, w.Wv, w.Wg};
+    PrepBatch pb;
+    for (int k = 0; k < 4; ++k) {
+      pb.copy(ws[k], Cin, Wcat + (size_t)k * 64 * Cin, Cin, 64, Cin);
+      pb.transpose(ws[k], Cin, WcatT + 64 * k, 256, 64, Cin, Cin, 64);  // columns [64 k, 64 k + 64) of [Cin, 256]
+    }
+    pb.zero(bcat, 192);
+    pb.copy(w.bg, 64, bcat + 192, 64, 1, 64, 0);
+    pb.transpose(w.Wo, 64, WoT, Cin, Cin, 64, 64, Cin);  // Wo [Cin, 64] -> [64, Cin]
+    if (bw_prep(pb, st)) return 1;
+  }
   if (bw_ln_fwd(x, R, Cin, nullptr, nullptr, xh, st)) return 1;
   {
     GemmArgs g = tfg((int)R, 256, Cin, xh, Cin, Wcat, Cin, qkvg, 256);
@@ -327,15 +339,20 @@ PRD_BWD_OP(triangle_multiplication) {
   const float *x = IN(0), *mask = IN(1);
   float* dy = OUT(0);
   // packed projection [ab_proj ; ab_gate ; out_gate] : [5 c_z, c_z]
-  if (bw_copy2d(WT(0), CZ, Wcat, CZ, C2, CZ, st)) return 1;
-  if (bw_copy2d(WT(2), CZ, Wcat + (size_t)C2 * CZ, CZ, C2, CZ, st)) return 1;
-  if (bw_copy2d(WT(6), CZ, Wcat + (size_t)2 * C2 * CZ, CZ, CZ, CZ, st)) return 1;
-  PRD_CUDA_OK(cudaMemcpyAsync(bcat, WT(1), C2 * sizeof(float), cudaMemcpyDeviceToDevice, st));
-  PRD_CUDA_OK(cudaMemcpyAsync(bcat + C2, WT(3), C2 * sizeof(float), cudaMemcpyDeviceToDevice, st));
-  PRD_CUDA_OK(cudaMemcpyAsync(bcat + 2 * C2, WT(7), CZ * sizeof(float), cudaMemcpyDeviceToDevice, st));
-  if (bw_transpose(Wcat, CZ, 0, WcatT, up4(CP), 0, CP, CZ, 1, 1.f, st)) return 1;
-  if (bw_copy2d(WT(4), CZ, Wor, CZ, CZ, CZ, st)) return 1;
-  if (bw_transpose(WT(4), CZ, 0, WoT, CZ, 0, CZ, CZ, 1, 1.f, st)) return 1;
+  {
+    PrepBatch pb;
+    const float* wsrc[3] = {WT(0), WT(2), WT(6)};
+    const float* bsrc[3] = {WT(1), WT(3), WT(7)};
+    const int wrows[3] = {C2, C2, CZ}, woff[3] = {0, C2, 2 * C2};
+    for (int k = 0; k < 3; ++k) {
+      pb.copy(wsrc[k], CZ, Wcat + (size_t)woff[k] * CZ, CZ, wrows[k], CZ);
+      pb.transpose(wsrc[k], CZ, WcatT + woff[k], up4(CP), wrows[k], CZ, CZ, wrows[k]);  // columns of [CZ, up4(CP)]
+      pb.copy(bsrc[k], wrows[k], bcat + woff[k], wrows[k], 1, wrows[k], 0);
+    }
+    pb.copy(WT(4), CZ, Wor, CZ, CZ, CZ);
+    pb.transpose(WT(4), CZ, WoT, CZ, CZ, CZ, CZ, CZ);
+    if (bw_prep(pb, st)) return 1;
+  }
   // ---- recompute forward ----
   if (bw_ln_fwd(x, R, CZ, nullptr, nullptr, p, st)) return 1;
   {
