@@ -298,8 +298,7 @@ int bw_dw_acc(const float* dY, long long ldy, const float* X, long long ldx, lon
   if (R <= 0) return 0;
   static const bool simt_only = getenv("PRD_DW_SIMT") && getenv("PRD_DW_SIMT")[0] == '1';  // A/B switch
   if (!simt_only && bw_dw_tc_applies(dY, ldy, X, ldx, R)) {
-    if (db != nullptr && bw_colsum(dY, ldy, R, Nout, db, alpha, s)) return 1;
-    return bw_dw_tc(dY, ldy, X, ldx, R, Nout, K, dW, ldw, alpha, s);
+    return bw_dw_tc(dY, ldy, X, ldx, R, Nout, K, dW, ldw, alpha, s, db);
   }
   const int gx = (K + 63) / 64, gy = (Nout + 63) / 64;
   long long want = (148LL * 4 + gx * gy - 1) / (gx * gy);  // ~4 CTAs per SM in total

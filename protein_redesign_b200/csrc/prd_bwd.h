@@ -26,8 +26,9 @@ int bw_dw_acc(const float* dY, long long ldy, const float* X, long long ldx, lon
 // the same reduction on the tensor cores (prd_bwd_dw.cu: tcgen05 kind::tf32, both operands MN-major, split over CTAs);
 // bw_dw_acc dispatches to it when bw_dw_tc_applies and PRD_DW_SIMT is not set
 bool bw_dw_tc_applies(const float* dY, long long ldy, const float* X, long long ldx, long long R);
+// db (optional): db[n] += alpha * sum_r dY[r, n], added up from the dY tiles the kernel stages anyway
 int bw_dw_tc(const float* dY, long long ldy, const float* X, long long ldx, long long R, int Nout, int K, float* dW,
-             long long ldw, float alpha, cudaStream_t s);
+             long long ldw, float alpha, cudaStream_t s, float* db = nullptr);
 // dst[b][c][r] = round_tf32(alpha * src[b][r][c]),  r < rows, c < cols
 int bw_transpose(const float* src, long long lds, long long src_bs, float* dst, long long ldd, long long dst_bs, int rows,
                  int cols, int batch, float alpha, cudaStream_t s);

@@ -221,8 +221,7 @@ int prd_dw_acc(const float* dY, long long ldy, const float* X, long long ldx, lo
   if (prd_device_check()) return 1;
   if (mode == 2) {
     PRD_REQUIRE(bw_dw_tc_applies(dY, ldy, X, ldx, R), "dw_acc: operands do not qualify for the tensor-core kernel");
-    if (db != nullptr && bw_colsum(dY, ldy, R, Nout, db, alpha, S(stream))) return 1;
-    return bw_dw_tc(dY, ldy, X, ldx, R, Nout, K, dW, ldw, alpha, S(stream));
+    return bw_dw_tc(dY, ldy, X, ldx, R, Nout, K, dW, ldw, alpha, S(stream), db);
   }
   return bw_dw_acc(dY, ldy, X, ldx, R, Nout, K, dW, ldw, db, alpha, S(stream));
 }

@@ -45,7 +45,8 @@ __host__ __device__ constexpr uint32_t umma_idesc_tf32_mn(uint32_t M, uint32_t N
 template <int BN>
 __global__ void __launch_bounds__(192, 1)
 bw_dw_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constant__ CUtensorMap map_x, long long R,
-                long long rows_per_cta, int Nout, int K, float* __restrict__ dW, long long ldw, float alpha) {
+                long long rows_per_cta, int Nout, int K, float* __restrict__ dW, long long ldw, float alpha,
+                float* __restrict__ db) {
   extern __shared__ uint8_t smem_raw[];
   using L = DwSmem<BN>;
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -61,10 +62,14 @@ bw_dw_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
   long long r_end = r_begin + rows_per_cta;
   if (r_end > R) r_end = R;
   const int nblk = r_end > r_begin ? static_cast<int>((r_end - r_begin + kRowsPerBlock - 1) / kRowsPerBlock) : 0;
+  // db (the bias gradient, = the column sums of dY): the four epilogue warps are idle during the main loop and the dY tile
+  // sits in shared memory anyway -- they add the 32 rows of every stage for their column (the CTAs of the first k-tile
+  // only), which replaces a separate pass over dY
+  const bool colsum = db != nullptr && blockIdx.y == 0;
   if (threadIdx.x == 0) {
     for (int s = 0; s < kDwStages; ++s) {
       mbar_init(&full[s], 1);
-      mbar_init(&empty[s], 1);
+      mbar_init(&empty[s], colsum ? 5 : 1);
     }
     mbar_init(done, 1);
     fence_barrier_init();
@@ -109,6 +114,24 @@ bw_dw_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
       }
     } else {
       const int q = warp & 3;
+      if (colsum) {
+        const int col = q * 32 + lane;
+        float csum = 0.f;
+        for (int it = 0; it < nblk; ++it) {
+          const int s = it % kDwStages;
+          mbar_wait(&full[s], (it / kDwStages) & 1);
+          if (n0 + col < Nout) {
+            // box q = columns [32 q, 32 q + 32): 32 rows of 128 bytes, the 32-byte chunks of row r XOR-ed with (r mod 4)
+            const uint8_t* box = smem + s * L::kStage + q * 4096 + ((lane & 7) << 2);
+            const int ch = lane >> 3;
+#pragma unroll 8
+            for (int r = 0; r < kRowsPerBlock; ++r) csum += *reinterpret_cast<const float*>(box + r * 128 + ((ch ^ (r & 3)) << 5));
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&empty[s]);
+        }
+        if (n0 + col < Nout) atomicAdd(db + n0 + col, alpha * csum);
+      }
       mbar_wait(done, 0);
       tc_fence_after();
       const int n = n0 + q * 32 + lane;
@@ -133,7 +156,7 @@ bw_dw_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
 
 template <int BN>
 int launch_dw(const float* dY, long long ldy, const float* X, long long ldx, long long R, int Nout, int K, float* dW,
-              long long ldw, float alpha, cudaStream_t s) {
+              long long ldw, float alpha, float* db, cudaStream_t s) {
   using L = DwSmem<BN>;
   CUtensorMap map_dy, map_x;
   TmaDims d;
@@ -156,7 +179,7 @@ int launch_dw(const float* dY, long long ldy, const float* X, long long ldx, lon
   if (chunks < 1) chunks = 1;
   long long rows_per_cta = ((R + chunks - 1) / chunks + kRowsPerBlock - 1) / kRowsPerBlock * kRowsPerBlock;
   chunks = (R + rows_per_cta - 1) / rows_per_cta;
-  bw_dw_tc_kernel<BN><<<dim3(gx, gy, (unsigned)chunks), 192, L::kTotal, s>>>(map_dy, map_x, R, rows_per_cta, Nout, K, dW, ldw, alpha);
+  bw_dw_tc_kernel<BN><<<dim3(gx, gy, (unsigned)chunks), 192, L::kTotal, s>>>(map_dy, map_x, R, rows_per_cta, Nout, K, dW, ldw, alpha, db);
   PRD_LAUNCHED();
   return 0;
 }
@@ -169,10 +192,10 @@ bool bw_dw_tc_applies(const float* dY, long long ldy, const float* X, long long 
          ((reinterpret_cast<uintptr_t>(X) & 15) == 0) && R >= 256 && R < 0x7fffffffLL;
 }
 int bw_dw_tc(const float* dY, long long ldy, const float* X, long long ldx, long long R, int Nout, int K, float* dW,
-             long long ldw, float alpha, cudaStream_t s) {
-  if (K <= 64) return launch_dw<64>(dY, ldy, X, ldx, R, Nout, K, dW, ldw, alpha, s);
-  if (K <= 128) return launch_dw<128>(dY, ldy, X, ldx, R, Nout, K, dW, ldw, alpha, s);
-  return launch_dw<256>(dY, ldy, X, ldx, R, Nout, K, dW, ldw, alpha, s);
+             long long ldw, float alpha, cudaStream_t s, float* db) {
+  if (K <= 64) return launch_dw<64>(dY, ldy, X, ldx, R, Nout, K, dW, ldw, alpha, db, s);
+  if (K <= 128) return launch_dw<128>(dY, ldy, X, ldx, R, Nout, K, dW, ldw, alpha, db, s);
+  return launch_dw<256>(dY, ldy, X, ldx, R, Nout, K, dW, ldw, alpha, db, s);
 }
 
 }  // namespace prd
