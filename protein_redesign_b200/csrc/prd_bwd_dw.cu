@@ -10,6 +10,9 @@
 // partial sum to global memory with fp32 atomics (split-K over CTAs).  Operands are expected rounded to tf32 by their
 // producers (prd_bwd.h conventions); products of two tf32 values are exact in the fp32 accumulator.
 #include "prd_bwd.h"
+
+#include <stdlib.h>
+
 #include "prd_common.cuh"
 
 namespace prd {
@@ -134,17 +137,26 @@ bw_dw_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
       }
       mbar_wait(done, 0);
       tc_fence_after();
-      const int n = n0 + q * 32 + lane;
+      // TMEM lane = row n of dW: adding straight from the registers makes every RED instruction touch 32 different lines
+      // (32 L2 atomic transactions; 148+ CTAs x 4096 of them were ~20 us of every launch).  Each warp transposes its
+      // 32 x 32 chunk through shared memory (the pipeline stages are free now) and adds whole 128-byte rows instead.
+      float* tile = reinterpret_cast<float*>(smem) + q * (32 * 33);
 #pragma unroll 1
       for (int c = 0; c < BN / 32; ++c) {
         uint32_t r[32];
         tmem_ld32(tmem + (static_cast<uint32_t>(q * 32) << 16) + c * 32, r);
         tmem_ld_wait();
-        if (n < Nout) {
-          float* row = dW + (long long)n * ldw + k0 + c * 32;
+        __syncwarp();
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (k0 + c * 32 + j < K) atomicAdd(row + j, alpha * __uint_as_float(r[j]));
+        for (int j = 0; j < 32; ++j) tile[lane * 33 + j] = alpha * __uint_as_float(r[j]);
+        __syncwarp();
+        const int k = k0 + c * 32 + lane;
+        if (k < K) {
+#pragma unroll 8
+          for (int i = 0; i < 32; ++i) {
+            const int n = n0 + q * 32 + i;
+            if (n < Nout) atomicAdd(dW + (long long)n * ldw + k, tile[i * 33 + lane]);
+          }
         }
       }
     }
@@ -173,7 +185,11 @@ int launch_dw(const float* dY, long long ldy, const float* X, long long ldx, lon
     attr_set = true;
   }
   const int gx = (Nout + 127) / 128, gy = (K + BN - 1) / BN;
-  long long chunks = (2LL * kNumSMs + gx * gy - 1) / (gx * gy);        // ~2 CTAs per SM in total
+  // CTAs per SM in total (PRD_DW_CPS: tuning switch): two pipelines per SM hide each other's prologue / epilogue; the widest
+  // tile's stages leave room for one
+  static const int cps_env = getenv("PRD_DW_CPS") ? atoi(getenv("PRD_DW_CPS")) : 0;
+  const int cps = cps_env > 0 ? cps_env : (BN == 256 ? 1 : 2);
+  long long chunks = ((long long)cps * kNumSMs + gx * gy - 1) / (gx * gy);
   const long long max_chunks = (R + 8 * kRowsPerBlock - 1) / (8 * kRowsPerBlock);  // at least 8 pipeline blocks per CTA
   if (chunks > max_chunks) chunks = max_chunks;
   if (chunks < 1) chunks = 1;

@@ -44,6 +44,22 @@ def main():
         ms = timeit(lambda: _lib.gemm_f16(A, Bm, C, mul=mul, mul_step=mul is not None, round_tf32=True))
         byts = 4 * (M * K + M * N * (2 if mul is not None else 1))
         print(f"{name:36s} M={M} N={N:3d} K={K:3d}  {ms:7.3f} ms  {byts / ms / 1e6:7.0f} GB/s  floor {byts / 6454e6:6.3f} ms")
+    # weight-gradient reductions dW[n, k] = sum_r dY[r, n] X[r, k] (tensor-core kernel, bias gradient fused)
+    import ctypes
+    lib = _lib.load()
+    lib.prd_dw_acc.restype = ctypes.c_int
+    lib.prd_dw_acc.argtypes = [ctypes.c_void_p, ctypes.c_longlong, ctypes.c_void_p, ctypes.c_longlong, ctypes.c_longlong, ctypes.c_int,
+                               ctypes.c_int, ctypes.c_void_p, ctypes.c_longlong, ctypes.c_void_p, ctypes.c_float, ctypes.c_int, ctypes.c_void_p]
+    for name, Nout, K in (("dW 64 x 64", 64, 64), ("dW 128 x 64", 128, 64), ("dW 256 x 64 (q k v g)", 256, 64), ("dW 64 x 256 (pair_fc W2)", 64, 256),
+                          ("dW 256 x 64 (pair_fc W1)", 256, 64)):
+        dY = torch.randn(R, Nout, device=dev)
+        X = torch.randn(R, K, device=dev)
+        dW = torch.zeros(Nout, K, device=dev)
+        db = torch.zeros(Nout, device=dev)
+        st = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        ms = timeit(lambda: lib.prd_dw_acc(dY.data_ptr(), Nout, X.data_ptr(), K, R, Nout, K, dW.data_ptr(), K, db.data_ptr(), 1.0, 2, st))
+        byts = 4 * R * (Nout + K)
+        print(f"{name:36s} R={R}  {ms:7.3f} ms  {byts / ms / 1e6:7.0f} GB/s  floor {byts / 6454e6:6.3f} ms")
     # what bounds the wide-output shapes: pure-write bandwidth, fp16 output (half the bytes), an L2-resident problem
     big = torch.empty(R, 256, device=dev)
     ms = timeit(lambda: big.fill_(1.0))
