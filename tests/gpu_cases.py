@@ -1207,3 +1207,60 @@ def case_fused_bias(cfg=syn.PAPER, B=2, N=72, seed=62):
 
 CASES["fused_bias"] = lambda: case_fused_bias()
 CASES["fused_bias_readme"] = lambda: case_fused_bias(syn.README, 2, 40)
+
+
+# ------------------------------------------------------------------------------------------
+# round 2, second half: the GEMM's TMA-store epilogue, the tensor-core backward attention, batched weight preparation
+# ------------------------------------------------------------------------------------------
+def case_gemm_tf32_epilogue(M=197, N=100, K=64, nb1=2, seed=3):
+    """fp32 C through the tensor-map store (ldc % 4 == 0) on tiles that are ragged in M and N (boxes clipped by the TMA unit),
+    with every epilogue operand: bias, [M, N] gate (ReLU backward) and [M, N] addend, tf32-rounded result."""
+    g = torch.Generator().manual_seed(seed)
+
+    def r_tf32(x):
+        return ((x.view(torch.int32) + 0x1000) & ~0x1FFF).view(torch.float32)
+
+    a = r_tf32(torch.randn(1, nb1, M, K, generator=g))
+    b = r_tf32(torch.randn(1, nb1, N, K, generator=g))
+    bias = torch.randn(N, generator=g)
+    gate = torch.randn(1, nb1, M, N, generator=g)
+    add = torch.randn(1, nb1, M, N, generator=g)
+    prod = torch.matmul(a.double(), b.double().transpose(-1, -2)) + bias.double()
+    want = r_tf32((torch.where(gate > 0, prod, torch.zeros_like(prod)) + add.double()).float())
+    out = torch.full((1, nb1, M, N), float("nan"), dtype=torch.float32, device=DEV)
+    _lib.gemm_f16(a.to(DEV).contiguous(), b.to(DEV).contiguous(), out, bias=bias.to(DEV), mul=gate.to(DEV).contiguous(), mul_step=True,
+                  add=add.to(DEV).contiguous(), round_tf32=True)
+    torch.cuda.synchronize()
+    # a result within half a tf32 ulp of a rounding boundary may land on the other side: compare at tf32 resolution
+    return {"rel": (rel(out, want), 2e-4), "finite": (0.0 if bool(torch.isfinite(out).all()) else 1.0, 0.0)}
+
+
+def case_attn_tc_vs_simt(cfg=syn.PAPER, B=2, N=77, mode="ending", seed=61, pad=6):
+    """The tensor-core backward attention (mma.sync tf32) against the exact fp32 SIMT kernels it replaced, on a length that
+    is no multiple of any tile (77 = 2 x 32 + 13), with padded tokens: same op, PRD_ATTN_SIMT toggled."""
+    import os
+    from protein_redesign_b200 import autograd as ag
+    prefix = _block_prefix() + f"pair_attn_{mode}."
+    res = {}
+    for tag, env in (("tc", "0"), ("simt", "1")):
+        os.environ["PRD_ATTN_SIMT"] = env
+        try:
+            m, sd, P, G = _bwd_setup(cfg, seed, [prefix])
+            _, pair, mask = _pair_inputs(cfg, B, N, seed, pad)
+            d = _rand_like(pair, seed + 1).to(DEV).contiguous()
+            ag.triangle_attention_bwd(cfg, P, G, prefix + "attn.", 1 if mode == "ending" else 0, pair.to(DEV).contiguous(), mask.to(DEV), d)
+            torch.cuda.synchronize()
+            res[tag] = (d.clone(), {k: v.clone() for k, v in G.items()})
+        finally:
+            os.environ.pop("PRD_ATTN_SIMT", None)
+    out = {"dx": (rel(res["tc"][0], res["simt"][0]), 1e-3)}
+    for k in res["tc"][1]:
+        if k.startswith(prefix) and float(res["simt"][1][k].norm()) > 0:
+            out["dW:" + k] = (rel(res["tc"][1][k], res["simt"][1][k]), 2e-3)
+    return out
+
+
+CASES["gemm_tf32_epilogue"] = lambda: case_gemm_tf32_epilogue()
+CASES["gemm_tf32_epilogue_unaligned"] = lambda: case_gemm_tf32_epilogue(M=130, N=70, K=96, nb1=1, seed=4)   # ldc % 4 != 0: no tensor map
+CASES["attn_tc_vs_simt"] = lambda: case_attn_tc_vs_simt()
+CASES["attn_tc_vs_simt_starting"] = lambda: case_attn_tc_vs_simt(mode="starting", N=45, seed=62, pad=0)

@@ -35,7 +35,7 @@ CASE_NAMES = [
     "triattn_n512_ending", "outer_linear_n512", "pair_transition_n512", "heads_n512", "embeddings_n512", "denoiser_forward",
     "folding_block_forward", "predict_step_ema", "back_to_back_batches",
     # round 2: backward pass (every prd_<op>_bwd vs autograd through the oracle)
-    "gemm_tf32", "gemm_tf32_batch_tails", "bwd_pair_fc", "bwd_single_fc", "bwd_triattn_starting", "bwd_triattn_ending", "bwd_triattn_n140",
+    "gemm_tf32", "gemm_tf32_batch_tails", "gemm_tf32_epilogue", "gemm_tf32_epilogue_unaligned", "attn_tc_vs_simt", "attn_tc_vs_simt_starting", "bwd_pair_fc", "bwd_single_fc", "bwd_triattn_starting", "bwd_triattn_ending", "bwd_triattn_n140",
     "bwd_trimul_outgoing", "bwd_trimul_incoming", "bwd_trimul_n75", "bwd_outer_linear", "bwd_single_attention", "bwd_spattention",
     "bwd_heads", "bwd_embeddings", "bwd_embeddings_readme", "train_step_paper_n72",
     # round 2: Lightning-free predict loop and GPU post-processing
