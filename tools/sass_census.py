@@ -33,7 +33,8 @@ def main():
                     counts[cur][k] += 1
     print("# SASS census of libprd_sm100.so (cuobjdump -sass, sm_100a): instruction counts per kernel\n")
     print("UTCHMMA = tcgen05.mma (kind::f16 / kind::tf32), LDTM / STTM = tcgen05.ld / st (TMEM), UTMALDG = cp.async.bulk.tensor (TMA),")
-    print("UBLKCP = cp.async.bulk, SYNCS = mbarrier ops, HMMA = legacy mma.sync (none expected).\n")
+    print("UBLKCP = cp.async.bulk, SYNCS = mbarrier ops, HMMA = warp-level mma.sync (only the head-dim-16 attention of the backward pass: prd_bwd_attn.cu, HMMA.1688.F32.TF32),\n"
+          "UTMASTG = cp.async.bulk.tensor store (the GEMM's fp32 epilogue).\n")
     print("| kernel | " + " | ".join(KEYS) + " |")
     print("|---|" + "---:|" * len(KEYS))
     tot = collections.Counter()
