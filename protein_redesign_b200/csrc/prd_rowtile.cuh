@@ -95,28 +95,6 @@ __device__ __forceinline__ void layernorm_inplace(float (&x)[CZ]) {
   for (int i = 0; i < CZ; ++i) x[i] *= rstd;
 }
 
-// Write channels [32 half, 32 half + 32) of one row of a [128 x 64] fp16 K-block (two threads per row).
-template <int CZ>
-__device__ __forceinline__ void store_a_half_row(uint8_t* a_tile, int t, int half, const float (&y)[CZ]) {
-#pragma unroll
-  for (int c4 = 0; c4 < 4; ++c4) {
-    uint4 o = make_uint4(0, 0, 0, 0);
-#pragma unroll
-    for (int hh = 0; hh < 2; ++hh) {
-      if (hh == half) {
-        const int ch = hh * 4 + c4;
-        if (ch * 8 < CZ) {
-          o.x = pack_half2(y[ch * 8 + 0], y[ch * 8 + 1]);
-          o.y = pack_half2(y[ch * 8 + 2], y[ch * 8 + 3]);
-          o.z = pack_half2(y[ch * 8 + 4], y[ch * 8 + 5]);
-          o.w = pack_half2(y[ch * 8 + 6], y[ch * 8 + 7]);
-        }
-      }
-    }
-    *reinterpret_cast<uint4*>(a_tile + sw128_offset(t, half * 4 + c4)) = o;
-  }
-}
-
 // Write one row (CZ <= 64 values, zero padded to 64) of a [128 x 64] fp16 K-block.
 template <int CZ>
 __device__ __forceinline__ void store_a_row(uint8_t* a_tile, int t, const float (&y)[CZ]) {
