@@ -4,6 +4,7 @@
 //   triattn_proj/out  TriangleAttention q,k,v,gate / out_proj    (modules.py:185-225,236-243)
 // See prd_rowtile.cuh for the execution model.
 #include "prd_kernels.h"
+#include <stdlib.h>
 #include <string.h>
 #include "prd_rowtile.cuh"
 
@@ -895,7 +896,11 @@ template <int CZ>
 __global__ void __launch_bounds__(256, 1)
 trimul_out_kernel(const float* pair, float* dst, int residual, const __half* __restrict__ xpl,
                   const __grid_constant__ CUtensorMap map_x, int use_tma, int N, int Nx, long long R,
-                  const __half* __restrict__ w_out, const float* __restrict__ b_out) {
+                  const __half* __restrict__ w_out, const float* __restrict__ b_out,
+                  const __grid_constant__ CUtensorMap map_in, const __grid_constant__ CUtensorMap map_out, int row_tma) {
+  // row_tma (pair_dim 64): the 128 pair rows of a tile arrive as ONE TMA tile (two swizzled boxes) and the output rows leave
+  // as two tile stores per warp.  Per-thread 256-byte bulk copies serialise lane by lane on the uniform datapath
+  // (ELECT / R2UR / UBLKCP loops: 26 % of this kernel's instructions in ncu, profiles/r02_launches.md).
   extern __shared__ uint8_t raw[];
   pdl_trigger();
   constexpr int kStage = (RowStage<CZ>::kBytes + 1023) / 1024 * 1024;
@@ -919,13 +924,17 @@ trimul_out_kernel(const float* pair, float* dst, int residual, const __half* __r
   uint64_t* mma_bar = bars + 2 + g.grp;
   uint64_t* xfull = bars + 4 + g.grp;
   if (threadIdx.x == 0) {
-    mbar_init(&bars[0], kTileRows);
-    mbar_init(&bars[1], kTileRows);
+    mbar_init(&bars[0], row_tma ? 1 : kTileRows);
+    mbar_init(&bars[1], row_tma ? 1 : kTileRows);
     mbar_init(&bars[2], 1);
     mbar_init(&bars[3], 1);
     mbar_init(&bars[4], 1);
     mbar_init(&bars[5], 1);
     if (use_tma) tma_prefetch_desc(&map_x);
+    if (row_tma) {
+      tma_prefetch_desc(&map_in);
+      tma_prefetch_desc(&map_out);
+    }
     fence_barrier_init();
   }
   if (threadIdx.x < 32) tmem_alloc(tmem_slot, 2 * TCOLS);
@@ -955,9 +964,19 @@ trimul_out_kernel(const float* pair, float* dst, int residual, const __half* __r
     mbar_expect_tx(xfull, kXBytes);
     tma_load_4d(const_cast<__half*>(sX), &map_x, xfull, j0, i, 0, b);
   };
+  auto issue_rows = [&](long long tl) {  // one thread: the tile's 128 rows (rows past R are zero-filled)
+    mbar_expect_tx(full, 32768);
+    const int r0 = static_cast<int>(tl * kTileRows);
+    tma_load_2d(sSt, &map_in, full, 0, r0);
+    tma_load_2d(sSt + 16384, &map_in, full, 32, r0);
+  };
   if (tile < num_tiles) {
     const long long r = tile * kTileRows + t;
-    issue_row_load<CZ>(sSt, t, pair + r * CZ, r < R, full);
+    if (row_tma) {
+      if (t == 0) issue_rows(tile);
+    } else {
+      issue_row_load<CZ>(sSt, t, pair + r * CZ, r < R, full);
+    }
     if (use_tma && t == 0) issue_x(tile);
   }
   for (int it = 0; tile < num_tiles; tile += stride, ++it) {
@@ -995,13 +1014,15 @@ trimul_out_kernel(const float* pair, float* dst, int residual, const __half* __r
     }
     mbar_wait(full, it & 1);
     float xr[CZ];
-    if (valid) {
+    if (row_tma) {
+      if constexpr (CZ == 64) read_row_tma64(sSt, t, xr);
+    } else if (valid) {
       read_row<CZ>(stage_row<CZ>(sSt, t), xr);
     } else {
 #pragma unroll
       for (int q = 0; q < CZ; ++q) xr[q] = 0.f;
     }
-    if (tile + stride < num_tiles) {
+    if (!row_tma && tile + stride < num_tiles) {
       const long long rn = (tile + stride) * kTileRows + t;
       issue_row_load<CZ>(sSt, t, pair + rn * CZ, rn < R, full);
     }
@@ -1016,6 +1037,7 @@ trimul_out_kernel(const float* pair, float* dst, int residual, const __half* __r
     store_a_row<CZ>(sAx, t, x);
     g.sync_before_mma();
     if (use_tma && t == 64 && tile + stride < num_tiles) issue_x(tile + stride);  // every thread has read the x tile
+    if (row_tma && t == 96 && tile + stride < num_tiles) issue_rows(tile + stride);  // ... and its pair row
     if (t < 32) {  // warp-uniform issue: UMMA operands stay in uniform registers
       tc_fence_after();
       if (elect_one()) {
@@ -1046,11 +1068,23 @@ trimul_out_kernel(const float* pair, float* dst, int residual, const __half* __r
           o[e] = sigmoidf_fast(__uint_as_float(ga[j + e]) + sB[cc]) * (__uint_as_float(pr[j + e]) + sB[CZ + cc]);
           if (residual) o[e] += xr[cc];
         }
-        *reinterpret_cast<float4*>(my + c * 32 + j) = make_float4(o[0], o[1], o[2], o[3]);
+        if (row_tma)  // swizzled [2 boxes][128 rows][128 bytes] tile: box c, row t, 16-byte chunk (j / 4) ^ (t & 7)
+          *reinterpret_cast<float4*>(sAp + c * 16384 + t * 128 + ((((j >> 2)) ^ (t & 7)) << 4)) = make_float4(o[0], o[1], o[2], o[3]);
+        else
+          *reinterpret_cast<float4*>(my + c * 32 + j) = make_float4(o[0], o[1], o[2], o[3]);
       }
     }
     fence_proxy_async_smem();
-    if (valid) bulk_s2g(dst + r * CZ, my, CZ * 4);
+    if (row_tma) {
+      __syncwarp();
+      if ((t & 31) == 0 && tile * kTileRows + g.warp * 32 < R) {  // this warp's 32 rows x 2 boxes (clipped at R by the TMA unit)
+        const int r0 = static_cast<int>(tile * kTileRows) + g.warp * 32;
+        tma_store_2d(&map_out, sAp + g.warp * 4096, 0, r0);
+        tma_store_2d(&map_out, sAp + 16384 + g.warp * 4096, 32, r0);
+      }
+    } else if (valid) {
+      bulk_s2g(dst + r * CZ, my, CZ * 4);
+    }
     bulk_commit();
     tc_fence_before();
   }
@@ -1081,7 +1115,22 @@ static int launch_trimul_out(const PairDims& d, const float* pair, float* dst, i
     t.box[0] = use_tma ? kTileRows : 8; t.box[1] = 1; t.box[2] = CZ; t.box[3] = 1;
     if (make_tensor_map(&mx, x, 2, 4, t, false)) return 1;
   }
-  PRD_CUDA_OK(launch_pdl(kern, grid_for((tiles + 1) / 2, 1), 256, smem, s, pair, dst, residual, x, mx, use_tma, d.N, Nx, R, w_out, b_out));
+  // pair rows as a 2-D tensor [R, CZ]: load box = [32 channels][128 rows], store box = [32 channels][32 rows] (one warp)
+  CUtensorMap m_in = mx, m_out = mx;
+  static const bool row_tma_off = getenv("PRD_ROW_TMA") && getenv("PRD_ROW_TMA")[0] == '0';  // A/B switch
+  const int row_tma = (!row_tma_off && CZ == 64 && R < 0x7fffffffLL && (reinterpret_cast<uintptr_t>(pair) & 15) == 0 &&
+                       (reinterpret_cast<uintptr_t>(dst) & 15) == 0) ? 1 : 0;
+  if (row_tma) {
+    TmaDims t;
+    t.size[0] = (uint64_t)CZ; t.size[1] = (uint64_t)R; t.size[2] = 1; t.size[3] = 1;
+    t.stride[0] = (uint64_t)CZ * 4; t.stride[1] = (uint64_t)CZ * 4 * R; t.stride[2] = t.stride[1];
+    t.box[0] = 32; t.box[1] = kTileRows; t.box[2] = 1; t.box[3] = 1;
+    if (make_tensor_map(&m_in, pair, 4, 2, t, true)) return 1;
+    t.box[1] = 32;
+    if (make_tensor_map(&m_out, dst, 4, 2, t, true)) return 1;
+  }
+  PRD_CUDA_OK(launch_pdl(kern, grid_for((tiles + 1) / 2, 1), 256, smem, s, pair, dst, residual, x, mx, use_tma, d.N, Nx, R, w_out, b_out,
+                         m_in, m_out, row_tma));
   PRD_LAUNCHED();
   return 0;
 }
