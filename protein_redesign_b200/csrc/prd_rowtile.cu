@@ -1381,7 +1381,11 @@ int triattn_proj(const PairDims& d, const float* pair, int mode, const __half* w
 template <int CZ>
 __global__ void __launch_bounds__(256, 1)
 triattn_out_kernel(const __grid_constant__ CUtensorMap map_og, const float* pair, float* dst, int residual, RowMap map,
-                   long long R, const __half* __restrict__ w_o, const float* __restrict__ b_o) {
+                   long long R, const __half* __restrict__ w_o, const float* __restrict__ b_o,
+                   const __grid_constant__ CUtensorMap map_in, const __grid_constant__ CUtensorMap map_out, int row_tma) {
+  // row_tma (pair_dim 64; "ending" needs N % 128 == 0 so that a tile is one sequence): the residual rows of a tile arrive as
+  // ONE TMA tile (two swizzled boxes) and the output rows leave as two tile stores per warp -- the per-thread 256-byte bulk
+  // copies serialise lane by lane on the uniform datapath and were 58 % of this kernel's instructions (ncu).
   // Both inputs of a tile are in flight a tile ahead: the og tile [128 rows x 64 halves] is one swizzled TMA box that IS the
   // UMMA A operand (issued as soon as the previous tile's UMMAs have completed), the residual rows go to the other of two row
   // stages (the stage a tile was read from also carries its output rows to the bulk store).
@@ -1405,9 +1409,13 @@ triattn_out_kernel(const __grid_constant__ CUtensorMap map_og, const float* pair
   uint64_t* mma_bar = bars + 4 + g.grp;
   uint64_t* afull = bars + 6 + g.grp;
   if (threadIdx.x == 0) {
-    for (int q = 0; q < 4; ++q) mbar_init(&bars[q], kTileRows);
+    for (int q = 0; q < 4; ++q) mbar_init(&bars[q], row_tma ? 1 : kTileRows);
     for (int q = 4; q < 8; ++q) mbar_init(&bars[q], 1);
     tma_prefetch_desc(&map_og);
+    if (row_tma) {
+      tma_prefetch_desc(&map_in);
+      tma_prefetch_desc(&map_out);
+    }
     fence_barrier_init();
   }
   if (threadIdx.x < 32) tmem_alloc(tmem_slot, 2 * TCOLS);
@@ -1441,11 +1449,34 @@ triattn_out_kernel(const __grid_constant__ CUtensorMap map_og, const float* pair
     mbar_expect_tx(afull, 16384);
     tma_load_3d(sA, &map_og, afull, 0, static_cast<int>(tl * kTileRows), 0);
   };
+  // coordinates of the tile's first row in map_in / map_out: (row, 0, 0) for "starting" (the rows are consecutive in memory),
+  // (seq, tok, b) for "ending"
+  auto tile_coords = [&](long long tl, int row_off, int& c1, int& c2, int& c3) {
+    const long long r0 = tl * kTileRows + row_off;
+    if (map.transposed) {
+      int b, sq, tk;
+      map.decompose(r0, b, sq, tk);
+      c1 = sq; c2 = tk; c3 = b;
+    } else {
+      c1 = static_cast<int>(r0); c2 = 0; c3 = 0;
+    }
+  };
+  auto issue_rows = [&](long long tl, uint8_t* stage, uint64_t* bar) {  // one thread; rows past R are zero-filled
+    int c1, c2, c3;
+    tile_coords(tl, 0, c1, c2, c3);
+    mbar_expect_tx(bar, 32768);
+    tma_load_4d(stage, &map_in, bar, 0, c1, c2, c3);
+    tma_load_4d(stage + 16384, &map_in, bar, 32, c1, c2, c3);
+  };
   bool valid = false;
   long long src = 0;
   if (tile < num_tiles) {
-    src = src_of(tile, valid);
-    issue_row_load<CZ>(sSt, t, pair + src * CZ, valid && residual, full);
+    if (row_tma) {
+      if (t == 32 && residual) issue_rows(tile, sSt, full);
+    } else {
+      src = src_of(tile, valid);
+      issue_row_load<CZ>(sSt, t, pair + src * CZ, valid && residual, full);
+    }
     if (t == 0) issue_og(tile);
   }
   for (int it = 0; tile < num_tiles; tile += stride, ++it) {
@@ -1455,13 +1486,15 @@ triattn_out_kernel(const __grid_constant__ CUtensorMap map_og, const float* pair
     long long src_n = 0;
     // the other stage carried the previous tile's output row of this thread: its bulk store must have read it
     bulk_wait_read0();
-    if (has_next) {
+    if (has_next && !row_tma) {
       src_n = src_of(tile + stride, valid_n);
       issue_row_load<CZ>(sSt + (cur ^ 1) * kStage, t, pair + src_n * CZ, valid_n && residual, full + (cur ^ 1));
     }
     // every thread of the group has finished the previous tile's TMEM reads
     tc_fence_before();
     g.bar();
+    // (row_tma) ... and every warp's tile stores out of the other stage have been read: it can take the next tile's rows
+    if (row_tma && has_next && residual && t == 32) issue_rows(tile + stride, sSt + (cur ^ 1) * kStage, full + (cur ^ 1));
     if (t < 32) {  // warp-uniform issue: UMMA operands stay in uniform registers
       mbar_wait(afull, it & 1);
       tc_fence_after();
@@ -1472,12 +1505,13 @@ triattn_out_kernel(const __grid_constant__ CUtensorMap map_og, const float* pair
       }
       __syncwarp();
     }
-    mbar_wait(full + cur, (it >> 1) & 1);
+    if (!row_tma || residual) mbar_wait(full + cur, (it >> 1) & 1);
     mbar_wait(mma_bar, mma_phase);
     mma_phase ^= 1;
     tc_fence_after();
     if (t == 64 && has_next) issue_og(tile + stride);  // the A tile is free: this tile's UMMAs have completed
     float* my = stage_row<CZ>(sSt + cur * kStage, t);
+    uint8_t* tstage = sSt + cur * kStage;  // row_tma: swizzled [2 boxes][128 rows][128 bytes]
 #pragma unroll
     for (int c = 0; c < CZ / 32; ++c) {
       uint32_t acc[32];
@@ -1485,16 +1519,28 @@ triattn_out_kernel(const __grid_constant__ CUtensorMap map_og, const float* pair
       tmem_ld_wait();
 #pragma unroll
       for (int j = 0; j < 32; j += 4) {
-        float4 x = (residual && valid) ? *reinterpret_cast<float4*>(my + c * 32 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+        float4* px = row_tma ? reinterpret_cast<float4*>(tstage + c * 16384 + t * 128 + (((j >> 2) ^ (t & 7)) << 4))
+                             : reinterpret_cast<float4*>(my + c * 32 + j);
+        float4 x = (residual && (row_tma || valid)) ? *px : make_float4(0.f, 0.f, 0.f, 0.f);
         x.x += __uint_as_float(acc[j + 0]) + sB[c * 32 + j + 0];
         x.y += __uint_as_float(acc[j + 1]) + sB[c * 32 + j + 1];
         x.z += __uint_as_float(acc[j + 2]) + sB[c * 32 + j + 2];
         x.w += __uint_as_float(acc[j + 3]) + sB[c * 32 + j + 3];
-        *reinterpret_cast<float4*>(my + c * 32 + j) = x;
+        *px = x;
       }
     }
     fence_proxy_async_smem();
-    if (valid) bulk_s2g(dst + src * CZ, my, CZ * 4);
+    if (row_tma) {
+      __syncwarp();
+      if ((t & 31) == 0 && tile * kTileRows + g.warp * 32 < R) {  // this warp's 32 rows x 2 boxes, clipped at R by the TMA unit
+        int c1, c2, c3;
+        tile_coords(tile, g.warp * 32, c1, c2, c3);
+        tma_store_4d(&map_out, tstage + g.warp * 4096, 0, c1, c2, c3);
+        tma_store_4d(&map_out, tstage + 16384 + g.warp * 4096, 32, c1, c2, c3);
+      }
+    } else if (valid) {
+      bulk_s2g(dst + src * CZ, my, CZ * 4);
+    }
     bulk_commit();
     valid = valid_n;
     src = src_n;
@@ -1525,7 +1571,30 @@ static int launch_triattn_out(const PairDims& d, const float* pair, float* dst, 
     t.box[0] = 64; t.box[1] = 128; t.box[2] = 1; t.box[3] = 1;
     if (make_tensor_map(&mo, og, 2, 3, t, true)) return 1;
   }
-  PRD_CUDA_OK(launch_pdl(kern, grid_for((tiles + 1) / 2, 1), 256, smem, s, mo, pair, dst, residual, map, R, w_o, b_o));
+  // pair rows: "starting" = the 2-D tensor [R, CZ] (consecutive rows); "ending" = (channel, seq, tok, b) of [B][tok][seq][CZ]
+  // with the tile along tok.  Load box = 128 rows, store box = 32 rows (one warp).
+  static const bool row_tma_off = getenv("PRD_ROW_TMA") && getenv("PRD_ROW_TMA")[0] == '0';  // A/B switch
+  const int row_tma = (!row_tma_off && CZ == 64 && R < 0x7fffffffLL && (mode == 0 || d.N % kTileRows == 0) &&
+                       (reinterpret_cast<uintptr_t>(pair) & 15) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) ? 1 : 0;
+  CUtensorMap m_in = mo, m_out = mo;
+  if (row_tma) {
+    TmaDims t;
+    for (int pass = 0; pass < 2; ++pass) {
+      const uint32_t rows = pass == 0 ? kTileRows : 32;
+      if (mode == 0) {
+        t.size[0] = (uint64_t)CZ; t.size[1] = (uint64_t)R; t.size[2] = 1; t.size[3] = 1;
+        t.stride[0] = (uint64_t)CZ * 4; t.stride[1] = (uint64_t)CZ * 4 * R; t.stride[2] = t.stride[1];
+        t.box[0] = 32; t.box[1] = rows; t.box[2] = 1; t.box[3] = 1;
+      } else {
+        t.size[0] = (uint64_t)CZ; t.size[1] = (uint64_t)d.N; t.size[2] = (uint64_t)d.N; t.size[3] = (uint64_t)d.B;
+        t.stride[0] = (uint64_t)CZ * 4; t.stride[1] = (uint64_t)d.N * CZ * 4; t.stride[2] = (uint64_t)d.N * d.N * CZ * 4;
+        t.box[0] = 32; t.box[1] = 1; t.box[2] = rows; t.box[3] = 1;
+      }
+      if (make_tensor_map(pass == 0 ? &m_in : &m_out, pass == 0 ? pair : dst, 4, 4, t, true)) return 1;
+    }
+  }
+  PRD_CUDA_OK(launch_pdl(kern, grid_for((tiles + 1) / 2, 1), 256, smem, s, mo, pair, dst, residual, map, R, w_o, b_o, m_in, m_out,
+                         row_tma));
   PRD_LAUNCHED();
   return 0;
 }
