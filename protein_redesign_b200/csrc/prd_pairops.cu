@@ -549,7 +549,11 @@ __global__ void __launch_bounds__(256, 1)
 pair_embed_lut_kernel(const __grid_constant__ CUtensorMap map_b, const float* __restrict__ pstatic, float* __restrict__ pair,
                       const float* __restrict__ z, const float* __restrict__ mask, const float* __restrict__ beta,
                       const float* __restrict__ opm_a, const __half* __restrict__ w_opm, const float* __restrict__ b_opm,
-                      int N, long long num_tiles, const float* __restrict__ lut) {
+                      int N, long long num_tiles, const float* __restrict__ lut,
+                      const __grid_constant__ CUtensorMap map_in, const __grid_constant__ CUtensorMap map_out) {
+  // The static rows of a tile arrive as ONE TMA tile (two swizzled boxes [128 rows][32 channels], thread (t, half) owns row t
+  // of box half) and the finished rows leave as two tile stores, all issued by thread 0: 256-byte bulk copies per thread
+  // serialise lane by lane on the uniform datapath.
   constexpr int CZ = 64, OD = 128, KBO = 2;
   extern __shared__ uint8_t raw[];
   uint8_t* sm = smem_align1024(raw);
@@ -567,12 +571,14 @@ pair_embed_lut_kernel(const __grid_constant__ CUtensorMap map_b, const float* __
 
   const int tid = threadIdx.x, t = tid & 127, half = tid >> 7, warp = t >> 5;
   if (tid == 0) {
-    mbar_init(full, kTileRows);
+    mbar_init(full, 1);
     mbar_init(mma_bar, 1);
     mbar_init(bt_bar, 1);
     mbar_init(&ai_bar[0], 1);
     mbar_init(&ai_bar[1], 1);
     tma_prefetch_desc(&map_b);
+    tma_prefetch_desc(&map_in);
+    tma_prefetch_desc(&map_out);
     fence_barrier_init();
   }
   if (tid < 32) tmem_alloc(tmem_slot, CZ);
@@ -605,9 +611,13 @@ pair_embed_lut_kernel(const __grid_constant__ CUtensorMap map_b, const float* __
     int b, i, jt;
     decode(tile, b, i, jt);
     const long long r = tile * kTileRows + t;
-    if (half == 0) {
-      bulk_wait_read0();  // previous tile's bulk store has finished reading the stage
-      issue_row_load<CZ>(sSt, t, pstatic + r * CZ, pstatic != nullptr, full);
+    if (tid == 0) {
+      bulk_wait_read0();  // the previous tile's stores have finished reading the stage (CTA barriers order the rest behind this)
+      if (pstatic != nullptr) {
+        mbar_expect_tx(full, 32768);
+        tma_load_2d(sSt, &map_in, full, 0, static_cast<int>(tile * kTileRows));
+        tma_load_2d(sSt + 16384, &map_in, full, 32, static_cast<int>(tile * kTileRows));
+      }
     }
     if (tid == 0 && tile + gridDim.x < num_tiles) {  // a_i of the next tile (its buffer was last read two tiles ago)
       int nb, ni, njt;
@@ -675,11 +685,11 @@ pair_embed_lut_kernel(const __grid_constant__ CUtensorMap map_b, const float* __
       }
       __syncwarp();
     }
-    mbar_wait(full, it & 1);
+    if (pstatic != nullptr) mbar_wait(full, it & 1);
     mbar_wait(mma_bar, mma_phase);
     mma_phase ^= 1;
     tc_fence_after();
-    float* my = stage_row<CZ>(sSt, t) + 32 * half;
+    uint8_t* my = sSt + half * 16384 + t * 128;  // row t of box `half`; 16-byte chunk q sits at (q ^ (t & 7)) << 4
     const float* bt = beta + (long long)b * CZ + 32 * half;
     const float* bo = sBo + 32 * half;
     const float inv_norm = m2 / (m2 + 1e-3f);  // mask_2d * (.) / (mask_2d + 1e-3)  (AF2_modules.py:539-543, modules.py:395)
@@ -690,20 +700,22 @@ pair_embed_lut_kernel(const __grid_constant__ CUtensorMap map_b, const float* __
       tmem_ld_wait();
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
-        float4 x = have_static ? *reinterpret_cast<float4*>(my + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
+        float4* px = reinterpret_cast<float4*>(my + ((q ^ (t & 7)) << 4));
+        float4 x = have_static ? *px : make_float4(0.f, 0.f, 0.f, 0.f);
         const float4 be = __ldg(reinterpret_cast<const float4*>(bt + 4 * q));
         x.x += (__uint_as_float(a2[4 * q + 0]) + bo[4 * q + 0]) * inv_norm + m2 * (fmaf(lfrac, l1[q].x - l0[q].x, l0[q].x) + be.x);
         x.y += (__uint_as_float(a2[4 * q + 1]) + bo[4 * q + 1]) * inv_norm + m2 * (fmaf(lfrac, l1[q].y - l0[q].y, l0[q].y) + be.y);
         x.z += (__uint_as_float(a2[4 * q + 2]) + bo[4 * q + 2]) * inv_norm + m2 * (fmaf(lfrac, l1[q].z - l0[q].z, l0[q].z) + be.z);
         x.w += (__uint_as_float(a2[4 * q + 3]) + bo[4 * q + 3]) * inv_norm + m2 * (fmaf(lfrac, l1[q].w - l0[q].w, l0[q].w) + be.w);
-        *reinterpret_cast<float4*>(my + 4 * q) = x;
+        *px = x;
       }
     }
-    fence_proxy_async_smem();  // output rows -> bulk store; also orders this tile's reads of sAi / sBt before later refills
+    fence_proxy_async_smem();  // output rows -> tile store; also orders this tile's reads of sAi / sBt before later refills
     tc_fence_before();
     __syncthreads();  // both halves of every row are staged; TMEM / A tiles are free for the next tile
-    if (half == 0) {
-      bulk_s2g(pair + r * CZ, stage_row<CZ>(sSt, t), CZ * 4);
+    if (tid == 0) {
+      tma_store_2d(&map_out, sSt, 0, static_cast<int>(tile * kTileRows));
+      tma_store_2d(&map_out, sSt + 16384, 32, static_cast<int>(tile * kTileRows));
       bulk_commit();
     }
   }
@@ -724,7 +736,7 @@ int pair_embed_dynamic(const PairDims& d, const float* pair_static, float* pair,
   const int KBD = ((flags & 1) == 0 && lut == nullptr) ? dist_dim / 64 : 0, KBO = opm_dim / 64;
   const int grid = (int)(tiles < kNumSMs ? tiles : kNumSMs);
   static const bool resident_off = getenv("PRD_PAIR_EMBED_RESIDENT") && getenv("PRD_PAIR_EMBED_RESIDENT")[0] == '0';  // A/B timing
-  if (d.CZ == 64 && opm_dim == 128 && flags == 0 && lut != nullptr && d.N % kTileRows == 0 && !resident_off) {
+  if (d.CZ == 64 && opm_dim == 128 && flags == 0 && lut != nullptr && d.N % kTileRows == 0 && !resident_off && R < 0x7fffffffLL) {
     // resident-operand kernel: opm_b [B][N][128] fp32 as (k, j, b); box = [32 k][128 j] with the 128-byte swizzle
     CUtensorMap mb;
     TmaDims t;
@@ -732,9 +744,19 @@ int pair_embed_dynamic(const PairDims& d, const float* pair_static, float* pair,
     t.stride[0] = 128 * 4; t.stride[1] = (uint64_t)d.N * 128 * 4; t.stride[2] = 0;
     t.box[0] = 32; t.box[1] = 128; t.box[2] = 1; t.box[3] = 1;
     if (make_tensor_map(&mb, opm_b, 4, 3, t, true)) return 1;
+    // static rows in / finished rows out: the 2-D tensors [R, 64], box = [32 channels][128 rows]
+    CUtensorMap m_in, m_out;
+    {
+      TmaDims tr;
+      tr.size[0] = 64; tr.size[1] = (uint64_t)R; tr.size[2] = 1; tr.size[3] = 1;
+      tr.stride[0] = 256; tr.stride[1] = (uint64_t)R * 256; tr.stride[2] = tr.stride[1];
+      tr.box[0] = 32; tr.box[1] = kTileRows; tr.box[2] = 1; tr.box[3] = 1;
+      if (make_tensor_map(&m_out, pair, 4, 2, tr, true)) return 1;
+      if (make_tensor_map(&m_in, pair_static != nullptr ? pair_static : pair, 4, 2, tr, true)) return 1;
+    }
     constexpr int smem = 1024 + 2 * 16384 + 4 * 16384 + 2 * 64 * 128 + RowStage<64>::kBytes + (2 * 128 + 64) * 4 + 64;
     PRD_CUDA_OK(cudaFuncSetAttribute(pair_embed_lut_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    pair_embed_lut_kernel<<<grid, 256, smem, s>>>(mb, pair_static, pair, z, mask, beta, opm_a, w_opm, b_opm, d.N, tiles, lut);
+    pair_embed_lut_kernel<<<grid, 256, smem, s>>>(mb, pair_static, pair, z, mask, beta, opm_a, w_opm, b_opm, d.N, tiles, lut, m_in, m_out);
     PRD_LAUNCHED();
     return 0;
   }
