@@ -825,7 +825,10 @@ template <int CZ>
 __global__ void __launch_bounds__(128, 2)
 coord_head_kernel(const float* __restrict__ pair, const float* __restrict__ z, const float* __restrict__ mask,
                   const __half* __restrict__ w1, const float* __restrict__ b1, const float* __restrict__ w2,
-                  float* __restrict__ eps_raw, int N) {
+                  float* __restrict__ eps_raw, int N, const __grid_constant__ CUtensorMap map_rows,
+                  const __grid_constant__ CUtensorMap map_cols, int row_tma) {
+  // row_tma (pair_dim 64): the 128 rows (i, j0..) and the 128 transposed rows (j0.., i) of a tile arrive as two TMA tiles
+  // issued by one thread instead of 256 per-thread bulk copies (which serialise lane by lane on the uniform datapath)
   extern __shared__ uint8_t raw[];
   uint8_t* sm = smem_align1024(raw);
   uint8_t* sA = sm;
@@ -842,8 +845,12 @@ coord_head_kernel(const float* __restrict__ pair, const float* __restrict__ z, c
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
   const int b = blockIdx.x / N, i = blockIdx.x % N;
   if (t == 0) {
-    mbar_init(full, 2 * kTileRows);
+    mbar_init(full, row_tma ? 1 : 2 * kTileRows);
     mbar_init(mma_bar, 1);
+    if (row_tma) {
+      tma_prefetch_desc(&map_rows);
+      tma_prefetch_desc(&map_cols);
+    }
     fence_barrier_init();
   }
   if (warp == 0) tmem_alloc(tmem_slot, TCOLS);
@@ -868,12 +875,31 @@ coord_head_kernel(const float* __restrict__ pair, const float* __restrict__ z, c
   for (int jt = 0; jt < ntiles; ++jt) {
     const int j = jt * 128 + t;
     const bool valid = j < N;
-    issue_row_load<CZ>(sSt, t, pair + (((long long)b * N + i) * N + j) * CZ, valid, full);
-    issue_row_load<CZ>(sSt + RowStage<CZ>::kBytes, t, pair + (((long long)b * N + j) * N + i) * CZ, valid, full);
+    if (row_tma) {
+      if (t == 0) {  // every thread is past its reads of the previous tile (end-of-tile barrier)
+        mbar_expect_tx(full, 65536);
+        const int r0 = static_cast<int>(((long long)b * N + i) * N + jt * 128);  // rows past the tensor's end are zero-filled
+        uint8_t* sT = sSt + RowStage<CZ>::kBytes;
+        for (int hh = 0; hh < 2; ++hh) {
+          tma_load_2d(sSt + hh * 16384, &map_rows, full, hh * 32, r0);
+          tma_load_4d(sT + hh * 16384, &map_cols, full, hh * 32, i, jt * 128, b);
+        }
+      }
+    } else {
+      issue_row_load<CZ>(sSt, t, pair + (((long long)b * N + i) * N + j) * CZ, valid, full);
+      issue_row_load<CZ>(sSt + RowStage<CZ>::kBytes, t, pair + (((long long)b * N + j) * N + i) * CZ, valid, full);
+    }
     mbar_wait(full, jt & 1);
     {
       float x[CZ], y[CZ];
-      if (valid) {
+      if (valid && row_tma) {
+        if constexpr (CZ == 64) {
+          read_row_tma64(sSt, t, x);
+          read_row_tma64(sSt + RowStage<CZ>::kBytes, t, y);
+        }
+#pragma unroll
+        for (int q = 0; q < CZ; ++q) x[q] = 0.5f * (x[q] + y[q]);
+      } else if (valid) {
         read_row<CZ>(stage_row<CZ>(sSt, t), x);
         read_row<CZ>(stage_row<CZ>(sSt + RowStage<CZ>::kBytes, t), y);
 #pragma unroll
@@ -940,15 +966,32 @@ int coord_head(const PairDims& d, const float* pair, const float* z, const float
   if (d.CZ == 64) {
     constexpr int CZ = 64;
     constexpr int smem = 1024 + 16384 + 2 * CZ * 128 + 2 * RowStage<CZ>::kBytes + (2 * CZ + 16) * 4 + 64;
+    static_assert(RowStage<CZ>::kBytes % 1024 == 0 && RowStage<CZ>::kBytes >= 32768, "coord_head: the row stages double as TMA tiles");
     auto kern = coord_head_kernel<CZ>;
     PRD_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    kern<<<grid, 128, smem, s>>>(pair, z, mask, w1, b1, w2, eps_raw, d.N);
+    // rows (b, i, j0..): the 2-D tensor [R, 64]; transposed rows (b, j0.., i): (channel, i, j, b) with the box along j
+    const long long R = (long long)d.B * d.N * d.N;
+    const int row_tma = (R < 0x7fffffffLL && (reinterpret_cast<uintptr_t>(pair) & 15) == 0) ? 1 : 0;
+    CUtensorMap m_rows, m_cols;
+    {
+      TmaDims tr;
+      tr.size[0] = 64; tr.size[1] = (uint64_t)R; tr.size[2] = 1; tr.size[3] = 1;
+      tr.stride[0] = 256; tr.stride[1] = (uint64_t)R * 256; tr.stride[2] = tr.stride[1];
+      tr.box[0] = 32; tr.box[1] = kTileRows; tr.box[2] = 1; tr.box[3] = 1;
+      if (make_tensor_map(&m_rows, pair, 4, 2, tr, true)) return 1;
+      tr.size[1] = (uint64_t)d.N; tr.size[2] = (uint64_t)d.N; tr.size[3] = (uint64_t)d.B;
+      tr.stride[1] = (uint64_t)d.N * 256; tr.stride[2] = (uint64_t)d.N * d.N * 256;
+      tr.box[1] = 1; tr.box[2] = kTileRows;
+      if (make_tensor_map(&m_cols, pair, 4, 4, tr, true)) return 1;
+    }
+    kern<<<grid, 128, smem, s>>>(pair, z, mask, w1, b1, w2, eps_raw, d.N, m_rows, m_cols, row_tma);
   } else if (d.CZ == 32) {
     constexpr int CZ = 32;
     constexpr int smem = 1024 + 16384 + 2 * CZ * 128 + 2 * RowStage<CZ>::kBytes + (2 * CZ + 16) * 4 + 64;
     auto kern = coord_head_kernel<CZ>;
     PRD_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    kern<<<grid, 128, smem, s>>>(pair, z, mask, w1, b1, w2, eps_raw, d.N);
+    CUtensorMap none{};
+    kern<<<grid, 128, smem, s>>>(pair, z, mask, w1, b1, w2, eps_raw, d.N, none, none, 0);
   } else {
     set_error("coord_head: unsupported pair_dim %d", d.CZ);
     return 1;
