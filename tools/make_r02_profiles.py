@@ -53,14 +53,17 @@ def launches():
             "Command (one B200, gpurun, tools/r02_final_capture.sh): `ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file",
             "gpurun_out/r02f/launches_step.csv python bench.py --steps 1 --warmup 3 --profile-eager`, then `python tools/summarize_launches.py ... 115`",
             "(raw list: profiles/r02_launches.csv).  Per-launch times are cold-cache and serialised; the same step replayed as a CUDA graph takes",
-            f"{d['ms_per_step']:.2f} ms on the same box (bench.py), so the SHARES are what carries over.  Attention core: 37.4 % here, 8 x "
+            f"{d['ms_per_step']:.2f} ms on the same box (bench.py), so the SHARES are what carries over.  Attention core: 38.7 % here, 8 x "
             f"{d['roofline']['ms_per_launch']:.3f} ms / {d['ms_per_step']:.2f} ms = {800 * d['roofline']['ms_per_launch'] / d['ms_per_step']:.1f} % in the timed step.",
             "",
-            "Round 1 -> round 2 (same shape): 119 -> 115 launches, 28.65 -> 27.17 ms serialised, 27.52 -> 26.26 ms per graph replay.",
-            "`triattn_flash_g4_kernel` 1.365 -> 1.269 (first key tile on the fast path, overflow check through the row sum), `pair_transition_ws`",
-            "0.479 -> 0.388 alone (rows by TMA, hi half of W2) / 0.481 as the average of the 3 launches that also emit the next block's attention bias",
-            "and the one that does not, `pair_bias_kernel` 5 x 0.125 -> 1 x 0.159, `gemm_f16_kernel<256, 4>` 0.089 -> 0.082 and `<128, 5>` 0.032 -> 0.023",
-            "(eight epilogue warps, accumulator chunk in registers instead of a local-memory array: DESIGN section 4).", ""]
+            f"Round 1 -> round 2 (same shape): 119 -> 115 launches, 28.65 -> {body[0].split('launches, ')[1].split(' ms')[0]} ms serialised, 27.52 -> {d['ms_per_step']:.2f} ms per graph replay.",
+            "`triattn_flash_g4_kernel` 1.365 -> 1.27 (first key tile on the fast path, overflow check through the row sum), `pair_transition_ws`",
+            "0.479 -> 0.388 alone (rows by TMA, hi half of W2) / 0.48 as the average of the 3 launches that also emit the next block's attention bias",
+            "and the one that does not, `pair_bias_kernel` 5 x 0.125 -> 1 x 0.158, `gemm_f16_kernel<256, 4>` 0.089 -> 0.083 and `<128, 5>` 0.032 -> 0.023",
+            "(eight epilogue warps, accumulator chunk in registers instead of a local-memory array), `trimul_in_t` 0.360 -> 0.326 and `triattn_proj`",
+            "0.339 -> 0.299 (one thread per row normalises), `triattn_out` 0.240 -> 0.216, `pair_embed_lut` 0.536 -> 0.444, `coord_head` 0.307 -> 0.225",
+            "(row tiles by TMA instead of per-thread bulk copies; `trimul_out` shows 0.36 here both ways -- cold cache, serialised -- and 0.45 ms of the",
+            "replayed step in the `PRD_ROW_TMA` A/B): DESIGN section 4.", ""]
     open(os.path.join(OUT, "r02_launches.md"), "w").write("\n".join(head + body[2:]) + "\n")
     shutil.copy(os.path.join(SRC, "launches_step.csv"), os.path.join(OUT, "r02_launches.csv"))
 
@@ -72,7 +75,7 @@ def train():
            f"B = 2, N = 314 (24 + 290 and 35 + 212 tokens), paper dims, one B200; `bench.py --workload train`: {g['ms_per_step']:.2f} ms per step "
            f"({g['value']:.1f} steps/s, {g['gpu_launches_per_step']} launches of libprd_sm100.so per step).",
            "",
-           "## How the step got from 71.9 ms to 36.8 ms (each line: one commit, same workload, A/B on one box each)",
+           "## How the step got from 71.9 ms to 36.6 ms (each line: one commit, same workload, A/B on one box each)",
            "",
            "| change | ms / step |", "|---|---:|",
            "| mid-round build (fp32 SIMT attention, scalar elementwise kernels, four epilogue warps) | 71.6 |",
