@@ -15,6 +15,8 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libprd_sm100.so")
+# A/B of two builds on one box (tools/ab_bench.sh PRD_LIB_PATH ...): needs PRD_ALLOW_STALE_LIB=1 next to it
+LIB_PATH = os.environ.get("PRD_LIB_PATH") or LIB_PATH
 
 OPS = (
     "esm_embed", "single_embed", "pair_embed_static", "opm_project", "pair_embed", "pair_bias", "spattention",

@@ -200,12 +200,16 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Wait with a watchdog: a pipeline bug traps (visible as a launch failure) instead of hanging.
+// Wait with a watchdog: a pipeline bug traps (visible as a launch failure) instead of hanging.  A warp whose barrier is
+// not ready yet sleeps a few tens of nanoseconds between polls: a polling warp is always "ready" to the scheduler, and in
+// the warp-specialised row kernels the polls (try_wait + 64-bit clock compare + branch, 8 instructions) were 48 - 55 % of
+// all executed instructions (ncu: pair_transition_ws, outer_linear), issued in competition with the warps that had work.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
+  uint32_t polls = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) {  // ~2 s at 2 GHz
+    __nanosleep(32);
+    if (++polls > (1u << 26)) {  // > 2 s of sleeping alone
       printf("prd: mbarrier watchdog (block %d,%d,%d thread %d)\n", blockIdx.x, blockIdx.y, blockIdx.z, threadIdx.x);
       __trap();
     }
