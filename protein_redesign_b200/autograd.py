@@ -138,7 +138,42 @@ def single_embed_bwd(cfg, P, G, batch, seq_t, d_single) -> None:
 class DenoiserTape:
     """Checkpoints of one forward evaluation (what the reference's per-block ``checkpoint`` keeps)."""
 
-    __slots__ = ("batch", "z", "seq_t", "mask", "t", "single0", "opm_a", "opm_b", "pair1", "blocks", "single_out", "pair_out")
+    __slots__ = ("batch", "z", "seq_t", "mask", "t", "single0", "opm_a", "opm_b", "pair1", "blocks", "single_out", "pair_out", "per_op")
+
+
+_TAPE_OPS_MAX_BYTES = 32 << 30
+
+
+def _tape_per_op(cfg, pair: torch.Tensor) -> bool:
+    """Keep the input of every residual update (True) or one checkpoint per block and re-run it in the backward pass."""
+    import os
+    mode = os.environ.get("PRD_TAPE", "")
+    if mode in ("ops", "blocks"):
+        return mode == "ops"
+    return 6 * cfg.num_blocks * pair.numel() * pair.element_size() <= _TAPE_OPS_MAX_BYTES
+
+
+def _block_forward_taped(cfg, block, single: torch.Tensor, pair: torch.Tensor, mask: torch.Tensor, all_valid: bool):
+    """One FoldingBlock in place on (single, pair), op by op in the reference order (modules.py:335-342), returning the input
+    of each residual update: (s0, p0) single_attn [+ pair bias], s1 single_fc, s2 outer_linear, p1 pair_mul_outgoing,
+    p2 pair_mul_incoming, p3 pair_attn_starting, p4 pair_attn_ending, p5 pair_fc."""
+    s0, p0 = single.clone(), pair.clone()
+    ops.single_attention(cfg, single, p0, mask, block.single_attn.packed_single(block.attn_bias[1]), single)
+    s1 = single.clone()
+    ops.single_transition(cfg, single, block.single_fc.packed_single(), single)
+    s2 = single.clone()
+    block.outer_linear.apply_(cfg, s2, pair)
+    p1 = pair.clone()
+    block.pair_mul_outgoing.apply_(cfg, pair, mask)
+    p2 = pair.clone()
+    block.pair_mul_incoming.apply_(cfg, pair, mask)
+    p3 = pair.clone()
+    block.pair_attn_starting.apply_(cfg, pair, mask, all_valid=all_valid)
+    p4 = pair.clone()
+    block.pair_attn_ending.apply_(cfg, pair, mask, all_valid=all_valid)
+    p5 = pair.clone()
+    ops.pair_transition(cfg, pair, block.pair_fc.packed_pair(), pair)
+    return s0, p0, s1, s2, p1, p2, p3, p4, p5
 
 
 def forward_with_checkpoints(model, batch, z, seq_t, mask, t) -> Tuple[torch.Tensor, torch.Tensor, DenoiserTape]:
@@ -160,9 +195,18 @@ def forward_with_checkpoints(model, batch, z, seq_t, mask, t) -> Tuple[torch.Ten
     tape.pair1 = pair.clone()
     den.SPAAttnBlock(single, pair, tape.mask, cfg=cfg, out=single)
     tape.blocks = []
+    all_valid = bool(batch.get("_all_valid", False))
+    # Reference behaviour = one checkpoint per block and a re-run of the block in the backward pass (modules.py:399-401): that
+    # trades a second forward for memory on 16 - 80 GB devices.  With 180 GB the inputs of all eight residual updates of every
+    # block are simply kept (6 pair tensors per block: 1.2 GB at B = 2, N = 314) and the re-run disappears -- unless they would
+    # not fit (_TAPE_OPS_MAX_BYTES) or PRD_TAPE=blocks asks for the reference scheme.
+    tape.per_op = _tape_per_op(cfg, pair)
     for block in den.folding_blocks:
-        tape.blocks.append((single.clone(), pair.clone()))
-        block.forward_(cfg, single, pair, tape.mask, all_valid=bool(batch.get("_all_valid", False)))
+        if tape.per_op:
+            tape.blocks.append(_block_forward_taped(cfg, block, single, pair, tape.mask, all_valid))
+        else:
+            tape.blocks.append((single.clone(), pair.clone()))
+            block.forward_(cfg, single, pair, tape.mask, all_valid=all_valid)
     tape.single_out, tape.pair_out = single, pair
     noise_pred = ops.coord_head(cfg, pair, tape.z, tape.mask, w["coord"])
     seq_pred = ops.seq_head(cfg, single, w["seq"])
@@ -180,23 +224,13 @@ def backward_from_checkpoints(model, tape: DenoiserTape, d_noise_pred: torch.Ten
     tape.single_out = tape.pair_out = None
     for k in reversed(range(len(den.folding_blocks))):
         block, bp = den.folding_blocks[k], f"Denoiser.folding_blocks.{k}."
-        s0, p0 = tape.blocks.pop()
-        # re-run the block once, keeping the input of each residual update (reference order modules.py:335-342)
-        s1 = s0.clone()
-        ops.single_attention(cfg, s1, p0, mask, block.single_attn.packed_single(block.attn_bias[1]), s1)
-        s2 = s1.clone()
-        ops.single_transition(cfg, s2, block.single_fc.packed_single(), s2)
-        p1 = p0.clone()
-        block.outer_linear.apply_(cfg, s2, p1)
-        p2 = p1.clone()
-        block.pair_mul_outgoing.apply_(cfg, p2, mask)
-        p3 = p2.clone()
-        block.pair_mul_incoming.apply_(cfg, p3, mask)
         all_valid = bool(tape.batch.get("_all_valid", False))
-        p4 = p3.clone()
-        block.pair_attn_starting.apply_(cfg, p4, mask, all_valid=all_valid)
-        p5 = p4.clone()
-        block.pair_attn_ending.apply_(cfg, p5, mask, all_valid=all_valid)
+        if tape.per_op:
+            s0, p0, s1, s2, p1, p2, p3, p4, p5 = tape.blocks.pop()
+        else:
+            # re-run the block once, keeping the input of each residual update (reference order modules.py:335-342)
+            s0, p0 = tape.blocks.pop()
+            s0, p0, s1, s2, p1, p2, p3, p4, p5 = _block_forward_taped(cfg, block, s0.clone(), p0.clone(), mask, all_valid)
         transition_bwd(cfg, P, G, bp + "pair_fc.", p5, d_pair)
         del p5
         triangle_attention_bwd(cfg, P, G, bp + "pair_attn_ending.attn.", 1, p4, mask, d_pair)
