@@ -44,7 +44,7 @@ inline unsigned grid_for(long long n, int per_block, long long cap = 148LL * 32)
 // ------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) bw_ln_fwd_kernel(const float* __restrict__ x, long long R, int C,
                                                         const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                        float* __restrict__ out, float* __restrict__ out_lo) {
+                                                        float* __restrict__ out, float* __restrict__ out_lo, long long ldo) {
   const int lane = threadIdx.x & 31;
   const long long warp0 = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const long long nw = (long long)gridDim.x * (blockDim.x >> 5);
@@ -63,8 +63,8 @@ __global__ void __launch_bounds__(256) bw_ln_fwd_kernel(const float* __restrict_
       float y = (xr[c] - mean) * rstd;
       if (gamma) y = y * gamma[c] + (beta ? beta[c] : 0.f);
       const float hi = round_tf32(y);
-      out[r * C + c] = hi;
-      if (out_lo) out_lo[r * C + c] = round_tf32(y - hi);
+      out[r * ldo + c] = hi;
+      if (out_lo) out_lo[r * ldo + c] = round_tf32(y - hi);
     }
   }
 }
@@ -74,7 +74,7 @@ __global__ void __launch_bounds__(256) bw_ln_fwd_kernel(const float* __restrict_
 template <int LPR>
 __global__ void __launch_bounds__(256) bw_ln_fwd_vec_kernel(const float* __restrict__ x, long long R,
                                                             const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                            float* __restrict__ out, float* __restrict__ out_lo) {
+                                                            float* __restrict__ out, float* __restrict__ out_lo, long long ldo) {
   constexpr int C = 4 * LPR, RPW = 32 / LPR, U = 2;
   const int lane = threadIdx.x & 31, sub = lane / LPR, l = lane % LPR;
   const long long warp0 = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -99,29 +99,30 @@ __global__ void __launch_bounds__(256) bw_ln_fwd_vec_kernel(const float* __restr
                                    fmaf(d.w * rstd, gm.w, bt.w));
       const float4 hi = round4(y);
       if (r[u] < R) {
-        st4(out + r[u] * C + 4 * l, hi);
-        if (out_lo) st4(out_lo + r[u] * C + 4 * l, round4(make_float4(y.x - hi.x, y.y - hi.y, y.z - hi.z, y.w - hi.w)));
+        st4(out + r[u] * ldo + 4 * l, hi);
+        if (out_lo) st4(out_lo + r[u] * ldo + 4 * l, round4(make_float4(y.x - hi.x, y.y - hi.y, y.z - hi.z, y.w - hi.w)));
       }
     }
   }
 }
 template <int LPR>
 static void launch_ln_fwd_vec(const float* x, long long R, const float* gamma, const float* beta, float* out, float* out_lo,
-                              cudaStream_t s) {
-  bw_ln_fwd_vec_kernel<LPR><<<grid_for(R, 8 * (32 / LPR) * 2), 256, 0, s>>>(x, R, gamma, beta, out, out_lo);
+                              long long ldo, cudaStream_t s) {
+  bw_ln_fwd_vec_kernel<LPR><<<grid_for(R, 8 * (32 / LPR) * 2), 256, 0, s>>>(x, R, gamma, beta, out, out_lo, ldo);
 }
 int bw_ln_fwd(const float* x, long long R, int C, const float* gamma, const float* beta, float* out, cudaStream_t s,
-              float* out_lo) {
-  const bool vec = aligned16(x) && aligned16(out) && (out_lo == nullptr || aligned16(out_lo)) &&
+              float* out_lo, long long ldo) {
+  if (ldo == 0) ldo = C;
+  const bool vec = aligned16(x) && aligned16(out) && (out_lo == nullptr || aligned16(out_lo)) && ldo % 4 == 0 &&
                    (gamma == nullptr || aligned16(gamma)) && (beta == nullptr || aligned16(beta));
   if (vec && (C == 32 || C == 64 || C == 128)) {
-    if (C == 32) launch_ln_fwd_vec<8>(x, R, gamma, beta, out, out_lo, s);
-    else if (C == 64) launch_ln_fwd_vec<16>(x, R, gamma, beta, out, out_lo, s);
-    else launch_ln_fwd_vec<32>(x, R, gamma, beta, out, out_lo, s);
+    if (C == 32) launch_ln_fwd_vec<8>(x, R, gamma, beta, out, out_lo, ldo, s);
+    else if (C == 64) launch_ln_fwd_vec<16>(x, R, gamma, beta, out, out_lo, ldo, s);
+    else launch_ln_fwd_vec<32>(x, R, gamma, beta, out, out_lo, ldo, s);
     PRD_LAUNCHED();
     return 0;
   }
-  bw_ln_fwd_kernel<<<grid_for(R, 8), 256, 0, s>>>(x, R, C, gamma, beta, out, out_lo);
+  bw_ln_fwd_kernel<<<grid_for(R, 8), 256, 0, s>>>(x, R, C, gamma, beta, out, out_lo, ldo);
   PRD_LAUNCHED();
   return 0;
 }

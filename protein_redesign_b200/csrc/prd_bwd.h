@@ -14,8 +14,10 @@ namespace prd {
 
 // out[r, :] = round_tf32(LN(x[r, :]) * gamma + beta)   (gamma / beta may be NULL); eps 1e-5
 // out_lo (optional): round_tf32(y - out), so that out + out_lo carries 21 mantissa bits (split-operand GEMMs)
+// ldo: row stride of out / out_lo (0 = C); with out_lo = out + C and ldo = 2 C the rows are [hi | lo], the A operand of the
+// three-term split GEMM (GemmArgs::split = 3)
 int bw_ln_fwd(const float* x, long long R, int C, const float* gamma, const float* beta, float* out, cudaStream_t s,
-              float* out_lo = nullptr);
+              float* out_lo = nullptr, long long ldo = 0);
 // dx_io[r, :] = round_tf32((accumulate ? dx_io[r, :] : 0) + dLN/dx . g[r, :]);  with gamma: g is first multiplied by gamma,
 // and dgamma += sum_r g * xhat, dbeta += sum_r g (either may be NULL)
 int bw_ln_bwd(const float* x, const float* g, long long R, int C, const float* gamma, float* dx_io, int accumulate,

@@ -63,32 +63,31 @@ float* transposed(bool dry, Carver& c, cudaStream_t st, const float* W, int rows
   return r;
 }
 
-// h = relu(LN(x) W^T + b) with split operands (x_hi + x_lo)(W_hi + W_lo), three tf32 GEMMs: the ReLU mask [h > 0] of the
-// backward pass must agree with an fp32 evaluation -- with single tf32 operands ~3e-4 of the pre-activations change sign,
-// and every flipped element costs a full-size error in dh (relative L2 of dW ~ sqrt(3e-4) = 1.7e-2, measured 1.3e-2).
-// xh receives LN(x) rounded (the operand of the weight-gradient reductions).
+// h = relu(LN(x) W^T + b) with split operands (x_hi + x_lo)(W_hi + W_lo): the ReLU mask [h > 0] of the backward pass must
+// agree with an fp32 evaluation -- with single tf32 operands ~3e-4 of the pre-activations change sign, and every flipped
+// element costs a full-size error in dh (relative L2 of dW ~ sqrt(3e-4) = 1.7e-2, measured 1.3e-2).  The three products
+// x_hi W_hi + x_lo W_hi + x_hi W_lo run as ONE tf32 GEMM over K = 3 Cin into one accumulator (GemmArgs::split = 3: LayerNorm
+// writes rows [hi | lo], the weight is laid out [W_hi | W_hi | W_lo]) with bias, ReLU and the tf32 rounding in its epilogue;
+// as three GEMMs chained through memory plus a ReLU pass the same math moved 3.3 x the bytes.
+// *xop / *ldx: LN(x) rounded (the hi half of the rows), the operand of the weight-gradient reductions.
 // prep: jobs of the caller that go into the same weight-preparation launch as the hi / lo split of W
 int relu_layer_fwd(bool dry, Carver& c, cudaStream_t st, long long R, int Cin, int Chid, const float* x, const float* W,
-                   const float* b, float* xh, float* h, PrepBatch* prep = nullptr) {
-  float* xlo = c.take((size_t)R * Cin);
-  float* Whi = c.take((size_t)Chid * Cin);
-  float* Wlo = c.take((size_t)Chid * Cin);
+                   const float* b, const float** xop, long long* ldx, float* h, PrepBatch* prep = nullptr) {
+  float* xcat = c.take((size_t)R * 2 * Cin);      // rows [LN(x)_hi | LN(x)_lo]
+  float* Wcat = c.take((size_t)Chid * 3 * Cin);   // rows [W_hi | W_hi | W_lo]
+  *xop = xcat;
+  *ldx = 2 * Cin;
   if (dry) return 0;
+  PRD_REQUIRE(Cin % 32 == 0, "relu_layer_fwd: input width %d must be a multiple of 32", Cin);
   PrepBatch own;
   PrepBatch& pb = prep ? *prep : own;
-  pb.split(W, Cin, Whi, Wlo, Cin, Chid, Cin);
+  pb.split(W, Cin, Wcat, Wcat + 2 * Cin, 3 * Cin, Chid, Cin);
+  pb.copy(W, Cin, Wcat + Cin, 3 * Cin, Chid, Cin);
   if (bw_prep(pb, st)) return 1;
-  if (bw_ln_fwd(x, R, Cin, nullptr, nullptr, xh, st, xlo)) return 1;
-  GemmArgs g = tfg((int)R, Chid, Cin, xlo, Cin, Whi, Cin, h, Chid);
-  g.round_tf32 = 0;
-  if (gemm_f16(g, st)) return 1;
-  g = tfg((int)R, Chid, Cin, xh, Cin, Wlo, Cin, h, Chid);
-  g.round_tf32 = 0; g.add = h; g.ldadd = Chid;
-  if (gemm_f16(g, st)) return 1;
-  g = tfg((int)R, Chid, Cin, xh, Cin, Whi, Cin, h, Chid);
-  g.round_tf32 = 0; g.add = h; g.ldadd = Chid; g.bias = b;
-  if (gemm_f16(g, st)) return 1;
-  return bw_relu_inplace(h, R * Chid, st);
+  if (bw_ln_fwd(x, R, Cin, nullptr, nullptr, xcat, st, xcat + Cin, 2 * Cin)) return 1;
+  GemmArgs g = tfg((int)R, Chid, Cin, xcat, 2 * Cin, Wcat, 3 * Cin, h, Chid);
+  g.split = 3; g.bias = b; g.act = 1;
+  return gemm_f16(g, st);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -100,7 +99,8 @@ int mlp_bwd(bool dry, Carver& c, cudaStream_t st, long long R, int Cin, int Chid
             float* db2) {
   int rc = 0;
   const int Cop = up4(Cout) < 32 && Cout % 4 != 0 ? 32 : up4(Cout);  // padded width of dy as a GEMM operand
-  float* xh = c.take((size_t)R * Cin);
+  const float* xh = nullptr;
+  long long ldxh = 0;
   float* h = c.take((size_t)R * Chid);
   float* dh = c.take((size_t)R * Chid);
   float* dxh = c.take((size_t)R * Cin);
@@ -111,7 +111,7 @@ int mlp_bwd(bool dry, Carver& c, cudaStream_t st, long long R, int Cin, int Chid
     pb.transpose(W1, Cin, W1T, up4(Chid), Chid, Cin, Cin, Chid);
     pb.transpose(W2, Chid, W2T, Cop, Cout, Chid, Chid, Cop);
   }
-  if (relu_layer_fwd(dry, c, st, R, Cin, Chid, x, W1, b1, xh, h, &pb)) return 1;
+  if (relu_layer_fwd(dry, c, st, R, Cin, Chid, x, W1, b1, &xh, &ldxh, h, &pb)) return 1;
   const float* dyop = dy;
   float* dypad = nullptr;
   if (Cop != Cout) dypad = c.take((size_t)R * Cop);
@@ -128,7 +128,7 @@ int mlp_bwd(bool dry, Carver& c, cudaStream_t st, long long R, int Cin, int Chid
     g.mul = h; g.ldmul = Chid; g.mul_step = 1;
     if (gemm_f16(g, st)) return 1;
   }
-  if (bw_dw_acc(dh, Chid, xh, Cin, R, Chid, Cin, dW1, Cin, db1, 1.f, st)) return 1;
+  if (bw_dw_acc(dh, Chid, xh, ldxh, R, Chid, Cin, dW1, Cin, db1, 1.f, st)) return 1;
   {
     GemmArgs g = tfg((int)R, Cin, Chid, dh, Chid, W1T, up4(Chid), dxh, Cin);
     if (gemm_f16(g, st)) return 1;
@@ -459,7 +459,8 @@ PRD_BWD_OP(coord_head) {
   const long long R = (long long)B * N * N;
   int rc = 0;
   float* ps = c.take((size_t)R * CZ);
-  float* xh = c.take((size_t)R * CZ);
+  const float* xh = nullptr;
+  long long ldxh = 0;
   float* h = c.take((size_t)R * CZ);
   float* dh = c.take((size_t)R * CZ);
   float* dxh = c.take((size_t)R * CZ);
@@ -470,11 +471,11 @@ PRD_BWD_OP(coord_head) {
     PRD_CUDA_OK(cudaMemcpyAsync(ps, IN(0), (size_t)R * CZ * sizeof(float), cudaMemcpyDeviceToDevice, st));
     if (symmetrize_pair(PairDims{B, N, CZ}, ps, st)) return 1;
   }
-  if (relu_layer_fwd(dry, c, st, R, CZ, CZ, ps, WT(0), WT(1), xh, h)) return 1;
+  if (relu_layer_fwd(dry, c, st, R, CZ, CZ, ps, WT(0), WT(1), &xh, &ldxh, h)) return 1;
   if (dry) return 0;
   if (bw_remove_mean_adj(IN(3), IN(2), B, N, d_eps, st)) return 1;
   if (bw_coord_dh(h, IN(1), IN(2), d_eps, WT(2), B, N, CZ, dh, OUT(3), st)) return 1;
-  if (bw_dw_acc(dh, CZ, xh, CZ, R, CZ, CZ, OUT(1), CZ, OUT(2), 1.f, st)) return 1;
+  if (bw_dw_acc(dh, CZ, xh, ldxh, R, CZ, CZ, OUT(1), CZ, OUT(2), 1.f, st)) return 1;
   {
     GemmArgs g = tfg((int)R, CZ, CZ, dh, CZ, W1T, CZ, dxh, CZ);
     if (gemm_f16(g, st)) return 1;

@@ -435,8 +435,8 @@ static int launch_gemm(const GemmArgs& g, cudaStream_t stream) {
   const int kb_half = (g.K + kKb - 1) / kKb;
   if (g.split != 0) PRD_REQUIRE(g.K % kKb == 0, "gemm: split weights need K %% %d == 0 (K=%d)", kKb, g.K);
   PRD_REQUIRE(!(TF32 && g.c_fp16), "gemm: tf32 operands write fp32 results");
-  auto fill = [&](TmaDims& d, long long rows, long long ld, long long bs1, long long bs2, int box_rows, bool is_split) {
-    d.size[0] = (uint64_t)(is_split ? 2 * g.K : g.K);
+  auto fill = [&](TmaDims& d, long long rows, long long ld, long long bs1, long long bs2, int box_rows, int k_copies) {
+    d.size[0] = (uint64_t)k_copies * g.K;
     d.size[1] = (uint64_t)rows;
     d.size[2] = bs1 != 0 ? (uint64_t)nb1 : 1;
     d.size[3] = bs2 != 0 ? (uint64_t)nb2 : 1;
@@ -454,8 +454,8 @@ static int launch_gemm(const GemmArgs& g, cudaStream_t stream) {
   PRD_REQUIRE(g.M > 0 && g.N > 0 && g.K > 0, "gemm: empty problem M=%d N=%d K=%d", g.M, g.N, g.K);
   PRD_REQUIRE(g.lda % kAl == 0 && g.ldb % kAl == 0, "gemm: lda/ldb must be multiples of 16 bytes (lda=%lld ldb=%lld)", g.lda, g.ldb);
   PRD_REQUIRE((g.a_bs1 % kAl == 0) && (g.a_bs2 % kAl == 0) && (g.b_bs1 % kAl == 0) && (g.b_bs2 % kAl == 0), "gemm: batch strides must be multiples of 16 bytes");
-  fill(da, g.M, g.lda, g.a_bs1, g.a_bs2, 128, g.split == 2);
-  fill(db, g.N, g.ldb, g.b_bs1, g.b_bs2, BN, g.split == 1);
+  fill(da, g.M, g.lda, g.a_bs1, g.a_bs2, 128, (g.split == 2 || g.split == 3) ? 2 : 1);
+  fill(db, g.N, g.ldb, g.b_bs1, g.b_bs2, BN, g.split == 1 ? 2 : (g.split == 3 ? 3 : 1));
   if (make_tensor_map(&map_a, g.A, kEl, 4, da, true)) return 1;
   if (make_tensor_map(&map_b, g.B, kEl, 4, db, true)) return 1;
   GemmEpilogue ep;
@@ -493,8 +493,8 @@ static int launch_gemm(const GemmArgs& g, cudaStream_t stream) {
   tl.nb1 = nb1;
   tl.total = (long long)tl.tiles_n * tl.tiles_m * nb1 * nb2;
   const int grid = (int)(tl.total < kNumSMs ? tl.total : kNumSMs);
-  const int num_kb = g.split != 0 ? 2 * kb_half : kb_half;
-  const int a_wrap = g.split == 1 ? kb_half : num_kb;
+  const int num_kb = g.split == 3 ? 3 * kb_half : (g.split != 0 ? 2 * kb_half : kb_half);
+  const int a_wrap = g.split == 1 ? kb_half : (g.split == 3 ? 2 * kb_half : num_kb);  // split 3: hi, lo, hi again
   const int b_wrap = g.split == 2 ? kb_half : num_kb;
   PRD_CUDA_OK(launch_pdl(kern, grid, 384, L::kTotal, stream, map_a, map_b, map_c, num_kb, a_wrap, b_wrap, tl, g.a_bs1 != 0 ? 1 : 0,
                          g.a_bs2 != 0 ? 1 : 0, g.b_bs1 != 0 ? 1 : 0, g.b_bs2 != 0 ? 1 : 0, ep));

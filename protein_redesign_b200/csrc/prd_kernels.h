@@ -28,6 +28,8 @@ struct GemmArgs {
   long long ldc = 0, c_bs1 = 0, c_bs2 = 0;
   int c_fp16 = 0;
   // 0: plain.  1: B is a weight stored as [hi | lo] along K (ldb >= 2K).  2: same for A.
+  // 3: three-term split product in ONE accumulator: A = [a_hi | a_lo] (lda >= 2K), B = [b_hi | b_hi | b_lo] (ldb >= 3K):
+  //    a_hi b_hi + a_lo b_hi + a_hi b_lo (the lo x lo term is below fp32 resolution)
   int split = 0;
   int tf32 = 0;        // A, B are fp32 in memory, multiplied on kind::tf32 (producers round to nearest tf32); C fp32
   int mul_step = 0;    // `mul` gates instead of scaling: v = mul > 0 ? v : 0

@@ -75,7 +75,7 @@ def train():
            f"B = 2, N = 314 (24 + 290 and 35 + 212 tokens), paper dims, one B200; `bench.py --workload train`: {g['ms_per_step']:.2f} ms per step "
            f"({g['value']:.1f} steps/s, {g['gpu_launches_per_step']} launches of libprd_sm100.so per step).",
            "",
-           "## How the step got from 71.9 ms to 35.1 ms (each line: one commit, same workload, A/B on one box each)",
+           "## How the step got from 71.9 ms to 31.4 ms (each line: one commit, same workload, A/B on one box each)",
            "",
            "| change | ms / step |", "|---|---:|",
            "| mid-round build (fp32 SIMT attention, scalar elementwise kernels, four epilogue warps) | 71.6 |",
@@ -89,6 +89,7 @@ def train():
            "| bias gradients added up inside the dW kernel from the tiles it stages | 38.8 |",
            "| dW partial sums leave as whole 128-byte rows (transposed through shared memory) instead of 32 scattered atomics per instruction | 36.6 |",
            "| the forward keeps the input of every residual update (1.2 GB) instead of one checkpoint per block + a re-run of the block (`PRD_TAPE=blocks` A/B: 37.2 vs 35.1 on one box; measured after the captures below) | 35.1 |",
+           "| the split-operand recompute of every ReLU layer as ONE tf32 GEMM over K = 3 C_in with bias + ReLU + rounding in its epilogue (was three GEMMs chained through memory + a ReLU pass; two builds A/B on one box: 32.6 vs 31.4, 759 vs 729 launches) | 31.4 |",
            "",
            "## Per op (tools/train_breakdown.py: CUDA events around every C-ABI call, serialised)", "", "```", text("train_breakdown.txt").strip(), "```", "",
            "## Per kernel (tools/train_breakdown.py --kernels: torch.profiler / CUPTI over one step)", "", "```",
