@@ -158,3 +158,20 @@ def test_collate_fn_matches_reference_golden():
     assert int(batch["residue_type"].min()) == 0 and int(batch["residue_type"].max()) <= 20
     assert len(RepeatDataset(items[0], 5)) == 5 and RepeatDataset(items[0], 5)[3] is items[0]
     assert len(InferenceDataset(items, 0)) == 3 and InferenceDataset(items, 0)[1] is items[1]
+
+
+def test_training_tape_policy(monkeypatch):
+    """The forward keeps the input of every residual update when that fits (a few GB at training sizes) and falls back to
+    the reference's one-checkpoint-per-block scheme otherwise; PRD_TAPE overrides either way."""
+    import torch
+    from protein_redesign_b200 import autograd as ag
+    from protein_redesign_b200 import synthetic as syn
+    monkeypatch.delenv("PRD_TAPE", raising=False)
+    small = torch.empty(2, 314, 314, 64, device="meta")   # 50 MB: 24 copies = 1.2 GB
+    huge = torch.empty(8, 2048, 2048, 64, device="meta")  # 8.6 GB: 24 copies do not fit the 32 GB tape budget
+    assert ag._tape_per_op(syn.PAPER, small) is True
+    assert ag._tape_per_op(syn.PAPER, huge) is False
+    monkeypatch.setenv("PRD_TAPE", "blocks")
+    assert ag._tape_per_op(syn.PAPER, small) is False
+    monkeypatch.setenv("PRD_TAPE", "ops")
+    assert ag._tape_per_op(syn.PAPER, huge) is True
